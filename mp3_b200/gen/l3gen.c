@@ -1,0 +1,515 @@
+/* l3gen.c -- synthetic, spec-valid MPEG-1/2 Layer III bitstream generator.
+ *
+ * There is no MP3 encoder on the box and no corpus, so every test and
+ * benchmark input is produced here: random but LEGAL frames -- exact part2_3_length, big_values
+ * <= 288, region boundaries on scalefactor-band edges, code books 4/14 never selected,
+ * main_data_begin never larger than the bytes actually left in the bit reservoir, legal window
+ * switching sequences, MS / intensity joint stereo, MPEG-2 LSF scalefactor partitions, VBR.
+ *
+ * It shares only the ISO tables (../csrc/iso_tables.h) with the decoders: nothing of the decode
+ * logic is reused, so a generator bug and a decoder bug cannot cancel silently -- and the FFmpeg
+ * differential tests decode these streams with a third, independent implementation.
+ *
+ * The reference repository has no generator or sample audio to mirror
+ * (/root/reference/README.md:1-84).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../csrc/iso_tables.h"
+
+typedef struct {
+    uint64_t seed;
+    int32_t sample_rate;   /* 44100 48000 32000 | 22050 24000 16000 */
+    int32_t mode;          /* 0 stereo, 1 joint stereo, 2 dual channel, 3 mono */
+    int32_t bitrate_kbps;  /* CBR rate; ignored when vbr_max_kbps > 0 */
+    int32_t vbr_min_kbps, vbr_max_kbps;
+    int32_t nframes;
+    int32_t blocks;        /* 0 = long blocks only, 1 = random legal window switching */
+    int32_t mixed_pct;     /* % of short granules with mixed_block_flag (MPEG-1 only) */
+    int32_t reservoir;     /* 0 = main_data_begin always 0, 1 = use the bit reservoir */
+    int32_t fill_lo_pct, fill_hi_pct; /* share of the available bits a frame uses */
+    int32_t mode_ext_mask; /* joint stereo: bit v set => mode_ext value v may be drawn */
+    int32_t crc;           /* 1 = protection on (CRC-16 word written) */
+    int32_t lsf_avoid_illegal_ispos; /* LSF intensity: keep is_pos legal and <= 15 (what FFmpeg models) */
+    int32_t level_lo_db, level_hi_db; /* target rms level range, dB below full scale */
+    int32_t only_table;    /* >0: force this table_select everywhere */
+    int32_t scfsi_pct;
+    int32_t max_linbits_value; /* cap on escape magnitudes (<=8191+15); 0 = no cap */
+    int32_t mixed_free;    /* 0 = mixed_block_flag is drawn once per run of short granules (what real
+                              encoders do); 1 = drawn per granule, which also produces mixed -> pure
+                              short transitions (legal to decode, but FFmpeg drops the long-window
+                              tail of subbands 0-1 there, so differential tests keep this 0) */
+} l3gen_cfg;
+
+/* ------------------------------------------------------------------ rng */
+typedef struct { uint64_t s; } rng_t;
+static uint64_t rnd64(rng_t *r)
+{
+    uint64_t z = (r->s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static int rndi(rng_t *r, int lo, int hi) /* inclusive */
+{
+    return lo + (int)(rnd64(r) % (uint64_t)(hi - lo + 1));
+}
+static double rndu(rng_t *r) { return (rnd64(r) >> 11) * (1.0 / 9007199254740992.0); }
+
+/* ------------------------------------------------------------------ bit writer (into logical main-data stream) */
+typedef struct {
+    uint8_t *p;
+    size_t cap_bits;
+    size_t pos;
+} bitw;
+static void putbits(bitw *w, unsigned v, int n)
+{
+    for (int i = n - 1; i >= 0; i--) {
+        if (w->pos < w->cap_bits && ((v >> i) & 1)) w->p[w->pos >> 3] |= (uint8_t)(0x80 >> (w->pos & 7));
+        w->pos++;
+    }
+}
+
+typedef struct {
+    int part2_3_length, big_values, global_gain, scalefac_compress;
+    int window_switching, block_type, mixed;
+    int table_select[3], subblock_gain[3];
+    int region0_count, region1_count;
+    int preflag, scalefac_scale, count1table;
+} gr_side;
+
+typedef struct {
+    int lsf, sr_row, nch, mode;
+    const l3gen_cfg *cfg;
+    rng_t rng;
+    int bt_state[2];       /* previous block type per channel */
+    int mixed_run[2];      /* mixed flag of the current run of short granules */
+    uint8_t sf_gr0[2][40];
+    int bt_gr0[2];
+} gen_t;
+
+static int pick_table(gen_t *g)
+{
+    if (g->cfg->only_table > 0) return g->cfg->only_table;
+    for (;;) {
+        int t = rndi(&g->rng, 0, 31);
+        if (t == 4 || t == 14) continue;
+        if (t == 0 && rndi(&g->rng, 0, 3)) continue; /* the empty book is legal but make it rarer */
+        return t;
+    }
+}
+
+static int next_block_type(gen_t *g, int ch)
+{
+    int prev = g->bt_state[ch], nx;
+    if (!g->cfg->blocks) return 0;
+    if (prev == 0 || prev == 3) nx = rndi(&g->rng, 0, 99) < 60 ? 0 : 1;
+    else if (prev == 1) nx = 2;
+    else nx = rndi(&g->rng, 0, 99) < 50 ? 2 : 3;
+    g->bt_state[ch] = nx;
+    return nx;
+}
+
+static int pair_bits(int tsel, int x, int y)
+{
+    int book = l3_book_of_table[tsel], lin = l3_linbits_of_table[tsel];
+    const uint8_t *hl;
+    const uint32_t *hc;
+    int dim = l3_book(book, &hl, &hc);
+    if (!dim) return 0;
+    int ax = abs(x), ay = abs(y), cx = ax > 15 ? 15 : ax, cy = ay > 15 ? 15 : ay;
+    if (!lin) { cx = ax; cy = ay; }
+    int n = hl[cx * dim + cy];
+    if (lin && cx == 15) n += lin;
+    if (lin && cy == 15) n += lin;
+    return n + (ax != 0) + (ay != 0);
+}
+
+static void put_pair(bitw *w, int tsel, int x, int y)
+{
+    int book = l3_book_of_table[tsel], lin = l3_linbits_of_table[tsel];
+    const uint8_t *hl;
+    const uint32_t *hc;
+    int dim = l3_book(book, &hl, &hc);
+    if (!dim) return;
+    int ax = abs(x), ay = abs(y), cx = ax, cy = ay;
+    if (lin) { if (cx > 15) cx = 15; if (cy > 15) cy = 15; }
+    putbits(w, hc[cx * dim + cy], hl[cx * dim + cy]);
+    if (lin && cx == 15) putbits(w, (unsigned)(ax - 15), lin);
+    if (ax) putbits(w, x < 0, 1);
+    if (lin && cy == 15) putbits(w, (unsigned)(ay - 15), lin);
+    if (ay) putbits(w, y < 0, 1);
+}
+
+static int draw_value(gen_t *g, int tsel, double scale)
+{
+    int book = l3_book_of_table[tsel], lin = l3_linbits_of_table[tsel];
+    const uint8_t *hl;
+    const uint32_t *hc;
+    int dim = l3_book(book, &hl, &hc);
+    if (!dim) return 0;
+    int maxv = dim - 1;
+    if (lin) {
+        maxv = 15 + (1 << lin) - 1;
+        if (g->cfg->max_linbits_value > 0 && maxv > g->cfg->max_linbits_value) maxv = g->cfg->max_linbits_value;
+    }
+    int v;
+    double u = rndu(&g->rng);
+    if (u < 0.02) v = maxv;                       /* make sure the extremes are exercised */
+    else if (u < 0.04 && lin) v = rndi(&g->rng, 15, maxv);
+    else {
+        v = (int)(-log(1.0 - rndu(&g->rng)) * scale);
+        if (v > maxv) v = maxv;
+    }
+    return rndi(&g->rng, 0, 1) ? -v : v;
+}
+
+/* Generate one granule-channel into w (at most `budget` bits).  Returns bits written. */
+static int gen_granule(gen_t *g, int gr, int ch, int block_type, int mixed, int mode_ext,
+                       int budget, bitw *w, gr_side *s, int scfsi[4], int line_limit)
+{
+    const l3gen_cfg *c = g->cfg;
+    rng_t *r = &g->rng;
+    size_t start = w->pos;
+    memset(s, 0, sizeof *s);
+    for (int i = 0; i < 4; i++) scfsi[i] = 0;
+    if (budget > 4095) budget = 4095;
+    s->block_type = block_type;
+    s->mixed = mixed;
+    s->window_switching = block_type != 0;
+    s->scalefac_scale = rndi(r, 0, 1);
+    s->count1table = rndi(r, 0, 1);
+    s->preflag = (!g->lsf && block_type != 2) ? (rndi(r, 0, 3) == 0) : 0;
+    if (block_type == 2)
+        for (int i = 0; i < 3; i++) s->subblock_gain[i] = rndi(r, 0, 3) ? rndi(r, 0, 7) : 0;
+    for (int i = 0; i < 3; i++) s->table_select[i] = pick_table(g);
+    if (s->window_switching) {
+        s->table_select[2] = 0;
+        s->region0_count = (block_type == 2 && !mixed) ? 8 : 7;
+        s->region1_count = 36;
+    } else {
+        s->region0_count = rndi(r, 0, 15);
+        int m = 20 - s->region0_count;
+        s->region1_count = rndi(r, 0, m > 7 ? 7 : m);
+    }
+
+    /* ---- part 2: scalefactors (band order) */
+    uint8_t sf[40];
+    memset(sf, 0, sizeof sf);
+    int ist = g->mode == 1 && (mode_ext & 1) && ch == 1;
+    if (!g->lsf) {
+        int sfc = rndi(r, 0, 15), s1, s2, nbits;
+        for (;; sfc = 0) {
+            s1 = l3_slen[0][sfc];
+            s2 = l3_slen[1][sfc];
+            if (block_type == 2) nbits = mixed ? 17 * s1 + 18 * s2 : 18 * s1 + 18 * s2;
+            else nbits = 11 * s1 + 10 * s2;
+            if (nbits <= budget || sfc == 0) break;
+        }
+        s->scalefac_compress = sfc;
+        if (block_type == 2) {
+            int n1 = mixed ? 17 : 18, ntot = mixed ? 35 : 36;
+            for (int i = 0; i < ntot; i++) {
+                int sl = i < n1 ? s1 : s2;
+                sf[i] = (uint8_t)(sl ? rndi(r, 0, (1 << sl) - 1) : 0);
+                putbits(w, sf[i], sl);
+            }
+        } else {
+            static const int grp[5] = {0, 6, 11, 16, 21};
+            int may_share = gr == 1 && g->bt_gr0[ch] != 2;
+            for (int k = 0; k < 4; k++) {
+                scfsi[k] = may_share && rndi(r, 0, 99) < c->scfsi_pct;
+                for (int b = grp[k]; b < grp[k + 1]; b++) {
+                    int sl = b < 11 ? s1 : s2;
+                    if (scfsi[k]) sf[b] = g->sf_gr0[ch][b];
+                    else {
+                        sf[b] = (uint8_t)(sl ? rndi(r, 0, (1 << sl) - 1) : 0);
+                        putbits(w, sf[b], sl);
+                    }
+                }
+            }
+        }
+        if (gr == 0) { memcpy(g->sf_gr0[ch], sf, 40); g->bt_gr0[ch] = block_type; }
+    } else {
+        int bt = block_type == 2 ? (mixed ? 2 : 1) : 0;
+        int sfc, slen[4], tbl, nbits;
+        for (int tries = 0;; tries++) {
+            sfc = tries < 8 ? rndi(r, 0, 511) : 0;
+            int v = sfc;
+            if (!ist) {
+                if (v < 400) { slen[0] = (v >> 4) / 5; slen[1] = (v >> 4) % 5; slen[2] = (v & 15) >> 2; slen[3] = v & 3; tbl = 0; }
+                else if (v < 500) { v -= 400; slen[0] = (v >> 2) / 5; slen[1] = (v >> 2) % 5; slen[2] = v & 3; slen[3] = 0; tbl = 1; }
+                else { v -= 500; slen[0] = v / 3; slen[1] = v % 3; slen[2] = 0; slen[3] = 0; tbl = 2; }
+            } else {
+                v >>= 1;
+                if (v < 180) { slen[0] = v / 36; slen[1] = (v % 36) / 6; slen[2] = v % 6; slen[3] = 0; tbl = 3; }
+                else if (v < 244) { v -= 180; slen[0] = (v & 63) >> 4; slen[1] = (v & 15) >> 2; slen[2] = v & 3; slen[3] = 0; tbl = 4; }
+                else { v -= 244; slen[0] = v / 3; slen[1] = v % 3; slen[2] = 0; slen[3] = 0; tbl = 5; }
+            }
+            nbits = 0;
+            for (int k = 0; k < 4; k++) nbits += slen[k] * l3_lsf_nsfb[tbl][bt][k];
+            if (nbits <= budget || tries >= 8) break;
+        }
+        s->scalefac_compress = sfc;
+        int n = 0;
+        for (int k = 0; k < 4; k++)
+            for (int i = 0; i < l3_lsf_nsfb[tbl][bt][k]; i++) {
+                int hi = slen[k] ? (1 << slen[k]) - 1 : 0;
+                if (ist && c->lsf_avoid_illegal_ispos && hi > 0) {
+                    hi--;                 /* never the 'illegal' position 2^slen - 1 ... */
+                    if (hi > 15) hi = 15; /* ... nor positions FFmpeg's 16-entry table cannot express */
+                }
+                sf[n] = (uint8_t)rndi(r, 0, hi);
+                putbits(w, sf[n], slen[k]);
+                n++;
+            }
+    }
+
+    /* ---- part 3: Huffman */
+    const uint16_t *bl = l3_sfb_long[g->sr_row];
+    int r1, r2;
+    if (s->window_switching) { r1 = (block_type == 2 || !g->lsf) ? 36 : 54; r2 = 576; }
+    else { r1 = bl[s->region0_count + 1]; r2 = bl[s->region0_count + s->region1_count + 2]; }
+    int bv_target = rndi(r, 0, 9) == 0 ? rndi(r, 0, 288) : rndi(r, 40, 200);
+    if (bv_target * 2 > line_limit) bv_target = line_limit / 2;
+    double scale[3];
+    for (int i = 0; i < 3; i++) scale[i] = rndi(r, 0, 4) == 0 ? 8.0 + 30.0 * rndu(r) : 0.4 + 3.0 * rndu(r);
+    double energy = 0;
+    int i = 0, bv = 0;
+    for (; bv < bv_target; bv++, i += 2) {
+        int reg = i < r1 ? 0 : (i < r2 ? 1 : 2);
+        int tsel = s->table_select[reg];
+        int x = draw_value(g, tsel, scale[reg]), y = draw_value(g, tsel, scale[reg]);
+        int nb = pair_bits(tsel, x, y);
+        if ((int)(w->pos - start) + nb > budget) break;
+        put_pair(w, tsel, x, y);
+        energy += pow(fabs((double)x), 8.0 / 3.0) + pow(fabs((double)y), 8.0 / 3.0);
+    }
+    s->big_values = bv;
+    int quads_target = rndi(r, 0, 3) == 0 ? 200 : rndi(r, 0, 60);
+    const uint8_t *ql = l3_quad_hlen[s->count1table], *qc = l3_quad_hcod[s->count1table];
+    for (int q = 0; q < quads_target && i + 4 <= 576 && i + 4 <= line_limit; q++, i += 4) {
+        int sym = rndi(r, 0, 15), nb = ql[sym] + ((sym >> 3) & 1) + ((sym >> 2) & 1) + ((sym >> 1) & 1) + (sym & 1);
+        if ((int)(w->pos - start) + nb > budget) break;
+        putbits(w, qc[sym], ql[sym]);
+        for (int k = 3; k >= 0; k--)
+            if ((sym >> k) & 1) { putbits(w, (unsigned)rndi(r, 0, 1), 1); energy += 1.0; }
+    }
+    s->part2_3_length = (int)(w->pos - start);
+
+    /* ---- level: choose global_gain so the decoded granule sits at a sane level */
+    if (energy > 0) {
+        double db = c->level_lo_db + (c->level_hi_db - c->level_lo_db) * rndu(r);
+        double target = 2.0 * pow(10.0, -db / 10.0); /* sum(xr^2) = 2 * rms^2 */
+        int gg = 210 + (int)floor(2.0 * log2(target / energy));
+        if (gg < 0) gg = 0;
+        if (gg > 255) gg = 255;
+        s->global_gain = gg;
+    } else
+        s->global_gain = rndi(r, 100, 200);
+    return s->part2_3_length;
+}
+
+static unsigned crc16_update(unsigned crc, const uint8_t *p, int nbits)
+{
+    for (int i = 0; i < nbits; i++) {
+        unsigned bit = (p[i >> 3] >> (7 - (i & 7))) & 1u;
+        unsigned top = (crc >> 15) & 1u;
+        crc = (crc << 1) & 0xffff;
+        if (top ^ bit) crc ^= 0x8005;
+    }
+    return crc;
+}
+
+static int bitrate_index(int lsf, int kbps)
+{
+    for (int i = 1; i < 15; i++)
+        if (l3_bitrate_kbps[lsf][i] == kbps) return i;
+    return -1;
+}
+
+/* Upper bound on the stream size for a config (for caller allocation). */
+size_t l3gen_max_bytes(const l3gen_cfg *c)
+{
+    int lsf = c->sample_rate < 32000;
+    int kb = c->vbr_max_kbps > 0 ? c->vbr_max_kbps : c->bitrate_kbps;
+    size_t fl = (size_t)(lsf ? 72 : 144) * kb * 1000 / c->sample_rate + 1;
+    return fl * (size_t)c->nframes + 16;
+}
+
+/* Generate one stream.  Returns bytes written, or 0 on a bad config / small buffer. */
+size_t l3gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
+{
+    gen_t g;
+    memset(&g, 0, sizeof g);
+    g.cfg = c;
+    g.rng.s = c->seed * 0x2545F4914F6CDD1Dull + 0x1234567;
+    int row = -1;
+    for (int i = 0; i < 6; i++)
+        if ((int)l3_sample_rate[i] == c->sample_rate) row = i;
+    if (row < 0 || c->nframes <= 0) return 0;
+    g.sr_row = row;
+    g.lsf = row >= 3;
+    g.mode = c->mode;
+    g.nch = c->mode == 3 ? 1 : 2;
+    int ngr = g.lsf ? 1 : 2, nch = g.nch;
+    int side_len = g.lsf ? (nch == 1 ? 9 : 17) : (nch == 1 ? 17 : 32);
+    int hdr_len = 4 + (c->crc ? 2 : 0);
+    int max_mdb = g.lsf ? 255 : 511;
+
+    /* logical main-data stream */
+    size_t lcap = l3gen_max_bytes(c) + 1024;
+    uint8_t *logical = (uint8_t *)calloc(lcap, 1);
+    typedef struct { uint8_t hdr[4]; uint8_t side[32]; int payload; } fr_t;
+    fr_t *fr = (fr_t *)calloc((size_t)c->nframes, sizeof(fr_t));
+    size_t lstart = 0;   /* logical offset of this frame's payload */
+    size_t wcur = 0;     /* first unused logical byte */
+    long pad_rest = 0;
+
+    for (int f = 0; f < c->nframes; f++) {
+        int kbps = c->bitrate_kbps, pad = 0;
+        if (c->vbr_max_kbps > 0) {
+            int lo = bitrate_index(g.lsf, c->vbr_min_kbps), hi = bitrate_index(g.lsf, c->vbr_max_kbps);
+            if (lo < 0 || hi < 0) { free(logical); free(fr); return 0; }
+            kbps = l3_bitrate_kbps[g.lsf][rndi(&g.rng, lo, hi)];
+            pad = rndi(&g.rng, 0, 1);
+        } else {
+            /* CBR padding: keep the long-run byte rate exact */
+            long num = (long)(g.lsf ? 72 : 144) * kbps * 1000;
+            pad_rest -= num % c->sample_rate;
+            if (pad_rest < 0) { pad = 1; pad_rest += c->sample_rate; }
+        }
+        int bri = bitrate_index(g.lsf, kbps);
+        if (bri < 0) { free(logical); free(fr); return 0; }
+        int frame_len = (g.lsf ? 72 : 144) * kbps * 1000 / c->sample_rate + pad;
+        int payload = frame_len - hdr_len - side_len;
+        if (payload < 0) { free(logical); free(fr); return 0; }
+        int mode_ext = 0;
+        if (c->mode == 1) {
+            int mask = c->mode_ext_mask & 15;
+            if (!mask) mask = 15;
+            do mode_ext = rndi(&g.rng, 0, 3); while (!((mask >> mode_ext) & 1));
+        }
+        /* reservoir */
+        size_t tail = lstart - wcur;
+        int mdb = 0;
+        if (c->reservoir && tail > 0) {
+            int m = tail > (size_t)max_mdb ? max_mdb : (int)tail;
+            mdb = rndi(&g.rng, 0, 3) ? m : rndi(&g.rng, 0, m);
+        }
+        size_t dstart = lstart - (size_t)mdb;
+        long avail = 8L * (mdb + payload);
+        double fill = (c->fill_lo_pct + (c->fill_hi_pct - c->fill_lo_pct) * rndu(&g.rng)) / 100.0;
+        long use = (long)(avail * fill);
+        bitw w = {logical, lcap * 8, dstart * 8};
+        size_t wstart = w.pos;
+
+        gr_side gs[2][2];
+        int scfsi[2][4];
+        memset(scfsi, 0, sizeof scfsi);
+        int nunits = ngr * nch, u = 0;
+        for (int gr = 0; gr < ngr; gr++) {
+            int bt_shared = 0, mixed_shared = 0;
+            for (int ch = 0; ch < nch; ch++, u++) {
+                int bt, mixed;
+                if (ch == 1 && c->mode == 1) { bt = bt_shared; mixed = mixed_shared; g.bt_state[1] = g.bt_state[0]; }
+                else {
+                    int prev = g.bt_state[ch];
+                    bt = next_block_type(&g, ch);
+                    mixed = (bt == 2 && !g.lsf && rndi(&g.rng, 0, 99) < c->mixed_pct);
+                    if (bt == 2 && !c->mixed_free) {
+                        if (prev == 2) mixed = g.mixed_run[ch];
+                        else g.mixed_run[ch] = mixed;
+                    }
+                    bt_shared = bt;
+                    mixed_shared = mixed;
+                }
+                long used = (long)(w.pos - wstart);
+                long left = use - used;
+                int remaining_units = nunits - u;
+                long share = left / remaining_units;
+                if (remaining_units > 1) share = (long)(share * (0.6 + 0.8 * rndu(&g.rng)));
+                if (share > left) share = left;
+                if (share < 0) share = 0;
+                int limit = 576;
+                if (c->mode == 1 && (mode_ext & 1) && ch == 1) limit = rndi(&g.rng, 0, 3) ? rndi(&g.rng, 0, 400) : 576;
+                int sc[4];
+                gen_granule(&g, gr, ch, bt, mixed, mode_ext, (int)share, &w, &gs[gr][ch], sc, limit);
+                if (gr == 1) memcpy(scfsi[ch], sc, sizeof sc);
+            }
+        }
+        size_t used_bytes = (w.pos - wstart + 7) / 8;
+        wcur = dstart + used_bytes;
+
+        /* header */
+        uint8_t *h = fr[f].hdr;
+        int sri = row % 3;
+        h[0] = 0xFF;
+        h[1] = (uint8_t)(0xE0 | ((g.lsf ? 2 : 3) << 3) | (1 << 1) | (c->crc ? 0 : 1));
+        h[2] = (uint8_t)((bri << 4) | (sri << 2) | (pad << 1));
+        h[3] = (uint8_t)((c->mode << 6) | (mode_ext << 4));
+        /* side info */
+        uint8_t *sp = fr[f].side;
+        memset(sp, 0, 32);
+        bitw sw = {sp, (size_t)side_len * 8, 0};
+        if (!g.lsf) {
+            putbits(&sw, (unsigned)mdb, 9);
+            putbits(&sw, 0, nch == 1 ? 5 : 3);
+            for (int ch = 0; ch < nch; ch++)
+                for (int k = 0; k < 4; k++) putbits(&sw, (unsigned)scfsi[ch][k], 1);
+        } else {
+            putbits(&sw, (unsigned)mdb, 8);
+            putbits(&sw, 0, nch == 1 ? 1 : 2);
+        }
+        for (int gr = 0; gr < ngr; gr++)
+            for (int ch = 0; ch < nch; ch++) {
+                gr_side *s = &gs[gr][ch];
+                putbits(&sw, (unsigned)s->part2_3_length, 12);
+                putbits(&sw, (unsigned)s->big_values, 9);
+                putbits(&sw, (unsigned)s->global_gain, 8);
+                putbits(&sw, (unsigned)s->scalefac_compress, g.lsf ? 9 : 4);
+                putbits(&sw, (unsigned)s->window_switching, 1);
+                if (s->window_switching) {
+                    putbits(&sw, (unsigned)s->block_type, 2);
+                    putbits(&sw, (unsigned)s->mixed, 1);
+                    putbits(&sw, (unsigned)s->table_select[0], 5);
+                    putbits(&sw, (unsigned)s->table_select[1], 5);
+                    for (int k = 0; k < 3; k++) putbits(&sw, (unsigned)s->subblock_gain[k], 3);
+                } else {
+                    for (int k = 0; k < 3; k++) putbits(&sw, (unsigned)s->table_select[k], 5);
+                    putbits(&sw, (unsigned)s->region0_count, 4);
+                    putbits(&sw, (unsigned)s->region1_count, 3);
+                }
+                if (!g.lsf) putbits(&sw, (unsigned)s->preflag, 1);
+                putbits(&sw, (unsigned)s->scalefac_scale, 1);
+                putbits(&sw, (unsigned)s->count1table, 1);
+            }
+        fr[f].payload = payload;
+        lstart += (size_t)payload;
+    }
+
+    /* interleave headers / side info / payload slices into the physical stream */
+    size_t o = 0, lp = 0;
+    for (int f = 0; f < c->nframes; f++) {
+        size_t need = (size_t)hdr_len + side_len + fr[f].payload;
+        if (o + need > cap) { free(logical); free(fr); return 0; }
+        memcpy(out + o, fr[f].hdr, 4);
+        if (c->crc) {
+            unsigned crc = 0xffff;
+            crc = crc16_update(crc, fr[f].hdr + 2, 16);
+            crc = crc16_update(crc, fr[f].side, side_len * 8);
+            out[o + 4] = (uint8_t)(crc >> 8);
+            out[o + 5] = (uint8_t)crc;
+        }
+        memcpy(out + o + hdr_len, fr[f].side, (size_t)side_len);
+        memcpy(out + o + hdr_len + side_len, logical + lp, (size_t)fr[f].payload);
+        o += need;
+        lp += (size_t)fr[f].payload;
+    }
+    free(logical);
+    free(fr);
+    return o;
+}

@@ -1,0 +1,52 @@
+"""Small pure-Python helpers for tests: frame splitting and the ISO 11172-4 accuracy criterion."""
+import numpy as np
+
+_BR = [[0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 0],
+       [0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, 0]]
+_SR = [[44100, 48000, 32000], [22050, 24000, 16000]]
+
+
+def frame_len(h):
+    """Length in bytes of the Layer III frame whose 4 header bytes are h, or 0 if invalid."""
+    if h[0] != 0xFF or (h[1] & 0xE0) != 0xE0:
+        return 0
+    ver = (h[1] >> 3) & 3
+    if ver not in (2, 3) or ((h[1] >> 1) & 3) != 1:
+        return 0
+    lsf = 1 if ver == 2 else 0
+    bri, sri = h[2] >> 4, (h[2] >> 2) & 3
+    if bri in (0, 15) or sri == 3:
+        return 0
+    pad = (h[2] >> 1) & 1
+    return (72 if lsf else 144) * _BR[lsf][bri] * 1000 // _SR[lsf][sri] + pad
+
+
+def split_frames(data):
+    out, p = [], 0
+    while p + 4 <= len(data):
+        n = frame_len(data[p:p + 4])
+        if n == 0 or p + n > len(data):
+            p += 1
+            continue
+        out.append(data[p:p + n])
+        p += n
+    return out
+
+
+RMS_LIMIT = 2.0 ** -15 / np.sqrt(12.0)   # ISO/IEC 11172-4 full accuracy: rms of the difference
+MAX_LIMIT = 2.0 ** -14                    # and maximum absolute difference, full scale = +-1.0
+
+
+def iso_compliance(test, ref):
+    """Return (rms_error, max_abs_error) between two PCM arrays in full-scale +-1 units."""
+    d = np.asarray(test, np.float64) - np.asarray(ref, np.float64)
+    if d.size == 0:
+        return 0.0, 0.0
+    return float(np.sqrt(np.mean(d * d))), float(np.max(np.abs(d)))
+
+
+def assert_iso_full_accuracy(test, ref, what=""):
+    rms, mx = iso_compliance(test, ref)
+    assert rms < RMS_LIMIT and mx <= MAX_LIMIT, "%s: rms %.3g (limit %.3g) max %.3g (limit %.3g)" % (
+        what, rms, RMS_LIMIT, mx, MAX_LIMIT)
+    return rms, mx

@@ -1,0 +1,66 @@
+"""Pin the ISO tables compiled into the oracle against libavcodec's .rodata."""
+import os
+import struct
+import sys
+
+import pytest
+
+import ffmpeg_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+SFB_LONG_WIDTH_441 = bytes([4, 4, 4, 4, 4, 4, 6, 6, 8, 8, 10, 12, 16, 20, 24, 28, 34, 42, 50, 54, 76, 158])
+
+
+def test_tables_are_complete_prefix_codes(oracle_mod):
+    import ctypes
+    L = oracle_mod.lib()
+    for book, dim in ((1, 2), (2, 3), (3, 3), (5, 4), (6, 4), (7, 6), (8, 6), (9, 6), (10, 8), (11, 8), (12, 8),
+                      (13, 16), (15, 16), (16, 16), (24, 16)):
+        kraft = 0
+        seen = set()
+        for x in range(dim):
+            for y in range(dim):
+                hl, hc = ctypes.c_int(), ctypes.c_uint()
+                assert L.l3o_book_entry(book, x, y, ctypes.byref(hl), ctypes.byref(hc)) == dim
+                assert 1 <= hl.value <= 19 and hc.value < (1 << hl.value)
+                kraft += 1 << (19 - hl.value)
+                seen.add((hl.value, hc.value))
+        assert kraft == 1 << 19 and len(seen) == dim * dim, book
+
+
+def test_window_symmetry(oracle_mod):
+    L = oracle_mod.lib()
+    d = [L.l3o_dwin(i) for i in range(512)]
+    assert d[0] == 0.0 and abs(d[256] - 75038 / 65536.0) == 0.0
+    for i in range(1, 256):
+        if i % 64:
+            assert d[512 - i] == -d[i]
+        else:
+            assert d[512 - i] == d[i]
+    assert all(abs(v * 65536 - round(v * 65536)) == 0 for v in d)
+
+
+@pytest.mark.skipif(ffmpeg_ref.libavcodec_path() is None, reason="libavcodec not present")
+def test_tables_match_libavcodec_rodata(oracle_mod):
+    import ctypes
+    import derive_tables
+    books, win = derive_tables.extract(ffmpeg_ref.libavcodec_path())
+    L = oracle_mod.lib()
+    for bid, (dim, hlen, hcod) in books.items():
+        for x in range(dim):
+            for y in range(dim):
+                hl, hc = ctypes.c_int(), ctypes.c_uint()
+                L.l3o_book_entry(bid, x, y, ctypes.byref(hl), ctypes.byref(hc))
+                assert (hl.value, hc.value) == (hlen[x * dim + y], hcod[x * dim + y])
+    for i in range(257):
+        assert L.l3o_dwin(i) == win[i] / 65536.0
+    blob = open(ffmpeg_ref.libavcodec_path(), "rb").read()
+    # band widths: 44.1 kHz long row
+    i = blob.find(SFB_LONG_WIDTH_441)
+    assert i >= 0
+    rows = [blob[i + 22 * r: i + 22 * (r + 1)] for r in range(6)]
+    for r in range(6):
+        edges = [L.l3o_sfb_long(r, k) for k in range(23)]
+        assert bytes(b - a for a, b in zip(edges, edges[1:])) == rows[r], r
