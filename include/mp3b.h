@@ -1,0 +1,155 @@
+/* mp3b.h -- C-ABI of libmp3b, the B200-native batched MPEG-1/2 Layer III decoder.
+ *
+ * Reference interface replaced: NONE EXISTS.  The reference repository (lxm0851/mp3) exposes no
+ * plugin / operator / FFI boundary and names no decoder library: /root/reference/README.md:1-84
+ * is prose (the only technical statement is "audio player", README.md:2; the only input format is
+ * "user-uploaded audio", README.md:71).  The boundary below is therefore the one SURVEY.md
+ * section 8(b) specifies for the inferred hot path (open stream / enqueue bytes / decode / fetch
+ * PCM, plus a bulk batch entry), in the shape a player written in a scripting language would
+ * bind through ctypes/cffi (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain C types only; no C++ types, exceptions, errno or signals cross this boundary;
+ *   - every function returning int returns MP3B_OK (0) or a negative mp3b_status;
+ *   - one mp3b_ctx per GPU, owned by one thread; different contexts share nothing, so N GPUs are
+ *     N contexts in N threads or processes with no communication (no NCCL);
+ *   - corrupt or undecodable frames are never fatal: they are skipped (sync search) or
+ *     concealed as silence, and counted in mp3b_stats;
+ *   - there is NO CPU fallback: if no CUDA device is usable, mp3b_ctx_create fails with
+ *     MP3B_E_CUDA.
+ */
+#ifndef MP3B_H
+#define MP3B_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP3B_ABI_VERSION 1
+
+typedef enum mp3b_status {
+    MP3B_OK = 0,
+    MP3B_E_INVAL = -1,       /* bad argument */
+    MP3B_E_NOSYNC = -2,      /* no Layer III frame found in a stream */
+    MP3B_E_TRUNCATED = -3,   /* destination buffer too small */
+    MP3B_E_UNSUPPORTED = -4, /* Layer I/II, free format, MPEG-2.5 */
+    MP3B_E_CUDA = -5,        /* CUDA runtime error; mp3b_last_error() has the text */
+    MP3B_E_NOMEM = -6,
+    MP3B_E_STATE = -7        /* call order violated (e.g. fetch before decode) */
+} mp3b_status;
+
+typedef enum mp3b_pcm_format {
+    MP3B_PCM_S16 = 0, /* interleaved int16, round-to-nearest, saturated */
+    MP3B_PCM_F32 = 1  /* interleaved float32, full scale +-1.0, not clipped */
+} mp3b_pcm_format;
+
+typedef enum mp3b_where { MP3B_HOST = 0, MP3B_DEVICE = 1 } mp3b_where;
+
+typedef enum mp3b_indexer {
+    MP3B_INDEX_DEVICE = 0, /* frame scan + side-info parse on the GPU (default) */
+    MP3B_INDEX_HOST = 1    /* frame scan on host threads, table uploaded */
+} mp3b_indexer;
+
+typedef enum mp3b_pipeline {
+    MP3B_PIPE_FUSED = 0,  /* default: fewest HBM round trips */
+    MP3B_PIPE_STAGED = 1  /* one kernel per stage, every intermediate in HBM (debug / parity) */
+} mp3b_pipeline;
+
+typedef struct mp3b_opts {
+    uint32_t struct_size;  /* = sizeof(mp3b_opts); lets the struct grow compatibly */
+    int32_t pcm_format;    /* mp3b_pcm_format */
+    int32_t indexer;       /* mp3b_indexer */
+    int32_t pipeline;      /* mp3b_pipeline */
+    int32_t host_threads;  /* host indexer / gather threads; 0 = hardware concurrency */
+    int32_t keep_stages;   /* 1 = keep intermediates addressable through mp3b_debug_stage */
+} mp3b_opts;
+
+typedef struct mp3b_stream_info {
+    int32_t sample_rate;
+    int32_t channels;
+    int32_t lsf;            /* 0 = MPEG-1, 1 = MPEG-2 LSF */
+    int32_t reserved;
+    int64_t frames;
+    int64_t samples;        /* per channel */
+    int64_t concealed_frames;
+    int64_t pcm_offset;     /* element offset of this stream's PCM in the batch PCM arena */
+} mp3b_stream_info;
+
+typedef struct mp3b_stats {
+    int64_t streams, frames, granules, units; /* unit = one granule-channel (576 lines) */
+    int64_t bytes_in, pcm_bytes;
+    int64_t concealed_frames;
+    int64_t kernel_launches;  /* kernels launched by the last decode call */
+    float ms_index, ms_huffman, ms_requant, ms_imdct, ms_overlap, ms_synth, ms_fused, ms_total;
+} mp3b_stats;
+
+typedef struct mp3b_ctx mp3b_ctx;
+typedef struct mp3b_stream mp3b_stream;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int mp3b_abi_version(void);
+int mp3b_device_count(void);
+void mp3b_opts_default(mp3b_opts *o);
+int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out);
+void mp3b_ctx_destroy(mp3b_ctx *ctx);
+const char *mp3b_strerror(int status);
+const char *mp3b_last_error(const mp3b_ctx *ctx);
+
+/* Pinned host memory (page-locked) so that H2D / D2H copies run at PCIe speed and async. */
+void *mp3b_host_alloc(size_t bytes);
+void mp3b_host_free(void *p);
+
+/* ---- bulk batch decode ----------------------------------------------------------------------
+ * Streams are given either as an array of host pointers (gathered by the library) or packed in one
+ * buffer with offsets (offsets[nstreams] = end of the last stream), host or device resident.
+ * The call enqueues everything on the context's CUDA stream; mp3b_sync() waits for it.
+ * Results stay in the context (device memory) until the next decode call or mp3b_ctx_destroy. */
+int mp3b_decode_batch(mp3b_ctx *ctx, const uint8_t *const *bufs, const size_t *lens, int nstreams);
+int mp3b_decode_packed(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams,
+                       int where /* mp3b_where: where `base` lives */);
+int mp3b_sync(mp3b_ctx *ctx);
+
+int mp3b_batch_stream_info(const mp3b_ctx *ctx, int stream_index, mp3b_stream_info *info);
+/* Whole-batch PCM arena: streams back to back in input order, interleaved channels. */
+int mp3b_batch_pcm_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems);
+/* Copy the whole arena (nelems elements of the context's pcm_format) to `dst`; async when dst is
+ * pinned; call mp3b_sync() before reading it. */
+int mp3b_batch_fetch_pcm(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got);
+int mp3b_get_stats(const mp3b_ctx *ctx, mp3b_stats *st);
+
+/* ---- stream interface (open / enqueue / decode / fetch) ------------------------------------- */
+int mp3b_stream_open(mp3b_ctx *ctx, mp3b_stream **out);
+void mp3b_stream_close(mp3b_stream *s);
+/* Appends raw MP3 bytes; the library copies, the caller may free its buffer on return. */
+int mp3b_stream_enqueue(mp3b_stream *s, const uint8_t *bytes, size_t n);
+/* Decodes everything enqueued so far on every open stream of the context (async), as one batch. */
+int mp3b_decode(mp3b_ctx *ctx);
+int mp3b_stream_get_info(const mp3b_stream *s, mp3b_stream_info *info);
+/* Copies up to cap_samples (per channel) of not-yet-fetched PCM, advancing the stream's read
+ * cursor; *got = samples per channel copied. */
+int mp3b_stream_fetch_pcm(mp3b_stream *s, void *dst, size_t cap_samples, int where, size_t *got);
+/* Zero-copy view of the stream's decoded PCM (valid until the next decode call / close). */
+int mp3b_stream_pcm_device_ptr(const mp3b_stream *s, const void **ptr, size_t *nsamples);
+
+/* ---- debug / parity access to intermediates (keep_stages = 1) -------------------------------
+ * stage: see mp3b_stage.  Copies the whole stage array for the last batch to host memory.
+ * *elem_size receives the element size in bytes, *count the number of elements. */
+typedef enum mp3b_stage {
+    MP3B_STAGE_FRAMES = 0,   /* uint32[4] per frame: rel_off, payload_off, header, stream */
+    MP3B_STAGE_UNITDESC = 1, /* 32-byte unit descriptors */
+    MP3B_STAGE_IS = 2,       /* int16[576] per unit: Huffman output */
+    MP3B_STAGE_SF = 3,       /* uint8[40] per unit: scalefactors in band order */
+    MP3B_STAGE_XR = 4,       /* float[576] per unit: after requant/stereo/reorder/alias */
+    MP3B_STAGE_SB = 5,       /* float[18][32] per unit: subband samples */
+    MP3B_STAGE_MAINDATA = 6  /* uint8: compacted main-data arena */
+} mp3b_stage;
+int mp3b_debug_stage(mp3b_ctx *ctx, int stage, void *dst, uint64_t cap_bytes, uint32_t *elem_size,
+                     uint64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP3B_H */

@@ -1,1 +1,305 @@
-"""mp3_b200 -- B200-native batched MPEG-1/2 Layer III decoder (host-side Python mirror of the C-ABI)."""
+"""mp3_b200 -- B200-native batched MPEG-1/2 Layer III decoder.
+
+Python host-side mirror of the C-ABI in include/mp3b.h (ctypes).  The reference project
+(lxm0851/mp3) is a scripting-language audio player with no published source
+(/root/reference/README.md:2,44), so this is the binding such a player would use: open a context
+on a GPU, hand it MP3 byte strings, get PCM back.
+
+There is deliberately no CPU fallback: if libmp3b.so is missing, or no CUDA device is usable,
+the calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from ._build import LIB, build_lib  # noqa: F401
+
+PCM_S16, PCM_F32 = 0, 1
+HOST, DEVICE = 0, 1
+INDEX_DEVICE, INDEX_HOST = 0, 1
+PIPE_FUSED, PIPE_STAGED = 0, 1
+STAGE_FRAMES, STAGE_UNITDESC, STAGE_IS, STAGE_SF, STAGE_XR, STAGE_SB, STAGE_MAINDATA = range(7)
+
+
+class Mp3bError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("mp3b: %s (status %d)" % (msg, status))
+        self.status = status
+
+
+class Opts(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("pcm_format", ctypes.c_int32), ("indexer", ctypes.c_int32),
+                ("pipeline", ctypes.c_int32), ("host_threads", ctypes.c_int32), ("keep_stages", ctypes.c_int32)]
+
+
+class StreamInfo(ctypes.Structure):
+    _fields_ = [("sample_rate", ctypes.c_int32), ("channels", ctypes.c_int32), ("lsf", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("frames", ctypes.c_int64), ("samples", ctypes.c_int64),
+                ("concealed_frames", ctypes.c_int64), ("pcm_offset", ctypes.c_int64)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("streams", ctypes.c_int64), ("frames", ctypes.c_int64), ("granules", ctypes.c_int64),
+                ("units", ctypes.c_int64), ("bytes_in", ctypes.c_int64), ("pcm_bytes", ctypes.c_int64),
+                ("concealed_frames", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
+                ("ms_index", ctypes.c_float), ("ms_huffman", ctypes.c_float), ("ms_requant", ctypes.c_float),
+                ("ms_imdct", ctypes.c_float), ("ms_overlap", ctypes.c_float), ("ms_synth", ctypes.c_float),
+                ("ms_fused", ctypes.c_float), ("ms_total", ctypes.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = [
+    "mp3b_abi_version", "mp3b_device_count", "mp3b_opts_default", "mp3b_ctx_create", "mp3b_ctx_destroy",
+    "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
+    "mp3b_decode_packed", "mp3b_sync", "mp3b_batch_stream_info", "mp3b_batch_pcm_device_ptr",
+    "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
+    "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
+    "mp3b_debug_stage",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libmp3b.so (never builds implicitly; call build_lib() / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        raise Mp3bError(-5, "libmp3b.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                            "there is no CPU fallback")
+    L = ctypes.CDLL(LIB)
+    vp, i32, u64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t
+    L.mp3b_strerror.restype = ctypes.c_char_p
+    L.mp3b_last_error.restype = ctypes.c_char_p
+    L.mp3b_last_error.argtypes = [vp]
+    L.mp3b_host_alloc.restype = vp
+    L.mp3b_host_alloc.argtypes = [sz]
+    L.mp3b_host_free.argtypes = [vp]
+    L.mp3b_ctx_create.argtypes = [i32, ctypes.POINTER(Opts), ctypes.POINTER(vp)]
+    L.mp3b_ctx_destroy.argtypes = [vp]
+    L.mp3b_opts_default.argtypes = [ctypes.POINTER(Opts)]
+    L.mp3b_decode_batch.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), i32]
+    L.mp3b_decode_packed.argtypes = [vp, vp, ctypes.POINTER(u64), i32, i32]
+    L.mp3b_sync.argtypes = [vp]
+    L.mp3b_batch_stream_info.argtypes = [vp, i32, ctypes.POINTER(StreamInfo)]
+    L.mp3b_batch_pcm_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
+    L.mp3b_batch_fetch_pcm.argtypes = [vp, vp, u64, i32, ctypes.POINTER(u64)]
+    L.mp3b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.mp3b_stream_open.argtypes = [vp, ctypes.POINTER(vp)]
+    L.mp3b_stream_close.argtypes = [vp]
+    L.mp3b_stream_enqueue.argtypes = [vp, vp, sz]
+    L.mp3b_decode.argtypes = [vp]
+    L.mp3b_stream_get_info.argtypes = [vp, ctypes.POINTER(StreamInfo)]
+    L.mp3b_stream_fetch_pcm.argtypes = [vp, vp, sz, i32, ctypes.POINTER(sz)]
+    L.mp3b_stream_pcm_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]
+    L.mp3b_debug_stage.argtypes = [vp, i32, vp, u64, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64)]
+    _lib = L
+    return L
+
+
+class PinnedBuffer:
+    """Page-locked host memory from mp3b_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, nbytes):
+        self._L = load_library()
+        self.nbytes = int(nbytes)
+        self.ptr = self._L.mp3b_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise Mp3bError(-6, "pinned allocation of %d bytes failed" % nbytes)
+        self.array = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(ctypes.c_uint8)), (max(self.nbytes, 1),))
+
+    def view(self, dtype, count=None):
+        a = self.array[: self.nbytes].view(dtype)
+        return a if count is None else a[:count]
+
+    def free(self):
+        if self.ptr:
+            self._L.mp3b_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Stream:
+    """open / enqueue / decode / fetch interface of one MP3 stream (mp3b_stream_*)."""
+
+    def __init__(self, dec):
+        self.dec = dec
+        h = ctypes.c_void_p()
+        dec._ck(dec.L.mp3b_stream_open(dec.ctx, ctypes.byref(h)))
+        self.h = h
+
+    def enqueue(self, data):
+        data = bytes(data)
+        buf = (ctypes.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
+        self.dec._ck(self.dec.L.mp3b_stream_enqueue(self.h, buf, len(data)))
+
+    def info(self):
+        inf = StreamInfo()
+        self.dec._ck(self.dec.L.mp3b_stream_get_info(self.h, ctypes.byref(inf)))
+        return inf
+
+    def fetch(self, max_samples):
+        inf = self.info()
+        dt = np.int16 if self.dec.pcm_format == PCM_S16 else np.float32
+        out = np.zeros((max_samples, max(inf.channels, 1)), dt)
+        got = ctypes.c_size_t()
+        self.dec._ck(self.dec.L.mp3b_stream_fetch_pcm(self.h, out.ctypes.data_as(ctypes.c_void_p), max_samples, HOST,
+                                                     ctypes.byref(got)))
+        return out[: got.value]
+
+    def close(self):
+        if self.h:
+            self.dec.L.mp3b_stream_close(self.h)
+            self.h = None
+
+
+class Decoder:
+    """One context on one GPU (mp3b_ctx).  Not thread-safe; use one per GPU."""
+
+    def __init__(self, device=0, pcm_format=PCM_S16, indexer=INDEX_DEVICE, pipeline=None, host_threads=0,
+                 keep_stages=False):
+        self.L = load_library()
+        o = Opts()
+        self.L.mp3b_opts_default(ctypes.byref(o))
+        o.pcm_format, o.indexer, o.host_threads, o.keep_stages = pcm_format, indexer, host_threads, int(keep_stages)
+        if pipeline is not None:
+            o.pipeline = pipeline
+        self.pcm_format = pcm_format
+        ctx = ctypes.c_void_p()
+        rc = self.L.mp3b_ctx_create(device, ctypes.byref(o), ctypes.byref(ctx))
+        if rc != 0:
+            raise Mp3bError(rc, self.L.mp3b_strerror(rc).decode() + " -- no CPU fallback exists")
+        self.ctx = ctx
+        self.nstreams = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            extra = self.L.mp3b_last_error(self.ctx).decode() if self.ctx else ""
+            raise Mp3bError(rc, self.L.mp3b_strerror(rc).decode() + (": " + extra if extra else ""))
+
+    def close(self):
+        if self.ctx:
+            self.L.mp3b_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- bulk interface
+    def decode_batch(self, streams, sync=True):
+        """streams: list of bytes-like.  Gathers on the host (mp3b_decode_batch)."""
+        n = len(streams)
+        keep = [np.frombuffer(bytes(s) if not isinstance(s, (bytes, bytearray, np.ndarray)) else s, np.uint8)
+                for s in streams]
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[k.ctypes.data if k.size else None for k in keep])
+        lens = (ctypes.c_size_t * max(n, 1))(*[k.size for k in keep])
+        self._ck(self.L.mp3b_decode_batch(self.ctx, ptrs, lens, n))
+        self.nstreams = n
+        if sync:
+            self.sync()
+
+    def decode_packed(self, base_ptr, offsets, where=HOST, sync=True):
+        """base_ptr: integer address (host pinned / pageable, or device); offsets: uint64[n+1]."""
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = offsets.size - 1
+        self._ck(self.L.mp3b_decode_packed(self.ctx, ctypes.c_void_p(base_ptr),
+                                           offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), n, where))
+        self.nstreams = n
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._ck(self.L.mp3b_sync(self.ctx))
+
+    def stream_info(self, i):
+        inf = StreamInfo()
+        rc = self.L.mp3b_batch_stream_info(self.ctx, i, ctypes.byref(inf))
+        if rc not in (0, -2):
+            self._ck(rc)
+        return inf
+
+    def pcm_device(self):
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._ck(self.L.mp3b_batch_pcm_device_ptr(self.ctx, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def fetch_pcm(self, out=None):
+        """Whole-batch PCM arena as a flat numpy array (int16 or float32)."""
+        _, n = self.pcm_device()
+        dt = np.int16 if self.pcm_format == PCM_S16 else np.float32
+        if out is None:
+            out = np.empty(n, dt)
+        got = ctypes.c_uint64()
+        self._ck(self.L.mp3b_batch_fetch_pcm(self.ctx, out.ctypes.data_as(ctypes.c_void_p), out.size, HOST,
+                                             ctypes.byref(got)))
+        self.sync()
+        return out[: got.value]
+
+    def fetch_pcm_into(self, host_ptr, cap_elems):
+        got = ctypes.c_uint64()
+        self._ck(self.L.mp3b_batch_fetch_pcm(self.ctx, ctypes.c_void_p(host_ptr), cap_elems, HOST, ctypes.byref(got)))
+        return got.value
+
+    def stream_pcm(self, i, arena=None):
+        """PCM of stream i as [samples, channels]."""
+        inf = self.stream_info(i)
+        if arena is None:
+            arena = self.fetch_pcm()
+        n = inf.samples * inf.channels
+        return arena[inf.pcm_offset: inf.pcm_offset + n].reshape(inf.samples, max(inf.channels, 1))
+
+    def stats(self):
+        st = Stats()
+        self._ck(self.L.mp3b_get_stats(self.ctx, ctypes.byref(st)))
+        return st
+
+    def stage(self, which):
+        es, cnt = ctypes.c_uint32(), ctypes.c_uint64()
+        self._ck(self.L.mp3b_debug_stage(self.ctx, which, None, 0, ctypes.byref(es), ctypes.byref(cnt)))
+        dt = {STAGE_IS: np.int16, STAGE_SF: np.uint8, STAGE_XR: np.float32, STAGE_SB: np.float32,
+              STAGE_MAINDATA: np.uint8, STAGE_FRAMES: np.uint32, STAGE_UNITDESC: np.uint8}[which]
+        nbytes = es.value * cnt.value
+        out = np.empty(nbytes // np.dtype(dt).itemsize, dt)
+        self._ck(self.L.mp3b_debug_stage(self.ctx, which, out.ctypes.data_as(ctypes.c_void_p), nbytes, None, None))
+        if which in (STAGE_IS, STAGE_XR):
+            return out.reshape(-1, 576)
+        if which == STAGE_SF:
+            return out.reshape(-1, 40)
+        if which == STAGE_SB:
+            return out.reshape(-1, 18, 32)
+        if which == STAGE_FRAMES:
+            return out.reshape(-1, 4)
+        if which == STAGE_UNITDESC:
+            return out.reshape(-1, 32)
+        return out
+
+    # ---- stream interface
+    def open_stream(self):
+        return Stream(self)
+
+    def decode_streams(self):
+        self._ck(self.L.mp3b_decode(self.ctx))
+        self.sync()
+
+
+def pack_streams(streams):
+    """Concatenate byte strings; returns (uint8 array, uint64 offsets[n+1])."""
+    lens = np.array([len(s) for s in streams], np.uint64)
+    offs = np.zeros(len(streams) + 1, np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    buf = np.empty(int(offs[-1]), np.uint8)
+    for s, o in zip(streams, offs[:-1]):
+        buf[int(o): int(o) + len(s)] = np.frombuffer(s, np.uint8)
+    return buf, offs

@@ -1,0 +1,750 @@
+// api.cu -- the C-ABI of libmp3b (include/mp3b.h): contexts, device memory, the decode
+// orchestration and the host-side frame indexer.
+//
+// There is no reference interface to mirror (/root/reference/README.md:1-84 is prose; see the
+// header of include/mp3b.h); the entry points are the ones SURVEY.md section 8(b) specifies.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "iso_tables.h"
+#include "kernels.h"
+#include "l3_side.h"
+#include "mp3b.h"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { // retry exact
+            e = cudaMalloc(&p, n);
+            want = n;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum { EV_START = 0, EV_INDEX, EV_HUFF, EV_REQ, EV_IMDCT, EV_OVL, EV_SYNTH, EV_END, EV_COUNT };
+
+} // namespace
+
+struct mp3b_stream {
+    mp3b_ctx *ctx;
+    std::vector<uint8_t> pending;
+    int batch_index = -1; // index in the last mp3b_decode() batch
+    size_t cursor = 0;    // samples per channel already fetched
+};
+
+struct mp3b_ctx {
+    int device = 0;
+    mp3b_opts opts{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT]{};
+    std::string err;
+
+    // device tables
+    DevBuf d_tables;
+    L3DevTables T{};
+
+    // per-batch device state
+    DevBuf d_raw, d_streams, d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm;
+    DevBuf d_is, d_sf, d_xr, d_imd, d_sb; // wave-sized intermediates
+    PinBuf h_streams, h_frames, h_tiles, h_stage, h_counter;
+
+    const uint8_t *raw_dev = nullptr; // d_raw or the caller's device buffer
+    std::vector<mp3b_stream_info> infos;
+    uint64_t pcm_elems = 0;
+    uint64_t arena_bytes = 0;
+    uint32_t nstreams = 0, nframes = 0, ngran = 0, nunits = 0, ntiles = 0;
+    uint64_t wave_units = 2u << 20;
+    bool have_batch = false, timed = false;
+    mp3b_stats stats{};
+    std::vector<mp3b_stream *> open_streams;
+    PinBuf h_gather;
+    std::vector<uint64_t> gather_offsets;
+};
+
+namespace {
+
+int fail(mp3b_ctx *c, cudaError_t e, const char *what)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    c->err = buf;
+    cudaGetLastError();
+    return MP3B_E_CUDA;
+}
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail(ctx, e__, #call); \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int upload_tables(mp3b_ctx *ctx)
+{
+    L3HostTables *h = new L3HostTables;
+    l3_build_host_tables(h);
+    if (!h->huff_lut_len) { delete h; ctx->err = "table build failed"; return MP3B_E_INVAL; }
+    // one allocation: [lut][huffinfo][quad][bands][pow43][sfb_long]
+    size_t o_lut = 0, o_info = align_up(o_lut + sizeof h->huff_lut, 256);
+    size_t o_quad = align_up(o_info + sizeof(L3HuffInfo), 256), o_bands = align_up(o_quad + 64, 256);
+    size_t o_pow = align_up(o_bands + sizeof(L3BandTables), 256), o_sfb = align_up(o_pow + sizeof h->pow43, 256);
+    size_t total = o_sfb + sizeof(uint16_t) * 6 * 23;
+    std::vector<uint8_t> blob(total, 0);
+    memcpy(blob.data() + o_lut, h->huff_lut, sizeof h->huff_lut);
+    memcpy(blob.data() + o_info, &h->huff, sizeof(L3HuffInfo));
+    memcpy(blob.data() + o_quad, h->quad_a, 64);
+    memcpy(blob.data() + o_bands, &h->bands, sizeof(L3BandTables));
+    memcpy(blob.data() + o_pow, h->pow43, sizeof h->pow43);
+    memcpy(blob.data() + o_sfb, l3_sfb_long, sizeof(uint16_t) * 6 * 23);
+    uint32_t lut_len = h->huff_lut_len;
+    delete h;
+    CK(ctx->d_tables.ensure(total));
+    CK(cudaMemcpy(ctx->d_tables.p, blob.data(), total, cudaMemcpyHostToDevice));
+    uint8_t *b = ctx->d_tables.as<uint8_t>();
+    ctx->T.huff_lut = reinterpret_cast<const uint16_t *>(b + o_lut);
+    ctx->T.huff_lut_len = lut_len;
+    ctx->T.huff = reinterpret_cast<const L3HuffInfo *>(b + o_info);
+    ctx->T.quad_a = b + o_quad;
+    ctx->T.bands = reinterpret_cast<const L3BandTables *>(b + o_bands);
+    ctx->T.pow43 = reinterpret_cast<const float *>(b + o_pow);
+    ctx->T.sfb_long = reinterpret_cast<const uint16_t *>(b + o_sfb);
+    l3_requant_init();
+    l3_hybrid_init();
+    l3_synth_init();
+    CK(cudaGetLastError());
+    return MP3B_OK;
+}
+
+// Host frame indexer (MP3B_INDEX_HOST): same walk as k_index_count + k_index_fill.
+void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRec> *out, uint32_t sidx)
+{
+    uint32_t len = r->raw_len, p = l3_id3v2_len(buf, len), first = 0, first_off = 0, n = 0, payload = 0;
+    while (p + 4 <= len) {
+        L3Hdr h;
+        uint32_t w;
+        if (!l3_frame_at(buf, len, p, first, &h, &w)) { p++; continue; }
+        if (!first) { first = w; first_off = p; }
+        L3FrameRec f;
+        f.rel_off = p;
+        f.payload_off = payload;
+        f.hdr = w;
+        f.stream = sidx;
+        out->push_back(f);
+        n++;
+        payload += (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
+        p += (uint32_t)h.frame_len;
+    }
+    r->first_off = first_off;
+    r->first_hdr = first;
+    r->nframes = n;
+    r->payload_len = payload;
+}
+
+int nthreads_of(const mp3b_ctx *ctx)
+{
+    int n = ctx->opts.host_threads;
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    return n < 1 ? 1 : (n > 64 ? 64 : n);
+}
+
+template <class F> void parallel_for(int nthreads, size_t n, F f)
+{
+    if (nthreads <= 1 || n < 2) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    auto body = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            f(i);
+        }
+    };
+    for (int t = 0; t < nthreads; t++) th.emplace_back(body);
+    for (auto &t : th) t.join();
+}
+
+// The whole decode of one batch.  `base` holds the streams at offsets[i]..offsets[i+1].
+int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams, int where)
+{
+    if (!ctx || !offsets || nstreams < 0 || (nstreams > 0 && !base)) return MP3B_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->have_batch = false;
+    ctx->infos.assign((size_t)nstreams, mp3b_stream_info{});
+    ctx->stats = mp3b_stats{};
+    ctx->nstreams = (uint32_t)nstreams;
+    ctx->nframes = ctx->ngran = ctx->nunits = ctx->ntiles = 0;
+    ctx->pcm_elems = 0;
+    int64_t launches = 0;
+    const uint64_t raw0 = nstreams ? offsets[0] : 0, raw_total = nstreams ? offsets[nstreams] - raw0 : 0;
+    for (int i = 0; i < nstreams; i++)
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xFFFFFF00ull) return MP3B_E_INVAL;
+    const bool host_index = ctx->opts.indexer == MP3B_INDEX_HOST;
+    if (host_index && where != MP3B_HOST) { ctx->err = "host indexer needs host-resident input"; return MP3B_E_INVAL; }
+
+    CK(cudaEventRecord(ctx->ev[EV_START], st));
+    // ---- raw bytes to the device
+    if (where == MP3B_HOST) {
+        CK(ctx->d_raw.ensure(raw_total + 64));
+        if (raw_total) CK(cudaMemcpyAsync(ctx->d_raw.p, base + raw0, raw_total, cudaMemcpyHostToDevice, st));
+        ctx->raw_dev = ctx->d_raw.as<uint8_t>();
+    } else
+        ctx->raw_dev = base + raw0;
+
+    // ---- stream records, frame count
+    CK(ctx->h_streams.ensure(sizeof(L3StreamRec) * (size_t)std::max(nstreams, 1)));
+    CK(ctx->d_streams.ensure(sizeof(L3StreamRec) * (size_t)std::max(nstreams, 1)));
+    L3StreamRec *hs = ctx->h_streams.as<L3StreamRec>();
+    for (int i = 0; i < nstreams; i++) {
+        memset(&hs[i], 0, sizeof hs[i]);
+        hs[i].raw_off = offsets[i] - raw0;
+        hs[i].raw_len = (uint32_t)(offsets[i + 1] - offsets[i]);
+    }
+    std::vector<std::vector<L3FrameRec>> host_frames;
+    if (host_index) {
+        host_frames.resize((size_t)nstreams);
+        parallel_for(nthreads_of(ctx), (size_t)nstreams, [&](size_t i) {
+            host_index_stream(base + offsets[i], &hs[i], &host_frames[i], (uint32_t)i);
+        });
+    } else if (nstreams) {
+        CK(cudaMemcpyAsync(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
+        l3_launch_index_count(ctx->raw_dev, ctx->d_streams.as<L3StreamRec>(), nstreams, st);
+        launches++;
+        CK(cudaMemcpyAsync(hs, ctx->d_streams.p, sizeof(L3StreamRec) * nstreams, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st)); // the one host round trip: sizes of everything downstream
+    }
+
+    // ---- prefix sums, per-stream info, synthesis tiles
+    const int G = l3_synth_tile_granules();
+    uint64_t frames = 0, grans = 0, units = 0, payload = 0, ntiles = 0;
+    for (int i = 0; i < nstreams; i++) {
+        L3StreamRec &r = hs[i];
+        mp3b_stream_info &inf = ctx->infos[(size_t)i];
+        r.frame_base = (uint32_t)frames;
+        r.gran_base = (uint32_t)grans;
+        r.unit_base = (uint32_t)units;
+        r.payload_base = payload;
+        inf.pcm_offset = (int64_t)(units * 576);
+        if (r.nframes) {
+            L3Hdr h;
+            l3_parse_hdr(r.first_hdr, &h);
+            inf.sample_rate = l3_sr_hz(h.sr_row);
+            inf.channels = h.nch;
+            inf.lsf = h.lsf;
+            inf.frames = r.nframes;
+            inf.samples = (int64_t)r.nframes * h.ngr * 576;
+            frames += r.nframes;
+            uint64_t g = (uint64_t)r.nframes * h.ngr;
+            ntiles += (g + G - 1) / G;
+            grans += g;
+            units += g * h.nch;
+            payload = align_up(payload + r.payload_len, 16);
+        }
+    }
+    if (units > L3G_UNIT_MASK || frames > 0xFFFFFFF0ull) { ctx->err = "batch too large"; return MP3B_E_INVAL; }
+    ctx->nframes = (uint32_t)frames;
+    ctx->ngran = (uint32_t)grans;
+    ctx->nunits = (uint32_t)units;
+    ctx->ntiles = (uint32_t)ntiles;
+    ctx->arena_bytes = align_up(payload + 32, 16);
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    ctx->pcm_elems = units * 576;
+
+    CK(ctx->h_tiles.ensure(sizeof(uint2) * std::max<uint64_t>(ntiles, 1)));
+    {
+        uint2 *t = ctx->h_tiles.as<uint2>();
+        uint64_t k = 0;
+        for (int i = 0; i < nstreams; i++) {
+            const L3StreamRec &r = hs[i];
+            if (!r.nframes) continue;
+            uint32_t g = r.nframes * (uint32_t)(ctx->infos[(size_t)i].lsf ? 1 : 2);
+            for (uint32_t a = 0; a < g; a += (uint32_t)G) t[k++] = make_uint2(r.gran_base + a, std::min<uint32_t>((uint32_t)G, g - a));
+        }
+    }
+
+    // ---- device buffers
+    CK(ctx->d_frames.ensure(sizeof(L3FrameRec) * std::max<uint64_t>(frames, 1)));
+    CK(ctx->d_units.ensure(sizeof(L3UnitDesc) * std::max<uint64_t>(units, 1)));
+    CK(ctx->d_gran.ensure(sizeof(uint32_t) * std::max<uint64_t>(grans, 1)));
+    CK(ctx->d_arena.ensure(ctx->arena_bytes));
+    CK(ctx->d_tiles.ensure(sizeof(uint2) * std::max<uint64_t>(ntiles, 1)));
+    CK(ctx->d_counter.ensure(64));
+    CK(ctx->h_counter.ensure(64));
+    CK(ctx->d_pcm.ensure(std::max<uint64_t>(ctx->pcm_elems * elem, 16)));
+    const bool keep = ctx->opts.keep_stages != 0;
+    const uint64_t wave = keep ? std::max<uint64_t>(units, 1) : std::min<uint64_t>(std::max<uint64_t>(units, 1), ctx->wave_units);
+    // a wave is a whole number of streams; size the intermediates for the largest wave
+    std::vector<std::pair<int, int>> waves; // [first stream, last stream)
+    uint64_t max_wave_units = 1;
+    {
+        int s0 = 0;
+        while (s0 < nstreams) {
+            int s1 = s0;
+            uint64_t u = 0;
+            while (s1 < nstreams) {
+                uint64_t us = (uint64_t)ctx->infos[(size_t)s1].samples / 576 * (uint64_t)std::max(ctx->infos[(size_t)s1].channels, 0);
+                if (s1 > s0 && u + us > wave) break;
+                u += us;
+                s1++;
+            }
+            waves.emplace_back(s0, s1);
+            max_wave_units = std::max(max_wave_units, u);
+            s0 = s1;
+        }
+    }
+    CK(ctx->d_is.ensure(max_wave_units * 576 * sizeof(int16_t)));
+    CK(ctx->d_sf.ensure(max_wave_units * 40));
+    CK(ctx->d_xr.ensure(max_wave_units * 576 * sizeof(float)));
+    CK(ctx->d_imd.ensure(max_wave_units * 1152 * sizeof(float)));
+    CK(ctx->d_sb.ensure(max_wave_units * 576 * sizeof(float)));
+
+    if (nstreams) CK(cudaMemcpyAsync(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
+    if (ntiles) CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->h_tiles.p, sizeof(uint2) * ntiles, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, st));
+    CK(cudaMemsetAsync(ctx->d_arena.as<uint8_t>() + (ctx->arena_bytes - 48), 0, 48, st));
+
+    // ---- frame table
+    L3StreamRec *ds = ctx->d_streams.as<L3StreamRec>();
+    L3FrameRec *df = ctx->d_frames.as<L3FrameRec>();
+    if (host_index) {
+        CK(ctx->h_frames.ensure(sizeof(L3FrameRec) * std::max<uint64_t>(frames, 1)));
+        L3FrameRec *hf = ctx->h_frames.as<L3FrameRec>();
+        parallel_for(nthreads_of(ctx), (size_t)nstreams, [&](size_t i) {
+            if (!host_frames[i].empty())
+                memcpy(hf + hs[i].frame_base, host_frames[i].data(), host_frames[i].size() * sizeof(L3FrameRec));
+        });
+        if (frames) CK(cudaMemcpyAsync(df, hf, sizeof(L3FrameRec) * frames, cudaMemcpyHostToDevice, st));
+    } else if (nstreams) {
+        l3_launch_index_fill(ctx->raw_dev, ds, df, nstreams, st);
+        launches++;
+    }
+    L3UnitDesc *du = ctx->d_units.as<L3UnitDesc>();
+    uint32_t *dg = ctx->d_gran.as<uint32_t>();
+    if (frames) {
+        l3_launch_side_parse(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), st);
+        l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
+        launches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[EV_INDEX], st));
+
+    // ---- decode waves
+    for (size_t w = 0; w < waves.size(); w++) {
+        const int s0 = waves[w].first, s1 = waves[w].second;
+        // unit / granule / tile ranges of the wave
+        uint32_t u_lo = hs[s0].unit_base, g_lo = hs[s0].gran_base;
+        uint32_t u_hi = s1 < nstreams ? hs[s1].unit_base : (uint32_t)units;
+        uint32_t g_hi = s1 < nstreams ? hs[s1].gran_base : (uint32_t)grans;
+        uint64_t t_lo = 0, t_hi = 0;
+        {
+            // tiles are laid out stream by stream in the same order
+            uint64_t k = 0;
+            for (int i = 0; i < s1; i++) {
+                if (i == s0) t_lo = k;
+                uint64_t g = (uint64_t)ctx->infos[(size_t)i].samples / 576;
+                k += (g + G - 1) / G;
+            }
+            if (s0 == s1) t_lo = k;
+            t_hi = k;
+        }
+        const uint32_t nu = u_hi - u_lo, ngw = g_hi - g_lo;
+        if (!nu) continue;
+        // wave-relative views of the intermediates (kernels index them by absolute unit id)
+        int16_t *is = ctx->d_is.as<int16_t>() - (size_t)u_lo * 576;
+        uint8_t *sf = ctx->d_sf.as<uint8_t>() - (size_t)u_lo * 40;
+        float *xr = ctx->d_xr.as<float>() - (size_t)u_lo * 576;
+        float *imd = ctx->d_imd.as<float>() - (size_t)u_lo * 1152;
+        float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
+        l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, ctx->T, is, sf, st);
+        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
+        l3_launch_requant_range(du, dg, g_lo, ngw, is, sf, ctx->T, xr, st);
+        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_REQ], st));
+        l3_launch_imdct_range(du, u_lo, nu, xr, imd, st);
+        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_IMDCT], st));
+        l3_launch_overlap_range(du, u_lo, nu, imd, sb, st);
+        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_OVL], st));
+        l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, ctx->d_pcm.p,
+                        ctx->opts.pcm_format, st);
+        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
+        launches += 5;
+    }
+    CK(cudaMemcpyAsync(ctx->h_counter.p, ctx->d_counter.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[EV_END], st));
+    CK(cudaGetLastError());
+
+    ctx->timed = waves.size() == 1;
+    ctx->stats.streams = nstreams;
+    ctx->stats.frames = (int64_t)frames;
+    ctx->stats.granules = (int64_t)grans;
+    ctx->stats.units = (int64_t)units;
+    ctx->stats.bytes_in = (int64_t)raw_total;
+    ctx->stats.pcm_bytes = (int64_t)(ctx->pcm_elems * elem);
+    ctx->stats.kernel_launches = launches;
+    ctx->have_batch = true;
+    return MP3B_OK;
+}
+
+} // namespace
+
+// ================================================================================ C-ABI
+extern "C" {
+
+int mp3b_abi_version(void) { return MP3B_ABI_VERSION; }
+
+int mp3b_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void mp3b_opts_default(mp3b_opts *o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->struct_size = sizeof *o;
+    o->pcm_format = MP3B_PCM_S16;
+    o->indexer = MP3B_INDEX_DEVICE;
+    o->pipeline = MP3B_PIPE_STAGED;
+}
+
+int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
+{
+    if (!out) return MP3B_E_INVAL;
+    *out = nullptr;
+    int n = mp3b_device_count();
+    if (n <= 0 || device < 0 || device >= n) return MP3B_E_CUDA; // no CPU fallback, by design
+    mp3b_ctx *ctx = new (std::nothrow) mp3b_ctx;
+    if (!ctx) return MP3B_E_NOMEM;
+    ctx->device = device;
+    mp3b_opts_default(&ctx->opts);
+    if (opts) {
+        size_t sz = std::min<size_t>(opts->struct_size, sizeof(mp3b_opts));
+        if (sz < 8) { delete ctx; return MP3B_E_INVAL; }
+        memcpy(&ctx->opts, opts, sz);
+        ctx->opts.struct_size = sizeof(mp3b_opts);
+    }
+    if (const char *w = getenv("MP3B_WAVE_UNITS")) {
+        long long v = atoll(w);
+        if (v > 0) ctx->wave_units = (uint64_t)v;
+    }
+    auto bail = [&](int rc) { mp3b_ctx_destroy(ctx); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
+    for (auto &e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(MP3B_E_CUDA);
+    int rc = upload_tables(ctx);
+    if (rc != MP3B_OK) return bail(rc);
+    *out = ctx;
+    return MP3B_OK;
+}
+
+void mp3b_ctx_destroy(mp3b_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto *s : ctx->open_streams) delete s;
+    for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw, &ctx->d_streams, &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_is, &ctx->d_sf, &ctx->d_xr,
+                      &ctx->d_imd, &ctx->d_sb})
+        b->release();
+    for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather})
+        b->release();
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *mp3b_strerror(int status)
+{
+    switch (status) {
+    case MP3B_OK: return "ok";
+    case MP3B_E_INVAL: return "invalid argument";
+    case MP3B_E_NOSYNC: return "no Layer III frame found";
+    case MP3B_E_TRUNCATED: return "destination buffer too small";
+    case MP3B_E_UNSUPPORTED: return "unsupported stream (Layer I/II, free format or MPEG-2.5)";
+    case MP3B_E_CUDA: return "CUDA error (no usable device, or a runtime failure)";
+    case MP3B_E_NOMEM: return "out of memory";
+    case MP3B_E_STATE: return "call order violated";
+    default: return "unknown status";
+    }
+}
+
+const char *mp3b_last_error(const mp3b_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+void *mp3b_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void mp3b_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int mp3b_decode_packed(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams, int where)
+{
+    return decode_impl(ctx, base, offsets, nstreams, where);
+}
+
+int mp3b_decode_batch(mp3b_ctx *ctx, const uint8_t *const *bufs, const size_t *lens, int nstreams)
+{
+    if (!ctx || nstreams < 0 || (nstreams > 0 && (!bufs || !lens))) return MP3B_E_INVAL;
+    ctx->gather_offsets.assign((size_t)nstreams + 1, 0);
+    uint64_t tot = 0;
+    for (int i = 0; i < nstreams; i++) {
+        if (lens[i] && !bufs[i]) return MP3B_E_INVAL;
+        ctx->gather_offsets[(size_t)i] = tot;
+        tot += lens[i];
+    }
+    ctx->gather_offsets[(size_t)nstreams] = tot;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream)); // the staging buffer may still feed a previous copy
+    CK(ctx->h_gather.ensure(tot + 64));
+    uint8_t *dst = ctx->h_gather.as<uint8_t>();
+    parallel_for(nthreads_of(ctx), (size_t)nstreams, [&](size_t i) {
+        if (lens[i]) memcpy(dst + ctx->gather_offsets[i], bufs[i], lens[i]);
+    });
+    return decode_impl(ctx, dst, ctx->gather_offsets.data(), nstreams, MP3B_HOST);
+}
+
+int mp3b_sync(mp3b_ctx *ctx)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->have_batch) {
+        ctx->stats.concealed_frames = *ctx->h_counter.as<uint32_t>();
+        auto ms = [&](int a, int b) {
+            float v = 0.f;
+            if (cudaEventElapsedTime(&v, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); v = 0.f; }
+            return v;
+        };
+        ctx->stats.ms_total = ms(EV_START, EV_END);
+        ctx->stats.ms_index = ms(EV_START, EV_INDEX);
+        if (ctx->timed && ctx->nunits) {
+            ctx->stats.ms_huffman = ms(EV_INDEX, EV_HUFF);
+            ctx->stats.ms_requant = ms(EV_HUFF, EV_REQ);
+            ctx->stats.ms_imdct = ms(EV_REQ, EV_IMDCT);
+            ctx->stats.ms_overlap = ms(EV_IMDCT, EV_OVL);
+            ctx->stats.ms_synth = ms(EV_OVL, EV_SYNTH);
+        }
+    }
+    return MP3B_OK;
+}
+
+int mp3b_batch_stream_info(const mp3b_ctx *ctx, int i, mp3b_stream_info *info)
+{
+    if (!ctx || !info) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    if (i < 0 || (size_t)i >= ctx->infos.size()) return MP3B_E_INVAL;
+    *info = ctx->infos[(size_t)i];
+    return info->frames ? MP3B_OK : MP3B_E_NOSYNC;
+}
+
+int mp3b_batch_pcm_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems)
+{
+    if (!ctx || !ptr || !nelems) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    *ptr = ctx->d_pcm.p;
+    *nelems = ctx->pcm_elems;
+    return MP3B_OK;
+}
+
+int mp3b_batch_fetch_pcm(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got)
+{
+    if (!ctx || (!dst && cap_elems)) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    if (cap_elems < ctx->pcm_elems) return MP3B_E_TRUNCATED;
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->pcm_elems)
+        CK(cudaMemcpyAsync(dst, ctx->d_pcm.p, ctx->pcm_elems * elem,
+                           where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (got) *got = ctx->pcm_elems;
+    return MP3B_OK;
+}
+
+int mp3b_get_stats(const mp3b_ctx *ctx, mp3b_stats *st)
+{
+    if (!ctx || !st) return MP3B_E_INVAL;
+    *st = ctx->stats;
+    return MP3B_OK;
+}
+
+// ---------------------------------------------------------------------------- stream interface
+int mp3b_stream_open(mp3b_ctx *ctx, mp3b_stream **out)
+{
+    if (!ctx || !out) return MP3B_E_INVAL;
+    mp3b_stream *s = new (std::nothrow) mp3b_stream;
+    if (!s) return MP3B_E_NOMEM;
+    s->ctx = ctx;
+    ctx->open_streams.push_back(s);
+    *out = s;
+    return MP3B_OK;
+}
+
+void mp3b_stream_close(mp3b_stream *s)
+{
+    if (!s) return;
+    auto &v = s->ctx->open_streams;
+    v.erase(std::remove(v.begin(), v.end(), s), v.end());
+    for (auto *o : v) o->batch_index = -1; // batch indices are positional: invalidate
+    delete s;
+}
+
+int mp3b_stream_enqueue(mp3b_stream *s, const uint8_t *bytes, size_t n)
+{
+    if (!s || (n && !bytes)) return MP3B_E_INVAL;
+    try {
+        s->pending.insert(s->pending.end(), bytes, bytes + n);
+    } catch (...) {
+        return MP3B_E_NOMEM;
+    }
+    return MP3B_OK;
+}
+
+int mp3b_decode(mp3b_ctx *ctx)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    std::vector<const uint8_t *> bufs;
+    std::vector<size_t> lens;
+    int k = 0;
+    for (auto *s : ctx->open_streams) {
+        bufs.push_back(s->pending.data());
+        lens.push_back(s->pending.size());
+        s->batch_index = k++;
+        s->cursor = 0;
+    }
+    return mp3b_decode_batch(ctx, bufs.data(), lens.data(), k);
+}
+
+int mp3b_stream_get_info(const mp3b_stream *s, mp3b_stream_info *info)
+{
+    if (!s || !info) return MP3B_E_INVAL;
+    if (s->batch_index < 0) return MP3B_E_STATE;
+    return mp3b_batch_stream_info(s->ctx, s->batch_index, info);
+}
+
+int mp3b_stream_pcm_device_ptr(const mp3b_stream *s, const void **ptr, size_t *nsamples)
+{
+    if (!s || !ptr || !nsamples) return MP3B_E_INVAL;
+    if (s->batch_index < 0 || !s->ctx->have_batch) return MP3B_E_STATE;
+    const mp3b_stream_info &inf = s->ctx->infos[(size_t)s->batch_index];
+    const int elem = s->ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    *ptr = s->ctx->d_pcm.as<uint8_t>() + (size_t)inf.pcm_offset * elem;
+    *nsamples = (size_t)inf.samples;
+    return MP3B_OK;
+}
+
+int mp3b_stream_fetch_pcm(mp3b_stream *s, void *dst, size_t cap_samples, int where, size_t *got)
+{
+    if (!s || (!dst && cap_samples)) return MP3B_E_INVAL;
+    mp3b_ctx *ctx = s->ctx;
+    if (s->batch_index < 0 || !ctx->have_batch) return MP3B_E_STATE;
+    const mp3b_stream_info &inf = ctx->infos[(size_t)s->batch_index];
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    size_t left = (size_t)inf.samples - std::min<size_t>(s->cursor, (size_t)inf.samples);
+    size_t n = std::min(left, cap_samples);
+    CK(cudaSetDevice(ctx->device));
+    if (n) {
+        const uint8_t *src = ctx->d_pcm.as<uint8_t>() + ((size_t)inf.pcm_offset + s->cursor * inf.channels) * elem;
+        CK(cudaMemcpyAsync(dst, src, n * inf.channels * elem,
+                           where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    s->cursor += n;
+    if (got) *got = n;
+    return MP3B_OK;
+}
+
+// ---------------------------------------------------------------------------- debug stages
+int mp3b_debug_stage(mp3b_ctx *ctx, int stage, void *dst, uint64_t cap_bytes, uint32_t *elem_size, uint64_t *count)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    const void *src = nullptr;
+    uint32_t es = 1;
+    uint64_t n = 0;
+    switch (stage) {
+    case MP3B_STAGE_FRAMES: src = ctx->d_frames.p; es = 16; n = ctx->nframes; break;
+    case MP3B_STAGE_UNITDESC: src = ctx->d_units.p; es = 32; n = ctx->nunits; break;
+    case MP3B_STAGE_MAINDATA: src = ctx->d_arena.p; es = 1; n = ctx->arena_bytes; break;
+    case MP3B_STAGE_IS: src = ctx->d_is.p; es = 2; n = (uint64_t)ctx->nunits * 576; break;
+    case MP3B_STAGE_SF: src = ctx->d_sf.p; es = 1; n = (uint64_t)ctx->nunits * 40; break;
+    case MP3B_STAGE_XR: src = ctx->d_xr.p; es = 4; n = (uint64_t)ctx->nunits * 576; break;
+    case MP3B_STAGE_SB: src = ctx->d_sb.p; es = 4; n = (uint64_t)ctx->nunits * 576; break;
+    default: return MP3B_E_INVAL;
+    }
+    if (stage >= MP3B_STAGE_IS && stage <= MP3B_STAGE_SB && !ctx->opts.keep_stages) {
+        ctx->err = "intermediates are only kept with opts.keep_stages = 1";
+        return MP3B_E_STATE;
+    }
+    if (elem_size) *elem_size = es;
+    if (count) *count = n;
+    if (!dst) return MP3B_OK;
+    if (cap_bytes < n * es) return MP3B_E_TRUNCATED;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n) CK(cudaMemcpy(dst, src, n * es, cudaMemcpyDeviceToHost));
+    return MP3B_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,163 @@
+// k_synth.cu -- K4: polyphase synthesis filterbank (a11).
+//
+// Per slot of 32 subband samples S[k] the standard computes V[i] = sum_k cos((16+i)(2k+1)pi/64) S[k]
+// (64x32), shifts V into a 1024-entry FIFO and forms 32 PCM samples as a 512-tap dot product with
+// the window D.  All 64 V values are signed copies of the 32-point transform
+//     C[n] = sum_k cos(n (2k+1) pi / 64) S[k],  n = 0..31
+// (V[i] = C[16+i] for i < 16, V[16] = 0, V[i] = -C[48-i] for 17 <= i <= 47, V[48] = -C[0],
+//  V[i] = -C[i-48] for i >= 49), so the matrixing is a batched [slots x 32] x [32 x 32] product and
+// the FIFO is never materialised: PCM of slot T is
+//     pcm[j] = sum_{l<16} W[l][j] * C_{T-l}[src_{l&1}[j]]
+// with the signs folded into the rearranged window W.  A tile (one stream, G granules, both
+// channels) keeps its C vectors in shared memory; the 15-slot history comes from the previous
+// granule's subband samples (re-transformed: a 10 % halo at G = 8), or is zero at stream start.
+// FP32 FMA throughout; lanes write interleaved (L, R) pairs so every store is a full 128-byte row.
+// Restates oracle/l3_oracle.c::synth_slot in float32.
+// No reference code exists for this stage (/root/reference/README.md:1-84).
+#include <math.h>
+
+#include "iso_tables.h"
+#include "kernels.h"
+#include "mp3b.h"
+
+namespace {
+
+constexpr int K4_G = 8;                 // granules per tile
+constexpr int K4_SLOTS = 15 + K4_G * 18; // with history
+constexpr int K4_THREADS = 256;
+
+__device__ float g_dct32[32][32];  // [k][n] = cos(n (2k+1) pi / 64)
+__device__ float g_synwin[16][32]; // W[l][j]
+
+__device__ __forceinline__ int16_t to_s16(float v)
+{
+    float s = rintf(v * 32768.f);
+    s = fminf(fmaxf(s, -32768.f), 32767.f);
+    return (int16_t)s;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(K4_THREADS)
+k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
+        const float *__restrict__ sb, void *__restrict__ pcm)
+{
+    extern __shared__ float s_c[]; // [nch][K4_SLOTS][32]
+    const uint32_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    const uint2 tl = tiles[tile];
+    const uint32_t g0 = tl.x, ng = tl.y & 0xffu;
+    const uint32_t gu0 = gran_unit0[g0];
+    const bool first = (gu0 & L3G_FIRST) != 0;
+    const int nch = (gu0 & L3G_STEREO) ? 2 : 1;
+    const uint32_t u0 = gu0 & L3G_UNIT_MASK;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = K4_THREADS / 32;
+    const int nslots = 15 + (int)ng * 18;
+
+    // ---- load subband samples: history (last 15 slots of the previous granule) + ng granules.
+    // units of this stream are contiguous: unit(g, c) = u0 + (g - g0) * nch + c
+    for (int c = 0; c < nch; c++) {
+        float *dst = s_c + c * (K4_SLOTS * 32);
+        for (int i = threadIdx.x; i < 15 * 32; i += K4_THREADS) {
+            float v = 0.f;
+            if (!first) v = sb[(size_t)(u0 - nch + c) * 576 + 3 * 32 + i];
+            dst[i] = v;
+        }
+        for (int i = threadIdx.x; i < (int)ng * 576; i += K4_THREADS) {
+            const int gi = i / 576, r = i % 576;
+            dst[15 * 32 + i] = sb[(size_t)(u0 + gi * nch + c) * 576 + r];
+        }
+    }
+    __syncthreads();
+
+    // ---- matrixing: C[n] = sum_k S[k] cos(n(2k+1)pi/64), in place, one (channel, slot) per warp step
+    {
+        float cn[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) cn[k] = g_dct32[k][lane];
+        for (int it = warp; it < nch * nslots; it += nwarps) {
+            float *row = s_c + (it / nslots) * (K4_SLOTS * 32) + (it % nslots) * 32;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; k++) acc = fmaf(row[k], cn[k], acc);
+            __syncwarp();
+            row[lane] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- windowing
+    {
+        float w[16];
+#pragma unroll
+        for (int l = 0; l < 16; l++) w[l] = g_synwin[l][lane];
+        const int src_e = lane <= 15 ? 16 + lane : (lane == 16 ? 0 : 48 - lane); // lane 16: weight is 0
+        const int src_o = lane <= 16 ? 16 - lane : lane - 16;
+        for (int t = warp; t < (int)ng * 18; t += nwarps) {
+            const int T = 15 + t;
+            float out[2] = {0.f, 0.f};
+            for (int c = 0; c < nch; c++) {
+                const float *base = s_c + c * (K4_SLOTS * 32) + T * 32;
+                float acc = 0.f;
+#pragma unroll
+                for (int l = 0; l < 16; l += 2) {
+                    acc = fmaf(w[l], base[-l * 32 + src_e], acc);
+                    acc = fmaf(w[l + 1], base[-(l + 1) * 32 + src_o], acc);
+                }
+                out[c] = acc;
+            }
+            // PCM element index of (granule gi, slot tt, sample lane, channel 0)
+            const int gi = t / 18, tt = t % 18;
+            const size_t e0 = (size_t)(u0 + gi * nch) * 576 + (size_t)(tt * 32 + lane) * nch;
+            if (FMT == MP3B_PCM_S16) {
+                int16_t *p = reinterpret_cast<int16_t *>(pcm);
+                if (nch == 2) {
+                    const uint32_t pk = (uint16_t)to_s16(out[0]) | ((uint32_t)(uint16_t)to_s16(out[1]) << 16);
+                    *reinterpret_cast<uint32_t *>(p + e0) = pk;
+                } else
+                    p[e0] = to_s16(out[0]);
+            } else {
+                float *p = reinterpret_cast<float *>(pcm);
+                if (nch == 2) *reinterpret_cast<float2 *>(p + e0) = make_float2(out[0], out[1]);
+                else p[e0] = out[0];
+            }
+        }
+    }
+}
+
+} // namespace
+
+int l3_synth_tile_granules(void) { return K4_G; }
+
+void l3_synth_init(void)
+{
+    static float dct[32][32], win[16][32];
+    for (int k = 0; k < 32; k++)
+        for (int n = 0; n < 32; n++) dct[k][n] = (float)cos(n * (2 * k + 1) * M_PI / 64.0);
+    for (int l = 0; l < 16; l++)
+        for (int j = 0; j < 32; j++) {
+            const int i = l >> 1;
+            double v;
+            if (!(l & 1)) v = l3_dwin(64 * i + j) * (j <= 15 ? 1.0 : (j == 16 ? 0.0 : -1.0));
+            else v = -l3_dwin(64 * i + 32 + j);
+            win[l][j] = (float)v;
+        }
+    cudaMemcpyToSymbol(g_dct32, dct, sizeof dct);
+    cudaMemcpyToSymbol(g_synwin, win, sizeof win);
+}
+
+void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const float *sb, void *pcm,
+                     int pcm_format, cudaStream_t st)
+{
+    if (!ntiles) return;
+    const size_t smem = (size_t)2 * K4_SLOTS * 32 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_synth<MP3B_PCM_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_synth<MP3B_PCM_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    if (pcm_format == MP3B_PCM_S16)
+        k_synth<MP3B_PCM_S16><<<ntiles, K4_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, sb, pcm);
+    else
+        k_synth<MP3B_PCM_F32><<<ntiles, K4_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, sb, pcm);
+}

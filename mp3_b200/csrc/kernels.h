@@ -1,0 +1,61 @@
+/* kernels.h -- launch wrappers of the CUDA kernels (one translation unit per stage). */
+#ifndef MP3B_KERNELS_H
+#define MP3B_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "l3_defs.h"
+#include "l3_tables.h"
+
+/* Device-resident tables (pointers into one allocation owned by the context). */
+struct L3DevTables {
+    const uint16_t *huff_lut;
+    uint32_t huff_lut_len;
+    const L3HuffInfo *huff;
+    const uint8_t *quad_a;
+    const L3BandTables *bands;
+    const float *pow43;
+    const uint16_t *sfb_long; /* [6][23] */
+};
+
+/* K0: device frame indexer (a1-a3) */
+void l3_launch_index_count(const uint8_t *raw, L3StreamRec *streams, int nstreams, cudaStream_t st);
+void l3_launch_index_fill(const uint8_t *raw, const L3StreamRec *streams, L3FrameRec *frames, int nstreams,
+                          cudaStream_t st);
+void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
+                          uint32_t nframes, const L3DevTables &T, L3UnitDesc *units, uint32_t *gran_unit0,
+                          uint32_t *concealed_counter, cudaStream_t st);
+void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
+                            uint32_t nframes, uint8_t *arena, cudaStream_t st);
+
+/* K1: scalefactor + Huffman / count1 decode (a4, a5) */
+/* arena_bytes: readable size of the main-data arena (a multiple of 4; reads beyond it return 0) */
+/* units [u_lo, u_lo + nunits); output arrays are indexed by absolute unit id */
+void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
+                             uint32_t nunits, const L3DevTables &T, int16_t *is_out, uint8_t *sf_out,
+                             cudaStream_t st);
+
+/* K2: requantise + stereo + reorder + alias reduction (a6-a8) */
+/* granules [g_lo, g_lo + ngranules) */
+void l3_launch_requant_range(const L3UnitDesc *units, const uint32_t *gran_unit0, uint32_t g_lo, uint32_t ngranules,
+                             const int16_t *is_in, const uint8_t *sf_in, const L3DevTables &T, float *xr_out,
+                             cudaStream_t st);
+
+/* K3a: IMDCT + window (a9); K3b: overlap-add + frequency inversion (a10) */
+void l3_requant_init(void);
+void l3_hybrid_init(void);
+void l3_launch_imdct_range(const L3UnitDesc *units, uint32_t u_lo, uint32_t nunits, const float *xr, float *imd,
+                           cudaStream_t st);
+void l3_launch_overlap_range(const L3UnitDesc *units, uint32_t u_lo, uint32_t nunits, const float *imd, float *sb,
+                             cudaStream_t st);
+
+/* K4: polyphase synthesis (a11) */
+void l3_synth_init(void);
+/* tiles[i] = {first global granule, number of granules (<= l3_synth_tile_granules())}; a tile
+ * never spans two streams */
+int l3_synth_tile_granules(void);
+void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const float *sb, void *pcm,
+                     int pcm_format, cudaStream_t st);
+
+#endif

@@ -1,0 +1,167 @@
+/* l3_defs.h -- record layouts and header arithmetic shared by the host indexer and the kernels.
+ *
+ * Stage ids (a1..a11) refer to SURVEY.md section 8(a).  The reference repository has no code for
+ * any of them (/root/reference/README.md:1-84); the behaviour implemented is ISO/IEC 11172-3 /
+ * 13818-3 as restated by oracle/l3_oracle.c.
+ */
+#ifndef MP3B_L3_DEFS_H
+#define MP3B_L3_DEFS_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define L3_HD __host__ __device__ __forceinline__
+#else
+#define L3_HD static inline
+#endif
+
+/* One MPEG audio frame found by the indexer (a1, a3). */
+typedef struct L3FrameRec {
+    uint32_t rel_off;     /* byte offset of the header inside its stream */
+    uint32_t payload_off; /* main-data bytes of this stream that precede this frame */
+    uint32_t hdr;         /* the four header bytes, big endian */
+    uint32_t stream;
+} L3FrameRec;
+
+/* One input stream of a batch. */
+typedef struct L3StreamRec {
+    uint64_t raw_off;      /* offset of the stream in the raw byte arena */
+    uint64_t payload_base; /* offset of its compacted main data in the main-data arena */
+    uint32_t raw_len;
+    uint32_t first_off;    /* offset of the first frame (after ID3v2 / junk) */
+    uint32_t first_hdr;    /* header of the first frame, 0 if none */
+    uint32_t nframes;
+    uint32_t payload_len;
+    uint32_t frame_base;   /* global index of its first frame */
+    uint32_t gran_base;    /* global index of its first granule */
+    uint32_t unit_base;    /* global index of its first unit (granule-channel) */
+} L3StreamRec;
+
+/* One granule-channel ("unit": 576 spectral lines), from the side info (a2, a3). 32 bytes. */
+typedef struct __attribute__((aligned(16))) L3UnitDesc {
+    uint64_t bit_off;     /* absolute bit offset of part2 in the main-data arena */
+    uint16_t p23len;      /* part2_3_length */
+    uint16_t big_values;  /* clamped to 288 */
+    uint16_t r1, r2;      /* region 1 / 2 start lines, clamped to 2*big_values */
+    uint16_t sfc;         /* scalefac_compress */
+    uint8_t global_gain;
+    uint8_t tsel[3];
+    uint8_t sbg[3];       /* subblock_gain */
+    uint8_t flags;        /* L3F_* */
+    uint8_t hdr;          /* L3H_* */
+    uint8_t pos;          /* L3P_* */
+    uint32_t stream;
+} L3UnitDesc;
+
+#define L3F_BT_MASK 0x03      /* block_type */
+#define L3F_MIXED 0x04
+#define L3F_PREFLAG 0x08      /* effective preflag (MPEG-1 bit, or LSF scalefac_compress >= 500) */
+#define L3F_SFSCALE 0x10
+#define L3F_C1TAB 0x20
+#define L3F_VALID 0x40        /* main data available (main_data_begin within the reservoir) */
+#define L3F_WS 0x80           /* window_switching_flag */
+
+#define L3H_LSF 0x01
+#define L3H_SR_SHIFT 1        /* bits 1..3: sample-rate row 0..5 */
+#define L3H_STEREO 0x10       /* two channels */
+#define L3H_MS 0x20           /* joint stereo with mode_ext MS bit */
+#define L3H_IS 0x40           /* joint stereo with mode_ext intensity bit */
+
+#define L3P_GR 0x01
+#define L3P_CH 0x02
+#define L3P_SCFSI_SHIFT 2     /* bits 2..5: scfsi[0..3], bit (2+k) = group k */
+#define L3P_FIRST 0x40        /* first granule of its stream: no overlap / synthesis history */
+
+/* gran_unit0[g]: unit index of channel 0 of global granule g, with flags in the top bits. */
+#define L3G_UNIT_MASK 0x3FFFFFFFu
+#define L3G_STEREO 0x40000000u
+#define L3G_FIRST 0x80000000u
+
+typedef struct L3Hdr {
+    int lsf, sr_row, nch, mode, mode_ext, crc, frame_len, side_len, ngr;
+} L3Hdr;
+
+L3_HD int l3_kbps(int lsf, int idx)
+{
+    /* kbit/s divided by 8, one byte per bitrate_index 1..14 */
+    const unsigned long long m1a = 0x0E0C0A0807060504ull; /* 4 5 6 7 8 10 12 14 */
+    const unsigned long long m2a = 0x0807060504030201ull; /* 1 .. 8 */
+    int i = idx - 1;
+    unsigned v;
+    if (!lsf) {
+        const unsigned long long hi = 0x000028201C181410ull; /* 16 20 24 28 32 40 */
+        v = i < 8 ? (unsigned)(m1a >> (8 * i)) & 0xff : (unsigned)(hi >> (8 * (i - 8))) & 0xff;
+    } else {
+        const unsigned long long hi = 0x00001412100E0C0Aull; /* 10 12 14 16 18 20 */
+        v = i < 8 ? (unsigned)(m2a >> (8 * i)) & 0xff : (unsigned)(hi >> (8 * (i - 8))) & 0xff;
+    }
+    return (int)v * 8;
+}
+
+L3_HD int l3_sr_hz(int row)
+{
+    return row == 0 ? 44100 : row == 1 ? 48000 : row == 2 ? 32000 : row == 3 ? 22050 : row == 4 ? 24000 : 16000;
+}
+
+/* a1: parse the 32 header bits (big-endian word).  Returns 0 if this is not a decodable
+ * MPEG-1 / MPEG-2 LSF Layer III header (free format and MPEG-2.5 are rejected). */
+L3_HD int l3_parse_hdr(uint32_t w, L3Hdr *h)
+{
+    if ((w & 0xFFE00000u) != 0xFFE00000u) return 0;
+    int ver = (w >> 19) & 3, layer = (w >> 17) & 3;
+    if (layer != 1 || (ver != 3 && ver != 2)) return 0;
+    int bri = (w >> 12) & 15, sri = (w >> 10) & 3;
+    if (bri == 0 || bri == 15 || sri == 3) return 0;
+    h->lsf = ver == 2;
+    h->crc = !((w >> 16) & 1);
+    h->mode = (w >> 6) & 3;
+    h->mode_ext = (w >> 4) & 3;
+    h->nch = h->mode == 3 ? 1 : 2;
+    h->sr_row = sri + (h->lsf ? 3 : 0);
+    h->ngr = h->lsf ? 1 : 2;
+    int pad = (w >> 9) & 1;
+    h->frame_len = (h->lsf ? 72000 : 144000) * l3_kbps(h->lsf, bri) / l3_sr_hz(h->sr_row) + pad;
+    h->side_len = h->lsf ? (h->nch == 1 ? 9 : 17) : (h->nch == 1 ? 17 : 32);
+    return 1;
+}
+
+/* Two headers belong to the same stream when version, sample rate and channel count agree. */
+L3_HD int l3_same_stream(uint32_t a, uint32_t b)
+{
+    /* version+layer bits 19..17, sample-rate bits 11..10; mono-ness = (mode == 3) */
+    if (((a ^ b) & 0x001E0C00u) != 0) return 0;
+    return (((a >> 6) & 3) == 3) == (((b >> 6) & 3) == 3);
+}
+
+/* Length of an ID3v2 tag at the start of a buffer, or 0. */
+L3_HD uint32_t l3_id3v2_len(const uint8_t *b, uint32_t len)
+{
+    if (len >= 10 && b[0] == 'I' && b[1] == 'D' && b[2] == '3' && !((b[6] | b[7] | b[8] | b[9]) & 0x80)) {
+        uint32_t n = ((uint32_t)b[6] << 21) | ((uint32_t)b[7] << 14) | ((uint32_t)b[8] << 7) | b[9];
+        n += 10 + ((b[5] & 0x10) ? 10 : 0);
+        if (n <= len) return n;
+    }
+    return 0;
+}
+
+L3_HD uint32_t l3_load_be32(const uint8_t *p)
+{
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+
+/* One step of the frame walk shared by the host and device indexers (the scan policy of
+ * oracle/l3_oracle.c: l3o_decode): at byte p, is there a frame of this stream that fits?
+ * `first` is the stream's first header (0 while none has been found). */
+L3_HD int l3_frame_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t first, L3Hdr *h, uint32_t *word)
+{
+    if (p + 4 > len) return 0;
+    uint32_t w = l3_load_be32(buf + p);
+    if (!l3_parse_hdr(w, h)) return 0;
+    if (first && !l3_same_stream(w, first)) return 0;
+    if (h->frame_len < 4 + (h->crc ? 2 : 0) + h->side_len) return 0;
+    if (p + (uint32_t)h->frame_len > len) return 0;
+    *word = w;
+    return 1;
+}
+
+#endif

@@ -1,0 +1,169 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the CPU
+oracle on the same generated streams.
+
+  * frame index, scalefactors and Huffman output: bit-exact
+  * requantised spectrum, subband samples: float32 vs the oracle's double, relative to the block scale
+  * PCM: ISO/IEC 11172-4 full accuracy (rms < 2^-15/sqrt(12), max |err| <= 2^-14, full scale 1.0);
+    s16 output: |diff| <= 1 LSB against round(oracle * 32768)
+"""
+import numpy as np
+import pytest
+
+import cases
+import l3util
+
+pytestmark = pytest.mark.gpu
+
+ALL = dict(cases.FF)
+ALL.update(cases.EXTRA)
+NAMES = sorted(ALL)
+
+
+@pytest.fixture(scope="module")
+def mp3b():
+    import mp3_b200
+    mp3_b200.load_library()
+    return mp3_b200
+
+
+@pytest.fixture(scope="module")
+def batch(mp3b, synth_mod, oracle_mod):
+    streams = [synth_mod.make_stream(**ALL[n]) for n in NAMES]
+    refs = [oracle_mod.decode(s, dumps=True) for s in streams]
+    return streams, refs
+
+
+@pytest.fixture(scope="module", params=["device_index", "host_index"])
+def decoded(request, mp3b, batch):
+    streams, refs = batch
+    idx = mp3b.INDEX_DEVICE if request.param == "device_index" else mp3b.INDEX_HOST
+    dec = mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, indexer=idx, pipeline=mp3b.PIPE_STAGED, keep_stages=True)
+    dec.decode_batch(streams)
+    out = dict(dec=dec, pcm=dec.fetch_pcm(), is_=dec.stage(mp3b.STAGE_IS), sf=dec.stage(mp3b.STAGE_SF),
+               xr=dec.stage(mp3b.STAGE_XR), sb=dec.stage(mp3b.STAGE_SB), frames=dec.stage(mp3b.STAGE_FRAMES))
+    yield out
+    dec.close()
+
+
+def _ubase(dec, i):
+    inf = dec.stream_info(i)
+    return inf, inf.pcm_offset // 576
+
+
+def test_stream_info_and_frame_table(decoded, batch):
+    streams, refs = batch
+    dec = decoded["dec"]
+    fbase = 0
+    for i, (s, r) in enumerate(zip(streams, refs)):
+        inf = dec.stream_info(i)
+        assert (inf.sample_rate, inf.channels, inf.frames, inf.samples) == (r.sample_rate, r.channels, r.frames, r.samples)
+        fr = decoded["frames"][fbase: fbase + r.frames]
+        py = l3util.split_frames(s)
+        offs = np.cumsum([0] + [len(f) for f in py[:-1]])
+        assert np.array_equal(fr[:, 0], offs.astype(np.uint32)), NAMES[i]
+        assert np.all(fr[:, 3] == i)
+        fbase += r.frames
+    assert dec.stats().concealed_frames == sum(r.concealed_frames for r in refs)
+
+
+@pytest.mark.parametrize("k", range(len(NAMES)))
+def test_huffman_and_scalefactors_bit_exact(k, decoded, batch):
+    _, refs = batch
+    inf, ub = _ubase(decoded["dec"], k)
+    r = refs[k]
+    assert np.array_equal(decoded["sf"][ub: ub + r.units], r.sf), NAMES[k]
+    assert np.array_equal(decoded["is_"][ub: ub + r.units], r.is_), NAMES[k]
+
+
+@pytest.mark.parametrize("k", range(len(NAMES)))
+def test_spectrum_and_subbands(k, decoded, batch):
+    _, refs = batch
+    inf, ub = _ubase(decoded["dec"], k)
+    r = refs[k]
+    for name, got, ref in (("xr", decoded["xr"][ub: ub + r.units], r.xr),
+                           ("sb", decoded["sb"][ub: ub + r.units].reshape(r.units, 576), r.sb.reshape(r.units, 576))):
+        scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-30)
+        err = np.abs(got.astype(np.float64) - ref) / scale
+        assert err.max() < 2e-5, (NAMES[k], name, err.max())
+
+
+@pytest.mark.parametrize("k", range(len(NAMES)))
+def test_pcm_iso_full_accuracy(k, decoded, batch):
+    _, refs = batch
+    dec = decoded["dec"]
+    got = dec.stream_pcm(k, decoded["pcm"]).astype(np.float64)
+    ref = refs[k].pcm.T
+    assert got.shape == ref.shape
+    if NAMES[k] == "loud_clipping":
+        # far above full scale: the absolute ISO bound is meaningless, check relative error instead
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+    else:
+        l3util.assert_iso_full_accuracy(got, ref, NAMES[k])
+
+
+def test_s16_output_rounding_and_saturation(mp3b, batch):
+    streams, refs = batch
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=mp3b.PIPE_STAGED) as dec:
+        dec.decode_batch(streams)
+        arena = dec.fetch_pcm()
+        clipped = 0
+        for k, r in enumerate(refs):
+            got = dec.stream_pcm(k, arena).astype(np.int64)
+            ref = np.clip(np.rint(r.pcm.T * 32768.0), -32768, 32767).astype(np.int64)
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= 1, NAMES[k]
+            clipped += int(np.count_nonzero(np.abs(got) >= 32767))
+        assert clipped > 0, "the loud case should exercise saturation"
+
+
+def test_stream_interface_matches_batch(mp3b, batch):
+    streams, refs = batch
+    pick = [0, 3, 9]
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=mp3b.PIPE_STAGED) as dec:
+        hs = [dec.open_stream() for _ in pick]
+        for h, k in zip(hs, pick):
+            s = streams[k]
+            h.enqueue(s[: len(s) // 3])
+            h.enqueue(s[len(s) // 3:])
+        dec.decode_streams()
+        for h, k in zip(hs, pick):
+            inf = h.info()
+            assert inf.samples == refs[k].samples
+            a = h.fetch(1000)
+            b = h.fetch(inf.samples)
+            got = np.concatenate([a, b]).astype(np.float64)
+            assert got.shape[0] == inf.samples
+            assert h.fetch(10).shape[0] == 0
+            l3util.assert_iso_full_accuracy(got, refs[k].pcm.T, NAMES[k])
+        for h in hs:
+            h.close()
+
+
+def test_garbage_id3_and_truncation(mp3b, synth_mod, oracle_mod):
+    s = synth_mod.make_stream(nframes=10, seed=77, blocks=1)
+    id3 = b"ID3\x03\x00\x00" + bytes([0, 0, 1, 10]) + bytes(138)
+    variants = [id3 + s, b"\x00\xff\x12junk" * 7 + s, s[:-100], s[5:], b"", b"\xff" * 50, s[: 4], s + s[:300]]
+    refs = [oracle_mod.decode(v) for v in variants]
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=mp3b.PIPE_STAGED) as dec:
+        for idx in (mp3b.INDEX_DEVICE,):
+            dec.decode_batch(variants)
+            arena = dec.fetch_pcm()
+            for k, r in enumerate(refs):
+                inf = dec.stream_info(k)
+                assert inf.frames == r.frames, k
+                if r.frames:
+                    got = dec.stream_pcm(k, arena).astype(np.float64)
+                    l3util.assert_iso_full_accuracy(got, r.pcm.T, "variant %d" % k)
+            assert dec.stats().concealed_frames == sum(r.concealed_frames for r in refs)
+
+
+def test_waves_give_identical_pcm(mp3b, batch, monkeypatch):
+    streams, _ = batch
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=mp3b.PIPE_STAGED) as dec:
+        dec.decode_batch(streams)
+        one = dec.fetch_pcm().copy()
+    monkeypatch.setenv("MP3B_WAVE_UNITS", "150")
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=mp3b.PIPE_STAGED) as dec:
+        dec.decode_batch(streams)
+        many = dec.fetch_pcm().copy()
+    assert np.array_equal(one, many)
