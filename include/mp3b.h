@@ -95,6 +95,10 @@ int mp3b_device_count(void);
 void mp3b_opts_default(mp3b_opts *o);
 int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out);
 void mp3b_ctx_destroy(mp3b_ctx *ctx);
+/* Run all work of the context on the caller's CUDA stream (a cudaStream_t passed as void*), so that
+ * the caller's events / graphs / other kernels order with the decode.  NULL restores the
+ * context's own stream.  The caller keeps ownership of the stream. */
+int mp3b_ctx_set_stream(mp3b_ctx *ctx, void *cuda_stream);
 const char *mp3b_strerror(int status);
 const char *mp3b_last_error(const mp3b_ctx *ctx);
 

@@ -53,7 +53,7 @@ class Stats(ctypes.Structure):
 
 EXPORTS = [
     "mp3b_abi_version", "mp3b_device_count", "mp3b_opts_default", "mp3b_ctx_create", "mp3b_ctx_destroy",
-    "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
+    "mp3b_ctx_set_stream", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
     "mp3b_decode_packed", "mp3b_sync", "mp3b_batch_stream_info", "mp3b_batch_pcm_device_ptr",
     "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
@@ -81,6 +81,7 @@ def load_library():
     L.mp3b_host_free.argtypes = [vp]
     L.mp3b_ctx_create.argtypes = [i32, ctypes.POINTER(Opts), ctypes.POINTER(vp)]
     L.mp3b_ctx_destroy.argtypes = [vp]
+    L.mp3b_ctx_set_stream.argtypes = [vp, vp]
     L.mp3b_opts_default.argtypes = [ctypes.POINTER(Opts)]
     L.mp3b_decode_batch.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), i32]
     L.mp3b_decode_packed.argtypes = [vp, vp, ctypes.POINTER(u64), i32, i32]
@@ -190,6 +191,10 @@ class Decoder:
         if self.ctx:
             self.L.mp3b_ctx_destroy(self.ctx)
             self.ctx = None
+
+    def set_stream(self, cuda_stream_handle):
+        """Enqueue on the caller's CUDA stream (an integer cudaStream_t, e.g. torch's .cuda_stream)."""
+        self._ck(self.L.mp3b_ctx_set_stream(self.ctx, ctypes.c_void_p(cuda_stream_handle)))
 
     def __enter__(self):
         return self

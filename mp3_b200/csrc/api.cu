@@ -85,7 +85,8 @@ struct mp3b_stream {
 struct mp3b_ctx {
     int device = 0;
     mp3b_opts opts{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // the stream work is enqueued on
+    cudaStream_t own_stream = nullptr; // created by the context
     cudaEvent_t ev[EV_COUNT]{};
     std::string err;
 
@@ -104,6 +105,7 @@ struct mp3b_ctx {
     uint64_t arena_bytes = 0;
     uint32_t nstreams = 0, nframes = 0, ngran = 0, nunits = 0, ntiles = 0;
     uint64_t wave_units = 2u << 20;
+    uint32_t tile_override = 0; // MP3B_FUSED_TILE: granules per fused tile (tests)
     bool have_batch = false, timed = false;
     mp3b_stats stats{};
     std::vector<mp3b_stream *> open_streams;
@@ -162,6 +164,7 @@ int upload_tables(mp3b_ctx *ctx)
     l3_requant_init();
     l3_hybrid_init();
     l3_synth_init();
+    l3_fused_init();
     CK(cudaGetLastError());
     return MP3B_OK;
 }
@@ -304,16 +307,39 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
     ctx->pcm_elems = units * 576;
 
-    CK(ctx->h_tiles.ensure(sizeof(uint2) * std::max<uint64_t>(ntiles, 1)));
+    const bool fused = ctx->opts.pipeline == MP3B_PIPE_FUSED;
+    // fused back end: tile length chosen so that the grid has a few CTAs per SM-resident slot
+    uint32_t GF = 8;
+    if (fused) {
+        uint64_t want = grans / 1776; // 148 SMs x 3 resident CTAs x 4 waves
+        GF = (uint32_t)std::min<uint64_t>(128, std::max<uint64_t>(8, want / 4 * 4));
+        if (ctx->tile_override) GF = ctx->tile_override;
+        ntiles = 0;
+        for (int i = 0; i < nstreams; i++) {
+            uint64_t g = (uint64_t)ctx->infos[(size_t)i].samples / 576;
+            ntiles += (g + GF - 1) / GF;
+        }
+        ctx->ntiles = (uint32_t)ntiles;
+    }
+    CK(ctx->h_tiles.ensure(sizeof(uint4) * std::max<uint64_t>(ntiles, 1)));
+    std::vector<uint64_t> tile_start((size_t)nstreams + 1, 0); // first tile of each stream
     {
-        uint2 *t = ctx->h_tiles.as<uint2>();
+        uint2 *t2 = ctx->h_tiles.as<uint2>();
+        uint4 *t4 = ctx->h_tiles.as<uint4>();
         uint64_t k = 0;
         for (int i = 0; i < nstreams; i++) {
             const L3StreamRec &r = hs[i];
+            tile_start[(size_t)i] = k;
             if (!r.nframes) continue;
             uint32_t g = r.nframes * (uint32_t)(ctx->infos[(size_t)i].lsf ? 1 : 2);
-            for (uint32_t a = 0; a < g; a += (uint32_t)G) t[k++] = make_uint2(r.gran_base + a, std::min<uint32_t>((uint32_t)G, g - a));
+            if (fused)
+                for (uint32_t a = 0; a < g; a += GF)
+                    t4[k++] = make_uint4(r.gran_base + a, std::min<uint32_t>(GF, g - a), std::min<uint32_t>(2u, a), 0u);
+            else
+                for (uint32_t a = 0; a < g; a += (uint32_t)G)
+                    t2[k++] = make_uint2(r.gran_base + a, std::min<uint32_t>((uint32_t)G, g - a));
         }
+        tile_start[(size_t)nstreams] = k;
     }
 
     // ---- device buffers
@@ -321,7 +347,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(ctx->d_units.ensure(sizeof(L3UnitDesc) * std::max<uint64_t>(units, 1)));
     CK(ctx->d_gran.ensure(sizeof(uint32_t) * std::max<uint64_t>(grans, 1)));
     CK(ctx->d_arena.ensure(ctx->arena_bytes));
-    CK(ctx->d_tiles.ensure(sizeof(uint2) * std::max<uint64_t>(ntiles, 1)));
+    CK(ctx->d_tiles.ensure(sizeof(uint4) * std::max<uint64_t>(ntiles, 1)));
     CK(ctx->d_counter.ensure(64));
     CK(ctx->h_counter.ensure(64));
     CK(ctx->d_pcm.ensure(std::max<uint64_t>(ctx->pcm_elems * elem, 16)));
@@ -348,12 +374,16 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     }
     CK(ctx->d_is.ensure(max_wave_units * 576 * sizeof(int16_t)));
     CK(ctx->d_sf.ensure(max_wave_units * 40));
-    CK(ctx->d_xr.ensure(max_wave_units * 576 * sizeof(float)));
-    CK(ctx->d_imd.ensure(max_wave_units * 1152 * sizeof(float)));
-    CK(ctx->d_sb.ensure(max_wave_units * 576 * sizeof(float)));
+    if (!fused) {
+        CK(ctx->d_xr.ensure(max_wave_units * 576 * sizeof(float)));
+        CK(ctx->d_imd.ensure(max_wave_units * 1152 * sizeof(float)));
+        CK(ctx->d_sb.ensure(max_wave_units * 576 * sizeof(float)));
+    }
 
     if (nstreams) CK(cudaMemcpyAsync(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
-    if (ntiles) CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->h_tiles.p, sizeof(uint2) * ntiles, cudaMemcpyHostToDevice, st));
+    if (ntiles)
+        CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->h_tiles.p, (fused ? sizeof(uint4) : sizeof(uint2)) * ntiles,
+                           cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, st));
     CK(cudaMemsetAsync(ctx->d_arena.as<uint8_t>() + (ctx->arena_bytes - 48), 0, 48, st));
 
@@ -388,18 +418,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         uint32_t u_lo = hs[s0].unit_base, g_lo = hs[s0].gran_base;
         uint32_t u_hi = s1 < nstreams ? hs[s1].unit_base : (uint32_t)units;
         uint32_t g_hi = s1 < nstreams ? hs[s1].gran_base : (uint32_t)grans;
-        uint64_t t_lo = 0, t_hi = 0;
-        {
-            // tiles are laid out stream by stream in the same order
-            uint64_t k = 0;
-            for (int i = 0; i < s1; i++) {
-                if (i == s0) t_lo = k;
-                uint64_t g = (uint64_t)ctx->infos[(size_t)i].samples / 576;
-                k += (g + G - 1) / G;
-            }
-            if (s0 == s1) t_lo = k;
-            t_hi = k;
-        }
+        const uint64_t t_lo = tile_start[(size_t)s0], t_hi = tile_start[(size_t)s1];
         const uint32_t nu = u_hi - u_lo, ngw = g_hi - g_lo;
         if (!nu) continue;
         // wave-relative views of the intermediates (kernels index them by absolute unit id)
@@ -410,6 +429,13 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
         l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, ctx->T, is, sf, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
+        if (fused) {
+            l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, ctx->T,
+                              ctx->d_pcm.p, ctx->opts.pcm_format, st);
+            if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
+            launches += 2;
+            continue;
+        }
         l3_launch_requant_range(du, dg, g_lo, ngw, is, sf, ctx->T, xr, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_REQ], st));
         l3_launch_imdct_range(du, u_lo, nu, xr, imd, st);
@@ -458,7 +484,7 @@ void mp3b_opts_default(mp3b_opts *o)
     o->struct_size = sizeof *o;
     o->pcm_format = MP3B_PCM_S16;
     o->indexer = MP3B_INDEX_DEVICE;
-    o->pipeline = MP3B_PIPE_STAGED;
+    o->pipeline = MP3B_PIPE_FUSED;
 }
 
 int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
@@ -481,9 +507,14 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
         long long v = atoll(w);
         if (v > 0) ctx->wave_units = (uint64_t)v;
     }
+    if (const char *w = getenv("MP3B_FUSED_TILE")) {
+        int v = atoi(w);
+        if (v > 0 && v <= 4096) ctx->tile_override = (uint32_t)v;
+    }
     auto bail = [&](int rc) { mp3b_ctx_destroy(ctx); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(MP3B_E_CUDA);
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
+    ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return bail(MP3B_E_CUDA);
     int rc = upload_tables(ctx);
@@ -506,8 +537,17 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
         b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+}
+
+int mp3b_ctx_set_stream(mp3b_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return MP3B_OK;
 }
 
 const char *mp3b_strerror(int status)
@@ -579,7 +619,10 @@ int mp3b_sync(mp3b_ctx *ctx)
         };
         ctx->stats.ms_total = ms(EV_START, EV_END);
         ctx->stats.ms_index = ms(EV_START, EV_INDEX);
-        if (ctx->timed && ctx->nunits) {
+        if (ctx->timed && ctx->nunits && ctx->opts.pipeline == MP3B_PIPE_FUSED) {
+            ctx->stats.ms_huffman = ms(EV_INDEX, EV_HUFF);
+            ctx->stats.ms_fused = ms(EV_HUFF, EV_SYNTH);
+        } else if (ctx->timed && ctx->nunits) {
             ctx->stats.ms_huffman = ms(EV_INDEX, EV_HUFF);
             ctx->stats.ms_requant = ms(EV_HUFF, EV_REQ);
             ctx->stats.ms_imdct = ms(EV_REQ, EV_IMDCT);

@@ -58,4 +58,11 @@ int l3_synth_tile_granules(void);
 void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const float *sb, void *pcm,
                      int pcm_format, cudaStream_t st);
 
+/* KF: fused back end (a6-a11).  tiles[i] = {first granule to output, granules to output,
+ * warm-up granules before it (0..2) that re-derive the overlap / synthesis state, 0}. */
+void l3_fused_init(void);
+void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const L3UnitDesc *units,
+                       const int16_t *is_in, const uint8_t *sf_in, const L3DevTables &T, void *pcm, int pcm_format,
+                       cudaStream_t st);
+
 #endif

@@ -121,8 +121,10 @@ def make_workload(name, nstreams=None, nframes=None, seed=20261018, distinct=Non
 
     `distinct` bounds the number of distinct streams generated (the rest repeat cyclically); the
     bench says so in its `config` when it uses this to bound host-side generation time."""
+    from concurrent.futures import ThreadPoolExecutor
     cfgs = workload_cfgs(name, nstreams, nframes, seed)
-    if distinct is None or distinct >= len(cfgs):
-        return [make_stream(**c) for c in cfgs]
-    base = [make_stream(**c) for c in cfgs[:distinct]]
-    return [base[i % distinct] for i in range(len(cfgs))]
+    _load()
+    nd = len(cfgs) if distinct is None else min(distinct, len(cfgs))
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:  # the C call releases the GIL
+        base = list(ex.map(lambda c: make_stream(**c), cfgs[:nd]))
+    return [base[i % nd] for i in range(len(cfgs))]

@@ -101,9 +101,43 @@ def test_pcm_iso_full_accuracy(k, decoded, batch):
         l3util.assert_iso_full_accuracy(got, ref, NAMES[k])
 
 
-def test_s16_output_rounding_and_saturation(mp3b, batch):
+@pytest.mark.parametrize("tile", [0, 1, 3, 5, 16])
+def test_fused_pipeline_pcm(tile, mp3b, batch, monkeypatch):
+    """The fused back end (default pipeline) against the oracle, for several tile lengths: tile
+    boundaries re-derive the overlap / synthesis state from two warm-up granules."""
     streams, refs = batch
-    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=mp3b.PIPE_STAGED) as dec:
+    if tile:
+        monkeypatch.setenv("MP3B_FUSED_TILE", str(tile))
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=mp3b.PIPE_FUSED) as dec:
+        dec.decode_batch(streams)
+        arena = dec.fetch_pcm()
+        assert dec.stats().kernel_launches == 6
+        for k, r in enumerate(refs):
+            got = dec.stream_pcm(k, arena).astype(np.float64)
+            ref = r.pcm.T
+            assert got.shape == ref.shape
+            if NAMES[k] == "loud_clipping":
+                assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+            else:
+                l3util.assert_iso_full_accuracy(got, ref, "%s tile=%d" % (NAMES[k], tile))
+
+
+def test_fused_equals_staged_s16(mp3b, batch):
+    streams, _ = batch
+    out = []
+    for pipe in (mp3b.PIPE_STAGED, mp3b.PIPE_FUSED):
+        with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=pipe) as dec:
+            dec.decode_batch(streams)
+            out.append(dec.fetch_pcm().astype(np.int32))
+    assert out[0].shape == out[1].shape
+    assert np.abs(out[0] - out[1]).max() <= 1
+
+
+@pytest.mark.parametrize("pipe", ["staged", "fused"])
+def test_s16_output_rounding_and_saturation(pipe, mp3b, batch):
+    streams, refs = batch
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16,
+                      pipeline=mp3b.PIPE_STAGED if pipe == "staged" else mp3b.PIPE_FUSED) as dec:
         dec.decode_batch(streams)
         arena = dec.fetch_pcm()
         clipped = 0
@@ -119,7 +153,7 @@ def test_s16_output_rounding_and_saturation(mp3b, batch):
 def test_stream_interface_matches_batch(mp3b, batch):
     streams, refs = batch
     pick = [0, 3, 9]
-    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=mp3b.PIPE_STAGED) as dec:
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
         hs = [dec.open_stream() for _ in pick]
         for h, k in zip(hs, pick):
             s = streams[k]
@@ -144,7 +178,7 @@ def test_garbage_id3_and_truncation(mp3b, synth_mod, oracle_mod):
     id3 = b"ID3\x03\x00\x00" + bytes([0, 0, 1, 10]) + bytes(138)
     variants = [id3 + s, b"\x00\xff\x12junk" * 7 + s, s[:-100], s[5:], b"", b"\xff" * 50, s[: 4], s + s[:300]]
     refs = [oracle_mod.decode(v) for v in variants]
-    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=mp3b.PIPE_STAGED) as dec:
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
         for idx in (mp3b.INDEX_DEVICE,):
             dec.decode_batch(variants)
             arena = dec.fetch_pcm()
@@ -157,13 +191,15 @@ def test_garbage_id3_and_truncation(mp3b, synth_mod, oracle_mod):
             assert dec.stats().concealed_frames == sum(r.concealed_frames for r in refs)
 
 
-def test_waves_give_identical_pcm(mp3b, batch, monkeypatch):
+@pytest.mark.parametrize("pipe", ["staged", "fused"])
+def test_waves_give_identical_pcm(pipe, mp3b, batch, monkeypatch):
     streams, _ = batch
-    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=mp3b.PIPE_STAGED) as dec:
+    pl = mp3b.PIPE_STAGED if pipe == "staged" else mp3b.PIPE_FUSED
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=pl) as dec:
         dec.decode_batch(streams)
         one = dec.fetch_pcm().copy()
     monkeypatch.setenv("MP3B_WAVE_UNITS", "150")
-    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=mp3b.PIPE_STAGED) as dec:
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, pipeline=pl) as dec:
         dec.decode_batch(streams)
         many = dec.fetch_pcm().copy()
     assert np.array_equal(one, many)
