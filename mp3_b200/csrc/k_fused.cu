@@ -11,19 +11,25 @@
 // the last 15 transformed slots (the synthesis FIR reaches 15 slots back).  A tile that does not
 // start at the head of its stream first re-derives that state from the two preceding granules
 // (warm-up: decoded, not output), so tiles are independent and a long stream is time-parallel.
-//   S1  4 groups of 64 threads, one granule each: gains, requantise, intensity/MS decisions,
-//       reorder, alias butterflies                                  -> X  (padded rows of 19)
-//   S2  8 warps = 4 granules x 2 channels, lane = subband: 36-point IMDCT by its two symmetries
-//       (324 FMA, coefficients as constant-bank operands), window, frequency inversion
-//                                                                   -> F (first halves), H (second)
-//   S3  warp per (channel, slot), lane = output index n: S = F + H(previous granule);
-//       C[n] = sum_k S[k] cos(n(2k+1)pi/64) in place (the 64 "V" values are signed copies of C)
-//   S4  warp per slot, lane = sample j, both channels: 16-tap dot product with the rearranged
-//       window; (L, R) pairs stored interleaved, one full 128-byte row per store
+//   S1  all threads, one (granule, line) pair each: per-band gains, requantise both channels,
+//       MS / intensity stereo, short-block reorder                  -> X  (padded rows of 19)
+//       (intensity decisions need the right channel's zero bands first: a short pre-pass)
+//   S2  8 warps = 4 granules x 2 channels, lane = subband: alias butterflies by shuffle, 36-point
+//       IMDCT by its two symmetries (324 FFMA with immediate coefficients), window, frequency
+//       inversion                                                   -> F (first halves), H (second)
+//   S3  warp per (channel, slot): S = F + H(previous granule), one even/odd butterfly by shuffle
+//       (u = S[k] + S[31-k], v = S[k] - S[31-k]), then lane n: C[n] = sum_{k<16} (n even ? u : v)[k]
+//       cos(n(2k+1)pi/64) in place (the 64 "V" values of the standard are signed copies of C)
+//   S4  warp per (granule, channel), lane = sample j: the 16-tap window as a fully unrolled sliding
+//       accumulation over the 33 rows a granule touches (2 LDS per row instead of 16 per output);
+//       PCM is staged in shared memory and leaves the CTA as 16-byte stores
 // Results must equal the staged pipeline's (tests/test_gpu_parity.py runs both).
 // No reference code exists for these stages (/root/reference/README.md:1-84).
 #include <math.h>
 
+#include <type_traits>
+
+#include "consts_gen.h"
 #include "iso_tables.h"
 #include "kernels.h"
 #include "mp3b.h"
@@ -35,167 +41,229 @@ constexpr int KF_THREADS = 256;
 constexpr int KF_ROWS = 15 + KF_B * 18;
 constexpr int XROW = 19;        // padded subband row of X
 constexpr int XSZ = 32 * XROW;  // 608 floats per channel spectrum
+constexpr int KF_POW_LUT = 1024;
 
 __constant__ float f_pow2q[4];
 __constant__ float f_is_kl[7], f_is_kr[7];
 __constant__ float f_lsf_pow[2][16];
 __constant__ float f_cs[8], f_ca[8];
 __constant__ uint8_t f_pretab[22];
-__constant__ float f_cosA[9][18], f_cosB[9][18], f_cos12[12][6], f_win[4][36];
-__device__ float f_dct32[32][32];  // [k][n]
+__constant__ float f_win[4][36];
+__device__ float f_dct32[16][32];  // [k][n], k < 16
 __device__ float f_synwin[16][32];
 
-struct GroupScratch {
-    float gain[2][40];
-    float kl[40], kr[40];
-    int nz[40];
-    uint8_t mode[40];
+struct GranMeta {
+    L3UnitDesc d[2];
+    int row, lay[2];
+    int joint;      // 0 = independent channels, 1 = MS and/or intensity processing applies
+    int ms, ist;
 };
 
 struct FusedShared {
-    float X[KF_B][2][XSZ];          // spectra of the batch, padded rows
+    float X[KF_B][2][XSZ];          // spectra of the batch, padded rows; reused as PCM staging in S4
     float F[2][KF_ROWS][32];        // rows 0..14: C history; rows 15..: first IMDCT halves -> S -> C
     float H[2][KF_B + 1][18][32];   // second IMDCT halves; [0] = last granule of the previous batch
-    GroupScratch gs[KF_B];
+    float pow43[KF_POW_LUT];        // |is|^(4/3) for the common small values
+    float gain[KF_B][2][40];
+    float kl[KF_B][40], kr[KF_B][40];
+    int nz[KF_B][40];               // right-channel band has a non-zero line (intensity bound)
+    uint8_t mode[KF_B][40];         // 1 = intensity-coded band
+    GranMeta gm[KF_B];
+    int any_ist;
+    // next batch's Huffman output and scalefactors, fetched with cp.async while this batch computes
+    __align__(16) int16_t is_buf[KF_B * 2][576];
+    __align__(16) uint8_t sf_buf[KF_B * 2][40];
 };
 
-__device__ __forceinline__ int xpad(int i) { return i + i / 18; }
-
-__device__ __forceinline__ void group_sync(int group)
-{
-    asm volatile("bar.sync %0, 64;" ::"r"(group + 1));
-}
+__device__ __forceinline__ int xpad(int i) { return i + ((i * 3641) >> 16); } // i + i / 18 for i < 608
 
 __device__ __forceinline__ int16_t to_s16(float v)
 {
-    float s = rintf(v * 32768.f);
-    s = fminf(fmaxf(s, -32768.f), 32767.f);
-    return (int16_t)s;
+    int r;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r) : "f"(v * 32768.f));
+    return (int16_t)r;
 }
 
-// ---- S1: one granule, executed by one 64-thread group -------------------------------------------
-__device__ __forceinline__ void stage_requant(FusedShared &S, int grp, int t64, uint32_t u0, int nch,
-                                              const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in,
-                                              const uint8_t *__restrict__ sf_in, const L3BandTables *__restrict__ bands,
-                                              const float *__restrict__ pow43, float *tmp /* [2][576] scratch */)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
-    GroupScratch &G = S.gs[grp];
-    const L3UnitDesc d0 = units[u0], d1 = units[u0 + (nch - 1)];
-    const int row = (d0.hdr >> L3H_SR_SHIFT) & 7;
-    const int lay0 = (d0.flags & L3F_BT_MASK) == 2 ? ((d0.flags & L3F_MIXED) ? 2 : 1) : 0;
-    const int lay1 = (d1.flags & L3F_BT_MASK) == 2 ? ((d1.flags & L3F_MIXED) ? 2 : 1) : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-    for (int t = t64; t < 80; t += 64) {
-        const int c = t / 40, b = t % 40;
-        if (c < nch) {
-            const L3UnitDesc &dd = c ? d1 : d0;
-            const int lay = c ? lay1 : lay0;
-            float gn = 0.f;
-            if (b < bands->nbands[row][lay]) {
-                const int s = sf_in[(size_t)(u0 + c) * 40 + b] & 0x7f;
-                const int win = bands->win[row][lay][b];
-                const int sh = (dd.flags & L3F_SFSCALE) ? 4 : 2;
-                int q = (int)dd.global_gain - 210;
-                if (win < 0) q -= sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[bands->sfb[row][lay][b]] : 0));
-                else q -= 8 * dd.sbg[win] + sh * s;
-                gn = ldexpf(f_pow2q[q & 3], q >> 2);
-            }
-            G.gain[c][b] = gn;
-        }
+// Start fetching the Huffman output (1152 B / unit) and scalefactors (40 B / unit) of `n` consecutive
+// units into shared memory; the caller waits (cp_async_wait_all + barrier) before reading them.
+__device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t u_first, int n,
+                                               const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in)
+{
+    const char *gi = reinterpret_cast<const char *>(is_in + (size_t)u_first * 576);
+    char *si = reinterpret_cast<char *>(&S.is_buf[0][0]);
+    for (int i = tid; i < n * 72; i += KF_THREADS) cp_async16(si + i * 16, gi + i * 16);
+    const char *gs = reinterpret_cast<const char *>(sf_in + (size_t)u_first * 40);
+    char *ss = reinterpret_cast<char *>(&S.sf_buf[0][0]);
+    for (int i = tid; i < n * 5; i += KF_THREADS) cp_async8(ss + i * 8, gs + i * 8);
+    cp_async_commit();
+}
+
+// ---- per-batch metadata (descriptors, layouts), loaded one batch ahead ---------------------------
+__device__ __forceinline__ void load_meta(FusedShared &S, int tid, uint32_t u_first, int nb, int nch,
+                                          const L3UnitDesc *__restrict__ units)
+{
+    if (tid < nb * 2) {
+        const int gi = tid >> 1, c = tid & 1;
+        S.gm[gi].d[c] = units[u_first + (uint32_t)gi * nch + (c < nch ? c : 0)];
     }
-    if (t64 < 40) { G.nz[t64] = 0; G.mode[t64] = 0; }
-    group_sync(grp);
-
-    for (int c = 0; c < nch; c++) {
-        const int16_t *is = is_in + (size_t)(u0 + c) * 576;
-        const uint8_t *l2b = bands->line2band[row][c ? lay1 : lay0];
-        for (int i = t64; i < 576; i += 64) {
-            const int v = is[i], b = l2b[i];
-            const float a = __ldg(pow43 + (v < 0 ? -v : v)) * G.gain[c][b];
-            tmp[c * 576 + i] = v < 0 ? -a : a;
-            if (c == 1 && v != 0) G.nz[b] = 1;
-        }
+    for (int i = tid; i < KF_B * 40; i += KF_THREADS) {
+        (&S.nz[0][0])[i] = 0;
+        (&S.mode[0][0])[i] = 0;
     }
-    group_sync(grp);
+    if (tid == 0) S.any_ist = 0;
+}
 
-    const bool ms = (d0.hdr & L3H_MS) != 0, ist = (d0.hdr & L3H_IS) != 0;
-    const bool ok = (d0.flags & L3F_VALID) != 0;
-    if (nch == 2 && ist && ok && t64 == 0) {
-        const int nb = bands->nbands[row][lay1];
-        const bool lsf = (d1.hdr & L3H_LSF) != 0;
-        const uint8_t *sf1 = sf_in + (size_t)(u0 + 1) * 40;
-        int found[3] = {0, 0, 0}, found_long = 0;
-        bool first_long = true;
-        for (int b = nb - 1; b >= 0; b--) {
-            const int w = bands->win[row][lay1][b];
-            int *fnd;
-            if (w >= 0) fnd = &found[w];
-            else {
-                if (first_long) { found_long = found[0] | found[1] | found[2]; first_long = false; }
-                fnd = &found_long;
-            }
-            if (*fnd) continue;
-            if (G.nz[b]) { *fnd = 1; continue; }
-            const int sfb = bands->sfb[row][lay1][b];
-            int bsf = b;
-            if (w >= 0 && sfb == 12) bsf = b - 3;
-            if (w < 0 && sfb == 21) bsf = b - 1;
-            const int p = sf1[bsf];
-            if (!lsf) {
-                if (p < 7) { G.mode[b] = 1; G.kl[b] = f_is_kl[p]; G.kr[b] = f_is_kr[p]; }
-            } else if (!(p & 0x80)) {
-                const int j = d1.sfc & 1;
-                G.mode[b] = 1;
-                G.kl[b] = (p & 1) ? f_lsf_pow[j][(p + 1) >> 1] : 1.f;
-                G.kr[b] = (p & 1) ? 1.f : f_lsf_pow[j][p >> 1];
-            }
-        }
+__device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int nch)
+{
+    if (tid < nb) {
+        GranMeta &m = S.gm[tid];
+        m.row = (m.d[0].hdr >> L3H_SR_SHIFT) & 7;
+        for (int c = 0; c < 2; c++)
+            m.lay[c] = (m.d[c].flags & L3F_BT_MASK) == 2 ? ((m.d[c].flags & L3F_MIXED) ? 2 : 1) : 0;
+        const bool ok = (m.d[0].flags & L3F_VALID) != 0;
+        m.ms = (nch == 2 && ok && (m.d[0].hdr & L3H_MS)) ? 1 : 0;
+        m.ist = (nch == 2 && ok && (m.d[0].hdr & L3H_IS)) ? 1 : 0;
+        m.joint = m.ms | m.ist;
+        if (m.ist) S.any_ist = 1;
     }
-    group_sync(grp);
+}
 
-    const float isq2 = 0.70710678118654752440f;
-    const bool joint = nch == 2 && ok && (ms || ist);
-    float *X0 = S.X[grp][0], *X1 = S.X[grp][1];
-    for (int i = t64; i < 576; i += 64) {
-        float l = tmp[i], r = nch == 2 ? tmp[576 + i] : 0.f;
-        if (joint) {
-            const int b = bands->line2band[row][lay1][i];
-            if (ist && G.mode[b]) { const float a = l; l = a * G.kl[b]; r = a * G.kr[b]; }
-            else if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
+// ---- S1a: per-band gains, and the right channel's non-zero bands for intensity granules ---------
+__device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int nch,
+                                            const L3BandTables *__restrict__ bands)
+{
+    for (int it = tid; it < nb * 80; it += KF_THREADS) {
+        const int gi = it / 80, c = (it % 80) / 40, b = it % 40;
+        if (c >= nch) continue;
+        const GranMeta &m = S.gm[gi];
+        const L3UnitDesc &dd = m.d[c];
+        const int lay = m.lay[c];
+        float gn = 0.f;
+        if (b < bands->nbands[m.row][lay]) {
+            const int s = S.sf_buf[gi * nch + c][b] & 0x7f;
+            const int win = bands->win[m.row][lay][b];
+            const int sh = (dd.flags & L3F_SFSCALE) ? 4 : 2;
+            int q = (int)dd.global_gain - 210;
+            if (win < 0) q -= sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[bands->sfb[m.row][lay][b]] : 0));
+            else q -= 8 * dd.sbg[win] + sh * s;
+            gn = ldexpf(f_pow2q[q & 3], q >> 2);
         }
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            if (c >= nch) break;
-            const int lay = c ? lay1 : lay0;
-            int dst = i;
-            if (lay != 0) {
-                const int b = bands->line2band[row][lay][i];
-                const int w = bands->win[row][lay][b];
-                if (w >= 0) {
-                    const int wd = bands->width[row][lay][b], s = bands->start[row][lay][b];
-                    dst = (s - w * wd) + 3 * (i - s) + w;
-                }
-            }
-            (c ? X1 : X0)[xpad(dst)] = c ? r : l;
-        }
+        S.gain[gi][c][b] = gn;
     }
-    group_sync(grp);
-
-    for (int t = t64; t < 248 * nch; t += 64) {
-        const int c = t / 248, k = t % 248, sb = 1 + (k >> 3), i = k & 7;
-        const uint8_t fl = c ? d1.flags : d0.flags;
-        const int nb = (fl & L3F_BT_MASK) == 2 ? ((fl & L3F_MIXED) ? 1 : 0) : 31;
-        if (sb <= nb) {
-            float *Xc = c ? X1 : X0;
-            const int ilo = (sb - 1) * XROW + 17 - i, ihi = sb * XROW + i;
-            const float lo = Xc[ilo], hi = Xc[ihi];
-            Xc[ilo] = lo * f_cs[i] - hi * f_ca[i];
-            Xc[ihi] = hi * f_cs[i] + lo * f_ca[i];
+    if (S.any_ist) {
+        for (int it = tid; it < nb * 576; it += KF_THREADS) {
+            const int gi = it / 576, i = it - gi * 576;
+            const GranMeta &m = S.gm[gi];
+            if (!m.ist) continue;
+            if (S.is_buf[gi * nch + 1][i] != 0)
+                S.nz[gi][bands->line2band[m.row][m.lay[1]][i]] = 1;
         }
     }
 }
 
-// ---- S2: IMDCT of one (granule, channel) by one warp, lane = subband ----------------------------
+// ---- S1b: intensity decisions, one thread per intensity granule (right channel's bands, high to low)
+__device__ __forceinline__ void stage_intensity(FusedShared &S, int gi, int u1 /* batch-local unit */,
+                                                const L3BandTables *__restrict__ bands)
+{
+    const GranMeta &m = S.gm[gi];
+    const int row = m.row, lay1 = m.lay[1];
+    const int nbands = bands->nbands[row][lay1];
+    const bool lsf = (m.d[1].hdr & L3H_LSF) != 0;
+    const uint8_t *sf1 = S.sf_buf[u1];
+    int found[3] = {0, 0, 0}, found_long = 0;
+    bool first_long = true;
+    for (int b = nbands - 1; b >= 0; b--) {
+        const int w = bands->win[row][lay1][b];
+        int *fnd;
+        if (w >= 0) fnd = &found[w];
+        else {
+            if (first_long) { found_long = found[0] | found[1] | found[2]; first_long = false; }
+            fnd = &found_long;
+        }
+        if (*fnd) continue;
+        if (S.nz[gi][b]) { *fnd = 1; continue; }
+        const int sfb = bands->sfb[row][lay1][b];
+        int bsf = b;
+        if (w >= 0 && sfb == 12) bsf = b - 3;
+        if (w < 0 && sfb == 21) bsf = b - 1;
+        const int p = sf1[bsf];
+        if (!lsf) {
+            if (p < 7) { S.mode[gi][b] = 1; S.kl[gi][b] = f_is_kl[p]; S.kr[gi][b] = f_is_kr[p]; }
+        } else if (!(p & 0x80)) {
+            const int j = m.d[1].sfc & 1;
+            S.mode[gi][b] = 1;
+            S.kl[gi][b] = (p & 1) ? f_lsf_pow[j][(p + 1) >> 1] : 1.f;
+            S.kr[gi][b] = (p & 1) ? 1.f : f_lsf_pow[j][p >> 1];
+        }
+    }
+}
+
+__device__ __forceinline__ float requant1(const FusedShared &S, int v, float gain, const float *__restrict__ pow43)
+{
+    const int m = v < 0 ? -v : v;
+    const float p = m < KF_POW_LUT ? S.pow43[m] : __ldg(pow43 + m);
+    const float a = p * gain;
+    return v < 0 ? -a : a;
+}
+
+__device__ __forceinline__ int reorder_dst(const L3BandTables *__restrict__ bands, int row, int lay, int i, int b)
+{
+    if (lay == 0) return i;
+    const int w = bands->win[row][lay][b];
+    if (w < 0) return i;
+    const int wd = bands->width[row][lay][b], s = bands->start[row][lay][b];
+    return (s - w * wd) + 3 * (i - s) + w;
+}
+
+// ---- S1c: requantise + stereo + reorder, one (granule, line) per item -----------------------------
+__device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, int nch,
+                                              const L3BandTables *__restrict__ bands, const float *__restrict__ pow43)
+{
+    constexpr int ITEMS = KF_B * 576 / KF_THREADS; // 9
+    const float isq2 = 0.70710678118654752440f;
+    int v0[ITEMS], v1[ITEMS];
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+        const int it = tid + q * KF_THREADS, gi = it / 576, i = it - gi * 576;
+        v0[q] = v1[q] = 0;
+        if (gi < nb) {
+            v0[q] = S.is_buf[gi * nch][i];
+            if (nch == 2) v1[q] = S.is_buf[gi * nch + 1][i];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+        const int it = tid + q * KF_THREADS, gi = it / 576, i = it - gi * 576;
+        if (gi >= nb) continue;
+        const GranMeta &m = S.gm[gi];
+        const int row = m.row, lay0 = m.lay[0], lay1 = m.lay[1];
+        const int b0 = bands->line2band[row][lay0][i];
+        const int b1 = (nch == 2 && lay1 != lay0) ? bands->line2band[row][lay1][i] : b0;
+        float l = requant1(S, v0[q], S.gain[gi][0][b0], pow43);
+        if (nch == 2) {
+            float r = requant1(S, v1[q], S.gain[gi][1][b1], pow43);
+            if (m.joint) {
+                if (m.ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
+                else if (m.ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
+            }
+            S.X[gi][1][xpad(reorder_dst(bands, row, lay1, i, b1))] = r;
+        }
+        S.X[gi][0][xpad(reorder_dst(bands, row, lay0, i, b0))] = l;
+    }
+}
+
+// ---- S2: alias reduction + IMDCT of one (granule, channel) by one warp, lane = subband ----------
 __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lane, uint8_t flags,
                                             float *__restrict__ Fdst /* [18][32] */, float *__restrict__ Hdst /* [18][32] */)
 {
@@ -203,7 +271,22 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
 #pragma unroll
     for (int k = 0; k < 18; k++) x[k] = X[lane * XROW + k];
     int bt = flags & L3F_BT_MASK;
-    if (bt == 2 && (flags & L3F_MIXED) && lane < 2) bt = 0;
+    const bool mixed = bt == 2 && (flags & L3F_MIXED);
+    // alias butterflies between subband `lane - 1` (its lines 17-i) and `lane` (its lines i), i < 8
+    {
+        const int nbnd = bt == 2 ? (mixed ? 1 : 0) : 31; // boundaries 1..nbnd are processed
+        const bool lo_side = lane + 1 <= nbnd;           // this lane is the lower subband of a boundary
+        const bool hi_side = lane >= 1 && lane <= nbnd;  // this lane is the upper subband of a boundary
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float from_next = __shfl_down_sync(0xffffffffu, x[i], 1);    // next subband's line i
+            const float from_prev = __shfl_up_sync(0xffffffffu, x[17 - i], 1); // previous subband's line 17-i
+            const float hi = x[i], lo = x[17 - i];
+            if (hi_side) x[i] = hi * f_cs[i] + from_prev * f_ca[i];
+            if (lo_side) x[17 - i] = lo * f_cs[i] - from_next * f_ca[i];
+        }
+    }
+    if (mixed && lane < 2) bt = 0;
     const float sgn = (lane & 1) ? -1.f : 1.f; // frequency inversion: odd subband, odd slot
     if (bt != 2) {
         const float *w = f_win[bt];
@@ -212,8 +295,8 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
             float sa = 0.f, sb = 0.f;
 #pragma unroll
             for (int k = 0; k < 18; k++) {
-                sa = fmaf(x[k], f_cosA[i][k], sa);
-                sb = fmaf(x[k], f_cosB[i][k], sb);
+                sa = fmaf(x[k], K36A[i][k], sa);
+                sb = fmaf(x[k], K36B[i][k], sb);
             }
             // out[i] = sa, out[17-i] = -sa, out[18+i] = sb, out[35-i] = sb
             const float s_i = (i & 1) ? sgn : 1.f, s_m = ((17 - i) & 1) ? sgn : 1.f;
@@ -230,7 +313,7 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
             for (int i = 0; i < 12; i++) {
                 float s = 0.f;
 #pragma unroll
-                for (int k = 0; k < 6; k++) s = fmaf(x[3 * k + wdw], f_cos12[i][k], s);
+                for (int k = 0; k < 6; k++) s = fmaf(x[3 * k + wdw], K12[i][k], s);
                 y[wdw][i] = s * f_win[2][i];
             }
 #pragma unroll
@@ -246,8 +329,36 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
     }
 }
 
+// ---- S4: synthesis window for one (granule, channel), lane = sample j ---------------------------
+// rows r0 .. r0+32 of Fc are the transformed slots T0-15 .. T0+17.  Output slot T (0..17) is
+//   sum_{l<16} W[l][j] * C_{T-l}[l even ? src_e : src_o]
+// evaluated as a sliding accumulation over the rows: each row is loaded once (2 LDS) and feeds the
+// up to 16 outputs it contributes to.  Everything is unrolled, so the 16-entry accumulator ring and
+// the window taps live in registers.
+template <typename Emit>
+__device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r0, int src_e, int src_o,
+                                             const float (&wn)[16], Emit emit)
+{
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 33; q++) {
+        const float e = Fc[(r0 + q) * 32 + src_e], o = Fc[(r0 + q) * 32 + src_o];
+#pragma unroll
+        for (int l = 0; l < 16; l++) {
+            const int T = q + l - 15;
+            if (T >= 0 && T < 18) acc[T & 15] = fmaf(wn[l], (l & 1) ? o : e, acc[T & 15]);
+        }
+        if (q >= 15) {
+            emit(q - 15, acc[(q - 15) & 15]);
+            acc[(q - 15) & 15] = 0.f;
+        }
+    }
+}
+
 template <int FMT>
-__global__ void __launch_bounds__(KF_THREADS)
+__global__ void __launch_bounds__(KF_THREADS, 2)
 k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
           const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
           const L3BandTables *__restrict__ bands, const float *__restrict__ pow43, void *__restrict__ pcm)
@@ -263,99 +374,115 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
     const uint32_t gu_first = gran_unit0[gstart];
     const int nch = (gu_first & L3G_STEREO) ? 2 : 1;
     const uint32_t ubase = gu_first & L3G_UNIT_MASK; // units of a stream are contiguous
+    typedef typename std::conditional<FMT == MP3B_PCM_S16, int16_t, float>::type pcm_t;
 
     // history starts at zero (stream head, or about to be re-derived by the warm-up granules)
-    for (int i = tid; i < 2 * 15 * 32; i += KF_THREADS) S.F[i / 480][(i % 480) / 32][i % 32] = 0.f;
-    for (int i = tid; i < 2 * 576; i += KF_THREADS) S.H[i / 576][0][(i % 576) / 32][i % 32] = 0.f;
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < 2 * 120; i += KF_THREADS) reinterpret_cast<float4 *>(&S.F[i / 120][0][0])[i % 120] = z;
+        for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.H[i / 144][0][0][0])[i % 144] = z;
+        for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) S.pow43[i] = pow43[i];
+        load_meta(S, tid, ubase, min(KF_B, total), nch, units);
+        prefetch_units(S, tid, ubase, min(KF_B, total) * nch, is_in, sf_in);
+    }
     __syncthreads();
 
-    float cn[32];
+    // per-lane constants: 16 DCT coefficients of output n = lane, 16 window taps of sample j = lane
+    float cn[16];
 #pragma unroll
-    for (int k = 0; k < 32; k++) cn[k] = f_dct32[k][lane];
+    for (int k = 0; k < 16; k++) cn[k] = f_dct32[k][lane];
     float wn[16];
 #pragma unroll
     for (int l = 0; l < 16; l++) wn[l] = f_synwin[l][lane];
     const int src_e = lane <= 15 ? 16 + lane : (lane == 16 ? 0 : 48 - lane);
     const int src_o = lane <= 16 ? 16 - lane : lane - 16;
+    pcm_t *stage = reinterpret_cast<pcm_t *>(&S.X[0][0][0]);
 
     for (int b0 = 0; b0 < total; b0 += KF_B) {
         const int nb = min(KF_B, total - b0);
+        const uint32_t u_first = ubase + (uint32_t)b0 * nch;
         // ---- S1
-        {
-            const int grp = tid >> 6, t64 = tid & 63;
-            if (grp < nb) {
-                const uint32_t u0 = ubase + (uint32_t)(b0 + grp) * nch;
-                float *tmp = &S.F[grp >> 1][15][0] + (grp & 1) * 1152; // rows 15.. of F are free until S2
-                stage_requant(S, grp, t64, u0, nch, units, is_in, sf_in, bands, pow43, tmp);
-            }
-        }
+        finish_meta(S, tid, nb, nch);
+        cp_async_wait_all();
         __syncthreads();
+        stage_gains(S, tid, nb, nch, bands);
+        __syncthreads();
+        if (S.any_ist) {
+            if ((tid & 63) == 0 && (tid >> 6) < nb && S.gm[tid >> 6].ist)
+                stage_intensity(S, tid >> 6, (tid >> 6) * nch + 1, bands);
+            __syncthreads();
+        }
+        stage_requant(S, tid, nb, nch, bands, pow43);
+        __syncthreads();
+        // is_buf / sf_buf are consumed: start fetching the next batch behind S2..S5
+        if (b0 + KF_B < total)
+            prefetch_units(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B) * nch, is_in, sf_in);
         // ---- S2
         {
             const int gi = warp >> 1, c = warp & 1;
-            if (gi < nb && c < nch) {
-                const uint8_t fl = units[ubase + (uint32_t)(b0 + gi) * nch + c].flags;
-                stage_imdct(S.X[gi][c], lane, fl, &S.F[c][15 + gi * 18][0], &S.H[c][gi + 1][0][0]);
-            }
+            if (gi < nb && c < nch)
+                stage_imdct(S.X[gi][c], lane, S.gm[gi].d[c].flags, &S.F[c][15 + gi * 18][0], &S.H[c][gi + 1][0][0]);
         }
         __syncthreads();
-        // ---- S3
-        for (int it = warp; it < nch * nb * 18; it += KF_THREADS / 32) {
-            const int c = it / (nb * 18), s = it % (nb * 18), gi = s / 18, t = s % 18;
-            float *row = &S.F[c][15 + s][0];
-            const float *hrow = &S.H[c][gi][t][0];
-            float acc = 0.f;
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-                const float4 a = *reinterpret_cast<const float4 *>(row + k);
-                const float4 h = *reinterpret_cast<const float4 *>(hrow + k);
-                acc = fmaf(a.x + h.x, cn[k], acc);
-                acc = fmaf(a.y + h.y, cn[k + 1], acc);
-                acc = fmaf(a.z + h.z, cn[k + 2], acc);
-                acc = fmaf(a.w + h.w, cn[k + 3], acc);
-            }
-            __syncwarp();
-            row[lane] = acc;
-        }
-        __syncthreads();
-        // ---- S4
-        for (int s = warp; s < nb * 18; s += KF_THREADS / 32) {
-            const int gi = s / 18, t = s % 18;
-            if (b0 + gi < warm) continue; // warm-up granule: state only
-            float out[2] = {0.f, 0.f};
-            for (int c = 0; c < nch; c++) {
-                const float *base = &S.F[c][15 + s][0];
+        // next batch's descriptors can be fetched now (gm is dead until the next S1)
+        if (b0 + KF_B < total)
+            load_meta(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B), nch, units);
+        // ---- S3: overlap-add + 32-point transform, in place
+        for (int c = 0; c < nch; c++)
+            for (int s = warp; s < nb * 18; s += KF_THREADS / 32) {
+                const int gi = s / 18, t = s - gi * 18;
+                float *row = &S.F[c][15 + s][0];
+                const float v = row[lane] + S.H[c][gi][t][lane];
+                const float p = __shfl_sync(0xffffffffu, v, 31 - lane);
+                // lanes 0..15 hold u[k] = S[k] + S[31-k]; lanes 16..31 hold v[31-lane] = S[31-lane] - S[lane]
+                __syncwarp();
+                if (lane < 16) row[lane] = v + p;
+                else row[47 - lane] = p - v;
+                __syncwarp();
+                const float4 *in = reinterpret_cast<const float4 *>(row + ((lane & 1) << 4));
                 float acc = 0.f;
 #pragma unroll
-                for (int l = 0; l < 16; l += 2) {
-                    acc = fmaf(wn[l], base[-l * 32 + src_e], acc);
-                    acc = fmaf(wn[l + 1], base[-(l + 1) * 32 + src_o], acc);
+                for (int k = 0; k < 4; k++) {
+                    const float4 a = in[k];
+                    acc = fmaf(a.x, cn[4 * k], acc);
+                    acc = fmaf(a.y, cn[4 * k + 1], acc);
+                    acc = fmaf(a.z, cn[4 * k + 2], acc);
+                    acc = fmaf(a.w, cn[4 * k + 3], acc);
                 }
-                out[c] = acc;
+                __syncwarp();
+                row[lane] = acc;
             }
-            const size_t e0 = (size_t)(ubase + (uint32_t)(b0 + gi) * nch) * 576 + (size_t)(t * 32 + lane) * nch;
-            if (FMT == MP3B_PCM_S16) {
-                int16_t *p = reinterpret_cast<int16_t *>(pcm);
-                if (nch == 2)
-                    *reinterpret_cast<uint32_t *>(p + e0) =
-                        (uint16_t)to_s16(out[0]) | ((uint32_t)(uint16_t)to_s16(out[1]) << 16);
-                else
-                    p[e0] = to_s16(out[0]);
-            } else {
-                float *p = reinterpret_cast<float *>(pcm);
-                if (nch == 2) *reinterpret_cast<float2 *>(p + e0) = make_float2(out[0], out[1]);
-                else p[e0] = out[0];
+        __syncthreads();
+        // ---- S4: window -> PCM staging (X is free now)
+        {
+            const int gi = warp >> 1, c = warp & 1;
+            if (gi < nb && c < nch && b0 + gi >= warm) {
+                pcm_t *dst = stage + (size_t)gi * 576 * nch + c;
+                stage_window(&S.F[c][0][0], gi * 18, src_e, src_o, wn, [&](int t, float val) {
+                    if (FMT == MP3B_PCM_S16) dst[(t * 32 + lane) * nch] = (pcm_t)to_s16(val);
+                    else dst[(t * 32 + lane) * nch] = (pcm_t)val;
+                });
             }
         }
         __syncthreads();
-        // ---- S5: carry the state to the next batch
-        for (int i = tid; i < 2 * 15 * 32; i += KF_THREADS) {
-            const int c = i / 480, r = (i % 480) / 32, k = i % 32;
-            S.F[c][r][k] = S.F[c][nb * 18 + r][k];
-        }
-        for (int i = tid; i < 2 * 576; i += KF_THREADS) {
-            const int c = i / 576, r = (i % 576) / 32, k = i % 32;
-            S.H[c][0][r][k] = S.H[c][nb][r][k];
+        // ---- S5: PCM out (16-byte stores), carry the state to the next batch
+        {
+            const int first_out = max(0, warm - b0); // warm-up granules of this batch produce no PCM
+            if (first_out < nb) {
+                const size_t e0 = (size_t)(u_first + (uint32_t)first_out * nch) * 576;
+                const int nvec = (nb - first_out) * 576 * nch * (int)sizeof(pcm_t) / 16;
+                const uint4 *src = reinterpret_cast<const uint4 *>(stage + (size_t)first_out * 576 * nch);
+                uint4 *dstg = reinterpret_cast<uint4 *>(reinterpret_cast<pcm_t *>(pcm) + e0);
+                for (int i = tid; i < nvec; i += KF_THREADS) dstg[i] = src[i];
+            }
+            for (int i = tid; i < 2 * 120; i += KF_THREADS) {
+                const int c = i / 120, k = i % 120;
+                reinterpret_cast<float4 *>(&S.F[c][0][0])[k] = reinterpret_cast<const float4 *>(&S.F[c][nb * 18][0])[k];
+            }
+            for (int i = tid; i < 2 * 144; i += KF_THREADS) {
+                const int c = i / 144, k = i % 144;
+                reinterpret_cast<float4 *>(&S.H[c][0][0][0])[k] = reinterpret_cast<const float4 *>(&S.H[c][nb][0][0])[k];
+            }
         }
         __syncthreads();
     }
@@ -390,14 +517,7 @@ void l3_fused_init(void)
     cudaMemcpyToSymbol(f_ca, ca, sizeof ca);
     cudaMemcpyToSymbol(f_pretab, l3_pretab, sizeof l3_pretab);
 
-    static float A[9][18], B[9][18], C12[12][6], W[4][36];
-    for (int i = 0; i < 9; i++)
-        for (int k = 0; k < 18; k++) {
-            A[i][k] = (float)cos(M_PI / 72.0 * (2 * i + 1 + 18) * (2 * k + 1));
-            B[i][k] = (float)cos(M_PI / 72.0 * (2 * (18 + i) + 1 + 18) * (2 * k + 1));
-        }
-    for (int i = 0; i < 12; i++)
-        for (int k = 0; k < 6; k++) C12[i][k] = (float)cos(M_PI / 24.0 * (2 * i + 1 + 6) * (2 * k + 1));
+    static float W[4][36];
     for (int i = 0; i < 36; i++) {
         W[0][i] = (float)sin(M_PI / 36.0 * (i + 0.5));
         W[1][i] = i < 18 ? (float)sin(M_PI / 36.0 * (i + 0.5))
@@ -406,13 +526,10 @@ void l3_fused_init(void)
         W[3][i] = i < 6 ? 0.f : (i < 12 ? (float)sin(M_PI / 12.0 * (i - 6 + 0.5))
                                         : (i < 18 ? 1.f : (float)sin(M_PI / 36.0 * (i + 0.5))));
     }
-    cudaMemcpyToSymbol(f_cosA, A, sizeof A);
-    cudaMemcpyToSymbol(f_cosB, B, sizeof B);
-    cudaMemcpyToSymbol(f_cos12, C12, sizeof C12);
     cudaMemcpyToSymbol(f_win, W, sizeof W);
 
-    static float dct[32][32], win[16][32];
-    for (int k = 0; k < 32; k++)
+    static float dct[16][32], win[16][32];
+    for (int k = 0; k < 16; k++)
         for (int n = 0; n < 32; n++) dct[k][n] = (float)cos(n * (2 * k + 1) * M_PI / 64.0);
     for (int l = 0; l < 16; l++)
         for (int j = 0; j < 32; j++) {
