@@ -214,9 +214,10 @@ def run_ours(args, rank, world):
     h_out = mp3_b200.PinnedBuffer(pcm_bytes + 64)
     pcm_elems = pcm_bytes // 2
 
+    dec.set_pcm_sink(h_out.ptr, pcm_elems)  # D2H of each wave overlaps the next wave's kernels
+
     def step_e2e():
         dec.decode_packed(h_in.ptr, offs, where=mp3_b200.HOST, sync=False)
-        dec.fetch_pcm_into(h_out.ptr, pcm_elems)
 
     for _ in range(min(args.warmup, 3)):
         step_e2e()
@@ -229,6 +230,7 @@ def run_ours(args, rank, world):
     e3.record(tstream)
     barrier()
     sampler.stop_flag = True
+    dec.set_pcm_sink(0, 0)
     ms_e2e = e2.elapsed_time(e3) / args.steps
     checksum = int(h_out.view(np.int16, pcm_elems)[:: max(1, pcm_elems // 4096)].astype(np.int64).sum())
 

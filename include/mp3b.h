@@ -123,6 +123,12 @@ int mp3b_batch_pcm_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *n
  * pinned; call mp3b_sync() before reading it. */
 int mp3b_batch_fetch_pcm(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got);
 int mp3b_get_stats(const mp3b_ctx *ctx, mp3b_stats *st);
+/* Streaming PCM sink: register a host buffer (pinned memory from mp3b_host_alloc for full PCIe speed)
+ * of cap_elems PCM elements.  Every following decode call splits the batch into waves and copies each
+ * wave's PCM to host_dst + its arena offset on a second CUDA stream while the next wave decodes, so
+ * the D2H transfer overlaps the kernels.  mp3b_sync() (and the context's stream) waits for the copies.
+ * host_dst = NULL removes the sink.  A too-small sink makes the decode call fail with TRUNCATED. */
+int mp3b_set_pcm_sink(mp3b_ctx *ctx, void *host_dst, uint64_t cap_elems);
 
 /* ---- stream interface (open / enqueue / decode / fetch) ------------------------------------- */
 int mp3b_stream_open(mp3b_ctx *ctx, mp3b_stream **out);

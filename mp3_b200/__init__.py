@@ -55,7 +55,7 @@ EXPORTS = [
     "mp3b_abi_version", "mp3b_device_count", "mp3b_opts_default", "mp3b_ctx_create", "mp3b_ctx_destroy",
     "mp3b_ctx_set_stream", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
     "mp3b_decode_packed", "mp3b_sync", "mp3b_batch_stream_info", "mp3b_batch_pcm_device_ptr",
-    "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
+    "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_set_pcm_sink", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
     "mp3b_debug_stage",
 ]
@@ -90,6 +90,7 @@ def load_library():
     L.mp3b_batch_pcm_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.mp3b_batch_fetch_pcm.argtypes = [vp, vp, u64, i32, ctypes.POINTER(u64)]
     L.mp3b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.mp3b_set_pcm_sink.argtypes = [vp, vp, u64]
     L.mp3b_stream_open.argtypes = [vp, ctypes.POINTER(vp)]
     L.mp3b_stream_close.argtypes = [vp]
     L.mp3b_stream_enqueue.argtypes = [vp, vp, sz]
@@ -256,6 +257,10 @@ class Decoder:
         got = ctypes.c_uint64()
         self._ck(self.L.mp3b_batch_fetch_pcm(self.ctx, ctypes.c_void_p(host_ptr), cap_elems, HOST, ctypes.byref(got)))
         return got.value
+
+    def set_pcm_sink(self, host_ptr, cap_elems):
+        """Stream every decode's PCM to this (pinned) host buffer, overlapped with the kernels."""
+        self._ck(self.L.mp3b_set_pcm_sink(self.ctx, ctypes.c_void_p(host_ptr) if host_ptr else None, cap_elems))
 
     def stream_pcm(self, i, arena=None):
         """PCM of stream i as [samples, channels]."""

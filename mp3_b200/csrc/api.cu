@@ -87,6 +87,11 @@ struct mp3b_ctx {
     mp3b_opts opts{};
     cudaStream_t stream = nullptr;     // the stream work is enqueued on
     cudaStream_t own_stream = nullptr; // created by the context
+    cudaStream_t copy_stream = nullptr; // D2H of finished waves (PCM sink)
+    std::vector<cudaEvent_t> wave_ev;
+    cudaEvent_t copy_done = nullptr;
+    void *sink = nullptr;
+    uint64_t sink_cap = 0;
     cudaEvent_t ev[EV_COUNT]{};
     std::string err;
 
@@ -240,6 +245,10 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     if (host_index && where != MP3B_HOST) { ctx->err = "host indexer needs host-resident input"; return MP3B_E_INVAL; }
 
     CK(cudaEventRecord(ctx->ev[EV_START], st));
+    if (ctx->sink) { // a previous call's sink copies must have left the PCM arena before it is rewritten
+        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    }
     // ---- raw bytes to the device
     if (where == MP3B_HOST) {
         CK(ctx->d_raw.ensure(raw_total + 64));
@@ -352,7 +361,11 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(ctx->h_counter.ensure(64));
     CK(ctx->d_pcm.ensure(std::max<uint64_t>(ctx->pcm_elems * elem, 16)));
     const bool keep = ctx->opts.keep_stages != 0;
-    const uint64_t wave = keep ? std::max<uint64_t>(units, 1) : std::min<uint64_t>(std::max<uint64_t>(units, 1), ctx->wave_units);
+    const bool sink = ctx->sink != nullptr && !keep;
+    if (sink && ctx->sink_cap < ctx->pcm_elems) { ctx->err = "PCM sink too small"; return MP3B_E_TRUNCATED; }
+    uint64_t wave = keep ? std::max<uint64_t>(units, 1) : std::min<uint64_t>(std::max<uint64_t>(units, 1), ctx->wave_units);
+    if (sink) // several waves so that the D2H of wave k overlaps the kernels of wave k+1
+        wave = std::min<uint64_t>(wave, std::max<uint64_t>(units / 8, 32768));
     // a wave is a whole number of streams; size the intermediates for the largest wave
     std::vector<std::pair<int, int>> waves; // [first stream, last stream)
     uint64_t max_wave_units = 1;
@@ -429,11 +442,26 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
         l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, ctx->T, is, sf, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
+        auto wave_done = [&]() -> int {
+            if (!sink) return MP3B_OK;
+            while (ctx->wave_ev.size() <= w) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->wave_ev.push_back(e);
+            }
+            CK(cudaEventRecord(ctx->wave_ev[w], st));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->wave_ev[w], 0));
+            const size_t lo = (size_t)u_lo * 576 * elem, n = (size_t)nu * 576 * elem;
+            CK(cudaMemcpyAsync(static_cast<char *>(ctx->sink) + lo, ctx->d_pcm.as<char>() + lo, n,
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+            return MP3B_OK;
+        };
         if (fused) {
             l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, ctx->T,
                               ctx->d_pcm.p, ctx->opts.pcm_format, st);
             if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
             launches += 2;
+            if (int rc = wave_done()) return rc;
             continue;
         }
         l3_launch_requant_range(du, dg, g_lo, ngw, is, sf, ctx->T, xr, st);
@@ -446,6 +474,11 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
                         ctx->opts.pcm_format, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
         launches += 5;
+        if (int rc = wave_done()) return rc;
+    }
+    if (sink) { // the context's stream (and so the caller's events on it) also covers the copies
+        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
     }
     CK(cudaMemcpyAsync(ctx->h_counter.p, ctx->d_counter.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[EV_END], st));
@@ -515,6 +548,8 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     if (cudaSetDevice(device) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     for (auto &e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return bail(MP3B_E_CUDA);
     int rc = upload_tables(ctx);
@@ -537,6 +572,12 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
         b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -662,6 +703,17 @@ int mp3b_batch_fetch_pcm(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where
         CK(cudaMemcpyAsync(dst, ctx->d_pcm.p, ctx->pcm_elems * elem,
                            where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     if (got) *got = ctx->pcm_elems;
+    return MP3B_OK;
+}
+
+int mp3b_set_pcm_sink(mp3b_ctx *ctx, void *host_dst, uint64_t cap_elems)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->sink = host_dst;
+    ctx->sink_cap = host_dst ? cap_elems : 0;
     return MP3B_OK;
 }
 

@@ -203,3 +203,25 @@ def test_waves_give_identical_pcm(pipe, mp3b, batch, monkeypatch):
         dec.decode_batch(streams)
         many = dec.fetch_pcm().copy()
     assert np.array_equal(one, many)
+
+
+def test_pcm_sink_matches_fetch(mp3b, batch):
+    """The overlapped D2H path (mp3b_set_pcm_sink) delivers the same bytes as an explicit fetch."""
+    streams, _ = batch
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16) as dec:
+        dec.decode_batch(streams)
+        ref = dec.fetch_pcm().copy()
+        sink = mp3b.PinnedBuffer(ref.nbytes + 64)
+        sink.view(np.uint8)[:] = 0xEE
+        dec.set_pcm_sink(sink.ptr, ref.size)
+        for _ in range(2):                    # twice: the second call must wait for the first copies
+            dec.decode_batch(streams)
+        got = sink.view(np.int16, ref.size).copy()
+        dec.set_pcm_sink(0, 0)
+        assert np.array_equal(got, ref)
+        small = mp3b.PinnedBuffer(1024)
+        dec.set_pcm_sink(small.ptr, 10)
+        with pytest.raises(mp3b.Mp3bError) as e:
+            dec.decode_batch(streams)
+        assert e.value.status == -3
+        dec.set_pcm_sink(0, 0)
