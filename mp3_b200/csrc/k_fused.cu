@@ -62,7 +62,8 @@ struct GranMeta {
 struct FusedShared {
     float X[KF_B][2][XSZ];          // spectra of the batch, padded rows; reused as PCM staging in S4
     float F[2][KF_ROWS][32];        // rows 0..14: C history; rows 15..: first IMDCT halves -> S -> C
-    float H[2][KF_B + 1][18][32];   // second IMDCT halves; [0] = last granule of the previous batch
+    float Hc[2][18][32];            // second IMDCT half of the last granule of the previous batch
+    float dct[16][32], win[16][32]; // per-lane transform / window constants (copied from global once)
     float pow43[KF_POW_LUT];        // |is|^(4/3) for the common small values
     float gain[KF_B][2][40];
     float kl[KF_B][40], kr[KF_B][40];
@@ -230,24 +231,22 @@ __device__ __forceinline__ int reorder_dst(const L3BandTables *__restrict__ band
 __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, int nch,
                                               const L3BandTables *__restrict__ bands, const float *__restrict__ pow43)
 {
-    constexpr int ITEMS = KF_B * 576 / KF_THREADS; // 9
+    constexpr int ITEMS = 576 / 64; // 9 lines per thread: 64 threads per granule
     const float isq2 = 0.70710678118654752440f;
+    const int gi = tid >> 6, t64 = tid & 63;
+    if (gi >= nb) return;
+    const GranMeta &m = S.gm[gi];
+    const int row = m.row, lay0 = m.lay[0], lay1 = m.lay[1];
     int v0[ITEMS], v1[ITEMS];
 #pragma unroll
     for (int q = 0; q < ITEMS; q++) {
-        const int it = tid + q * KF_THREADS, gi = it / 576, i = it - gi * 576;
-        v0[q] = v1[q] = 0;
-        if (gi < nb) {
-            v0[q] = S.is_buf[gi * nch][i];
-            if (nch == 2) v1[q] = S.is_buf[gi * nch + 1][i];
-        }
+        const int i = t64 + 64 * q;
+        v0[q] = S.is_buf[gi * nch][i];
+        v1[q] = nch == 2 ? S.is_buf[gi * nch + 1][i] : 0;
     }
 #pragma unroll
     for (int q = 0; q < ITEMS; q++) {
-        const int it = tid + q * KF_THREADS, gi = it / 576, i = it - gi * 576;
-        if (gi >= nb) continue;
-        const GranMeta &m = S.gm[gi];
-        const int row = m.row, lay0 = m.lay[0], lay1 = m.lay[1];
+        const int i = t64 + 64 * q;
         const int b0 = bands->line2band[row][lay0][i];
         const int b1 = (nch == 2 && lay1 != lay0) ? bands->line2band[row][lay1][i] : b0;
         float l = requant1(S, v0[q], S.gain[gi][0][b0], pow43);
@@ -264,8 +263,12 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
 }
 
 // ---- S2: alias reduction + IMDCT of one (granule, channel) by one warp, lane = subband ----------
+// First halves go to Fdst (plus `carry`, the previous batch's last second half, for the batch's first
+// granule); the second half stays in registers (h) and is added to the next granule's rows after a
+// barrier, so no second-half buffer is needed.
 __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lane, uint8_t flags,
-                                            float *__restrict__ Fdst /* [18][32] */, float *__restrict__ Hdst /* [18][32] */)
+                                            float *__restrict__ Fdst /* [18][32] */,
+                                            const float *__restrict__ carry /* [18][32] or null */, float (&h)[18])
 {
     float x[18];
 #pragma unroll
@@ -300,10 +303,12 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
             }
             // out[i] = sa, out[17-i] = -sa, out[18+i] = sb, out[35-i] = sb
             const float s_i = (i & 1) ? sgn : 1.f, s_m = ((17 - i) & 1) ? sgn : 1.f;
-            Fdst[i * 32 + lane] = sa * w[i] * s_i;
-            Fdst[(17 - i) * 32 + lane] = -sa * w[17 - i] * s_m;
-            Hdst[i * 32 + lane] = sb * w[18 + i] * s_i;
-            Hdst[(17 - i) * 32 + lane] = sb * w[35 - i] * s_m;
+            float f0 = sa * w[i] * s_i, f1 = -sa * w[17 - i] * s_m;
+            if (carry) { f0 += carry[i * 32 + lane]; f1 += carry[(17 - i) * 32 + lane]; }
+            Fdst[i * 32 + lane] = f0;
+            Fdst[(17 - i) * 32 + lane] = f1;
+            h[i] = sb * w[18 + i] * s_i;
+            h[17 - i] = sb * w[35 - i] * s_m;
         }
     } else {
         float y[3][12];
@@ -319,12 +324,18 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             const float s_i = (i & 1) ? sgn : 1.f; // 6 and 12 are even: parity of i everywhere
-            Fdst[i * 32 + lane] = 0.f;
-            Fdst[(6 + i) * 32 + lane] = y[0][i] * s_i;
-            Fdst[(12 + i) * 32 + lane] = (y[0][6 + i] + y[1][i]) * s_i;
-            Hdst[i * 32 + lane] = (y[1][6 + i] + y[2][i]) * s_i;
-            Hdst[(6 + i) * 32 + lane] = y[2][6 + i] * s_i;
-            Hdst[(12 + i) * 32 + lane] = 0.f;
+            float f0 = 0.f, f1 = y[0][i] * s_i, f2 = (y[0][6 + i] + y[1][i]) * s_i;
+            if (carry) {
+                f0 += carry[i * 32 + lane];
+                f1 += carry[(6 + i) * 32 + lane];
+                f2 += carry[(12 + i) * 32 + lane];
+            }
+            Fdst[i * 32 + lane] = f0;
+            Fdst[(6 + i) * 32 + lane] = f1;
+            Fdst[(12 + i) * 32 + lane] = f2;
+            h[i] = (y[1][6 + i] + y[2][i]) * s_i;
+            h[6 + i] = y[2][6 + i] * s_i;
+            h[12 + i] = 0.f;
         }
     }
 }
@@ -358,7 +369,7 @@ __device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(KF_THREADS, 2)
+__global__ void __launch_bounds__(KF_THREADS, 3)
 k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
           const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
           const L3BandTables *__restrict__ bands, const float *__restrict__ pow43, void *__restrict__ pcm)
@@ -380,20 +391,17 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = tid; i < 2 * 120; i += KF_THREADS) reinterpret_cast<float4 *>(&S.F[i / 120][0][0])[i % 120] = z;
-        for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.H[i / 144][0][0][0])[i % 144] = z;
+        for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.Hc[i / 144][0][0])[i % 144] = z;
         for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) S.pow43[i] = pow43[i];
+        for (int i = tid; i < 512; i += KF_THREADS) {
+            (&S.dct[0][0])[i] = (&f_dct32[0][0])[i];
+            (&S.win[0][0])[i] = (&f_synwin[0][0])[i];
+        }
         load_meta(S, tid, ubase, min(KF_B, total), nch, units);
         prefetch_units(S, tid, ubase, min(KF_B, total) * nch, is_in, sf_in);
     }
     __syncthreads();
 
-    // per-lane constants: 16 DCT coefficients of output n = lane, 16 window taps of sample j = lane
-    float cn[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) cn[k] = f_dct32[k][lane];
-    float wn[16];
-#pragma unroll
-    for (int l = 0; l < 16; l++) wn[l] = f_synwin[l][lane];
     const int src_e = lane <= 15 ? 16 + lane : (lane == 16 ? 0 : 48 - lane);
     const int src_o = lane <= 16 ? 16 - lane : lane - 16;
     pcm_t *stage = reinterpret_cast<pcm_t *>(&S.X[0][0][0]);
@@ -417,22 +425,39 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         // is_buf / sf_buf are consumed: start fetching the next batch behind S2..S5
         if (b0 + KF_B < total)
             prefetch_units(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B) * nch, is_in, sf_in);
-        // ---- S2
+        // ---- S2: alias + IMDCT; second halves travel in registers to the next granule's rows
         {
             const int gi = warp >> 1, c = warp & 1;
-            if (gi < nb && c < nch)
-                stage_imdct(S.X[gi][c], lane, S.gm[gi].d[c].flags, &S.F[c][15 + gi * 18][0], &S.H[c][gi + 1][0][0]);
+            const bool act = gi < nb && c < nch;
+            float h[18];
+            if (act)
+                stage_imdct(S.X[gi][c], lane, S.gm[gi].d[c].flags, &S.F[c][15 + gi * 18][0],
+                            gi == 0 ? &S.Hc[c][0][0] : nullptr, h);
+            __syncthreads();
+            if (act) {
+                float *dst = gi + 1 < nb ? &S.F[c][15 + (gi + 1) * 18][0] : &S.Hc[c][0][0];
+                if (gi + 1 < nb) {
+#pragma unroll
+                    for (int t = 0; t < 18; t++) dst[t * 32 + lane] += h[t];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 18; t++) dst[t * 32 + lane] = h[t];
+                }
+            }
         }
         __syncthreads();
         // next batch's descriptors can be fetched now (gm is dead until the next S1)
         if (b0 + KF_B < total)
             load_meta(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B), nch, units);
         // ---- S3: overlap-add + 32-point transform, in place
+        {
+            float cn[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) cn[k] = S.dct[k][lane];
         for (int c = 0; c < nch; c++)
             for (int s = warp; s < nb * 18; s += KF_THREADS / 32) {
-                const int gi = s / 18, t = s - gi * 18;
                 float *row = &S.F[c][15 + s][0];
-                const float v = row[lane] + S.H[c][gi][t][lane];
+                const float v = row[lane];
                 const float p = __shfl_sync(0xffffffffu, v, 31 - lane);
                 // lanes 0..15 hold u[k] = S[k] + S[31-k]; lanes 16..31 hold v[31-lane] = S[31-lane] - S[lane]
                 __syncwarp();
@@ -452,11 +477,15 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                 __syncwarp();
                 row[lane] = acc;
             }
+        }
         __syncthreads();
         // ---- S4: window -> PCM staging (X is free now)
         {
             const int gi = warp >> 1, c = warp & 1;
             if (gi < nb && c < nch && b0 + gi >= warm) {
+                float wn[16];
+#pragma unroll
+                for (int l = 0; l < 16; l++) wn[l] = S.win[l][lane];
                 pcm_t *dst = stage + (size_t)gi * 576 * nch + c;
                 stage_window(&S.F[c][0][0], gi * 18, src_e, src_o, wn, [&](int t, float val) {
                     if (FMT == MP3B_PCM_S16) dst[(t * 32 + lane) * nch] = (pcm_t)to_s16(val);
@@ -478,10 +507,6 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
             for (int i = tid; i < 2 * 120; i += KF_THREADS) {
                 const int c = i / 120, k = i % 120;
                 reinterpret_cast<float4 *>(&S.F[c][0][0])[k] = reinterpret_cast<const float4 *>(&S.F[c][nb * 18][0])[k];
-            }
-            for (int i = tid; i < 2 * 144; i += KF_THREADS) {
-                const int c = i / 144, k = i % 144;
-                reinterpret_cast<float4 *>(&S.H[c][0][0][0])[k] = reinterpret_cast<const float4 *>(&S.H[c][nb][0][0])[k];
             }
         }
         __syncthreads();
