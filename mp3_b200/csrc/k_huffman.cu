@@ -26,49 +26,50 @@ __constant__ uint8_t c_lsf_nsfb[6][3][4] = {
     {{8, 8, 5, 0}, {15, 12, 9, 0}, {6, 18, 9, 0}},
 };
 
+// Bit reader over the big-endian main-data arena.  Two consecutive 32-bit words are cached in
+// registers; a peek is one funnel shift, a skip is one add plus a (rarely taken) refill when the
+// position crosses into the next word.  Positions are 32-bit and relative to the word the unit
+// starts in (the arena itself can exceed 2^32 bits).
 struct BitReader {
-    const uint32_t *words;
-    uint32_t widx, wend;
-    unsigned long long acc; // unread bits, left aligned
-    int n;                  // number of valid bits in acc
-    uint32_t consumed;
+    const uint32_t *words; // arena + first word of this unit
+    uint32_t wlimit;       // words readable from `words`
+    uint32_t w0, w1, w2;   // words[wi], words[wi + 1] in bit order; w2 = raw words[wi + 2], loaded one
+                           // word ahead so that its latency is off the decode chain
+    uint32_t wi;
+    uint32_t pos, start;   // bit position relative to words[0]
 
-    __device__ __forceinline__ uint32_t load(uint32_t w) const
-    {
-        uint32_t v = w < wend ? __ldg(words + w) : 0u;
-        return __byte_perm(v, 0, 0x0123);
-    }
+    __device__ __forceinline__ uint32_t load_raw(uint32_t w) const { return w < wlimit ? __ldg(words + w) : 0u; }
+    __device__ __forceinline__ uint32_t load(uint32_t w) const { return __byte_perm(load_raw(w), 0, 0x0123); }
     __device__ __forceinline__ void init(const uint8_t *arena, uint64_t arena_bytes, uint64_t bit_off)
     {
-        words = reinterpret_cast<const uint32_t *>(arena);
-        wend = (uint32_t)(arena_bytes >> 2);
-        widx = (uint32_t)(bit_off >> 5);
-        acc = ((unsigned long long)load(widx) << 32) | load(widx + 1);
-        widx += 2;
-        int sh = (int)(bit_off & 31);
-        acc <<= sh;
-        n = 64 - sh;
-        consumed = 0;
+        const uint64_t w = bit_off >> 5, total = arena_bytes >> 2;
+        words = reinterpret_cast<const uint32_t *>(arena) + w;
+        const uint64_t left = total > w ? total - w : 0;
+        wlimit = left > 0x7fffffffull ? 0x7fffffffu : (uint32_t)left;
+        wi = 0;
+        w0 = load(0);
+        w1 = load(1);
+        w2 = load_raw(2);
+        pos = start = (uint32_t)(bit_off & 31);
     }
-    __device__ __forceinline__ void refill()
+    __device__ __forceinline__ uint32_t consumed() const { return pos - start; }
+    // the next 32 bits, left aligned
+    __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_l(w1, w0, pos & 31); }
+    // k in 1..32
+    __device__ __forceinline__ uint32_t peek(int k) const { return peek32() >> (32 - k); }
+    __device__ __forceinline__ void skip(int k) // k in 0..32
     {
-        if (n <= 32) {
-            acc |= (unsigned long long)load(widx++) << (32 - n);
-            n += 32;
+        pos += (uint32_t)k;
+        if ((pos >> 5) != wi) {
+            wi++;
+            w0 = w1;
+            w1 = __byte_perm(w2, 0, 0x0123);
+            w2 = load_raw(wi + 2);
         }
-    }
-    // k in 1..32, n >= k must hold
-    __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }
-    __device__ __forceinline__ void skip(int k)
-    {
-        acc <<= k;
-        n -= k;
-        consumed += (uint32_t)k;
     }
     __device__ __forceinline__ uint32_t get(int k) // k in 0..16
     {
         if (k == 0) return 0;
-        refill();
         uint32_t v = peek(k);
         skip(k);
         return v;
@@ -87,7 +88,7 @@ __device__ __forceinline__ uint32_t bits_at(const uint8_t *arena, uint64_t arena
     return (uint32_t)((v << (bit & 31)) >> (64 - n));
 }
 
-constexpr int K1_THREADS = 128;
+constexpr int K1_THREADS = 256;
 
 __global__ void __launch_bounds__(K1_THREADS)
 k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitDesc *__restrict__ units,
@@ -103,9 +104,40 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         s_info[threadIdx.x] = g_info->base[threadIdx.x] | ((uint32_t)g_info->root[threadIdx.x] << 16) |
                               ((uint32_t)g_info->linbits[threadIdx.x] << 24);
     if (threadIdx.x < 64) s_quad[threadIdx.x] = g_quad[threadIdx.x];
+
+    // Units of a CTA are regrouped by big_values so that the 32 lanes of a warp run loops of similar
+    // length (lanes stay converged inside an iteration; what is left to lose is the loop count).
+    __shared__ uint32_t s_hist[160];
+    __shared__ uint16_t s_perm[K1_THREADS];
+    const uint32_t cta_first = blockIdx.x * K1_THREADS;
+    for (int i = threadIdx.x; i < 160; i += K1_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t bucket = 159; // units past the end sort last
+    if (cta_first + threadIdx.x < nunits) {
+        const L3UnitDesc *dp = units + u_lo + cta_first + threadIdx.x;
+        bucket = (dp->flags & L3F_VALID) ? (uint32_t)min((int)dp->big_values, 288) >> 1 : 0u;
+    }
+    atomicAdd(&s_hist[bucket], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) { // exclusive scan of 160 buckets: 5 per lane
+        uint32_t v[5], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) { v[k] = s_hist[threadIdx.x * 5 + k]; sum += v[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += t;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 5; k++) { s_hist[threadIdx.x * 5 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    s_perm[atomicAdd(&s_hist[bucket], 1u)] = (uint16_t)threadIdx.x;
     __syncthreads();
 
-    uint32_t u = blockIdx.x * K1_THREADS + threadIdx.x;
+    uint32_t u = cta_first + s_perm[threadIdx.x];
     if (u >= nunits) return;
     u += u_lo;
     const L3UnitDesc d = units[u];
@@ -215,52 +247,61 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
     const uint32_t i0 = s_info[d.tsel[0]], i1 = s_info[d.tsel[1]], i2 = s_info[d.tsel[2]];
     bool dead = !valid;
     for (int i = 0; i < bv2; i += 2) {
+        // One pair per iteration, written without branches: lanes differ in table, code length and
+        // escapes, but all of that is data (selects and predicated loads), not control flow.
         const uint32_t info = i < r1 ? i0 : (i < r2 ? i1 : i2);
-        const int root = (info >> 16) & 0xff;
-        int x = 0, y = 0;
-        if (root && !dead) {
-            if (br.consumed >= p23) dead = true;
-            else {
-                const uint32_t base = info & 0xffffu;
-                const int lin = (int)(info >> 24);
-                br.refill();
-                uint32_t e = s_lut[base + br.peek(root)];
-                int width = root;
-                while (e & 0x8000u) {
-                    br.skip(width);
-                    width = (e >> 11) & 15;
-                    e = s_lut[base + (e & 0x7ffu) + br.peek(width)];
-                }
-                br.skip((e >> 8) & 15);
-                x = (e >> 4) & 15;
-                y = e & 15;
-                br.refill();
-                if (lin && x == 15) { x += (int)br.peek(lin); br.skip(lin); }
-                if (x) { if (br.peek(1)) x = -x; br.skip(1); }
-                if (lin && y == 15) { y += (int)br.peek(lin); br.skip(lin); }
-                if (y) { if (br.peek(1)) y = -y; br.skip(1); }
-            }
+        const int root = (info >> 16) & 0xff; // 0 = the empty book: (0, 0), no bits
+        dead = dead || (root != 0 && br.consumed() >= p23);
+        const bool act = root != 0 && !dead;
+        const uint32_t base = info & 0xffffu;
+        const int lin = (int)(info >> 24);
+        // 64 bits of look-ahead: code (<= 19) + escapes and signs (<= 28)
+        const uint32_t sh = br.pos & 31;
+        const uint32_t hi = __funnelshift_l(br.w1, br.w0, sh);
+        const uint32_t lo = __funnelshift_l(__byte_perm(br.w2, 0, 0x0123), br.w1, sh);
+        uint32_t e = s_lut[base + ((hi >> 1) >> (31 - root))];
+        int len = (e >> 8) & 15;
+        if (e & 0x8000u) { // longer than the root: one second-level lookup covers the rest
+            const int w2 = (e >> 11) & 15;
+            e = s_lut[base + (e & 0x7ffu) + ((hi << root) >> (32 - w2))];
+            len = root + ((e >> 8) & 15);
         }
+        int x = (e >> 4) & 15, y = e & 15;
+        const uint32_t rest = __funnelshift_l(lo, hi, len);
+        const int lx = x == 15 ? lin : 0;
+        x += (int)((rest >> 1) >> (31 - lx));
+        int n = lx;
+        const int sx = x != 0;
+        if (((rest << n) >> 31) & sx) x = -x;
+        n += sx;
+        const int ly = y == 15 ? lin : 0;
+        y += (int)(((rest << n) >> 1) >> (31 - ly));
+        n += ly;
+        const int sy = y != 0;
+        if (((rest << n) >> 31) & sy) y = -y;
+        n += sy;
+        if (!act) { x = 0; y = 0; len = 0; n = 0; }
+        br.skip(len);
+        br.skip(n);
         push(x, y);
     }
     // count1 quadruples
     {
         const bool tab_b = (d.flags & L3F_C1TAB) != 0;
         int i = bv2;
-        while (!dead && i <= 572 && br.consumed < p23) {
-            br.refill();
+        while (!dead && i <= 572 && br.consumed() < p23) {
+            const uint32_t bits = br.peek32(); // code (<= 6 bits) + up to 4 sign bits
             int sym, len;
-            if (tab_b) { sym = 15 - (int)br.peek(4); len = 4; }
-            else { uint32_t e = s_quad[br.peek(6)]; sym = e & 15; len = e >> 4; }
-            br.skip(len);
-            const uint32_t s4 = br.peek(4);
+            if (tab_b) { sym = 15 - (int)(bits >> 28); len = 4; }
+            else { uint32_t e = s_quad[bits >> 26]; sym = e & 15; len = e >> 4; }
+            const uint32_t s4 = (bits << len) >> 28;
             int k = 0, v = 0, w = 0, x = 0, y = 0;
             if (sym & 8) { v = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
             if (sym & 4) { w = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
             if (sym & 2) { x = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
             if (sym & 1) { y = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
-            br.skip(k);
-            if (br.consumed > p23) break; // overran part2_3_length: discard this quadruple
+            br.skip(len + k);
+            if (br.consumed() > p23) break; // overran part2_3_length: discard this quadruple
             push(v, w);
             push(x, y);
             i += 4;

@@ -5,9 +5,9 @@
 
 #include <stdint.h>
 
-#define L3_HUFF_ROOT_BITS 8
-#define L3_HUFF_SUB_BITS 6
-#define L3_HUFF_LUT_MAX 6144 /* entries; actual size is computed at build time */
+#define L3_HUFF_ROOT_BITS 9
+#define L3_HUFF_SUB_BITS 10 /* one second level covers every code longer than the root */
+#define L3_HUFF_LUT_MAX 12288 /* entries; actual size is computed at build time */
 
 /* Huffman LUT entry (uint16):
  *   leaf : bit15 = 0, bits 11..8 = code bits consumed at this level, bits 7..0 = (x << 4) | y
