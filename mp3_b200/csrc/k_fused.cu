@@ -17,9 +17,9 @@
 //   S2  8 warps = 4 granules x 2 channels, lane = subband: alias butterflies by shuffle, 36-point
 //       IMDCT by its two symmetries (324 FFMA with immediate coefficients), window, frequency
 //       inversion                                                   -> F (first halves), H (second)
-//   S3  warp per (channel, slot): S = F + H(previous granule), one even/odd butterfly by shuffle
-//       (u = S[k] + S[31-k], v = S[k] - S[31-k]), then lane n: C[n] = sum_{k<16} (n even ? u : v)[k]
-//       cos(n(2k+1)pi/64) in place (the 64 "V" values of the standard are signed copies of C)
+//   S3  thread per (channel, slot): C[n] = sum_k S[k] cos(n(2k+1)pi/64) as an in-register fast DCT-II
+//       (304 operations, fast_dct.h), in place (the 64 "V" values of the standard are signed copies
+//       of C); rows have an odd stride so this lane = row pattern is bank-conflict free too
 //   S4  warp per (granule, channel), lane = sample j: the 16-tap window as a fully unrolled sliding
 //       accumulation over the 33 rows a granule touches (2 LDS per row instead of 16 per output);
 //       PCM is staged in shared memory and leaves the CTA as 16-byte stores
@@ -30,6 +30,7 @@
 #include <type_traits>
 
 #include "consts_gen.h"
+#include "fast_dct.h"
 #include "iso_tables.h"
 #include "kernels.h"
 #include "mp3b.h"
@@ -42,6 +43,7 @@ constexpr int KF_ROWS = 15 + KF_B * 18;
 constexpr int XROW = 19;        // padded subband row of X
 constexpr int XSZ = 32 * XROW;  // 608 floats per channel spectrum
 constexpr int KF_POW_LUT = 1024;
+constexpr int FS = 33;         // row stride of F: odd, so rows are conflict-free both by lane = column and lane = row
 
 __constant__ float f_pow2q[4];
 __constant__ float f_is_kl[7], f_is_kr[7];
@@ -49,7 +51,6 @@ __constant__ float f_lsf_pow[2][16];
 __constant__ float f_cs[8], f_ca[8];
 __constant__ uint8_t f_pretab[22];
 __constant__ float f_win[4][36];
-__device__ float f_dct32[16][32];  // [k][n], k < 16
 __device__ float f_synwin[16][32];
 
 struct GranMeta {
@@ -61,9 +62,9 @@ struct GranMeta {
 
 struct FusedShared {
     float X[KF_B][2][XSZ];          // spectra of the batch, padded rows; reused as PCM staging in S4
-    float F[2][KF_ROWS][32];        // rows 0..14: C history; rows 15..: first IMDCT halves -> S -> C
-    float Hc[2][18][32];            // second IMDCT half of the last granule of the previous batch
-    float dct[16][32], win[16][32]; // per-lane transform / window constants (copied from global once)
+    float F[2][KF_ROWS][FS];        // rows 0..14: C history; rows 15..: first IMDCT halves -> S -> C
+    __align__(16) float Hc[2][18][32]; // second IMDCT half of the last granule of the previous batch
+    float win[16][32];              // per-lane window taps (copied from global once)
     float pow43[KF_POW_LUT];        // |is|^(4/3) for the common small values
     float gain[KF_B][2][40];
     float kl[KF_B][40], kr[KF_B][40];
@@ -305,8 +306,8 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
             const float s_i = (i & 1) ? sgn : 1.f, s_m = ((17 - i) & 1) ? sgn : 1.f;
             float f0 = sa * w[i] * s_i, f1 = -sa * w[17 - i] * s_m;
             if (carry) { f0 += carry[i * 32 + lane]; f1 += carry[(17 - i) * 32 + lane]; }
-            Fdst[i * 32 + lane] = f0;
-            Fdst[(17 - i) * 32 + lane] = f1;
+            Fdst[i * FS + lane] = f0;
+            Fdst[(17 - i) * FS + lane] = f1;
             h[i] = sb * w[18 + i] * s_i;
             h[17 - i] = sb * w[35 - i] * s_m;
         }
@@ -330,9 +331,9 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
                 f1 += carry[(6 + i) * 32 + lane];
                 f2 += carry[(12 + i) * 32 + lane];
             }
-            Fdst[i * 32 + lane] = f0;
-            Fdst[(6 + i) * 32 + lane] = f1;
-            Fdst[(12 + i) * 32 + lane] = f2;
+            Fdst[i * FS + lane] = f0;
+            Fdst[(6 + i) * FS + lane] = f1;
+            Fdst[(12 + i) * FS + lane] = f2;
             h[i] = (y[1][6 + i] + y[2][i]) * s_i;
             h[6 + i] = y[2][6 + i] * s_i;
             h[12 + i] = 0.f;
@@ -355,7 +356,7 @@ __device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r
     for (int i = 0; i < 16; i++) acc[i] = 0.f;
 #pragma unroll
     for (int q = 0; q < 33; q++) {
-        const float e = Fc[(r0 + q) * 32 + src_e], o = Fc[(r0 + q) * 32 + src_o];
+        const float e = Fc[(r0 + q) * FS + src_e], o = Fc[(r0 + q) * FS + src_o];
 #pragma unroll
         for (int l = 0; l < 16; l++) {
             const int T = q + l - 15;
@@ -390,13 +391,10 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
     // history starts at zero (stream head, or about to be re-derived by the warm-up granules)
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = tid; i < 2 * 120; i += KF_THREADS) reinterpret_cast<float4 *>(&S.F[i / 120][0][0])[i % 120] = z;
+        for (int i = tid; i < 2 * 15 * FS; i += KF_THREADS) S.F[i / (15 * FS)][0][i % (15 * FS)] = 0.f;
         for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.Hc[i / 144][0][0])[i % 144] = z;
         for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) S.pow43[i] = pow43[i];
-        for (int i = tid; i < 512; i += KF_THREADS) {
-            (&S.dct[0][0])[i] = (&f_dct32[0][0])[i];
-            (&S.win[0][0])[i] = (&f_synwin[0][0])[i];
-        }
+        for (int i = tid; i < 512; i += KF_THREADS) (&S.win[0][0])[i] = (&f_synwin[0][0])[i];
         load_meta(S, tid, ubase, min(KF_B, total), nch, units);
         prefetch_units(S, tid, ubase, min(KF_B, total) * nch, is_in, sf_in);
     }
@@ -438,7 +436,7 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                 float *dst = gi + 1 < nb ? &S.F[c][15 + (gi + 1) * 18][0] : &S.Hc[c][0][0];
                 if (gi + 1 < nb) {
 #pragma unroll
-                    for (int t = 0; t < 18; t++) dst[t * 32 + lane] += h[t];
+                    for (int t = 0; t < 18; t++) dst[t * FS + lane] += h[t];
                 } else {
 #pragma unroll
                     for (int t = 0; t < 18; t++) dst[t * 32 + lane] = h[t];
@@ -449,33 +447,19 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         // next batch's descriptors can be fetched now (gm is dead until the next S1)
         if (b0 + KF_B < total)
             load_meta(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B), nch, units);
-        // ---- S3: overlap-add + 32-point transform, in place
+        // ---- S3: 32-point transform of every slot, in place; one thread per (channel, slot) row,
+        // the whole transform in registers (fast_dct.h: 304 operations instead of 1024 FMAs)
         {
-            float cn[16];
+            const int rows_c = nb * 18;
+            if (tid < nch * rows_c) {
+                const int c = tid >= rows_c ? 1 : 0;
+                float *row = &S.F[c][15 + tid - c * rows_c][0];
+                float x[32];
 #pragma unroll
-            for (int k = 0; k < 16; k++) cn[k] = S.dct[k][lane];
-        for (int c = 0; c < nch; c++)
-            for (int s = warp; s < nb * 18; s += KF_THREADS / 32) {
-                float *row = &S.F[c][15 + s][0];
-                const float v = row[lane];
-                const float p = __shfl_sync(0xffffffffu, v, 31 - lane);
-                // lanes 0..15 hold u[k] = S[k] + S[31-k]; lanes 16..31 hold v[31-lane] = S[31-lane] - S[lane]
-                __syncwarp();
-                if (lane < 16) row[lane] = v + p;
-                else row[47 - lane] = p - v;
-                __syncwarp();
-                const float4 *in = reinterpret_cast<const float4 *>(row + ((lane & 1) << 4));
-                float acc = 0.f;
+                for (int k = 0; k < 32; k++) x[k] = row[k];
+                L3Dct2<32>::run(x);
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float4 a = in[k];
-                    acc = fmaf(a.x, cn[4 * k], acc);
-                    acc = fmaf(a.y, cn[4 * k + 1], acc);
-                    acc = fmaf(a.z, cn[4 * k + 2], acc);
-                    acc = fmaf(a.w, cn[4 * k + 3], acc);
-                }
-                __syncwarp();
-                row[lane] = acc;
+                for (int k = 0; k < 32; k++) row[k] = x[k];
             }
         }
         __syncthreads();
@@ -504,9 +488,9 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                 uint4 *dstg = reinterpret_cast<uint4 *>(reinterpret_cast<pcm_t *>(pcm) + e0);
                 for (int i = tid; i < nvec; i += KF_THREADS) dstg[i] = src[i];
             }
-            for (int i = tid; i < 2 * 120; i += KF_THREADS) {
-                const int c = i / 120, k = i % 120;
-                reinterpret_cast<float4 *>(&S.F[c][0][0])[k] = reinterpret_cast<const float4 *>(&S.F[c][nb * 18][0])[k];
+            for (int i = tid; i < 2 * 15 * FS; i += KF_THREADS) {
+                const int c = i / (15 * FS), k = i % (15 * FS);
+                S.F[c][0][k] = S.F[c][nb * 18][k];
             }
         }
         __syncthreads();
@@ -553,9 +537,7 @@ void l3_fused_init(void)
     }
     cudaMemcpyToSymbol(f_win, W, sizeof W);
 
-    static float dct[16][32], win[16][32];
-    for (int k = 0; k < 16; k++)
-        for (int n = 0; n < 32; n++) dct[k][n] = (float)cos(n * (2 * k + 1) * M_PI / 64.0);
+    static float win[16][32];
     for (int l = 0; l < 16; l++)
         for (int j = 0; j < 32; j++) {
             const int i = l >> 1;
@@ -564,7 +546,6 @@ void l3_fused_init(void)
             else v = -l3_dwin(64 * i + 32 + j);
             win[l][j] = (float)v;
         }
-    cudaMemcpyToSymbol(f_dct32, dct, sizeof dct);
     cudaMemcpyToSymbol(f_synwin, win, sizeof win);
     const int smem = (int)sizeof(FusedShared);
     cudaFuncSetAttribute(k_backend<MP3B_PCM_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
