@@ -16,7 +16,6 @@
 
 #include "iso_tables.h"
 #include "kernels.h"
-#include "l3_side.h"
 #include "mp3b.h"
 
 namespace {
@@ -100,7 +99,7 @@ struct mp3b_ctx {
     L3DevTables T{};
 
     // per-batch device state
-    DevBuf d_raw, d_streams, d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm;
+    DevBuf d_raw, d_streams, d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_scratch;
     DevBuf d_is, d_sf, d_xr, d_imd, d_sb; // wave-sized intermediates
     PinBuf h_streams, h_frames, h_tiles, h_stage, h_counter;
 
@@ -174,7 +173,7 @@ int upload_tables(mp3b_ctx *ctx)
     return MP3B_OK;
 }
 
-// Host frame indexer (MP3B_INDEX_HOST): same walk as k_index_count + k_index_fill.
+// Host frame indexer (MP3B_INDEX_HOST): the same walk as k_index_walk, on host threads.
 void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRec> *out, uint32_t sidx)
 {
     uint32_t len = r->raw_len, p = l3_id3v2_len(buf, len), first = 0, first_off = 0, n = 0, payload = 0;
@@ -273,8 +272,9 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             host_index_stream(base + offsets[i], &hs[i], &host_frames[i], (uint32_t)i);
         });
     } else if (nstreams) {
+        CK(ctx->d_scratch.ensure(sizeof(L3FrameRec) * l3_index_scratch_records(raw_total, (uint64_t)nstreams)));
         CK(cudaMemcpyAsync(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
-        l3_launch_index_count(ctx->raw_dev, ctx->d_streams.as<L3StreamRec>(), nstreams, st);
+        l3_launch_index_walk(ctx->raw_dev, ctx->d_streams.as<L3StreamRec>(), nstreams, ctx->d_scratch.as<L3FrameRec>(), st);
         launches++;
         CK(cudaMemcpyAsync(hs, ctx->d_streams.p, sizeof(L3StreamRec) * nstreams, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st)); // the one host round trip: sizes of everything downstream
@@ -411,14 +411,12 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
                 memcpy(hf + hs[i].frame_base, host_frames[i].data(), host_frames[i].size() * sizeof(L3FrameRec));
         });
         if (frames) CK(cudaMemcpyAsync(df, hf, sizeof(L3FrameRec) * frames, cudaMemcpyHostToDevice, st));
-    } else if (nstreams) {
-        l3_launch_index_fill(ctx->raw_dev, ds, df, nstreams, st);
-        launches++;
     }
     L3UnitDesc *du = ctx->d_units.as<L3UnitDesc>();
     uint32_t *dg = ctx->d_gran.as<uint32_t>();
     if (frames) {
-        l3_launch_side_parse(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), st);
+        l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : ctx->d_scratch.as<L3FrameRec>(),
+                             (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), st);
         l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
         launches += 2;
     }
@@ -565,7 +563,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto *s : ctx->open_streams) delete s;
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw, &ctx->d_streams, &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_is, &ctx->d_sf, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_scratch, &ctx->d_is, &ctx->d_sf, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather})

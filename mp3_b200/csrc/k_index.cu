@@ -1,8 +1,9 @@
 // k_index.cu -- K0: device-side frame indexer (stages a1-a3 of SURVEY.md section 8).
 //
-//   index_count   thread per stream: walk the frame chain, count frames and main-data bytes
-//   index_fill    thread per stream: walk again, write one L3FrameRec per frame
-//   side_parse    thread per frame : side info -> unit descriptors (+ bit-reservoir offsets)
+//   index_walk    thread per stream: walk the frame chain once; count frames and main-data bytes and
+//                                    leave one L3FrameRec per frame in a scratch table
+//   side_parse    thread per frame : gather the record into the dense frame table;
+//                                    side info -> unit descriptors (+ bit-reservoir offsets)
 //   payload_copy  warp per frame   : compact the frames' main-data bytes into one arena so
 //                                    that every unit's bits are contiguous and addressable
 //
@@ -11,22 +12,44 @@
 // frame, and parallel across streams only.  Everything else is embarrassingly parallel.
 // No reference code exists for this stage (/root/reference/README.md:1-84).
 #include "kernels.h"
-#include "l3_side.h"
 
 namespace {
 
-__global__ void k_index_count(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Scratch slot of frame i of stream s: frames are at least 24 bytes long (MPEG-2 LSF, 8 kbit/s,
+// 24 kHz), so a stream of raw_len bytes starting at raw_off never needs more than raw_len / 24 + 1
+// slots, and raw_off / 24 + s is a collision-free base.
+__device__ __forceinline__ uint64_t scratch_base(const L3StreamRec &r, uint32_t s) { return r.raw_off / 24 + s; }
+
+// One walk per stream: counts frames and main-data bytes AND leaves one record per frame in the
+// scratch table, so that no second walk is needed once the host has turned the counts into bases.
+__global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams,
+                             L3FrameRec *__restrict__ scratch)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nstreams) return;
     L3StreamRec r = streams[s];
     const uint8_t *buf = raw + r.raw_off;
+    L3FrameRec *out = scratch + scratch_base(r, (uint32_t)s);
     uint32_t len = r.raw_len, p = l3_id3v2_len(buf, len), first = 0, first_off = 0, n = 0, payload = 0;
     while (p + 4 <= len) {
         L3Hdr h;
         uint32_t w;
         if (!l3_frame_at(buf, len, p, first, &h, &w)) { p++; continue; }
-        if (!first) { first = w; first_off = p; }
+        if (!first) {
+            first = w;
+            first_off = p;
+            for (int j = 1; j < 6; j++) // the chain is latency-bound: pull the next headers towards L2
+                if (p + (uint32_t)(j * h.frame_len) < len) prefetch_l2(buf + p + j * h.frame_len);
+        }
+        if (p + 6u * (uint32_t)h.frame_len < len) prefetch_l2(buf + p + 6 * h.frame_len);
+        L3FrameRec f;
+        f.rel_off = p;
+        f.payload_off = payload;
+        f.hdr = w;
+        f.stream = (uint32_t)s;
+        out[n] = f;
         n++;
         payload += (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
         p += (uint32_t)h.frame_len;
@@ -37,53 +60,156 @@ __global__ void k_index_count(const uint8_t *__restrict__ raw, L3StreamRec *__re
     streams[s].payload_len = payload;
 }
 
-__global__ void k_index_fill(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams,
-                             L3FrameRec *__restrict__ frames, int nstreams)
-{
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nstreams) return;
-    L3StreamRec r = streams[s];
-    if (!r.nframes) return;
-    const uint8_t *buf = raw + r.raw_off;
-    uint32_t len = r.raw_len, p = r.first_off, first = r.first_hdr, n = 0, payload = 0;
-    while (p + 4 <= len && n < r.nframes) {
-        L3Hdr h;
-        uint32_t w;
-        if (!l3_frame_at(buf, len, p, first, &h, &w)) { p++; continue; }
-        L3FrameRec f;
-        f.rel_off = p;
-        f.payload_off = payload;
-        f.hdr = w;
-        f.stream = (uint32_t)s;
-        frames[r.frame_base + n] = f;
-        n++;
-        payload += (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
-        p += (uint32_t)h.frame_len;
+// Sequential big-endian bit reader over unaligned bytes (side info is 9..32 bytes).
+struct SideBits {
+    const uint8_t *p, *end; // never reads at or beyond `end` (the end of the stream's bytes)
+    unsigned long long acc;
+    int n;
+    __device__ __forceinline__ uint32_t byte() { return p < end ? *p++ : (p++, 0u); }
+    __device__ __forceinline__ void init(const uint8_t *q, const uint8_t *e)
+    {
+        p = q;
+        end = e;
+        acc = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc = (acc << 8) | byte();
+        n = 64;
     }
-}
+    __device__ __forceinline__ uint32_t get(int k) // k in 1..16
+    {
+        if (n < 32) {
+            uint32_t w = byte() << 24;
+            w |= byte() << 16;
+            w |= byte() << 8;
+            w |= byte();
+            acc |= (unsigned long long)w << (32 - n);
+            n += 32;
+        }
+        uint32_t v = (uint32_t)(acc >> (64 - k));
+        acc <<= k;
+        n -= k;
+        return v;
+    }
+};
 
-__global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams,
-                             const L3FrameRec *__restrict__ frames, uint32_t nframes,
-                             const uint16_t *__restrict__ sfb_long, L3UnitDesc *__restrict__ units,
-                             uint32_t *__restrict__ gran_unit0, uint32_t *__restrict__ concealed)
+// Thread per frame: side info -> unit descriptors (a2, a3).  In gather mode (scratch != null) the
+// frame record is fetched from the walk's scratch table (stream found by binary search over the
+// frame bases) and also written to the dense frame table.
+__global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams, int nstreams,
+                             L3FrameRec *__restrict__ frames, const L3FrameRec *__restrict__ scratch,
+                             uint32_t nframes, const uint16_t *__restrict__ sfb_long_all,
+                             L3UnitDesc *__restrict__ units, uint32_t *__restrict__ gran_unit0,
+                             uint32_t *__restrict__ concealed)
 {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
-    L3FrameRec fr = frames[f];
-    L3StreamRec sr = streams[fr.stream];
+    L3FrameRec fr;
+    if (scratch) {
+        int lo = 0, hi = nstreams - 1; // last stream with frame_base <= f (empty streams share a base)
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (streams[mid].frame_base <= f) lo = mid;
+            else hi = mid - 1;
+        }
+        // skip back over empty streams that share this base
+        while (lo > 0 && streams[lo].nframes == 0) lo--;
+        const L3StreamRec &r = streams[lo];
+        fr = scratch[scratch_base(r, (uint32_t)lo) + (f - r.frame_base)];
+        frames[f] = fr;
+    } else
+        fr = frames[f];
+    const L3StreamRec sr = streams[fr.stream];
     L3Hdr h;
     l3_parse_hdr(fr.hdr, &h);
-    uint32_t fi = f - sr.frame_base; /* frame index inside its stream */
-    L3UnitDesc d[4];
-    int ok = l3_parse_side(raw + sr.raw_off + fr.rel_off, &h, sfb_long + h.sr_row * 23, sr.payload_base,
-                           fr.payload_off, fr.stream, fi == 0, d);
-    if (!ok) atomicAdd(concealed, 1u);
-    uint32_t u0 = sr.unit_base + fi * (uint32_t)(h.ngr * h.nch);
-    uint32_t g0 = sr.gran_base + fi * (uint32_t)h.ngr;
-    for (int i = 0; i < h.ngr * h.nch; i++) units[u0 + i] = d[i];
-    for (int gr = 0; gr < h.ngr; gr++)
-        gran_unit0[g0 + gr] = (u0 + (uint32_t)(gr * h.nch)) | (h.nch == 2 ? L3G_STEREO : 0u) |
+    const uint32_t fi = f - sr.frame_base; /* frame index inside its stream */
+    const uint16_t *sfb_long = sfb_long_all + h.sr_row * 23;
+    SideBits b;
+    b.init(raw + sr.raw_off + fr.rel_off + 4 + (h.crc ? 2 : 0), raw + sr.raw_off + sr.raw_len);
+    const int nch = h.nch, ngr = h.ngr;
+    uint32_t mdb, scfsi[2] = {0, 0};
+    if (!h.lsf) {
+        mdb = b.get(9);
+        b.get(nch == 1 ? 5 : 3);
+        for (int ch = 0; ch < nch; ch++) {
+            const uint32_t v = b.get(4); // scfsi bits for groups 0..3, first transmitted = group 0
+            scfsi[ch] = ((v >> 3) & 1) | (((v >> 2) & 1) << 1) | (((v >> 1) & 1) << 2) | ((v & 1) << 3);
+        }
+    } else {
+        mdb = b.get(8);
+        b.get(nch == 1 ? 1 : 2);
+    }
+    const int valid = mdb <= fr.payload_off;
+    if (!valid) atomicAdd(concealed, 1u);
+    uint64_t bit = valid ? (sr.payload_base + fr.payload_off - mdb) * 8ull : 0ull;
+    uint8_t hdrbits = (uint8_t)((h.lsf ? L3H_LSF : 0) | (h.sr_row << L3H_SR_SHIFT) | (nch == 2 ? L3H_STEREO : 0));
+    if (h.mode == 1) hdrbits |= (uint8_t)(((h.mode_ext & 2) ? L3H_MS : 0) | ((h.mode_ext & 1) ? L3H_IS : 0));
+    const uint32_t u0 = sr.unit_base + fi * (uint32_t)(ngr * nch);
+    const uint32_t g0 = sr.gran_base + fi * (uint32_t)ngr;
+    for (int gr = 0; gr < ngr; gr++) {
+        for (int ch = 0; ch < nch; ch++) {
+            L3UnitDesc d;
+            uint32_t p23 = b.get(12), bv = b.get(9), gg = b.get(8);
+            uint32_t sfc = b.get(h.lsf ? 9 : 4), ws = b.get(1);
+            uint32_t bt = 0, mixed = 0, t0, t1, t2 = 0, r0c = 0, r1c = 0, sbg0 = 0, sbg1 = 0, sbg2 = 0;
+            if (ws) {
+                const uint32_t v = b.get(13); // block_type 2, mixed 1, table_select 5 + 5
+                bt = v >> 11;
+                mixed = (v >> 10) & 1;
+                t0 = (v >> 5) & 31;
+                t1 = v & 31;
+                const uint32_t g3 = b.get(9);
+                sbg0 = g3 >> 6;
+                sbg1 = (g3 >> 3) & 7;
+                sbg2 = g3 & 7;
+            } else {
+                const uint32_t v = b.get(15);
+                t0 = v >> 10;
+                t1 = (v >> 5) & 31;
+                t2 = v & 31;
+                const uint32_t rc = b.get(7);
+                r0c = rc >> 3;
+                r1c = rc & 7;
+            }
+            uint32_t preflag = h.lsf ? 0 : b.get(1);
+            const uint32_t tail = b.get(2);
+            const uint32_t sfscale = tail >> 1, c1tab = tail & 1;
+            if (h.lsf && !((hdrbits & L3H_IS) && ch == 1) && sfc >= 500) preflag = 1;
+            if (bv > 288) bv = 288;
+            uint32_t bv2 = bv * 2, r1, r2;
+            if (ws) {
+                r1 = (bt == 2 || !h.lsf) ? 36 : 54;
+                r2 = 576;
+            } else {
+                uint32_t a = r0c + 1, c = r0c + r1c + 2;
+                if (a > 22) a = 22;
+                if (c > 22) c = 22;
+                r1 = sfb_long[a];
+                r2 = sfb_long[c];
+            }
+            if (r1 > bv2) r1 = bv2;
+            if (r2 > bv2) r2 = bv2;
+            d.bit_off = bit;
+            d.p23len = (uint16_t)(valid ? p23 : 0);
+            d.big_values = (uint16_t)(valid ? bv : 0);
+            d.r1 = (uint16_t)(valid ? r1 : 0);
+            d.r2 = (uint16_t)(valid ? r2 : 0);
+            d.sfc = (uint16_t)sfc;
+            d.global_gain = (uint8_t)gg;
+            d.tsel[0] = (uint8_t)t0; d.tsel[1] = (uint8_t)t1; d.tsel[2] = (uint8_t)t2;
+            d.sbg[0] = (uint8_t)sbg0; d.sbg[1] = (uint8_t)sbg1; d.sbg[2] = (uint8_t)sbg2;
+            d.flags = (uint8_t)(bt | (mixed ? L3F_MIXED : 0) | (preflag ? L3F_PREFLAG : 0) |
+                                (sfscale ? L3F_SFSCALE : 0) | (c1tab ? L3F_C1TAB : 0) |
+                                (valid ? L3F_VALID : 0) | (ws ? L3F_WS : 0));
+            d.hdr = hdrbits;
+            d.pos = (uint8_t)((gr ? L3P_GR : 0) | (ch ? L3P_CH : 0) | (scfsi[ch] << L3P_SCFSI_SHIFT) |
+                              ((fi == 0 && gr == 0) ? L3P_FIRST : 0));
+            d.stream = fr.stream;
+            units[u0 + gr * nch + ch] = d;
+            if (valid) bit += p23;
+        }
+        gran_unit0[g0 + gr] = (u0 + (uint32_t)(gr * nch)) | (nch == 2 ? L3G_STEREO : 0u) |
                               ((fi == 0 && gr == 0) ? L3G_FIRST : 0u);
+    }
 }
 
 // One warp per frame; byte-granular because source and destination have arbitrary alignment.
@@ -104,24 +230,18 @@ __global__ void k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRe
 
 } // namespace
 
-void l3_launch_index_count(const uint8_t *raw, L3StreamRec *streams, int nstreams, cudaStream_t st)
+void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *scratch, cudaStream_t st)
 {
     if (nstreams <= 0) return;
-    k_index_count<<<(nstreams + 63) / 64, 64, 0, st>>>(raw, streams, nstreams);
+    k_index_walk<<<(nstreams + 31) / 32, 32, 0, st>>>(raw, streams, nstreams, scratch);
 }
-void l3_launch_index_fill(const uint8_t *raw, const L3StreamRec *streams, L3FrameRec *frames, int nstreams,
-                          cudaStream_t st)
-{
-    if (nstreams <= 0) return;
-    k_index_fill<<<(nstreams + 63) / 64, 64, 0, st>>>(raw, streams, frames, nstreams);
-}
-void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
-                          uint32_t nframes, const L3DevTables &T, L3UnitDesc *units, uint32_t *gran_unit0,
-                          uint32_t *concealed_counter, cudaStream_t st)
+void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
+                          const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,
+                          uint32_t *gran_unit0, uint32_t *concealed_counter, cudaStream_t st)
 {
     if (!nframes) return;
-    k_side_parse<<<(nframes + 127) / 128, 128, 0, st>>>(raw, streams, frames, nframes, T.sfb_long, units,
-                                                        gran_unit0, concealed_counter);
+    k_side_parse<<<(nframes + 127) / 128, 128, 0, st>>>(raw, streams, nstreams, frames, scratch, nframes, T.sfb_long,
+                                                        units, gran_unit0, concealed_counter);
 }
 void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
                             uint32_t nframes, uint8_t *arena, cudaStream_t st)

@@ -20,12 +20,17 @@ struct L3DevTables {
 };
 
 /* K0: device frame indexer (a1-a3) */
-void l3_launch_index_count(const uint8_t *raw, L3StreamRec *streams, int nstreams, cudaStream_t st);
-void l3_launch_index_fill(const uint8_t *raw, const L3StreamRec *streams, L3FrameRec *frames, int nstreams,
+/* scratch: at least l3_index_scratch_records(raw_total, nstreams) records */
+static inline uint64_t l3_index_scratch_records(uint64_t raw_total, uint64_t nstreams)
+{
+    return raw_total / 24 + 2 * nstreams + 2;
+}
+void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *scratch,
                           cudaStream_t st);
-void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
-                          uint32_t nframes, const L3DevTables &T, L3UnitDesc *units, uint32_t *gran_unit0,
-                          uint32_t *concealed_counter, cudaStream_t st);
+/* scratch == NULL: `frames` is already dense (host indexer) */
+void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
+                          const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,
+                          uint32_t *gran_unit0, uint32_t *concealed_counter, cudaStream_t st);
 void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
                             uint32_t nframes, uint8_t *arena, cudaStream_t st);
 
