@@ -229,8 +229,12 @@ __device__ __forceinline__ int reorder_dst(const L3BandTables *__restrict__ band
 }
 
 // ---- S1c: requantise + stereo + reorder, one (granule, line) per item -----------------------------
+// `bq` holds this thread's nine long-block band indices (lines t64 + 64 q), one byte each: they
+// depend only on the stream's sample rate, so the common case (both channels long blocks, no
+// intensity stereo) needs no table lookups, no reorder and no branches per line.
 __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, int nch,
-                                              const L3BandTables *__restrict__ bands, const float *__restrict__ pow43)
+                                              const L3BandTables *__restrict__ bands, const float *__restrict__ pow43,
+                                              const uint32_t (&bq)[3])
 {
     constexpr int ITEMS = 576 / 64; // 9 lines per thread: 64 threads per granule
     const float isq2 = 0.70710678118654752440f;
@@ -238,6 +242,29 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
     if (gi >= nb) return;
     const GranMeta &m = S.gm[gi];
     const int row = m.row, lay0 = m.lay[0], lay1 = m.lay[1];
+    if (nch == 2 && (lay0 | lay1) == 0 && !m.ist) {
+        const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
+        const int16_t *s0 = S.is_buf[gi * 2], *s1 = S.is_buf[gi * 2 + 1];
+        float *X0 = S.X[gi][0], *X1 = S.X[gi][1];
+        const bool ms = m.ms != 0;
+        int v0[ITEMS], v1[ITEMS];
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) { v0[q] = s0[t64 + 64 * q]; v1[q] = s1[t64 + 64 * q]; }
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) {
+            const int b = (bq[q >> 2] >> (8 * (q & 3))) & 0xff;
+            const int m0 = abs(v0[q]), m1 = abs(v1[q]);
+            const float p0 = m0 < KF_POW_LUT ? S.pow43[m0] : __ldg(pow43 + m0);
+            const float p1 = m1 < KF_POW_LUT ? S.pow43[m1] : __ldg(pow43 + m1);
+            float l = __int_as_float(__float_as_int(p0 * g0[b]) | (v0[q] & 0x80000000));
+            float r = __int_as_float(__float_as_int(p1 * g1[b]) | (v1[q] & 0x80000000));
+            if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
+            const int xp = xpad(t64 + 64 * q);
+            X0[xp] = l;
+            X1[xp] = r;
+        }
+        return;
+    }
     int v0[ITEMS], v1[ITEMS];
 #pragma unroll
     for (int q = 0; q < ITEMS; q++) {
@@ -403,6 +430,13 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
     const int src_e = lane <= 15 ? 16 + lane : (lane == 16 ? 0 : 48 - lane);
     const int src_o = lane <= 16 ? 16 - lane : lane - 16;
     pcm_t *stage = reinterpret_cast<pcm_t *>(&S.X[0][0][0]);
+    uint32_t bq[3] = {0, 0, 0}; // long-block band index of this thread's nine lines (see stage_requant)
+    {
+        const int row0 = (units[ubase].hdr >> L3H_SR_SHIFT) & 7;
+#pragma unroll
+        for (int q = 0; q < 9; q++)
+            bq[q >> 2] |= (uint32_t)bands->line2band[row0][0][(tid & 63) + 64 * q] << (8 * (q & 3));
+    }
 
     for (int b0 = 0; b0 < total; b0 += KF_B) {
         const int nb = min(KF_B, total - b0);
@@ -418,7 +452,7 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                 stage_intensity(S, tid >> 6, (tid >> 6) * nch + 1, bands);
             __syncthreads();
         }
-        stage_requant(S, tid, nb, nch, bands, pow43);
+        stage_requant(S, tid, nb, nch, bands, pow43, bq);
         __syncthreads();
         // is_buf / sf_buf are consumed: start fetching the next batch behind S2..S5
         if (b0 + KF_B < total)
