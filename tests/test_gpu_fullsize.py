@@ -1,0 +1,129 @@
+"""Parity at BASELINE.json's full sizes, through size-independent properties and oracle samples.
+
+  cfg2 (1024 x 383 frames), cfg3 (320 kbit/s joint stereo, switching windows, reservoir), cfg4 (LSF +
+  VBR + mono/stereo mix): a sample of streams against the oracle over their full length (ISO 11172-4),
+  every stream's length / rate / channel count, and
+  * replication: the same stream at different batch positions decodes to identical PCM;
+  * linearity: lowering every global_gain by 4 halves the float PCM exactly (requantiser gain is a
+    power of two, all later stages are linear);
+  * corruption: bit flips and truncation never fault the device, sizes stay consistent.
+"""
+import numpy as np
+import pytest
+
+import l3util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mp3b():
+    import mp3_b200
+    mp3_b200.load_library()
+    return mp3_b200
+
+
+def _check_sample(mp3b, oracle_mod, streams, pick, fmt_tol=True):
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
+        dec.decode_batch(streams)
+        arena = dec.fetch_pcm()
+        infos = [dec.stream_info(i) for i in range(len(streams))]
+        for i in pick:
+            ref = oracle_mod.decode(streams[i])
+            got = dec.stream_pcm(i, arena).astype(np.float64)
+            assert got.shape == ref.pcm.T.shape, i
+            l3util.assert_iso_full_accuracy(got, ref.pcm.T, "stream %d" % i)
+        st = dec.stats()
+    return infos, st
+
+
+@pytest.mark.parametrize("name,nstreams", [("cfg2", 1024), ("cfg3", 1024), ("cfg4", 1024)])
+def test_full_workloads_against_oracle_samples(name, nstreams, mp3b, synth_mod, oracle_mod):
+    streams = synth_mod.make_workload(name, nstreams)
+    pick = [0, 1, 2, 3, 4, 5, nstreams // 2, nstreams // 2 + 1, nstreams - 2, nstreams - 1]
+    infos, st = _check_sample(mp3b, oracle_mod, streams, pick)
+    assert st.streams == nstreams and st.concealed_frames == 0
+    for inf, s in zip(infos, streams):
+        assert inf.frames == 383
+    if name == "cfg2":
+        assert st.units == 1568768 and all(i.channels == 2 and i.sample_rate == 44100 for i in infos)
+    if name == "cfg4":
+        assert {i.sample_rate for i in infos} == {22050, 24000, 44100}
+        assert {i.channels for i in infos} == {1, 2}
+
+
+def test_replicated_streams_decode_identically(mp3b, synth_mod):
+    base = synth_mod.make_workload("cfg3", 8, 200)
+    streams = [base[i % 8] for i in range(512)]
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16) as dec:
+        dec.decode_batch(streams)
+        arena = dec.fetch_pcm()
+        first = [dec.stream_pcm(i, arena).copy() for i in range(8)]
+        for i in range(8, 512, 37):
+            assert np.array_equal(dec.stream_pcm(i, arena), first[i % 8]), i
+
+
+def _lower_gain(stream, delta):
+    """Return a copy of an MPEG-1 stereo/mono Layer III stream with every global_gain lowered by delta."""
+    out = bytearray(stream)
+    p = 0
+    for f in l3util.split_frames(stream):
+        mono = (f[3] >> 6) == 3
+        crc = 0 if (f[1] & 1) else 2
+        base = (p + 4 + crc) * 8
+        hdr_bits = 9 + (5 if mono else 3) + (4 if mono else 8)
+        for u in range(2 if mono else 4):
+            pos = base + hdr_bits + 59 * u + 21
+            v = 0
+            for k in range(8):
+                v = (v << 1) | ((out[(pos + k) >> 3] >> (7 - ((pos + k) & 7))) & 1)
+            v = max(v - delta, 0)
+            for k in range(8):
+                bit = (v >> (7 - k)) & 1
+                idx, sh = (pos + k) >> 3, 7 - ((pos + k) & 7)
+                out[idx] = (out[idx] & ~(1 << sh)) | (bit << sh)
+        p += len(f)
+    return bytes(out)
+
+
+def test_gain_linearity_is_exact(mp3b, synth_mod):
+    streams = synth_mod.make_workload("cfg3", 16, 100)
+    half = [_lower_gain(s, 4) for s in streams]
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
+        dec.decode_batch(streams)
+        a = dec.fetch_pcm().copy()
+        dec.decode_batch(half)
+        b = dec.fetch_pcm().copy()
+    assert a.shape == b.shape and np.abs(a).max() > 1e-3
+    assert np.array_equal(b * 2.0, a)
+
+
+def test_corrupted_streams_never_fault(mp3b, synth_mod):
+    rng = np.random.default_rng(20261018)
+    base = synth_mod.make_workload("cfg3", 8, 60) + synth_mod.make_workload("cfg4", 9, 60)
+    bad = []
+    for s in base:
+        a = np.frombuffer(s, np.uint8).copy()
+        for _ in range(6):                       # bit flips anywhere (headers, side info, main data)
+            b = a.copy()
+            idx = rng.integers(0, b.size, 40)
+            b[idx] ^= (1 << rng.integers(0, 8, 40)).astype(np.uint8)
+            bad.append(b.tobytes())
+        bad.append(a[: rng.integers(1, a.size)].tobytes())          # truncation
+        bad.append(a[rng.integers(1, 500):].tobytes())               # lost head
+        bad.append(rng.integers(0, 256, 3000, dtype=np.uint8).tobytes())  # noise
+        bad.append(bytes([0xFF, 0xFB, 0x90, 0x00]) * 200)            # headers only
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
+        for _ in range(2):
+            dec.decode_batch(bad)
+            arena = dec.fetch_pcm()
+            assert np.all(np.isfinite(arena))
+            tot = 0
+            for i in range(len(bad)):
+                inf = dec.stream_info(i)
+                assert inf.pcm_offset == tot
+                tot += inf.samples * inf.channels
+            assert tot == arena.size
+        good = synth_mod.make_stream(nframes=8, seed=3)
+        dec.decode_batch([good])               # the context is still healthy afterwards
+        assert dec.stream_info(0).frames == 8
