@@ -15,8 +15,9 @@
 //       MS / intensity stereo, short-block reorder                  -> X  (padded rows of 19)
 //       (intensity decisions need the right channel's zero bands first: a short pre-pass)
 //   S2  8 warps = 4 granules x 2 channels, lane = subband: alias butterflies by shuffle, 36-point
-//       IMDCT by its two symmetries (324 FFMA with immediate coefficients), window, frequency
-//       inversion                                                   -> F (first halves), H (second)
+//       IMDCT as an in-register fast 18-point DCT-IV (fast_imdct.h, ~170 operations instead of 648
+//       multiply-adds), window, frequency inversion; first halves -> F, second halves stay in
+//       registers and are added to the next granule's rows (overlap-add)
 //   S3  thread per (channel, slot): C[n] = sum_k S[k] cos(n(2k+1)pi/64) as an in-register fast DCT-II
 //       (304 operations, fast_dct.h), in place (the 64 "V" values of the standard are signed copies
 //       of C); rows have an odd stride so this lane = row pattern is bank-conflict free too
@@ -31,6 +32,7 @@
 
 #include "consts_gen.h"
 #include "fast_dct.h"
+#include "fast_imdct.h"
 #include "iso_tables.h"
 #include "kernels.h"
 #include "mp3b.h"
@@ -321,14 +323,11 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
     const float sgn = (lane & 1) ? -1.f : 1.f; // frequency inversion: odd subband, odd slot
     if (bt != 2) {
         const float *w = f_win[bt];
+        float Z[18];
+        l3_dct4_18(x, Z); // the 18 distinct IMDCT values (fast_imdct.h)
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            float sa = 0.f, sb = 0.f;
-#pragma unroll
-            for (int k = 0; k < 18; k++) {
-                sa = fmaf(x[k], K36A[i][k], sa);
-                sb = fmaf(x[k], K36B[i][k], sb);
-            }
+            const float sa = Z[9 + i], sb = -Z[8 - i];
             // out[i] = sa, out[17-i] = -sa, out[18+i] = sb, out[35-i] = sb
             const float s_i = (i & 1) ? sgn : 1.f, s_m = ((17 - i) & 1) ? sgn : 1.f;
             float f0 = sa * w[i] * s_i, f1 = -sa * w[17 - i] * s_m;

@@ -34,6 +34,39 @@ int main() {
 '''
 
 
+SRC_IMDCT = r'''
+#include <cstdio>
+#include <cmath>
+#include <cstdlib>
+#include "fast_imdct.h"
+int main() {
+    double worst = 0; srand(3);
+    for (int t = 0; t < 2000; t++) {
+        float X[18], Z[18]; double xd[18], peak = 1e-30, ref[18];
+        for (int k = 0; k < 18; k++) { X[k] = (float)((rand() / (double)RAND_MAX - 0.5) * 2); xd[k] = X[k]; }
+        for (int n = 0; n < 18; n++) {
+            double s = 0;
+            for (int k = 0; k < 18; k++) s += xd[k] * cos(M_PI / 72 * (2 * n + 1) * (2 * k + 1));
+            ref[n] = s; if (fabs(s) > peak) peak = fabs(s);
+        }
+        l3_dct4_18(X, Z);
+        for (int n = 0; n < 18; n++) { double e = fabs(Z[n] - ref[n]) / peak; if (e > worst) worst = e; }
+    }
+    printf("%g\\n", worst);
+    return worst < 2e-6 ? 0 : 1;
+}
+'''
+
+
+def test_fast_dct4_18_matches_definition(tmp_path):
+    src = tmp_path / "i.cpp"
+    src.write_text(SRC_IMDCT)
+    exe = tmp_path / "i"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "mp3_b200", "csrc"), "-o", str(exe), str(src)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+
+
 def test_fast_dct_matches_definition(tmp_path):
     src = tmp_path / "t.cpp"
     src.write_text(SRC)
