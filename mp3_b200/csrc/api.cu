@@ -100,7 +100,7 @@ struct mp3b_ctx {
 
     // per-batch device state
     DevBuf d_raw, d_streams, d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_scratch;
-    DevBuf d_is, d_sf, d_xr, d_imd, d_sb; // wave-sized intermediates
+    DevBuf d_is, d_sf, d_nzv, d_xr, d_imd, d_sb; // wave-sized intermediates
     PinBuf h_streams, h_frames, h_tiles, h_stage, h_counter;
 
     const uint8_t *raw_dev = nullptr; // d_raw or the caller's device buffer
@@ -387,6 +387,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     }
     CK(ctx->d_is.ensure(max_wave_units * 576 * sizeof(int16_t)));
     CK(ctx->d_sf.ensure(max_wave_units * 40));
+    CK(ctx->d_nzv.ensure(max_wave_units + 16));
     if (!fused) {
         CK(ctx->d_xr.ensure(max_wave_units * 576 * sizeof(float)));
         CK(ctx->d_imd.ensure(max_wave_units * 1152 * sizeof(float)));
@@ -438,7 +439,9 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         float *xr = ctx->d_xr.as<float>() - (size_t)u_lo * 576;
         float *imd = ctx->d_imd.as<float>() - (size_t)u_lo * 1152;
         float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
-        l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, ctx->T, is, sf, st);
+        uint8_t *nzv = ctx->d_nzv.as<uint8_t>() - (size_t)u_lo;
+        l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, ctx->T, is, sf, nzv,
+                                (!fused || keep) ? 1 : 0, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
         auto wave_done = [&]() -> int {
             if (!sink) return MP3B_OK;
@@ -455,7 +458,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             return MP3B_OK;
         };
         if (fused) {
-            l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, ctx->T,
+            l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
                               ctx->d_pcm.p, ctx->opts.pcm_format, st);
             if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
             launches += 2;
@@ -563,7 +566,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto *s : ctx->open_streams) delete s;
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw, &ctx->d_streams, &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_scratch, &ctx->d_is, &ctx->d_sf, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_scratch, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather})

@@ -101,12 +101,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Start fetching the Huffman output (1152 B / unit) and scalefactors (40 B / unit) of `n` consecutive
 // units into shared memory; the caller waits (cp_async_wait_all + barrier) before reading them.
+// Only the vectors that hold data are fetched (nzv_in[u] of the 72 per unit); the all-zero tail of
+// each spectrum is never written by the Huffman kernel nor read here: it is zeroed in place.
 __device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t u_first, int n,
-                                               const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in)
+                                               const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
+                                               const uint8_t *__restrict__ nzv_in)
 {
     const char *gi = reinterpret_cast<const char *>(is_in + (size_t)u_first * 576);
     char *si = reinterpret_cast<char *>(&S.is_buf[0][0]);
-    for (int i = tid; i < n * 72; i += KF_THREADS) cp_async16(si + i * 16, gi + i * 16);
+    for (int i = tid; i < n * 72; i += KF_THREADS) {
+        const int unit = i / 72, v = i - unit * 72;
+        if (v < (int)nzv_in[u_first + unit]) cp_async16(si + i * 16, gi + i * 16);
+        else *reinterpret_cast<uint4 *>(si + i * 16) = make_uint4(0, 0, 0, 0);
+    }
     const char *gs = reinterpret_cast<const char *>(sf_in + (size_t)u_first * 40);
     char *ss = reinterpret_cast<char *>(&S.sf_buf[0][0]);
     for (int i = tid; i < n * 5; i += KF_THREADS) cp_async8(ss + i * 8, gs + i * 8);
@@ -399,7 +406,8 @@ template <int FMT>
 __global__ void __launch_bounds__(KF_THREADS, 3)
 k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
           const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
-          const L3BandTables *__restrict__ bands, const float *__restrict__ pow43, void *__restrict__ pcm)
+          const uint8_t *__restrict__ nzv_in, const L3BandTables *__restrict__ bands,
+          const float *__restrict__ pow43, void *__restrict__ pcm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedShared &S = *reinterpret_cast<FusedShared *>(smem_raw);
@@ -422,7 +430,7 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) S.pow43[i] = pow43[i];
         for (int i = tid; i < 512; i += KF_THREADS) (&S.win[0][0])[i] = (&f_synwin[0][0])[i];
         load_meta(S, tid, ubase, min(KF_B, total), nch, units);
-        prefetch_units(S, tid, ubase, min(KF_B, total) * nch, is_in, sf_in);
+        prefetch_units(S, tid, ubase, min(KF_B, total) * nch, is_in, sf_in, nzv_in);
     }
     __syncthreads();
 
@@ -455,7 +463,8 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         __syncthreads();
         // is_buf / sf_buf are consumed: start fetching the next batch behind S2..S5
         if (b0 + KF_B < total)
-            prefetch_units(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B) * nch, is_in, sf_in);
+            prefetch_units(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B) * nch, is_in, sf_in,
+                           nzv_in);
         // ---- S2: alias + IMDCT; second halves travel in registers to the next granule's rows
         {
             const int gi = warp >> 1, c = warp & 1;
@@ -586,15 +595,15 @@ void l3_fused_init(void)
 }
 
 void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const L3UnitDesc *units,
-                       const int16_t *is_in, const uint8_t *sf_in, const L3DevTables &T, void *pcm, int pcm_format,
-                       cudaStream_t st)
+                       const int16_t *is_in, const uint8_t *sf_in, const uint8_t *nzv_in, const L3DevTables &T,
+                       void *pcm, int pcm_format, cudaStream_t st)
 {
     if (!ntiles) return;
     const size_t smem = sizeof(FusedShared);
     if (pcm_format == MP3B_PCM_S16)
         k_backend<MP3B_PCM_S16><<<ntiles, KF_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
-                                                                  T.bands, T.pow43, pcm);
+                                                                  nzv_in, T.bands, T.pow43, pcm);
     else
         k_backend<MP3B_PCM_F32><<<ntiles, KF_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
-                                                                  T.bands, T.pow43, pcm);
+                                                                  nzv_in, T.bands, T.pow43, pcm);
 }

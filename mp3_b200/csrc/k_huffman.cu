@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(K1_THREADS)
 k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitDesc *__restrict__ units,
           uint32_t u_lo, uint32_t nunits, const uint16_t *__restrict__ g_lut, uint32_t lut_len,
           const L3HuffInfo *__restrict__ g_info, const uint8_t *__restrict__ g_quad,
-          int16_t *__restrict__ is_out, uint8_t *__restrict__ sf_out)
+          int16_t *__restrict__ is_out, uint8_t *__restrict__ sf_out, uint8_t *__restrict__ nzv_out, int zero_fill)
 {
     extern __shared__ uint16_t s_lut[];
     __shared__ uint32_t s_info[32]; // base | root << 16 | linbits << 24
@@ -307,21 +307,26 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
             i += 4;
         }
     }
-    // flush the partial vector, then zero the rest of the 576 lines
+    // flush the partial vector (zero padded).  The all-zero tail of the spectrum is not written:
+    // nzv_out[u] tells the consumer how many 16-byte vectors (8 lines each) hold data, and it treats
+    // the rest as zero.  zero_fill (staged pipeline, parity dumps) writes the tail anyway.
     if (npairs) {
         while (npairs) push(0, 0);
     }
-    for (int k = nst; k < 72; k++) out[k] = make_uint4(0, 0, 0, 0);
+    nzv_out[u] = (uint8_t)nst;
+    if (zero_fill)
+        for (int k = nst; k < 72; k++) out[k] = make_uint4(0, 0, 0, 0);
 }
 
 } // namespace
 
 void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
                              uint32_t nunits, const L3DevTables &T, int16_t *is_out, uint8_t *sf_out,
-                             cudaStream_t st)
+                             uint8_t *nzv_out, int zero_fill, cudaStream_t st)
 {
     if (!nunits) return;
     size_t smem = (size_t)T.huff_lut_len * sizeof(uint16_t);
     k_huffman<<<(nunits + K1_THREADS - 1) / K1_THREADS, K1_THREADS, smem, st>>>(
-        arena, arena_bytes, units, u_lo, nunits, T.huff_lut, T.huff_lut_len, T.huff, T.quad_a, is_out, sf_out);
+        arena, arena_bytes, units, u_lo, nunits, T.huff_lut, T.huff_lut_len, T.huff, T.quad_a, is_out, sf_out,
+        nzv_out, zero_fill);
 }

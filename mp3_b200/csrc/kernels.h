@@ -39,7 +39,8 @@ void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, cons
 /* units [u_lo, u_lo + nunits); output arrays are indexed by absolute unit id */
 void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
                              uint32_t nunits, const L3DevTables &T, int16_t *is_out, uint8_t *sf_out,
-                             cudaStream_t st);
+                             uint8_t *nzv_out /* [unit]: 16-byte vectors of is_out that hold data */,
+                             int zero_fill /* also write the all-zero tail */, cudaStream_t st);
 
 /* K2: requantise + stereo + reorder + alias reduction (a6-a8) */
 /* granules [g_lo, g_lo + ngranules) */
@@ -67,7 +68,7 @@ void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_u
  * warm-up granules before it (0..2) that re-derive the overlap / synthesis state, 0}. */
 void l3_fused_init(void);
 void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const L3UnitDesc *units,
-                       const int16_t *is_in, const uint8_t *sf_in, const L3DevTables &T, void *pcm, int pcm_format,
-                       cudaStream_t st);
+                       const int16_t *is_in, const uint8_t *sf_in, const uint8_t *nzv_in, const L3DevTables &T,
+                       void *pcm, int pcm_format, cudaStream_t st);
 
 #endif
