@@ -76,6 +76,7 @@ typedef struct mp3b_stream_info {
     int64_t samples;        /* per channel */
     int64_t concealed_frames;
     int64_t pcm_offset;     /* element offset of this stream's PCM in the batch PCM arena */
+    int64_t total_samples;  /* stream interface: samples per channel emitted since mp3b_stream_open */
 } mp3b_stream_info;
 
 typedef struct mp3b_stats {
@@ -130,7 +131,12 @@ int mp3b_get_stats(const mp3b_ctx *ctx, mp3b_stats *st);
  * host_dst = NULL removes the sink.  A too-small sink makes the decode call fail with TRUNCATED. */
 int mp3b_set_pcm_sink(mp3b_ctx *ctx, void *host_dst, uint64_t cap_elems);
 
-/* ---- stream interface (open / enqueue / decode / fetch) ------------------------------------- */
+/* ---- stream interface (open / enqueue / decode / fetch) -------------------------------------
+ * Incremental: bytes may be enqueued in pieces of any size; each mp3b_decode() decodes the frames
+ * completed since the previous call (for every open stream, as one batch) and mp3b_stream_fetch_pcm
+ * returns exactly their samples -- concatenated over the calls, the PCM equals a one-shot decode of
+ * the whole stream.  PCM of a call that is not fetched before the next mp3b_decode() is dropped.
+ * frames / samples in mp3b_stream_info describe the last call, total_samples the stream's life. */
 int mp3b_stream_open(mp3b_ctx *ctx, mp3b_stream **out);
 void mp3b_stream_close(mp3b_stream *s);
 /* Appends raw MP3 bytes; the library copies, the caller may free its buffer on return. */

@@ -36,7 +36,8 @@ class Opts(ctypes.Structure):
 class StreamInfo(ctypes.Structure):
     _fields_ = [("sample_rate", ctypes.c_int32), ("channels", ctypes.c_int32), ("lsf", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("frames", ctypes.c_int64), ("samples", ctypes.c_int64),
-                ("concealed_frames", ctypes.c_int64), ("pcm_offset", ctypes.c_int64)]
+                ("concealed_frames", ctypes.c_int64), ("pcm_offset", ctypes.c_int64),
+                ("total_samples", ctypes.c_int64)]
 
 
 class Stats(ctypes.Structure):
@@ -146,7 +147,9 @@ class Stream:
 
     def info(self):
         inf = StreamInfo()
-        self.dec._ck(self.dec.L.mp3b_stream_get_info(self.h, ctypes.byref(inf)))
+        rc = self.dec.L.mp3b_stream_get_info(self.h, ctypes.byref(inf))
+        if rc not in (0, -2):  # -2: no frame seen yet
+            self.dec._ck(rc)
         return inf
 
     def fetch(self, max_samples):

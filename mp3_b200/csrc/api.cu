@@ -76,9 +76,14 @@ enum { EV_START = 0, EV_INDEX, EV_HUFF, EV_REQ, EV_IMDCT, EV_OVL, EV_SYNTH, EV_E
 
 struct mp3b_stream {
     mp3b_ctx *ctx;
+    // bytes not yet retired: `ctx_frames` frames that were already output (kept so that the next call can
+    // re-derive the bit reservoir, the overlap-add half and the synthesis history), then new bytes
     std::vector<uint8_t> pending;
-    int batch_index = -1; // index in the last mp3b_decode() batch
-    size_t cursor = 0;    // samples per channel already fetched
+    uint32_t ctx_frames = 0;
+    uint32_t first_hdr = 0;      // the stream's first header once seen (identity for the sync search)
+    int batch_index = -1;        // index in the last mp3b_decode() batch
+    size_t cursor = 0;           // samples per channel of the last decode already fetched
+    int64_t total_samples = 0;   // samples per channel emitted over the stream's life
 };
 
 struct mp3b_ctx {
@@ -113,6 +118,8 @@ struct mp3b_ctx {
     bool have_batch = false, timed = false;
     mp3b_stats stats{};
     std::vector<mp3b_stream *> open_streams;
+    bool stream_batch_pending = false; // mp3b_decode() issued, per-stream bookkeeping not done yet
+    PinBuf h_frames_out;
     PinBuf h_gather;
     std::vector<uint64_t> gather_offsets;
 };
@@ -176,12 +183,19 @@ int upload_tables(mp3b_ctx *ctx)
 // Host frame indexer (MP3B_INDEX_HOST): the same walk as k_index_walk, on host threads.
 void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRec> *out, uint32_t sidx)
 {
-    uint32_t len = r->raw_len, p = l3_id3v2_len(buf, len), first = 0, first_off = 0, n = 0, payload = 0;
+    uint32_t len = r->raw_len, p = l3_id3v2_len(buf, len), first = r->first_hdr, first_off = 0, n = 0, payload = 0;
+    uint32_t end_off = p;
+    const bool streaming = (r->flags & L3S_STREAMING) != 0;
     while (p + 4 <= len) {
         L3Hdr h;
         uint32_t w;
-        if (!l3_frame_at(buf, len, p, first, &h, &w)) { p++; continue; }
-        if (!first) { first = w; first_off = p; }
+        const int fa = l3_frame_at(buf, len, p, first, &h, &w);
+        if (fa != 1) {
+            if (fa == 2 && streaming) break;
+            p++;
+            continue;
+        }
+        if (n == 0) { first = first ? first : w; first_off = p; }
         L3FrameRec f;
         f.rel_off = p;
         f.payload_off = payload;
@@ -191,7 +205,9 @@ void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRe
         n++;
         payload += (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
         p += (uint32_t)h.frame_len;
+        end_off = p;
     }
+    r->end_off = end_off;
     r->first_off = first_off;
     r->first_hdr = first;
     r->nframes = n;
@@ -224,8 +240,15 @@ template <class F> void parallel_for(int nthreads, size_t n, F f)
     for (auto &t : th) t.join();
 }
 
+// Per-stream hints of the incremental (open / enqueue / decode / fetch) interface.
+struct StreamHint {
+    uint32_t skip_frames; // leading frames already output by an earlier call: decoded for state only
+    uint32_t first_hdr;   // the stream's first header, once known (stream identity for the sync search)
+};
+
 // The whole decode of one batch.  `base` holds the streams at offsets[i]..offsets[i+1].
-int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams, int where)
+int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams, int where,
+                const StreamHint *hints = nullptr)
 {
     if (!ctx || !offsets || nstreams < 0 || (nstreams > 0 && !base)) return MP3B_E_INVAL;
     CK(cudaSetDevice(ctx->device));
@@ -264,6 +287,11 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         memset(&hs[i], 0, sizeof hs[i]);
         hs[i].raw_off = offsets[i] - raw0;
         hs[i].raw_len = (uint32_t)(offsets[i + 1] - offsets[i]);
+        if (hints) {
+            hs[i].skip_frames = hints[i].skip_frames;
+            hs[i].first_hdr = hints[i].first_hdr;
+            hs[i].flags = L3S_STREAMING;
+        }
     }
     std::vector<std::vector<L3FrameRec>> host_frames;
     if (host_index) {
@@ -283,6 +311,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     // ---- prefix sums, per-stream info, synthesis tiles
     const int G = l3_synth_tile_granules();
     uint64_t frames = 0, grans = 0, units = 0, payload = 0, ntiles = 0;
+    std::vector<uint32_t> sgran((size_t)nstreams, 0), sunit((size_t)nstreams, 0), sskip((size_t)nstreams, 0);
     for (int i = 0; i < nstreams; i++) {
         L3StreamRec &r = hs[i];
         mp3b_stream_info &inf = ctx->infos[(size_t)i];
@@ -291,16 +320,24 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         r.unit_base = (uint32_t)units;
         r.payload_base = payload;
         inf.pcm_offset = (int64_t)(units * 576);
-        if (r.nframes) {
+        if (r.first_hdr) {
             L3Hdr h;
             l3_parse_hdr(r.first_hdr, &h);
             inf.sample_rate = l3_sr_hz(h.sr_row);
             inf.channels = h.nch;
             inf.lsf = h.lsf;
-            inf.frames = r.nframes;
-            inf.samples = (int64_t)r.nframes * h.ngr * 576;
+            // leading `skip` frames were output by an earlier call: they are decoded again only to
+            // re-derive the reservoir / overlap / synthesis state, and produce no PCM
+            const uint32_t skip = std::min(r.skip_frames, r.nframes);
+            r.skip_frames = skip;
+            inf.frames = r.nframes - skip;
+            inf.samples = (int64_t)(r.nframes - skip) * h.ngr * 576;
+            inf.pcm_offset += (int64_t)skip * h.ngr * h.nch * 576;
             frames += r.nframes;
             uint64_t g = (uint64_t)r.nframes * h.ngr;
+            sgran[(size_t)i] = (uint32_t)g;
+            sunit[(size_t)i] = (uint32_t)(g * h.nch);
+            sskip[(size_t)i] = skip * (uint32_t)h.ngr;
             ntiles += (g + G - 1) / G;
             grans += g;
             units += g * h.nch;
@@ -312,7 +349,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     ctx->ngran = (uint32_t)grans;
     ctx->nunits = (uint32_t)units;
     ctx->ntiles = (uint32_t)ntiles;
-    ctx->arena_bytes = align_up(payload + 32, 16);
+    ctx->arena_bytes = align_up(payload + 64, 16);
     const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
     ctx->pcm_elems = units * 576;
 
@@ -325,7 +362,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         if (ctx->tile_override) GF = ctx->tile_override;
         ntiles = 0;
         for (int i = 0; i < nstreams; i++) {
-            uint64_t g = (uint64_t)ctx->infos[(size_t)i].samples / 576;
+            uint64_t g = sgran[(size_t)i] - sskip[(size_t)i];
             ntiles += (g + GF - 1) / GF;
         }
         ctx->ntiles = (uint32_t)ntiles;
@@ -340,9 +377,9 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             const L3StreamRec &r = hs[i];
             tile_start[(size_t)i] = k;
             if (!r.nframes) continue;
-            uint32_t g = r.nframes * (uint32_t)(ctx->infos[(size_t)i].lsf ? 1 : 2);
+            const uint32_t g = sgran[(size_t)i];
             if (fused)
-                for (uint32_t a = 0; a < g; a += GF)
+                for (uint32_t a = sskip[(size_t)i]; a < g; a += GF)
                     t4[k++] = make_uint4(r.gran_base + a, std::min<uint32_t>(GF, g - a), std::min<uint32_t>(2u, a), 0u);
             else
                 for (uint32_t a = 0; a < g; a += (uint32_t)G)
@@ -375,7 +412,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             int s1 = s0;
             uint64_t u = 0;
             while (s1 < nstreams) {
-                uint64_t us = (uint64_t)ctx->infos[(size_t)s1].samples / 576 * (uint64_t)std::max(ctx->infos[(size_t)s1].channels, 0);
+                uint64_t us = sunit[(size_t)s1];
                 if (s1 > s0 && u + us > wave) break;
                 u += us;
                 s1++;
@@ -569,7 +606,8 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
                       &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_scratch, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
-    for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather})
+    for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
+                      &ctx->h_frames_out})
         b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -621,14 +659,21 @@ void mp3b_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
+static int finalize_stream_batch(mp3b_ctx *ctx);
+
 int mp3b_decode_packed(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams, int where)
 {
+    if (!ctx) return MP3B_E_INVAL;
+    if (int rc = finalize_stream_batch(ctx)) return rc;
+    for (auto *s : ctx->open_streams) s->batch_index = -1; // the bulk call replaces the streams' batch
     return decode_impl(ctx, base, offsets, nstreams, where);
 }
 
 int mp3b_decode_batch(mp3b_ctx *ctx, const uint8_t *const *bufs, const size_t *lens, int nstreams)
 {
     if (!ctx || nstreams < 0 || (nstreams > 0 && (!bufs || !lens))) return MP3B_E_INVAL;
+    if (int rc = finalize_stream_batch(ctx)) return rc;
+    for (auto *s : ctx->open_streams) s->batch_index = -1;
     ctx->gather_offsets.assign((size_t)nstreams + 1, 0);
     uint64_t tot = 0;
     for (int i = 0; i < nstreams; i++) {
@@ -726,9 +771,48 @@ int mp3b_get_stats(const mp3b_ctx *ctx, mp3b_stats *st)
 }
 
 // ---------------------------------------------------------------------------- stream interface
+// Incremental: every mp3b_decode() emits PCM for the frames completed since the previous call.  A
+// stream keeps, besides the not yet decodable tail, the last few frames it already output: enough
+// main data behind them to serve any main_data_begin (511 / 255 bytes) plus the two granules the
+// fused back end replays to re-derive its overlap-add and synthesis state.  Nothing else is carried
+// between calls, so a resumed stream produces exactly the samples a one-shot decode would.
+static int finalize_stream_batch(mp3b_ctx *ctx)
+{
+    if (!ctx->stream_batch_pending) return MP3B_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream_batch_pending = false;
+    const L3StreamRec *hs = ctx->h_streams.as<L3StreamRec>();
+    const L3FrameRec *fr = ctx->h_frames_out.as<L3FrameRec>();
+    for (auto *s : ctx->open_streams) {
+        if (s->batch_index < 0) continue;
+        const L3StreamRec &r = hs[s->batch_index];
+        const mp3b_stream_info &inf = ctx->infos[(size_t)s->batch_index];
+        s->total_samples += inf.samples;
+        size_t keep_from = 0;
+        if (r.nframes) {
+            if (!s->first_hdr) s->first_hdr = r.first_hdr;
+            L3Hdr h;
+            l3_parse_hdr(r.first_hdr, &h);
+            const uint32_t nfr = r.nframes, W = h.lsf ? 2u : 1u, need = h.lsf ? 255u : 511u;
+            const L3FrameRec *f = fr + r.frame_base;
+            const uint32_t wf = nfr > W ? nfr - W : 0; // first frame the back end will replay
+            uint32_t idx = wf;
+            while (idx > 0 && nfr - idx < 192 && f[wf].payload_off - f[idx].payload_off < need) idx--;
+            keep_from = f[idx].rel_off;
+            s->ctx_frames = nfr - idx;
+        } else if (s->pending.size() > (1u << 20)) {
+            keep_from = s->pending.size() - 4096; // megabytes without a single frame: drop the junk
+        }
+        if (keep_from) s->pending.erase(s->pending.begin(), s->pending.begin() + (ptrdiff_t)keep_from);
+    }
+    return MP3B_OK;
+}
+
 int mp3b_stream_open(mp3b_ctx *ctx, mp3b_stream **out)
 {
     if (!ctx || !out) return MP3B_E_INVAL;
+    if (int rc = finalize_stream_batch(ctx)) return rc;
     mp3b_stream *s = new (std::nothrow) mp3b_stream;
     if (!s) return MP3B_E_NOMEM;
     s->ctx = ctx;
@@ -740,6 +824,7 @@ int mp3b_stream_open(mp3b_ctx *ctx, mp3b_stream **out)
 void mp3b_stream_close(mp3b_stream *s)
 {
     if (!s) return;
+    finalize_stream_batch(s->ctx);
     auto &v = s->ctx->open_streams;
     v.erase(std::remove(v.begin(), v.end(), s), v.end());
     for (auto *o : v) o->batch_index = -1; // batch indices are positional: invalidate
@@ -760,23 +845,51 @@ int mp3b_stream_enqueue(mp3b_stream *s, const uint8_t *bytes, size_t n)
 int mp3b_decode(mp3b_ctx *ctx)
 {
     if (!ctx) return MP3B_E_INVAL;
-    std::vector<const uint8_t *> bufs;
-    std::vector<size_t> lens;
-    int k = 0;
-    for (auto *s : ctx->open_streams) {
-        bufs.push_back(s->pending.data());
-        lens.push_back(s->pending.size());
-        s->batch_index = k++;
+    if (int rc = finalize_stream_batch(ctx)) return rc;
+    const int n = (int)ctx->open_streams.size();
+    std::vector<StreamHint> hints((size_t)n);
+    ctx->gather_offsets.assign((size_t)n + 1, 0);
+    uint64_t tot = 0;
+    for (int i = 0; i < n; i++) {
+        mp3b_stream *s = ctx->open_streams[(size_t)i];
+        s->batch_index = i;
         s->cursor = 0;
+        hints[(size_t)i].skip_frames = s->ctx_frames;
+        hints[(size_t)i].first_hdr = s->first_hdr;
+        ctx->gather_offsets[(size_t)i] = tot;
+        tot += s->pending.size();
     }
-    return mp3b_decode_batch(ctx, bufs.data(), lens.data(), k);
+    ctx->gather_offsets[(size_t)n] = tot;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->h_gather.ensure(tot + 64));
+    uint8_t *dst = ctx->h_gather.as<uint8_t>();
+    for (int i = 0; i < n; i++) {
+        const auto &pb = ctx->open_streams[(size_t)i]->pending;
+        if (!pb.empty()) memcpy(dst + ctx->gather_offsets[(size_t)i], pb.data(), pb.size());
+    }
+    int rc = decode_impl(ctx, dst, ctx->gather_offsets.data(), n, MP3B_HOST, hints.data());
+    if (rc != MP3B_OK) {
+        for (auto *s : ctx->open_streams) s->batch_index = -1;
+        return rc;
+    }
+    // the frame table comes back for the bookkeeping done in finalize_stream_batch()
+    CK(ctx->h_frames_out.ensure(sizeof(L3FrameRec) * std::max<uint32_t>(ctx->nframes, 1)));
+    if (ctx->nframes)
+        CK(cudaMemcpyAsync(ctx->h_frames_out.p, ctx->d_frames.p, sizeof(L3FrameRec) * ctx->nframes,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stream_batch_pending = true;
+    return MP3B_OK;
 }
 
 int mp3b_stream_get_info(const mp3b_stream *s, mp3b_stream_info *info)
 {
     if (!s || !info) return MP3B_E_INVAL;
-    if (s->batch_index < 0) return MP3B_E_STATE;
-    return mp3b_batch_stream_info(s->ctx, s->batch_index, info);
+    if (s->batch_index < 0 || !s->ctx->have_batch) return MP3B_E_STATE;
+    if (int rc = finalize_stream_batch(s->ctx)) return rc;
+    *info = s->ctx->infos[(size_t)s->batch_index];
+    info->total_samples = s->total_samples;
+    return s->first_hdr ? MP3B_OK : MP3B_E_NOSYNC;
 }
 
 int mp3b_stream_pcm_device_ptr(const mp3b_stream *s, const void **ptr, size_t *nsamples)
@@ -795,6 +908,7 @@ int mp3b_stream_fetch_pcm(mp3b_stream *s, void *dst, size_t cap_samples, int whe
     if (!s || (!dst && cap_samples)) return MP3B_E_INVAL;
     mp3b_ctx *ctx = s->ctx;
     if (s->batch_index < 0 || !ctx->have_batch) return MP3B_E_STATE;
+    if (int rc = finalize_stream_batch(ctx)) return rc;
     const mp3b_stream_info &inf = ctx->infos[(size_t)s->batch_index];
     const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
     size_t left = (size_t)inf.samples - std::min<size_t>(s->cursor, (size_t)inf.samples);

@@ -32,13 +32,20 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     L3StreamRec r = streams[s];
     const uint8_t *buf = raw + r.raw_off;
     L3FrameRec *out = scratch + scratch_base(r, (uint32_t)s);
-    uint32_t len = r.raw_len, p = l3_id3v2_len(buf, len), first = 0, first_off = 0, n = 0, payload = 0;
+    uint32_t len = r.raw_len, p = l3_id3v2_len(buf, len), first = r.first_hdr, first_off = 0, n = 0, payload = 0;
+    uint32_t end_off = p;
+    const bool streaming = (r.flags & L3S_STREAMING) != 0;
     while (p + 4 <= len) {
         L3Hdr h;
         uint32_t w;
-        if (!l3_frame_at(buf, len, p, first, &h, &w)) { p++; continue; }
-        if (!first) {
-            first = w;
+        const int fa = l3_frame_at(buf, len, p, first, &h, &w);
+        if (fa != 1) {
+            if (fa == 2 && streaming) break; // the rest of this frame has not arrived yet
+            p++;
+            continue;
+        }
+        if (n == 0) {
+            first = first ? first : w;
             first_off = p;
             for (int j = 1; j < 6; j++) // the chain is latency-bound: pull the next headers towards L2
                 if (p + (uint32_t)(j * h.frame_len) < len) prefetch_l2(buf + p + j * h.frame_len);
@@ -53,7 +60,9 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
         n++;
         payload += (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
         p += (uint32_t)h.frame_len;
+        end_off = p;
     }
+    streams[s].end_off = end_off;
     streams[s].first_off = first_off;
     streams[s].first_hdr = first;
     streams[s].nframes = n;
@@ -139,7 +148,7 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
         b.get(nch == 1 ? 1 : 2);
     }
     const int valid = mdb <= fr.payload_off;
-    if (!valid) atomicAdd(concealed, 1u);
+    if (!valid && fi >= sr.skip_frames) atomicAdd(concealed, 1u);
     uint64_t bit = valid ? (sr.payload_base + fr.payload_off - mdb) * 8ull : 0ull;
     uint8_t hdrbits = (uint8_t)((h.lsf ? L3H_LSF : 0) | (h.sr_row << L3H_SR_SHIFT) | (nch == 2 ? L3H_STEREO : 0));
     if (h.mode == 1) hdrbits |= (uint8_t)(((h.mode_ext & 2) ? L3H_MS : 0) | ((h.mode_ext & 1) ? L3H_IS : 0));

@@ -35,7 +35,14 @@ typedef struct L3StreamRec {
     uint32_t frame_base;   /* global index of its first frame */
     uint32_t gran_base;    /* global index of its first granule */
     uint32_t unit_base;    /* global index of its first unit (granule-channel) */
+    uint32_t end_off;      /* out: first byte not consumed by a complete frame (streaming) */
+    uint32_t skip_frames;  /* in: leading frames that only re-derive state (already output earlier) */
+    uint32_t flags;        /* in: L3S_* */
+    uint32_t reserved;
 } L3StreamRec;
+
+#define L3S_STREAMING 1u   /* more bytes may follow: stop at a valid header whose frame is not complete yet
+                              instead of searching for a sync inside it; first_hdr may be preset */
 
 /* One granule-channel ("unit": 576 spectral lines), from the side info (a2, a3). 32 bytes. */
 typedef struct __attribute__((aligned(16))) L3UnitDesc {
@@ -152,6 +159,7 @@ L3_HD uint32_t l3_load_be32(const uint8_t *p)
 /* One step of the frame walk shared by the host and device indexers (the scan policy of
  * oracle/l3_oracle.c: l3o_decode): at byte p, is there a frame of this stream that fits?
  * `first` is the stream's first header (0 while none has been found). */
+/* returns 1: a complete frame; 2: a valid header of this stream whose frame runs past the buffer; 0: none */
 L3_HD int l3_frame_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t first, L3Hdr *h, uint32_t *word)
 {
     if (p + 4 > len) return 0;
@@ -159,7 +167,7 @@ L3_HD int l3_frame_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t fir
     if (!l3_parse_hdr(w, h)) return 0;
     if (first && !l3_same_stream(w, first)) return 0;
     if (h->frame_len < 4 + (h->crc ? 2 : 0) + h->side_len) return 0;
-    if (p + (uint32_t)h->frame_len > len) return 0;
+    if (p + (uint32_t)h->frame_len > len) return 2;
     *word = w;
     return 1;
 }

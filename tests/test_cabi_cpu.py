@@ -44,7 +44,7 @@ def test_no_cpu_fallback(lib):
 def test_struct_sizes_match_header(lib):
     import mp3_b200
     assert ctypes.sizeof(mp3_b200.Opts) == 24
-    assert ctypes.sizeof(mp3_b200.StreamInfo) == 48
+    assert ctypes.sizeof(mp3_b200.StreamInfo) == 56
     assert ctypes.sizeof(mp3_b200.Stats) == 96
     o = mp3_b200.Opts()
     lib.mp3b_opts_default(ctypes.byref(o))
