@@ -107,12 +107,16 @@ __device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t
                                                const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
                                                const uint8_t *__restrict__ nzv_in)
 {
-    const char *gi = reinterpret_cast<const char *>(is_in + (size_t)u_first * 576);
-    char *si = reinterpret_cast<char *>(&S.is_buf[0][0]);
-    for (int i = tid; i < n * 72; i += KF_THREADS) {
-        const int unit = i / 72, v = i - unit * 72;
-        if (v < (int)nzv_in[u_first + unit]) cp_async16(si + i * 16, gi + i * 16);
-        else *reinterpret_cast<uint4 *>(si + i * 16) = make_uint4(0, 0, 0, 0);
+    const int unit = tid >> 5, lane = tid & 31; // one warp per unit: 72 vectors of 16 bytes
+    if (unit < n) {
+        const char *gi = reinterpret_cast<const char *>(is_in + (size_t)(u_first + unit) * 576);
+        char *si = reinterpret_cast<char *>(&S.is_buf[unit][0]);
+        const int nv = nzv_in[u_first + unit];
+#pragma unroll
+        for (int v = lane; v < 72; v += 32) {
+            if (v < nv) cp_async16(si + v * 16, gi + v * 16);
+            else *reinterpret_cast<uint4 *>(si + v * 16) = make_uint4(0, 0, 0, 0);
+        }
     }
     const char *gs = reinterpret_cast<const char *>(sf_in + (size_t)u_first * 40);
     char *ss = reinterpret_cast<char *>(&S.sf_buf[0][0]);
@@ -154,12 +158,27 @@ __device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int
 __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int nch,
                                             const L3BandTables *__restrict__ bands)
 {
+    // 64 threads per granule: lanes 0..39 of each of its two warps take one band of one channel
+    {
+        const int gi = tid >> 6, c = (tid >> 5) & 1, b = tid & 31;
+        if (gi < nb && c < nch && S.gm[gi].lay[c] == 0) {
+            // long blocks (22 bands, the band index is the sfb): no table lookups
+            const L3UnitDesc &dd = S.gm[gi].d[c];
+            if (b < 22) {
+                const int s = S.sf_buf[gi * nch + c][b] & 0x7f;
+                const int sh = (dd.flags & L3F_SFSCALE) ? 4 : 2;
+                const int q = (int)dd.global_gain - 210 - sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[b] : 0));
+                S.gain[gi][c][b] = ldexpf(f_pow2q[q & 3], q >> 2);
+            }
+        }
+    }
     for (int it = tid; it < nb * 80; it += KF_THREADS) {
         const int gi = it / 80, c = (it % 80) / 40, b = it % 40;
         if (c >= nch) continue;
         const GranMeta &m = S.gm[gi];
         const L3UnitDesc &dd = m.d[c];
         const int lay = m.lay[c];
+        if (lay == 0) continue; // done above
         float gn = 0.f;
         if (b < bands->nbands[m.row][lay]) {
             const int s = S.sf_buf[gi * nch + c][b] & 0x7f;
