@@ -23,7 +23,9 @@
 //       of C); rows have an odd stride so this lane = row pattern is bank-conflict free too
 //   S4  warp per (granule, channel), lane = sample j: the 16-tap window as a fully unrolled sliding
 //       accumulation over the 33 rows a granule touches (2 LDS per row instead of 16 per output);
-//       PCM is staged in shared memory and leaves the CTA as 16-byte stores
+//       PCM is staged in shared memory and leaves the CTA as one TMA bulk store per batch
+//   Input staging: the next batch's spectra are fetched by TMA bulk copies (cp.async.bulk + mbarrier,
+//   only the vectors that hold data) while the current batch computes.
 // Results must equal the staged pipeline's (tests/test_gpu_parity.py runs both).
 // No reference code exists for these stages (/root/reference/README.md:1-84).
 #include <math.h>
@@ -77,6 +79,7 @@ struct FusedShared {
     // next batch's Huffman output and scalefactors, fetched with cp.async while this batch computes
     __align__(16) int16_t is_buf[KF_B * 2][576];
     __align__(16) uint8_t sf_buf[KF_B * 2][40];
+    __align__(8) uint64_t bar;  // mbarrier: completion of the bulk copies into is_buf
 };
 
 __device__ __forceinline__ int xpad(int i) { return i + ((i * 3641) >> 16); } // i + i / 18 for i < 608
@@ -88,16 +91,44 @@ __device__ __forceinline__ int16_t to_s16(float v)
     return (int16_t)r;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS: UBLKCP) with an mbarrier for completion -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // Start fetching the Huffman output (1152 B / unit) and scalefactors (40 B / unit) of `n` consecutive
 // units into shared memory; the caller waits (cp_async_wait_all + barrier) before reading them.
@@ -107,16 +138,28 @@ __device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t
                                                const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
                                                const uint8_t *__restrict__ nzv_in)
 {
-    const int unit = tid >> 5, lane = tid & 31; // one warp per unit: 72 vectors of 16 bytes
+    // spectra: one TMA bulk copy per unit, issued by the lanes of the last warp (which has no S3 work);
+    // every warp zeroes the tail of "its" unit
+    if ((tid >> 5) == KF_THREADS / 32 - 1) {
+        const int k = tid & 31;
+        const uint32_t b = k < n ? 16u * nzv_in[u_first + k] : 0u;
+        uint32_t tot = b;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (k == 0) {
+            fence_proxy_async(); // earlier generic-proxy reads of is_buf are ordered before the async writes
+            mbar_expect_tx(&S.bar, tot);
+        }
+        __syncwarp();
+        if (b) bulk_g2s(&S.is_buf[k][0], is_in + (size_t)(u_first + k) * 576, b, &S.bar);
+    }
+    const int unit = tid >> 5, lane = tid & 31;
     if (unit < n) {
-        const char *gi = reinterpret_cast<const char *>(is_in + (size_t)(u_first + unit) * 576);
         char *si = reinterpret_cast<char *>(&S.is_buf[unit][0]);
         const int nv = nzv_in[u_first + unit];
 #pragma unroll
-        for (int v = lane; v < 72; v += 32) {
-            if (v < nv) cp_async16(si + v * 16, gi + v * 16);
-            else *reinterpret_cast<uint4 *>(si + v * 16) = make_uint4(0, 0, 0, 0);
-        }
+        for (int v = lane; v < 72; v += 32)
+            if (v >= nv) *reinterpret_cast<uint4 *>(si + v * 16) = make_uint4(0, 0, 0, 0);
     }
     const char *gs = reinterpret_cast<const char *>(sf_in + (size_t)u_first * 40);
     char *ss = reinterpret_cast<char *>(&S.sf_buf[0][0]);
@@ -441,6 +484,8 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
     const uint32_t ubase = gu_first & L3G_UNIT_MASK; // units of a stream are contiguous
     typedef typename std::conditional<FMT == MP3B_PCM_S16, int16_t, float>::type pcm_t;
 
+    if (tid == 0) mbar_init(&S.bar, 1);
+    __syncthreads();
     // history starts at zero (stream head, or about to be re-derived by the warm-up granules)
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -469,7 +514,9 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         const uint32_t u_first = ubase + (uint32_t)b0 * nch;
         // ---- S1
         finish_meta(S, tid, nb, nch);
-        cp_async_wait_all();
+        cp_async_wait_all();                        // scalefactors (LDGSTS)
+        mbar_wait(&S.bar, (uint32_t)(b0 / KF_B) & 1u); // spectra (TMA); one phase per batch
+        if (tid == KF_THREADS - 32) bulk_wait_read_all(); // the previous batch's PCM has left the staging buffer
         __syncthreads();
         stage_gains(S, tid, nb, nch, bands);
         __syncthreads();
@@ -480,10 +527,6 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         }
         stage_requant(S, tid, nb, nch, bands, pow43, bq);
         __syncthreads();
-        // is_buf / sf_buf are consumed: start fetching the next batch behind S2..S5
-        if (b0 + KF_B < total)
-            prefetch_units(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B) * nch, is_in, sf_in,
-                           nzv_in);
         // ---- S2: alias + IMDCT; second halves travel in registers to the next granule's rows
         {
             const int gi = warp >> 1, c = warp & 1;
@@ -505,9 +548,12 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
             }
         }
         __syncthreads();
-        // next batch's descriptors can be fetched now (gm is dead until the next S1)
-        if (b0 + KF_B < total)
+        // next batch: descriptors (gm is dead until the next S1) and, behind S3..S5, spectra + scalefactors
+        if (b0 + KF_B < total) {
             load_meta(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B), nch, units);
+            prefetch_units(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B) * nch, is_in, sf_in,
+                           nzv_in);
+        }
         // ---- S3: 32-point transform of every slot, in place; one thread per (channel, slot) row,
         // the whole transform in registers (fast_dct.h: 304 operations instead of 1024 FMAs)
         {
@@ -536,18 +582,17 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                     if (FMT == MP3B_PCM_S16) dst[(t * 32 + lane) * nch] = (pcm_t)to_s16(val);
                     else dst[(t * 32 + lane) * nch] = (pcm_t)val;
                 });
+                fence_proxy_async(); // make the staged PCM visible to the TMA store issued after the barrier
             }
         }
         __syncthreads();
-        // ---- S5: PCM out (16-byte stores), carry the state to the next batch
+        // ---- S5: PCM out (TMA bulk store), carry the state to the next batch
         {
             const int first_out = max(0, warm - b0); // warm-up granules of this batch produce no PCM
-            if (first_out < nb) {
+            if (first_out < nb && tid == KF_THREADS - 32) { // one TMA bulk store for the whole batch
                 const size_t e0 = (size_t)(u_first + (uint32_t)first_out * nch) * 576;
-                const int nvec = (nb - first_out) * 576 * nch * (int)sizeof(pcm_t) / 16;
-                const uint4 *src = reinterpret_cast<const uint4 *>(stage + (size_t)first_out * 576 * nch);
-                uint4 *dstg = reinterpret_cast<uint4 *>(reinterpret_cast<pcm_t *>(pcm) + e0);
-                for (int i = tid; i < nvec; i += KF_THREADS) dstg[i] = src[i];
+                const uint32_t bytes = (uint32_t)((nb - first_out) * 576 * nch) * (uint32_t)sizeof(pcm_t);
+                bulk_s2g(reinterpret_cast<pcm_t *>(pcm) + e0, stage + (size_t)first_out * 576 * nch, bytes);
             }
             for (int i = tid; i < 2 * 15 * FS; i += KF_THREADS) {
                 const int c = i / (15 * FS), k = i % (15 * FS);
@@ -556,6 +601,7 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         }
         __syncthreads();
     }
+    if (tid == KF_THREADS - 32) bulk_wait_read_all(); // the last PCM store must have read the staging buffer
 }
 
 } // namespace
