@@ -227,6 +227,7 @@ def run_ours(args, rank, world):
     e2.record(tstream)
     for _ in range(args.steps):
         step_e2e()
+    dec.flush()  # the stream (and so the end event) waits for every D2H copy of every step
     e3.record(tstream)
     barrier()
     sampler.stop_flag = True

@@ -116,6 +116,10 @@ int mp3b_decode_batch(mp3b_ctx *ctx, const uint8_t *const *bufs, const size_t *l
 int mp3b_decode_packed(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams,
                        int where /* mp3b_where: where `base` lives */);
 int mp3b_sync(mp3b_ctx *ctx);
+/* Asynchronous join: makes the context's CUDA stream wait for the sink copies issued so far (see
+ * mp3b_set_pcm_sink), without blocking the host.  An event the caller records on that stream after
+ * mp3b_flush() therefore covers the D2H transfers too. */
+int mp3b_flush(mp3b_ctx *ctx);
 
 int mp3b_batch_stream_info(const mp3b_ctx *ctx, int stream_index, mp3b_stream_info *info);
 /* Whole-batch PCM arena: streams back to back in input order, interleaved channels. */
@@ -127,7 +131,9 @@ int mp3b_get_stats(const mp3b_ctx *ctx, mp3b_stats *st);
 /* Streaming PCM sink: register a host buffer (pinned memory from mp3b_host_alloc for full PCIe speed)
  * of cap_elems PCM elements.  Every following decode call splits the batch into waves and copies each
  * wave's PCM to host_dst + its arena offset on a second CUDA stream while the next wave decodes, so
- * the D2H transfer overlaps the kernels.  mp3b_sync() (and the context's stream) waits for the copies.
+ * the D2H transfer overlaps the kernels -- and, because two PCM arenas alternate, the next decode call's
+ * upload and kernels as well.  mp3b_sync() waits for the copies; mp3b_flush() orders them into the
+ * context's stream.  The device PCM of a call stays valid until the call after the next one.
  * host_dst = NULL removes the sink.  A too-small sink makes the decode call fail with TRUNCATED. */
 int mp3b_set_pcm_sink(mp3b_ctx *ctx, void *host_dst, uint64_t cap_elems);
 

@@ -55,7 +55,7 @@ class Stats(ctypes.Structure):
 EXPORTS = [
     "mp3b_abi_version", "mp3b_device_count", "mp3b_opts_default", "mp3b_ctx_create", "mp3b_ctx_destroy",
     "mp3b_ctx_set_stream", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
-    "mp3b_decode_packed", "mp3b_sync", "mp3b_batch_stream_info", "mp3b_batch_pcm_device_ptr",
+    "mp3b_decode_packed", "mp3b_sync", "mp3b_flush", "mp3b_batch_stream_info", "mp3b_batch_pcm_device_ptr",
     "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_set_pcm_sink", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
     "mp3b_debug_stage",
@@ -87,6 +87,7 @@ def load_library():
     L.mp3b_decode_batch.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), i32]
     L.mp3b_decode_packed.argtypes = [vp, vp, ctypes.POINTER(u64), i32, i32]
     L.mp3b_sync.argtypes = [vp]
+    L.mp3b_flush.argtypes = [vp]
     L.mp3b_batch_stream_info.argtypes = [vp, i32, ctypes.POINTER(StreamInfo)]
     L.mp3b_batch_pcm_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.mp3b_batch_fetch_pcm.argtypes = [vp, vp, u64, i32, ctypes.POINTER(u64)]
@@ -231,6 +232,10 @@ class Decoder:
 
     def sync(self):
         self._ck(self.L.mp3b_sync(self.ctx))
+
+    def flush(self):
+        """Order the outstanding sink copies into the context's stream (non-blocking)."""
+        self._ck(self.L.mp3b_flush(self.ctx))
 
     def stream_info(self, i):
         inf = StreamInfo()

@@ -94,6 +94,7 @@ struct mp3b_ctx {
     cudaStream_t copy_stream = nullptr; // D2H of finished waves (PCM sink)
     std::vector<cudaEvent_t> wave_ev;
     cudaEvent_t copy_done = nullptr;
+    cudaEvent_t staging_done = nullptr; // the last H2D out of the pinned staging tables has executed
     void *sink = nullptr;
     uint64_t sink_cap = 0;
     cudaEvent_t ev[EV_COUNT]{};
@@ -104,7 +105,11 @@ struct mp3b_ctx {
     L3DevTables T{};
 
     // per-batch device state
-    DevBuf d_raw, d_streams, d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_scratch;
+    DevBuf d_raw, d_streams, d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_pcm2, d_scratch;
+    int pcm_cur = 0;                       // PCM arena of the last decode (two alternate in sink mode)
+    cudaEvent_t pcm_free[2] = {nullptr, nullptr}; // sink copies out of arena i have finished
+    DevBuf &pcm() { return pcm_cur ? d_pcm2 : d_pcm; }
+    const DevBuf &pcm() const { return pcm_cur ? d_pcm2 : d_pcm; }
     DevBuf d_is, d_sf, d_nzv, d_xr, d_imd, d_sb; // wave-sized intermediates
     PinBuf h_streams, h_frames, h_tiles, h_stage, h_counter;
 
@@ -266,11 +271,10 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     const bool host_index = ctx->opts.indexer == MP3B_INDEX_HOST;
     if (host_index && where != MP3B_HOST) { ctx->err = "host indexer needs host-resident input"; return MP3B_E_INVAL; }
 
+    // the pinned staging tables (stream records, tiles, frames) are rewritten below: the previous call's
+    // asynchronous uploads out of them must have executed (they are early in that call, so this is short)
+    CK(cudaEventSynchronize(ctx->staging_done));
     CK(cudaEventRecord(ctx->ev[EV_START], st));
-    if (ctx->sink) { // a previous call's sink copies must have left the PCM arena before it is rewritten
-        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-        CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
-    }
     // ---- raw bytes to the device
     if (where == MP3B_HOST) {
         CK(ctx->d_raw.ensure(raw_total + 64));
@@ -304,7 +308,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         CK(cudaMemcpyAsync(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
         l3_launch_index_walk(ctx->raw_dev, ctx->d_streams.as<L3StreamRec>(), nstreams, ctx->d_scratch.as<L3FrameRec>(), st);
         launches++;
-        CK(cudaMemcpyAsync(hs, ctx->d_streams.p, sizeof(L3StreamRec) * nstreams, cudaMemcpyDeviceToHost, st));
+        l3_launch_publish(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, st);
+        launches++;
         CK(cudaStreamSynchronize(st)); // the one host round trip: sizes of everything downstream
     }
 
@@ -396,10 +401,16 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(ctx->d_tiles.ensure(sizeof(uint4) * std::max<uint64_t>(ntiles, 1)));
     CK(ctx->d_counter.ensure(64));
     CK(ctx->h_counter.ensure(64));
-    CK(ctx->d_pcm.ensure(std::max<uint64_t>(ctx->pcm_elems * elem, 16)));
+
     const bool keep = ctx->opts.keep_stages != 0;
     const bool sink = ctx->sink != nullptr && !keep;
     if (sink && ctx->sink_cap < ctx->pcm_elems) { ctx->err = "PCM sink too small"; return MP3B_E_TRUNCATED; }
+    // Sink mode alternates between two PCM arenas, so that this call's kernels need not wait for the
+    // previous call's D2H copies (still draining on the copy stream): successive calls pipeline.
+    ctx->pcm_cur = sink ? (ctx->pcm_cur ^ 1) : 0;
+    CK(ctx->pcm().ensure(std::max<uint64_t>(ctx->pcm_elems * elem, 16)));
+    if (sink) CK(cudaStreamWaitEvent(st, ctx->pcm_free[ctx->pcm_cur], 0)); // copies issued two calls ago
+    void *const pcm_dev = ctx->pcm().p;
     uint64_t wave = keep ? std::max<uint64_t>(units, 1) : std::min<uint64_t>(std::max<uint64_t>(units, 1), ctx->wave_units);
     if (sink) // several waves so that the D2H of wave k overlaps the kernels of wave k+1
         wave = std::min<uint64_t>(wave, std::max<uint64_t>(units / 8, 32768));
@@ -436,6 +447,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->h_tiles.p, (fused ? sizeof(uint4) : sizeof(uint2)) * ntiles,
                            cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, st));
+    bool staging_recorded = false;
+    if (!host_index) { CK(cudaEventRecord(ctx->staging_done, st)); staging_recorded = true; }
     CK(cudaMemsetAsync(ctx->d_arena.as<uint8_t>() + (ctx->arena_bytes - 48), 0, 48, st));
 
     // ---- frame table
@@ -450,6 +463,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         });
         if (frames) CK(cudaMemcpyAsync(df, hf, sizeof(L3FrameRec) * frames, cudaMemcpyHostToDevice, st));
     }
+    if (!staging_recorded) CK(cudaEventRecord(ctx->staging_done, st));
     L3UnitDesc *du = ctx->d_units.as<L3UnitDesc>();
     uint32_t *dg = ctx->d_gran.as<uint32_t>();
     if (frames) {
@@ -490,13 +504,13 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             CK(cudaEventRecord(ctx->wave_ev[w], st));
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->wave_ev[w], 0));
             const size_t lo = (size_t)u_lo * 576 * elem, n = (size_t)nu * 576 * elem;
-            CK(cudaMemcpyAsync(static_cast<char *>(ctx->sink) + lo, ctx->d_pcm.as<char>() + lo, n,
+            CK(cudaMemcpyAsync(static_cast<char *>(ctx->sink) + lo, static_cast<char *>(pcm_dev) + lo, n,
                                cudaMemcpyDeviceToHost, ctx->copy_stream));
             return MP3B_OK;
         };
         if (fused) {
             l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
-                              ctx->d_pcm.p, ctx->opts.pcm_format, st);
+                              pcm_dev, ctx->opts.pcm_format, st);
             if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
             launches += 2;
             if (int rc = wave_done()) return rc;
@@ -508,17 +522,15 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_IMDCT], st));
         l3_launch_overlap_range(du, u_lo, nu, imd, sb, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_OVL], st));
-        l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, ctx->d_pcm.p,
+        l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, pcm_dev,
                         ctx->opts.pcm_format, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
         launches += 5;
         if (int rc = wave_done()) return rc;
     }
-    if (sink) { // the context's stream (and so the caller's events on it) also covers the copies
-        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-        CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
-    }
-    CK(cudaMemcpyAsync(ctx->h_counter.p, ctx->d_counter.p, 4, cudaMemcpyDeviceToHost, st));
+    if (sink) CK(cudaEventRecord(ctx->pcm_free[ctx->pcm_cur], ctx->copy_stream));
+    l3_launch_publish(ctx->d_counter.p, ctx->h_counter.p, 4, st);
+    launches++;
     CK(cudaEventRecord(ctx->ev[EV_END], st));
     CK(cudaGetLastError());
 
@@ -588,6 +600,9 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     ctx->stream = ctx->own_stream;
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->staging_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
+    for (auto &e : ctx->pcm_free)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     for (auto &e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return bail(MP3B_E_CUDA);
     int rc = upload_tables(ctx);
@@ -603,7 +618,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto *s : ctx->open_streams) delete s;
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw, &ctx->d_streams, &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_scratch, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_scratch, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -617,6 +632,9 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     }
     for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
+    for (auto &e : ctx->pcm_free)
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -697,6 +715,7 @@ int mp3b_sync(mp3b_ctx *ctx)
     if (!ctx) return MP3B_E_INVAL;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     if (ctx->have_batch) {
         ctx->stats.concealed_frames = *ctx->h_counter.as<uint32_t>();
         auto ms = [&](int a, int b) {
@@ -720,6 +739,15 @@ int mp3b_sync(mp3b_ctx *ctx)
     return MP3B_OK;
 }
 
+int mp3b_flush(mp3b_ctx *ctx)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+    return MP3B_OK;
+}
+
 int mp3b_batch_stream_info(const mp3b_ctx *ctx, int i, mp3b_stream_info *info)
 {
     if (!ctx || !info) return MP3B_E_INVAL;
@@ -733,7 +761,7 @@ int mp3b_batch_pcm_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *n
 {
     if (!ctx || !ptr || !nelems) return MP3B_E_INVAL;
     if (!ctx->have_batch) return MP3B_E_STATE;
-    *ptr = ctx->d_pcm.p;
+    *ptr = ctx->pcm().p;
     *nelems = ctx->pcm_elems;
     return MP3B_OK;
 }
@@ -746,7 +774,7 @@ int mp3b_batch_fetch_pcm(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where
     const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
     CK(cudaSetDevice(ctx->device));
     if (ctx->pcm_elems)
-        CK(cudaMemcpyAsync(dst, ctx->d_pcm.p, ctx->pcm_elems * elem,
+        CK(cudaMemcpyAsync(dst, ctx->pcm().p, ctx->pcm_elems * elem,
                            where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     if (got) *got = ctx->pcm_elems;
     return MP3B_OK;
@@ -898,7 +926,7 @@ int mp3b_stream_pcm_device_ptr(const mp3b_stream *s, const void **ptr, size_t *n
     if (s->batch_index < 0 || !s->ctx->have_batch) return MP3B_E_STATE;
     const mp3b_stream_info &inf = s->ctx->infos[(size_t)s->batch_index];
     const int elem = s->ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
-    *ptr = s->ctx->d_pcm.as<uint8_t>() + (size_t)inf.pcm_offset * elem;
+    *ptr = s->ctx->pcm().as<uint8_t>() + (size_t)inf.pcm_offset * elem;
     *nsamples = (size_t)inf.samples;
     return MP3B_OK;
 }
@@ -915,7 +943,7 @@ int mp3b_stream_fetch_pcm(mp3b_stream *s, void *dst, size_t cap_samples, int whe
     size_t n = std::min(left, cap_samples);
     CK(cudaSetDevice(ctx->device));
     if (n) {
-        const uint8_t *src = ctx->d_pcm.as<uint8_t>() + ((size_t)inf.pcm_offset + s->cursor * inf.channels) * elem;
+        const uint8_t *src = ctx->pcm().as<uint8_t>() + ((size_t)inf.pcm_offset + s->cursor * inf.channels) * elem;
         CK(cudaMemcpyAsync(dst, src, n * inf.channels * elem,
                            where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

@@ -237,8 +237,24 @@ __global__ void k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRe
     for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
+// Small results go to the host through stores into pinned (UVA-mapped) memory instead of a D2H
+// memcpy: a memcpy would queue on the DMA engine behind the multi-hundred-megabyte PCM copies of the
+// previous call and serialise the pipeline on a 64-byte transfer.
+__global__ void k_publish_words(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst_host, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst_host[i] = src[i];
+    __threadfence_system();
+}
+
 } // namespace
 
+void l3_launch_publish(const void *src_dev, void *dst_pinned_host, size_t bytes, cudaStream_t st)
+{
+    const uint32_t n = (uint32_t)(bytes / 4);
+    if (!n) return;
+    const unsigned blocks = n > 65536 ? 64 : (n + 255) / 256;
+    k_publish_words<<<blocks, 256, 0, st>>>(static_cast<const uint32_t *>(src_dev), static_cast<uint32_t *>(dst_pinned_host), n);
+}
 void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *scratch, cudaStream_t st)
 {
     if (nstreams <= 0) return;

@@ -25,6 +25,8 @@ static inline uint64_t l3_index_scratch_records(uint64_t raw_total, uint64_t nst
 {
     return raw_total / 24 + 2 * nstreams + 2;
 }
+/* device -> pinned host through kernel stores (no DMA engine involved); bytes is a multiple of 4 */
+void l3_launch_publish(const void *src_dev, void *dst_pinned_host, size_t bytes, cudaStream_t st);
 void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *scratch,
                           cudaStream_t st);
 /* scratch == NULL: `frames` is already dense (host indexer) */

@@ -111,7 +111,7 @@ def test_fused_pipeline_pcm(tile, mp3b, batch, monkeypatch):
     with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=mp3b.PIPE_FUSED) as dec:
         dec.decode_batch(streams)
         arena = dec.fetch_pcm()
-        assert dec.stats().kernel_launches == 5  # walk, side_parse, payload_copy, huffman, backend
+        assert dec.stats().kernel_launches == 7  # walk, publish, side_parse, payload_copy, huffman, backend, publish
         for k, r in enumerate(refs):
             got = dec.stream_pcm(k, arena).astype(np.float64)
             ref = r.pcm.T
