@@ -35,22 +35,40 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     uint32_t len = r.raw_len, p = l3_id3v2_len(buf, len), first = r.first_hdr, first_off = 0, n = 0, payload = 0;
     uint32_t end_off = p;
     const bool streaming = (r.flags & L3S_STREAMING) != 0;
+    // Fast path for the overwhelmingly common case: the header equals the previous one in every bit that
+    // determines the frame geometry (sync, version, layer, protection, bitrate, sample rate, mode), so
+    // the length is the previous base length plus this frame's padding bit -- no header arithmetic.
+    const uint32_t GEOM = 0xFFFFFCC0u;
+    uint32_t prev_w = 0, base_len = 0, overhead = 0;
     while (p + 4 <= len) {
         L3Hdr h;
-        uint32_t w;
-        const int fa = l3_frame_at(buf, len, p, first, &h, &w);
-        if (fa != 1) {
-            if (fa == 2 && streaming) break; // the rest of this frame has not arrived yet
-            p++;
-            continue;
+        uint32_t w = l3_load_be32(buf + p), flen;
+        if (n && ((w ^ prev_w) & GEOM) == 0) {
+            flen = base_len + ((w >> 9) & 1u);
+            if (p + flen > len) {
+                if (streaming) break; // the rest of this frame has not arrived yet
+                p++;
+                continue;
+            }
+        } else {
+            const int fa = l3_frame_at(buf, len, p, first, &h, &w);
+            if (fa != 1) {
+                if (fa == 2 && streaming) break;
+                p++;
+                continue;
+            }
+            flen = (uint32_t)h.frame_len;
+            prev_w = w;
+            base_len = flen - ((w >> 9) & 1u);
+            overhead = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len;
+            if (n == 0) {
+                first = first ? first : w;
+                first_off = p;
+                for (int j = 1; j < 8; j++) // the chain is latency-bound: pull the next headers towards L2
+                    if (p + (uint32_t)j * flen < len) prefetch_l2(buf + p + j * flen);
+            }
         }
-        if (n == 0) {
-            first = first ? first : w;
-            first_off = p;
-            for (int j = 1; j < 6; j++) // the chain is latency-bound: pull the next headers towards L2
-                if (p + (uint32_t)(j * h.frame_len) < len) prefetch_l2(buf + p + j * h.frame_len);
-        }
-        if (p + 6u * (uint32_t)h.frame_len < len) prefetch_l2(buf + p + 6 * h.frame_len);
+        if (p + 8u * flen < len) prefetch_l2(buf + p + 8 * flen);
         L3FrameRec f;
         f.rel_off = p;
         f.payload_off = payload;
@@ -58,8 +76,8 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
         f.stream = (uint32_t)s;
         out[n] = f;
         n++;
-        payload += (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
-        p += (uint32_t)h.frame_len;
+        payload += flen - overhead;
+        p += flen;
         end_off = p;
     }
     streams[s].end_off = end_off;
