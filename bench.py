@@ -42,8 +42,23 @@ def workload(name, nstreams, nframes, seed, distinct):
     return streams, time.time() - t
 
 
-def audio_seconds(name, streams_info):
-    return sum(n / float(sr) for n, sr in streams_info)
+WORKLOADS = {
+    "cfg1": "44.1 kHz stereo 128 kbps CBR, long blocks, bit reservoir in use (BASELINE.json configs[0])",
+    "cfg2": "44.1 kHz stereo 128 kbps CBR, long blocks, bit reservoir in use (BASELINE.json configs[1])",
+    "cfg3": "44.1 kHz 320 kbps joint stereo (MS+IS), long/short/mixed/switching windows, reservoir swept "
+            "(BASELINE.json configs[2])",
+    "cfg4": "MPEG-2 LSF 22.05/24 kHz + MPEG-1 44.1 kHz, VBR 8-320 kbps, mono and stereo mixed (BASELINE.json configs[3])",
+    "cfg5": "100k-stream sweep of the cfg2 type, 128 frames each, streams sharded over the GPUs "
+            "(BASELINE.json configs[4])",
+}
+DEFAULT_FRAMES = {"cfg5": 128}
+DEFAULT_STREAMS = {"cfg1": 1, "cfg5": 100000}
+
+
+def cpu_sample_size(nstreams, cores):
+    """Streams for the bounded CPU sample: about 10-30 s of CPU work (a 10-s stream costs the oracle
+    ~40 ms on one core), never more than the workload has."""
+    return max(1, min(nstreams, cores * 32))
 
 
 class ClockSampler(threading.Thread):
@@ -107,7 +122,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nsample = max(cores * 4, 32)
+    nsample = cpu_sample_size(1 << 30, cores)
     streams, _ = workload(args.workload, nsample, args.frames, args.seed, None)
     vals = []
     for i in range(args.warmup + args.steps):
@@ -120,8 +135,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %d-stream sample of 44.1 kHz stereo 128 kbps CBR, %d frames each" % (
-            args.workload, nsample, args.frames or 383)},
+        "config": {"workload": "%s: %d-stream sample x %d frames, %s" % (
+            args.workload, nsample, args.frames or DEFAULT_FRAMES.get(args.workload, 383), WORKLOADS[args.workload])},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d streams per step, all host threads; the reference repository has no code, "
                                    "so this is the from-spec oracle port" % nsample},
@@ -149,7 +164,16 @@ def run_ours(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    streams, gen_s = workload(args.workload, args.streams, args.frames, args.seed + 100000 * rank, args.distinct)
+    # cfg2 (the headline config): weak scaling, every rank decodes its own 1,024 streams.
+    # cfg5 (the 100k-stream sweep): strong scaling, the 100k streams are sharded over the ranks.
+    strong = args.workload == "cfg5"
+    nstreams = args.streams
+    if strong:
+        total = args.streams or DEFAULT_STREAMS["cfg5"]
+        nstreams = total // world + (1 if rank < total % world else 0)
+        if args.distinct is None:
+            args.distinct = 1024  # bounds host-side generation; the decoder still decodes every stream
+    streams, gen_s = workload(args.workload, nstreams, args.frames, args.seed + 100000 * rank, args.distinct)
     packed, offs = mp3_b200.pack_streams(streams)
     nbytes_in = int(packed.size)
 
@@ -209,6 +233,17 @@ def run_ours(args, rank, world):
     stage_ms = {k: v / nst for k, v in stage_ms.items()}
 
     # ---- end to end: pinned host in, pinned host out
+    do_e2e = not args.no_e2e and pcm_bytes < (8 << 30)  # cfg5 would need 59 GB of pinned host memory
+    ms_e2e, checksum = float("nan"), None
+    if do_e2e:
+        ms_e2e, checksum = run_e2e(args, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier)
+    sampler.stop_flag = True
+    finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, ms_e2e, stage_ms,
+           launches, sampler, gen_s, checksum, strong)
+
+
+def run_e2e(args, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier):
+    import torch
     h_in = mp3_b200.PinnedBuffer(nbytes_in + 64)
     h_in.view(np.uint8)[:nbytes_in] = packed
     h_out = mp3_b200.PinnedBuffer(pcm_bytes + 64)
@@ -230,11 +265,15 @@ def run_ours(args, rank, world):
     dec.flush()  # the stream (and so the end event) waits for every D2H copy of every step
     e3.record(tstream)
     barrier()
-    sampler.stop_flag = True
     dec.set_pcm_sink(0, 0)
     ms_e2e = e2.elapsed_time(e3) / args.steps
     checksum = int(h_out.view(np.int16, pcm_elems)[:: max(1, pcm_elems // 4096)].astype(np.int64).sum())
+    return ms_e2e, checksum
 
+
+def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, ms_e2e, stage_ms,
+           launches, sampler, gen_s, checksum, strong):
+    import torch
     # ---- max over ranks
     if dist is not None:
         t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
@@ -262,8 +301,13 @@ def run_ours(args, rank, world):
                "synth": 2304.0 + 1152.0,
                "fused": 1152.0 + 40.0 + 1152.0}                  # int16 spectrum + scalefactors in; s16 PCM out
         kern = {k: v for k, v in stage_ms.items() if k != "index" and v > 0}
-        dom = max(kern, key=kern.get) if kern else "huffman"
-        achieved = alg[dom] * units / (kern.get(dom, 1e-9) * 1e-3) / 1e9
+        if kern:
+            dom = max(kern, key=kern.get)
+            achieved = alg[dom] * units / (kern[dom] * 1e-3) / 1e9
+        else:  # a decode cut into several waves has no per-stage events: whole pipeline only
+            dom = "pipeline"
+            alg[dom] = in_per_unit + 1152.0
+            achieved = alg[dom] * units / (ms_dev * 1e-3) / 1e9
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -271,15 +315,16 @@ def run_ours(args, rank, world):
         except Exception:
             pass
         cores = os.cpu_count() or 1
-        nsample = min(len(streams), max(cores * 4, 32))
+        nsample = cpu_sample_size(len(streams), cores)
         cpu_v, cpu_dt = cpu_oracle_throughput(streams[:nsample], cores)
         line = {
             "metric": METRIC, "value": audio_all / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "%s: %d streams/GPU x %d frames, 44.1 kHz stereo 128 kbps CBR, long blocks, bit "
-                            "reservoir in use (BASELINE.json configs[1])" % (args.workload, len(streams), args.frames or 383),
+                "workload": "%s: %d streams/GPU x %d frames, %s" % (
+                    args.workload, len(streams), args.frames or DEFAULT_FRAMES.get(args.workload, 383),
+                    WORKLOADS[args.workload]),
                 "streams_per_gpu": len(streams), "distinct_streams": args.distinct or len(streams),
                 "pcm": "s16 interleaved", "pipeline": args.pipeline, "indexer": "device",
                 "l2_policy": "inputs_larger_than_l2 (%.0f MB in, %.0f MB PCM out per step)" % (nbytes_in / 1e6, pcm_bytes / 1e6),
@@ -298,11 +343,12 @@ def run_ours(args, rank, world):
                          "note": "the back end is FP32-issue bound, not HBM bound (ncu: fma pipe ~30 %, issue ~67 %, "
                                  "dram ~9 %); its DRAM traffic equals the algorithmic bytes (profiles/)"},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "first %d streams of the workload (%.1f s of wall time), oracle/l3_oracle.c, "
-                                       "one stream per host thread" % (nsample, cpu_dt)},
-            "e2e": {"value": audio_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(in_all),
-                    "d2h_bytes_per_step": int(pcm_all), "ms_per_step": ms_e2e,
-                    "pcm_gbs": pcm_all / (ms_e2e * 1e-3) / 1e9},
+                             "sample": "first %d streams of the workload (%.1f s of wall time on %d threads = %.0f s of "
+                                       "CPU work), oracle/l3_oracle.c, one stream per host thread" % (
+                                           nsample, cpu_dt, cores, cpu_dt * min(cores, nsample))},
+            "e2e": ({"value": audio_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(in_all),
+                     "d2h_bytes_per_step": int(pcm_all), "ms_per_step": ms_e2e,
+                     "pcm_gbs": pcm_all / (ms_e2e * 1e-3) / 1e9} if ms_e2e == ms_e2e else None),
             "gpu_launches": int(launches * args.steps),
             "clocks": sampler.result(),
             "gen_seconds": gen_s, "pcm_checksum": checksum,
@@ -326,9 +372,12 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--pipeline", default="default", choices=["default", "fused", "staged"])
     ap.add_argument("--stage-times", action="store_true", help="sync after every step to read per-stage events")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.pipeline_id = {"default": None, "fused": 0, "staged": 1}[args.pipeline]
+    if args.frames is None:
+        args.frames = DEFAULT_FRAMES.get(args.workload)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
