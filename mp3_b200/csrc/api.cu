@@ -491,7 +491,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         float *imd = ctx->d_imd.as<float>() - (size_t)u_lo * 1152;
         float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
         uint8_t *nzv = ctx->d_nzv.as<uint8_t>() - (size_t)u_lo;
-        l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, ctx->T, is, sf, nzv,
+        l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu,
+                                (uint32_t)((ctx->arena_bytes + units - 1) / std::max<uint64_t>(units, 1)), ctx->T, is, sf, nzv,
                                 (!fused || keep) ? 1 : 0, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
         auto wave_done = [&]() -> int {

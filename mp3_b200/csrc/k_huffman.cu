@@ -3,16 +3,27 @@
 // One thread per unit (granule-channel).  Decoding a unit is a serial bit walk (every codeword's
 // position depends on the previous one), so the parallelism is across units: 1.57 M of them in
 // the 1024-stream workload.  What the GPU mapping has to get right is
-//   * table lookups: all 15 code books as one multi-level LUT (8-bit root, 6-bit sub levels,
-//     8.8 KB) staged in shared memory, so a codeword costs one or two LDS, not a tree walk;
-//   * convergence: one flat loop over pairs for all three regions (the table is selected by
-//     data, not by control flow), then one loop over count1 quadruples, so the lanes of a warp
-//     stay on the same instruction even though their tables and lengths differ;
-//   * stores: spectral values are packed 8 per 16-byte store (a shift register of four words,
-//     no dynamically indexed local array).
+//   * the bits: the main data of a CTA's chunk of units (<= 512 consecutive units) is one
+//     contiguous range of the arena, so it is staged into shared memory by ONE TMA bulk copy
+//     (cp.async.bulk + mbarrier) and byte-swapped once; after that a peek is three LDS and two
+//     funnel shifts, a skip is one add, and no global-load latency sits on the decode chain
+//     (a chunk whose range does not fit falls back to a register-window reader over global memory
+//     whose refill is predicated, not branched);
+//   * table lookups: all 15 code books as one two-level LUT (9-bit root, 15.5 KB) in shared
+//     memory, so a codeword costs two LDS, not a tree walk;
+//   * convergence: one flat loop over pairs for all three regions (table, code length, escapes
+//     and signs are data -- selects -- not control flow), then one loop over count1 quadruples
+//     whose (symbol, sign bits) -> four lines mapping is a 256-entry table;
+//   * balance: trip counts differ between units, so a chunk is sorted (big_values for the pair
+//     loop, remaining bits for the count1 loop) into groups of 32 that the warps pull longest
+//     first from a shared counter: lanes of a group run similar loops and warps finish together;
+//   * stores: big_values pairs are packed 8 lines per 16-byte store (a shift register of four
+//     words; all lanes push in lock step); count1 quadruples leave as two packed words.
 // Output is bit-exact by construction (integer work only) and is compared word for word with
-// oracle/l3_oracle.c::huffman_decode / read_scalefactors in tests/test_gpu_stages.py.
+// oracle/l3_oracle.c::huffman_decode / read_scalefactors in tests/test_gpu_parity.py.
 // No reference code exists for this stage (/root/reference/README.md:1-84).
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace {
@@ -26,20 +37,52 @@ __constant__ uint8_t c_lsf_nsfb[6][3][4] = {
     {{8, 8, 5, 0}, {15, 12, 9, 0}, {6, 18, 9, 0}},
 };
 
-// Bit reader over the big-endian main-data arena.  Two consecutive 32-bit words are cached in
-// registers; a peek is one funnel shift, a skip is one add plus a (rarely taken) refill when the
-// position crosses into the next word.  Positions are 32-bit and relative to the word the unit
-// starts in (the arena itself can exceed 2^32 bits).
-struct BitReader {
-    const uint32_t *words; // arena + first word of this unit
-    uint32_t wlimit;       // words readable from `words`
-    uint32_t w0, w1, w2;   // words[wi], words[wi + 1] in bit order; w2 = raw words[wi + 2], loaded one
-                           // word ahead so that its latency is off the decode chain
+constexpr int K1_THREADS = 256;
+constexpr int K1_CHUNK = 512;       // most units per CTA (16 groups of 32 for 8 warps)
+constexpr int K1_TAIL_PAD = 160;    // bytes staged beyond the last unit's part2_3 end (look-ahead, overruns)
+
+// ---- bit reader over the staged (shared memory, already in bit order) main data -----------------
+struct SmemReader {
+    const uint32_t *w;
+    uint32_t pos; // bit position relative to the stage start
+
+    __device__ __forceinline__ void init(const uint32_t *stage, uint32_t bit) { w = stage; pos = bit; }
+    __device__ __forceinline__ uint32_t bitpos() const { return pos; }
+    __device__ __forceinline__ uint32_t peek32() const
+    {
+        const uint32_t *q = w + (pos >> 5);
+        return __funnelshift_l(q[1], q[0], pos);
+    }
+    __device__ __forceinline__ void peek64(uint32_t &hi, uint32_t &lo) const
+    {
+        const uint32_t *q = w + (pos >> 5);
+        const uint32_t a = q[0], b = q[1], c = q[2];
+        hi = __funnelshift_l(b, a, pos); // the shift count wraps at 32
+        lo = __funnelshift_l(c, b, pos);
+    }
+    __device__ __forceinline__ void skip(int k) { pos += (uint32_t)k; }
+    __device__ __forceinline__ void skip_long(int k) { pos += (uint32_t)k; }
+    __device__ __forceinline__ uint32_t get(int k) // k in 0..16 (0 reads nothing), branch-free
+    {
+        const uint32_t v = (peek32() >> 1) >> (31 - k);
+        pos += (uint32_t)k;
+        return v;
+    }
+};
+
+// ---- fallback reader over the big-endian arena in global memory ---------------------------------
+// Three consecutive words are cached in registers (the third one raw, loaded a word ahead).  The
+// refill has no branch: the load is predicated and the window moves by selects, so lanes that cross
+// a word boundary and lanes that do not stay on one instruction stream.  Reads past the arena
+// return 0.  Positions are 32-bit and relative to the word the unit starts in.
+struct GlobalReader {
+    const uint32_t *words;
+    uint32_t wlimit;
+    uint32_t w0, w1, w2;
     uint32_t wi;
-    uint32_t pos, start;   // bit position relative to words[0]
+    uint32_t pos;
 
     __device__ __forceinline__ uint32_t load_raw(uint32_t w) const { return w < wlimit ? __ldg(words + w) : 0u; }
-    __device__ __forceinline__ uint32_t load(uint32_t w) const { return __byte_perm(load_raw(w), 0, 0x0123); }
     __device__ __forceinline__ void init(const uint8_t *arena, uint64_t arena_bytes, uint64_t bit_off)
     {
         const uint64_t w = bit_off >> 5, total = arena_bytes >> 2;
@@ -47,30 +90,46 @@ struct BitReader {
         const uint64_t left = total > w ? total - w : 0;
         wlimit = left > 0x7fffffffull ? 0x7fffffffu : (uint32_t)left;
         wi = 0;
-        w0 = load(0);
-        w1 = load(1);
+        w0 = __byte_perm(load_raw(0), 0, 0x0123);
+        w1 = __byte_perm(load_raw(1), 0, 0x0123);
         w2 = load_raw(2);
-        pos = start = (uint32_t)(bit_off & 31);
+        pos = (uint32_t)(bit_off & 31);
     }
-    __device__ __forceinline__ uint32_t consumed() const { return pos - start; }
-    // the next 32 bits, left aligned
+    __device__ __forceinline__ uint32_t bitpos() const { return pos; }
     __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_l(w1, w0, pos & 31); }
-    // k in 1..32
-    __device__ __forceinline__ uint32_t peek(int k) const { return peek32() >> (32 - k); }
+    __device__ __forceinline__ void peek64(uint32_t &hi, uint32_t &lo) const
+    {
+        const uint32_t sh = pos & 31;
+        hi = __funnelshift_l(w1, w0, sh);
+        lo = __funnelshift_l(__byte_perm(w2, 0, 0x0123), w1, sh);
+    }
+    __device__ __forceinline__ void advance()
+    {
+        const bool cross = (pos >> 5) != wi;
+        const uint32_t nxt = wi + 3;
+        const uint32_t ok = (cross && nxt < wlimit) ? 1u : 0u;
+        uint32_t nw = 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
+                     : "+r"(nw) : "l"(words + nxt), "r"(ok));
+        w0 = cross ? w1 : w0;
+        w1 = cross ? __byte_perm(w2, 0, 0x0123) : w1;
+        w2 = cross ? nw : w2;
+        wi += cross ? 1u : 0u;
+    }
     __device__ __forceinline__ void skip(int k) // k in 0..32
     {
         pos += (uint32_t)k;
-        if ((pos >> 5) != wi) {
-            wi++;
-            w0 = w1;
-            w1 = __byte_perm(w2, 0, 0x0123);
-            w2 = load_raw(wi + 2);
-        }
+        advance();
     }
-    __device__ __forceinline__ uint32_t get(int k) // k in 0..16
+    __device__ __forceinline__ void skip_long(int k) // k in 0..64: may cross two words (rare)
     {
-        if (k == 0) return 0;
-        uint32_t v = peek(k);
+        pos += (uint32_t)k;
+        advance();
+        if ((pos >> 5) != wi) advance();
+    }
+    __device__ __forceinline__ uint32_t get(int k)
+    {
+        const uint32_t v = (peek32() >> 1) >> (31 - k);
         skip(k);
         return v;
     }
@@ -88,41 +147,38 @@ __device__ __forceinline__ uint32_t bits_at(const uint8_t *arena, uint64_t arena
     return (uint32_t)((v << (bit & 31)) >> (64 - n));
 }
 
-constexpr int K1_THREADS = 256;
-
-__global__ void __launch_bounds__(K1_THREADS)
-k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitDesc *__restrict__ units,
-          uint32_t u_lo, uint32_t nunits, const uint16_t *__restrict__ g_lut, uint32_t lut_len,
-          const L3HuffInfo *__restrict__ g_info, const uint8_t *__restrict__ g_quad,
-          int16_t *__restrict__ is_out, uint8_t *__restrict__ sf_out, uint8_t *__restrict__ nzv_out, int zero_fill)
+// ---- TMA bulk copy global -> shared with an mbarrier for completion ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-    extern __shared__ uint16_t s_lut[];
-    __shared__ uint32_t s_info[32]; // base | root << 16 | linbits << 24
-    __shared__ uint8_t s_quad[64];
-    for (uint32_t i = threadIdx.x; i < lut_len; i += K1_THREADS) s_lut[i] = g_lut[i];
-    if (threadIdx.x < 32)
-        s_info[threadIdx.x] = g_info->base[threadIdx.x] | ((uint32_t)g_info->root[threadIdx.x] << 16) |
-                              ((uint32_t)g_info->linbits[threadIdx.x] << 24);
-    if (threadIdx.x < 64) s_quad[threadIdx.x] = g_quad[threadIdx.x];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
-    // Units of a CTA are regrouped by big_values so that the 32 lanes of a warp run loops of similar
-    // length (lanes stay converged inside an iteration; what is left to lose is the loop count).
-    __shared__ uint32_t s_hist[160];
-    __shared__ uint16_t s_perm[K1_THREADS];
-    const uint32_t cta_first = blockIdx.x * K1_THREADS;
-    for (int i = threadIdx.x; i < 160; i += K1_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    uint32_t bucket = 159; // units past the end sort last
-    if (cta_first + threadIdx.x < nunits) {
-        const L3UnitDesc *dp = units + u_lo + cta_first + threadIdx.x;
-        bucket = (dp->flags & L3F_VALID) ? (uint32_t)min((int)dp->big_values, 288) >> 1 : 0u;
-    }
-    atomicAdd(&s_hist[bucket], 1u);
-    __syncthreads();
-    if (threadIdx.x < 32) { // exclusive scan of 160 buckets: 5 per lane
+// exclusive scan of 160 histogram buckets by the first warp: 5 per lane
+__device__ __forceinline__ void cta_scan160(uint32_t *hist)
+{
+    if (threadIdx.x < 32) {
         uint32_t v[5], sum = 0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) { v[k] = s_hist[threadIdx.x * 5 + k]; sum += v[k]; }
+        for (int k = 0; k < 5; k++) { v[k] = hist[threadIdx.x * 5 + k]; sum += v[k]; }
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -131,27 +187,33 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         }
         uint32_t run = incl - sum;
 #pragma unroll
-        for (int k = 0; k < 5; k++) { s_hist[threadIdx.x * 5 + k] = run; run += v[k]; }
+        for (int k = 0; k < 5; k++) { hist[threadIdx.x * 5 + k] = run; run += v[k]; }
     }
-    __syncthreads();
-    s_perm[atomicAdd(&s_hist[bucket], 1u)] = (uint16_t)threadIdx.x;
-    __syncthreads();
+}
 
-    uint32_t u = cta_first + s_perm[threadIdx.x];
-    if (u >= nunits) return;
-    u += u_lo;
-    const L3UnitDesc d = units[u];
-    const bool valid = (d.flags & L3F_VALID) != 0;
+struct K1Shared {
+    uint32_t info[32];        // per table_select: base | root << 16 | linbits << 24
+    uint8_t quad[128];        // count1 book A (6-bit peek), then book B (4-bit code = 15 - value)
+    uint2 c1[256];            // (symbol vwxy << 4 | next 4 bits) -> the four signed lines, packed
+    uint32_t hist[160];
+    uint16_t perm[K1_CHUNK];  // sorted order -> slot (unit of the chunk)
+    uint32_t state[K1_CHUNK]; // per slot after the pair loop: bits consumed (13) | line index (10) << 13 | dead << 31
+    uint8_t est[K1_CHUNK];    // per slot: estimated count1 iterations (sort key)
+    unsigned long long lo_bit, hi_bit; // bit range of the chunk's main data in the arena
+    uint32_t next;            // group counter of the running phase
+    __align__(8) uint64_t bar;
+};
+
+// ---------------------------------------------------------------- part 2: scalefactors (a4)
+template <class R>
+__device__ __forceinline__ void read_scalefactors(R &br, const L3UnitDesc &d, uint32_t u, bool valid,
+                                                  const L3UnitDesc *__restrict__ units,
+                                                  const uint8_t *__restrict__ arena, uint64_t arena_bytes,
+                                                  uint32_t (&sfw)[10])
+{
     const int bt = d.flags & L3F_BT_MASK;
     const bool mixed = (d.flags & L3F_MIXED) != 0;
     const bool lsf = (d.hdr & L3H_LSF) != 0;
-    const uint32_t p23 = d.p23len;
-
-    BitReader br;
-    br.init(arena, arena_bytes, d.bit_off);
-
-    // ---------------------------------------------------------------- part 2: scalefactors (a4)
-    uint32_t sfw[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) sfw[i] = 0;
     if (valid) {
@@ -223,110 +285,346 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
             }
         }
     }
-    {
-        uint2 *o = reinterpret_cast<uint2 *>(sf_out + (size_t)u * 40);
-#pragma unroll
-        for (int i = 0; i < 5; i++) o[i] = make_uint2(sfw[2 * i], sfw[2 * i + 1]);
-    }
+}
 
-    // ---------------------------------------------------------------- part 3: Huffman (a5)
-    uint4 *out = reinterpret_cast<uint4 *>(is_out + (size_t)u * 576);
-    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0; // shift register of packed (x, y) pairs
-    int npairs = 0, nst = 0;
-    auto push = [&](int x, int y) {
-        q0 = q1; q1 = q2; q2 = q3;
-        q3 = ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
-        if (++npairs == 4) {
-            out[nst++] = make_uint4(q0, q1, q2, q3);
-            npairs = 0;
-        }
-    };
-
+// ---------------------------------------------------------------- part 3a: big_values pairs (a5)
+// Returns the state word of the unit: bits consumed | line index << 13.
+// The loop is bound by the integer (ALU) pipe, so it is written to keep that pipe's instruction
+// count down: the table of the current region lives in registers and changes in a rarely taken
+// branch; "the unit ran out of bits" is simply `position >= limit` (positions never move back, so
+// no sticky flag: a pair that starts past the limit decodes to (0, 0) and consumes nothing, exactly
+// what stopping at the first such pair does); the empty book is a real table whose two leaves are
+// (0, 0) of length 0; bit fields come out of the stream with single funnel shifts; four pairs are
+// decoded per trip, so the 16-byte store needs no shift register.
+template <class R>
+__device__ __forceinline__ uint32_t decode_pairs(R &br, uint32_t start, const L3UnitDesc &d, bool valid,
+                                                 const uint16_t *__restrict__ s_lut, const K1Shared &S,
+                                                 uint32_t *__restrict__ out32)
+{
+    uint4 *out = reinterpret_cast<uint4 *>(out32);
     const int bv2 = valid ? d.big_values * 2 : 0;
     const int r1 = d.r1, r2 = d.r2;
-    const uint32_t i0 = s_info[d.tsel[0]], i1 = s_info[d.tsel[1]], i2 = s_info[d.tsel[2]];
-    bool dead = !valid;
-    for (int i = 0; i < bv2; i += 2) {
-        // One pair per iteration, written without branches: lanes differ in table, code length and
-        // escapes, but all of that is data (selects and predicated loads), not control flow.
-        const uint32_t info = i < r1 ? i0 : (i < r2 ? i1 : i2);
-        const int root = (info >> 16) & 0xff; // 0 = the empty book: (0, 0), no bits
-        dead = dead || (root != 0 && br.consumed() >= p23);
-        const bool act = root != 0 && !dead;
-        const uint32_t base = info & 0xffffu;
-        const int lin = (int)(info >> 24);
+    const uint32_t limit = start + d.p23len;
+    int i = 0, nst = 0;
+    // current region: table info unpacked, and the line at which the next region starts
+    int reg = -1, nextb = 0;
+    uint32_t base = 0;
+    int root = 1, lin = 0;
+    auto one = [&]() -> uint32_t {
+        if (i >= nextb) { // region change: at most three times per unit
+            uint32_t info;
+            do {
+                reg++;
+                info = S.info[reg == 0 ? d.tsel[0] : (reg == 1 ? d.tsel[1] : d.tsel[2])];
+                nextb = reg == 0 ? r1 : (reg == 1 ? r2 : 0x7fffffff);
+            } while (i >= nextb);
+            base = info & 0xffffu;
+            root = (int)((info >> 16) & 0xffu);
+            lin = (int)(info >> 24);
+        }
+        const bool act = br.bitpos() < limit;
         // 64 bits of look-ahead: code (<= 19) + escapes and signs (<= 28)
-        const uint32_t sh = br.pos & 31;
-        const uint32_t hi = __funnelshift_l(br.w1, br.w0, sh);
-        const uint32_t lo = __funnelshift_l(__byte_perm(br.w2, 0, 0x0123), br.w1, sh);
-        uint32_t e = s_lut[base + ((hi >> 1) >> (31 - root))];
-        int len = (e >> 8) & 15;
-        if (e & 0x8000u) { // longer than the root: one second-level lookup covers the rest
-            const int w2 = (e >> 11) & 15;
-            e = s_lut[base + (e & 0x7ffu) + ((hi << root) >> (32 - w2))];
-            len = root + ((e >> 8) & 15);
-        }
+        uint32_t hi, lo;
+        br.peek64(hi, lo);
+        const uint32_t e1 = s_lut[base + __funnelshift_l(hi, 0u, root)];
+        // codes longer than the root: one second-level lookup covers the rest
+        // (always issued, as selects: a branch here would split the warp on almost every pair)
+        const bool lng = (e1 & 0x8000u) != 0;
+        const uint32_t w2 = (e1 >> 11) & 15u;
+        const uint32_t sub = lng ? (e1 & 0x7ffu) + __funnelshift_l(hi << root, 0u, w2) : 0u;
+        const uint32_t e2 = s_lut[base + sub];
+        const uint32_t e = lng ? e2 : e1;
+        const int len = (int)((e >> 8) & 15u) + (lng ? root : 0);
         int x = (e >> 4) & 15, y = e & 15;
-        const uint32_t rest = __funnelshift_l(lo, hi, len);
+        uint32_t rest = __funnelshift_l(lo, hi, len);
         const int lx = x == 15 ? lin : 0;
-        x += (int)((rest >> 1) >> (31 - lx));
-        int n = lx;
+        x += (int)__funnelshift_l(rest, 0u, lx);
+        rest <<= lx;
         const int sx = x != 0;
-        if (((rest << n) >> 31) & sx) x = -x;
-        n += sx;
+        {
+            const int m = (int)rest >> 31; // sign bit (consumed only when x != 0; negating 0 gives 0 anyway)
+            x = (x ^ m) - m;
+        }
+        rest <<= sx;
         const int ly = y == 15 ? lin : 0;
-        y += (int)(((rest << n) >> 1) >> (31 - ly));
-        n += ly;
+        y += (int)__funnelshift_l(rest, 0u, ly);
+        rest <<= ly;
         const int sy = y != 0;
-        if (((rest << n) >> 31) & sy) y = -y;
-        n += sy;
-        if (!act) { x = 0; y = 0; len = 0; n = 0; }
-        br.skip(len);
-        br.skip(n);
-        push(x, y);
+        {
+            const int m = (int)rest >> 31;
+            y = (y ^ m) - m;
+        }
+        const int n = len + lx + sx + ly + sy;
+        br.skip_long(act ? n : 0);
+        i += 2;
+        return act ? __byte_perm((uint32_t)x, (uint32_t)y, 0x5410) : 0u;
+    };
+    while (i + 8 <= bv2) { // whole 16-byte vectors: the same trips for every lane of a sorted group
+        const uint32_t a = one(), b = one(), c = one(), e = one();
+        out[nst++] = make_uint4(a, b, c, e);
     }
-    // count1 quadruples
-    {
-        const bool tab_b = (d.flags & L3F_C1TAB) != 0;
-        int i = bv2;
-        while (!dead && i <= 572 && br.consumed() < p23) {
-            const uint32_t bits = br.peek32(); // code (<= 6 bits) + up to 4 sign bits
-            int sym, len;
-            if (tab_b) { sym = 15 - (int)(bits >> 28); len = 4; }
-            else { uint32_t e = s_quad[bits >> 26]; sym = e & 15; len = e >> 4; }
-            const uint32_t s4 = (bits << len) >> 28;
-            int k = 0, v = 0, w = 0, x = 0, y = 0;
-            if (sym & 8) { v = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
-            if (sym & 4) { w = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
-            if (sym & 2) { x = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
-            if (sym & 1) { y = ((s4 >> (3 - k)) & 1) ? -1 : 1; k++; }
-            br.skip(len + k);
-            if (br.consumed() > p23) break; // overran part2_3_length: discard this quadruple
-            push(v, w);
-            push(x, y);
-            i += 4;
+    if (i < bv2) { // up to 3 pairs more, as single words (the count1 loop stores words as well)
+        uint32_t *o = out32 + nst * 4;
+        o[0] = one();
+        if (i < bv2) {
+            o[1] = one();
+            if (i < bv2) o[2] = one();
         }
     }
-    // flush the partial vector (zero padded).  The all-zero tail of the spectrum is not written:
-    // nzv_out[u] tells the consumer how many 16-byte vectors (8 lines each) hold data, and it treats
-    // the rest as zero.  zero_fill (staged pipeline, parity dumps) writes the tail anyway.
-    if (npairs) {
-        while (npairs) push(0, 0);
+    return min(br.bitpos() - start, 8191u) | ((uint32_t)i << 13);
+}
+
+// ---------------------------------------------------------------- part 3b: count1 quadruples (a5)
+// code (<= 6 bits) + up to 4 sign bits per iteration; returns the line index after the last one
+template <class R>
+__device__ __forceinline__ int decode_count1(R &br, uint32_t limit, int i, uint32_t qoff, const K1Shared &S,
+                                             uint32_t *__restrict__ out32)
+{
+    while (i <= 572 && br.bitpos() < limit) {
+        const uint32_t bits = br.peek32();
+        const uint32_t e = S.quad[qoff + (bits >> 26)];
+        const uint32_t sym = e & 15u, len = e >> 4;
+        const uint32_t s4 = (bits << len) >> 28;
+        br.skip((int)(len + __popc(sym)));
+        if (br.bitpos() > limit) break; // overran part2_3_length: discard this quadruple
+        const uint2 vw = S.c1[(sym << 4) | s4];
+        out32[i >> 1] = vw.x;
+        out32[(i >> 1) + 1] = vw.y;
+        i += 4;
     }
-    nzv_out[u] = (uint8_t)nst;
-    if (zero_fill)
-        for (int k = nst; k < 72; k++) out[k] = make_uint4(0, 0, 0, 0);
+    return i;
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitDesc *__restrict__ units,
+          uint32_t u_lo, uint32_t nunits, const uint16_t *__restrict__ g_lut, uint32_t lut_len,
+          uint32_t stage_bytes, uint32_t chunk, const L3HuffInfo *__restrict__ g_info, const uint8_t *__restrict__ g_quad,
+          int16_t *__restrict__ is_out, uint8_t *__restrict__ sf_out, uint8_t *__restrict__ nzv_out, int zero_fill)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ K1Shared S;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);                // stage_bytes
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw + stage_bytes);  // lut_len entries
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t chunk_first = blockIdx.x * chunk;
+    const int n = (int)min(chunk, nunits - chunk_first);
+    const L3UnitDesc *cu = units + u_lo + chunk_first;
+
+    // ---- tables, histogram, the chunk's bit range
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        S.lo_bit = ~0ull;
+        S.hi_bit = 0ull;
+        S.next = 0;
+    }
+    for (int k = tid; k < 160; k += K1_THREADS) S.hist[k] = 0;
+    __syncthreads();
+    uint32_t bucket[2];
+    {
+        unsigned long long lo = ~0ull, hi = 0ull;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int slot = tid + r * K1_THREADS;
+            bucket[r] = 0;
+            if (slot < n) {
+                const L3UnitDesc dd = cu[slot];
+                if (dd.flags & L3F_VALID) {
+                    bucket[r] = (uint32_t)min((int)dd.big_values, 288) >> 1;
+                    lo = min(lo, (unsigned long long)dd.bit_off);
+                    hi = max(hi, (unsigned long long)dd.bit_off + dd.p23len);
+                }
+                atomicAdd(&S.hist[bucket[r]], 1u);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0 && hi) {
+            atomicMin(&S.lo_bit, lo);
+            atomicMax(&S.hi_bit, hi);
+        }
+    }
+    __syncthreads();
+    // stage the range [a0, a1) if it fits: one TMA bulk copy, issued now, awaited after the sort
+    const uint64_t a0 = S.hi_bit ? ((S.lo_bit >> 3) & ~15ull) : 0ull;
+    const uint64_t a1 = S.hi_bit ? ((((S.hi_bit + 7) >> 3) + K1_TAIL_PAD + 15) & ~15ull) : 0ull;
+    const bool staged = a1 - a0 <= stage_bytes;
+    const uint32_t span = (uint32_t)(a1 - a0);
+    const uint32_t ncopy = staged ? (uint32_t)(min(a1, arena_bytes) > a0 ? min(a1, arena_bytes) - a0 : 0ull) : 0u;
+    if (tid == 0 && ncopy) {
+        mbar_expect_tx(&S.bar, ncopy);
+        bulk_g2s(stage, arena + a0, ncopy, &S.bar);
+    }
+    for (uint32_t k = tid; k < lut_len; k += K1_THREADS) s_lut[k] = g_lut[k];
+    if (tid < 32)
+        S.info[tid] = g_info->base[tid] | ((uint32_t)g_info->root[tid] << 16) | ((uint32_t)g_info->linbits[tid] << 24);
+    if (tid < 64) S.quad[tid] = g_quad[tid];
+    else if (tid < 128) S.quad[tid] = (uint8_t)((4u << 4) | (15u - ((tid - 64u) >> 2)));
+    {
+        const uint32_t sym = tid >> 4, s4 = tid & 15u;
+        uint32_t val[4], k = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            val[c] = 0;
+            if (sym & (8u >> c)) { val[c] = ((s4 >> (3 - k)) & 1u) ? 0xffffu : 1u; k++; }
+        }
+        S.c1[tid] = make_uint2(val[0] | (val[1] << 16), val[2] | (val[3] << 16));
+    }
+    // sort the chunk by big_values, longest first
+    cta_scan160(S.hist);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int slot = tid + r * K1_THREADS;
+        if (slot < n) S.perm[n - 1 - (int)atomicAdd(&S.hist[bucket[r]], 1u)] = (uint16_t)slot;
+    }
+    if (ncopy) {
+        mbar_wait(&S.bar, 0);
+        for (uint32_t k = tid; k < (ncopy >> 2); k += K1_THREADS) stage[k] = __byte_perm(stage[k], 0, 0x0123);
+    }
+    if (staged)
+        for (uint32_t k = (ncopy >> 2) + tid; k < (span >> 2); k += K1_THREADS) stage[k] = 0u; // past the arena
+    __syncthreads();
+    for (int k = tid; k < 160; k += K1_THREADS) S.hist[k] = 0; // reused by the count1 sort
+    __syncthreads();
+
+    const int ngroups = (n + 31) >> 5;
+    // ---- phase 1: scalefactors + big_values pairs; warps pull groups of 32 units, longest first
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&S.next, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if ((int)g >= ngroups) break;
+        const int idx = (int)g * 32 + lane;
+        if (idx >= n) continue;
+        const uint32_t slot = S.perm[idx];
+        const uint32_t u = u_lo + chunk_first + slot;
+        const L3UnitDesc d = units[u];
+        const bool valid = (d.flags & L3F_VALID) != 0;
+        uint32_t sfw[10];
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(is_out + (size_t)u * 576);
+        uint32_t stw;
+        if (staged) {
+            SmemReader br;
+            br.init(stage, valid ? (uint32_t)(d.bit_off - a0 * 8) : 0u);
+            const uint32_t start = br.bitpos();
+            read_scalefactors(br, d, u, valid, units, arena, arena_bytes, sfw);
+            stw = decode_pairs(br, start, d, valid, s_lut, S, out32);
+        } else {
+            GlobalReader br;
+            br.init(arena, arena_bytes, d.bit_off);
+            const uint32_t start = br.bitpos();
+            read_scalefactors(br, d, u, valid, units, arena, arena_bytes, sfw);
+            stw = decode_pairs(br, start, d, valid, s_lut, S, out32);
+        }
+        {
+            uint2 *o = reinterpret_cast<uint2 *>(sf_out + (size_t)u * 40);
+#pragma unroll
+            for (int k = 0; k < 5; k++) o[k] = make_uint2(sfw[2 * k], sfw[2 * k + 1]);
+        }
+        // count1 work left, estimated from the bits left (the sort key of phase 2)
+        uint32_t est = 0;
+        if (!(stw & 0x80000000u)) {
+            const int used = (int)(stw & 0x1fffu), i = (int)((stw >> 13) & 0x3ffu);
+            const int by_bits = ((int)d.p23len - used + 3) >> 2, by_lines = (576 - i) >> 2;
+            est = (uint32_t)max(0, min(min(by_bits, by_lines) + 1, 159));
+        }
+        S.state[slot] = stw;
+        S.est[slot] = (uint8_t)est;
+        atomicAdd(&S.hist[est], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) S.next = 0;
+    cta_scan160(S.hist);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int slot = tid + r * K1_THREADS;
+        if (slot < n) S.perm[n - 1 - (int)atomicAdd(&S.hist[S.est[slot]], 1u)] = (uint16_t)slot;
+    }
+    __syncthreads();
+
+    // ---- phase 2: count1 quadruples, zero padding of the last vector, vector counts
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&S.next, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if ((int)g >= ngroups) break;
+        const int idx = (int)g * 32 + lane;
+        if (idx >= n) continue;
+        const uint32_t slot = S.perm[idx];
+        const uint32_t u = u_lo + chunk_first + slot;
+        const L3UnitDesc d = units[u];
+        const uint32_t stw = S.state[slot];
+        const uint32_t used = stw & 0x1fffu, p23 = d.p23len;
+        int i = (int)((stw >> 13) & 0x3ffu);
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(is_out + (size_t)u * 576);
+        if (!(stw & 0x80000000u) && used < p23) {
+            const uint32_t qoff = (d.flags & L3F_C1TAB) ? 64u : 0u;
+            if (staged) {
+                SmemReader br;
+                br.init(stage, (uint32_t)(d.bit_off - a0 * 8) + used);
+                i = decode_count1(br, br.bitpos() + (p23 - used), i, qoff, S, out32);
+            } else {
+                GlobalReader br;
+                br.init(arena, arena_bytes, d.bit_off + used);
+                i = decode_count1(br, br.bitpos() + (p23 - used), i, qoff, S, out32);
+            }
+        }
+        // zero the rest of the last 16-byte vector.  The all-zero tail of the spectrum is not written:
+        // nzv_out[u] tells the consumer how many 16-byte vectors (8 lines each) hold data, and it treats
+        // the rest as zero.  zero_fill (staged pipeline, parity dumps) writes the tail anyway.
+        const int nst = (i + 7) >> 3;
+        for (int k = i >> 1; k < nst * 4; k++) out32[k] = 0u;
+        nzv_out[u] = (uint8_t)nst;
+        if (zero_fill) {
+            uint4 *out = reinterpret_cast<uint4 *>(out32);
+            for (int k = nst; k < 72; k++) out[k] = make_uint4(0, 0, 0, 0);
+        }
+    }
 }
 
 } // namespace
 
 void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
-                             uint32_t nunits, const L3DevTables &T, int16_t *is_out, uint8_t *sf_out,
-                             uint8_t *nzv_out, int zero_fill, cudaStream_t st)
+                             uint32_t nunits, uint32_t avg_unit_bytes, const L3DevTables &T, int16_t *is_out,
+                             uint8_t *sf_out, uint8_t *nzv_out, int zero_fill, cudaStream_t st)
 {
     if (!nunits) return;
-    size_t smem = (size_t)T.huff_lut_len * sizeof(uint16_t);
-    k_huffman<<<(nunits + K1_THREADS - 1) / K1_THREADS, K1_THREADS, smem, st>>>(
-        arena, arena_bytes, units, u_lo, nunits, T.huff_lut, T.huff_lut_len, T.huff, T.quad_a, is_out, sf_out,
-        nzv_out, zero_fill);
+    // stage size: the average chunk plus slack, bounded so that at least one CTA fits an SM; chunks
+    // that do not fit (high bitrates, VBR peaks) take the global-memory reader
+    static int configured = 0;
+    if (!configured) {
+        cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = 1;
+    }
+    const uint64_t lut_bytes = ((uint64_t)T.huff_lut_len * sizeof(uint16_t) + 15) & ~15ull;
+    // Chunk length and stage size: as many CTAs per SM as still leave every warp a few groups to pull.
+    // The stage holds the chunk's main data (average bytes per unit plus slack); a chunk whose range
+    // does not fit (VBR peaks) takes the global-memory reader.
+    static long f_stage = -1, f_chunk = -1;
+    if (f_stage < 0) {
+        const char *e = getenv("MP3B_K1_STAGE"), *c = getenv("MP3B_K1_CHUNK");
+        f_stage = e ? atol(e) : 0;
+        f_chunk = c ? atol(c) : 0;
+    }
+    const uint64_t per_unit = (uint64_t)avg_unit_bytes + avg_unit_bytes / 24 + 1;
+    const uint64_t fixed = lut_bytes + 6656 + 1024; // LUT, static shared memory, per-CTA reservation
+    uint64_t want = 0;
+    uint32_t chunk = 0;
+    for (int k = 3; k >= 1 && chunk < 320; k--) { // prefer 3 CTAs per SM if they get >= 10 groups each
+        const uint64_t budget = (227ull * 1024 / k - fixed) & ~15ull;
+        uint64_t c = (budget - 1280) / per_unit / 32 * 32;
+        c = c > K1_CHUNK ? K1_CHUNK : c;
+        if (c >= 32) { chunk = (uint32_t)c; want = (c * per_unit + 1280 + 15) & ~15ull; }
+    }
+    if (!chunk) { chunk = 32; want = 32 * 1024; }
+    if (f_chunk > 0) { chunk = (uint32_t)(f_chunk > K1_CHUNK ? K1_CHUNK : f_chunk) / 32 * 32; want = (chunk * per_unit + 1280 + 15) & ~15ull; }
+    if (f_stage > 0) want = ((uint64_t)f_stage + 15) & ~15ull;
+    const size_t smem = (size_t)(want + lut_bytes);
+    k_huffman<<<(nunits + chunk - 1) / chunk, K1_THREADS, smem, st>>>(
+        arena, arena_bytes, units, u_lo, nunits, T.huff_lut, T.huff_lut_len, (uint32_t)want, chunk, T.huff, T.quad_a,
+        is_out, sf_out, nzv_out, zero_fill);
 }

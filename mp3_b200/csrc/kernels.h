@@ -39,8 +39,10 @@ void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, cons
 /* K1: scalefactor + Huffman / count1 decode (a4, a5) */
 /* arena_bytes: readable size of the main-data arena (a multiple of 4; reads beyond it return 0) */
 /* units [u_lo, u_lo + nunits); output arrays are indexed by absolute unit id */
+/* avg_unit_bytes: average main-data bytes per unit of the batch (sizes the shared-memory bit stage) */
 void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
-                             uint32_t nunits, const L3DevTables &T, int16_t *is_out, uint8_t *sf_out,
+                             uint32_t nunits, uint32_t avg_unit_bytes, const L3DevTables &T, int16_t *is_out,
+                             uint8_t *sf_out,
                              uint8_t *nzv_out /* [unit]: 16-byte vectors of is_out that hold data */,
                              int zero_fill /* also write the all-zero tail */, cudaStream_t st);
 

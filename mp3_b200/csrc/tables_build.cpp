@@ -64,17 +64,22 @@ extern "C" void l3_build_host_tables(L3HostTables *t)
         int root = std::min(mx, L3_HUFF_ROOT_BITS);
         std::vector<uint16_t> lut((size_t)1 << root, 0);
         fill_level(lut, 0, root, 0, items);
-        if (total + lut.size() > L3_HUFF_LUT_MAX || lut.size() > 2048) return; // cannot happen
+        if (total + lut.size() + 2 > L3_HUFF_LUT_MAX || lut.size() > 2048) return; // cannot happen
         std::memcpy(t->huff_lut + total, lut.data(), lut.size() * sizeof(uint16_t));
         book_base[book] = (uint16_t)total;
         book_root[book] = (uint8_t)root;
         total += (uint32_t)lut.size();
     }
+    // the empty book (table_select 0, 4, 14) as a real one-bit table: two leaves (0, 0) of length 0,
+    // so the decoder needs no special case for it
+    t->huff_lut[total] = t->huff_lut[total + 1] = 0;
+    const uint32_t empty_base = total;
+    total += 2;
     t->huff_lut_len = total;
     for (int ts = 0; ts < 32; ts++) {
         int book = l3_book_of_table[ts];
-        t->huff.base[ts] = book_base[book];
-        t->huff.root[ts] = book_root[book];
+        t->huff.base[ts] = book ? book_base[book] : (uint16_t)empty_base;
+        t->huff.root[ts] = book ? book_root[book] : 1;
         t->huff.linbits[ts] = l3_linbits_of_table[ts];
     }
     for (int v = 0; v < 64; v++)
