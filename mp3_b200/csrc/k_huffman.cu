@@ -41,12 +41,33 @@ constexpr int K1_THREADS = 256;
 constexpr int K1_CHUNK = 512;       // most units per CTA (16 groups of 32 for 8 warps)
 constexpr int K1_TAIL_PAD = 160;    // bytes staged beyond the last unit's part2_3 end (look-ahead, overruns)
 
+__device__ __forceinline__ uint32_t bits_at(const uint8_t *arena, uint64_t arena_bytes, uint64_t bit, int n);
+
 // ---- bit reader over the staged (shared memory, already in bit order) main data -----------------
 struct SmemReader {
     const uint32_t *w;
-    uint32_t pos; // bit position relative to the stage start
+    uint32_t pos;       // bit position relative to the stage start
+    uint64_t base_bit;  // arena bit offset of the stage start
+    uint32_t span_bits; // staged bits
 
-    __device__ __forceinline__ void init(const uint32_t *stage, uint32_t bit) { w = stage; pos = bit; }
+    __device__ __forceinline__ void init(const uint32_t *stage, uint32_t bit, uint64_t stage_bit0, uint32_t nbits)
+    {
+        w = stage;
+        pos = bit;
+        base_bit = stage_bit0;
+        span_bits = nbits;
+    }
+    // n (0..5) bits at an absolute arena position (scfsi reuse): from the stage when it covers them
+    __device__ __forceinline__ uint32_t bits_abs(const uint8_t *arena, uint64_t arena_bytes, uint64_t bit, int n) const
+    {
+        const uint64_t rel = bit - base_bit;
+        if (bit >= base_bit && rel + 64 <= span_bits) {
+            const uint32_t r = (uint32_t)rel;
+            const uint32_t *q = w + (r >> 5);
+            return __funnelshift_l(__funnelshift_l(q[1], q[0], r), 0u, n);
+        }
+        return bits_at(arena, arena_bytes, bit, n);
+    }
     __device__ __forceinline__ uint32_t bitpos() const { return pos; }
     __device__ __forceinline__ uint32_t peek32() const
     {
@@ -94,6 +115,10 @@ struct GlobalReader {
         w1 = __byte_perm(load_raw(1), 0, 0x0123);
         w2 = load_raw(2);
         pos = (uint32_t)(bit_off & 31);
+    }
+    __device__ __forceinline__ uint32_t bits_abs(const uint8_t *arena, uint64_t arena_bytes, uint64_t bit, int n) const
+    {
+        return bits_at(arena, arena_bytes, bit, n);
     }
     __device__ __forceinline__ uint32_t bitpos() const { return pos; }
     __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_l(w1, w0, pos & 31); }
@@ -254,7 +279,7 @@ __device__ __forceinline__ void read_scalefactors(R &br, const L3UnitDesc &d, ui
                         int w0 = b < g0_n1 ? g0_s1 : (b < g0_ntot ? g0_s2 : 0);
                         uint64_t off = b < g0_n1 ? (uint64_t)(b * g0_s1)
                                                  : (uint64_t)(g0_n1 * g0_s1 + (b - g0_n1) * g0_s2);
-                        v = bits_at(arena, arena_bytes, g0_bit + off, w0);
+                        v = br.bits_abs(arena, arena_bytes, g0_bit + off, w0);
                     } else
                         v = br.get(b < 11 ? s1 : s2);
                     sfw[b >> 2] |= v << (8 * (b & 3));
@@ -508,7 +533,7 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         uint32_t stw;
         if (staged) {
             SmemReader br;
-            br.init(stage, valid ? (uint32_t)(d.bit_off - a0 * 8) : 0u);
+            br.init(stage, valid ? (uint32_t)(d.bit_off - a0 * 8) : 0u, a0 * 8, span * 8);
             const uint32_t start = br.bitpos();
             read_scalefactors(br, d, u, valid, units, arena, arena_bytes, sfw);
             stw = decode_pairs(br, start, d, valid, s_lut, S, out32);
@@ -565,7 +590,7 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
             const uint32_t qoff = (d.flags & L3F_C1TAB) ? 64u : 0u;
             if (staged) {
                 SmemReader br;
-                br.init(stage, (uint32_t)(d.bit_off - a0 * 8) + used);
+                br.init(stage, (uint32_t)(d.bit_off - a0 * 8) + used, a0 * 8, span * 8);
                 i = decode_count1(br, br.bitpos() + (p23 - used), i, qoff, S, out32);
             } else {
                 GlobalReader br;
