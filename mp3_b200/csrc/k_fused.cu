@@ -76,11 +76,15 @@ struct FusedShared {
     uint8_t mode[KF_B][40];         // 1 = intensity-coded band
     GranMeta gm[KF_B];
     int any_ist;
+    int any_short;                  // some unit of the batch has short / mixed blocks
     // next batch's Huffman output and scalefactors, fetched with cp.async while this batch computes
     __align__(16) int16_t is_buf[KF_B * 2][576];
     __align__(16) uint8_t sf_buf[KF_B * 2][40];
     __align__(8) uint64_t bar;  // mbarrier: completion of the bulk copies into is_buf
 };
+
+// f_pow2q[q & 3] * 2^(q >> 2), exactly (q >> 2 stays within the normal exponent range: -82 .. 11)
+__device__ __forceinline__ float gain_of(int q) { return __int_as_float((127 + (q >> 2)) << 23) * f_pow2q[q & 3]; }
 
 __device__ __forceinline__ int xpad(int i) { return i + ((i * 3641) >> 16); } // i + i / 18 for i < 608
 
@@ -179,7 +183,7 @@ __device__ __forceinline__ void load_meta(FusedShared &S, int tid, uint32_t u_fi
         (&S.nz[0][0])[i] = 0;
         (&S.mode[0][0])[i] = 0;
     }
-    if (tid == 0) S.any_ist = 0;
+    if (tid == 0) { S.any_ist = 0; S.any_short = 0; }
 }
 
 __device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int nch)
@@ -194,6 +198,7 @@ __device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int
         m.ist = (nch == 2 && ok && (m.d[0].hdr & L3H_IS)) ? 1 : 0;
         m.joint = m.ms | m.ist;
         if (m.ist) S.any_ist = 1;
+        if (m.lay[0] | (nch == 2 ? m.lay[1] : 0)) S.any_short = 1;
     }
 }
 
@@ -211,10 +216,11 @@ __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int
                 const int s = S.sf_buf[gi * nch + c][b] & 0x7f;
                 const int sh = (dd.flags & L3F_SFSCALE) ? 4 : 2;
                 const int q = (int)dd.global_gain - 210 - sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[b] : 0));
-                S.gain[gi][c][b] = ldexpf(f_pow2q[q & 3], q >> 2);
+                S.gain[gi][c][b] = gain_of(q);
             }
         }
     }
+    if (S.any_short)
     for (int it = tid; it < nb * 80; it += KF_THREADS) {
         const int gi = it / 80, c = (it % 80) / 40, b = it % 40;
         if (c >= nch) continue;
@@ -230,7 +236,7 @@ __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int
             int q = (int)dd.global_gain - 210;
             if (win < 0) q -= sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[bands->sfb[m.row][lay][b]] : 0));
             else q -= 8 * dd.sbg[win] + sh * s;
-            gn = ldexpf(f_pow2q[q & 3], q >> 2);
+            gn = gain_of(q);
         }
         S.gain[gi][c][b] = gn;
     }
@@ -594,9 +600,9 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                 const uint32_t bytes = (uint32_t)((nb - first_out) * 576 * nch) * (uint32_t)sizeof(pcm_t);
                 bulk_s2g(reinterpret_cast<pcm_t *>(pcm) + e0, stage + (size_t)first_out * 576 * nch, bytes);
             }
-            for (int i = tid; i < 2 * 15 * FS; i += KF_THREADS) {
-                const int c = i / (15 * FS), k = i % (15 * FS);
-                S.F[c][0][k] = S.F[c][nb * 18][k];
+            for (int k = tid; k < 15 * FS; k += KF_THREADS) {
+                S.F[0][0][k] = S.F[0][nb * 18][k];
+                S.F[1][0][k] = S.F[1][nb * 18][k];
             }
         }
         __syncthreads();
