@@ -65,6 +65,10 @@ typedef struct mp3b_opts {
     int32_t pipeline;      /* mp3b_pipeline */
     int32_t host_threads;  /* host indexer / gather threads; 0 = hardware concurrency */
     int32_t keep_stages;   /* 1 = keep intermediates addressable through mp3b_debug_stage */
+    int32_t async_index;   /* 1 (default) = the frame walk of a decode call runs ahead on a private CUDA
+                              stream, overlapping the previous call's kernels.  Device-resident input must
+                              then be completely written when the call is made (it is not ordered behind
+                              work the caller queued on the context's stream).  0 = strictly stream-ordered. */
 } mp3b_opts;
 
 typedef struct mp3b_stream_info {

@@ -30,7 +30,8 @@ class Mp3bError(RuntimeError):
 
 class Opts(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("pcm_format", ctypes.c_int32), ("indexer", ctypes.c_int32),
-                ("pipeline", ctypes.c_int32), ("host_threads", ctypes.c_int32), ("keep_stages", ctypes.c_int32)]
+                ("pipeline", ctypes.c_int32), ("host_threads", ctypes.c_int32), ("keep_stages", ctypes.c_int32),
+                ("async_index", ctypes.c_int32)]
 
 
 class StreamInfo(ctypes.Structure):
@@ -172,13 +173,15 @@ class Decoder:
     """One context on one GPU (mp3b_ctx).  Not thread-safe; use one per GPU."""
 
     def __init__(self, device=0, pcm_format=PCM_S16, indexer=INDEX_DEVICE, pipeline=None, host_threads=0,
-                 keep_stages=False):
+                 keep_stages=False, async_index=None):
         self.L = load_library()
         o = Opts()
         self.L.mp3b_opts_default(ctypes.byref(o))
         o.pcm_format, o.indexer, o.host_threads, o.keep_stages = pcm_format, indexer, host_threads, int(keep_stages)
         if pipeline is not None:
             o.pipeline = pipeline
+        if async_index is not None:
+            o.async_index = int(bool(async_index))
         self.pcm_format = pcm_format
         ctx = ctypes.c_void_p()
         rc = self.L.mp3b_ctx_create(device, ctypes.byref(o), ctypes.byref(ctx))

@@ -92,6 +92,10 @@ struct mp3b_ctx {
     cudaStream_t stream = nullptr;     // the stream work is enqueued on
     cudaStream_t own_stream = nullptr; // created by the context
     cudaStream_t copy_stream = nullptr; // D2H of finished waves (PCM sink)
+    cudaStream_t index_stream = nullptr; // run-ahead frame walk (opts.async_index)
+    cudaEvent_t walk_done = nullptr, walk_t0 = nullptr, walk_t1 = nullptr;
+    bool walk_timed = false;
+    int idx_cur = 0;                     // which set of (raw, stream records, walk scratch) the last call used
     std::vector<cudaEvent_t> wave_ev;
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t staging_done = nullptr; // the last H2D out of the pinned staging tables has executed
@@ -105,7 +109,11 @@ struct mp3b_ctx {
     L3DevTables T{};
 
     // per-batch device state
-    DevBuf d_raw, d_streams, d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_pcm2, d_scratch;
+    // Two sets of the buffers the frame walk touches: the walk of call N+1 runs on its own stream while
+    // call N's kernels are still queued, so it must not overwrite what call N's side-info / payload
+    // kernels read.
+    DevBuf d_raw[2], d_streams[2], d_scratch[2];
+    DevBuf d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_pcm2;
     int pcm_cur = 0;                       // PCM arena of the last decode (two alternate in sink mode)
     cudaEvent_t pcm_free[2] = {nullptr, nullptr}; // sink copies out of arena i have finished
     DevBuf &pcm() { return pcm_cur ? d_pcm2 : d_pcm; }
@@ -270,6 +278,15 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xFFFFFF00ull) return MP3B_E_INVAL;
     const bool host_index = ctx->opts.indexer == MP3B_INDEX_HOST;
     if (host_index && where != MP3B_HOST) { ctx->err = "host indexer needs host-resident input"; return MP3B_E_INVAL; }
+    // Run-ahead walk: the upload and the frame walk (the one serial chain, a few hundred microseconds of
+    // latency on a handful of CTAs) go to a private stream, so they execute while the previous call's
+    // Huffman / back-end kernels still occupy the context's stream, and the host round trip that follows
+    // them costs the GPU nothing.
+    const bool ahead = ctx->opts.async_index != 0 && !host_index;
+    if (ahead) ctx->idx_cur ^= 1;
+    DevBuf &d_raw = ctx->d_raw[ctx->idx_cur], &d_streams = ctx->d_streams[ctx->idx_cur],
+           &d_scratch = ctx->d_scratch[ctx->idx_cur];
+    cudaStream_t ist = ahead ? ctx->index_stream : st;
 
     // the pinned staging tables (stream records, tiles, frames) are rewritten below: the previous call's
     // asynchronous uploads out of them must have executed (they are early in that call, so this is short)
@@ -277,15 +294,15 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(cudaEventRecord(ctx->ev[EV_START], st));
     // ---- raw bytes to the device
     if (where == MP3B_HOST) {
-        CK(ctx->d_raw.ensure(raw_total + 64));
-        if (raw_total) CK(cudaMemcpyAsync(ctx->d_raw.p, base + raw0, raw_total, cudaMemcpyHostToDevice, st));
-        ctx->raw_dev = ctx->d_raw.as<uint8_t>();
+        CK(d_raw.ensure(raw_total + 64));
+        if (raw_total) CK(cudaMemcpyAsync(d_raw.p, base + raw0, raw_total, cudaMemcpyHostToDevice, ist));
+        ctx->raw_dev = d_raw.as<uint8_t>();
     } else
         ctx->raw_dev = base + raw0;
 
     // ---- stream records, frame count
     CK(ctx->h_streams.ensure(sizeof(L3StreamRec) * (size_t)std::max(nstreams, 1)));
-    CK(ctx->d_streams.ensure(sizeof(L3StreamRec) * (size_t)std::max(nstreams, 1)));
+    CK(d_streams.ensure(sizeof(L3StreamRec) * (size_t)std::max(nstreams, 1)));
     L3StreamRec *hs = ctx->h_streams.as<L3StreamRec>();
     for (int i = 0; i < nstreams; i++) {
         memset(&hs[i], 0, sizeof hs[i]);
@@ -304,13 +321,19 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             host_index_stream(base + offsets[i], &hs[i], &host_frames[i], (uint32_t)i);
         });
     } else if (nstreams) {
-        CK(ctx->d_scratch.ensure(sizeof(L3FrameRec) * l3_index_scratch_records(raw_total, (uint64_t)nstreams)));
-        CK(cudaMemcpyAsync(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
-        l3_launch_index_walk(ctx->raw_dev, ctx->d_streams.as<L3StreamRec>(), nstreams, ctx->d_scratch.as<L3FrameRec>(), st);
+        CK(d_scratch.ensure(sizeof(L3FrameRec) * l3_index_scratch_records(raw_total, (uint64_t)nstreams)));
+        CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, ist));
+        if (ahead) CK(cudaEventRecord(ctx->walk_t0, ist));
+        l3_launch_index_walk(ctx->raw_dev, d_streams.as<L3StreamRec>(), nstreams, d_scratch.as<L3FrameRec>(), ist);
         launches++;
-        l3_launch_publish(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, st);
+        l3_launch_publish(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, ist);
         launches++;
-        CK(cudaStreamSynchronize(st)); // the one host round trip: sizes of everything downstream
+        if (ahead) {
+            CK(cudaEventRecord(ctx->walk_t1, ist));
+            CK(cudaEventRecord(ctx->walk_done, ist));
+            CK(cudaStreamWaitEvent(st, ctx->walk_done, 0));
+        }
+        CK(cudaStreamSynchronize(ist)); // the one host round trip: sizes of everything downstream
     }
 
     // ---- prefix sums, per-stream info, synthesis tiles
@@ -442,7 +465,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         CK(ctx->d_sb.ensure(max_wave_units * 576 * sizeof(float)));
     }
 
-    if (nstreams) CK(cudaMemcpyAsync(ctx->d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
+    if (ahead && where == MP3B_HOST && !nstreams) CK(cudaStreamSynchronize(ist));
+    if (nstreams) CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
     if (ntiles)
         CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->h_tiles.p, (fused ? sizeof(uint4) : sizeof(uint2)) * ntiles,
                            cudaMemcpyHostToDevice, st));
@@ -452,7 +476,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(cudaMemsetAsync(ctx->d_arena.as<uint8_t>() + (ctx->arena_bytes - 48), 0, 48, st));
 
     // ---- frame table
-    L3StreamRec *ds = ctx->d_streams.as<L3StreamRec>();
+    L3StreamRec *ds = d_streams.as<L3StreamRec>();
     L3FrameRec *df = ctx->d_frames.as<L3FrameRec>();
     if (host_index) {
         CK(ctx->h_frames.ensure(sizeof(L3FrameRec) * std::max<uint64_t>(frames, 1)));
@@ -467,7 +491,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     L3UnitDesc *du = ctx->d_units.as<L3UnitDesc>();
     uint32_t *dg = ctx->d_gran.as<uint32_t>();
     if (frames) {
-        l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : ctx->d_scratch.as<L3FrameRec>(),
+        l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : d_scratch.as<L3FrameRec>(),
                              (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), st);
         l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
         launches += 2;
@@ -536,6 +560,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(cudaGetLastError());
 
     ctx->timed = waves.size() == 1;
+    ctx->walk_timed = ahead && nstreams > 0;
     ctx->stats.streams = nstreams;
     ctx->stats.frames = (int64_t)frames;
     ctx->stats.granules = (int64_t)grans;
@@ -569,6 +594,7 @@ void mp3b_opts_default(mp3b_opts *o)
     o->pcm_format = MP3B_PCM_S16;
     o->indexer = MP3B_INDEX_DEVICE;
     o->pipeline = MP3B_PIPE_FUSED;
+    o->async_index = 1;
 }
 
 int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
@@ -600,6 +626,10 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     ctx->stream = ctx->own_stream;
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->index_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->walk_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaEventCreate(&ctx->walk_t0) != cudaSuccess || cudaEventCreate(&ctx->walk_t1) != cudaSuccess)
+        return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->staging_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     for (auto &e : ctx->pcm_free)
@@ -618,8 +648,10 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto *s : ctx->open_streams) delete s;
-    for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw, &ctx->d_streams, &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_scratch, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+    if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
+    for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
+                      &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -632,6 +664,9 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
         cudaStreamDestroy(ctx->copy_stream);
     }
     for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
+    if (ctx->index_stream) cudaStreamDestroy(ctx->index_stream);
+    for (cudaEvent_t e : {ctx->walk_done, ctx->walk_t0, ctx->walk_t1})
+        if (e) cudaEventDestroy(e);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
     for (auto &e : ctx->pcm_free)
@@ -726,6 +761,11 @@ int mp3b_sync(mp3b_ctx *ctx)
         };
         ctx->stats.ms_total = ms(EV_START, EV_END);
         ctx->stats.ms_index = ms(EV_START, EV_INDEX);
+        if (ctx->walk_timed) { // the run-ahead walk is not between those two events: add its own time
+            float v = 0.f;
+            if (cudaEventElapsedTime(&v, ctx->walk_t0, ctx->walk_t1) != cudaSuccess) { cudaGetLastError(); v = 0.f; }
+            ctx->stats.ms_index += v;
+        }
         if (ctx->timed && ctx->nunits && ctx->opts.pipeline == MP3B_PIPE_FUSED) {
             ctx->stats.ms_huffman = ms(EV_INDEX, EV_HUFF);
             ctx->stats.ms_fused = ms(EV_HUFF, EV_SYNTH);

@@ -324,6 +324,7 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
         const int16_t *s0 = S.is_buf[gi * 2], *s1 = S.is_buf[gi * 2 + 1];
         float *X0 = S.X[gi][0], *X1 = S.X[gi][1];
         const bool ms = m.ms != 0;
+        const float gs = ms ? isq2 : 1.f; // MS: (M +- S) / sqrt 2 with the factor folded into the band gains
         int v0[ITEMS], v1[ITEMS];
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) { v0[q] = s0[t64 + 64 * q]; v1[q] = s1[t64 + 64 * q]; }
@@ -333,12 +334,11 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
             const int m0 = abs(v0[q]), m1 = abs(v1[q]);
             const float p0 = m0 < KF_POW_LUT ? S.pow43[m0] : __ldg(pow43 + m0);
             const float p1 = m1 < KF_POW_LUT ? S.pow43[m1] : __ldg(pow43 + m1);
-            float l = __int_as_float(__float_as_int(p0 * g0[b]) | (v0[q] & 0x80000000));
-            float r = __int_as_float(__float_as_int(p1 * g1[b]) | (v1[q] & 0x80000000));
-            if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
+            const float a = __int_as_float(__float_as_int(p0 * (g0[b] * gs)) | (v0[q] & 0x80000000));
+            const float c = __int_as_float(__float_as_int(p1 * (g1[b] * gs)) | (v1[q] & 0x80000000));
             const int xp = xpad(t64 + 64 * q);
-            X0[xp] = l;
-            X1[xp] = r;
+            X0[xp] = ms ? a + c : a;
+            X1[xp] = ms ? a - c : c;
         }
         return;
     }
@@ -403,14 +403,15 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             const float sa = Z[9 + i], sb = -Z[8 - i];
-            // out[i] = sa, out[17-i] = -sa, out[18+i] = sb, out[35-i] = sb
-            const float s_i = (i & 1) ? sgn : 1.f, s_m = ((17 - i) & 1) ? sgn : 1.f;
-            float f0 = sa * w[i] * s_i, f1 = -sa * w[17 - i] * s_m;
+            // out[i] = sa, out[17-i] = -sa, out[18+i] = sb, out[35-i] = sb; slots i and 17 - i have
+            // opposite parity, so exactly one of each pair takes the inversion sign
+            const float sa_s = sa * sgn, sb_s = sb * sgn;
+            float f0 = ((i & 1) ? sa_s : sa) * w[i], f1 = -((i & 1) ? sa : sa_s) * w[17 - i];
             if (carry) { f0 += carry[i * 32 + lane]; f1 += carry[(17 - i) * 32 + lane]; }
             Fdst[i * FS + lane] = f0;
             Fdst[(17 - i) * FS + lane] = f1;
-            h[i] = sb * w[18 + i] * s_i;
-            h[17 - i] = sb * w[35 - i] * s_m;
+            h[i] = ((i & 1) ? sb_s : sb) * w[18 + i];
+            h[17 - i] = ((i & 1) ? sb : sb_s) * w[35 - i];
         }
     } else {
         float y[3][12];
