@@ -35,7 +35,7 @@ typedef enum mp3b_status {
     MP3B_E_INVAL = -1,       /* bad argument */
     MP3B_E_NOSYNC = -2,      /* no Layer III frame found in a stream */
     MP3B_E_TRUNCATED = -3,   /* destination buffer too small */
-    MP3B_E_UNSUPPORTED = -4, /* Layer I/II, free format, MPEG-2.5 */
+    MP3B_E_UNSUPPORTED = -4, /* Layer I/II, free format */
     MP3B_E_CUDA = -5,        /* CUDA runtime error; mp3b_last_error() has the text */
     MP3B_E_NOMEM = -6,
     MP3B_E_STATE = -7        /* call order violated (e.g. fetch before decode) */
@@ -74,7 +74,7 @@ typedef struct mp3b_opts {
 typedef struct mp3b_stream_info {
     int32_t sample_rate;
     int32_t channels;
-    int32_t lsf;            /* 0 = MPEG-1, 1 = MPEG-2 LSF */
+    int32_t lsf;            /* 0 = MPEG-1, 1 = MPEG-2 LSF or MPEG-2.5 (sample_rate tells which) */
     int32_t reserved;
     int64_t frames;
     int64_t samples;        /* per channel */

@@ -165,14 +165,14 @@ int upload_tables(mp3b_ctx *ctx)
     size_t o_lut = 0, o_info = align_up(o_lut + sizeof h->huff_lut, 256);
     size_t o_quad = align_up(o_info + sizeof(L3HuffInfo), 256), o_bands = align_up(o_quad + 64, 256);
     size_t o_pow = align_up(o_bands + sizeof(L3BandTables), 256), o_sfb = align_up(o_pow + sizeof h->pow43, 256);
-    size_t total = o_sfb + sizeof(uint16_t) * 6 * 23;
+    size_t total = o_sfb + sizeof(uint16_t) * 9 * 23;
     std::vector<uint8_t> blob(total, 0);
     memcpy(blob.data() + o_lut, h->huff_lut, sizeof h->huff_lut);
     memcpy(blob.data() + o_info, &h->huff, sizeof(L3HuffInfo));
     memcpy(blob.data() + o_quad, h->quad_a, 64);
     memcpy(blob.data() + o_bands, &h->bands, sizeof(L3BandTables));
     memcpy(blob.data() + o_pow, h->pow43, sizeof h->pow43);
-    memcpy(blob.data() + o_sfb, l3_sfb_long, sizeof(uint16_t) * 6 * 23);
+    memcpy(blob.data() + o_sfb, l3_sfb_long, sizeof(uint16_t) * 9 * 23);
     uint32_t lut_len = h->huff_lut_len;
     delete h;
     CK(ctx->d_tables.ensure(total));

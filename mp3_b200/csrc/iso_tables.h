@@ -26,26 +26,34 @@ static const uint16_t l3_bitrate_kbps[2][16] = {
 };
 
 /* sampling_frequency index -> Hz, by row (see header comment). */
-static const uint32_t l3_sample_rate[6] = {44100, 48000, 32000, 22050, 24000, 16000};
+/* rows 0..2 MPEG-1, 3..5 MPEG-2 LSF, 6..8 MPEG-2.5 (the unofficial low-rate extension: version bits 00) */
+static const uint32_t l3_sample_rate[9] = {44100, 48000, 32000, 22050, 24000, 16000, 11025, 12000, 8000};
 
 /* Annex B Table 3-B.8: scalefactor band edges, long blocks (23 edges = 22 bands). */
-static const uint16_t l3_sfb_long[6][23] = {
+static const uint16_t l3_sfb_long[9][23] = {
     {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 52, 62, 74, 90, 110, 134, 162, 196, 238, 288, 342, 418, 576},
     {0, 4, 8, 12, 16, 20, 24, 30, 36, 42, 50, 60, 72, 88, 106, 128, 156, 190, 230, 276, 330, 384, 576},
     {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576},
     {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
     {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 114, 136, 162, 194, 232, 278, 332, 394, 464, 540, 576},
     {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+    /* MPEG-2.5: 11.025 and 12 kHz use the 16 kHz partition, 8 kHz has its own */
+    {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+    {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+    {0, 12, 24, 36, 48, 60, 72, 88, 108, 132, 160, 192, 232, 280, 336, 400, 476, 566, 568, 570, 572, 574, 576},
 };
 
 /* Table 3-B.8: scalefactor band edges, short blocks (14 edges = 13 bands, per window). */
-static const uint16_t l3_sfb_short[6][14] = {
+static const uint16_t l3_sfb_short[9][14] = {
     {0, 4, 8, 12, 16, 22, 30, 40, 52, 66, 84, 106, 136, 192},
     {0, 4, 8, 12, 16, 22, 28, 38, 50, 64, 80, 100, 126, 192},
     {0, 4, 8, 12, 16, 22, 30, 42, 58, 78, 104, 138, 180, 192},
     {0, 4, 8, 12, 18, 24, 32, 42, 56, 74, 100, 132, 174, 192},
     {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 136, 180, 192},
     {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+    {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+    {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+    {0, 8, 16, 24, 36, 52, 72, 96, 124, 160, 162, 164, 166, 192},
 };
 
 /* 2.4.2.7 scalefac_compress -> (slen1, slen2), MPEG-1. */

@@ -190,7 +190,7 @@ __device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int
 {
     if (tid < nb) {
         GranMeta &m = S.gm[tid];
-        m.row = (m.d[0].hdr >> L3H_SR_SHIFT) & 7;
+        m.row = (m.d[0].hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
         for (int c = 0; c < 2; c++)
             m.lay[c] = (m.d[c].flags & L3F_BT_MASK) == 2 ? ((m.d[c].flags & L3F_MIXED) ? 2 : 1) : 0;
         const bool ok = (m.d[0].flags & L3F_VALID) != 0;
@@ -510,7 +510,7 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
     pcm_t *stage = reinterpret_cast<pcm_t *>(&S.X[0][0][0]);
     uint32_t bq[3] = {0, 0, 0}; // long-block band index of this thread's nine lines (see stage_requant)
     {
-        const int row0 = (units[ubase].hdr >> L3H_SR_SHIFT) & 7;
+        const int row0 = (units[ubase].hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
 #pragma unroll
         for (int q = 0; q < 9; q++)
             bq[q >> 2] |= (uint32_t)bands->line2band[row0][0][(tid & 63) + 64 * q] << (8 * (q & 3));

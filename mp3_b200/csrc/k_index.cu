@@ -204,7 +204,7 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
             if (bv > 288) bv = 288;
             uint32_t bv2 = bv * 2, r1, r2;
             if (ws) {
-                r1 = (bt == 2 || !h.lsf) ? 36 : 54;
+                r1 = (bt == 2 || !h.lsf) ? (h.sr_row == 8 ? 72 : 36) : (h.sr_row == 8 ? 108 : 54); // sfb_long[8] / 3 sfb_short[3]
                 r2 = 576;
             } else {
                 uint32_t a = r0c + 1, c = r0c + r1c + 2;

@@ -46,7 +46,7 @@ k_requant(const L3UnitDesc *__restrict__ units, const uint32_t *__restrict__ gra
     L3UnitDesc d[2];
     d[0] = units[u0];
     d[1] = units[u0 + (nch - 1)];
-    const int row = (d[0].hdr >> L3H_SR_SHIFT) & 7;
+    const int row = (d[0].hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
     int lay[2];
 #pragma unroll
     for (int c = 0; c < 2; c++) lay[c] = (d[c].flags & L3F_BT_MASK) == 2 ? ((d[c].flags & L3F_MIXED) ? 2 : 1) : 0;

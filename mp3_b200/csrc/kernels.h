@@ -16,7 +16,7 @@ struct L3DevTables {
     const uint8_t *quad_a;
     const L3BandTables *bands;
     const float *pow43;
-    const uint16_t *sfb_long; /* [6][23] */
+    const uint16_t *sfb_long; /* [9][23] */
 };
 
 /* K0: device frame indexer (a1-a3) */

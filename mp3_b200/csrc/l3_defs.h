@@ -69,10 +69,11 @@ typedef struct __attribute__((aligned(16))) L3UnitDesc {
 #define L3F_WS 0x80           /* window_switching_flag */
 
 #define L3H_LSF 0x01
-#define L3H_SR_SHIFT 1        /* bits 1..3: sample-rate row 0..5 */
-#define L3H_STEREO 0x10       /* two channels */
-#define L3H_MS 0x20           /* joint stereo with mode_ext MS bit */
-#define L3H_IS 0x40           /* joint stereo with mode_ext intensity bit */
+#define L3H_SR_SHIFT 1        /* bits 1..4: sample-rate row 0..8 */
+#define L3H_SR_MASK 15
+#define L3H_STEREO 0x20       /* two channels */
+#define L3H_MS 0x40           /* joint stereo with mode_ext MS bit */
+#define L3H_IS 0x80           /* joint stereo with mode_ext intensity bit */
 
 #define L3P_GR 0x01
 #define L3P_CH 0x02
@@ -107,24 +108,26 @@ L3_HD int l3_kbps(int lsf, int idx)
 
 L3_HD int l3_sr_hz(int row)
 {
-    return row == 0 ? 44100 : row == 1 ? 48000 : row == 2 ? 32000 : row == 3 ? 22050 : row == 4 ? 24000 : 16000;
+    return row == 0 ? 44100 : row == 1 ? 48000 : row == 2 ? 32000 : row == 3 ? 22050 : row == 4 ? 24000
+         : row == 5 ? 16000 : row == 6 ? 11025 : row == 7 ? 12000 : 8000;
 }
 
 /* a1: parse the 32 header bits (big-endian word).  Returns 0 if this is not a decodable
- * MPEG-1 / MPEG-2 LSF Layer III header (free format and MPEG-2.5 are rejected). */
+ * MPEG-1 / MPEG-2 LSF / MPEG-2.5 Layer III header (free format is rejected).  MPEG-2.5 (version
+ * bits 00) is MPEG-2 LSF syntax at half the sample rates: rows 6..8. */
 L3_HD int l3_parse_hdr(uint32_t w, L3Hdr *h)
 {
     if ((w & 0xFFE00000u) != 0xFFE00000u) return 0;
     int ver = (w >> 19) & 3, layer = (w >> 17) & 3;
-    if (layer != 1 || (ver != 3 && ver != 2)) return 0;
+    if (layer != 1 || ver == 1) return 0;
     int bri = (w >> 12) & 15, sri = (w >> 10) & 3;
     if (bri == 0 || bri == 15 || sri == 3) return 0;
-    h->lsf = ver == 2;
+    h->lsf = ver != 3;
     h->crc = !((w >> 16) & 1);
     h->mode = (w >> 6) & 3;
     h->mode_ext = (w >> 4) & 3;
     h->nch = h->mode == 3 ? 1 : 2;
-    h->sr_row = sri + (h->lsf ? 3 : 0);
+    h->sr_row = sri + (ver == 3 ? 0 : ver == 2 ? 3 : 6);
     h->ngr = h->lsf ? 1 : 2;
     int pad = (w >> 9) & 1;
     h->frame_len = (h->lsf ? 72000 : 144000) * l3_kbps(h->lsf, bri) / l3_sr_hz(h->sr_row) + pad;

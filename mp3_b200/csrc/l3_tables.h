@@ -19,15 +19,15 @@ typedef struct L3HuffInfo {
     uint8_t linbits[32];
 } L3HuffInfo;
 
-/* Band layouts: [sample-rate row 0..5][0 = long, 1 = short, 2 = mixed]. */
+/* Band layouts: [sample-rate row 0..8][0 = long, 1 = short, 2 = mixed]. */
 typedef struct L3BandTables {
-    uint8_t line2band[6][3][576];
-    uint16_t start[6][3][40];
-    uint8_t width[6][3][40];
-    int8_t win[6][3][40];    /* window 0..2 of a short band, -1 for a long band */
-    uint8_t sfb[6][3][40];
-    uint8_t nbands[6][3];
-    uint8_t nlong[6][3];
+    uint8_t line2band[9][3][576];
+    uint16_t start[9][3][40];
+    uint8_t width[9][3][40];
+    int8_t win[9][3][40];    /* window 0..2 of a short band, -1 for a long band */
+    uint8_t sfb[9][3][40];
+    uint8_t nbands[9][3];
+    uint8_t nlong[9][3];
 } L3BandTables;
 
 typedef struct L3HostTables {

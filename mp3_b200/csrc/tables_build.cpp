@@ -88,7 +88,7 @@ extern "C" void l3_build_host_tables(L3HostTables *t)
             if ((v >> (6 - len)) == l3_quad_hcod[0][s]) t->quad_a[v] = (uint8_t)((len << 4) | s);
         }
     // ---- band layouts
-    for (int row = 0; row < 6; row++) {
+    for (int row = 0; row < 9; row++) {
         const uint16_t *bl = l3_sfb_long[row], *bs = l3_sfb_short[row];
         for (int lay = 0; lay < 3; lay++) {
             int n = 0, pos = 0, s0 = 0, nl = 0;

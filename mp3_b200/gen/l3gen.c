@@ -22,7 +22,7 @@
 
 typedef struct {
     uint64_t seed;
-    int32_t sample_rate;   /* 44100 48000 32000 | 22050 24000 16000 */
+    int32_t sample_rate;   /* 44100 48000 32000 | 22050 24000 16000 | 11025 12000 8000 (MPEG-2.5) */
     int32_t mode;          /* 0 stereo, 1 joint stereo, 2 dual channel, 3 mono */
     int32_t bitrate_kbps;  /* CBR rate; ignored when vbr_max_kbps > 0 */
     int32_t vbr_min_kbps, vbr_max_kbps;
@@ -271,7 +271,7 @@ static int gen_granule(gen_t *g, int gr, int ch, int block_type, int mixed, int 
     /* ---- part 3: Huffman */
     const uint16_t *bl = l3_sfb_long[g->sr_row];
     int r1, r2;
-    if (s->window_switching) { r1 = (block_type == 2 || !g->lsf) ? 36 : 54; r2 = 576; }
+    if (s->window_switching) { r1 = block_type == 2 ? 3 * l3_sfb_short[g->sr_row][3] : bl[8]; r2 = 576; }
     else { r1 = bl[s->region0_count + 1]; r2 = bl[s->region0_count + s->region1_count + 2]; }
     int bv_target = rndi(r, 0, 9) == 0 ? rndi(r, 0, 288) : rndi(r, 40, 200);
     if (bv_target * 2 > line_limit) bv_target = line_limit / 2;
@@ -348,7 +348,7 @@ size_t l3gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
     g.cfg = c;
     g.rng.s = c->seed * 0x2545F4914F6CDD1Dull + 0x1234567;
     int row = -1;
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 9; i++)
         if ((int)l3_sample_rate[i] == c->sample_rate) row = i;
     if (row < 0 || c->nframes <= 0) return 0;
     g.sr_row = row;
@@ -448,7 +448,7 @@ size_t l3gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
         uint8_t *h = fr[f].hdr;
         int sri = row % 3;
         h[0] = 0xFF;
-        h[1] = (uint8_t)(0xE0 | ((g.lsf ? 2 : 3) << 3) | (1 << 1) | (c->crc ? 0 : 1));
+        h[1] = (uint8_t)(0xE0 | ((row >= 6 ? 0 : g.lsf ? 2 : 3) << 3) | (1 << 1) | (c->crc ? 0 : 1));
         h[2] = (uint8_t)((bri << 4) | (sri << 2) | (pad << 1));
         h[3] = (uint8_t)((c->mode << 6) | (mode_ext << 4));
         /* side info */

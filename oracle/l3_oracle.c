@@ -97,7 +97,7 @@ void l3o_init(void)
 }
 
 typedef struct {
-    int lsf;        /* 0 = MPEG-1, 1 = MPEG-2 LSF */
+    int lsf;        /* 0 = MPEG-1, 1 = MPEG-2 LSF or MPEG-2.5 */
     int sr_row;     /* row into l3_sfb_* / l3_sample_rate */
     int nch;
     int mode, mode_ext;
@@ -147,8 +147,8 @@ int l3o_parse_header(const uint8_t *p, l3o_hdr *h)
     int ver = (p[1] >> 3) & 3;   /* 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5, 1 = reserved */
     int layer = (p[1] >> 1) & 3; /* 1 = Layer III */
     if (layer != 1) return 0;
-    if (ver != 3 && ver != 2) return 0;
-    h->lsf = (ver == 2);
+    if (ver == 1) return 0;
+    h->lsf = (ver != 3); /* MPEG-2.5 = the LSF syntax at half the MPEG-2 sample rates (rows 6..8) */
     h->crc = !(p[1] & 1);
     h->bitrate_idx = p[2] >> 4;
     int sri = (p[2] >> 2) & 3;
@@ -157,7 +157,7 @@ int l3o_parse_header(const uint8_t *p, l3o_hdr *h)
     h->mode = p[3] >> 6;
     h->mode_ext = (p[3] >> 4) & 3;
     h->nch = h->mode == 3 ? 1 : 2;
-    h->sr_row = sri + (h->lsf ? 3 : 0);
+    h->sr_row = sri + (ver == 3 ? 0 : ver == 2 ? 3 : 6);
     int br = l3_bitrate_kbps[h->lsf][h->bitrate_idx] * 1000;
     int sr = (int)l3_sample_rate[h->sr_row];
     h->frame_len = (h->lsf ? 72 : 144) * br / sr + h->padding;
@@ -336,7 +336,8 @@ static void huffman_decode(bitr *b, size_t part3_end, const l3o_hdr *h, const l3
     if (bv2 > 576) bv2 = 576;
     int r1, r2;
     if (g->window_switching) {
-        r1 = (g->block_type == 2 || !h->lsf) ? 36 : 54;
+        /* region0_count is 8 (short: 9 short-window bands = 3 * sfb_short[3] lines) or 7 (8 long bands) */
+        r1 = g->block_type == 2 ? 3 * l3_sfb_short[h->sr_row][3] : l3_sfb_long[h->sr_row][8];
         r2 = 576;
     } else {
         int a = g->region0_count + 1, c = g->region0_count + g->region1_count + 2;

@@ -26,6 +26,12 @@ FF = {
     "low_bitrate_32k": dict(bitrate_kbps=32, nframes=24, seed=18, blocks=1, mode=1),
     "no_reservoir": dict(reservoir=0, nframes=16, seed=19, blocks=1),
     "sparse_frames": dict(fill_lo_pct=0, fill_hi_pct=30, nframes=24, seed=20, blocks=1, mode=1),
+    # MPEG-2.5 (version bits 00): LSF syntax at 11.025 / 12 / 8 kHz; 8 kHz has its own band partition
+    "m25_11k_stereo": dict(sample_rate=11025, bitrate_kbps=32, nframes=24, seed=41, blocks=1),
+    "m25_12k_joint": dict(sample_rate=12000, bitrate_kbps=48, nframes=24, seed=42, blocks=1, mode=1,
+                          lsf_avoid_illegal_ispos=1),
+    "m25_8k_mono": dict(sample_rate=8000, bitrate_kbps=16, nframes=24, seed=43, blocks=1, mode=3),
+    "m25_8k_stereo_vbr": dict(sample_rate=8000, vbr_min_kbps=8, vbr_max_kbps=64, nframes=24, seed=44, blocks=1),
 }
 # one case per big_values code book (table_select), so every codeword family is exercised
 for _t in [1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31]:

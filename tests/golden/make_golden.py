@@ -24,7 +24,7 @@ import l3util  # noqa: E402
 from mp3_b200 import synth  # noqa: E402
 
 PICK = ["cfg1_long_cbr128", "mixed_blocks", "ms_plus_intensity", "cfg3_320k_joint", "mono", "lsf22_stereo",
-        "lsf24_joint", "lsf16_mono", "vbr_32_320", "48k_crc"]
+        "lsf24_joint", "lsf16_mono", "vbr_32_320", "48k_crc", "m25_12k_joint", "m25_8k_stereo_vbr"]
 
 
 def main():

@@ -3,7 +3,7 @@ import numpy as np
 
 _BR = [[0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 0],
        [0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, 0]]
-_SR = [[44100, 48000, 32000], [22050, 24000, 16000]]
+_SR = {3: [44100, 48000, 32000], 2: [22050, 24000, 16000], 0: [11025, 12000, 8000]}  # by version bits
 
 
 def frame_len(h):
@@ -11,14 +11,14 @@ def frame_len(h):
     if h[0] != 0xFF or (h[1] & 0xE0) != 0xE0:
         return 0
     ver = (h[1] >> 3) & 3
-    if ver not in (2, 3) or ((h[1] >> 1) & 3) != 1:
+    if ver == 1 or ((h[1] >> 1) & 3) != 1:
         return 0
-    lsf = 1 if ver == 2 else 0
+    lsf = 0 if ver == 3 else 1  # MPEG-2 and MPEG-2.5 share the LSF syntax
     bri, sri = h[2] >> 4, (h[2] >> 2) & 3
     if bri in (0, 15) or sri == 3:
         return 0
     pad = (h[2] >> 1) & 1
-    return (72 if lsf else 144) * _BR[lsf][bri] * 1000 // _SR[lsf][sri] + pad
+    return (72 if lsf else 144) * _BR[lsf][bri] * 1000 // _SR[ver][sri] + pad
 
 
 def split_frames(data):

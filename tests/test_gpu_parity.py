@@ -266,3 +266,42 @@ def test_incremental_stream_equals_one_shot(seed, mp3b, batch):
             assert hs[j].info().total_samples == whole[j].shape[0]
         for h in hs:
             h.close()
+
+
+def test_run_ahead_walk_back_to_back_calls(mp3b, batch):
+    """opts.async_index: the frame walk of call N+1 runs on a private stream while call N's kernels are
+    still queued, on double-buffered tables.  A large call X followed immediately (no synchronisation)
+    by a small call Y into the same PCM sink: the head of the sink must hold Y's PCM and the tail, which
+    Y does not reach, X's -- decoded while Y's walk ran ahead -- both equal to the stream-ordered mode."""
+    streams, _ = batch
+    big = [streams, streams[::-1], streams[1:] + streams[:1]]
+    small = [streams[:3], streams[5:7], streams[-2:]]
+    want = {}
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, async_index=False) as dec:
+        for k, st in enumerate(big + small):
+            dec.decode_batch(st)
+            want[k] = dec.fetch_pcm().copy()
+
+    def pinned(st):
+        packed, offs = mp3b.pack_streams(st)
+        b = mp3b.PinnedBuffer(packed.size + 64)
+        b.view(np.uint8)[:packed.size] = packed
+        return b, offs
+
+    ins = [pinned(st) for st in big + small]
+    cap = max(w.size for w in want.values())
+    sink = mp3b.PinnedBuffer(cap * 2 + 64)
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, async_index=True) as dec:
+        dec.set_pcm_sink(sink.ptr, cap)
+        for rep in range(2):
+            for x in range(len(big)):
+                for y in range(len(big), len(big) + len(small)):
+                    dec.decode_packed(ins[x][0].ptr, ins[x][1], where=mp3b.HOST, sync=False)
+                    dec.decode_packed(ins[y][0].ptr, ins[y][1], where=mp3b.HOST, sync=False)
+                    dec.sync()
+                    got = sink.view(np.int16, cap)
+                    ny, nx = want[y].size, want[x].size
+                    assert ny < nx
+                    assert np.array_equal(got[:ny], want[y]), (x, y, "head")
+                    assert np.array_equal(got[ny:nx], want[x][ny:]), (x, y, "tail")
+        dec.set_pcm_sink(0, 0)

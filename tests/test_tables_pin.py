@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 SFB_LONG_WIDTH_441 = bytes([4, 4, 4, 4, 4, 4, 6, 6, 8, 8, 10, 12, 16, 20, 24, 28, 34, 42, 50, 54, 76, 158])
+SFB_SHORT_WIDTH_441 = bytes([4, 4, 4, 4, 6, 8, 10, 12, 14, 18, 22, 30, 56])
 
 
 def test_tables_are_complete_prefix_codes(oracle_mod):
@@ -60,7 +61,13 @@ def test_tables_match_libavcodec_rodata(oracle_mod):
     # band widths: 44.1 kHz long row
     i = blob.find(SFB_LONG_WIDTH_441)
     assert i >= 0
-    rows = [blob[i + 22 * r: i + 22 * (r + 1)] for r in range(6)]
-    for r in range(6):
+    # rows: 44.1 / 48 / 32 (MPEG-1), 22.05 / 24 / 16 (MPEG-2), 11.025 / 12 / 8 kHz (MPEG-2.5)
+    rows = [blob[i + 22 * r: i + 22 * (r + 1)] for r in range(9)]
+    for r in range(9):
         edges = [L.l3o_sfb_long(r, k) for k in range(23)]
         assert bytes(b - a for a, b in zip(edges, edges[1:])) == rows[r], r
+    j = blob.find(SFB_SHORT_WIDTH_441)
+    assert j >= 0
+    for r in range(9):
+        edges = [L.l3o_sfb_short(r, k) for k in range(14)]
+        assert bytes(b - a for a, b in zip(edges, edges[1:])) == blob[j + 13 * r: j + 13 * (r + 1)], r
