@@ -69,6 +69,8 @@ typedef struct mp3b_opts {
                               stream, overlapping the previous call's kernels.  Device-resident input must
                               then be completely written when the call is made (it is not ordered behind
                               work the caller queued on the context's stream).  0 = strictly stream-ordered. */
+    int32_t gapless;       /* 1 = mp3b_stream_info.samples / pcm_offset of the batch interface describe the
+                              gapless window of mp3b_tag_info instead of everything decoded.  Default 0. */
 } mp3b_opts;
 
 typedef struct mp3b_stream_info {
@@ -82,6 +84,20 @@ typedef struct mp3b_stream_info {
     int64_t pcm_offset;     /* element offset of this stream's PCM in the batch PCM arena */
     int64_t total_samples;  /* stream interface: samples per channel emitted since mp3b_stream_open */
 } mp3b_stream_info;
+
+/* The encoder's tag frame (the first frame of many files: "Xing" / "Info", optionally with the LAME
+ * extension, or "VBRI") and the gapless window it implies inside the stream's decoded PCM: the tag
+ * frame is not audio; with LAME delay / padding fields the first enc_delay + 528 + 1 samples and the
+ * last enc_padding samples are encoder / decoder latency, not signal. */
+typedef struct mp3b_tag_info {
+    int32_t kind;          /* 0 = no tag, 1 = Xing, 2 = Info, 3 = VBRI */
+    int32_t has_lame;      /* delay / padding fields present */
+    uint32_t frames;       /* frame count announced by the tag (0 if absent) */
+    uint32_t bytes;        /* byte count announced by the tag (0 if absent) */
+    int32_t enc_delay, enc_padding;
+    int64_t first_sample;  /* window start, samples per channel from the start of the decoded stream */
+    int64_t num_samples;   /* window length, samples per channel */
+} mp3b_tag_info;
 
 typedef struct mp3b_stats {
     int64_t streams, frames, granules, units; /* unit = one granule-channel (576 lines) */
@@ -126,6 +142,7 @@ int mp3b_sync(mp3b_ctx *ctx);
 int mp3b_flush(mp3b_ctx *ctx);
 
 int mp3b_batch_stream_info(const mp3b_ctx *ctx, int stream_index, mp3b_stream_info *info);
+int mp3b_batch_tag_info(const mp3b_ctx *ctx, int stream_index, mp3b_tag_info *info);
 /* Whole-batch PCM arena: streams back to back in input order, interleaved channels. */
 int mp3b_batch_pcm_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems);
 /* Copy the whole arena (nelems elements of the context's pcm_format) to `dst`; async when dst is

@@ -31,7 +31,13 @@ class Mp3bError(RuntimeError):
 class Opts(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("pcm_format", ctypes.c_int32), ("indexer", ctypes.c_int32),
                 ("pipeline", ctypes.c_int32), ("host_threads", ctypes.c_int32), ("keep_stages", ctypes.c_int32),
-                ("async_index", ctypes.c_int32)]
+                ("async_index", ctypes.c_int32), ("gapless", ctypes.c_int32)]
+
+
+class TagInfo(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("has_lame", ctypes.c_int32), ("frames", ctypes.c_uint32),
+                ("bytes", ctypes.c_uint32), ("enc_delay", ctypes.c_int32), ("enc_padding", ctypes.c_int32),
+                ("first_sample", ctypes.c_int64), ("num_samples", ctypes.c_int64)]
 
 
 class StreamInfo(ctypes.Structure):
@@ -56,7 +62,7 @@ class Stats(ctypes.Structure):
 EXPORTS = [
     "mp3b_abi_version", "mp3b_device_count", "mp3b_opts_default", "mp3b_ctx_create", "mp3b_ctx_destroy",
     "mp3b_ctx_set_stream", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
-    "mp3b_decode_packed", "mp3b_sync", "mp3b_flush", "mp3b_batch_stream_info", "mp3b_batch_pcm_device_ptr",
+    "mp3b_decode_packed", "mp3b_sync", "mp3b_flush", "mp3b_batch_stream_info", "mp3b_batch_tag_info", "mp3b_batch_pcm_device_ptr",
     "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_set_pcm_sink", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
     "mp3b_debug_stage",
@@ -90,6 +96,7 @@ def load_library():
     L.mp3b_sync.argtypes = [vp]
     L.mp3b_flush.argtypes = [vp]
     L.mp3b_batch_stream_info.argtypes = [vp, i32, ctypes.POINTER(StreamInfo)]
+    L.mp3b_batch_tag_info.argtypes = [vp, i32, ctypes.POINTER(TagInfo)]
     L.mp3b_batch_pcm_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.mp3b_batch_fetch_pcm.argtypes = [vp, vp, u64, i32, ctypes.POINTER(u64)]
     L.mp3b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
@@ -173,7 +180,7 @@ class Decoder:
     """One context on one GPU (mp3b_ctx).  Not thread-safe; use one per GPU."""
 
     def __init__(self, device=0, pcm_format=PCM_S16, indexer=INDEX_DEVICE, pipeline=None, host_threads=0,
-                 keep_stages=False, async_index=None):
+                 keep_stages=False, async_index=None, gapless=False):
         self.L = load_library()
         o = Opts()
         self.L.mp3b_opts_default(ctypes.byref(o))
@@ -182,6 +189,7 @@ class Decoder:
             o.pipeline = pipeline
         if async_index is not None:
             o.async_index = int(bool(async_index))
+        o.gapless = int(bool(gapless))
         self.pcm_format = pcm_format
         ctx = ctypes.c_void_p()
         rc = self.L.mp3b_ctx_create(device, ctypes.byref(o), ctypes.byref(ctx))
@@ -246,6 +254,12 @@ class Decoder:
         if rc not in (0, -2):
             self._ck(rc)
         return inf
+
+    def tag_info(self, i):
+        """Xing / Info / LAME / VBRI tag of stream i and the gapless window it implies."""
+        t = TagInfo()
+        self._ck(self.L.mp3b_batch_tag_info(self.ctx, i, ctypes.byref(t)))
+        return t
 
     def pcm_device(self):
         p, n = ctypes.c_void_p(), ctypes.c_uint64()

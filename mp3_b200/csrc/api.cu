@@ -123,6 +123,7 @@ struct mp3b_ctx {
 
     const uint8_t *raw_dev = nullptr; // d_raw or the caller's device buffer
     std::vector<mp3b_stream_info> infos;
+    std::vector<mp3b_tag_info> tags;
     uint64_t pcm_elems = 0;
     uint64_t arena_bytes = 0;
     uint32_t nstreams = 0, nframes = 0, ngran = 0, nunits = 0, ntiles = 0;
@@ -208,7 +209,12 @@ void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRe
             p++;
             continue;
         }
-        if (n == 0) { first = first ? first : w; first_off = p; }
+        if (n == 0) {
+            first = first ? first : w;
+            first_off = p;
+            if (r->skip_frames == 0)
+                r->tag_kind = l3_parse_tag(buf + p, (uint32_t)h.frame_len, &h, &r->tag_frames, &r->tag_bytes, &r->tag_delay_pad);
+        }
         L3FrameRec f;
         f.rel_off = p;
         f.payload_off = payload;
@@ -268,6 +274,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     cudaStream_t st = ctx->stream;
     ctx->have_batch = false;
     ctx->infos.assign((size_t)nstreams, mp3b_stream_info{});
+    ctx->tags.assign((size_t)nstreams, mp3b_tag_info{});
     ctx->stats = mp3b_stats{};
     ctx->nstreams = (uint32_t)nstreams;
     ctx->nframes = ctx->ngran = ctx->nunits = ctx->ntiles = 0;
@@ -361,6 +368,36 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             inf.frames = r.nframes - skip;
             inf.samples = (int64_t)(r.nframes - skip) * h.ngr * 576;
             inf.pcm_offset += (int64_t)skip * h.ngr * h.nch * 576;
+            // the encoder's tag frame and the gapless window it implies: the tag frame itself is not audio,
+            // the encoder delay plus the decoder's own 528 + 1 samples are cut from the head, the padding
+            // from the tail (what mpg123 / FFmpeg do with the same fields)
+            {
+                mp3b_tag_info &tg = ctx->tags[(size_t)i];
+                const int64_t spf = (int64_t)h.ngr * 576, total = (int64_t)r.nframes * spf;
+                tg.kind = (int32_t)(r.tag_kind & L3T_KIND_MASK);
+                tg.has_lame = (r.tag_kind & L3T_LAME) ? 1 : 0;
+                tg.frames = r.tag_frames;
+                tg.bytes = r.tag_bytes;
+                tg.enc_delay = (int32_t)(r.tag_delay_pad >> 16);
+                tg.enc_padding = (int32_t)(r.tag_delay_pad & 0xffffu);
+                int64_t start = 0, count = total;
+                if (tg.kind != 0) {
+                    start = spf;
+                    count = total - spf;
+                    if (tg.has_lame) {
+                        start += tg.enc_delay + 529;
+                        count -= (int64_t)tg.enc_delay + tg.enc_padding;
+                    }
+                }
+                start = std::min(start, total);
+                count = std::max<int64_t>(0, std::min(count, total - start));
+                tg.first_sample = start;
+                tg.num_samples = count;
+                if (ctx->opts.gapless && !hints) {
+                    inf.pcm_offset += start * h.nch;
+                    inf.samples = count;
+                }
+            }
             frames += r.nframes;
             uint64_t g = (uint64_t)r.nframes * h.ngr;
             sgran[(size_t)i] = (uint32_t)g;
@@ -796,6 +833,15 @@ int mp3b_batch_stream_info(const mp3b_ctx *ctx, int i, mp3b_stream_info *info)
     if (i < 0 || (size_t)i >= ctx->infos.size()) return MP3B_E_INVAL;
     *info = ctx->infos[(size_t)i];
     return info->frames ? MP3B_OK : MP3B_E_NOSYNC;
+}
+
+int mp3b_batch_tag_info(const mp3b_ctx *ctx, int i, mp3b_tag_info *info)
+{
+    if (!ctx || !info) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    if (i < 0 || (size_t)i >= ctx->tags.size()) return MP3B_E_INVAL;
+    *info = ctx->tags[(size_t)i];
+    return MP3B_OK;
 }
 
 int mp3b_batch_pcm_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems)

@@ -34,6 +34,7 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     L3FrameRec *out = scratch + scratch_base(r, (uint32_t)s);
     uint32_t len = r.raw_len, p = l3_id3v2_len(buf, len), first = r.first_hdr, first_off = 0, n = 0, payload = 0;
     uint32_t end_off = p;
+    uint32_t tag_kind = L3T_NONE, tag_frames = 0, tag_bytes = 0, tag_dp = 0;
     const bool streaming = (r.flags & L3S_STREAMING) != 0;
     // Fast path for the overwhelmingly common case: the header equals the previous one in every bit that
     // determines the frame geometry (sync, version, layer, protection, bitrate, sample rate, mode), so
@@ -64,6 +65,7 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
             if (n == 0) {
                 first = first ? first : w;
                 first_off = p;
+                if (r.skip_frames == 0) tag_kind = l3_parse_tag(buf + p, flen, &h, &tag_frames, &tag_bytes, &tag_dp);
                 for (int j = 1; j < 8; j++) // the chain is latency-bound: pull the next headers towards L2
                     if (p + (uint32_t)j * flen < len) prefetch_l2(buf + p + j * flen);
             }
@@ -85,6 +87,10 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     streams[s].first_hdr = first;
     streams[s].nframes = n;
     streams[s].payload_len = payload;
+    streams[s].tag_kind = tag_kind;
+    streams[s].tag_frames = tag_frames;
+    streams[s].tag_bytes = tag_bytes;
+    streams[s].tag_delay_pad = tag_dp;
 }
 
 // Sequential big-endian bit reader over unaligned bytes (side info is 9..32 bytes).

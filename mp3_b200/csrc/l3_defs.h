@@ -38,8 +38,20 @@ typedef struct L3StreamRec {
     uint32_t end_off;      /* out: first byte not consumed by a complete frame (streaming) */
     uint32_t skip_frames;  /* in: leading frames that only re-derive state (already output earlier) */
     uint32_t flags;        /* in: L3S_* */
+    /* out: the encoder's tag frame (Xing / Info / VBRI), parsed from the stream's first frame */
+    uint32_t tag_kind;     /* L3T_*; bit 8 (L3T_LAME): a LAME extension with delay / padding follows */
+    uint32_t tag_frames;   /* frame count field, 0 if absent */
+    uint32_t tag_bytes;    /* byte count field, 0 if absent */
+    uint32_t tag_delay_pad; /* encoder delay << 16 | padding (12 bits each; VBRI: delay only) */
     uint32_t reserved;
 } L3StreamRec;
+
+#define L3T_NONE 0u
+#define L3T_XING 1u
+#define L3T_INFO 2u
+#define L3T_VBRI 3u
+#define L3T_KIND_MASK 0xffu
+#define L3T_LAME 0x100u
 
 #define L3S_STREAMING 1u   /* more bytes may follow: stop at a valid header whose frame is not complete yet
                               instead of searching for a sync inside it; first_hdr may be preset */
@@ -157,6 +169,46 @@ L3_HD uint32_t l3_id3v2_len(const uint8_t *b, uint32_t len)
 L3_HD uint32_t l3_load_be32(const uint8_t *p)
 {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+
+/* The tag frame an encoder may put first (the container step just before the hot path, SURVEY.md
+ * 8(f) rank 1 / 3).  "Xing" (VBR) or "Info" (CBR) sits right after the side info of an otherwise
+ * empty Layer III frame: flags (bit 0 frames, 1 bytes, 2 TOC[100], 3 quality), then optionally the
+ * LAME extension (9-byte version string, ..., 12-bit encoder delay and 12-bit padding at +21).
+ * "VBRI" (Fraunhofer) sits 32 bytes after the header: version, delay, quality, bytes, frames.
+ * `f` points at the frame's header, `flen` is the frame length.  Returns L3T_* | L3T_LAME. */
+L3_HD uint32_t l3_parse_tag(const uint8_t *f, uint32_t flen, const L3Hdr *h, uint32_t *frames, uint32_t *bytes,
+                            uint32_t *delay_pad)
+{
+    *frames = *bytes = *delay_pad = 0;
+    for (int crc = 0; crc <= (h->crc ? 1 : 0); crc++) { /* writers differ on whether the CRC word shifts the tag */
+        uint32_t o = 4u + (uint32_t)h->side_len + 2u * (uint32_t)crc;
+        if (o + 8 > flen) break;
+        const uint32_t id = l3_load_be32(f + o);
+        if (id != 0x58696E67u /* Xing */ && id != 0x496E666Fu /* Info */) continue;
+        const uint32_t fl = l3_load_be32(f + o + 4);
+        uint32_t q = o + 8;
+        if ((fl & 1) && q + 4 <= flen) { *frames = l3_load_be32(f + q); q += 4; }
+        if ((fl & 2) && q + 4 <= flen) { *bytes = l3_load_be32(f + q); q += 4; }
+        if (fl & 4) q += 100;
+        if (fl & 8) q += 4;
+        uint32_t kind = id == 0x58696E67u ? L3T_XING : L3T_INFO;
+        /* LAME extension: a version string of printable characters ("LAME3.99r", "Lavc58.13", ...) */
+        if (q + 24 <= flen && f[q] >= 0x20 && f[q] < 0x7f && f[q + 1] >= 0x20 && f[q + 1] < 0x7f) {
+            const uint32_t d = ((uint32_t)f[q + 21] << 4) | (f[q + 22] >> 4);
+            const uint32_t p = (((uint32_t)f[q + 22] & 15u) << 8) | f[q + 23];
+            *delay_pad = (d << 16) | p;
+            kind |= L3T_LAME;
+        }
+        return kind;
+    }
+    if (4u + 32u + 18u <= flen && l3_load_be32(f + 36) == 0x56425249u /* VBRI */) {
+        *delay_pad = (((uint32_t)f[36 + 6] << 8) | f[36 + 7]) << 16;
+        *bytes = l3_load_be32(f + 36 + 10);
+        *frames = l3_load_be32(f + 36 + 14);
+        return L3T_VBRI;
+    }
+    return L3T_NONE;
 }
 
 /* One step of the frame walk shared by the host and device indexers (the scan policy of

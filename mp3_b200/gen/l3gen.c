@@ -42,6 +42,10 @@ typedef struct {
                               encoders do); 1 = drawn per granule, which also produces mixed -> pure
                               short transitions (legal to decode, but FFmpeg drops the long-window
                               tail of subbands 0-1 there, so differential tests keep this 0) */
+    int32_t tag;           /* 0 = none; 1 = "Xing", 2 = "Info" tag frame first (frames, bytes, TOC, quality);
+                              3 = "VBRI" (Fraunhofer) */
+    int32_t tag_lame;      /* 1 = LAME extension after the Xing/Info fields (encoder delay / padding) */
+    int32_t enc_delay, enc_padding; /* 0..4095 each */
 } l3gen_cfg;
 
 /* ------------------------------------------------------------------ rng */
@@ -337,7 +341,57 @@ size_t l3gen_max_bytes(const l3gen_cfg *c)
     int lsf = c->sample_rate < 32000;
     int kb = c->vbr_max_kbps > 0 ? c->vbr_max_kbps : c->bitrate_kbps;
     size_t fl = (size_t)(lsf ? 72 : 144) * kb * 1000 / c->sample_rate + 1;
-    return fl * (size_t)c->nframes + 16;
+    return fl * (size_t)c->nframes + 16 + (c->tag ? 1500 : 0);
+}
+
+/* The tag frame encoders put first: a Layer III frame of the stream's own version / sample rate /
+ * mode whose side info and main data are zero (it decodes to silence) and whose payload carries
+ * "Xing"/"Info" (+ the LAME extension) or "VBRI".  Returns its length. */
+static size_t put_tag_frame(const l3gen_cfg *c, int row, int lsf, int nch, int side_len, size_t audio_bytes,
+                            uint8_t *out, size_t cap)
+{
+    int need = 4 + side_len + 120 + 36 + 4;
+    if (c->tag == 3 && need < 4 + 32 + 26 + 4) need = 4 + 32 + 26 + 4;
+    int bri = 0, flen = 0;
+    for (int i = 1; i < 15; i++) {
+        flen = (lsf ? 72 : 144) * l3_bitrate_kbps[lsf][i] * 1000 / (int)l3_sample_rate[row];
+        if (flen >= need) { bri = i; break; }
+    }
+    if (!bri || (size_t)flen > cap) return 0;
+    memset(out, 0, (size_t)flen);
+    out[0] = 0xFF;
+    out[1] = (uint8_t)(0xE0 | ((row >= 6 ? 0 : lsf ? 2 : 3) << 3) | (1 << 1) | 1);
+    out[2] = (uint8_t)((bri << 4) | ((row % 3) << 2));
+    out[3] = (uint8_t)(c->mode << 6);
+    (void)nch;
+    uint32_t frames = (uint32_t)c->nframes, bytes = (uint32_t)(audio_bytes + (size_t)flen);
+    if (c->tag == 3) {
+        uint8_t *t = out + 4 + 32;
+        memcpy(t, "VBRI", 4);
+        t[4] = 0; t[5] = 1;                                   /* version */
+        t[6] = (uint8_t)(c->enc_delay >> 8); t[7] = (uint8_t)c->enc_delay;
+        t[8] = 0; t[9] = 75;                                  /* quality */
+        t[10] = (uint8_t)(bytes >> 24); t[11] = (uint8_t)(bytes >> 16); t[12] = (uint8_t)(bytes >> 8); t[13] = (uint8_t)bytes;
+        t[14] = (uint8_t)(frames >> 24); t[15] = (uint8_t)(frames >> 16); t[16] = (uint8_t)(frames >> 8); t[17] = (uint8_t)frames;
+        return (size_t)flen;
+    }
+    uint8_t *t = out + 4 + side_len;
+    memcpy(t, c->tag == 1 ? "Xing" : "Info", 4);
+    t[7] = 0x0F; /* frames | bytes | TOC | quality */
+    t[8] = (uint8_t)(frames >> 24); t[9] = (uint8_t)(frames >> 16); t[10] = (uint8_t)(frames >> 8); t[11] = (uint8_t)frames;
+    t[12] = (uint8_t)(bytes >> 24); t[13] = (uint8_t)(bytes >> 16); t[14] = (uint8_t)(bytes >> 8); t[15] = (uint8_t)bytes;
+    for (int i = 0; i < 100; i++) t[16 + i] = (uint8_t)(i * 256 / 100);
+    t[119] = 57; /* quality */
+    if (c->tag_lame) {
+        uint8_t *l = t + 120;
+        memcpy(l, "LAME3.100", 9);
+        l[9] = 0x04;  /* tag revision 0, VBR method 4 */
+        l[10] = 190;  /* lowpass / 100 */
+        l[21] = (uint8_t)(c->enc_delay >> 4);
+        l[22] = (uint8_t)(((c->enc_delay & 15) << 4) | ((c->enc_padding >> 8) & 15));
+        l[23] = (uint8_t)c->enc_padding;
+    }
+    return (size_t)flen;
 }
 
 /* Generate one stream.  Returns bytes written, or 0 on a bad config / small buffer. */
@@ -493,6 +547,12 @@ size_t l3gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
 
     /* interleave headers / side info / payload slices into the physical stream */
     size_t o = 0, lp = 0;
+    if (c->tag) {
+        size_t audio = 0;
+        for (int f = 0; f < c->nframes; f++) audio += (size_t)hdr_len + side_len + fr[f].payload;
+        o = put_tag_frame(c, row, g.lsf, nch, side_len, audio, out, cap);
+        if (!o) { free(logical); free(fr); return 0; }
+    }
     for (int f = 0; f < c->nframes; f++) {
         size_t need = (size_t)hdr_len + side_len + fr[f].payload;
         if (o + need > cap) { free(logical); free(fr); return 0; }

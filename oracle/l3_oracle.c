@@ -702,6 +702,99 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
     return 0;
 }
 
+/* ---------------------------------------------------------------- tag frame (container step before a1)
+ * Restated from the published layouts of the Xing/Info header (Xing Technology's VBR header SDK),
+ * the LAME tag (LAME "Mp3 info tag rev 1" specification) and Fraunhofer's VBRI header; the
+ * reference repository has no code for them (/root/reference/README.md:1-84).
+ *   Xing/Info: 4-byte id right after the side info; 4-byte flags (1 frames, 2 bytes, 4 TOC, 8 quality);
+ *              the fields present, in that order (4, 4, 100, 4 bytes).
+ *   LAME ext : directly after; 9-byte encoder version, 1 rev/method, 1 lowpass, 8 replay gain,
+ *              1 flags, 1 bitrate, then 3 bytes = 12-bit encoder delay, 12-bit end padding.
+ *   VBRI     : always 32 bytes after the 4-byte header: id, version(2), delay(2), quality(2),
+ *              bytes(4), frames(4), ...
+ * Gapless window (what mpg123 and FFmpeg derive from the same fields): the tag frame is dropped; with
+ * a LAME extension the next delay + 528 + 1 samples are dropped too and the padding comes off the end. */
+typedef struct {
+    int kind;     /* 0 none, 1 Xing, 2 Info, 3 VBRI */
+    int has_lame;
+    unsigned frames, bytes;
+    int enc_delay, enc_padding;
+    long first_sample, num_samples;
+} l3o_tag;
+
+static unsigned be32(const uint8_t *p) { return ((unsigned)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+int l3o_parse_tag(const uint8_t *buf, size_t len, l3o_tag *t)
+{
+    memset(t, 0, sizeof *t);
+    size_t p = id3v2_skip(buf, len);
+    l3o_hdr h;
+    for (;; p++) { /* the first decodable frame */
+        if (p + 4 > len) return -1;
+        if (l3o_parse_header(buf + p, &h) && h.frame_len >= 4 + (h.crc ? 2 : 0) + h.side_len &&
+            p + (size_t)h.frame_len <= len)
+            break;
+    }
+    const uint8_t *f = buf + p;
+    size_t flen = (size_t)h.frame_len;
+    /* count the frames of the stream the way l3o_decode does */
+    long nfr = 0;
+    {
+        size_t q = p;
+        while (q + 4 <= len) {
+            l3o_hdr g;
+            if (!l3o_parse_header(buf + q, &g) || g.lsf != h.lsf || g.sr_row != h.sr_row || g.nch != h.nch ||
+                g.frame_len < 4 + (g.crc ? 2 : 0) + g.side_len || q + (size_t)g.frame_len > len) {
+                q++;
+                continue;
+            }
+            nfr++;
+            q += (size_t)g.frame_len;
+        }
+    }
+    size_t at = 4 + (size_t)h.side_len;
+    for (int pass = 0; pass < 2 && t->kind == 0; pass++, at += 2) {
+        if (pass == 1 && !h.crc) break;
+        if (at + 8 > flen) break;
+        if (memcmp(f + at, "Xing", 4) == 0) t->kind = 1;
+        else if (memcmp(f + at, "Info", 4) == 0) t->kind = 2;
+        else continue;
+        unsigned flags = be32(f + at + 4);
+        size_t q = at + 8;
+        if ((flags & 1) && q + 4 <= flen) { t->frames = be32(f + q); q += 4; }
+        if ((flags & 2) && q + 4 <= flen) { t->bytes = be32(f + q); q += 4; }
+        if (flags & 4) q += 100;
+        if (flags & 8) q += 4;
+        if (q + 24 <= flen && f[q] >= 0x20 && f[q] <= 0x7e && f[q + 1] >= 0x20 && f[q + 1] <= 0x7e) {
+            t->has_lame = 1;
+            t->enc_delay = (f[q + 21] << 4) | (f[q + 22] >> 4);
+            t->enc_padding = ((f[q + 22] & 0x0f) << 8) | f[q + 23];
+        }
+    }
+    if (t->kind == 0 && flen >= 4 + 32 + 18 && memcmp(f + 36, "VBRI", 4) == 0) {
+        t->kind = 3;
+        t->enc_delay = (f[42] << 8) | f[43];
+        t->bytes = be32(f + 46);
+        t->frames = be32(f + 50);
+    }
+    long spf = h.lsf ? 576 : 1152, total = nfr * spf;
+    long start = 0, count = total;
+    if (t->kind) {
+        start = spf;
+        count = total - spf;
+        if (t->has_lame) {
+            start += t->enc_delay + 528 + 1;
+            count -= t->enc_delay + t->enc_padding;
+        }
+    }
+    if (start > total) start = total;
+    if (count > total - start) count = total - start;
+    if (count < 0) count = 0;
+    t->first_sample = start;
+    t->num_samples = count;
+    return 0;
+}
+
 /* Table accessors so that tests can pin the ISO tables from Python. */
 int l3o_book_entry(int book, int x, int y, int *hlen, unsigned *hcod)
 {

@@ -19,6 +19,12 @@ class Info(ctypes.Structure):
                 ("concealed_frames", ctypes.c_long)]
 
 
+class Tag(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("has_lame", ctypes.c_int), ("frames", ctypes.c_uint), ("bytes", ctypes.c_uint),
+                ("enc_delay", ctypes.c_int), ("enc_padding", ctypes.c_int), ("first_sample", ctypes.c_long),
+                ("num_samples", ctypes.c_long)]
+
+
 def build(force=False):
     srcs = [os.path.join(HERE, "l3_oracle.c"),
             os.path.join(HERE, "..", "mp3_b200", "csrc", "iso_tables.h"),
@@ -45,6 +51,16 @@ def lib():
         _lib.l3o_dwin.restype = ctypes.c_double
         _lib.l3o_init()
     return _lib
+
+
+def parse_tag(data):
+    """Xing / Info / LAME / VBRI tag of a stream and the gapless window it implies (l3o_parse_tag)."""
+    L = lib()
+    data = bytes(data)
+    buf = (ctypes.c_uint8 * max(len(data), 1)).from_buffer_copy(data if data else b"\0")
+    t = Tag()
+    rc = L.l3o_parse_tag(buf, ctypes.c_size_t(len(data)), ctypes.byref(t))
+    return t if rc == 0 else None
 
 
 class Decoded:
