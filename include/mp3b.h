@@ -71,6 +71,9 @@ typedef struct mp3b_opts {
                               work the caller queued on the context's stream).  0 = strictly stream-ordered. */
     int32_t gapless;       /* 1 = mp3b_stream_info.samples / pcm_offset of the batch interface describe the
                               gapless window of mp3b_tag_info instead of everything decoded.  Default 0. */
+    int32_t verify_crc;    /* 1 = check the CRC-16 of protected frames (header protection bit 0); a frame
+                              that fails is concealed as silence and counted.  Default 0: the word is
+                              skipped, which is what common decoders do. */
 } mp3b_opts;
 
 typedef struct mp3b_stream_info {

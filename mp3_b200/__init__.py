@@ -31,7 +31,8 @@ class Mp3bError(RuntimeError):
 class Opts(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("pcm_format", ctypes.c_int32), ("indexer", ctypes.c_int32),
                 ("pipeline", ctypes.c_int32), ("host_threads", ctypes.c_int32), ("keep_stages", ctypes.c_int32),
-                ("async_index", ctypes.c_int32), ("gapless", ctypes.c_int32)]
+                ("async_index", ctypes.c_int32), ("gapless", ctypes.c_int32),
+                ("verify_crc", ctypes.c_int32)]
 
 
 class TagInfo(ctypes.Structure):
@@ -180,7 +181,7 @@ class Decoder:
     """One context on one GPU (mp3b_ctx).  Not thread-safe; use one per GPU."""
 
     def __init__(self, device=0, pcm_format=PCM_S16, indexer=INDEX_DEVICE, pipeline=None, host_threads=0,
-                 keep_stages=False, async_index=None, gapless=False):
+                 keep_stages=False, async_index=None, gapless=False, verify_crc=False):
         self.L = load_library()
         o = Opts()
         self.L.mp3b_opts_default(ctypes.byref(o))
@@ -190,6 +191,7 @@ class Decoder:
         if async_index is not None:
             o.async_index = int(bool(async_index))
         o.gapless = int(bool(gapless))
+        o.verify_crc = int(bool(verify_crc))
         self.pcm_format = pcm_format
         ctx = ctypes.c_void_p()
         rc = self.L.mp3b_ctx_create(device, ctypes.byref(o), ctypes.byref(ctx))

@@ -529,7 +529,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     uint32_t *dg = ctx->d_gran.as<uint32_t>();
     if (frames) {
         l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : d_scratch.as<L3FrameRec>(),
-                             (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), st);
+                             (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), ctx->opts.verify_crc, st);
         l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
         launches += 2;
     }

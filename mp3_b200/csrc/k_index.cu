@@ -132,7 +132,7 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
                              L3FrameRec *__restrict__ frames, const L3FrameRec *__restrict__ scratch,
                              uint32_t nframes, const uint16_t *__restrict__ sfb_long_all,
                              L3UnitDesc *__restrict__ units, uint32_t *__restrict__ gran_unit0,
-                             uint32_t *__restrict__ concealed)
+                             uint32_t *__restrict__ concealed, int verify_crc)
 {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
@@ -171,7 +171,16 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
         mdb = b.get(8);
         b.get(nch == 1 ? 1 : 2);
     }
-    const int valid = mdb <= fr.payload_off;
+    int valid = mdb <= fr.payload_off;
+    if (verify_crc && h.crc) { // protected frame: a CRC mismatch conceals it like a lost reservoir does
+        const uint8_t *fp = raw + sr.raw_off + fr.rel_off;
+        const uint32_t avail = sr.raw_len - fr.rel_off; // >= frame_len >= 6 + side_len (checked by the walk)
+        if (avail >= 6u + (uint32_t)h.side_len) {
+            uint32_t crc = l3_crc16(0xffffu, fp + 2, 2);
+            crc = l3_crc16(crc, fp + 6, (uint32_t)h.side_len);
+            if (crc != (((uint32_t)fp[4] << 8) | fp[5])) valid = 0;
+        }
+    }
     if (!valid && fi >= sr.skip_frames) atomicAdd(concealed, 1u);
     uint64_t bit = valid ? (sr.payload_base + fr.payload_off - mdb) * 8ull : 0ull;
     uint8_t hdrbits = (uint8_t)((h.lsf ? L3H_LSF : 0) | (h.sr_row << L3H_SR_SHIFT) | (nch == 2 ? L3H_STEREO : 0));
@@ -245,7 +254,9 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
     }
 }
 
-// One warp per frame; byte-granular because source and destination have arbitrary alignment.
+// One warp per frame.  Source and destination have arbitrary alignment: the destination is brought to
+// a word boundary with a few byte stores, then each lane builds one aligned destination word from two
+// aligned source words (byte permute), 128 bytes per warp instruction; a byte tail finishes.
 __global__ void k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams,
                                const L3FrameRec *__restrict__ frames, uint32_t nframes, uint8_t *__restrict__ arena)
 {
@@ -258,7 +269,22 @@ __global__ void k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRe
     uint32_t skip = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len, n = (uint32_t)h.frame_len - skip;
     const uint8_t *src = raw + sr.raw_off + fr.rel_off + skip;
     uint8_t *dst = arena + sr.payload_base + fr.payload_off;
-    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    const uint32_t head = min(n, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+    if (lane < head) dst[lane] = src[lane];
+    src += head;
+    dst += head;
+    n -= head;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    // words whose two source words lie inside the frame's own bytes (no read past the stream's end)
+    const uint32_t nw = n >= 8u ? (n - (sh ? 4u : 0u)) >> 2 : 0u;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - sh);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+    const uint32_t sel = 0x3210u + 0x1111u * sh;
+    for (uint32_t i = lane; i < nw; i += 32) {
+        const uint32_t a = __ldg(sw + i), b = sh ? __ldg(sw + i + 1) : 0u;
+        dw[i] = __byte_perm(a, b, sel);
+    }
+    for (uint32_t i = nw * 4u + lane; i < n; i += 32) dst[i] = src[i];
 }
 
 // Small results go to the host through stores into pinned (UVA-mapped) memory instead of a D2H
@@ -286,11 +312,11 @@ void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams
 }
 void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
                           const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,
-                          uint32_t *gran_unit0, uint32_t *concealed_counter, cudaStream_t st)
+                          uint32_t *gran_unit0, uint32_t *concealed_counter, int verify_crc, cudaStream_t st)
 {
     if (!nframes) return;
     k_side_parse<<<(nframes + 127) / 128, 128, 0, st>>>(raw, streams, nstreams, frames, scratch, nframes, T.sfb_long,
-                                                        units, gran_unit0, concealed_counter);
+                                                        units, gran_unit0, concealed_counter, verify_crc);
 }
 void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
                             uint32_t nframes, uint8_t *arena, cudaStream_t st)

@@ -32,7 +32,7 @@ void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams
 /* scratch == NULL: `frames` is already dense (host indexer) */
 void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
                           const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,
-                          uint32_t *gran_unit0, uint32_t *concealed_counter, cudaStream_t st);
+                          uint32_t *gran_unit0, uint32_t *concealed_counter, int verify_crc, cudaStream_t st);
 void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
                             uint32_t nframes, uint8_t *arena, cudaStream_t st);
 

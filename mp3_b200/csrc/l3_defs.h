@@ -171,6 +171,17 @@ L3_HD uint32_t l3_load_be32(const uint8_t *p)
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
 }
 
+/* CRC-16 of the audio frame (11172-3 2.4.3.1): generator x^16 + x^15 + x^2 + 1, initial value 0xFFFF,
+ * most significant bit first, over the last two header bytes and the side info. */
+L3_HD uint32_t l3_crc16(uint32_t crc, const uint8_t *p, uint32_t nbytes)
+{
+    for (uint32_t i = 0; i < nbytes; i++) {
+        crc ^= (uint32_t)p[i] << 8;
+        for (int k = 0; k < 8; k++) crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x8005u) & 0xffffu : (crc << 1) & 0xffffu;
+    }
+    return crc;
+}
+
 /* The tag frame an encoder may put first (the container step just before the hot path, SURVEY.md
  * 8(f) rank 1 / 3).  "Xing" (VBR) or "Info" (CBR) sits right after the side info of an otherwise
  * empty Layer III frame: flags (bit 0 frames, 1 bytes, 2 TOC[100], 3 quality), then optionally the

@@ -588,6 +588,22 @@ static size_t id3v2_skip(const uint8_t *buf, size_t len)
     return 0;
 }
 
+/* 11172-3 2.4.3.1 error check: CRC-16, generator polynomial x^16 + x^15 + x^2 + 1, shift register preset
+ * to all ones, fed bit by bit (MSB first) with header bits 16..31 and the side information.
+ * Off by default (the word is skipped); l3o_set_verify_crc(1) makes a mismatch conceal the frame. */
+static int g_verify_crc = 0;
+void l3o_set_verify_crc(int on) { g_verify_crc = on; }
+unsigned l3o_crc16(unsigned crc, const uint8_t *p, size_t nbits)
+{
+    for (size_t i = 0; i < nbits; i++) {
+        unsigned in = (p[i >> 3] >> (7 - (i & 7))) & 1u;
+        unsigned fb = ((crc >> 15) & 1u) ^ in;
+        crc = (crc << 1) & 0xffffu;
+        if (fb) crc ^= 0x8005u;
+    }
+    return crc;
+}
+
 /* Decode a whole buffer.  Any output pointer may be NULL.
  *   pcm      interleaved double, full scale +-1.0, cap_samples per channel
  *   dump_is  int16  [unit][576]   Huffman output (a5), bitstream order
@@ -645,6 +661,12 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
         l3o_side si;
         parse_side(buf + fr[f].off + 4 + (h->crc ? 2 : 0), h, &si);
         int ok = (size_t)si.main_data_begin <= fr[f].payload_off;
+        if (g_verify_crc && h->crc) {
+            const uint8_t *fp = buf + fr[f].off;
+            unsigned crc = l3o_crc16(0xffffu, fp + 2, 16);
+            crc = l3o_crc16(crc, fp + 6, (size_t)h->side_len * 8);
+            if (crc != (((unsigned)fp[4] << 8) | fp[5])) ok = 0;
+        }
         if (!ok) info->concealed_frames++;
         size_t bitpos = ok ? (fr[f].payload_off - si.main_data_begin) * 8 : 0;
         uint8_t sf[2][MAXCH][40];

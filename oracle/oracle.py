@@ -67,8 +67,9 @@ class Decoded:
     """Result of decode(): pcm [channels, samples] float64 (full scale +-1), plus optional dumps."""
 
 
-def decode(data, dumps=False, want_pcm=True):
+def decode(data, dumps=False, want_pcm=True, verify_crc=False):
     L = lib()
+    L.l3o_set_verify_crc(1 if verify_crc else 0)  # process-wide switch: tests that use it are single-threaded
     data = bytes(data)
     n = len(data)
     buf = (ctypes.c_uint8 * max(n, 1)).from_buffer_copy(data if n else b"\0")

@@ -43,13 +43,13 @@ def test_no_cpu_fallback(lib):
 
 def test_struct_sizes_match_header(lib):
     import mp3_b200
-    assert ctypes.sizeof(mp3_b200.Opts) == 32
+    assert ctypes.sizeof(mp3_b200.Opts) == 36
     assert ctypes.sizeof(mp3_b200.TagInfo) == 40
     assert ctypes.sizeof(mp3_b200.StreamInfo) == 56
     assert ctypes.sizeof(mp3_b200.Stats) == 96
     o = mp3_b200.Opts()
     lib.mp3b_opts_default(ctypes.byref(o))
-    assert o.struct_size == 32
+    assert o.struct_size == 36
 
 
 def test_product_does_not_import_oracle():

@@ -52,3 +52,33 @@ def test_tag_info_and_gapless_window(indexer, synth_mod, oracle_mod):
             assert gap.stream_info(i).samples == want.num_samples == win.shape[0]
             assert np.array_equal(win, whole[want.first_sample: want.first_sample + want.num_samples])
             l3util.assert_iso_full_accuracy(win, ref[want.first_sample: want.first_sample + want.num_samples], "stream %d" % i)
+
+
+def test_crc_verification_matches_oracle(synth_mod, oracle_mod):
+    """opts.verify_crc: a protected frame whose CRC-16 fails is concealed (and counted) exactly like the
+    oracle's 11172-3 2.4.3.1 check does; intact protected streams are unaffected."""
+    import mp3_b200 as m
+    cfgs = [dict(nframes=8, seed=90, crc=1, bitrate_kbps=192, sample_rate=48000),
+            dict(nframes=10, seed=91, crc=1, mode=1, blocks=1),
+            dict(nframes=12, seed=92, crc=1, sample_rate=22050, bitrate_kbps=64, mode=3, blocks=1),
+            dict(nframes=6, seed=93, crc=0)]
+    streams = [synth_mod.make_stream(**c) for c in cfgs]
+    damaged = []
+    for k, s in enumerate(streams):
+        frames = l3util.split_frames(s)
+        b = bytearray(s)
+        for j in (2, 4):
+            off = sum(len(f) for f in frames[:j])
+            b[off + 6 + 3 + k] ^= 0x04 << (k % 3)  # a bit inside the side info of frames 2 and 4
+        damaged.append(bytes(b))
+    for verify in (False, True):
+        with m.Decoder(device=0, pcm_format=m.PCM_F32, verify_crc=verify) as dec:
+            for batch in (streams, damaged):
+                dec.decode_batch(batch)
+                arena = dec.fetch_pcm()
+                refs = [oracle_mod.decode(s, verify_crc=verify) for s in batch]
+                assert dec.stats().concealed_frames == sum(r.concealed_frames for r in refs)
+                if verify and batch is damaged:
+                    assert [r.concealed_frames for r in refs][:3] == [2, 2, 2]
+                for i, r in enumerate(refs):
+                    l3util.assert_iso_full_accuracy(dec.stream_pcm(i, arena), r.pcm.T, "stream %d verify=%s" % (i, verify))

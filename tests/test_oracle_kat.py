@@ -62,3 +62,27 @@ def test_oracle_matches_committed_ffmpeg_golden(oracle_mod):
         # FFmpeg computes in float32: allow its rounding noise, far below the ISO limits
         rms, mx = l3util.iso_compliance(d.pcm, ref)
         assert rms < 5e-7 and mx < 1e-5, (name, rms, mx)
+
+
+def test_crc16_check_value(oracle_mod):
+    """CRC-16 with polynomial 0x8005, preset 0xFFFF, MSB first, no final xor: check value of "123456789"."""
+    import ctypes
+    L = oracle_mod.lib()
+    L.l3o_crc16.restype = ctypes.c_uint
+    L.l3o_crc16.argtypes = [ctypes.c_uint, ctypes.c_char_p, ctypes.c_size_t]
+    assert L.l3o_crc16(0xFFFF, b"123456789", 72) == 0xAEE7
+
+
+def test_crc_verification_conceals_exactly_the_damaged_frame(oracle_mod, synth_mod):
+    import l3util
+    s = synth_mod.make_stream(nframes=8, seed=90, crc=1, bitrate_kbps=192, sample_rate=48000)
+    good = oracle_mod.decode(s, verify_crc=True)
+    assert good.concealed_frames == 0  # the generator's own CRC routine agrees with the oracle's
+    frames = l3util.split_frames(s)
+    off = sum(len(f) for f in frames[:3])
+    bad = bytearray(s)
+    bad[off + 6 + 5] ^= 0x10  # one bit of frame 3's side info (inside a global_gain field)
+    d_off = oracle_mod.decode(bytes(bad))
+    d_on = oracle_mod.decode(bytes(bad), verify_crc=True)
+    assert d_off.concealed_frames == 0 and d_on.concealed_frames == 1
+    assert d_on.pcm.shape == d_off.pcm.shape == good.pcm.shape
