@@ -251,8 +251,12 @@ __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int
     }
 }
 
-// ---- S1b: intensity decisions, one thread per intensity granule (right channel's bands, high to low)
-__device__ __forceinline__ void stage_intensity(FusedShared &S, int gi, int u1 /* batch-local unit */,
+// ---- S1b: intensity decisions, one warp per intensity granule, lane = band (and band + 32) ------
+// A band of the right channel is intensity coded when no band of its own class (short window 0 / 1 / 2,
+// or long) at or above it holds a non-zero line -- and, for the long bands of a mixed block, no short
+// band does either (11172-3 2.4.3.4: intensity applies above the last non-zero band).  Scanned serially
+// from the top this is a chain; as "highest non-zero band per class" it is four ballots.
+__device__ __forceinline__ void stage_intensity(FusedShared &S, int gi, int u1 /* batch-local unit */, int lane,
                                                 const L3BandTables *__restrict__ bands)
 {
     const GranMeta &m = S.gm[gi];
@@ -260,22 +264,30 @@ __device__ __forceinline__ void stage_intensity(FusedShared &S, int gi, int u1 /
     const int nbands = bands->nbands[row][lay1];
     const bool lsf = (m.d[1].hdr & L3H_LSF) != 0;
     const uint8_t *sf1 = S.sf_buf[u1];
-    int found[3] = {0, 0, 0}, found_long = 0;
-    bool first_long = true;
-    for (int b = nbands - 1; b >= 0; b--) {
-        const int w = bands->win[row][lay1][b];
-        int *fnd;
-        if (w >= 0) fnd = &found[w];
-        else {
-            if (first_long) { found_long = found[0] | found[1] | found[2]; first_long = false; }
-            fnd = &found_long;
-        }
-        if (*fnd) continue;
-        if (S.nz[gi][b]) { *fnd = 1; continue; }
+    int cls[2], top[4] = {-1, -1, -1, -1}; // class of this lane's two bands; highest non-zero band per class
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int b = lane + 32 * r;
+        cls[r] = b < nbands ? (bands->win[row][lay1][b] < 0 ? 3 : bands->win[row][lay1][b]) : -1;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t lo = __ballot_sync(0xffffffffu, cls[0] == c && S.nz[gi][lane]);
+        const uint32_t hi = __ballot_sync(0xffffffffu, cls[1] == c && lane + 32 < 40 && S.nz[gi][lane + 32 < 40 ? lane + 32 : 0]);
+        top[c] = hi ? 63 - __clz(hi) : (lo ? 31 - __clz(lo) : -1);
+    }
+    const bool any_short_nz = top[0] >= 0 || top[1] >= 0 || top[2] >= 0;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int b = lane + 32 * r;
+        if (cls[r] < 0) continue;
+        const int c = cls[r];
+        const bool blocked = b <= top[c] || (c == 3 && any_short_nz);
+        if (blocked) continue;
         const int sfb = bands->sfb[row][lay1][b];
         int bsf = b;
-        if (w >= 0 && sfb == 12) bsf = b - 3;
-        if (w < 0 && sfb == 21) bsf = b - 1;
+        if (c != 3 && sfb == 12) bsf = b - 3;
+        if (c == 3 && sfb == 21) bsf = b - 1;
         const int p = sf1[bsf];
         if (!lsf) {
             if (p < 7) { S.mode[gi][b] = 1; S.kl[gi][b] = f_is_kl[p]; S.kr[gi][b] = f_is_kr[p]; }
@@ -296,13 +308,9 @@ __device__ __forceinline__ float requant1(const FusedShared &S, int v, float gai
     return v < 0 ? -a : a;
 }
 
-__device__ __forceinline__ int reorder_dst(const L3BandTables *__restrict__ bands, int row, int lay, int i, int b)
+__device__ __forceinline__ int reorder_dst(const L3BandTables *__restrict__ bands, int row, int lay, int i)
 {
-    if (lay == 0) return i;
-    const int w = bands->win[row][lay][b];
-    if (w < 0) return i;
-    const int wd = bands->width[row][lay][b], s = bands->start[row][lay][b];
-    return (s - w * wd) + 3 * (i - s) + w;
+    return lay == 0 ? i : (int)bands->dst[row][lay][i];
 }
 
 // ---- S1c: requantise + stereo + reorder, one (granule, line) per item -----------------------------
@@ -361,9 +369,9 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
                 if (m.ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
                 else if (m.ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
             }
-            S.X[gi][1][xpad(reorder_dst(bands, row, lay1, i, b1))] = r;
+            S.X[gi][1][xpad(reorder_dst(bands, row, lay1, i))] = r;
         }
-        S.X[gi][0][xpad(reorder_dst(bands, row, lay0, i, b0))] = l;
+        S.X[gi][0][xpad(reorder_dst(bands, row, lay0, i))] = l;
     }
 }
 
@@ -528,8 +536,8 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         stage_gains(S, tid, nb, nch, bands);
         __syncthreads();
         if (S.any_ist) {
-            if ((tid & 63) == 0 && (tid >> 6) < nb && S.gm[tid >> 6].ist)
-                stage_intensity(S, tid >> 6, (tid >> 6) * nch + 1, bands);
+            if ((tid & 32) == 0 && (tid >> 6) < nb && S.gm[tid >> 6].ist) // first warp of each granule's 64 threads
+                stage_intensity(S, tid >> 6, (tid >> 6) * nch + 1, lane, bands);
             __syncthreads();
         }
         stage_requant(S, tid, nb, nch, bands, pow43, bq);

@@ -22,6 +22,7 @@ typedef struct L3HuffInfo {
 /* Band layouts: [sample-rate row 0..8][0 = long, 1 = short, 2 = mixed]. */
 typedef struct L3BandTables {
     uint8_t line2band[9][3][576];
+    uint16_t dst[9][3][576]; /* where bitstream line i goes after the short-block reorder (identity for long bands) */
     uint16_t start[9][3][40];
     uint8_t width[9][3][40];
     int8_t win[9][3][40];    /* window 0..2 of a short band, -1 for a long band */

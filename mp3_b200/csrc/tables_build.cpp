@@ -114,7 +114,12 @@ extern "C" void l3_build_host_tables(L3HostTables *t)
             B.nbands[row][lay] = (uint8_t)n;
             B.nlong[row][lay] = (uint8_t)nl;
             for (int b = 0; b < n; b++)
-                for (int i = 0; i < B.width[row][lay][b]; i++) B.line2band[row][lay][B.start[row][lay][b] + i] = (uint8_t)b;
+                for (int i = 0; i < B.width[row][lay][b]; i++) {
+                    const int line = B.start[row][lay][b] + i, w = B.win[row][lay][b], wd = B.width[row][lay][b];
+                    B.line2band[row][lay][line] = (uint8_t)b;
+                    // short bands are transmitted window by window; the spectrum interleaves the windows
+                    B.dst[row][lay][line] = (uint16_t)(w < 0 ? line : (B.start[row][lay][b] - w * wd) + 3 * i + w);
+                }
         }
     }
     for (int i = 0; i < 8208; i++) t->pow43[i] = (float)std::pow((double)i, 4.0 / 3.0);
