@@ -77,6 +77,7 @@ struct FusedShared {
     GranMeta gm[KF_B];
     int any_ist;
     int any_short;                  // some unit of the batch has short / mixed blocks
+    uint32_t lmap[3][576];          // this stream's sample rate: [layout][line] -> band | xpad(reordered line) << 8
     // next batch's Huffman output and scalefactors, fetched with cp.async while this batch computes
     __align__(16) int16_t is_buf[KF_B * 2][576];
     __align__(16) uint8_t sf_buf[KF_B * 2][40];
@@ -85,6 +86,9 @@ struct FusedShared {
 
 // f_pow2q[q & 3] * 2^(q >> 2), exactly (q >> 2 stays within the normal exponent range: -82 .. 11)
 __device__ __forceinline__ float gain_of(int q) { return __int_as_float((127 + (q >> 2)) << 23) * f_pow2q[q & 3]; }
+
+// three CTAs per SM: 3 x (shared memory + 1 KB reserved per CTA) must fit 228 KB
+static_assert(sizeof(FusedShared) <= 75 * 1024, "FusedShared too large for 3 CTAs per SM");
 
 __device__ __forceinline__ int xpad(int i) { return i + ((i * 3641) >> 16); } // i + i / 18 for i < 608
 
@@ -220,33 +224,46 @@ __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int
             }
         }
     }
-    if (S.any_short)
-    for (int it = tid; it < nb * 80; it += KF_THREADS) {
-        const int gi = it / 80, c = (it % 80) / 40, b = it % 40;
-        if (c >= nch) continue;
-        const GranMeta &m = S.gm[gi];
-        const L3UnitDesc &dd = m.d[c];
-        const int lay = m.lay[c];
-        if (lay == 0) continue; // done above
-        float gn = 0.f;
-        if (b < bands->nbands[m.row][lay]) {
-            const int s = S.sf_buf[gi * nch + c][b] & 0x7f;
-            const int win = bands->win[m.row][lay][b];
+    if (S.any_short) {
+        // short / mixed layouts: up to 39 bands, lane and lane + 32 of the same (granule, channel) warp
+        const int gi = tid >> 6, c = (tid >> 5) & 1, lane = tid & 31;
+        if (gi < nb && c < nch && S.gm[gi].lay[c] != 0) {
+            const GranMeta &m = S.gm[gi];
+            const L3UnitDesc &dd = m.d[c];
+            const int lay = m.lay[c], nbands = bands->nbands[m.row][lay];
             const int sh = (dd.flags & L3F_SFSCALE) ? 4 : 2;
-            int q = (int)dd.global_gain - 210;
-            if (win < 0) q -= sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[bands->sfb[m.row][lay][b]] : 0));
-            else q -= 8 * dd.sbg[win] + sh * s;
-            gn = gain_of(q);
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int b = lane + 32 * r;
+                if (b >= 40) break;
+                float gn = 0.f;
+                if (b < nbands) {
+                    const int s = S.sf_buf[gi * nch + c][b] & 0x7f;
+                    const int win = bands->win[m.row][lay][b];
+                    int q = (int)dd.global_gain - 210;
+                    if (win < 0) q -= sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[bands->sfb[m.row][lay][b]] : 0));
+                    else q -= 8 * dd.sbg[win] + sh * s;
+                    gn = gain_of(q);
+                }
+                S.gain[gi][c][b] = gn;
+            }
         }
-        S.gain[gi][c][b] = gn;
     }
     if (S.any_ist) {
-        for (int it = tid; it < nb * 576; it += KF_THREADS) {
-            const int gi = it / 576, i = it - gi * 576;
+        // which bands of the right channel hold a non-zero line: one 16-byte vector (8 lines) per item
+        for (int it = tid; it < nb * 72; it += KF_THREADS) {
+            const int gi = it / 72, v = it - gi * 72;
             const GranMeta &m = S.gm[gi];
             if (!m.ist) continue;
-            if (S.is_buf[gi * nch + 1][i] != 0)
-                S.nz[gi][bands->line2band[m.row][m.lay[1]][i]] = 1;
+            const uint4 q = reinterpret_cast<const uint4 *>(&S.is_buf[gi * nch + 1][0])[v];
+            if ((q.x | q.y | q.z | q.w) == 0u) continue;
+            const uint32_t *lm = S.lmap[m.lay[1]] + v * 8;
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (w[k] & 0xffffu) S.nz[gi][lm[2 * k] & 0xffu] = 1;
+                if (w[k] >> 16) S.nz[gi][lm[2 * k + 1] & 0xffu] = 1;
+            }
         }
     }
 }
@@ -308,11 +325,6 @@ __device__ __forceinline__ float requant1(const FusedShared &S, int v, float gai
     return v < 0 ? -a : a;
 }
 
-__device__ __forceinline__ int reorder_dst(const L3BandTables *__restrict__ bands, int row, int lay, int i)
-{
-    return lay == 0 ? i : (int)bands->dst[row][lay][i];
-}
-
 // ---- S1c: requantise + stereo + reorder, one (granule, line) per item -----------------------------
 // `bq` holds this thread's nine long-block band indices (lines t64 + 64 q), one byte each: they
 // depend only on the stream's sample rate, so the common case (both channels long blocks, no
@@ -326,7 +338,7 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
     const int gi = tid >> 6, t64 = tid & 63;
     if (gi >= nb) return;
     const GranMeta &m = S.gm[gi];
-    const int row = m.row, lay0 = m.lay[0], lay1 = m.lay[1];
+    const int lay0 = m.lay[0], lay1 = m.lay[1];
     if (nch == 2 && (lay0 | lay1) == 0 && !m.ist) {
         const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
         const int16_t *s0 = S.is_buf[gi * 2], *s1 = S.is_buf[gi * 2 + 1];
@@ -357,21 +369,23 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
         v0[q] = S.is_buf[gi * nch][i];
         v1[q] = nch == 2 ? S.is_buf[gi * nch + 1][i] : 0;
     }
+    const uint32_t *lm0 = S.lmap[lay0], *lm1 = S.lmap[lay1];
+    const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
+    const bool ist = m.ist != 0, ms = m.ms != 0;
 #pragma unroll
     for (int q = 0; q < ITEMS; q++) {
         const int i = t64 + 64 * q;
-        const int b0 = bands->line2band[row][lay0][i];
-        const int b1 = (nch == 2 && lay1 != lay0) ? bands->line2band[row][lay1][i] : b0;
-        float l = requant1(S, v0[q], S.gain[gi][0][b0], pow43);
+        const uint32_t e0 = lm0[i];
+        float l = requant1(S, v0[q], g0[e0 & 0xffu], pow43);
         if (nch == 2) {
-            float r = requant1(S, v1[q], S.gain[gi][1][b1], pow43);
-            if (m.joint) {
-                if (m.ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
-                else if (m.ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
-            }
-            S.X[gi][1][xpad(reorder_dst(bands, row, lay1, i))] = r;
+            const uint32_t e1 = lm1[i];
+            const int b1 = (int)(e1 & 0xffu);
+            float r = requant1(S, v1[q], g1[b1], pow43);
+            if (ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
+            else if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
+            S.X[gi][1][e1 >> 8] = r;
         }
-        S.X[gi][0][xpad(reorder_dst(bands, row, lay0, i))] = l;
+        S.X[gi][0][e0 >> 8] = l;
     }
 }
 
@@ -508,6 +522,14 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.Hc[i / 144][0][0])[i % 144] = z;
         for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) S.pow43[i] = pow43[i];
         for (int i = tid; i < 512; i += KF_THREADS) (&S.win[0][0])[i] = (&f_synwin[0][0])[i];
+        {
+            const int row0 = (units[ubase].hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
+            for (int i = tid; i < 3 * 576; i += KF_THREADS) {
+                const int lay = i / 576, ln = i - lay * 576;
+                (&S.lmap[0][0])[i] = (uint32_t)bands->line2band[row0][lay][ln] |
+                                     ((uint32_t)xpad(lay == 0 ? ln : (int)bands->dst[row0][lay][ln]) << 8);
+            }
+        }
         load_meta(S, tid, ubase, min(KF_B, total), nch, units);
         prefetch_units(S, tid, ubase, min(KF_B, total) * nch, is_in, sf_in, nzv_in);
     }
