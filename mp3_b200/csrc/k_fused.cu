@@ -436,15 +436,23 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
             h[17 - i] = ((i & 1) ? sb : sb_s) * w[35 - i];
         }
     } else {
+        // 12-point IMDCT per window.  Only six of the twelve values are distinct (y[5-i] = -y[i],
+        // y[11-i] = y[6+i]: the kernel is a 6-point DCT-IV), so six dot products per window, not twelve.
         float y[3][12];
 #pragma unroll
         for (int wdw = 0; wdw < 3; wdw++)
 #pragma unroll
-            for (int i = 0; i < 12; i++) {
-                float s = 0.f;
+            for (int i = 0; i < 3; i++) {
+                float a = 0.f, b = 0.f;
 #pragma unroll
-                for (int k = 0; k < 6; k++) s = fmaf(x[3 * k + wdw], K12[i][k], s);
-                y[wdw][i] = s * f_win[2][i];
+                for (int k = 0; k < 6; k++) {
+                    a = fmaf(x[3 * k + wdw], K12[i][k], a);
+                    b = fmaf(x[3 * k + wdw], K12[6 + i][k], b);
+                }
+                y[wdw][i] = a * f_win[2][i];
+                y[wdw][5 - i] = -a * f_win[2][5 - i];
+                y[wdw][6 + i] = b * f_win[2][6 + i];
+                y[wdw][11 - i] = b * f_win[2][11 - i];
             }
 #pragma unroll
         for (int i = 0; i < 6; i++) {
