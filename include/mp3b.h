@@ -180,6 +180,16 @@ int mp3b_stream_fetch_pcm(mp3b_stream *s, void *dst, size_t cap_samples, int whe
 /* Zero-copy view of the stream's decoded PCM (valid until the next decode call / close). */
 int mp3b_stream_pcm_device_ptr(const mp3b_stream *s, const void **ptr, size_t *nsamples);
 
+/* ---- host-side frame index of one stream (no GPU involved) ---------------------------------
+ * The frame walk of the host indexer (MP3B_INDEX_HOST) as a utility: sync search past ID3v2 / junk,
+ * header validation, stream consistency, tag frame.  frames[i] = {byte offset of the header, main-data
+ * bytes of the stream before this frame, the 4 header bytes big-endian, 0}.  Returns MP3B_OK,
+ * MP3B_E_NOSYNC if no Layer III frame was found, MP3B_E_TRUNCATED if cap_frames was too small
+ * (*nframes then holds the number needed). */
+typedef struct mp3b_frame_rec { uint32_t offset, payload_offset, header, reserved; } mp3b_frame_rec;
+int mp3b_index_stream_host(const uint8_t *bytes, size_t n, mp3b_frame_rec *frames, size_t cap_frames,
+                           size_t *nframes, mp3b_stream_info *info, mp3b_tag_info *tag);
+
 /* ---- debug / parity access to intermediates (keep_stages = 1) -------------------------------
  * stage: see mp3b_stage.  Copies the whole stage array for the last batch to host memory.
  * *elem_size receives the element size in bytes, *count the number of elements. */

@@ -66,7 +66,7 @@ EXPORTS = [
     "mp3b_decode_packed", "mp3b_sync", "mp3b_flush", "mp3b_batch_stream_info", "mp3b_batch_tag_info", "mp3b_batch_pcm_device_ptr",
     "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_set_pcm_sink", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
-    "mp3b_debug_stage",
+    "mp3b_debug_stage", "mp3b_index_stream_host",
 ]
 
 _lib = None
@@ -175,6 +175,33 @@ class Stream:
         if self.h:
             self.dec.L.mp3b_stream_close(self.h)
             self.h = None
+
+
+class FrameRec(ctypes.Structure):
+    _fields_ = [("offset", ctypes.c_uint32), ("payload_offset", ctypes.c_uint32), ("header", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
+
+
+def index_stream_host(data):
+    """Frame index of one stream computed on the host (no GPU): (frames[n] structured array, StreamInfo,
+    TagInfo), or (empty, info, tag) when no Layer III frame is found."""
+    L = load_library()
+    data = bytes(data)
+    n = len(data)
+    buf = (ctypes.c_uint8 * max(n, 1)).from_buffer_copy(data if n else b"\0")
+    cap = n // 24 + 2
+    frames = (FrameRec * cap)()
+    got = ctypes.c_size_t()
+    info, tag = StreamInfo(), TagInfo()
+    L.mp3b_index_stream_host.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                         ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(StreamInfo),
+                                         ctypes.POINTER(TagInfo)]
+    rc = L.mp3b_index_stream_host(buf, n, frames, cap, ctypes.byref(got), ctypes.byref(info), ctypes.byref(tag))
+    if rc not in (0, -2):
+        raise Mp3bError(rc, L.mp3b_strerror(rc).decode())
+    arr = np.frombuffer(frames, dtype=np.dtype([("offset", "<u4"), ("payload_offset", "<u4"), ("header", "<u4"),
+                                                ("reserved", "<u4")]), count=got.value).copy()
+    return arr, info, tag
 
 
 class Decoder:

@@ -233,6 +233,33 @@ void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRe
     r->payload_len = payload;
 }
 
+// The encoder's tag frame and the gapless window it implies: the tag frame itself is not audio, the
+// encoder delay plus the decoder's own 528 + 1 samples are cut from the head, the padding from the tail
+// (what mpg123 / FFmpeg do with the same fields).
+void fill_tag_info(const L3StreamRec &r, const L3Hdr &h, mp3b_tag_info *tg)
+{
+    const int64_t spf = (int64_t)h.ngr * 576, total = (int64_t)r.nframes * spf;
+    tg->kind = (int32_t)(r.tag_kind & L3T_KIND_MASK);
+    tg->has_lame = (r.tag_kind & L3T_LAME) ? 1 : 0;
+    tg->frames = r.tag_frames;
+    tg->bytes = r.tag_bytes;
+    tg->enc_delay = (int32_t)(r.tag_delay_pad >> 16);
+    tg->enc_padding = (int32_t)(r.tag_delay_pad & 0xffffu);
+    int64_t start = 0, count = total;
+    if (tg->kind != 0) {
+        start = spf;
+        count = total - spf;
+        if (tg->has_lame) {
+            start += tg->enc_delay + 529;
+            count -= (int64_t)tg->enc_delay + tg->enc_padding;
+        }
+    }
+    start = std::min(start, total);
+    count = std::max<int64_t>(0, std::min(count, total - start));
+    tg->first_sample = start;
+    tg->num_samples = count;
+}
+
 int nthreads_of(const mp3b_ctx *ctx)
 {
     int n = ctx->opts.host_threads;
@@ -373,29 +400,10 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             // from the tail (what mpg123 / FFmpeg do with the same fields)
             {
                 mp3b_tag_info &tg = ctx->tags[(size_t)i];
-                const int64_t spf = (int64_t)h.ngr * 576, total = (int64_t)r.nframes * spf;
-                tg.kind = (int32_t)(r.tag_kind & L3T_KIND_MASK);
-                tg.has_lame = (r.tag_kind & L3T_LAME) ? 1 : 0;
-                tg.frames = r.tag_frames;
-                tg.bytes = r.tag_bytes;
-                tg.enc_delay = (int32_t)(r.tag_delay_pad >> 16);
-                tg.enc_padding = (int32_t)(r.tag_delay_pad & 0xffffu);
-                int64_t start = 0, count = total;
-                if (tg.kind != 0) {
-                    start = spf;
-                    count = total - spf;
-                    if (tg.has_lame) {
-                        start += tg.enc_delay + 529;
-                        count -= (int64_t)tg.enc_delay + tg.enc_padding;
-                    }
-                }
-                start = std::min(start, total);
-                count = std::max<int64_t>(0, std::min(count, total - start));
-                tg.first_sample = start;
-                tg.num_samples = count;
+                fill_tag_info(r, h, &tg);
                 if (ctx->opts.gapless && !hints) {
-                    inf.pcm_offset += start * h.nch;
-                    inf.samples = count;
+                    inf.pcm_offset += tg.first_sample * h.nch;
+                    inf.samples = tg.num_samples;
                 }
             }
             frames += r.nframes;
@@ -751,6 +759,40 @@ void mp3b_host_free(void *p)
 }
 
 static int finalize_stream_batch(mp3b_ctx *ctx);
+
+int mp3b_index_stream_host(const uint8_t *bytes, size_t n, mp3b_frame_rec *frames, size_t cap_frames,
+                           size_t *nframes, mp3b_stream_info *info, mp3b_tag_info *tag)
+{
+    if ((!bytes && n) || !nframes || n > 0xFFFFFF00ull) return MP3B_E_INVAL;
+    static_assert(sizeof(mp3b_frame_rec) == sizeof(L3FrameRec), "frame record layouts must agree");
+    L3StreamRec r;
+    memset(&r, 0, sizeof r);
+    r.raw_len = (uint32_t)n;
+    std::vector<L3FrameRec> out;
+    host_index_stream(bytes, &r, &out, 0);
+    *nframes = out.size();
+    if (info) memset(info, 0, sizeof *info);
+    if (tag) memset(tag, 0, sizeof *tag);
+    if (out.empty()) return MP3B_E_NOSYNC;
+    L3Hdr h;
+    l3_parse_hdr(r.first_hdr, &h);
+    if (info) {
+        info->sample_rate = l3_sr_hz(h.sr_row);
+        info->channels = h.nch;
+        info->lsf = h.lsf;
+        info->frames = (int64_t)out.size();
+        info->samples = (int64_t)out.size() * h.ngr * 576;
+    }
+    if (tag) fill_tag_info(r, h, tag);
+    if (out.size() > cap_frames || (!frames && cap_frames)) return MP3B_E_TRUNCATED;
+    for (size_t i = 0; i < out.size(); i++) {
+        frames[i].offset = out[i].rel_off;
+        frames[i].payload_offset = out[i].payload_off;
+        frames[i].header = out[i].hdr;
+        frames[i].reserved = 0;
+    }
+    return MP3B_OK;
+}
 
 int mp3b_decode_packed(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams, int where)
 {
