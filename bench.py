@@ -152,6 +152,10 @@ def run_ours(args, rank, world):
     import mp3_b200
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
+    numa = None
+    if world > 1 and not args.no_numa:  # before any pinned allocation: first touch decides the node
+        from mp3_b200 import multi
+        numa = multi.bind_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -239,7 +243,7 @@ def run_ours(args, rank, world):
         ms_e2e, checksum = run_e2e(args, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier)
     sampler.stop_flag = True
     finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, ms_e2e, stage_ms,
-           launches, sampler, gen_s, checksum, strong)
+           launches, sampler, gen_s, checksum, strong, numa)
 
 
 def run_e2e(args, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier):
@@ -272,7 +276,7 @@ def run_e2e(args, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, ba
 
 
 def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, ms_e2e, stage_ms,
-           launches, sampler, gen_s, checksum, strong):
+           launches, sampler, gen_s, checksum, strong, numa=None):
     import torch
     # ---- max over ranks
     if dist is not None:
@@ -329,6 +333,7 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
                 "pcm": "s16 interleaved", "pipeline": args.pipeline, "indexer": "device",
                 "l2_policy": "inputs_larger_than_l2 (%.0f MB in, %.0f MB PCM out per step)" % (nbytes_in / 1e6, pcm_bytes / 1e6),
                 "timing": "torch.cuda.Event on the stream the library launches on",
+                "host_binding": numa or "none",
             },
             "pcm_gbs": pcm_all / (ms_dev * 1e-3) / 1e9,
             "x_realtime_per_gpu": audio_all / world / (ms_dev * 1e-3),
@@ -373,6 +378,7 @@ def main():
     ap.add_argument("--pipeline", default="default", choices=["default", "fused", "staged"])
     ap.add_argument("--stage-times", action="store_true", help="sync after every step to read per-stage events")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.pipeline_id = {"default": None, "fused": 0, "staged": 1}[args.pipeline]

@@ -38,6 +38,51 @@ def merge(parts, ranges, n):
     return out
 
 
+def _parse_cpulist(txt):
+    cpus = []
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that the pinned
+    staging buffers it allocates afterwards (first touch) are local to that GPU's PCIe root: with one
+    process per GPU, cross-socket staging is what caps the aggregate host <-> device bandwidth.
+    Returns a short description, or None when the topology cannot be read (then nothing changes)."""
+    import os
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(device).pci_bus_id  # not on every torch build
+    except Exception:
+        bdf = None
+    try:
+        if bdf is None:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            if isinstance(bdf, bytes):
+                bdf = bdf.decode()
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return "numa node %d (%d cpus)" % (node, len(allowed))
+    except Exception:
+        return None
+
+
 class MultiDecoder:
     """One Decoder (context) per device, each driven by its own thread."""
 
