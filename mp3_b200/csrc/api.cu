@@ -453,7 +453,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             const uint32_t g = sgran[(size_t)i];
             if (fused)
                 for (uint32_t a = sskip[(size_t)i]; a < g; a += GF)
-                    t4[k++] = make_uint4(r.gran_base + a, std::min<uint32_t>(GF, g - a), std::min<uint32_t>(2u, a), 0u);
+                    t4[k++] = make_uint4(r.gran_base + a, std::min<uint32_t>(GF, g - a), std::min<uint32_t>(2u, a),
+                                         sunit[(size_t)i] == g ? 1u : 0u /* mono */);
             else
                 for (uint32_t a = 0; a < g; a += (uint32_t)G)
                     t2[k++] = make_uint2(r.gran_base + a, std::min<uint32_t>((uint32_t)G, g - a));
@@ -501,6 +502,14 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             s0 = s1;
         }
     }
+    // Inside a wave the tile order is free: stereo tiles first, mono tiles after, so that the CTAs
+    // resident on an SM at any time mostly run the same specialisation of the back end (instruction cache).
+    if (fused)
+        for (const auto &wv : waves) {
+            uint4 *t4 = ctx->h_tiles.as<uint4>();
+            std::stable_partition(t4 + tile_start[(size_t)wv.first], t4 + tile_start[(size_t)wv.second],
+                                  [](const uint4 &t) { return t.w == 0u; });
+        }
     CK(ctx->d_is.ensure(max_wave_units * 576 * sizeof(int16_t)));
     CK(ctx->d_sf.ensure(max_wave_units * 40));
     CK(ctx->d_nzv.ensure(max_wave_units + 16));

@@ -162,9 +162,9 @@ __device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t
         if (b) bulk_g2s(&S.is_buf[k][0], is_in + (size_t)(u_first + k) * 576, b, &S.bar);
     }
     const int unit = tid >> 5, lane = tid & 31;
-    if (unit < n) {
+    if (unit < n || (unit == n && (n & 1))) { // an odd mono batch leaves one slot of the last pair empty: all zero
         char *si = reinterpret_cast<char *>(&S.is_buf[unit][0]);
-        const int nv = nzv_in[u_first + unit];
+        const int nv = unit < n ? nzv_in[u_first + unit] : 0;
 #pragma unroll
         for (int v = lane; v < 72; v += 32)
             if (v >= nv) *reinterpret_cast<uint4 *>(si + v * 16) = make_uint4(0, 0, 0, 0);
@@ -176,13 +176,13 @@ __device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t
 }
 
 // ---- per-batch metadata (descriptors, layouts), loaded one batch ahead ---------------------------
-__device__ __forceinline__ void load_meta(FusedShared &S, int tid, uint32_t u_first, int nb, int nch,
+// A batch is held as pairs of unit slots: the two channels of a stereo granule, or two consecutive
+// granules of a mono stream (which doubles the granules per batch, so that mono tiles keep all eight
+// warps busy).  `nun` = units in the batch; an odd mono batch repeats its last descriptor.
+__device__ __forceinline__ void load_meta(FusedShared &S, int tid, uint32_t u_first, int nun,
                                           const L3UnitDesc *__restrict__ units)
 {
-    if (tid < nb * 2) {
-        const int gi = tid >> 1, c = tid & 1;
-        S.gm[gi].d[c] = units[u_first + (uint32_t)gi * nch + (c < nch ? c : 0)];
-    }
+    if (tid < ((nun + 1) & ~1)) S.gm[tid >> 1].d[tid & 1] = units[u_first + (uint32_t)min(tid, nun - 1)];
     for (int i = tid; i < KF_B * 40; i += KF_THREADS) {
         (&S.nz[0][0])[i] = 0;
         (&S.mode[0][0])[i] = 0;
@@ -202,7 +202,7 @@ __device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int
         m.ist = (nch == 2 && ok && (m.d[0].hdr & L3H_IS)) ? 1 : 0;
         m.joint = m.ms | m.ist;
         if (m.ist) S.any_ist = 1;
-        if (m.lay[0] | (nch == 2 ? m.lay[1] : 0)) S.any_short = 1;
+        if (m.lay[0] | m.lay[1]) S.any_short = 1;
     }
 }
 
@@ -501,25 +501,22 @@ __device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r
     }
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(KF_THREADS, 3)
-k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
-          const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
-          const uint8_t *__restrict__ nzv_in, const L3BandTables *__restrict__ bands,
-          const float *__restrict__ pow43, void *__restrict__ pcm)
+// One tile.  MONO is a compile-time switch so that the stereo path carries none of the mono index
+// arithmetic: pairs of consecutive mono granules take the two slots a stereo granule's channels would,
+// eight granules per batch, and the rows of F form ONE time sequence (F[0] and F[1] are contiguous).
+template <int FMT, bool MONO>
+__device__ __forceinline__ void backend_tile(FusedShared &S, const int warm, const int total, const uint32_t ubase,
+                                             const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in,
+                                             const uint8_t *__restrict__ sf_in, const uint8_t *__restrict__ nzv_in,
+                                             const L3BandTables *__restrict__ bands, const float *__restrict__ pow43,
+                                             void *__restrict__ pcm)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedShared &S = *reinterpret_cast<FusedShared *>(smem_raw);
-    if (blockIdx.x >= ntiles) return;
-    const uint4 tl = tiles[blockIdx.x];
-    const int warm = (int)tl.z, ng = (int)tl.y;    // granules before g0 to re-derive state from
-    const uint32_t gstart = tl.x - (uint32_t)warm;  // first granule processed
-    const int total = ng + warm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t gu_first = gran_unit0[gstart];
-    const int nch = (gu_first & L3G_STEREO) ? 2 : 1;
-    const uint32_t ubase = gu_first & L3G_UNIT_MASK; // units of a stream are contiguous
+    constexpr int nch = MONO ? 1 : 2;
     typedef typename std::conditional<FMT == MP3B_PCM_S16, int16_t, float>::type pcm_t;
+    constexpr bool mono = MONO;
+    constexpr int KFG = mono ? 2 * KF_B : KF_B;
+    float *const Fm = &S.F[0][0][0];
 
     if (tid == 0) mbar_init(&S.bar, 1);
     __syncthreads();
@@ -538,8 +535,8 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                                      ((uint32_t)xpad(lay == 0 ? ln : (int)bands->dst[row0][lay][ln]) << 8);
             }
         }
-        load_meta(S, tid, ubase, min(KF_B, total), nch, units);
-        prefetch_units(S, tid, ubase, min(KF_B, total) * nch, is_in, sf_in, nzv_in);
+        load_meta(S, tid, ubase, min(KFG, total) * nch, units);
+        prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in, nzv_in);
     }
     __syncthreads();
 
@@ -554,36 +551,40 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
             bq[q >> 2] |= (uint32_t)bands->line2band[row0][0][(tid & 63) + 64 * q] << (8 * (q & 3));
     }
 
-    for (int b0 = 0; b0 < total; b0 += KF_B) {
-        const int nb = min(KF_B, total - b0);
+    for (int b0 = 0; b0 < total; b0 += KFG) {
+        const int nb = min(KFG, total - b0);           // granules of this batch
+        const int np = mono ? (nb + 1) >> 1 : nb;      // slot pairs of this batch
         const uint32_t u_first = ubase + (uint32_t)b0 * nch;
         // ---- S1
-        finish_meta(S, tid, nb, nch);
+        finish_meta(S, tid, np, nch);
         cp_async_wait_all();                        // scalefactors (LDGSTS)
-        mbar_wait(&S.bar, (uint32_t)(b0 / KF_B) & 1u); // spectra (TMA); one phase per batch
+        mbar_wait(&S.bar, (uint32_t)(b0 / KFG) & 1u); // spectra (TMA); one phase per batch
         if (tid == KF_THREADS - 32) bulk_wait_read_all(); // the previous batch's PCM has left the staging buffer
         __syncthreads();
-        stage_gains(S, tid, nb, nch, bands);
+        stage_gains(S, tid, np, 2, bands);
         __syncthreads();
-        if (S.any_ist) {
-            if ((tid & 32) == 0 && (tid >> 6) < nb && S.gm[tid >> 6].ist) // first warp of each granule's 64 threads
-                stage_intensity(S, tid >> 6, (tid >> 6) * nch + 1, lane, bands);
+        if (S.any_ist) { // stereo only
+            if ((tid & 32) == 0 && (tid >> 6) < np && S.gm[tid >> 6].ist) // first warp of each granule's 64 threads
+                stage_intensity(S, tid >> 6, (tid >> 6) * 2 + 1, lane, bands);
             __syncthreads();
         }
-        stage_requant(S, tid, nb, nch, bands, pow43, bq);
+        stage_requant(S, tid, np, 2, bands, pow43, bq);
         __syncthreads();
         // ---- S2: alias + IMDCT; second halves travel in registers to the next granule's rows
         {
+            // warp -> slot (gi, c); j = its granule inside the batch, seq = the row sequence it belongs to
             const int gi = warp >> 1, c = warp & 1;
-            const bool act = gi < nb && c < nch;
+            const int j = mono ? warp : gi;
+            const bool act = j < nb;
+            float *const seq = mono ? Fm : &S.F[c][0][0];
+            float *const hc = &S.Hc[mono ? 0 : c][0][0];
             float h[18];
             if (act)
-                stage_imdct(S.X[gi][c], lane, S.gm[gi].d[c].flags, &S.F[c][15 + gi * 18][0],
-                            gi == 0 ? &S.Hc[c][0][0] : nullptr, h);
+                stage_imdct(S.X[gi][c], lane, S.gm[gi].d[c].flags, seq + (15 + j * 18) * FS, j == 0 ? hc : nullptr, h);
             __syncthreads();
             if (act) {
-                float *dst = gi + 1 < nb ? &S.F[c][15 + (gi + 1) * 18][0] : &S.Hc[c][0][0];
-                if (gi + 1 < nb) {
+                float *dst = j + 1 < nb ? seq + (15 + (j + 1) * 18) * FS : hc;
+                if (j + 1 < nb) {
 #pragma unroll
                     for (int t = 0; t < 18; t++) dst[t * FS + lane] += h[t];
                 } else {
@@ -594,18 +595,18 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         }
         __syncthreads();
         // next batch: descriptors (gm is dead until the next S1) and, behind S3..S5, spectra + scalefactors
-        if (b0 + KF_B < total) {
-            load_meta(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B), nch, units);
-            prefetch_units(S, tid, u_first + (uint32_t)KF_B * nch, min(KF_B, total - b0 - KF_B) * nch, is_in, sf_in,
+        if (b0 + KFG < total) {
+            load_meta(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, units);
+            prefetch_units(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, is_in, sf_in,
                            nzv_in);
         }
         // ---- S3: 32-point transform of every slot, in place; one thread per (channel, slot) row,
         // the whole transform in registers (fast_dct.h: 304 operations instead of 1024 FMAs)
         {
-            const int rows_c = nb * 18;
+            const int rows_c = nb * 18; // rows per sequence: stereo has two sequences, mono one
             if (tid < nch * rows_c) {
                 const int c = tid >= rows_c ? 1 : 0;
-                float *row = &S.F[c][15 + tid - c * rows_c][0];
+                float *row = &S.F[c][0][0] + (15 + tid - c * rows_c) * FS;
                 float x[32];
 #pragma unroll
                 for (int k = 0; k < 32; k++) x[k] = row[k];
@@ -617,13 +618,13 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
         __syncthreads();
         // ---- S4: window -> PCM staging (X is free now)
         {
-            const int gi = warp >> 1, c = warp & 1;
-            if (gi < nb && c < nch && b0 + gi >= warm) {
+            const int c = mono ? 0 : (warp & 1), j = mono ? warp : (warp >> 1);
+            if (j < nb && b0 + j >= warm) {
                 float wn[16];
 #pragma unroll
                 for (int l = 0; l < 16; l++) wn[l] = S.win[l][lane];
-                pcm_t *dst = stage + (size_t)gi * 576 * nch + c;
-                stage_window(&S.F[c][0][0], gi * 18, src_e, src_o, wn, [&](int t, float val) {
+                pcm_t *dst = stage + (size_t)j * 576 * nch + c;
+                stage_window(&S.F[c][0][0], j * 18, src_e, src_o, wn, [&](int t, float val) {
                     if (FMT == MP3B_PCM_S16) dst[(t * 32 + lane) * nch] = (pcm_t)to_s16(val);
                     else dst[(t * 32 + lane) * nch] = (pcm_t)val;
                 });
@@ -640,13 +641,34 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
                 bulk_s2g(reinterpret_cast<pcm_t *>(pcm) + e0, stage + (size_t)first_out * 576 * nch, bytes);
             }
             for (int k = tid; k < 15 * FS; k += KF_THREADS) {
-                S.F[0][0][k] = S.F[0][nb * 18][k];
-                S.F[1][0][k] = S.F[1][nb * 18][k];
+                Fm[k] = Fm[nb * 18 * FS + k];
+                if (!mono) S.F[1][0][k] = S.F[1][nb * 18][k];
             }
         }
         __syncthreads();
     }
     if (tid == KF_THREADS - 32) bulk_wait_read_all(); // the last PCM store must have read the staging buffer
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(KF_THREADS, 3)
+k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
+          const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
+          const uint8_t *__restrict__ nzv_in, const L3BandTables *__restrict__ bands,
+          const float *__restrict__ pow43, void *__restrict__ pcm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedShared &S = *reinterpret_cast<FusedShared *>(smem_raw);
+    if (blockIdx.x >= ntiles) return;
+    const uint4 tl = tiles[blockIdx.x];
+    const int warm = (int)tl.z, ng = (int)tl.y;    // granules before g0 to re-derive state from
+    const uint32_t gstart = tl.x - (uint32_t)warm;  // first granule processed
+    const uint32_t gu_first = gran_unit0[gstart];
+    const uint32_t ubase = gu_first & L3G_UNIT_MASK; // units of a stream are contiguous
+    if (gu_first & L3G_STEREO)
+        backend_tile<FMT, false>(S, warm, ng + warm, ubase, units, is_in, sf_in, nzv_in, bands, pow43, pcm);
+    else
+        backend_tile<FMT, true>(S, warm, ng + warm, ubase, units, is_in, sf_in, nzv_in, bands, pow43, pcm);
 }
 
 } // namespace
