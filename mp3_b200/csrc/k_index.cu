@@ -93,12 +93,41 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     streams[s].tag_delay_pad = tag_dp;
 }
 
-// Sequential big-endian bit reader over unaligned bytes (side info is 9..32 bytes).
+// Sequential big-endian bit reader over the side info (9..32 bytes), which the thread has staged in
+// its own shared-memory slot: the global loads of a frame's side info are issued together (aligned
+// words, all in flight at once) instead of byte after dependent byte.
+constexpr int SP_THREADS = 128, SP_WORDS = 9, SP_STRIDE = 11; // 9 aligned words cover 32 bytes at any alignment
 struct SideBits {
-    const uint8_t *p, *end; // never reads at or beyond `end` (the end of the stream's bytes)
+    const uint8_t *p, *end; // bytes at or beyond `end` read as zero
     unsigned long long acc;
     int n;
     __device__ __forceinline__ uint32_t byte() { return p < end ? *p++ : (p++, 0u); }
+    // copy the side info [q, q + len) (clipped to the stream's end e) into `slot` and read from there
+    __device__ __forceinline__ void stage(const uint8_t *q, const uint8_t *e, uint32_t len, uint32_t *slot)
+    {
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3u);
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(q - sh);
+        const uint32_t avail = (uint32_t)max((ptrdiff_t)0, min((ptrdiff_t)len, e - q)); // side-info bytes that exist
+        uint32_t w[SP_WORDS];
+#pragma unroll
+        for (int k = 0; k < SP_WORDS; k++) {
+            // word k is needed if it holds a byte of the side info; a word that would reach past the
+            // stream's end is fetched byte by byte (the buffer may end right there)
+            const bool need = 4u * k < sh + avail;
+            const bool whole = reinterpret_cast<const uint8_t *>(base + k + 1) <= e;
+            uint32_t v = 0;
+            if (need && whole) v = __ldg(base + k);
+            else if (need)
+                for (int j = 0; j < 4; j++) {
+                    const uint8_t *bp = reinterpret_cast<const uint8_t *>(base + k) + j;
+                    if (bp >= q && bp < e) v |= (uint32_t)*bp << (8 * j);
+                }
+            w[k] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < SP_WORDS; k++) slot[k] = w[k];
+        init(reinterpret_cast<const uint8_t *>(slot) + sh, reinterpret_cast<const uint8_t *>(slot) + sh + avail);
+    }
     __device__ __forceinline__ void init(const uint8_t *q, const uint8_t *e)
     {
         p = q;
@@ -156,8 +185,10 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
     l3_parse_hdr(fr.hdr, &h);
     const uint32_t fi = f - sr.frame_base; /* frame index inside its stream */
     const uint16_t *sfb_long = sfb_long_all + h.sr_row * 23;
+    __shared__ uint32_t s_side[SP_THREADS][SP_STRIDE];
     SideBits b;
-    b.init(raw + sr.raw_off + fr.rel_off + 4 + (h.crc ? 2 : 0), raw + sr.raw_off + sr.raw_len);
+    b.stage(raw + sr.raw_off + fr.rel_off + 4 + (h.crc ? 2 : 0), raw + sr.raw_off + sr.raw_len, (uint32_t)h.side_len,
+            s_side[threadIdx.x]);
     const int nch = h.nch, ngr = h.ngr;
     uint32_t mdb, scfsi[2] = {0, 0};
     if (!h.lsf) {
@@ -254,37 +285,59 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
     }
 }
 
-// One warp per frame.  Source and destination have arbitrary alignment: the destination is brought to
+// Main-data compaction.  A CTA takes 64 frames: 64 threads first resolve one frame each (record,
+// stream record, header -> source, destination, length) into shared memory, so that the dependent
+// loads of all 64 frames are in flight together instead of heading every warp's copy; then each warp
+// copies eight frames.  Source and destination have arbitrary alignment: the destination is brought to
 // a word boundary with a few byte stores, then each lane builds one aligned destination word from two
 // aligned source words (byte permute), 128 bytes per warp instruction; a byte tail finishes.
-__global__ void k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams,
-                               const L3FrameRec *__restrict__ frames, uint32_t nframes, uint8_t *__restrict__ arena)
+constexpr int PC_FRAMES = 64, PC_THREADS = 256;
+__global__ void __launch_bounds__(PC_THREADS)
+k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams,
+               const L3FrameRec *__restrict__ frames, uint32_t nframes, uint8_t *__restrict__ arena)
 {
-    uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (f >= nframes) return;
-    L3FrameRec fr = frames[f];
-    L3StreamRec sr = streams[fr.stream];
-    L3Hdr h;
-    l3_parse_hdr(fr.hdr, &h);
-    uint32_t skip = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len, n = (uint32_t)h.frame_len - skip;
-    const uint8_t *src = raw + sr.raw_off + fr.rel_off + skip;
-    uint8_t *dst = arena + sr.payload_base + fr.payload_off;
-    const uint32_t head = min(n, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
-    if (lane < head) dst[lane] = src[lane];
-    src += head;
-    dst += head;
-    n -= head;
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
-    // words whose two source words lie inside the frame's own bytes (no read past the stream's end)
-    const uint32_t nw = n >= 8u ? (n - (sh ? 4u : 0u)) >> 2 : 0u;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - sh);
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
-    const uint32_t sel = 0x3210u + 0x1111u * sh;
-    for (uint32_t i = lane; i < nw; i += 32) {
-        const uint32_t a = __ldg(sw + i), b = sh ? __ldg(sw + i + 1) : 0u;
-        dw[i] = __byte_perm(a, b, sel);
+    __shared__ const uint8_t *s_src[PC_FRAMES];
+    __shared__ uint8_t *s_dst[PC_FRAMES];
+    __shared__ uint32_t s_n[PC_FRAMES];
+    const uint32_t f0 = blockIdx.x * PC_FRAMES, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < PC_FRAMES) {
+        const uint32_t f = f0 + threadIdx.x;
+        uint32_t n = 0;
+        if (f < nframes) {
+            const L3FrameRec fr = frames[f];
+            const L3StreamRec &sr = streams[fr.stream];
+            L3Hdr h;
+            l3_parse_hdr(fr.hdr, &h);
+            const uint32_t skip = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len;
+            n = (uint32_t)h.frame_len - skip;
+            s_src[threadIdx.x] = raw + sr.raw_off + fr.rel_off + skip;
+            s_dst[threadIdx.x] = arena + sr.payload_base + fr.payload_off;
+        }
+        s_n[threadIdx.x] = n;
     }
-    for (uint32_t i = nw * 4u + lane; i < n; i += 32) dst[i] = src[i];
+    __syncthreads();
+    for (uint32_t k = warp; k < PC_FRAMES; k += PC_THREADS / 32) {
+        uint32_t n = s_n[k];
+        if (!n) continue;
+        const uint8_t *src = s_src[k];
+        uint8_t *dst = s_dst[k];
+        const uint32_t head = min(n, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+        if (lane < head) dst[lane] = src[lane];
+        src += head;
+        dst += head;
+        n -= head;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+        // words whose two source words lie inside the frame's own bytes (no read past the stream's end)
+        const uint32_t nw = n >= 8u ? (n - (sh ? 4u : 0u)) >> 2 : 0u;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - sh);
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+        const uint32_t sel = 0x3210u + 0x1111u * sh;
+        for (uint32_t i = lane; i < nw; i += 32) {
+            const uint32_t a = __ldg(sw + i), b = sh ? __ldg(sw + i + 1) : 0u;
+            dw[i] = __byte_perm(a, b, sel);
+        }
+        for (uint32_t i = nw * 4u + lane; i < n; i += 32) dst[i] = src[i];
+    }
 }
 
 // Small results go to the host through stores into pinned (UVA-mapped) memory instead of a D2H
@@ -315,14 +368,12 @@ void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int ns
                           uint32_t *gran_unit0, uint32_t *concealed_counter, int verify_crc, cudaStream_t st)
 {
     if (!nframes) return;
-    k_side_parse<<<(nframes + 127) / 128, 128, 0, st>>>(raw, streams, nstreams, frames, scratch, nframes, T.sfb_long,
+    k_side_parse<<<(nframes + SP_THREADS - 1) / SP_THREADS, SP_THREADS, 0, st>>>(raw, streams, nstreams, frames, scratch, nframes, T.sfb_long,
                                                         units, gran_unit0, concealed_counter, verify_crc);
 }
 void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
                             uint32_t nframes, uint8_t *arena, cudaStream_t st)
 {
     if (!nframes) return;
-    uint32_t threads = 256, warps_per_block = threads / 32;
-    k_payload_copy<<<(nframes + warps_per_block - 1) / warps_per_block, threads, 0, st>>>(raw, streams, frames,
-                                                                                         nframes, arena);
+    k_payload_copy<<<(nframes + PC_FRAMES - 1) / PC_FRAMES, PC_THREADS, 0, st>>>(raw, streams, frames, nframes, arena);
 }
