@@ -220,7 +220,11 @@ __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int
                 const int s = S.sf_buf[gi * nch + c][b] & 0x7f;
                 const int sh = (dd.flags & L3F_SFSCALE) ? 4 : 2;
                 const int q = (int)dd.global_gain - 210 - sh * (s + ((dd.flags & L3F_PREFLAG) ? f_pretab[b] : 0));
-                S.gain[gi][c][b] = gain_of(q);
+                // the table-free requantise path (both channels long, no intensity) takes the MS factor
+                // 1 / sqrt 2 from the gains; the general path applies it per line
+                const GranMeta &m = S.gm[gi];
+                const bool fold = m.ms && (m.lay[0] | m.lay[1]) == 0 && !m.ist;
+                S.gain[gi][c][b] = gain_of(q) * (fold ? 0.70710678118654752440f : 1.f);
             }
         }
     }
@@ -343,23 +347,26 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
         const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
         const int16_t *s0 = S.is_buf[gi * 2], *s1 = S.is_buf[gi * 2 + 1];
         float *X0 = S.X[gi][0], *X1 = S.X[gi][1];
-        const bool ms = m.ms != 0;
-        const float gs = ms ? isq2 : 1.f; // MS: (M +- S) / sqrt 2 with the factor folded into the band gains
+        // MS: (M +- S) / sqrt 2; stage_gains has folded the factor into this granule's band gains
         int v0[ITEMS], v1[ITEMS];
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) { v0[q] = s0[t64 + 64 * q]; v1[q] = s1[t64 + 64 * q]; }
+        auto lines = [&](auto ms_tag) {
 #pragma unroll
-        for (int q = 0; q < ITEMS; q++) {
-            const int b = (bq[q >> 2] >> (8 * (q & 3))) & 0xff;
-            const int m0 = abs(v0[q]), m1 = abs(v1[q]);
-            const float p0 = m0 < KF_POW_LUT ? S.pow43[m0] : __ldg(pow43 + m0);
-            const float p1 = m1 < KF_POW_LUT ? S.pow43[m1] : __ldg(pow43 + m1);
-            const float a = __int_as_float(__float_as_int(p0 * (g0[b] * gs)) | (v0[q] & 0x80000000));
-            const float c = __int_as_float(__float_as_int(p1 * (g1[b] * gs)) | (v1[q] & 0x80000000));
-            const int xp = xpad(t64 + 64 * q);
-            X0[xp] = ms ? a + c : a;
-            X1[xp] = ms ? a - c : c;
-        }
+            for (int q = 0; q < ITEMS; q++) {
+                const int b = (bq[q >> 2] >> (8 * (q & 3))) & 0xff;
+                const int m0 = abs(v0[q]), m1 = abs(v1[q]);
+                const float p0 = m0 < KF_POW_LUT ? S.pow43[m0] : __ldg(pow43 + m0);
+                const float p1 = m1 < KF_POW_LUT ? S.pow43[m1] : __ldg(pow43 + m1);
+                const float a = __int_as_float(__float_as_int(p0 * g0[b]) | (v0[q] & 0x80000000));
+                const float c = __int_as_float(__float_as_int(p1 * g1[b]) | (v1[q] & 0x80000000));
+                const int xp = xpad(t64 + 64 * q);
+                X0[xp] = decltype(ms_tag)::value ? a + c : a;
+                X1[xp] = decltype(ms_tag)::value ? a - c : c;
+            }
+        };
+        if (m.ms) lines(std::true_type{});
+        else lines(std::false_type{});
         return;
     }
     int v0[ITEMS], v1[ITEMS];
