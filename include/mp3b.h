@@ -180,6 +180,24 @@ int mp3b_stream_fetch_pcm(mp3b_stream *s, void *dst, size_t cap_samples, int whe
 /* Zero-copy view of the stream's decoded PCM (valid until the next decode call / close). */
 int mp3b_stream_pcm_device_ptr(const mp3b_stream *s, const void **ptr, size_t *nsamples);
 
+/* ---- sample-rate conversion of the decoded batch ----------------------------------------------
+ * The output step after the decode: every stream of the last batch (its gapless window when
+ * opts.gapless is set) is converted to out_rate by a polyphase Kaiser-windowed-sinc FIR (FP32
+ * accumulation, 32 zero crossings each side, pass band to 0.82 of the lower Nyquist frequency, about
+ * -90 dB from that Nyquist frequency up), into a second arena of the
+ * context's pcm_format, streams back to back.  Stream i then holds ceil(samples * out_rate / rate)
+ * frames at mp3b_batch_resampled_info's offset.  Asynchronous on the context's stream; the arena
+ * stays valid until the next decode or resample call. */
+int mp3b_batch_resample(mp3b_ctx *ctx, int out_rate);
+int mp3b_batch_resampled_info(const mp3b_ctx *ctx, int stream_index, int64_t *offset_elems, int64_t *samples);
+int mp3b_batch_resampled_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems);
+int mp3b_batch_fetch_resampled(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got);
+/* The FIR used for in_rate -> out_rate, for verification: out_rate / in_rate = L / M in lowest terms;
+ * taps[p * taps_per_phase + j] = h[p + j L], h centred at half * L with taps_per_phase = 2 half + 1.
+ * Returns MP3B_OK, MP3B_E_TRUNCATED (cap too small; *ncoef = needed) or MP3B_E_INVAL. */
+int mp3b_resample_filter(int in_rate, int out_rate, float *taps, size_t cap, size_t *ncoef, int *L, int *M,
+                         int *taps_per_phase);
+
 /* ---- host-side frame index of one stream (no GPU involved) ---------------------------------
  * The frame walk of the host indexer (MP3B_INDEX_HOST) as a utility: sync search past ID3v2 / junk,
  * header validation, stream consistency, tag frame.  frames[i] = {byte offset of the header, main-data

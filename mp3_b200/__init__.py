@@ -66,7 +66,8 @@ EXPORTS = [
     "mp3b_decode_packed", "mp3b_sync", "mp3b_flush", "mp3b_batch_stream_info", "mp3b_batch_tag_info", "mp3b_batch_pcm_device_ptr",
     "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_set_pcm_sink", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
-    "mp3b_debug_stage", "mp3b_index_stream_host",
+    "mp3b_debug_stage", "mp3b_index_stream_host", "mp3b_batch_resample", "mp3b_batch_resampled_info",
+    "mp3b_batch_resampled_device_ptr", "mp3b_batch_fetch_resampled", "mp3b_resample_filter",
 ]
 
 _lib = None
@@ -204,6 +205,25 @@ def index_stream_host(data):
     return arr, info, tag
 
 
+def resample_filter(in_rate, out_rate):
+    """The FIR the library uses for in_rate -> out_rate: (taps[L, taps_per_phase] float32, L, M)."""
+    L = load_library()
+    L.mp3b_resample_filter.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                       ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int),
+                                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    n, l, m, t = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = L.mp3b_resample_filter(in_rate, out_rate, None, 0, ctypes.byref(n), ctypes.byref(l), ctypes.byref(m),
+                                ctypes.byref(t))
+    if rc not in (0, -3):
+        raise Mp3bError(rc, L.mp3b_strerror(rc).decode())
+    taps = np.empty(n.value, np.float32)
+    rc = L.mp3b_resample_filter(in_rate, out_rate, taps.ctypes.data_as(ctypes.c_void_p), taps.size, ctypes.byref(n),
+                                ctypes.byref(l), ctypes.byref(m), ctypes.byref(t))
+    if rc != 0:
+        raise Mp3bError(rc, L.mp3b_strerror(rc).decode())
+    return taps.reshape(l.value, t.value), l.value, m.value
+
+
 class Decoder:
     """One context on one GPU (mp3b_ctx).  Not thread-safe; use one per GPU."""
 
@@ -323,6 +343,33 @@ class Decoder:
             arena = self.fetch_pcm()
         n = inf.samples * inf.channels
         return arena[inf.pcm_offset: inf.pcm_offset + n].reshape(inf.samples, max(inf.channels, 1))
+
+    def resample(self, out_rate):
+        """Convert every stream of the last batch to out_rate (async); see fetch_resampled()."""
+        self._ck(self.L.mp3b_batch_resample(self.ctx, int(out_rate)))
+
+    def fetch_resampled(self):
+        """(flat arena, [(offset_elems, samples)] per stream) of the resampled batch."""
+        L = self.L
+        L.mp3b_batch_resampled_device_ptr.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                      ctypes.POINTER(ctypes.c_uint64)]
+        L.mp3b_batch_fetch_resampled.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_uint64)]
+        L.mp3b_batch_resampled_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                                ctypes.POINTER(ctypes.c_int64)]
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._ck(L.mp3b_batch_resampled_device_ptr(self.ctx, ctypes.byref(p), ctypes.byref(n)))
+        out = np.empty(n.value, np.int16 if self.pcm_format == PCM_S16 else np.float32)
+        got = ctypes.c_uint64()
+        self._ck(L.mp3b_batch_fetch_resampled(self.ctx, out.ctypes.data_as(ctypes.c_void_p), out.size, HOST,
+                                              ctypes.byref(got)))
+        self.sync()
+        where = []
+        for i in range(self.nstreams):
+            o, c = ctypes.c_int64(), ctypes.c_int64()
+            self._ck(L.mp3b_batch_resampled_info(self.ctx, i, ctypes.byref(o), ctypes.byref(c)))
+            where.append((o.value, c.value))
+        return out, where
 
     def stats(self):
         st = Stats()

@@ -124,6 +124,11 @@ struct mp3b_ctx {
     const uint8_t *raw_dev = nullptr; // d_raw or the caller's device buffer
     std::vector<mp3b_stream_info> infos;
     std::vector<mp3b_tag_info> tags;
+    // resampled copy of the last batch
+    DevBuf d_rs, d_rs_jobs, d_rs_taps;
+    std::vector<L3ResampleJob> rs_jobs; // per stream (in_n = 0 for streams without audio)
+    uint64_t rs_elems = 0;
+    bool have_rs = false;
     uint64_t pcm_elems = 0;
     uint64_t arena_bytes = 0;
     uint32_t nstreams = 0, nframes = 0, ngran = 0, nunits = 0, ntiles = 0;
@@ -300,6 +305,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->have_batch = false;
+    ctx->have_rs = false;
     ctx->infos.assign((size_t)nstreams, mp3b_stream_info{});
     ctx->tags.assign((size_t)nstreams, mp3b_tag_info{});
     ctx->stats = mp3b_stats{};
@@ -705,7 +711,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -892,6 +898,120 @@ int mp3b_batch_tag_info(const mp3b_ctx *ctx, int i, mp3b_tag_info *info)
     if (!ctx->have_batch) return MP3B_E_STATE;
     if (i < 0 || (size_t)i >= ctx->tags.size()) return MP3B_E_INVAL;
     *info = ctx->tags[(size_t)i];
+    return MP3B_OK;
+}
+
+int mp3b_resample_filter(int in_rate, int out_rate, float *taps, size_t cap, size_t *ncoef, int *L, int *M,
+                         int *taps_per_phase)
+{
+    std::vector<float> hp;
+    int l = 0, m = 0, t = 0, h = 0;
+    if (in_rate == out_rate && in_rate > 0) { hp.assign(1, 1.f); l = m = t = 1; }
+    else if (!l3_resample_design(in_rate, out_rate, &hp, &l, &m, &t, &h)) return MP3B_E_INVAL;
+    if (ncoef) *ncoef = hp.size();
+    if (L) *L = l;
+    if (M) *M = m;
+    if (taps_per_phase) *taps_per_phase = t;
+    if (!taps || cap < hp.size()) return MP3B_E_TRUNCATED;
+    memcpy(taps, hp.data(), hp.size() * sizeof(float));
+    return MP3B_OK;
+}
+
+int mp3b_batch_resample(mp3b_ctx *ctx, int out_rate)
+{
+    if (!ctx || out_rate <= 0) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    const size_t ns = ctx->infos.size();
+    ctx->have_rs = false;
+    ctx->rs_jobs.assign(ns, L3ResampleJob{});
+    // output layout: streams back to back; one filter (and one launch) per distinct input rate
+    std::vector<int> rates;
+    uint64_t out_elems = 0;
+    for (size_t i = 0; i < ns; i++) {
+        const mp3b_stream_info &inf = ctx->infos[i];
+        L3ResampleJob &jb = ctx->rs_jobs[i];
+        if (!inf.frames || inf.sample_rate <= 0 || inf.samples <= 0) continue;
+        const int g = std::__gcd(inf.sample_rate, out_rate);
+        const int64_t L = out_rate / g, M = inf.sample_rate / g;
+        jb.in_off = inf.pcm_offset;
+        jb.in_n = inf.samples;
+        jb.out_off = (long long)out_elems;
+        jb.out_n = (inf.samples * L + M - 1) / M;
+        jb.channels = inf.channels;
+        out_elems += (uint64_t)jb.out_n * (uint64_t)inf.channels;
+        if (std::find(rates.begin(), rates.end(), inf.sample_rate) == rates.end()) rates.push_back(inf.sample_rate);
+    }
+    CK(ctx->d_rs.ensure(std::max<uint64_t>(out_elems * elem, 16)));
+    // the pageable staging vectors below are consumed by synchronous copies (cudaMemcpyAsync from pageable
+    // memory returns after the source has been read), so they may die at the end of each iteration
+    size_t job_bytes = 0, tap_bytes = 0;
+    std::vector<std::vector<L3ResampleJob>> jl(rates.size());
+    std::vector<std::vector<float>> taps(rates.size());
+    std::vector<int> pL(rates.size()), pM(rates.size()), pT(rates.size()), pH(rates.size());
+    for (size_t r = 0; r < rates.size(); r++) {
+        for (size_t i = 0; i < ns; i++)
+            if (ctx->rs_jobs[i].in_n && ctx->infos[i].sample_rate == rates[r]) jl[r].push_back(ctx->rs_jobs[i]);
+        if (rates[r] == out_rate) { taps[r].assign(1, 1.f); pL[r] = pM[r] = pT[r] = 1; pH[r] = 0; }
+        else if (!l3_resample_design(rates[r], out_rate, &taps[r], &pL[r], &pM[r], &pT[r], &pH[r])) {
+            ctx->err = "unsupported sample-rate pair";
+            return MP3B_E_UNSUPPORTED;
+        }
+        job_bytes += align_up(jl[r].size() * sizeof(L3ResampleJob), 256);
+        tap_bytes += align_up(taps[r].size() * sizeof(float), 256);
+    }
+    CK(ctx->d_rs_jobs.ensure(std::max<size_t>(job_bytes, 16)));
+    CK(ctx->d_rs_taps.ensure(std::max<size_t>(tap_bytes, 16)));
+    size_t jo = 0, to = 0;
+    for (size_t r = 0; r < rates.size(); r++) {
+        char *dj = ctx->d_rs_jobs.as<char>() + jo, *dt = ctx->d_rs_taps.as<char>() + to;
+        CK(cudaMemcpyAsync(dj, jl[r].data(), jl[r].size() * sizeof(L3ResampleJob), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dt, taps[r].data(), taps[r].size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        long long mx = 0;
+        for (const auto &j : jl[r]) mx = std::max(mx, j.out_n);
+        l3_launch_resample(ctx->pcm().p, ctx->d_rs.p, ctx->opts.pcm_format, reinterpret_cast<const L3ResampleJob *>(dj),
+                           (int)jl[r].size(), mx, reinterpret_cast<const float *>(dt), pL[r], pM[r], pT[r], pH[r], st);
+        jo += align_up(jl[r].size() * sizeof(L3ResampleJob), 256);
+        to += align_up(taps[r].size() * sizeof(float), 256);
+    }
+    CK(cudaGetLastError());
+    ctx->rs_elems = out_elems;
+    ctx->have_rs = true;
+    return MP3B_OK;
+}
+
+int mp3b_batch_resampled_info(const mp3b_ctx *ctx, int i, int64_t *offset_elems, int64_t *samples)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    if (!ctx->have_rs) return MP3B_E_STATE;
+    if (i < 0 || (size_t)i >= ctx->rs_jobs.size()) return MP3B_E_INVAL;
+    if (offset_elems) *offset_elems = ctx->rs_jobs[(size_t)i].out_off;
+    if (samples) *samples = ctx->rs_jobs[(size_t)i].out_n;
+    return MP3B_OK;
+}
+
+int mp3b_batch_resampled_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems)
+{
+    if (!ctx || !ptr) return MP3B_E_INVAL;
+    if (!ctx->have_rs) return MP3B_E_STATE;
+    *ptr = ctx->d_rs.p;
+    if (nelems) *nelems = ctx->rs_elems;
+    return MP3B_OK;
+}
+
+int mp3b_batch_fetch_resampled(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got)
+{
+    if (!ctx || (!dst && cap_elems)) return MP3B_E_INVAL;
+    if (!ctx->have_rs) return MP3B_E_STATE;
+    if (cap_elems < ctx->rs_elems) return MP3B_E_TRUNCATED;
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->rs_elems)
+        CK(cudaMemcpyAsync(dst, ctx->d_rs.p, ctx->rs_elems * elem,
+                           where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (got) *got = ctx->rs_elems;
     return MP3B_OK;
 }
 

@@ -75,4 +75,18 @@ void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran
                        const int16_t *is_in, const uint8_t *sf_in, const uint8_t *nzv_in, const L3DevTables &T,
                        void *pcm, int pcm_format, cudaStream_t st);
 
+
+/* Sample-rate conversion of decoded PCM (k_resample.cu).  One job per stream; offsets in elements
+ * of the arena's sample type, lengths in frames (samples per channel). */
+#ifdef __cplusplus
+#include <vector>
+struct L3ResampleJob {
+    long long in_off, in_n, out_off, out_n;
+    int channels, pad;
+};
+size_t l3_resample_design(int in_rate, int out_rate, std::vector<float> *hp, int *L, int *M, int *taps, int *half);
+void l3_launch_resample(const void *in, void *out, int pcm_format, const L3ResampleJob *jobs, int njobs,
+                        long long max_out_n, const float *hp, int L, int M, int taps, int half, cudaStream_t st);
+#endif
+
 #endif

@@ -1,0 +1,82 @@
+"""Sample-rate conversion (mp3b_batch_resample): the filter's properties (CPU) and the CUDA kernel
+against scipy's upfirdn -- an independent implementation of "zero-stuff by L, filter, keep every M-th
+sample" -- evaluated in float64 on the filter the library reports (GPU)."""
+import numpy as np
+import pytest
+
+
+def full_filter(taps, L):
+    T = taps.shape[1]
+    h = np.zeros(L * T)
+    for p in range(L):
+        h[p::L][:T] = taps[p]
+    return h  # h[p + j L] = taps[p][j]; centred at (T // 2) * L
+
+
+@pytest.mark.parametrize("rin,rout", [(44100, 48000), (48000, 44100), (44100, 22050), (8000, 48000), (22050, 44100),
+                                      (32000, 44100), (44100, 44100)])
+def test_filter_properties(rin, rout):
+    import mp3_b200
+    taps, L, M = mp3_b200.resample_filter(rin, rout)
+    g = np.gcd(rin, rout)
+    assert (L, M) == (rout // g, rin // g)
+    if rin == rout:
+        assert taps.shape == (1, 1) and taps[0, 0] == 1.0
+        return
+    T = taps.shape[1]
+    h = full_filter(taps.astype(np.float64), L)
+    D = (T // 2) * L
+    assert np.allclose(h[: D + 1], h[2 * D:: -1][: D + 1], atol=1e-7)      # linear phase, centre at D
+    assert abs(h.sum() / L - 1.0) < 1e-4                                    # unity gain at DC
+    n = 1 << 20
+    H = np.abs(np.fft.rfft(h, n)) / L
+    f = np.fft.rfftfreq(n)
+    ny = 0.5 / max(L, M)
+    assert np.abs(20 * np.log10(H[f < 0.8 * ny])).max() < 0.01             # flat pass band
+    assert 20 * np.log10(H[f >= ny].max()) < -85.0                          # nothing left to alias / image
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+@pytest.mark.parametrize("out_rate", [48000, 44100, 16000])
+def test_resample_matches_upfirdn(fmt, out_rate, synth_mod):
+    from scipy.signal import upfirdn
+    import mp3_b200 as m
+    cfgs = [dict(nframes=10, seed=1), dict(nframes=10, seed=2, mode=3, sample_rate=22050, bitrate_kbps=32),
+            dict(nframes=12, seed=3, sample_rate=8000, bitrate_kbps=16, mode=1), dict(nframes=6, seed=4, sample_rate=48000),
+            dict(nframes=8, seed=5, tag=2, tag_lame=1, enc_delay=576, enc_padding=1000)]
+    streams = [synth_mod.make_stream(**c) for c in cfgs] + [b"not an mp3 stream"]
+    with m.Decoder(device=0, pcm_format=m.PCM_F32 if fmt == "f32" else m.PCM_S16, gapless=True) as dec:
+        dec.decode_batch(streams)
+        arena = dec.fetch_pcm().copy()
+        dec.resample(out_rate)
+        out, where = dec.fetch_resampled()
+        assert where[-1][1] == 0
+        for i in range(len(cfgs)):
+            inf = dec.stream_info(i)
+            x = dec.stream_pcm(i, arena).astype(np.float64)
+            if fmt == "s16":
+                x /= 32768.0
+            taps, L, M = m.resample_filter(inf.sample_rate, out_rate)
+            T = taps.shape[1]
+            D = (T // 2) * L
+            nout = -(-inf.samples * L // M)
+            off, cnt = where[i]
+            assert cnt == nout
+            got = out[off: off + cnt * inf.channels].reshape(cnt, inf.channels).astype(np.float64)
+            if L == 1 and M == 1:
+                ref = x
+            else:
+                # y[n] = sum_i x[i] h[n M + D - i L]: upfirdn computes sum_i x[i] g[m M - i L]; shifting the
+                # filter by r = (-D) mod M puts n M + D on its output grid at m = n + (D + r) / M
+                r = (-D) % M
+                g = np.concatenate([np.zeros(r), full_filter(taps.astype(np.float64), L)])
+                k = (D + r) // M
+                ref = np.stack([upfirdn(g, x[:, c], up=L, down=M)[k: k + nout] for c in range(inf.channels)], axis=1)
+                if ref.shape[0] < nout:
+                    ref = np.pad(ref, ((0, nout - ref.shape[0]), (0, 0)))
+            if fmt == "f32":
+                assert np.abs(got - ref).max() < 2e-6 * max(1.0, np.abs(ref).max())
+            else:
+                want = np.clip(np.round(ref * 32768.0), -32768, 32767)
+                assert np.abs(got - want).max() <= 1
