@@ -198,6 +198,21 @@ int mp3b_batch_fetch_resampled(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int
 int mp3b_resample_filter(int in_rate, int out_rate, float *taps, size_t cap, size_t *ncoef, int *L, int *M,
                          int *taps_per_phase);
 
+/* ---- slow / fast playback of the decoded batch without pitch change -----------------------------
+ * Waveform-similarity overlap-add (WSOLA): every stream of the last batch (its gapless window when
+ * opts.gapless is set) is stretched to floor(samples * den / num) frames, speed = num / den (1/2 = half
+ * speed, the "slow listening" of the reference's README).  Segments of 2 * hop samples (hop = 512 / 256 /
+ * 128 by sample rate) are re-spaced and each is shifted by up to hop / 2 samples to where it best
+ * continues the previous one (exact integer cross-correlation of an 8-bit alignment signal), then
+ * cross-faded with a Hann window.  Result in a third arena of the context's pcm_format, streams back to
+ * back; asynchronous on the context's stream; valid until the next decode or stretch call. */
+int mp3b_batch_time_stretch(mp3b_ctx *ctx, int speed_num, int speed_den);
+int mp3b_batch_stretched_info(const mp3b_ctx *ctx, int stream_index, int64_t *offset_elems, int64_t *samples);
+int mp3b_batch_stretched_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems);
+int mp3b_batch_fetch_stretched(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got);
+/* The alignment offsets chosen for stream i (one per output segment of `hop` frames), for verification. */
+int mp3b_batch_stretch_offsets(mp3b_ctx *ctx, int stream_index, int32_t *dst, size_t cap, size_t *n, int *hop);
+
 /* ---- host-side frame index of one stream (no GPU involved) ---------------------------------
  * The frame walk of the host indexer (MP3B_INDEX_HOST) as a utility: sync search past ID3v2 / junk,
  * header validation, stream consistency, tag frame.  frames[i] = {byte offset of the header, main-data

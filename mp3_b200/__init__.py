@@ -68,6 +68,8 @@ EXPORTS = [
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
     "mp3b_debug_stage", "mp3b_index_stream_host", "mp3b_batch_resample", "mp3b_batch_resampled_info",
     "mp3b_batch_resampled_device_ptr", "mp3b_batch_fetch_resampled", "mp3b_resample_filter",
+    "mp3b_batch_time_stretch", "mp3b_batch_stretched_info", "mp3b_batch_stretched_device_ptr",
+    "mp3b_batch_fetch_stretched", "mp3b_batch_stretch_offsets",
 ]
 
 _lib = None
@@ -370,6 +372,48 @@ class Decoder:
             self._ck(L.mp3b_batch_resampled_info(self.ctx, i, ctypes.byref(o), ctypes.byref(c)))
             where.append((o.value, c.value))
         return out, where
+
+    def time_stretch(self, num, den):
+        """WSOLA time-scale modification of the last batch: speed = num / den (1, 2 = half speed); async."""
+        self._ck(self.L.mp3b_batch_time_stretch(self.ctx, int(num), int(den)))
+
+    def fetch_stretched(self):
+        """(flat arena, [(offset_elems, samples)] per stream) of the stretched batch."""
+        L = self.L
+        L.mp3b_batch_stretched_device_ptr.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                      ctypes.POINTER(ctypes.c_uint64)]
+        L.mp3b_batch_fetch_stretched.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_uint64)]
+        L.mp3b_batch_stretched_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                                ctypes.POINTER(ctypes.c_int64)]
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._ck(L.mp3b_batch_stretched_device_ptr(self.ctx, ctypes.byref(p), ctypes.byref(n)))
+        out = np.empty(n.value, np.int16 if self.pcm_format == PCM_S16 else np.float32)
+        got = ctypes.c_uint64()
+        self._ck(L.mp3b_batch_fetch_stretched(self.ctx, out.ctypes.data_as(ctypes.c_void_p), out.size, HOST,
+                                              ctypes.byref(got)))
+        self.sync()
+        where = []
+        for i in range(self.nstreams):
+            o, c = ctypes.c_int64(), ctypes.c_int64()
+            self._ck(L.mp3b_batch_stretched_info(self.ctx, i, ctypes.byref(o), ctypes.byref(c)))
+            where.append((o.value, c.value))
+        return out, where
+
+    def stretch_offsets(self, i):
+        """(alignment offsets chosen per output segment of stream i, hop)."""
+        L = self.L
+        L.mp3b_batch_stretch_offsets.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                 ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int)]
+        n, hop = ctypes.c_size_t(), ctypes.c_int()
+        rc = L.mp3b_batch_stretch_offsets(self.ctx, i, None, 0, ctypes.byref(n), ctypes.byref(hop))
+        if rc not in (0, -3):
+            self._ck(rc)
+        out = np.zeros(n.value, np.int32)
+        if n.value:
+            self._ck(L.mp3b_batch_stretch_offsets(self.ctx, i, out.ctypes.data_as(ctypes.c_void_p), out.size,
+                                                  ctypes.byref(n), ctypes.byref(hop)))
+        return out, hop.value
 
     def stats(self):
         st = Stats()

@@ -129,6 +129,12 @@ struct mp3b_ctx {
     std::vector<L3ResampleJob> rs_jobs; // per stream (in_n = 0 for streams without audio)
     uint64_t rs_elems = 0;
     bool have_rs = false;
+    // time-stretched copy of the last batch
+    DevBuf d_ts, d_ts_jobs, d_ts_off;
+    std::vector<L3StretchJob> ts_jobs;
+    uint64_t ts_elems = 0;
+    int ts_max_frames = 0;
+    bool have_ts = false;
     uint64_t pcm_elems = 0;
     uint64_t arena_bytes = 0;
     uint32_t nstreams = 0, nframes = 0, ngran = 0, nunits = 0, ntiles = 0;
@@ -306,6 +312,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     cudaStream_t st = ctx->stream;
     ctx->have_batch = false;
     ctx->have_rs = false;
+    ctx->have_ts = false;
     ctx->infos.assign((size_t)nstreams, mp3b_stream_info{});
     ctx->tags.assign((size_t)nstreams, mp3b_tag_info{});
     ctx->stats = mp3b_stats{};
@@ -711,7 +718,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -898,6 +905,101 @@ int mp3b_batch_tag_info(const mp3b_ctx *ctx, int i, mp3b_tag_info *info)
     if (!ctx->have_batch) return MP3B_E_STATE;
     if (i < 0 || (size_t)i >= ctx->tags.size()) return MP3B_E_INVAL;
     *info = ctx->tags[(size_t)i];
+    return MP3B_OK;
+}
+
+int mp3b_batch_time_stretch(mp3b_ctx *ctx, int num, int den)
+{
+    if (!ctx || num <= 0 || den <= 0 || num > 64 * den || den > 64 * num) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    const size_t ns = ctx->infos.size();
+    ctx->have_ts = false;
+    ctx->ts_jobs.assign(ns, L3StretchJob{});
+    std::vector<L3StretchJob> jl;
+    uint64_t out_elems = 0;
+    int64_t max_frames = 1;
+    for (size_t i = 0; i < ns; i++) {
+        const mp3b_stream_info &inf = ctx->infos[i];
+        L3StretchJob &jb = ctx->ts_jobs[i];
+        if (!inf.frames || inf.sample_rate <= 0 || inf.samples <= 0) continue;
+        jb.in_off = inf.pcm_offset;
+        jb.in_n = inf.samples;
+        jb.out_off = (long long)out_elems;
+        jb.out_n = inf.samples * den / num;
+        jb.channels = inf.channels;
+        jb.hop = l3_stretch_hop(inf.sample_rate);
+        out_elems += (uint64_t)jb.out_n * (uint64_t)inf.channels;
+        max_frames = std::max<int64_t>(max_frames, (jb.out_n + jb.hop - 1) / jb.hop);
+        jl.push_back(jb);
+    }
+    ctx->ts_max_frames = (int)max_frames;
+    CK(ctx->d_ts.ensure(std::max<uint64_t>(out_elems * elem, 16)));
+    CK(ctx->d_ts_jobs.ensure(std::max<size_t>(jl.size() * sizeof(L3StretchJob), 16)));
+    CK(ctx->d_ts_off.ensure(std::max<size_t>(jl.size() * (size_t)max_frames * sizeof(int), 16)));
+    if (!jl.empty()) {
+        CK(cudaMemcpyAsync(ctx->d_ts_jobs.p, jl.data(), jl.size() * sizeof(L3StretchJob), cudaMemcpyHostToDevice, st));
+        l3_launch_stretch(ctx->pcm().p, ctx->d_ts.p, ctx->opts.pcm_format, ctx->d_ts_jobs.as<L3StretchJob>(),
+                          (int)jl.size(), num, den, ctx->d_ts_off.as<int>(), (int)max_frames, st);
+    }
+    CK(cudaGetLastError());
+    ctx->ts_elems = out_elems;
+    ctx->have_ts = true;
+    return MP3B_OK;
+}
+
+int mp3b_batch_stretched_info(const mp3b_ctx *ctx, int i, int64_t *offset_elems, int64_t *samples)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    if (!ctx->have_ts) return MP3B_E_STATE;
+    if (i < 0 || (size_t)i >= ctx->ts_jobs.size()) return MP3B_E_INVAL;
+    if (offset_elems) *offset_elems = ctx->ts_jobs[(size_t)i].out_off;
+    if (samples) *samples = ctx->ts_jobs[(size_t)i].out_n;
+    return MP3B_OK;
+}
+
+int mp3b_batch_stretched_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems)
+{
+    if (!ctx || !ptr) return MP3B_E_INVAL;
+    if (!ctx->have_ts) return MP3B_E_STATE;
+    *ptr = ctx->d_ts.p;
+    if (nelems) *nelems = ctx->ts_elems;
+    return MP3B_OK;
+}
+
+int mp3b_batch_fetch_stretched(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got)
+{
+    if (!ctx || (!dst && cap_elems)) return MP3B_E_INVAL;
+    if (!ctx->have_ts) return MP3B_E_STATE;
+    if (cap_elems < ctx->ts_elems) return MP3B_E_TRUNCATED;
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->ts_elems)
+        CK(cudaMemcpyAsync(dst, ctx->d_ts.p, ctx->ts_elems * elem,
+                           where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (got) *got = ctx->ts_elems;
+    return MP3B_OK;
+}
+
+int mp3b_batch_stretch_offsets(mp3b_ctx *ctx, int i, int32_t *dst, size_t cap, size_t *n, int *hop)
+{
+    if (!ctx || !n) return MP3B_E_INVAL;
+    if (!ctx->have_ts) return MP3B_E_STATE;
+    if (i < 0 || (size_t)i >= ctx->ts_jobs.size()) return MP3B_E_INVAL;
+    const L3StretchJob &jb = ctx->ts_jobs[(size_t)i];
+    size_t row = 0; // jobs were compacted over streams with audio
+    for (int k = 0; k < i; k++) row += ctx->ts_jobs[(size_t)k].in_n ? 1 : 0;
+    *n = jb.in_n ? (size_t)((jb.out_n + jb.hop - 1) / jb.hop) : 0;
+    if (hop) *hop = jb.hop;
+    if (*n > cap || (!dst && *n)) return MP3B_E_TRUNCATED;
+    CK(cudaSetDevice(ctx->device));
+    if (*n) {
+        CK(cudaMemcpyAsync(dst, ctx->d_ts_off.as<int>() + row * (size_t)ctx->ts_max_frames, *n * sizeof(int),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return MP3B_OK;
 }
 

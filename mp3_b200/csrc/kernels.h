@@ -84,6 +84,14 @@ struct L3ResampleJob {
     long long in_off, in_n, out_off, out_n;
     int channels, pad;
 };
+/* Time-scale modification (k_stretch.cu).  One job (and one CTA) per stream. */
+struct L3StretchJob {
+    long long in_off, in_n, out_off, out_n;
+    int channels, hop;
+};
+int l3_stretch_hop(int sample_rate);
+void l3_launch_stretch(const void *in, void *out, int pcm_format, const L3StretchJob *jobs, int njobs, int num, int den,
+                       int *offsets_out, int max_frames, cudaStream_t st);
 size_t l3_resample_design(int in_rate, int out_rate, std::vector<float> *hp, int *L, int *M, int *taps, int *half);
 void l3_launch_resample(const void *in, void *out, int pcm_format, const L3ResampleJob *jobs, int njobs,
                         long long max_out_n, const float *hp, int L, int M, int taps, int half, cudaStream_t st);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Time mp3b_batch_resample on the cfg2 batch (1,024 x 10 s, 44.1 -> 48 kHz): CUDA events on the
-context's stream."""
+"""Time the output-side operators on the cfg2 batch (1,024 x 10 s stereo s16): mp3b_batch_resample
+(44.1 -> 48 / 22.05 kHz) and mp3b_batch_time_stretch (half speed); CUDA events on the context's stream."""
 import os
 import sys
 
@@ -28,3 +28,16 @@ for rate in (48000, 22050):
     ms = e0.elapsed_time(e1) / 5
     audio = 1024 * 383 * 1152 / 44100.0
     print("44100 -> %d: %.3f ms per batch, %.2e x realtime" % (rate, ms, audio / (ms * 1e-3)))
+
+for num, den in ((1, 2), (3, 4)):
+    dec.time_stretch(num, den)
+    dec.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(3):
+        dec.time_stretch(num, den)
+    e1.record(st)
+    dec.sync()
+    ms = e0.elapsed_time(e1) / 3
+    audio = 1024 * 383 * 1152 / 44100.0
+    print("stretch speed %d/%d: %.3f ms per batch, %.2e x realtime (of input audio)" % (num, den, ms, audio / (ms * 1e-3)))
