@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "../csrc/iso_tables.h"
+#include "../csrc/iso_tables_l2.h"
 
 typedef struct {
     uint64_t seed;
@@ -46,6 +47,8 @@ typedef struct {
                               3 = "VBRI" (Fraunhofer) */
     int32_t tag_lame;      /* 1 = LAME extension after the Xing/Info fields (encoder delay / padding) */
     int32_t enc_delay, enc_padding; /* 0..4095 each */
+    int32_t layer;         /* 0 / 3 = Layer III; 2 = Layer II (bitrate_kbps from the Layer II table, CBR;
+                              mode, mode_ext_mask, crc, level_*_db, fill_*_pct apply) */
 } l3gen_cfg;
 
 /* ------------------------------------------------------------------ rng */
@@ -338,7 +341,7 @@ static int bitrate_index(int lsf, int kbps)
 /* Upper bound on the stream size for a config (for caller allocation). */
 size_t l3gen_max_bytes(const l3gen_cfg *c)
 {
-    int lsf = c->sample_rate < 32000;
+    int lsf = c->sample_rate < 32000 && c->layer != 2;
     int kb = c->vbr_max_kbps > 0 ? c->vbr_max_kbps : c->bitrate_kbps;
     size_t fl = (size_t)(lsf ? 72 : 144) * kb * 1000 / c->sample_rate + 1;
     return fl * (size_t)c->nframes + 16 + (c->tag ? 1500 : 0);
@@ -394,9 +397,124 @@ static size_t put_tag_frame(const l3gen_cfg *c, int row, int lsf, int nch, int s
     return (size_t)flen;
 }
 
+/* Layer II: random bit allocation (thinned until the frame fits), random scfsi / scalefactors / sample
+ * codes.  Returns bytes written, or 0 on a bad config / small buffer. */
+static size_t l2gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
+{
+    rng_t rng;
+    rng.s = c->seed * 0x2545F4914F6CDD1Dull + 0x7654321;
+    int row = -1;
+    for (int i = 0; i < 9; i++)
+        if ((int)l3_sample_rate[i] == c->sample_rate) row = i;
+    if (row < 0 || c->nframes <= 0) return 0;
+    const int lsf = row >= 3, nch = c->mode == 3 ? 1 : 2;
+    int bri = 0;
+    for (int i = 1; i < 15; i++)
+        if (l2_bitrate_kbps[lsf][i] == c->bitrate_kbps) bri = i;
+    if (!bri) return 0;
+    const int tbl = l2_select_table(lsf, c->sample_rate, c->bitrate_kbps, nch), sblimit = l2_sblimit[tbl];
+    size_t o = 0;
+    long pad_rest = 0;
+    for (int f = 0; f < c->nframes; f++) {
+        int pad = 0;
+        long num = 144L * c->bitrate_kbps * 1000;
+        pad_rest -= num % c->sample_rate;
+        if (pad_rest < 0) { pad = 1; pad_rest += c->sample_rate; }
+        const int flen = (int)(num / c->sample_rate) + pad;
+        if (o + (size_t)flen > cap) return 0;
+        uint8_t *fr = out + o;
+        memset(fr, 0, (size_t)flen);
+        int mode_ext = 0;
+        if (c->mode == 1) mode_ext = rndi(&rng, 0, 3);
+        fr[0] = 0xFF;
+        fr[1] = (uint8_t)(0xE0 | ((row >= 6 ? 0 : lsf ? 2 : 3) << 3) | (2 << 1) | (c->crc ? 0 : 1));
+        fr[2] = (uint8_t)((bri << 4) | ((row % 3) << 2) | (pad << 1));
+        fr[3] = (uint8_t)((c->mode << 6) | (mode_ext << 4));
+        int bound = c->mode == 1 ? (mode_ext + 1) * 4 : sblimit;
+        if (bound > sblimit || nch == 1) bound = sblimit;
+        const int hdr_bits = 32 + (c->crc ? 16 : 0);
+        const long budget = ((long)flen * 8 - hdr_bits) * rndi(&rng, c->fill_lo_pct, c->fill_hi_pct) / 100;
+        int alloc[2][32];
+        memset(alloc, 0, sizeof alloc);
+        for (int s = 0; s < sblimit; s++) {
+            const uint8_t *rw = l2_rows[l2_row_of_sb[tbl][s]];
+            int hi = (1 << rw[0]) - 1;
+            for (int ch = 0; ch < (s < bound ? nch : 1); ch++) {
+                int a = rndi(&rng, 0, 9) < 2 ? 0 : rndi(&rng, 1, hi);
+                if (rndi(&rng, 0, 9) < 6 && a > 4) a = rndi(&rng, 1, 4); /* mostly coarse classes, sometimes the finest */
+                alloc[ch][s] = a;
+            }
+            if (s >= bound) alloc[1][s] = alloc[0][s];
+        }
+        for (;;) { /* thin the allocation until the frame fits its budget */
+            long bits = 0;
+            for (int s = 0; s < sblimit; s++) {
+                const uint8_t *rw = l2_rows[l2_row_of_sb[tbl][s]];
+                bits += rw[0] * (s < bound ? nch : 1);
+                for (int ch = 0; ch < nch; ch++)
+                    if (alloc[ch][s]) bits += 2 + 18; /* scfsi + up to three scalefactors */
+                for (int ch = 0; ch < (s < bound ? nch : 1); ch++)
+                    if (alloc[ch][s]) {
+                        int q = rw[alloc[ch][s]], b = l2_quant_bits[q];
+                        bits += 12L * (b < 0 ? -b : 3 * b);
+                    }
+            }
+            if (bits <= budget) break;
+            int s = rndi(&rng, 0, sblimit - 1), ch = rndi(&rng, 0, nch - 1);
+            if (s >= bound) { alloc[0][s] = alloc[1][s] = alloc[0][s] > 1 ? alloc[0][s] - 1 : 0; }
+            else alloc[ch][s] = alloc[ch][s] > 1 ? alloc[ch][s] / 2 : 0;
+        }
+        bitw w = {fr, (size_t)flen * 8, (size_t)hdr_bits};
+        for (int s = 0; s < sblimit; s++) {
+            const uint8_t *rw = l2_rows[l2_row_of_sb[tbl][s]];
+            for (int ch = 0; ch < (s < bound ? nch : 1); ch++) putbits(&w, (unsigned)alloc[ch][s], rw[0]);
+        }
+        int scfsi[2][32];
+        for (int s = 0; s < sblimit; s++)
+            for (int ch = 0; ch < nch; ch++)
+                if (alloc[ch][s]) { scfsi[ch][s] = rndi(&rng, 0, 3); putbits(&w, (unsigned)scfsi[ch][s], 2); }
+        const size_t crc_end = w.pos;
+        /* scalefactor index: 2^(1 - i/3); level_lo_db .. level_hi_db below full scale, spread over the subbands */
+        const int i_lo = 3 + c->level_lo_db / 2 + 8, i_hi = 3 + c->level_hi_db / 2 + 8;
+        for (int s = 0; s < sblimit; s++)
+            for (int ch = 0; ch < nch; ch++) {
+                if (!alloc[ch][s]) continue;
+                int n = scfsi[ch][s] == 0 ? 3 : (scfsi[ch][s] == 2 ? 1 : 2);
+                for (int k = 0; k < n; k++) {
+                    int v = rndi(&rng, i_lo, i_hi < 62 ? i_hi : 62);
+                    if (rndi(&rng, 0, 99) == 0) v = rndi(&rng, 0, 62); /* the whole range now and then */
+                    putbits(&w, (unsigned)v, 6);
+                }
+            }
+        for (int gr = 0; gr < 12; gr++)
+            for (int s = 0; s < sblimit; s++) {
+                const uint8_t *rw = l2_rows[l2_row_of_sb[tbl][s]];
+                for (int ch = 0; ch < (s < bound ? nch : 1); ch++) {
+                    if (!alloc[ch][s]) continue;
+                    int q = rw[alloc[ch][s]], steps = l2_quant_steps[q], b = l2_quant_bits[q];
+                    unsigned code[3];
+                    for (int i = 0; i < 3; i++) code[i] = (unsigned)rndi(&rng, 0, steps - 1);
+                    if (b < 0) putbits(&w, code[0] + (unsigned)steps * (code[1] + (unsigned)steps * code[2]), -b);
+                    else
+                        for (int i = 0; i < 3; i++) putbits(&w, code[i], b);
+                }
+            }
+        if (c->crc) { /* 11172-3 2.4.3.1: header bits 16..31, bit allocation and scfsi */
+            unsigned crc = 0xffff;
+            crc = crc16_update(crc, fr + 2, 16);
+            crc = crc16_update(crc, fr + 6, (int)(crc_end - 48));
+            fr[4] = (uint8_t)(crc >> 8);
+            fr[5] = (uint8_t)crc;
+        }
+        o += (size_t)flen;
+    }
+    return o;
+}
+
 /* Generate one stream.  Returns bytes written, or 0 on a bad config / small buffer. */
 size_t l3gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
 {
+    if (c->layer == 2) return l2gen_stream(c, out, cap);
     gen_t g;
     memset(&g, 0, sizeof g);
     g.cfg = c;

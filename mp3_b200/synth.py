@@ -24,18 +24,20 @@ class Cfg(ctypes.Structure):
                 ("lsf_avoid_illegal_ispos", ctypes.c_int32), ("level_lo_db", ctypes.c_int32),
                 ("level_hi_db", ctypes.c_int32), ("only_table", ctypes.c_int32), ("scfsi_pct", ctypes.c_int32),
                 ("max_linbits_value", ctypes.c_int32), ("mixed_free", ctypes.c_int32), ("tag", ctypes.c_int32),
-                ("tag_lame", ctypes.c_int32), ("enc_delay", ctypes.c_int32), ("enc_padding", ctypes.c_int32)]
+                ("tag_lame", ctypes.c_int32), ("enc_delay", ctypes.c_int32), ("enc_padding", ctypes.c_int32),
+                ("layer", ctypes.c_int32)]
 
 
 DEFAULTS = dict(seed=20261018, sample_rate=44100, mode=0, bitrate_kbps=128, vbr_min_kbps=0, vbr_max_kbps=0,
                 nframes=383, blocks=0, mixed_pct=0, reservoir=1, fill_lo_pct=85, fill_hi_pct=100,
                 mode_ext_mask=15, crc=0, lsf_avoid_illegal_ispos=0, level_lo_db=14, level_hi_db=40,
                 only_table=0, scfsi_pct=25, max_linbits_value=0, mixed_free=0, tag=0, tag_lame=0, enc_delay=0,
-                enc_padding=0)
+                enc_padding=0, layer=0)
 
 
 def build(force=False):
-    deps = [SRC, os.path.join(HERE, "csrc", "iso_tables.h"), os.path.join(HERE, "csrc", "iso_tables_gen.h")]
+    deps = [SRC, os.path.join(HERE, "csrc", "iso_tables.h"), os.path.join(HERE, "csrc", "iso_tables_gen.h"),
+            os.path.join(HERE, "csrc", "iso_tables_l2.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     subprocess.check_call(["gcc", "-O2", "-Wall", "-shared", "-fPIC", "-o", LIB, SRC, "-lm"])

@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include "iso_tables.h"
+#include "iso_tables_l2.h"
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -105,6 +106,7 @@ typedef struct {
     int frame_len;
     int side_len;
     int bitrate_idx, padding;
+    int layer;      /* 3 = Layer III, 2 = Layer II */
 } l3o_hdr;
 
 typedef struct {
@@ -145,9 +147,10 @@ int l3o_parse_header(const uint8_t *p, l3o_hdr *h)
 {
     if (p[0] != 0xFF || (p[1] & 0xE0) != 0xE0) return 0;
     int ver = (p[1] >> 3) & 3;   /* 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5, 1 = reserved */
-    int layer = (p[1] >> 1) & 3; /* 1 = Layer III */
-    if (layer != 1) return 0;
+    int layer = (p[1] >> 1) & 3; /* 1 = Layer III, 2 = Layer II, 3 = Layer I (not decoded) */
+    if (layer != 1 && layer != 2) return 0;
     if (ver == 1) return 0;
+    h->layer = layer == 1 ? 3 : 2;
     h->lsf = (ver != 3); /* MPEG-2.5 = the LSF syntax at half the MPEG-2 sample rates (rows 6..8) */
     h->crc = !(p[1] & 1);
     h->bitrate_idx = p[2] >> 4;
@@ -158,8 +161,13 @@ int l3o_parse_header(const uint8_t *p, l3o_hdr *h)
     h->mode_ext = (p[3] >> 4) & 3;
     h->nch = h->mode == 3 ? 1 : 2;
     h->sr_row = sri + (ver == 3 ? 0 : ver == 2 ? 3 : 6);
-    int br = l3_bitrate_kbps[h->lsf][h->bitrate_idx] * 1000;
     int sr = (int)l3_sample_rate[h->sr_row];
+    if (h->layer == 2) { /* 11172-3 2.4.3.1: 1152 samples per frame at every sample rate, no side info */
+        h->frame_len = 144 * l2_bitrate_kbps[h->lsf][h->bitrate_idx] * 1000 / sr + h->padding;
+        h->side_len = 0;
+        return 1;
+    }
+    int br = l3_bitrate_kbps[h->lsf][h->bitrate_idx] * 1000;
     h->frame_len = (h->lsf ? 72 : 144) * br / sr + h->padding;
     h->side_len = h->lsf ? (h->nch == 1 ? 9 : 17) : (h->nch == 1 ? 17 : 32);
     return 1;
@@ -588,6 +596,75 @@ static size_t id3v2_skip(const uint8_t *buf, size_t len)
     return 0;
 }
 
+/* ---------------------------------------------------------------- Layer II (11172-3 2.4.1.6, 2.4.3.3)
+ * One frame = bit allocation, scfsi, scalefactors, then 12 groups of 3 samples for each of the
+ * sblimit subbands (joint stereo: subbands >= bound carry one set of codes for both channels).
+ * Requantisation (2.4.3.3.4): a code c of a class with `steps` levels is the fraction
+ * (2 c + 1 - steps) / steps, times the scalefactor 2^(1 - index / 3) of its third of the frame.
+ * Output: sb[ch][slot 0..35][subband 0..31]. */
+static void l2_decode_frame(const uint8_t *frame, const l3o_hdr *h, double sb[MAXCH][36][32])
+{
+    int nch = h->nch;
+    int kbps = l2_bitrate_kbps[h->lsf][h->bitrate_idx];
+    int tbl = l2_select_table(h->lsf, (int)l3_sample_rate[h->sr_row], kbps, nch);
+    int sblimit = l2_sblimit[tbl];
+    int bound = h->mode == 1 ? (h->mode_ext + 1) * 4 : sblimit;
+    if (bound > sblimit) bound = sblimit;
+    if (nch == 1) bound = sblimit;
+    bitr b = {frame, (size_t)h->frame_len * 8, (size_t)(4 + (h->crc ? 2 : 0)) * 8};
+    int alloc[MAXCH][32], scfsi[MAXCH][32], scf[MAXCH][32][3];
+    memset(alloc, 0, sizeof alloc);
+    memset(scf, 0, sizeof scf);
+    memset(sb, 0, sizeof(double) * MAXCH * 36 * 32);
+    for (int s = 0; s < sblimit; s++) {
+        const uint8_t *row = l2_rows[l2_row_of_sb[tbl][s]];
+        if (s < bound)
+            for (int ch = 0; ch < nch; ch++) alloc[ch][s] = (int)getbits(&b, row[0]);
+        else
+            alloc[0][s] = alloc[1][s] = (int)getbits(&b, row[0]);
+    }
+    for (int s = 0; s < sblimit; s++)
+        for (int ch = 0; ch < nch; ch++)
+            if (alloc[ch][s]) scfsi[ch][s] = (int)getbits(&b, 2);
+    for (int s = 0; s < sblimit; s++)
+        for (int ch = 0; ch < nch; ch++) {
+            if (!alloc[ch][s]) continue;
+            int *f = scf[ch][s];
+            switch (scfsi[ch][s]) {
+            case 0: f[0] = (int)getbits(&b, 6); f[1] = (int)getbits(&b, 6); f[2] = (int)getbits(&b, 6); break;
+            case 1: f[0] = f[1] = (int)getbits(&b, 6); f[2] = (int)getbits(&b, 6); break;
+            case 2: f[0] = f[1] = f[2] = (int)getbits(&b, 6); break;
+            default: f[0] = (int)getbits(&b, 6); f[1] = f[2] = (int)getbits(&b, 6); break;
+            }
+        }
+    for (int gr = 0; gr < 12; gr++)
+        for (int s = 0; s < sblimit; s++) {
+            int nc = s < bound ? nch : 1;
+            for (int ch = 0; ch < nc; ch++) {
+                int a = alloc[ch][s];
+                if (!a) continue;
+                const uint8_t *row = l2_rows[l2_row_of_sb[tbl][s]];
+                int q = row[a], steps = l2_quant_steps[q], bits = l2_quant_bits[q];
+                int code[3];
+                if (bits < 0) {
+                    unsigned c = getbits(&b, -bits);
+                    code[0] = (int)(c % (unsigned)steps);
+                    c /= (unsigned)steps;
+                    code[1] = (int)(c % (unsigned)steps);
+                    code[2] = (int)(c / (unsigned)steps);
+                } else
+                    for (int i = 0; i < 3; i++) code[i] = (int)getbits(&b, bits);
+                for (int i = 0; i < 3; i++) {
+                    double fr = (double)(2 * code[i] + 1 - steps) / (double)steps;
+                    for (int c2 = ch; c2 < (s < bound ? ch + 1 : nch); c2++) {
+                        int idx = scf[c2][s][gr >> 2];
+                        sb[c2][gr * 3 + i][s] = idx < 63 ? fr * pow(2.0, 1.0 - idx / 3.0) : 0.0;
+                    }
+                }
+            }
+        }
+}
+
 /* 11172-3 2.4.3.1 error check: CRC-16, generator polynomial x^16 + x^15 + x^2 + 1, shift register preset
  * to all ones, fed bit by bit (MSB first) with header bits 16..31 and the side information.
  * Off by default (the word is skipped); l3o_set_verify_crc(1) makes a mismatch conceal the frame. */
@@ -620,12 +697,13 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
     uint8_t *arena = (uint8_t *)malloc(len + 8);
     size_t arena_len = 0;
     l3o_hdr first;
+    memset(&first, 0, sizeof first);
     int have_first = 0;
     size_t p = id3v2_skip(buf, len);
     while (p + 4 <= len) {
         l3o_hdr h;
         if (!l3o_parse_header(buf + p, &h) ||
-            (have_first && (h.lsf != first.lsf || h.sr_row != first.sr_row || h.nch != first.nch)) ||
+            (have_first && (h.lsf != first.lsf || h.sr_row != first.sr_row || h.nch != first.nch || h.layer != first.layer)) ||
             h.frame_len < 4 + (h.crc ? 2 : 0) + h.side_len || p + (size_t)h.frame_len > len) {
             p++;
             continue;
@@ -635,7 +713,7 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
         fr[nfr].off = p;
         fr[nfr].h = h;
         fr[nfr].payload_off = arena_len;
-        size_t skip = 4 + (h.crc ? 2 : 0) + h.side_len;
+        size_t skip = h.layer == 2 ? (size_t)h.frame_len : (size_t)(4 + (h.crc ? 2 : 0) + h.side_len);
         memcpy(arena + arena_len, buf + p + skip, h.frame_len - skip);
         arena_len += h.frame_len - skip;
         nfr++;
@@ -643,7 +721,7 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
     }
     memset(arena + arena_len, 0, 8);
     if (!have_first) { free(fr); free(arena); return -1; }
-    int nch = first.nch, ngr = first.lsf ? 1 : 2;
+    int nch = first.nch, ngr = (first.lsf && first.layer == 3) ? 1 : 2;
     info->sample_rate = (int)l3_sample_rate[first.sr_row];
     info->channels = nch;
     info->lsf = first.lsf;
@@ -658,6 +736,31 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
     long unit = 0;
     for (size_t f = 0; f < nfr; f++) {
         const l3o_hdr *h = &fr[f].h;
+        if (h->layer == 2) { /* Layer II: subband samples straight from the frame, then the same synthesis */
+            static __thread double l2sb[MAXCH][36][32];
+            l2_decode_frame(buf + fr[f].off, h, l2sb);
+            for (int gr = 0; gr < 2; gr++) {
+                for (int ch = 0; ch < nch; ch++) {
+                    long u = unit + ch;
+                    if (dump_is) memset(dump_is + u * 576, 0, 576 * sizeof(int16_t));
+                    if (dump_sf) memset(dump_sf + u * 40, 0, 40);
+                    if (dump_xr) memset(dump_xr + u * 576, 0, 576 * sizeof(double));
+                    if (dump_sb) memcpy(dump_sb + u * 576, &l2sb[ch][gr * 18][0], 576 * sizeof(double));
+                    size_t base = (f * 2 + gr) * 576;
+                    for (int t = 0; t < 18; t++) {
+                        double out[32];
+                        synth_slot(&syn[ch], &l2sb[ch][gr * 18 + t][0], out);
+                        if (pcm)
+                            for (int j = 0; j < 32; j++) {
+                                size_t n = base + t * 32 + j;
+                                if (n < cap_samples) pcm[n * nch + ch] = out[j];
+                            }
+                    }
+                }
+                unit += nch;
+            }
+            continue;
+        }
         l3o_side si;
         parse_side(buf + fr[f].off + 4 + (h->crc ? 2 : 0), h, &si);
         int ok = (size_t)si.main_data_begin <= fr[f].payload_off;
@@ -766,6 +869,7 @@ int l3o_parse_tag(const uint8_t *buf, size_t len, l3o_tag *t)
         while (q + 4 <= len) {
             l3o_hdr g;
             if (!l3o_parse_header(buf + q, &g) || g.lsf != h.lsf || g.sr_row != h.sr_row || g.nch != h.nch ||
+                g.layer != h.layer ||
                 g.frame_len < 4 + (g.crc ? 2 : 0) + g.side_len || q + (size_t)g.frame_len > len) {
                 q++;
                 continue;
@@ -799,7 +903,7 @@ int l3o_parse_tag(const uint8_t *buf, size_t len, l3o_tag *t)
         t->bytes = be32(f + 46);
         t->frames = be32(f + 50);
     }
-    long spf = h.lsf ? 576 : 1152, total = nfr * spf;
+    long spf = (h.lsf && h.layer == 3) ? 576 : 1152, total = nfr * spf;
     long start = 0, count = total;
     if (t->kind) {
         start = spf;

@@ -37,6 +37,19 @@ FF = {
 for _t in [1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31]:
     FF["table_%02d" % _t] = dict(only_table=_t, nframes=6, seed=100 + _t, bitrate_kbps=320)
 
+# Layer II (MP2): one case per allocation table (3-B.2a..d, LSF), mono / stereo / joint with every bound
+L2 = {
+    "l2_44k_192_stereo": dict(layer=2, bitrate_kbps=192, nframes=10, seed=51),             # table 1 (30 subbands)
+    "l2_48k_128_joint": dict(layer=2, sample_rate=48000, bitrate_kbps=128, mode=1, nframes=10, seed=52),  # table 0
+    "l2_44k_64_mono": dict(layer=2, bitrate_kbps=64, mode=3, nframes=10, seed=53),           # table 0
+    "l2_32k_48_mono": dict(layer=2, sample_rate=32000, bitrate_kbps=48, mode=3, nframes=10, seed=54),    # table 3
+    "l2_44k_64_joint": dict(layer=2, bitrate_kbps=64, mode=1, nframes=10, seed=55),          # table 2 (8 subbands)
+    "l2_44k_384_dual_crc": dict(layer=2, bitrate_kbps=384, mode=2, crc=1, nframes=8, seed=56),
+    "l2_lsf24_64_joint": dict(layer=2, sample_rate=24000, bitrate_kbps=64, mode=1, nframes=10, seed=57),  # table 4
+    "l2_lsf16_32_mono": dict(layer=2, sample_rate=16000, bitrate_kbps=32, mode=3, nframes=10, seed=58),
+    "l2_sparse": dict(layer=2, bitrate_kbps=256, nframes=8, seed=59, fill_lo_pct=5, fill_hi_pct=40),
+}
+
 EXTRA = {
     "mixed_free_transitions": dict(blocks=1, mixed_pct=50, mixed_free=1, nframes=24, seed=31, mode=1),
     "lsf_intensity_full_range": dict(sample_rate=24000, bitrate_kbps=96, nframes=24, seed=32, blocks=1, mode=1),

@@ -78,12 +78,13 @@ def available():
     return load() is not None
 
 
-def decode_frames(frames, nch):
-    """Decode a list of `bytes` (one MP3 frame each, in stream order) with one mp3float context.
+def decode_frames(frames, nch, codec_name=b"mp3float"):
+    """Decode a list of `bytes` (one frame each, in stream order) with one decoder context
+    (mp3float for Layer III, mp2float for Layer II).
 
     Returns float32 array [nch, nsamples] (raw codec output, no delay trimming)."""
     avc, avu = load()
-    codec = avc.avcodec_find_decoder_by_name(b"mp3float")
+    codec = avc.avcodec_find_decoder_by_name(codec_name)
     assert codec
     ctx = avc.avcodec_alloc_context3(codec)
     assert avc.avcodec_open2(ctx, codec, None) == 0

@@ -32,3 +32,20 @@ def test_oracle_vs_mp3float(name, oracle_mod, synth_mod):
         dim = {1: 2, 2: 3, 3: 3, 5: 4, 6: 4, 7: 6, 8: 6, 9: 6, 10: 8, 11: 8, 12: 8, 13: 16, 15: 16}.get(t, 16)
         maxv = dim - 1 + ((1 << lin[t]) - 1 if lin[t] else 0)
         assert np.abs(d.is_).max() == maxv, "the largest value of the book was not exercised"
+
+
+@pytest.mark.parametrize("name", sorted(cases.L2))
+def test_oracle_layer2_vs_mp2float(name, oracle_mod, synth_mod):
+    """Layer II: the allocation / quantisation tables, grouping, scalefactors and joint-stereo bound of the
+    oracle against FFmpeg's mp2float on generated streams."""
+    s = synth_mod.make_stream(**cases.L2[name])
+    d = oracle_mod.decode(s, dumps=True)
+    frames = l3util.split_frames(s)
+    assert len(frames) == d.frames == cases.L2[name]["nframes"] and d.samples == 1152 * d.frames
+    pcm, per = ffmpeg_ref.decode_frames(frames, d.channels, b"mp2float")
+    assert all(p is not None for p in per)
+    assert pcm.shape == d.pcm.shape
+    assert np.abs(d.pcm).max() > 1e-3, "degenerate (silent) test stream"
+    rms, mx = l3util.iso_compliance(pcm, d.pcm)
+    scale = max(1.0, float(np.abs(d.pcm).max()))
+    assert rms < 5e-7 * scale and mx < 1e-5 * scale, (rms, mx)

@@ -71,3 +71,30 @@ def test_tables_match_libavcodec_rodata(oracle_mod):
     for r in range(9):
         edges = [L.l3o_sfb_short(r, k) for k in range(14)]
         assert bytes(b - a for a, b in zip(edges, edges[1:])) == blob[j + 13 * r: j + 13 * (r + 1)], r
+
+
+@pytest.mark.skipif(ffmpeg_ref.libavcodec_path() is None, reason="libavcodec not present")
+def test_layer2_tables_match_libavcodec_rodata():
+    """Layer II allocation rows / quantisation classes (mp3_b200/csrc/iso_tables_l2.h) against the arrays in
+    libavcodec's .rodata they were read from."""
+    import re
+    src = open(os.path.join(ROOT, "mp3_b200", "csrc", "iso_tables_l2.h")).read()
+    rows = {m.group(1): bytes(int(v) for v in m.group(2).split(","))
+            for m in re.finditer(r"#define L2_ROW_(\w) \{([^}]*)\}", src)}
+    blob = open(ffmpeg_ref.libavcodec_path(), "rb").read()
+    t_ab = rows["A"] * 3 + rows["B"] * 8 + rows["C"] * 12 + rows["D"] * 7      # 3-B.2a/b: 27 / 30 subbands
+    t_cd = rows["E"] * 2 + rows["F"] * 10                                      # 3-B.2c/d: 8 / 12 subbands
+    t_lsf = rows["G"] * 4 + rows["F"] * 7 + rows["H"] * 19                     # 13818-3 B.1: 30 subbands
+    for t in (t_ab, t_cd, t_lsf):
+        assert blob.find(t) >= 0
+    steps = [int(v) for v in re.search(r"l2_quant_steps\[17\] = \{([^}]*)\}", src).group(1).split(",")]
+    bits = [int(v) for v in re.search(r"l2_quant_bits\[17\] = \{([^}]*)\}", src).group(1).split(",")]
+    assert blob.find(struct.pack("<17i", *steps)) >= 0 and blob.find(struct.pack("<17i", *bits)) >= 0
+    assert blob.find(struct.pack("<5i", 27, 30, 8, 12, 30)) >= 0
+    # row ids per subband reproduce those concatenations
+    ids = re.search(r"l2_row_of_sb\[5\]\[30\] = \{(.*?)\};", src, re.S).group(1)
+    tabs = [[int(v) for v in r.split(",") if v.strip()] for r in re.findall(r"\{([^}]*)\}", ids)]
+    names = "ABCDEFGH"
+    for t, lim, want in ((0, 27, t_ab), (1, 30, t_ab), (2, 8, t_cd), (3, 12, t_cd), (4, 30, t_lsf)):
+        got = b"".join(rows[names[i]] for i in tabs[t][:lim])
+        assert want.startswith(got), t
