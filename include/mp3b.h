@@ -33,9 +33,9 @@ extern "C" {
 typedef enum mp3b_status {
     MP3B_OK = 0,
     MP3B_E_INVAL = -1,       /* bad argument */
-    MP3B_E_NOSYNC = -2,      /* no Layer III frame found in a stream */
+    MP3B_E_NOSYNC = -2,      /* no Layer II / III frame found in a stream */
     MP3B_E_TRUNCATED = -3,   /* destination buffer too small */
-    MP3B_E_UNSUPPORTED = -4, /* Layer I/II, free format */
+    MP3B_E_UNSUPPORTED = -4, /* Layer I, free format, unusable sample-rate pair */
     MP3B_E_CUDA = -5,        /* CUDA runtime error; mp3b_last_error() has the text */
     MP3B_E_NOMEM = -6,
     MP3B_E_STATE = -7        /* call order violated (e.g. fetch before decode) */

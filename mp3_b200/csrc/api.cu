@@ -119,6 +119,8 @@ struct mp3b_ctx {
     DevBuf &pcm() { return pcm_cur ? d_pcm2 : d_pcm; }
     const DevBuf &pcm() const { return pcm_cur ? d_pcm2 : d_pcm; }
     DevBuf d_is, d_sf, d_nzv, d_xr, d_imd, d_sb; // wave-sized intermediates
+    DevBuf d_sb2, d_tiles2;                      // Layer II: subband samples of its streams, synthesis tiles
+    PinBuf h_tiles2;
     PinBuf h_streams, h_frames, h_tiles, h_stage, h_counter;
 
     const uint8_t *raw_dev = nullptr; // d_raw or the caller's device buffer
@@ -201,6 +203,7 @@ int upload_tables(mp3b_ctx *ctx)
     l3_hybrid_init();
     l3_synth_init();
     l3_fused_init();
+    l3_layer2_init();
     CK(cudaGetLastError());
     return MP3B_OK;
 }
@@ -233,7 +236,7 @@ void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRe
         f.stream = sidx;
         out->push_back(f);
         n++;
-        payload += (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
+        payload += h.layer == 2 ? 0u : (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
         p += (uint32_t)h.frame_len;
         end_off = p;
     }
@@ -387,6 +390,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     const int G = l3_synth_tile_granules();
     uint64_t frames = 0, grans = 0, units = 0, payload = 0, ntiles = 0;
     std::vector<uint32_t> sgran((size_t)nstreams, 0), sunit((size_t)nstreams, 0), sskip((size_t)nstreams, 0);
+    std::vector<uint8_t> sl2((size_t)nstreams, 0); // Layer II streams: decoded by k_layer2 + the synthesis kernel
+    bool any_l2 = false;
     for (int i = 0; i < nstreams; i++) {
         L3StreamRec &r = hs[i];
         mp3b_stream_info &inf = ctx->infos[(size_t)i];
@@ -424,7 +429,9 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             sgran[(size_t)i] = (uint32_t)g;
             sunit[(size_t)i] = (uint32_t)(g * h.nch);
             sskip[(size_t)i] = skip * (uint32_t)h.ngr;
-            ntiles += (g + G - 1) / G;
+            sl2[(size_t)i] = h.layer == 2;
+            any_l2 = any_l2 || h.layer == 2;
+            if (h.layer != 2) ntiles += (g + G - 1) / G;
             grans += g;
             units += g * h.nch;
             payload = align_up(payload + r.payload_len, 16);
@@ -449,7 +456,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         ntiles = 0;
         for (int i = 0; i < nstreams; i++) {
             uint64_t g = sgran[(size_t)i] - sskip[(size_t)i];
-            ntiles += (g + GF - 1) / GF;
+            if (!sl2[(size_t)i]) ntiles += (g + GF - 1) / GF;
         }
         ctx->ntiles = (uint32_t)ntiles;
     }
@@ -462,7 +469,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         for (int i = 0; i < nstreams; i++) {
             const L3StreamRec &r = hs[i];
             tile_start[(size_t)i] = k;
-            if (!r.nframes) continue;
+            if (!r.nframes || sl2[(size_t)i]) continue;
             const uint32_t g = sgran[(size_t)i];
             if (fused)
                 for (uint32_t a = sskip[(size_t)i]; a < g; a += GF)
@@ -620,6 +627,45 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         launches += 5;
         if (int rc = wave_done()) return rc;
     }
+    // ---- Layer II streams: frames -> subband samples -> the same polyphase synthesis
+    if (any_l2) {
+        uint64_t u_min = ~0ull, u_max = 0, nt2 = 0;
+        for (int i = 0; i < nstreams; i++)
+            if (sl2[(size_t)i]) {
+                u_min = std::min<uint64_t>(u_min, hs[i].unit_base);
+                u_max = std::max<uint64_t>(u_max, (uint64_t)hs[i].unit_base + sunit[(size_t)i]);
+                nt2 += (sgran[(size_t)i] - sskip[(size_t)i] + G - 1) / G;
+            }
+        CK(ctx->d_sb2.ensure(std::max<uint64_t>((u_max - u_min) * 576 * sizeof(float), 16)));
+        CK(ctx->h_tiles2.ensure(sizeof(uint2) * std::max<uint64_t>(nt2, 1)));
+        CK(ctx->d_tiles2.ensure(sizeof(uint2) * std::max<uint64_t>(nt2, 1)));
+        CK(cudaStreamSynchronize(st)); // h_tiles2 may still feed the previous call's upload (Layer II batches are rare)
+        uint2 *t2 = ctx->h_tiles2.as<uint2>();
+        uint64_t k = 0;
+        for (int i = 0; i < nstreams; i++)
+            if (sl2[(size_t)i])
+                for (uint32_t a = sskip[(size_t)i]; a < sgran[(size_t)i]; a += (uint32_t)G)
+                    t2[k++] = make_uint2(hs[i].gran_base + a, std::min<uint32_t>((uint32_t)G, sgran[(size_t)i] - a));
+        float *sb2 = ctx->d_sb2.as<float>() - (size_t)u_min * 576;
+        l3_launch_layer2(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
+        if (nt2) {
+            CK(cudaMemcpyAsync(ctx->d_tiles2.p, t2, sizeof(uint2) * nt2, cudaMemcpyHostToDevice, st));
+            l3_launch_synth(ctx->d_tiles2.as<uint2>(), (uint32_t)nt2, dg, sb2, pcm_dev, ctx->opts.pcm_format, st);
+        }
+        launches += 2;
+        if (sink) { // the waves above did not cover these streams' PCM: one more copy, whole ranges
+            while (ctx->wave_ev.size() <= waves.size()) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->wave_ev.push_back(e);
+            }
+            CK(cudaEventRecord(ctx->wave_ev[waves.size()], st));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->wave_ev[waves.size()], 0));
+            const size_t lo = (size_t)u_min * 576 * elem, n = (size_t)(u_max - u_min) * 576 * elem;
+            CK(cudaMemcpyAsync(static_cast<char *>(ctx->sink) + lo, static_cast<char *>(pcm_dev) + lo, n,
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
     if (sink) CK(cudaEventRecord(ctx->pcm_free[ctx->pcm_cur], ctx->copy_stream));
     l3_launch_publish(ctx->d_counter.p, ctx->h_counter.p, 4, st);
     launches++;
@@ -718,10 +764,10 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
-    for (PinBuf *b : {&ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
+    for (PinBuf *b : {&ctx->h_tiles2, &ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
                       &ctx->h_frames_out})
         b->release();
     for (auto &e : ctx->ev)
@@ -1182,7 +1228,9 @@ static int finalize_stream_batch(mp3b_ctx *ctx)
             if (!s->first_hdr) s->first_hdr = r.first_hdr;
             L3Hdr h;
             l3_parse_hdr(r.first_hdr, &h);
-            const uint32_t nfr = r.nframes, W = h.lsf ? 2u : 1u, need = h.lsf ? 255u : 511u;
+            // W frames = the two granules the back end replays; `need` = the reach of main_data_begin
+            // (Layer II frames are self-contained)
+            const uint32_t nfr = r.nframes, W = h.ngr == 1 ? 2u : 1u, need = h.layer == 2 ? 0u : (h.lsf ? 255u : 511u);
             const L3FrameRec *f = fr + r.frame_base;
             const uint32_t wf = nfr > W ? nfr - W : 0; // first frame the back end will replay
             uint32_t idx = wf;

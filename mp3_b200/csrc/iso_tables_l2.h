@@ -12,6 +12,12 @@
 
 #include <stdint.h>
 
+#if defined(__CUDACC__)
+#define L2_HD __host__ __device__ __forceinline__
+#else
+#define L2_HD static inline
+#endif
+
 /* bitrate_index -> kbit/s, Layer II.  [0] = MPEG-1, [1] = MPEG-2 LSF / 2.5. */
 static const uint16_t l2_bitrate_kbps[2][16] = {
     {0, 32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 0},
@@ -48,7 +54,9 @@ static const uint8_t l2_row_of_sb[5][30] = {
 
 /* 11172-3 2.4.2.3 / 2.4.3.3: which allocation table a frame uses (sample rate in Hz, total bitrate in
  * kbit/s, channels); LSF and MPEG-2.5 always use table 4. */
-static inline int l2_select_table(int lsf, int sample_rate, int kbps, int nch)
+L2_HD int l2_sblimit_of(int t) { return t == 0 ? 27 : (t == 2 ? 8 : (t == 3 ? 12 : 30)); }
+
+L2_HD int l2_select_table(int lsf, int sample_rate, int kbps, int nch)
 {
     if (lsf) return 4;
     const int per_ch = kbps / nch;

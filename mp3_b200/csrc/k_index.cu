@@ -41,6 +41,7 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     // the length is the previous base length plus this frame's padding bit -- no header arithmetic.
     const uint32_t GEOM = 0xFFFFFCC0u;
     uint32_t prev_w = 0, base_len = 0, overhead = 0;
+    bool l2 = false; // Layer II frames carry no main data for the arena
     while (p + 4 <= len) {
         L3Hdr h;
         uint32_t w = l3_load_be32(buf + p), flen;
@@ -62,6 +63,7 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
             prev_w = w;
             base_len = flen - ((w >> 9) & 1u);
             overhead = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len;
+            l2 = h.layer == 2;
             if (n == 0) {
                 first = first ? first : w;
                 first_off = p;
@@ -78,7 +80,7 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
         f.stream = (uint32_t)s;
         out[n] = f;
         n++;
-        payload += flen - overhead;
+        payload += l2 ? 0u : flen - overhead;
         p += flen;
         end_off = p;
     }
@@ -184,6 +186,24 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
     L3Hdr h;
     l3_parse_hdr(fr.hdr, &h);
     const uint32_t fi = f - sr.frame_base; /* frame index inside its stream */
+    if (h.layer == 2) {
+        // Layer II: no side info; its units exist (two granules x channels per frame, the PCM layout is the
+        // same) but stay invalid for the Huffman / back-end kernels: k_layer2 + the synthesis kernel fill them
+        const uint32_t u0 = sr.unit_base + fi * (uint32_t)(2 * h.nch), g0 = sr.gran_base + fi * 2u;
+        L3UnitDesc d;
+        memset(&d, 0, sizeof d);
+        d.hdr = (uint8_t)(L3H_LSF * 0 | (h.sr_row << L3H_SR_SHIFT) | (h.nch == 2 ? L3H_STEREO : 0) | (h.lsf ? L3H_LSF : 0));
+        d.stream = fr.stream;
+        for (int gr = 0; gr < 2; gr++) {
+            for (int ch = 0; ch < h.nch; ch++) {
+                d.pos = (uint8_t)((gr ? L3P_GR : 0) | (ch ? L3P_CH : 0) | ((fi == 0 && gr == 0) ? L3P_FIRST : 0));
+                units[u0 + gr * h.nch + ch] = d;
+            }
+            gran_unit0[g0 + gr] = (u0 + (uint32_t)(gr * h.nch)) | (h.nch == 2 ? L3G_STEREO : 0u) |
+                                  ((fi == 0 && gr == 0) ? L3G_FIRST : 0u);
+        }
+        return;
+    }
     const uint16_t *sfb_long = sfb_long_all + h.sr_row * 23;
     __shared__ uint32_t s_side[SP_THREADS][SP_STRIDE];
     SideBits b;
@@ -309,7 +329,7 @@ k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ 
             L3Hdr h;
             l3_parse_hdr(fr.hdr, &h);
             const uint32_t skip = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len;
-            n = (uint32_t)h.frame_len - skip;
+            n = h.layer == 2 ? 0u : (uint32_t)h.frame_len - skip;
             s_src[threadIdx.x] = raw + sr.raw_off + fr.rel_off + skip;
             s_dst[threadIdx.x] = arena + sr.payload_base + fr.payload_off;
         }

@@ -1,0 +1,182 @@
+// k_layer2.cu -- Layer II (MP2) frames -> subband samples (11172-3 2.4.1.6 / 2.4.3.3; SURVEY.md 8(f)
+// rank 4).  Layer II has no Huffman coding, no bit reservoir and no hybrid filter bank: a frame is bit
+// allocation, scfsi, scalefactors and 12 x 3 samples per subband, and its 36 time slots of 32 subband
+// samples go straight into the same polyphase synthesis as Layer III (k_synth.cu) -- a frame is two
+// "granules" of 18 slots, so the unit / PCM layout of the batch is unchanged.
+//
+// Mapping: one warp per frame, lane = subband.  Every field's position is a prefix sum of per-subband
+// bit counts, so the three header sections and the sample section are located with warp scans and each
+// lane reads its own bits; the frame's bytes are staged in shared memory first (coalesced).
+// Checked against oracle/l3_oracle.c::l2_decode_frame (itself pinned by FFmpeg's mp2float).
+// No reference code exists for this stage (/root/reference/README.md:1-84).
+#include <math.h>
+
+#include "iso_tables_l2.h"
+#include "kernels.h"
+
+namespace {
+
+constexpr int L2_WARPS = 4;
+constexpr int L2_MAX_FRAME = 1732; // 384 kbit/s at 32 kHz: 1728 + padding
+
+__constant__ uint8_t c_l2_rows[8][16];
+__constant__ uint8_t c_l2_row_of_sb[5][30];
+__constant__ int32_t c_l2_steps[17];
+__constant__ int8_t c_l2_bits[17];
+__constant__ float c_l2_scf[64]; // 2^(1 - i / 3); index 63 is not a scalefactor: 0
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total)
+{
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    *total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
+// n (0..16) bits at bit position `pos` of the staged frame (bytes past the frame read as zero)
+__device__ __forceinline__ uint32_t l2_bits(const uint8_t *f, uint32_t pos, int n)
+{
+    const uint32_t b = pos >> 3;
+    const uint32_t w = ((uint32_t)f[b] << 24) | ((uint32_t)f[b + 1] << 16) | ((uint32_t)f[b + 2] << 8) | f[b + 3];
+    return n ? (w << (pos & 7)) >> (32 - n) : 0u;
+}
+
+__global__ void __launch_bounds__(L2_WARPS * 32)
+k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams, const L3FrameRec *__restrict__ frames,
+         uint32_t nframes, float *__restrict__ sb_out)
+{
+    __shared__ __align__(4) uint8_t s_frame[L2_WARPS][L2_MAX_FRAME + 12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * L2_WARPS + warp;
+    if (f >= nframes) return;
+    const L3FrameRec fr = frames[f];
+    L3Hdr h;
+    if (!l3_parse_hdr(fr.hdr, &h) || h.layer != 2) return;
+    const L3StreamRec sr = streams[fr.stream];
+    const uint8_t *src = raw + sr.raw_off + fr.rel_off;
+    uint8_t *fb = s_frame[warp];
+    const int flen = min(h.frame_len, L2_MAX_FRAME);
+    for (int i = lane; i < flen + 8; i += 32) fb[i] = i < flen ? src[i] : (uint8_t)0;
+    __syncwarp();
+
+    const int nch = h.nch;
+    const int tbl = l2_select_table(h.lsf, l3_sr_hz(h.sr_row), h.kbps, nch);
+    const int sblimit = l2_sblimit_of(tbl);
+    int bound = h.mode == 1 ? (h.mode_ext + 1) * 4 : sblimit;
+    if (bound > sblimit || nch == 1) bound = sblimit;
+    const bool on = lane < sblimit;
+    const bool sep = lane < bound;                 // this subband carries separate codes per channel
+    const int ncode = on ? (sep ? nch : 1) : 0;     // code sets of this subband
+    const uint8_t *row = c_l2_rows[on ? c_l2_row_of_sb[tbl][lane] : 0];
+    const int nbal = on ? row[0] : 0;
+    uint32_t pos = (uint32_t)(4 + (h.crc ? 2 : 0)) * 8;
+    int tot;
+    // ---- bit allocation
+    int off = warp_excl_scan(nbal * ncode, lane, &tot);
+    int alloc[2] = {0, 0};
+    if (on) {
+        alloc[0] = (int)l2_bits(fb, pos + off, nbal);
+        alloc[1] = nch == 2 ? (sep ? (int)l2_bits(fb, pos + off + nbal, nbal) : alloc[0]) : 0;
+    }
+    pos += (uint32_t)tot;
+    // ---- scfsi: 2 bits per (subband, channel) that has samples
+    const int na = (alloc[0] ? 1 : 0) + (alloc[1] ? 1 : 0);
+    off = warp_excl_scan(2 * na, lane, &tot);
+    int scfsi[2] = {0, 0};
+    {
+        uint32_t p = pos + off;
+        for (int ch = 0; ch < nch; ch++)
+            if (alloc[ch]) { scfsi[ch] = (int)l2_bits(fb, p, 2); p += 2; }
+    }
+    pos += (uint32_t)tot;
+    // ---- scalefactors: 3 / 2 / 1 / 2 indices of 6 bits by scfsi
+    int nsf[2];
+    for (int ch = 0; ch < 2; ch++) nsf[ch] = alloc[ch] ? (scfsi[ch] == 0 ? 3 : (scfsi[ch] == 2 ? 1 : 2)) : 0;
+    off = warp_excl_scan(6 * (nsf[0] + nsf[1]), lane, &tot);
+    float scf[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    {
+        uint32_t p = pos + off;
+        for (int ch = 0; ch < nch; ch++) {
+            if (!alloc[ch]) continue;
+            const float a = c_l2_scf[l2_bits(fb, p, 6)];
+            p += 6;
+            float b = a, c = a;
+            if (scfsi[ch] == 0) { b = c_l2_scf[l2_bits(fb, p, 6)]; c = c_l2_scf[l2_bits(fb, p + 6, 6)]; p += 12; }
+            else if (scfsi[ch] == 1) { c = c_l2_scf[l2_bits(fb, p, 6)]; p += 6; }
+            else if (scfsi[ch] == 3) { b = c = c_l2_scf[l2_bits(fb, p, 6)]; p += 6; }
+            scf[ch][0] = a; scf[ch][1] = b; scf[ch][2] = c;
+        }
+    }
+    pos += (uint32_t)tot;
+    // ---- samples: 12 groups; within a group, subbands in order, channels inside a subband
+    int q[2], cbits[2];
+    for (int k = 0; k < 2; k++) {
+        const int a = k < ncode ? alloc[k] : 0;
+        q[k] = a ? row[a] : -1;
+        const int b = a ? c_l2_bits[q[k]] : 0;
+        cbits[k] = b < 0 ? -b : 3 * b;
+    }
+    off = warp_excl_scan(cbits[0] + cbits[1], lane, &tot);
+    const uint32_t fi = f - sr.frame_base;
+    const size_t u0 = (size_t)sr.unit_base + (size_t)fi * 2u * (size_t)nch;
+    for (int gr = 0; gr < 12; gr++) {
+        uint32_t p = pos + (uint32_t)(gr * tot + off);
+        float v[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        for (int k = 0; k < ncode; k++) {
+            if (q[k] < 0) continue;
+            const int steps = c_l2_steps[q[k]], b = c_l2_bits[q[k]];
+            int code[3];
+            if (b < 0) {
+                uint32_t c = l2_bits(fb, p, -b);
+                code[0] = (int)(c % (uint32_t)steps);
+                c /= (uint32_t)steps;
+                code[1] = (int)(c % (uint32_t)steps);
+                code[2] = (int)(c / (uint32_t)steps);
+            } else {
+                code[0] = (int)l2_bits(fb, p, b);
+                code[1] = (int)l2_bits(fb, p + b, b);
+                code[2] = (int)l2_bits(fb, p + 2 * b, b);
+            }
+            p += (uint32_t)cbits[k];
+            const float inv = 1.f / (float)steps;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float fr3 = (float)(2 * code[i] + 1 - steps) * inv;
+                if (sep) v[k][i] = fr3 * scf[k][gr >> 2];
+                else { v[0][i] = fr3 * scf[0][gr >> 2]; v[1][i] = fr3 * scf[1][gr >> 2]; }
+            }
+        }
+        for (int ch = 0; ch < nch; ch++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int slot = gr * 3 + i;
+                const size_t u = u0 + (size_t)(slot / 18) * nch + ch;
+                sb_out[u * 576 + (size_t)(slot % 18) * 32 + lane] = v[ch][i];
+            }
+    }
+}
+
+} // namespace
+
+void l3_layer2_init(void)
+{
+    float scf[64];
+    for (int i = 0; i < 63; i++) scf[i] = (float)pow(2.0, 1.0 - i / 3.0);
+    scf[63] = 0.f;
+    cudaMemcpyToSymbol(c_l2_rows, l2_rows, sizeof l2_rows);
+    cudaMemcpyToSymbol(c_l2_row_of_sb, l2_row_of_sb, sizeof l2_row_of_sb);
+    cudaMemcpyToSymbol(c_l2_steps, l2_quant_steps, sizeof l2_quant_steps);
+    cudaMemcpyToSymbol(c_l2_bits, l2_quant_bits, sizeof l2_quant_bits);
+    cudaMemcpyToSymbol(c_l2_scf, scf, sizeof scf);
+}
+
+void l3_launch_layer2(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames, uint32_t nframes,
+                      float *sb_out, cudaStream_t st)
+{
+    if (!nframes) return;
+    k_layer2<<<(nframes + L2_WARPS - 1) / L2_WARPS, L2_WARPS * 32, 0, st>>>(raw, streams, frames, nframes, sb_out);
+}

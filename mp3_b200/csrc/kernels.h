@@ -60,6 +60,11 @@ void l3_launch_imdct_range(const L3UnitDesc *units, uint32_t u_lo, uint32_t nuni
 void l3_launch_overlap_range(const L3UnitDesc *units, uint32_t u_lo, uint32_t nunits, const float *imd, float *sb,
                              cudaStream_t st);
 
+/* Layer II frames -> subband samples [unit][18][32] (k_layer2.cu); frames of other layers are skipped */
+void l3_layer2_init(void);
+void l3_launch_layer2(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames, uint32_t nframes,
+                      float *sb_out, cudaStream_t st);
+
 /* K4: polyphase synthesis (a11) */
 void l3_synth_init(void);
 /* tiles[i] = {first global granule, number of granules (<= l3_synth_tile_granules())}; a tile

@@ -99,6 +99,8 @@ typedef struct __attribute__((aligned(16))) L3UnitDesc {
 
 typedef struct L3Hdr {
     int lsf, sr_row, nch, mode, mode_ext, crc, frame_len, side_len, ngr;
+    int layer; /* 3, or 2: Layer II frames carry no side info / main data (side_len = 0, two granules) */
+    int kbps;
 } L3Hdr;
 
 L3_HD int l3_kbps(int lsf, int idx)
@@ -131,9 +133,10 @@ L3_HD int l3_parse_hdr(uint32_t w, L3Hdr *h)
 {
     if ((w & 0xFFE00000u) != 0xFFE00000u) return 0;
     int ver = (w >> 19) & 3, layer = (w >> 17) & 3;
-    if (layer != 1 || ver == 1) return 0;
+    if ((layer != 1 && layer != 2) || ver == 1) return 0; /* 01 = Layer III, 10 = Layer II; Layer I is not decoded */
     int bri = (w >> 12) & 15, sri = (w >> 10) & 3;
     if (bri == 0 || bri == 15 || sri == 3) return 0;
+    h->layer = layer == 1 ? 3 : 2;
     h->lsf = ver != 3;
     h->crc = !((w >> 16) & 1);
     h->mode = (w >> 6) & 3;
@@ -142,7 +145,17 @@ L3_HD int l3_parse_hdr(uint32_t w, L3Hdr *h)
     h->sr_row = sri + (ver == 3 ? 0 : ver == 2 ? 3 : 6);
     h->ngr = h->lsf ? 1 : 2;
     int pad = (w >> 9) & 1;
-    h->frame_len = (h->lsf ? 72000 : 144000) * l3_kbps(h->lsf, bri) / l3_sr_hz(h->sr_row) + pad;
+    if (h->layer == 2) { /* 1152 samples per frame at every rate; MPEG-1 has its own Layer II bitrate table */
+        /* kbit/s / 8 for bitrate_index 1..8 and 9..14: 32 48 56 64 80 96 112 128 | 160 192 224 256 320 384 */
+        const unsigned long long lo = 0x100E0C0A08070604ull, hi = 0x00003028201C1814ull;
+        h->kbps = h->lsf ? l3_kbps(1, bri) : 8 * (int)((bri <= 8 ? (lo >> (8 * (bri - 1))) : (hi >> (8 * (bri - 9)))) & 0xff);
+        h->ngr = 2;
+        h->frame_len = 144000 * h->kbps / l3_sr_hz(h->sr_row) + pad;
+        h->side_len = 0;
+        return 1;
+    }
+    h->kbps = l3_kbps(h->lsf, bri);
+    h->frame_len = (h->lsf ? 72000 : 144000) * h->kbps / l3_sr_hz(h->sr_row) + pad;
     h->side_len = h->lsf ? (h->nch == 1 ? 9 : 17) : (h->nch == 1 ? 17 : 32);
     return 1;
 }
@@ -234,6 +247,13 @@ L3_HD int l3_frame_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t fir
     if (first && !l3_same_stream(w, first)) return 0;
     if (h->frame_len < 4 + (h->crc ? 2 : 0) + h->side_len) return 0;
     if (p + (uint32_t)h->frame_len > len) return 2;
+    if (!first && p + (uint32_t)h->frame_len + 4 <= len) {
+        /* the stream's first frame must be followed by a header of the same stream (when the bytes are
+         * there to check): one valid-looking word inside junk or a tag does not start a stream */
+        const uint32_t w2 = l3_load_be32(buf + p + (uint32_t)h->frame_len);
+        L3Hdr h2;
+        if (!l3_parse_hdr(w2, &h2) || !l3_same_stream(w, w2)) return 0;
+    }
     *word = w;
     return 1;
 }

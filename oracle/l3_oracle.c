@@ -708,7 +708,19 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
             p++;
             continue;
         }
-        if (!have_first) { first = h; have_first = 1; }
+        if (!have_first) {
+            /* sync confirmation: the first frame must be followed by a header of the same stream when
+             * there are bytes to check (a lone valid-looking word in junk does not start a stream) */
+            size_t q = p + (size_t)h.frame_len;
+            l3o_hdr h2;
+            if (q + 4 <= len && (!l3o_parse_header(buf + q, &h2) || h2.lsf != h.lsf || h2.sr_row != h.sr_row ||
+                                 h2.nch != h.nch || h2.layer != h.layer)) {
+                p++;
+                continue;
+            }
+            first = h;
+            have_first = 1;
+        }
         if (nfr == capfr) { capfr *= 2; fr = (frame_ent *)realloc(fr, capfr * sizeof *fr); }
         fr[nfr].off = p;
         fr[nfr].h = h;
@@ -857,8 +869,13 @@ int l3o_parse_tag(const uint8_t *buf, size_t len, l3o_tag *t)
     for (;; p++) { /* the first decodable frame */
         if (p + 4 > len) return -1;
         if (l3o_parse_header(buf + p, &h) && h.frame_len >= 4 + (h.crc ? 2 : 0) + h.side_len &&
-            p + (size_t)h.frame_len <= len)
-            break;
+            p + (size_t)h.frame_len <= len) {
+            size_t q = p + (size_t)h.frame_len;
+            l3o_hdr h2;
+            if (q + 4 > len || (l3o_parse_header(buf + q, &h2) && h2.lsf == h.lsf && h2.sr_row == h.sr_row &&
+                                h2.nch == h.nch && h2.layer == h.layer))
+                break;
+        }
     }
     const uint8_t *f = buf + p;
     size_t flen = (size_t)h.frame_len;
