@@ -46,7 +46,7 @@ constexpr int KF_THREADS = 256;
 constexpr int KF_ROWS = 15 + KF_B * 18;
 constexpr int XROW = 19;        // padded subband row of X
 constexpr int XSZ = 32 * XROW;  // 608 floats per channel spectrum
-constexpr int KF_POW_LUT = 1024;
+constexpr int KF_POW_LUT = 512;
 constexpr int FS = 33;         // row stride of F: odd, so rows are conflict-free both by lane = column and lane = row
 
 __constant__ float f_pow2q[4];
@@ -64,31 +64,48 @@ struct GranMeta {
     int ms, ist;
 };
 
-struct FusedShared {
-    float X[KF_B][2][XSZ];          // spectra of the batch, padded rows; reused as PCM staging in S4
+// The Huffman output of the next batch (9216 bytes) is fetched while the current batch is in S3 / S4,
+// when X is dead except for the PCM staging area at its start.  With s16 output that area is 9216 bytes
+// too, so the fetch buffer lives INSIDE X (bytes 9216 .. 18431) and the CTA needs no separate buffer --
+// which is what brings shared memory under 56 KB and a fourth CTA onto the SM.  f32 output stages twice
+// as much and keeps its own buffer (three CTAs per SM).
+template <int FMT> struct IsOwn { __align__(16) int16_t buf[KF_B * 2][576]; };
+template <> struct IsOwn<MP3B_PCM_S16> {};
+
+template <int FMT>
+struct FusedSharedT {
+    __align__(16) float X[KF_B][2][XSZ]; // spectra of the batch, padded rows; PCM staging in S4; (s16) next batch's is
     float F[2][KF_ROWS][FS];        // rows 0..14: C history; rows 15..: first IMDCT halves -> S -> C
     __align__(16) float Hc[2][18][32]; // second IMDCT half of the last granule of the previous batch
-    float win[16][32];              // per-lane window taps (copied from global once)
     float pow43[KF_POW_LUT];        // |is|^(4/3) for the common small values
+    float win[16][32];              // per-lane window taps (copied from global once)
     float gain[KF_B][2][40];
     float kl[KF_B][40], kr[KF_B][40];
-    int nz[KF_B][40];               // right-channel band has a non-zero line (intensity bound)
+    uint8_t nz[KF_B][40];           // right-channel band has a non-zero line (intensity bound)
     uint8_t mode[KF_B][40];         // 1 = intensity-coded band
     GranMeta gm[KF_B];
     int any_ist;
     int any_short;                  // some unit of the batch has short / mixed blocks
-    uint32_t lmap[3][576];          // this stream's sample rate: [layout][line] -> band | xpad(reordered line) << 8
-    // next batch's Huffman output and scalefactors, fetched with cp.async while this batch computes
-    __align__(16) int16_t is_buf[KF_B * 2][576];
-    __align__(16) uint8_t sf_buf[KF_B * 2][40];
+    __align__(16) uint8_t sf_buf[KF_B * 2][40]; // next batch's scalefactors (cp.async)
     __align__(8) uint64_t bar;  // mbarrier: completion of the bulk copies into is_buf
+    IsOwn<FMT> own;
+    // next batch's Huffman output, fetched by TMA while this batch computes
+    __device__ __forceinline__ int16_t (*is_buf())[576]
+    {
+        if constexpr (FMT == MP3B_PCM_S16)
+            return reinterpret_cast<int16_t(*)[576]>(reinterpret_cast<unsigned char *>(&X[0][0][0]) + KF_B * 2 * 576 * 2);
+        else
+            return own.buf;
+    }
 };
+static_assert(KF_B * 2 * 576 * 2 * 2 <= (int)sizeof(float) * KF_B * 2 * XSZ, "is buffer must fit behind the s16 staging area");
 
 // f_pow2q[q & 3] * 2^(q >> 2), exactly (q >> 2 stays within the normal exponent range: -82 .. 11)
 __device__ __forceinline__ float gain_of(int q) { return __int_as_float((127 + (q >> 2)) << 23) * f_pow2q[q & 3]; }
 
-// three CTAs per SM: 3 x (shared memory + 1 KB reserved per CTA) must fit 228 KB
-static_assert(sizeof(FusedShared) <= 75 * 1024, "FusedShared too large for 3 CTAs per SM");
+// s16: four CTAs per SM, f32: three -- n x (shared memory + 1 KB reserved per CTA) must fit 228 KB
+static_assert(sizeof(FusedSharedT<MP3B_PCM_S16>) <= 56 * 1024, "s16 back end: too large for 4 CTAs per SM");
+static_assert(sizeof(FusedSharedT<MP3B_PCM_F32>) <= 75 * 1024, "f32 back end: too large for 3 CTAs per SM");
 
 __device__ __forceinline__ int xpad(int i) { return i + ((i * 3641) >> 16); } // i + i / 18 for i < 608
 
@@ -142,7 +159,8 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // units into shared memory; the caller waits (cp_async_wait_all + barrier) before reading them.
 // Only the vectors that hold data are fetched (nzv_in[u] of the 72 per unit); the all-zero tail of
 // each spectrum is never written by the Huffman kernel nor read here: it is zeroed in place.
-__device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t u_first, int n,
+template <class SH>
+__device__ __forceinline__ void prefetch_units(SH &S, int tid, uint32_t u_first, int n,
                                                const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
                                                const uint8_t *__restrict__ nzv_in)
 {
@@ -159,11 +177,11 @@ __device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t
             mbar_expect_tx(&S.bar, tot);
         }
         __syncwarp();
-        if (b) bulk_g2s(&S.is_buf[k][0], is_in + (size_t)(u_first + k) * 576, b, &S.bar);
+        if (b) bulk_g2s(&S.is_buf()[k][0], is_in + (size_t)(u_first + k) * 576, b, &S.bar);
     }
     const int unit = tid >> 5, lane = tid & 31;
     if (unit < n || (unit == n && (n & 1))) { // an odd mono batch leaves one slot of the last pair empty: all zero
-        char *si = reinterpret_cast<char *>(&S.is_buf[unit][0]);
+        char *si = reinterpret_cast<char *>(&S.is_buf()[unit][0]);
         const int nv = unit < n ? nzv_in[u_first + unit] : 0;
 #pragma unroll
         for (int v = lane; v < 72; v += 32)
@@ -179,7 +197,8 @@ __device__ __forceinline__ void prefetch_units(FusedShared &S, int tid, uint32_t
 // A batch is held as pairs of unit slots: the two channels of a stereo granule, or two consecutive
 // granules of a mono stream (which doubles the granules per batch, so that mono tiles keep all eight
 // warps busy).  `nun` = units in the batch; an odd mono batch repeats its last descriptor.
-__device__ __forceinline__ void load_meta(FusedShared &S, int tid, uint32_t u_first, int nun,
+template <class SH>
+__device__ __forceinline__ void load_meta(SH &S, int tid, uint32_t u_first, int nun,
                                           const L3UnitDesc *__restrict__ units)
 {
     if (tid < ((nun + 1) & ~1)) S.gm[tid >> 1].d[tid & 1] = units[u_first + (uint32_t)min(tid, nun - 1)];
@@ -190,7 +209,8 @@ __device__ __forceinline__ void load_meta(FusedShared &S, int tid, uint32_t u_fi
     if (tid == 0) { S.any_ist = 0; S.any_short = 0; }
 }
 
-__device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int nch)
+template <class SH>
+__device__ __forceinline__ void finish_meta(SH &S, int tid, int nb, int nch)
 {
     if (tid < nb) {
         GranMeta &m = S.gm[tid];
@@ -207,7 +227,8 @@ __device__ __forceinline__ void finish_meta(FusedShared &S, int tid, int nb, int
 }
 
 // ---- S1a: per-band gains, and the right channel's non-zero bands for intensity granules ---------
-__device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int nch,
+template <class SH>
+__device__ __forceinline__ void stage_gains(SH &S, int tid, int nb, int nch,
                                             const L3BandTables *__restrict__ bands)
 {
     // 64 threads per granule: lanes 0..39 of each of its two warps take one band of one channel
@@ -259,14 +280,14 @@ __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int
             const int gi = it / 72, v = it - gi * 72;
             const GranMeta &m = S.gm[gi];
             if (!m.ist) continue;
-            const uint4 q = reinterpret_cast<const uint4 *>(&S.is_buf[gi * nch + 1][0])[v];
+            const uint4 q = reinterpret_cast<const uint4 *>(&S.is_buf()[gi * nch + 1][0])[v];
             if ((q.x | q.y | q.z | q.w) == 0u) continue;
-            const uint32_t *lm = S.lmap[m.lay[1]] + v * 8;
+            const uint32_t *lm = bands->lmap[m.row][m.lay[1]] + v * 8;
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (w[k] & 0xffffu) S.nz[gi][lm[2 * k] & 0xffu] = 1;
-                if (w[k] >> 16) S.nz[gi][lm[2 * k + 1] & 0xffu] = 1;
+                if (w[k] & 0xffffu) S.nz[gi][__ldg(lm + 2 * k) & 0xffu] = 1;
+                if (w[k] >> 16) S.nz[gi][__ldg(lm + 2 * k + 1) & 0xffu] = 1;
             }
         }
     }
@@ -277,7 +298,8 @@ __device__ __forceinline__ void stage_gains(FusedShared &S, int tid, int nb, int
 // or long) at or above it holds a non-zero line -- and, for the long bands of a mixed block, no short
 // band does either (11172-3 2.4.3.4: intensity applies above the last non-zero band).  Scanned serially
 // from the top this is a chain; as "highest non-zero band per class" it is four ballots.
-__device__ __forceinline__ void stage_intensity(FusedShared &S, int gi, int u1 /* batch-local unit */, int lane,
+template <class SH>
+__device__ __forceinline__ void stage_intensity(SH &S, int gi, int u1 /* batch-local unit */, int lane,
                                                 const L3BandTables *__restrict__ bands)
 {
     const GranMeta &m = S.gm[gi];
@@ -321,7 +343,8 @@ __device__ __forceinline__ void stage_intensity(FusedShared &S, int gi, int u1 /
     }
 }
 
-__device__ __forceinline__ float requant1(const FusedShared &S, int v, float gain, const float *__restrict__ pow43)
+template <class SH>
+__device__ __forceinline__ float requant1(const SH &S, int v, float gain, const float *__restrict__ pow43)
 {
     const int m = v < 0 ? -v : v;
     const float p = m < KF_POW_LUT ? S.pow43[m] : __ldg(pow43 + m);
@@ -333,9 +356,24 @@ __device__ __forceinline__ float requant1(const FusedShared &S, int v, float gai
 // `bq` holds this thread's nine long-block band indices (lines t64 + 64 q), one byte each: they
 // depend only on the stream's sample rate, so the common case (both channels long blocks, no
 // intensity stereo) needs no table lookups, no reorder and no branches per line.
-__device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, int nch,
-                                              const L3BandTables *__restrict__ bands, const float *__restrict__ pow43,
-                                              const uint32_t (&bq)[3])
+// First half: every thread pulls its nine line pairs of the Huffman output into registers.  With s16
+// output that buffer lives inside X, which the second half overwrites: the caller puts a barrier between
+// the two.
+template <class SH>
+__device__ __forceinline__ void requant_load(SH &S, int tid, int nb, uint32_t (&v)[9])
+{
+    const int gi = tid >> 6, t64 = tid & 63;
+    if (gi >= nb) return;
+    const uint16_t *s0 = reinterpret_cast<const uint16_t *>(S.is_buf()[gi * 2]);
+    const uint16_t *s1 = reinterpret_cast<const uint16_t *>(S.is_buf()[gi * 2 + 1]);
+#pragma unroll
+    for (int q = 0; q < 9; q++) v[q] = (uint32_t)s0[t64 + 64 * q] | ((uint32_t)s1[t64 + 64 * q] << 16); // packed pair
+}
+
+template <class SH>
+__device__ __forceinline__ void stage_requant(SH &S, int tid, int nb, const L3BandTables *__restrict__ bands,
+                                              const float *__restrict__ pow43, const uint32_t (&bq)[3],
+                                              const uint32_t (&v)[9])
 {
     constexpr int ITEMS = 576 / 64; // 9 lines per thread: 64 threads per granule
     const float isq2 = 0.70710678118654752440f;
@@ -343,23 +381,20 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
     if (gi >= nb) return;
     const GranMeta &m = S.gm[gi];
     const int lay0 = m.lay[0], lay1 = m.lay[1];
-    if (nch == 2 && (lay0 | lay1) == 0 && !m.ist) {
-        const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
-        const int16_t *s0 = S.is_buf[gi * 2], *s1 = S.is_buf[gi * 2 + 1];
+    const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
+    if ((lay0 | lay1) == 0 && !m.ist) {
         float *X0 = S.X[gi][0], *X1 = S.X[gi][1];
         // MS: (M +- S) / sqrt 2; stage_gains has folded the factor into this granule's band gains
-        int v0[ITEMS], v1[ITEMS];
-#pragma unroll
-        for (int q = 0; q < ITEMS; q++) { v0[q] = s0[t64 + 64 * q]; v1[q] = s1[t64 + 64 * q]; }
         auto lines = [&](auto ms_tag) {
 #pragma unroll
             for (int q = 0; q < ITEMS; q++) {
                 const int b = (bq[q >> 2] >> (8 * (q & 3))) & 0xff;
-                const int m0 = abs(v0[q]), m1 = abs(v1[q]);
+                const int w0 = (int)(short)(v[q] & 0xffffu), w1 = (int)v[q] >> 16;
+                const int m0 = abs(w0), m1 = abs(w1);
                 const float p0 = m0 < KF_POW_LUT ? S.pow43[m0] : __ldg(pow43 + m0);
                 const float p1 = m1 < KF_POW_LUT ? S.pow43[m1] : __ldg(pow43 + m1);
-                const float a = __int_as_float(__float_as_int(p0 * g0[b]) | (v0[q] & 0x80000000));
-                const float c = __int_as_float(__float_as_int(p1 * g1[b]) | (v1[q] & 0x80000000));
+                const float a = __int_as_float(__float_as_int(p0 * g0[b]) | (w0 & 0x80000000));
+                const float c = __int_as_float(__float_as_int(p1 * g1[b]) | (w1 & 0x80000000));
                 const int xp = xpad(t64 + 64 * q);
                 X0[xp] = decltype(ms_tag)::value ? a + c : a;
                 X1[xp] = decltype(ms_tag)::value ? a - c : c;
@@ -369,29 +404,20 @@ __device__ __forceinline__ void stage_requant(FusedShared &S, int tid, int nb, i
         else lines(std::false_type{});
         return;
     }
-    int v0[ITEMS], v1[ITEMS];
-#pragma unroll
-    for (int q = 0; q < ITEMS; q++) {
-        const int i = t64 + 64 * q;
-        v0[q] = S.is_buf[gi * nch][i];
-        v1[q] = nch == 2 ? S.is_buf[gi * nch + 1][i] : 0;
-    }
-    const uint32_t *lm0 = S.lmap[lay0], *lm1 = S.lmap[lay1];
-    const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
+    // general path (short / mixed blocks, intensity stereo): band and reordered padded position of every
+    // line from the per-rate line map (global memory, L1-resident)
+    const uint32_t *lm0 = bands->lmap[m.row][lay0], *lm1 = bands->lmap[m.row][lay1];
     const bool ist = m.ist != 0, ms = m.ms != 0;
 #pragma unroll
     for (int q = 0; q < ITEMS; q++) {
         const int i = t64 + 64 * q;
-        const uint32_t e0 = lm0[i];
-        float l = requant1(S, v0[q], g0[e0 & 0xffu], pow43);
-        if (nch == 2) {
-            const uint32_t e1 = lm1[i];
-            const int b1 = (int)(e1 & 0xffu);
-            float r = requant1(S, v1[q], g1[b1], pow43);
-            if (ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
-            else if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
-            S.X[gi][1][e1 >> 8] = r;
-        }
+        const uint32_t e0 = __ldg(lm0 + i), e1 = __ldg(lm1 + i);
+        const int b1 = (int)(e1 & 0xffu);
+        float l = requant1(S, (int)(short)(v[q] & 0xffffu), g0[e0 & 0xffu], pow43);
+        float r = requant1(S, (int)v[q] >> 16, g1[b1], pow43);
+        if (ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
+        else if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
+        S.X[gi][1][e1 >> 8] = r;
         S.X[gi][0][e0 >> 8] = l;
     }
 }
@@ -512,7 +538,7 @@ __device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r
 // arithmetic: pairs of consecutive mono granules take the two slots a stereo granule's channels would,
 // eight granules per batch, and the rows of F form ONE time sequence (F[0] and F[1] are contiguous).
 template <int FMT, bool MONO>
-__device__ __forceinline__ void backend_tile(FusedShared &S, const int warm, const int total, const uint32_t ubase,
+__device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int warm, const int total, const uint32_t ubase,
                                              const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in,
                                              const uint8_t *__restrict__ sf_in, const uint8_t *__restrict__ nzv_in,
                                              const L3BandTables *__restrict__ bands, const float *__restrict__ pow43,
@@ -534,14 +560,6 @@ __device__ __forceinline__ void backend_tile(FusedShared &S, const int warm, con
         for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.Hc[i / 144][0][0])[i % 144] = z;
         for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) S.pow43[i] = pow43[i];
         for (int i = tid; i < 512; i += KF_THREADS) (&S.win[0][0])[i] = (&f_synwin[0][0])[i];
-        {
-            const int row0 = (units[ubase].hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
-            for (int i = tid; i < 3 * 576; i += KF_THREADS) {
-                const int lay = i / 576, ln = i - lay * 576;
-                (&S.lmap[0][0])[i] = (uint32_t)bands->line2band[row0][lay][ln] |
-                                     ((uint32_t)xpad(lay == 0 ? ln : (int)bands->dst[row0][lay][ln]) << 8);
-            }
-        }
         load_meta(S, tid, ubase, min(KFG, total) * nch, units);
         prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in, nzv_in);
     }
@@ -575,7 +593,12 @@ __device__ __forceinline__ void backend_tile(FusedShared &S, const int warm, con
                 stage_intensity(S, tid >> 6, (tid >> 6) * 2 + 1, lane, bands);
             __syncthreads();
         }
-        stage_requant(S, tid, np, 2, bands, pow43, bq);
+        {
+            uint32_t v[9];
+            requant_load(S, tid, np, v);
+            if (FMT == MP3B_PCM_S16) __syncthreads(); // the Huffman output sits inside X, which is written next
+            stage_requant(S, tid, np, bands, pow43, bq, v);
+        }
         __syncthreads();
         // ---- S2: alias + IMDCT; second halves travel in registers to the next granule's rows
         {
@@ -658,14 +681,14 @@ __device__ __forceinline__ void backend_tile(FusedShared &S, const int warm, con
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(KF_THREADS, 3)
+__global__ void __launch_bounds__(KF_THREADS, FMT == MP3B_PCM_S16 ? 4 : 3)
 k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
           const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
           const uint8_t *__restrict__ nzv_in, const L3BandTables *__restrict__ bands,
           const float *__restrict__ pow43, void *__restrict__ pcm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedShared &S = *reinterpret_cast<FusedShared *>(smem_raw);
+    FusedSharedT<FMT> &S = *reinterpret_cast<FusedSharedT<FMT> *>(smem_raw);
     if (blockIdx.x >= ntiles) return;
     const uint4 tl = tiles[blockIdx.x];
     const int warm = (int)tl.z, ng = (int)tl.y;    // granules before g0 to re-derive state from
@@ -728,9 +751,10 @@ void l3_fused_init(void)
             win[l][j] = (float)v;
         }
     cudaMemcpyToSymbol(f_synwin, win, sizeof win);
-    const int smem = (int)sizeof(FusedShared);
-    cudaFuncSetAttribute(k_backend<MP3B_PCM_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_backend<MP3B_PCM_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_backend<MP3B_PCM_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(FusedSharedT<MP3B_PCM_S16>));
+    cudaFuncSetAttribute(k_backend<MP3B_PCM_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(FusedSharedT<MP3B_PCM_F32>));
 }
 
 void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const L3UnitDesc *units,
@@ -738,11 +762,10 @@ void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran
                        void *pcm, int pcm_format, cudaStream_t st)
 {
     if (!ntiles) return;
-    const size_t smem = sizeof(FusedShared);
     if (pcm_format == MP3B_PCM_S16)
-        k_backend<MP3B_PCM_S16><<<ntiles, KF_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
+        k_backend<MP3B_PCM_S16><<<ntiles, KF_THREADS, sizeof(FusedSharedT<MP3B_PCM_S16>), st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
                                                                   nzv_in, T.bands, T.pow43, pcm);
     else
-        k_backend<MP3B_PCM_F32><<<ntiles, KF_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
+        k_backend<MP3B_PCM_F32><<<ntiles, KF_THREADS, sizeof(FusedSharedT<MP3B_PCM_F32>), st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
                                                                   nzv_in, T.bands, T.pow43, pcm);
 }
