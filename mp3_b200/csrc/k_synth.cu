@@ -11,11 +11,16 @@
 // with the signs folded into the rearranged window W.  A tile (one stream, G granules, both
 // channels) keeps its C vectors in shared memory; the 15-slot history comes from the previous
 // granule's subband samples (re-transformed: a 10 % halo at G = 8), or is zero at stream start.
+// The 32-point transform is the in-register fast DCT-II of fast_dct.h (304 operations per slot instead
+// of 1024 multiply-adds), one thread per (channel, slot) row; rows have an odd stride so that both the
+// row-per-lane transform and the column-per-lane window are free of bank conflicts.  This kernel is the
+// product path of Layer II (k_layer2.cu) and the last stage of the staged Layer III pipeline.
 // FP32 FMA throughout; lanes write interleaved (L, R) pairs so every store is a full 128-byte row.
 // Restates oracle/l3_oracle.c::synth_slot in float32.
 // No reference code exists for this stage (/root/reference/README.md:1-84).
 #include <math.h>
 
+#include "fast_dct.h"
 #include "iso_tables.h"
 #include "kernels.h"
 #include "mp3b.h"
@@ -25,8 +30,8 @@ namespace {
 constexpr int K4_G = 8;                 // granules per tile
 constexpr int K4_SLOTS = 15 + K4_G * 18; // with history
 constexpr int K4_THREADS = 256;
+constexpr int K4_FS = 33;               // row stride
 
-__device__ float g_dct32[32][32];  // [k][n] = cos(n (2k+1) pi / 64)
 __device__ float g_synwin[16][32]; // W[l][j]
 
 __device__ __forceinline__ int16_t to_s16(float v)
@@ -41,7 +46,7 @@ __global__ void __launch_bounds__(K4_THREADS)
 k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
         const float *__restrict__ sb, void *__restrict__ pcm)
 {
-    extern __shared__ float s_c[]; // [nch][K4_SLOTS][32]
+    extern __shared__ float s_c[]; // [nch][K4_SLOTS][K4_FS]
     const uint32_t tile = blockIdx.x;
     if (tile >= ntiles) return;
     const uint2 tl = tiles[tile];
@@ -56,32 +61,28 @@ k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__rest
     // ---- load subband samples: history (last 15 slots of the previous granule) + ng granules.
     // units of this stream are contiguous: unit(g, c) = u0 + (g - g0) * nch + c
     for (int c = 0; c < nch; c++) {
-        float *dst = s_c + c * (K4_SLOTS * 32);
+        float *dst = s_c + c * (K4_SLOTS * K4_FS);
         for (int i = threadIdx.x; i < 15 * 32; i += K4_THREADS) {
             float v = 0.f;
             if (!first) v = sb[(size_t)(u0 - nch + c) * 576 + 3 * 32 + i];
-            dst[i] = v;
+            dst[(i >> 5) * K4_FS + (i & 31)] = v;
         }
         for (int i = threadIdx.x; i < (int)ng * 576; i += K4_THREADS) {
             const int gi = i / 576, r = i % 576;
-            dst[15 * 32 + i] = sb[(size_t)(u0 + gi * nch + c) * 576 + r];
+            dst[(15 + (i >> 5)) * K4_FS + (i & 31)] = sb[(size_t)(u0 + gi * nch + c) * 576 + r];
         }
     }
     __syncthreads();
 
-    // ---- matrixing: C[n] = sum_k S[k] cos(n(2k+1)pi/64), in place, one (channel, slot) per warp step
-    {
-        float cn[32];
+    // ---- matrixing: C[n] = sum_k S[k] cos(n(2k+1)pi/64), in place, one thread per (channel, slot) row
+    for (int it = threadIdx.x; it < nch * nslots; it += K4_THREADS) {
+        float *row = s_c + (it / nslots) * (K4_SLOTS * K4_FS) + (it % nslots) * K4_FS;
+        float x[32];
 #pragma unroll
-        for (int k = 0; k < 32; k++) cn[k] = g_dct32[k][lane];
-        for (int it = warp; it < nch * nslots; it += nwarps) {
-            float *row = s_c + (it / nslots) * (K4_SLOTS * 32) + (it % nslots) * 32;
-            float acc = 0.f;
+        for (int k = 0; k < 32; k++) x[k] = row[k];
+        L3Dct2<32>::run(x);
 #pragma unroll
-            for (int k = 0; k < 32; k++) acc = fmaf(row[k], cn[k], acc);
-            __syncwarp();
-            row[lane] = acc;
-        }
+        for (int k = 0; k < 32; k++) row[k] = x[k];
     }
     __syncthreads();
 
@@ -96,12 +97,12 @@ k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__rest
             const int T = 15 + t;
             float out[2] = {0.f, 0.f};
             for (int c = 0; c < nch; c++) {
-                const float *base = s_c + c * (K4_SLOTS * 32) + T * 32;
+                const float *base = s_c + c * (K4_SLOTS * K4_FS) + T * K4_FS;
                 float acc = 0.f;
 #pragma unroll
                 for (int l = 0; l < 16; l += 2) {
-                    acc = fmaf(w[l], base[-l * 32 + src_e], acc);
-                    acc = fmaf(w[l + 1], base[-(l + 1) * 32 + src_o], acc);
+                    acc = fmaf(w[l], base[-l * K4_FS + src_e], acc);
+                    acc = fmaf(w[l + 1], base[-(l + 1) * K4_FS + src_o], acc);
                 }
                 out[c] = acc;
             }
@@ -130,9 +131,7 @@ int l3_synth_tile_granules(void) { return K4_G; }
 
 void l3_synth_init(void)
 {
-    static float dct[32][32], win[16][32];
-    for (int k = 0; k < 32; k++)
-        for (int n = 0; n < 32; n++) dct[k][n] = (float)cos(n * (2 * k + 1) * M_PI / 64.0);
+    static float win[16][32];
     for (int l = 0; l < 16; l++)
         for (int j = 0; j < 32; j++) {
             const int i = l >> 1;
@@ -141,7 +140,6 @@ void l3_synth_init(void)
             else v = -l3_dwin(64 * i + 32 + j);
             win[l][j] = (float)v;
         }
-    cudaMemcpyToSymbol(g_dct32, dct, sizeof dct);
     cudaMemcpyToSymbol(g_synwin, win, sizeof win);
 }
 
@@ -149,7 +147,7 @@ void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_u
                      int pcm_format, cudaStream_t st)
 {
     if (!ntiles) return;
-    const size_t smem = (size_t)2 * K4_SLOTS * 32 * sizeof(float);
+    const size_t smem = (size_t)2 * K4_SLOTS * K4_FS * sizeof(float);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_synth<MP3B_PCM_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
