@@ -127,3 +127,40 @@ def test_corrupted_streams_never_fault(mp3b, synth_mod):
         good = synth_mod.make_stream(nframes=8, seed=3)
         dec.decode_batch([good])               # the context is still healthy afterwards
         assert dec.stream_info(0).frames == 8
+
+
+def test_damaged_streams_decode_like_the_oracle(mp3b, synth_mod, oracle_mod):
+    """Parity does not stop at valid input: bit flips (headers, side info, main data, light and heavy),
+    truncation and a lost head must give the oracle's frame count, sync decisions, concealment and PCM --
+    the two implementations share the policy (sync confirmation, stream consistency, frames whose
+    main_data_begin reaches before the stream are concealed, out-of-bits handling in Huffman)."""
+    rng = np.random.default_rng(99)
+    base = synth_mod.make_workload("cfg3", 5, 24) + synth_mod.make_workload("cfg4", 9, 24) + [
+        synth_mod.make_stream(layer=2, bitrate_kbps=192, nframes=10, seed=5),
+        synth_mod.make_stream(layer=2, sample_rate=24000, bitrate_kbps=64, mode=1, nframes=10, seed=6)]
+    bad = []
+    for s in base:
+        a = np.frombuffer(s, np.uint8).copy()
+        for n in (1, 2, 3, 5, 8, 13, 40):
+            b = a.copy()
+            idx = rng.integers(0, b.size, n)
+            b[idx] ^= (1 << rng.integers(0, 8, n)).astype(np.uint8)
+            bad.append(b.tobytes())
+        bad.append(a[: rng.integers(1, a.size)].tobytes())
+        bad.append(a[rng.integers(1, 500):].tobytes())
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
+        dec.decode_batch(bad)
+        arena = dec.fetch_pcm()
+        concealed = 0
+        for i, s in enumerate(bad):
+            r = oracle_mod.decode(s)
+            inf = dec.stream_info(i)
+            if r.rc != 0:
+                assert inf.frames == 0, i
+                continue
+            concealed += r.concealed_frames
+            assert (inf.frames, inf.samples, inf.channels, inf.sample_rate) == (r.frames, r.samples, r.channels, r.sample_rate), i
+            got = dec.stream_pcm(i, arena).astype(np.float64)
+            scale = max(1.0, float(np.abs(r.pcm).max()))
+            assert np.abs(got - r.pcm.T).max() <= 2.0 ** -14 * scale, i
+        assert dec.stats().concealed_frames == concealed
