@@ -4,7 +4,8 @@ TEST INFRASTRUCTURE ONLY (tests/ imports it; nothing under mp3_b200/ does).  The
 describes slow playback (/root/reference/README.md:46) but has no code for it, so this is a numpy
 restatement of the textbook waveform-similarity overlap-add (Verhelst & Roelands 1993) with the
 parameters the product fixes: hop Hs = 512 / 256 / 128 by sample rate, frame 2 Hs, search radius Hs / 2,
-an int8 alignment signal, first-maximum tie break, periodic-Hann cross-fade.  float64 throughout.
+an int8 alignment signal, a coarse-to-fine search (every 4th offset on every 2nd sample, then +-3 in
+full), first-maximum tie break, periodic-Hann cross-fade.  float64 throughout.
 """
 import numpy as np
 
@@ -55,8 +56,12 @@ def wsola(x, s16, sample_rate, num, den):
             a = (m * hs * num) // den
             t = seg(c, p_prev + hs, N)
             region = seg(c, a - R, N + 2 * R)
-            scores = np.lib.stride_tricks.sliding_window_view(region, N) @ t
-            d = int(np.argmax(scores)) - R          # argmax returns the first maximum
+            win = np.lib.stride_tricks.sliding_window_view(region, N)   # win[c] = region[c : c + N], d = c - R
+            # coarse: every fourth candidate, every second sample; fine: +-3 around the winner, in full
+            coarse = win[::4, ::2] @ t[::2]
+            c0 = 4 * int(np.argmax(coarse))                              # argmax returns the first maximum
+            lo, hi = max(c0 - 3, 0), min(c0 + 3, 2 * R)
+            d = lo + int(np.argmax(win[lo: hi + 1] @ t)) - R
             offs[m] = d
             p = a + d
             y[m * hs: (m + 1) * hs] = (1.0 - w)[:, None] * seg(x, p_prev + hs, hs) + w[:, None] * seg(x, p, hs)
