@@ -620,10 +620,10 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     if (!nunits) return;
     // stage size: the average chunk plus slack, bounded so that at least one CTA fits an SM; chunks
     // that do not fit (high bitrates, VBR peaks) take the global-memory reader
-    static int configured = 0;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (l3_device_needs_setup(configured)) {
         cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = 1;
+        l3_device_setup_done(configured);
     }
     const uint64_t lut_bytes = ((uint64_t)T.huff_lut_len * sizeof(uint16_t) + 15) & ~15ull;
     // Chunk length and stage size: as many CTAs per SM as still leave every warp a few groups to pull.

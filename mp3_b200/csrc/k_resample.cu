@@ -172,13 +172,13 @@ void l3_launch_resample(const void *in, void *out, int pcm_format, const L3Resam
     const int span = (int)((255ll * M) / L) + taps + 2;
     const size_t smem = ((((size_t)L * taps + 3) & ~(size_t)3) + (size_t)span * 2) * sizeof(float);
     if (smem <= 160 * 1024) {
-        static bool configured = false;
-        if (!configured) {
+        static std::atomic<unsigned long long> configured{0};
+        if (l3_device_needs_setup(configured)) {
             cudaFuncSetAttribute(k_resample_tiled<int16_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             cudaFuncSetAttribute(k_resample_tiled<int16_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             cudaFuncSetAttribute(k_resample_tiled<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             cudaFuncSetAttribute(k_resample_tiled<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            configured = true;
+            l3_device_setup_done(configured);
         }
         // a few CTAs per stream, each walking many tiles, so that the table is loaded once per CTA
         const long long tiles = (max_out_n + 255) / 256;

@@ -148,11 +148,11 @@ void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_u
 {
     if (!ntiles) return;
     const size_t smem = (size_t)2 * K4_SLOTS * K4_FS * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> attr{0};
+    if (l3_device_needs_setup(attr)) {
         cudaFuncSetAttribute(k_synth<MP3B_PCM_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_synth<MP3B_PCM_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
+        l3_device_setup_done(attr);
     }
     if (pcm_format == MP3B_PCM_S16)
         k_synth<MP3B_PCM_S16><<<ntiles, K4_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, sb, pcm);

@@ -8,6 +8,22 @@
 #include "l3_defs.h"
 #include "l3_tables.h"
 
+/* cudaFuncSetAttribute is per device: launchers that raise a kernel's dynamic shared-memory limit do it
+ * once per device of the process (contexts on several GPUs may live in one process, on several threads). */
+#ifdef __cplusplus
+#include <atomic>
+/* usage: if (l3_device_needs_setup(mask)) { cudaFuncSetAttribute(...); l3_device_setup_done(mask); }
+ * (two threads may both run the set-up: harmless; neither launches before one of them has finished) */
+static inline unsigned long long l3_device_bit(void)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+}
+static inline bool l3_device_needs_setup(const std::atomic<unsigned long long> &mask) { return (mask.load() & l3_device_bit()) == 0; }
+static inline void l3_device_setup_done(std::atomic<unsigned long long> &mask) { mask.fetch_or(l3_device_bit()); }
+#endif
+
 /* Device-resident tables (pointers into one allocation owned by the context). */
 struct L3DevTables {
     const uint16_t *huff_lut;

@@ -305,3 +305,23 @@ def test_run_ahead_walk_back_to_back_calls(mp3b, batch):
                     assert np.array_equal(got[:ny], want[y]), (x, y, "head")
                     assert np.array_equal(got[ny:nx], want[x][ny:]), (x, y, "tail")
         dec.set_pcm_sink(0, 0)
+
+
+def test_two_contexts_on_two_threads(mp3b, batch):
+    """mp3_b200.multi.MultiDecoder: one context per entry, each driven by its own thread (here twice the
+    same GPU; with several GPUs the same code shards a batch) -- same PCM as one context."""
+    from mp3_b200 import multi
+    streams, _ = batch
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16) as dec:
+        dec.decode_batch(streams)
+        arena = dec.fetch_pcm()
+        want = [dec.stream_pcm(i, arena).copy() for i in range(len(streams))]
+    md = multi.MultiDecoder([0, 0], pcm_format=mp3b.PCM_S16)
+    try:
+        for _ in range(2):
+            got = md.decode(streams)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+    finally:
+        md.close()
