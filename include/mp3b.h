@@ -1,4 +1,4 @@
-/* mp3b.h -- C-ABI of libmp3b, the B200-native batched MPEG-1/2 Layer III decoder.
+/* mp3b.h -- C-ABI of libmp3b, the B200-native batched MPEG-1 / 2 / 2.5 Layer III (and Layer II) decoder.
  *
  * Reference interface replaced: NONE EXISTS.  The reference repository (lxm0851/mp3) exposes no
  * plugin / operator / FFI boundary and names no decoder library: /root/reference/README.md:1-84
@@ -80,7 +80,7 @@ typedef struct mp3b_stream_info {
     int32_t sample_rate;
     int32_t channels;
     int32_t lsf;            /* 0 = MPEG-1, 1 = MPEG-2 LSF or MPEG-2.5 (sample_rate tells which) */
-    int32_t reserved;
+    int32_t reserved;       /* (a Layer II stream reports the same fields; 1152 samples per frame at every rate) */
     int64_t frames;
     int64_t samples;        /* per channel */
     int64_t concealed_frames;
@@ -217,7 +217,7 @@ int mp3b_batch_stretch_offsets(mp3b_ctx *ctx, int stream_index, int32_t *dst, si
  * The frame walk of the host indexer (MP3B_INDEX_HOST) as a utility: sync search past ID3v2 / junk,
  * header validation, stream consistency, tag frame.  frames[i] = {byte offset of the header, main-data
  * bytes of the stream before this frame, the 4 header bytes big-endian, 0}.  Returns MP3B_OK,
- * MP3B_E_NOSYNC if no Layer III frame was found, MP3B_E_TRUNCATED if cap_frames was too small
+ * MP3B_E_NOSYNC if no Layer II / III frame was found, MP3B_E_TRUNCATED if cap_frames was too small
  * (*nframes then holds the number needed). */
 typedef struct mp3b_frame_rec { uint32_t offset, payload_offset, header, reserved; } mp3b_frame_rec;
 int mp3b_index_stream_host(const uint8_t *bytes, size_t n, mp3b_frame_rec *frames, size_t cap_frames,
