@@ -24,6 +24,14 @@ static const uint16_t l2_bitrate_kbps[2][16] = {
     {0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, 0},
 };
 
+/* bitrate_index -> kbit/s, Layer I.  [0] = MPEG-1, [1] = MPEG-2 LSF / 2.5.  A Layer I frame is 384 samples:
+ * (12 * bitrate / sample_rate + padding) slots of 4 bytes; 4-bit allocation per subband (0 = none, else
+ * allocation + 1 bits per sample, 15 is forbidden), one 6-bit scalefactor, 12 samples. */
+static const uint16_t l1_bitrate_kbps[2][16] = {
+    {0, 32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384, 416, 448, 0},
+    {0, 32, 48, 56, 64, 80, 96, 112, 128, 144, 160, 176, 192, 224, 256, 0},
+};
+
 /* Table 3-B.4: number of steps of the 17 quantisation classes, and bits per codeword: a negative value
  * is a grouped class (3, 5, 9 steps): ONE codeword of that many bits carries three consecutive samples,
  * least significant digit (base `steps`) first. */

@@ -341,7 +341,7 @@ static int bitrate_index(int lsf, int kbps)
 /* Upper bound on the stream size for a config (for caller allocation). */
 size_t l3gen_max_bytes(const l3gen_cfg *c)
 {
-    int lsf = c->sample_rate < 32000 && c->layer != 2;
+    int lsf = c->sample_rate < 32000 && c->layer != 2 && c->layer != 1;
     int kb = c->vbr_max_kbps > 0 ? c->vbr_max_kbps : c->bitrate_kbps;
     size_t fl = (size_t)(lsf ? 72 : 144) * kb * 1000 / c->sample_rate + 1;
     return fl * (size_t)c->nframes + 16 + (c->tag ? 1500 : 0);
@@ -511,10 +511,99 @@ static size_t l2gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
     return o;
 }
 
+/* Layer I: random 4-bit allocations (thinned to the frame's budget), scalefactors, sample codes. */
+static size_t l1gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
+{
+    rng_t rng;
+    rng.s = c->seed * 0x2545F4914F6CDD1Dull + 0x1357911;
+    int row = -1;
+    for (int i = 0; i < 9; i++)
+        if ((int)l3_sample_rate[i] == c->sample_rate) row = i;
+    if (row < 0 || c->nframes <= 0) return 0;
+    const int lsf = row >= 3, nch = c->mode == 3 ? 1 : 2;
+    int bri = 0;
+    for (int i = 1; i < 15; i++)
+        if (l1_bitrate_kbps[lsf][i] == c->bitrate_kbps) bri = i;
+    if (!bri) return 0;
+    size_t o = 0;
+    long pad_rest = 0;
+    for (int f = 0; f < c->nframes; f++) {
+        int pad = 0;
+        long num = 12L * c->bitrate_kbps * 1000;
+        pad_rest -= num % c->sample_rate;
+        if (pad_rest < 0) { pad = 1; pad_rest += c->sample_rate; }
+        const int flen = ((int)(num / c->sample_rate) + pad) * 4;
+        if (o + (size_t)flen > cap) return 0;
+        uint8_t *fr = out + o;
+        memset(fr, 0, (size_t)flen);
+        int mode_ext = c->mode == 1 ? rndi(&rng, 0, 3) : 0;
+        fr[0] = 0xFF;
+        fr[1] = (uint8_t)(0xE0 | ((row >= 6 ? 0 : lsf ? 2 : 3) << 3) | (3 << 1) | (c->crc ? 0 : 1));
+        fr[2] = (uint8_t)((bri << 4) | ((row % 3) << 2) | (pad << 1));
+        fr[3] = (uint8_t)((c->mode << 6) | (mode_ext << 4));
+        const int bound = (c->mode == 1 && nch == 2) ? (mode_ext + 1) * 4 : 32;
+        const int hdr_bits = 32 + (c->crc ? 16 : 0);
+        const long budget = ((long)flen * 8 - hdr_bits) * rndi(&rng, c->fill_lo_pct, c->fill_hi_pct) / 100;
+        int alloc[2][32];
+        for (int s = 0; s < 32; s++) {
+            for (int ch = 0; ch < (s < bound ? nch : 1); ch++) {
+                int a = rndi(&rng, 0, 9) < 3 ? 0 : rndi(&rng, 1, 14);
+                if (rndi(&rng, 0, 9) < 6 && a > 5) a = rndi(&rng, 1, 5);
+                alloc[ch][s] = a;
+            }
+            if (s >= bound) alloc[1][s] = alloc[0][s];
+            if (nch == 1) alloc[1][s] = 0;
+        }
+        for (;;) {
+            long bits = 0;
+            for (int s = 0; s < 32; s++) {
+                bits += 4 * (s < bound ? nch : 1);
+                for (int ch = 0; ch < nch; ch++)
+                    if (alloc[ch][s]) bits += 6;
+                for (int ch = 0; ch < (s < bound ? nch : 1); ch++)
+                    if (alloc[ch][s]) bits += 12L * (alloc[ch][s] + 1);
+            }
+            if (bits <= budget) break;
+            int s = rndi(&rng, 0, 31), ch = rndi(&rng, 0, nch - 1);
+            if (s >= bound) alloc[0][s] = alloc[1][s] = alloc[0][s] > 1 ? alloc[0][s] - 1 : 0;
+            else alloc[ch][s] = alloc[ch][s] > 1 ? alloc[ch][s] / 2 : 0;
+        }
+        bitw w = {fr, (size_t)flen * 8, (size_t)hdr_bits};
+        for (int s = 0; s < 32; s++)
+            for (int ch = 0; ch < (s < bound ? nch : 1); ch++) putbits(&w, (unsigned)alloc[ch][s], 4);
+        const size_t crc_end = w.pos;
+        const int i_lo = 3 + c->level_lo_db / 2 + 8, i_hi = 3 + c->level_hi_db / 2 + 8;
+        for (int s = 0; s < 32; s++)
+            for (int ch = 0; ch < nch; ch++)
+                if (alloc[ch][s]) {
+                    int v = rndi(&rng, i_lo, i_hi < 62 ? i_hi : 62);
+                    if (rndi(&rng, 0, 99) == 0) v = rndi(&rng, 0, 62);
+                    putbits(&w, (unsigned)v, 6);
+                }
+        for (int t = 0; t < 12; t++)
+            for (int s = 0; s < 32; s++)
+                for (int ch = 0; ch < (s < bound ? nch : 1); ch++)
+                    if (alloc[ch][s]) {
+                        int b = alloc[ch][s] + 1;
+                        putbits(&w, (unsigned)rndi(&rng, 0, (1 << b) - 2), b); /* the all-ones code is forbidden */
+                    }
+        if (c->crc) { /* header bits 16..31 and the bit allocation */
+            unsigned crc = 0xffff;
+            crc = crc16_update(crc, fr + 2, 16);
+            crc = crc16_update(crc, fr + 6, (int)(crc_end - 48));
+            fr[4] = (uint8_t)(crc >> 8);
+            fr[5] = (uint8_t)crc;
+        }
+        o += (size_t)flen;
+    }
+    return o;
+}
+
 /* Generate one stream.  Returns bytes written, or 0 on a bad config / small buffer. */
 size_t l3gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
 {
     if (c->layer == 2) return l2gen_stream(c, out, cap);
+    if (c->layer == 1) return l1gen_stream(c, out, cap);
     gen_t g;
     memset(&g, 0, sizeof g);
     g.cfg = c;

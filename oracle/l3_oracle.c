@@ -106,7 +106,7 @@ typedef struct {
     int frame_len;
     int side_len;
     int bitrate_idx, padding;
-    int layer;      /* 3 = Layer III, 2 = Layer II */
+    int layer;      /* 3 = Layer III, 2 = Layer II, 1 = Layer I */
 } l3o_hdr;
 
 typedef struct {
@@ -147,10 +147,10 @@ int l3o_parse_header(const uint8_t *p, l3o_hdr *h)
 {
     if (p[0] != 0xFF || (p[1] & 0xE0) != 0xE0) return 0;
     int ver = (p[1] >> 3) & 3;   /* 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5, 1 = reserved */
-    int layer = (p[1] >> 1) & 3; /* 1 = Layer III, 2 = Layer II, 3 = Layer I (not decoded) */
-    if (layer != 1 && layer != 2) return 0;
+    int layer = (p[1] >> 1) & 3; /* 1 = Layer III, 2 = Layer II, 3 = Layer I */
+    if (layer == 0) return 0;
     if (ver == 1) return 0;
-    h->layer = layer == 1 ? 3 : 2;
+    h->layer = 4 - layer;
     h->lsf = (ver != 3); /* MPEG-2.5 = the LSF syntax at half the MPEG-2 sample rates (rows 6..8) */
     h->crc = !(p[1] & 1);
     h->bitrate_idx = p[2] >> 4;
@@ -162,6 +162,11 @@ int l3o_parse_header(const uint8_t *p, l3o_hdr *h)
     h->nch = h->mode == 3 ? 1 : 2;
     h->sr_row = sri + (ver == 3 ? 0 : ver == 2 ? 3 : 6);
     int sr = (int)l3_sample_rate[h->sr_row];
+    if (h->layer == 1) { /* 384 samples per frame, slots of four bytes */
+        h->frame_len = (12 * l1_bitrate_kbps[h->lsf][h->bitrate_idx] * 1000 / sr + h->padding) * 4;
+        h->side_len = 0;
+        return 1;
+    }
     if (h->layer == 2) { /* 11172-3 2.4.3.1: 1152 samples per frame at every sample rate, no side info */
         h->frame_len = 144 * l2_bitrate_kbps[h->lsf][h->bitrate_idx] * 1000 / sr + h->padding;
         h->side_len = 0;
@@ -665,6 +670,44 @@ static void l2_decode_frame(const uint8_t *frame, const l3o_hdr *h, double sb[MA
         }
 }
 
+/* ---------------------------------------------------------------- Layer I (11172-3 2.4.1.5, 2.4.3.2)
+ * 4-bit allocation per subband and channel (joint stereo: shared above the bound), one 6-bit scalefactor
+ * per allocated subband, then 12 samples of allocation + 1 bits; same requantisation formula as Layer II
+ * with steps = 2^bits - 1.  Output: sb[ch][slot 0..11][subband]. */
+static void l1_decode_frame(const uint8_t *frame, const l3o_hdr *h, double sb[MAXCH][36][32])
+{
+    int nch = h->nch;
+    int bound = (h->mode == 1 && nch == 2) ? (h->mode_ext + 1) * 4 : 32;
+    bitr b = {frame, (size_t)h->frame_len * 8, (size_t)(4 + (h->crc ? 2 : 0)) * 8};
+    int alloc[MAXCH][32], scf[MAXCH][32];
+    memset(sb, 0, sizeof(double) * MAXCH * 36 * 32);
+    memset(alloc, 0, sizeof alloc);
+    memset(scf, 0, sizeof scf);
+    for (int s = 0; s < 32; s++) {
+        if (s < bound)
+            for (int ch = 0; ch < nch; ch++) alloc[ch][s] = (int)getbits(&b, 4);
+        else
+            alloc[0][s] = alloc[1][s] = (int)getbits(&b, 4);
+    }
+    for (int s = 0; s < 32; s++)
+        for (int ch = 0; ch < nch; ch++)
+            if (alloc[ch][s]) scf[ch][s] = (int)getbits(&b, 6);
+    for (int t = 0; t < 12; t++)
+        for (int s = 0; s < 32; s++) {
+            int nc = s < bound ? nch : 1;
+            for (int ch = 0; ch < nc; ch++) {
+                int a = alloc[ch][s];
+                if (!a) continue;
+                int bits = a + 1, steps = (1 << bits) - 1;
+                int code = (int)getbits(&b, bits);
+                double fr = (double)(2 * code + 1 - steps) / (double)steps;
+                if (a == 15) fr = 0.0; /* forbidden allocation: no defined value */
+                for (int c2 = ch; c2 < (s < bound ? ch + 1 : nch); c2++)
+                    sb[c2][t][s] = scf[c2][s] < 63 ? fr * pow(2.0, 1.0 - scf[c2][s] / 3.0) : 0.0;
+            }
+        }
+}
+
 /* 11172-3 2.4.3.1 error check: CRC-16, generator polynomial x^16 + x^15 + x^2 + 1, shift register preset
  * to all ones, fed bit by bit (MSB first) with header bits 16..31 and the side information.
  * Off by default (the word is skipped); l3o_set_verify_crc(1) makes a mismatch conceal the frame. */
@@ -725,7 +768,7 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
         fr[nfr].off = p;
         fr[nfr].h = h;
         fr[nfr].payload_off = arena_len;
-        size_t skip = h.layer == 2 ? (size_t)h.frame_len : (size_t)(4 + (h.crc ? 2 : 0) + h.side_len);
+        size_t skip = h.layer != 3 ? (size_t)h.frame_len : (size_t)(4 + (h.crc ? 2 : 0) + h.side_len);
         memcpy(arena + arena_len, buf + p + skip, h.frame_len - skip);
         arena_len += h.frame_len - skip;
         nfr++;
@@ -740,6 +783,10 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
     info->frames = (long)nfr;
     info->units = (long)nfr * ngr * nch;
     info->samples = (long)nfr * ngr * 576;
+    if (first.layer == 1) { /* 384 samples per frame: the units (576 samples) are granules of the slot sequence */
+        info->samples = (long)nfr * 384;
+        info->units = (long)((nfr * 12 + 17) / 18) * nch;
+    }
 
     double(*overlap)[576] = (double(*)[576])calloc(MAXCH, sizeof(double[576]));
     synth_state *syn = (synth_state *)calloc(MAXCH, sizeof(synth_state));
@@ -748,6 +795,25 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
     long unit = 0;
     for (size_t f = 0; f < nfr; f++) {
         const l3o_hdr *h = &fr[f].h;
+        if (h->layer == 1) { /* Layer I: 12 slots per frame into the same synthesis */
+            static __thread double l1sb[MAXCH][36][32];
+            l1_decode_frame(buf + fr[f].off, h, l1sb);
+            for (int t = 0; t < 12; t++) {
+                size_t slot = f * 12 + (size_t)t;
+                for (int ch = 0; ch < nch; ch++) {
+                    long u = (long)(slot / 18) * nch + ch;
+                    if (dump_sb) memcpy(dump_sb + u * 576 + (slot % 18) * 32, &l1sb[ch][t][0], 32 * sizeof(double));
+                    double out[32];
+                    synth_slot(&syn[ch], &l1sb[ch][t][0], out);
+                    if (pcm)
+                        for (int j = 0; j < 32; j++) {
+                            size_t n = slot * 32 + (size_t)j;
+                            if (n < cap_samples) pcm[n * nch + ch] = out[j];
+                        }
+                }
+            }
+            continue;
+        }
         if (h->layer == 2) { /* Layer II: subband samples straight from the frame, then the same synthesis */
             static __thread double l2sb[MAXCH][36][32];
             l2_decode_frame(buf + fr[f].off, h, l2sb);
@@ -920,7 +986,7 @@ int l3o_parse_tag(const uint8_t *buf, size_t len, l3o_tag *t)
         t->bytes = be32(f + 46);
         t->frames = be32(f + 50);
     }
-    long spf = (h.lsf && h.layer == 3) ? 576 : 1152, total = nfr * spf;
+    long spf = h.layer == 1 ? 384 : ((h.lsf && h.layer == 3) ? 576 : 1152), total = nfr * spf;
     long start = 0, count = total;
     if (t->kind) {
         start = spf;

@@ -50,6 +50,15 @@ L2 = {
     "l2_sparse": dict(layer=2, bitrate_kbps=256, nframes=8, seed=59, fill_lo_pct=5, fill_hi_pct=40),
 }
 
+# Layer I (MP1): 384-sample frames
+L1 = {
+    "l1_44k_384_stereo": dict(layer=1, bitrate_kbps=384, nframes=20, seed=61),
+    "l1_48k_256_joint": dict(layer=1, sample_rate=48000, bitrate_kbps=256, mode=1, nframes=20, seed=62),
+    "l1_32k_128_mono_crc": dict(layer=1, sample_rate=32000, bitrate_kbps=128, mode=3, crc=1, nframes=19, seed=63),
+    "l1_lsf22_96_stereo": dict(layer=1, sample_rate=22050, bitrate_kbps=96, nframes=20, seed=64),
+    "l1_lsf16_48_mono": dict(layer=1, sample_rate=16000, bitrate_kbps=48, mode=3, nframes=17, seed=65),
+}
+
 EXTRA = {
     "mixed_free_transitions": dict(blocks=1, mixed_pct=50, mixed_free=1, nframes=24, seed=31, mode=1),
     "lsf_intensity_full_range": dict(sample_rate=24000, bitrate_kbps=96, nframes=24, seed=32, blocks=1, mode=1),

@@ -4,6 +4,8 @@ import numpy as np
 _BR = [[0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 0],
        [0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, 0]]
 _BR2 = [[0, 32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 0], _BR[1]]  # Layer II
+_BR1 = [[0, 32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384, 416, 448, 0],
+        [0, 32, 48, 56, 64, 80, 96, 112, 128, 144, 160, 176, 192, 224, 256, 0]]                        # Layer I
 _SR = {3: [44100, 48000, 32000], 2: [22050, 24000, 16000], 0: [11025, 12000, 8000]}  # by version bits
 
 
@@ -12,14 +14,16 @@ def frame_len(h):
     if h[0] != 0xFF or (h[1] & 0xE0) != 0xE0:
         return 0
     ver = (h[1] >> 3) & 3
-    layer = (h[1] >> 1) & 3  # 1 = Layer III, 2 = Layer II
-    if ver == 1 or layer not in (1, 2):
+    layer = (h[1] >> 1) & 3  # 1 = Layer III, 2 = Layer II, 3 = Layer I
+    if ver == 1 or layer == 0:
         return 0
     lsf = 0 if ver == 3 else 1  # MPEG-2 and MPEG-2.5 share the LSF syntax
     bri, sri = h[2] >> 4, (h[2] >> 2) & 3
     if bri in (0, 15) or sri == 3:
         return 0
     pad = (h[2] >> 1) & 1
+    if layer == 3:
+        return (12 * _BR1[lsf][bri] * 1000 // _SR[ver][sri] + pad) * 4
     if layer == 2:
         return 144 * _BR2[lsf][bri] * 1000 // _SR[ver][sri] + pad
     return (72 if lsf else 144) * _BR[lsf][bri] * 1000 // _SR[ver][sri] + pad

@@ -49,3 +49,20 @@ def test_oracle_layer2_vs_mp2float(name, oracle_mod, synth_mod):
     rms, mx = l3util.iso_compliance(pcm, d.pcm)
     scale = max(1.0, float(np.abs(d.pcm).max()))
     assert rms < 5e-7 * scale and mx < 1e-5 * scale, (rms, mx)
+
+
+@pytest.mark.parametrize("name", sorted(cases.L1))
+def test_oracle_layer1_vs_mp1float(name, oracle_mod, synth_mod):
+    """Layer I: allocation, scalefactors, requantisation and the joint-stereo bound of the oracle against
+    FFmpeg's mp1float on generated streams (384 samples per frame)."""
+    s = synth_mod.make_stream(**cases.L1[name])
+    d = oracle_mod.decode(s, dumps=True)
+    frames = l3util.split_frames(s)
+    assert len(frames) == d.frames == cases.L1[name]["nframes"] and d.samples == 384 * d.frames
+    pcm, per = ffmpeg_ref.decode_frames(frames, d.channels, b"mp1float")
+    assert all(p is not None for p in per)
+    assert pcm.shape == d.pcm.shape
+    assert np.abs(d.pcm).max() > 1e-3, "degenerate (silent) test stream"
+    rms, mx = l3util.iso_compliance(pcm, d.pcm)
+    scale = max(1.0, float(np.abs(d.pcm).max()))
+    assert rms < 5e-7 * scale and mx < 1e-5 * scale, (rms, mx)
