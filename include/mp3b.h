@@ -1,4 +1,4 @@
-/* mp3b.h -- C-ABI of libmp3b, the B200-native batched MPEG-1 / 2 / 2.5 Layer III (and Layer II) decoder.
+/* mp3b.h -- C-ABI of libmp3b, the B200-native batched MPEG-1 / 2 / 2.5 Layer III (and Layer II / I) decoder.
  *
  * Reference interface replaced: NONE EXISTS.  The reference repository (lxm0851/mp3) exposes no
  * plugin / operator / FFI boundary and names no decoder library: /root/reference/README.md:1-84
@@ -33,9 +33,9 @@ extern "C" {
 typedef enum mp3b_status {
     MP3B_OK = 0,
     MP3B_E_INVAL = -1,       /* bad argument */
-    MP3B_E_NOSYNC = -2,      /* no Layer II / III frame found in a stream */
+    MP3B_E_NOSYNC = -2,      /* no MPEG audio frame found in a stream */
     MP3B_E_TRUNCATED = -3,   /* destination buffer too small */
-    MP3B_E_UNSUPPORTED = -4, /* Layer I, free format, unusable sample-rate pair */
+    MP3B_E_UNSUPPORTED = -4, /* free format, unusable sample-rate pair */
     MP3B_E_CUDA = -5,        /* CUDA runtime error; mp3b_last_error() has the text */
     MP3B_E_NOMEM = -6,
     MP3B_E_STATE = -7        /* call order violated (e.g. fetch before decode) */
@@ -146,7 +146,9 @@ int mp3b_flush(mp3b_ctx *ctx);
 
 int mp3b_batch_stream_info(const mp3b_ctx *ctx, int stream_index, mp3b_stream_info *info);
 int mp3b_batch_tag_info(const mp3b_ctx *ctx, int stream_index, mp3b_tag_info *info);
-/* Whole-batch PCM arena: streams back to back in input order, interleaved channels. */
+/* Whole-batch PCM arena: streams back to back in input order, interleaved channels; stream i starts at
+ * mp3b_stream_info.pcm_offset (a Layer I stream, whose frames are 384 samples, is padded to a multiple of
+ * 576 samples per channel). */
 int mp3b_batch_pcm_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems);
 /* Copy the whole arena (nelems elements of the context's pcm_format) to `dst`; async when dst is
  * pinned; call mp3b_sync() before reading it. */

@@ -236,7 +236,7 @@ void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRe
         f.stream = sidx;
         out->push_back(f);
         n++;
-        payload += h.layer == 2 ? 0u : (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
+        payload += h.layer != 3 ? 0u : (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len);
         p += (uint32_t)h.frame_len;
         end_off = p;
     }
@@ -252,7 +252,7 @@ void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRe
 // (what mpg123 / FFmpeg do with the same fields).
 void fill_tag_info(const L3StreamRec &r, const L3Hdr &h, mp3b_tag_info *tg)
 {
-    const int64_t spf = (int64_t)h.ngr * 576, total = (int64_t)r.nframes * spf;
+    const int64_t spf = h.spf, total = (int64_t)r.nframes * spf;
     tg->kind = (int32_t)(r.tag_kind & L3T_KIND_MASK);
     tg->has_lame = (r.tag_kind & L3T_LAME) ? 1 : 0;
     tg->frames = r.tag_frames;
@@ -390,7 +390,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     const int G = l3_synth_tile_granules();
     uint64_t frames = 0, grans = 0, units = 0, payload = 0, ntiles = 0;
     std::vector<uint32_t> sgran((size_t)nstreams, 0), sunit((size_t)nstreams, 0), sskip((size_t)nstreams, 0);
-    std::vector<uint8_t> sl2((size_t)nstreams, 0); // Layer II streams: decoded by k_layer2 + the synthesis kernel
+    std::vector<uint8_t> sl2((size_t)nstreams, 0); // Layer I / II streams: decoded by k_layer1/2 + the synthesis kernel
     bool any_l2 = false;
     for (int i = 0; i < nstreams; i++) {
         L3StreamRec &r = hs[i];
@@ -411,8 +411,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             const uint32_t skip = std::min(r.skip_frames, r.nframes);
             r.skip_frames = skip;
             inf.frames = r.nframes - skip;
-            inf.samples = (int64_t)(r.nframes - skip) * h.ngr * 576;
-            inf.pcm_offset += (int64_t)skip * h.ngr * h.nch * 576;
+            inf.samples = (int64_t)(r.nframes - skip) * h.spf;
+            inf.pcm_offset += (int64_t)skip * h.spf * h.nch;
             // the encoder's tag frame and the gapless window it implies: the tag frame itself is not audio,
             // the encoder delay plus the decoder's own 528 + 1 samples are cut from the head, the padding
             // from the tail (what mpg123 / FFmpeg do with the same fields)
@@ -425,13 +425,13 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
                 }
             }
             frames += r.nframes;
-            uint64_t g = (uint64_t)r.nframes * h.ngr;
+            uint64_t g = l3_stream_granules(&h, r.nframes);
             sgran[(size_t)i] = (uint32_t)g;
             sunit[(size_t)i] = (uint32_t)(g * h.nch);
-            sskip[(size_t)i] = skip * (uint32_t)h.ngr;
-            sl2[(size_t)i] = h.layer == 2;
-            any_l2 = any_l2 || h.layer == 2;
-            if (h.layer != 2) ntiles += (g + G - 1) / G;
+            sskip[(size_t)i] = (uint32_t)((uint64_t)skip * h.spf / 576); // whole granules before the first new sample
+            sl2[(size_t)i] = h.layer != 3;
+            any_l2 = any_l2 || h.layer != 3;
+            if (h.layer == 3) ntiles += (g + G - 1) / G;
             grans += g;
             units += g * h.nch;
             payload = align_up(payload + r.payload_len, 16);
@@ -648,6 +648,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
                     t2[k++] = make_uint2(hs[i].gran_base + a, std::min<uint32_t>((uint32_t)G, sgran[(size_t)i] - a));
         float *sb2 = ctx->d_sb2.as<float>() - (size_t)u_min * 576;
         l3_launch_layer2(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
+        l3_launch_layer1(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
         if (nt2) {
             CK(cudaMemcpyAsync(ctx->d_tiles2.p, t2, sizeof(uint2) * nt2, cudaMemcpyHostToDevice, st));
             l3_launch_synth(ctx->d_tiles2.as<uint2>(), (uint32_t)nt2, dg, sb2, pcm_dev, ctx->opts.pcm_format, st);
@@ -849,7 +850,7 @@ int mp3b_index_stream_host(const uint8_t *bytes, size_t n, mp3b_frame_rec *frame
         info->channels = h.nch;
         info->lsf = h.lsf;
         info->frames = (int64_t)out.size();
-        info->samples = (int64_t)out.size() * h.ngr * 576;
+        info->samples = (int64_t)out.size() * h.spf;
     }
     if (tag) fill_tag_info(r, h, tag);
     if (out.size() > cap_frames || (!frames && cap_frames)) return MP3B_E_TRUNCATED;
@@ -1230,7 +1231,7 @@ static int finalize_stream_batch(mp3b_ctx *ctx)
             l3_parse_hdr(r.first_hdr, &h);
             // W frames = the two granules the back end replays; `need` = the reach of main_data_begin
             // (Layer II frames are self-contained)
-            const uint32_t nfr = r.nframes, W = h.ngr == 1 ? 2u : 1u, need = h.layer == 2 ? 0u : (h.lsf ? 255u : 511u);
+            const uint32_t nfr = r.nframes, W = h.spf < 1152 ? 2u : 1u, need = h.layer != 3 ? 0u : (h.lsf ? 255u : 511u);
             const L3FrameRec *f = fr + r.frame_base;
             const uint32_t wf = nfr > W ? nfr - W : 0; // first frame the back end will replay
             uint32_t idx = wf;

@@ -41,12 +41,13 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     // the length is the previous base length plus this frame's padding bit -- no header arithmetic.
     const uint32_t GEOM = 0xFFFFFCC0u;
     uint32_t prev_w = 0, base_len = 0, overhead = 0;
-    bool l2 = false; // Layer II frames carry no main data for the arena
+    bool l2 = false; // Layer I / II frames carry no main data for the arena
+    uint32_t pad_unit = 1; // bytes a set padding bit adds: one slot = 1 byte, or 4 bytes in Layer I
     while (p + 4 <= len) {
         L3Hdr h;
         uint32_t w = l3_load_be32(buf + p), flen;
         if (n && ((w ^ prev_w) & GEOM) == 0) {
-            flen = base_len + ((w >> 9) & 1u);
+            flen = base_len + ((w >> 9) & 1u) * pad_unit;
             if (p + flen > len) {
                 if (streaming) break; // the rest of this frame has not arrived yet
                 p++;
@@ -61,9 +62,10 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
             }
             flen = (uint32_t)h.frame_len;
             prev_w = w;
-            base_len = flen - ((w >> 9) & 1u);
+            pad_unit = h.layer == 1 ? 4u : 1u;
+            base_len = flen - ((w >> 9) & 1u) * pad_unit;
             overhead = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len;
-            l2 = h.layer == 2;
+            l2 = h.layer != 3;
             if (n == 0) {
                 first = first ? first : w;
                 first_off = p;
@@ -186,6 +188,24 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
     L3Hdr h;
     l3_parse_hdr(fr.hdr, &h);
     const uint32_t fi = f - sr.frame_base; /* frame index inside its stream */
+    if (h.layer == 1) {
+        // Layer I: 12 slots per frame; the stream's granules are 18-slot pieces of its slot sequence, and the
+        // frame that holds a granule's first slot writes its placeholder units
+        const uint32_t g = (12u * fi + 17u) / 18u; // first granule starting at or after this frame's first slot
+        if (18u * g < 12u * fi + 12u) {
+            const uint32_t u0 = sr.unit_base + g * (uint32_t)h.nch;
+            L3UnitDesc d;
+            memset(&d, 0, sizeof d);
+            d.hdr = (uint8_t)((h.sr_row << L3H_SR_SHIFT) | (h.nch == 2 ? L3H_STEREO : 0) | (h.lsf ? L3H_LSF : 0));
+            d.stream = fr.stream;
+            for (int ch = 0; ch < h.nch; ch++) {
+                d.pos = (uint8_t)((ch ? L3P_CH : 0) | (g == 0 ? L3P_FIRST : 0));
+                units[u0 + ch] = d;
+            }
+            gran_unit0[sr.gran_base + g] = u0 | (h.nch == 2 ? L3G_STEREO : 0u) | (g == 0 ? L3G_FIRST : 0u);
+        }
+        return;
+    }
     if (h.layer == 2) {
         // Layer II: no side info; its units exist (two granules x channels per frame, the PCM layout is the
         // same) but stay invalid for the Huffman / back-end kernels: k_layer2 + the synthesis kernel fill them
@@ -329,7 +349,7 @@ k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ 
             L3Hdr h;
             l3_parse_hdr(fr.hdr, &h);
             const uint32_t skip = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len;
-            n = h.layer == 2 ? 0u : (uint32_t)h.frame_len - skip;
+            n = h.layer != 3 ? 0u : (uint32_t)h.frame_len - skip;
             s_src[threadIdx.x] = raw + sr.raw_off + fr.rel_off + skip;
             s_dst[threadIdx.x] = arena + sr.payload_base + fr.payload_off;
         }

@@ -160,6 +160,78 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     }
 }
 
+// Layer I (11172-3 2.4.1.5 / 2.4.3.2): 4-bit allocations, one scalefactor, 12 samples of allocation + 1
+// bits per subband.  A frame is 12 slots; a stream's slots are cut into 18-slot granules for the synthesis
+// kernel, so slot s of frame f goes to granule (12 f + s) / 18.  The stream's last frame also zeroes the
+// unused slots of the last granule.
+__global__ void __launch_bounds__(L2_WARPS * 32)
+k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams, const L3FrameRec *__restrict__ frames,
+         uint32_t nframes, float *__restrict__ sb_out)
+{
+    __shared__ __align__(4) uint8_t s_frame[L2_WARPS][L2_MAX_FRAME + 12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * L2_WARPS + warp;
+    if (f >= nframes) return;
+    const L3FrameRec fr = frames[f];
+    L3Hdr h;
+    if (!l3_parse_hdr(fr.hdr, &h) || h.layer != 1) return;
+    const L3StreamRec sr = streams[fr.stream];
+    const uint8_t *src = raw + sr.raw_off + fr.rel_off;
+    uint8_t *fb = s_frame[warp];
+    const int flen = min(h.frame_len, L2_MAX_FRAME);
+    for (int i = lane; i < flen + 8; i += 32) fb[i] = i < flen ? src[i] : (uint8_t)0;
+    __syncwarp();
+
+    const int nch = h.nch;
+    const int bound = (h.mode == 1 && nch == 2) ? (h.mode_ext + 1) * 4 : 32;
+    const bool sep = lane < bound;
+    const int ncode = sep ? nch : 1;
+    uint32_t pos = (uint32_t)(4 + (h.crc ? 2 : 0)) * 8;
+    int tot;
+    int off = warp_excl_scan(4 * ncode, lane, &tot);
+    int alloc[2];
+    alloc[0] = (int)l2_bits(fb, pos + off, 4);
+    alloc[1] = nch == 2 ? (sep ? (int)l2_bits(fb, pos + off + 4, 4) : alloc[0]) : 0;
+    pos += (uint32_t)tot;
+    const int na = (alloc[0] ? 1 : 0) + (alloc[1] ? 1 : 0);
+    off = warp_excl_scan(6 * na, lane, &tot);
+    float scf[2] = {0.f, 0.f};
+    {
+        uint32_t p = pos + off;
+        for (int ch = 0; ch < nch; ch++)
+            if (alloc[ch]) { scf[ch] = c_l2_scf[l2_bits(fb, p, 6)]; p += 6; }
+    }
+    pos += (uint32_t)tot;
+    int cb[2];
+    for (int k = 0; k < 2; k++) cb[k] = (k < ncode && alloc[k]) ? alloc[k] + 1 : 0;
+    off = warp_excl_scan(cb[0] + cb[1], lane, &tot);
+    const uint32_t fi = f - sr.frame_base;
+    for (int t = 0; t < 12; t++) {
+        uint32_t p = pos + (uint32_t)(t * tot + off);
+        float v[2] = {0.f, 0.f};
+        for (int k = 0; k < ncode; k++) {
+            if (!cb[k]) continue;
+            const int steps = (1 << cb[k]) - 1;
+            const int code = (int)l2_bits(fb, p, cb[k]);
+            p += (uint32_t)cb[k];
+            const float fr3 = alloc[k] == 15 ? 0.f : (float)(2 * code + 1 - steps) / (float)steps;
+            if (sep) v[k] = fr3 * scf[k];
+            else { v[0] = fr3 * scf[0]; v[1] = fr3 * scf[1]; }
+        }
+        const uint32_t slot = fi * 12u + (uint32_t)t;
+        for (int ch = 0; ch < nch; ch++) {
+            const size_t u = (size_t)sr.unit_base + (size_t)(slot / 18u) * nch + ch;
+            sb_out[u * 576 + (size_t)(slot % 18u) * 32 + lane] = v[ch];
+        }
+    }
+    if (fi + 1 == sr.nframes) // the tail of the last granule
+        for (uint32_t slot = sr.nframes * 12u; slot % 18u; slot++)
+            for (int ch = 0; ch < nch; ch++) {
+                const size_t u = (size_t)sr.unit_base + (size_t)(slot / 18u) * nch + ch;
+                sb_out[u * 576 + (size_t)(slot % 18u) * 32 + lane] = 0.f;
+            }
+}
+
 } // namespace
 
 void l3_layer2_init(void)
@@ -179,4 +251,11 @@ void l3_launch_layer2(const uint8_t *raw, const L3StreamRec *streams, const L3Fr
 {
     if (!nframes) return;
     k_layer2<<<(nframes + L2_WARPS - 1) / L2_WARPS, L2_WARPS * 32, 0, st>>>(raw, streams, frames, nframes, sb_out);
+}
+
+void l3_launch_layer1(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames, uint32_t nframes,
+                      float *sb_out, cudaStream_t st)
+{
+    if (!nframes) return;
+    k_layer1<<<(nframes + L2_WARPS - 1) / L2_WARPS, L2_WARPS * 32, 0, st>>>(raw, streams, frames, nframes, sb_out);
 }

@@ -80,6 +80,8 @@ void l3_launch_overlap_range(const L3UnitDesc *units, uint32_t u_lo, uint32_t nu
 void l3_layer2_init(void);
 void l3_launch_layer2(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames, uint32_t nframes,
                       float *sb_out, cudaStream_t st);
+void l3_launch_layer1(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames, uint32_t nframes,
+                      float *sb_out, cudaStream_t st);
 
 /* K4: polyphase synthesis (a11) */
 void l3_synth_init(void);

@@ -99,8 +99,10 @@ typedef struct __attribute__((aligned(16))) L3UnitDesc {
 
 typedef struct L3Hdr {
     int lsf, sr_row, nch, mode, mode_ext, crc, frame_len, side_len, ngr;
-    int layer; /* 3, or 2: Layer II frames carry no side info / main data (side_len = 0, two granules) */
+    int layer; /* 3, 2 or 1: Layer I / II frames carry no side info / main data (side_len = 0) */
     int kbps;
+    int spf;   /* samples per frame: 1152 / 576 (= ngr granules), or 384 for Layer I (ngr = 0: its granules are
+                  18-slot pieces of the stream's slot sequence, see l3_stream_granules) */
 } L3Hdr;
 
 L3_HD int l3_kbps(int lsf, int idx)
@@ -133,10 +135,10 @@ L3_HD int l3_parse_hdr(uint32_t w, L3Hdr *h)
 {
     if ((w & 0xFFE00000u) != 0xFFE00000u) return 0;
     int ver = (w >> 19) & 3, layer = (w >> 17) & 3;
-    if ((layer != 1 && layer != 2) || ver == 1) return 0; /* 01 = Layer III, 10 = Layer II; Layer I is not decoded */
+    if (layer == 0 || ver == 1) return 0; /* 01 = Layer III, 10 = Layer II, 11 = Layer I */
     int bri = (w >> 12) & 15, sri = (w >> 10) & 3;
     if (bri == 0 || bri == 15 || sri == 3) return 0;
-    h->layer = layer == 1 ? 3 : 2;
+    h->layer = 4 - layer;
     h->lsf = ver != 3;
     h->crc = !((w >> 16) & 1);
     h->mode = (w >> 6) & 3;
@@ -145,19 +147,37 @@ L3_HD int l3_parse_hdr(uint32_t w, L3Hdr *h)
     h->sr_row = sri + (ver == 3 ? 0 : ver == 2 ? 3 : 6);
     h->ngr = h->lsf ? 1 : 2;
     int pad = (w >> 9) & 1;
+    if (h->layer == 1) { /* 384 samples per frame, slots of four bytes; bitrates 32 .. 448 (MPEG-1) in steps of 32 */
+        /* LSF: kbit/s / 8 for bitrate_index 1..8 and 9..14: 32 48 56 64 80 96 112 128 | 144 160 176 192 224 256 */
+        const unsigned long long lo = 0x100E0C0A08070604ull, hi = 0x0000201C18161412ull;
+        h->kbps = h->lsf ? 8 * (int)((bri <= 8 ? (lo >> (8 * (bri - 1))) : (hi >> (8 * (bri - 9)))) & 0xff) : 32 * bri;
+        h->ngr = 0;
+        h->spf = 384;
+        h->frame_len = (12000 * h->kbps / l3_sr_hz(h->sr_row) + pad) * 4;
+        h->side_len = 0;
+        return 1;
+    }
     if (h->layer == 2) { /* 1152 samples per frame at every rate; MPEG-1 has its own Layer II bitrate table */
         /* kbit/s / 8 for bitrate_index 1..8 and 9..14: 32 48 56 64 80 96 112 128 | 160 192 224 256 320 384 */
         const unsigned long long lo = 0x100E0C0A08070604ull, hi = 0x00003028201C1814ull;
         h->kbps = h->lsf ? l3_kbps(1, bri) : 8 * (int)((bri <= 8 ? (lo >> (8 * (bri - 1))) : (hi >> (8 * (bri - 9)))) & 0xff);
         h->ngr = 2;
+        h->spf = 1152;
         h->frame_len = 144000 * h->kbps / l3_sr_hz(h->sr_row) + pad;
         h->side_len = 0;
         return 1;
     }
     h->kbps = l3_kbps(h->lsf, bri);
+    h->spf = h->ngr * 576;
     h->frame_len = (h->lsf ? 72000 : 144000) * h->kbps / l3_sr_hz(h->sr_row) + pad;
     h->side_len = h->lsf ? (h->nch == 1 ? 9 : 17) : (h->nch == 1 ? 17 : 32);
     return 1;
+}
+
+/* Granules (576 samples = 18 slots per channel) that n frames of this kind occupy. */
+L3_HD uint64_t l3_stream_granules(const L3Hdr *h, uint64_t nframes)
+{
+    return h->layer == 1 ? (nframes * 12 + 17) / 18 : nframes * (uint64_t)h->ngr;
 }
 
 /* Two headers belong to the same stream when version, sample rate and channel count agree. */

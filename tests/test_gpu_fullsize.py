@@ -119,11 +119,11 @@ def test_corrupted_streams_never_fault(mp3b, synth_mod):
             arena = dec.fetch_pcm()
             assert np.all(np.isfinite(arena))
             tot = 0
-            for i in range(len(bad)):
+            for i in range(len(bad)):  # streams back to back (a Layer I stream is padded to a whole granule)
                 inf = dec.stream_info(i)
-                assert inf.pcm_offset == tot
-                tot += inf.samples * inf.channels
-            assert tot == arena.size
+                assert tot <= inf.pcm_offset < tot + 576 * 2 or inf.frames == 0
+                tot = max(tot, inf.pcm_offset + inf.samples * inf.channels)
+            assert tot <= arena.size < tot + 576 * 2
         good = synth_mod.make_stream(nframes=8, seed=3)
         dec.decode_batch([good])               # the context is still healthy afterwards
         assert dec.stream_info(0).frames == 8
@@ -137,7 +137,8 @@ def test_damaged_streams_decode_like_the_oracle(mp3b, synth_mod, oracle_mod):
     rng = np.random.default_rng(99)
     base = synth_mod.make_workload("cfg3", 5, 24) + synth_mod.make_workload("cfg4", 9, 24) + [
         synth_mod.make_stream(layer=2, bitrate_kbps=192, nframes=10, seed=5),
-        synth_mod.make_stream(layer=2, sample_rate=24000, bitrate_kbps=64, mode=1, nframes=10, seed=6)]
+        synth_mod.make_stream(layer=2, sample_rate=24000, bitrate_kbps=64, mode=1, nframes=10, seed=6),
+        synth_mod.make_stream(layer=1, bitrate_kbps=256, mode=1, nframes=20, seed=7)]
     bad = []
     for s in base:
         a = np.frombuffer(s, np.uint8).copy()

@@ -1,5 +1,6 @@
-"""GPU: Layer II (MP2) streams through the C-ABI against the oracle (which FFmpeg's mp2float pins on the
-CPU side, tests/test_oracle_vs_ffmpeg.py), alone and mixed with Layer III streams in one batch."""
+"""GPU: Layer II (MP2) and Layer I (MP1) streams through the C-ABI against the oracle (which FFmpeg's
+mp2float / mp1float pin on the CPU side, tests/test_oracle_vs_ffmpeg.py), mixed with Layer III streams in
+one batch."""
 import numpy as np
 import pytest
 
@@ -8,12 +9,14 @@ import l3util
 
 pytestmark = pytest.mark.gpu
 
-NAMES = sorted(cases.L2)
+ALL = dict(cases.L2)
+ALL.update(cases.L1)
+NAMES = sorted(ALL)
 
 
 @pytest.fixture(scope="module")
 def batch(synth_mod, oracle_mod):
-    streams = [synth_mod.make_stream(**cases.L2[n]) for n in NAMES]
+    streams = [synth_mod.make_stream(**ALL[n]) for n in NAMES]
     # Layer III neighbours in the same batch: the two paths share the unit / PCM layout
     streams.insert(2, synth_mod.make_stream(**cases.FF["cfg3_320k_joint"]))
     streams.append(synth_mod.make_stream(**cases.FF["lsf16_mono"]))
@@ -61,7 +64,7 @@ def test_layer2_incremental_stream(batch):
     import mp3_b200 as m
     streams, refs = batch
     rng = np.random.default_rng(3)
-    for k in (0, 3, 9):
+    for k in (0, 1, 4, 5, 12):  # Layer I (384-sample frames), Layer II, and a Layer III neighbour
         s, r = streams[k], refs[k]
         with m.Decoder(device=0, pcm_format=m.PCM_F32) as dec:
             dec.decode_batch([s])
