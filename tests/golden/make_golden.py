@@ -40,6 +40,18 @@ def main():
         assert all(p is not None for p in per)
         out[name + ".mp3"] = np.frombuffer(s, np.uint8)
         out[name + ".pcm"] = pcm.astype(np.float32)
+    # Layer II / Layer I: FFmpeg's mp2float / mp1float
+    for group, codec in ((cases.L2, b"mp2float"), (cases.L1, b"mp1float")):
+        for name in sorted(group)[:3]:
+            kw = dict(group[name])
+            kw["nframes"] = 6
+            s = synth.make_stream(**kw)
+            frames = l3util.split_frames(s)
+            nch = 1 if kw.get("mode", 0) == 3 else 2
+            pcm, per = ffmpeg_ref.decode_frames(frames, nch, codec)
+            assert all(p is not None for p in per)
+            out[name + ".mp3"] = np.frombuffer(s, np.uint8)
+            out[name + ".pcm"] = pcm.astype(np.float32)
     # the survey's known-answer frames
     kat0 = bytes.fromhex("fffb9000") + bytes(413)
     side = bytes.fromhex("0000000401690021080000000D20042100000001A40084200000003480108400")
