@@ -200,6 +200,14 @@ int mp3b_batch_fetch_resampled(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int
 int mp3b_resample_filter(int in_rate, int out_rate, float *taps, size_t cap, size_t *ncoef, int *L, int *M,
                          int *taps_per_phase);
 
+/* ---- planar copy of the decoded batch -------------------------------------------------------------
+ * The decoder's arena is interleaved; this makes a second arena in which stream i (same pcm_offset, same
+ * format) is laid out [channel][sample]: channel c of stream i starts at pcm_offset + c * samples.
+ * Asynchronous on the context's stream; valid until the next decode or planar call. */
+int mp3b_batch_planar(mp3b_ctx *ctx);
+int mp3b_batch_planar_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems);
+int mp3b_batch_fetch_planar(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got);
+
 /* ---- slow / fast playback of the decoded batch without pitch change -----------------------------
  * Waveform-similarity overlap-add (WSOLA): every stream of the last batch (its gapless window when
  * opts.gapless is set) is stretched to floor(samples * den / num) frames, speed = num / den (1/2 = half

@@ -69,7 +69,8 @@ EXPORTS = [
     "mp3b_debug_stage", "mp3b_index_stream_host", "mp3b_batch_resample", "mp3b_batch_resampled_info",
     "mp3b_batch_resampled_device_ptr", "mp3b_batch_fetch_resampled", "mp3b_resample_filter",
     "mp3b_batch_time_stretch", "mp3b_batch_stretched_info", "mp3b_batch_stretched_device_ptr",
-    "mp3b_batch_fetch_stretched", "mp3b_batch_stretch_offsets",
+    "mp3b_batch_fetch_stretched", "mp3b_batch_stretch_offsets", "mp3b_batch_planar",
+    "mp3b_batch_planar_device_ptr", "mp3b_batch_fetch_planar",
 ]
 
 _lib = None
@@ -372,6 +373,22 @@ class Decoder:
             self._ck(L.mp3b_batch_resampled_info(self.ctx, i, ctypes.byref(o), ctypes.byref(c)))
             where.append((o.value, c.value))
         return out, where
+
+    def planar(self):
+        """Planar copy of the last batch: returns the flat arena in which stream i, channel c starts at
+        pcm_offset + c * samples."""
+        L = self.L
+        L.mp3b_batch_planar.argtypes = [ctypes.c_void_p]
+        L.mp3b_batch_fetch_planar.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_uint64)]
+        self._ck(L.mp3b_batch_planar(self.ctx))
+        _, n = self.pcm_device()
+        out = np.zeros(n, np.int16 if self.pcm_format == PCM_S16 else np.float32)
+        got = ctypes.c_uint64()
+        self._ck(L.mp3b_batch_fetch_planar(self.ctx, out.ctypes.data_as(ctypes.c_void_p), out.size, HOST,
+                                           ctypes.byref(got)))
+        self.sync()
+        return out
 
     def time_stretch(self, num, den):
         """WSOLA time-scale modification of the last batch: speed = num / den (1, 2 = half speed); async."""

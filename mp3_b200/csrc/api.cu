@@ -131,6 +131,9 @@ struct mp3b_ctx {
     std::vector<L3ResampleJob> rs_jobs; // per stream (in_n = 0 for streams without audio)
     uint64_t rs_elems = 0;
     bool have_rs = false;
+    // planar copy of the last batch
+    DevBuf d_pl, d_pl_jobs;
+    bool have_pl = false;
     // time-stretched copy of the last batch
     DevBuf d_ts, d_ts_jobs, d_ts_off;
     std::vector<L3StretchJob> ts_jobs;
@@ -316,6 +319,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     ctx->have_batch = false;
     ctx->have_rs = false;
     ctx->have_ts = false;
+    ctx->have_pl = false;
     ctx->infos.assign((size_t)nstreams, mp3b_stream_info{});
     ctx->tags.assign((size_t)nstreams, mp3b_tag_info{});
     ctx->stats = mp3b_stats{};
@@ -765,7 +769,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_tiles2, &ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -952,6 +956,67 @@ int mp3b_batch_tag_info(const mp3b_ctx *ctx, int i, mp3b_tag_info *info)
     if (!ctx->have_batch) return MP3B_E_STATE;
     if (i < 0 || (size_t)i >= ctx->tags.size()) return MP3B_E_INVAL;
     *info = ctx->tags[(size_t)i];
+    return MP3B_OK;
+}
+
+int mp3b_batch_planar(mp3b_ctx *ctx)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    ctx->have_pl = false;
+    std::vector<L3PlanarJob> jl;
+    std::vector<uint32_t> tjob, tfirst;
+    for (size_t i = 0; i < ctx->infos.size(); i++) {
+        const mp3b_stream_info &inf = ctx->infos[i];
+        if (!inf.frames || inf.samples <= 0) continue;
+        L3PlanarJob jb{};
+        jb.off = inf.pcm_offset;
+        jb.samples = inf.samples;
+        jb.channels = inf.channels;
+        tfirst.push_back((uint32_t)tjob.size());
+        for (int64_t t = 0; t < (inf.samples + 2047) / 2048; t++) tjob.push_back((uint32_t)jl.size());
+        jl.push_back(jb);
+    }
+    CK(ctx->d_pl.ensure(std::max<uint64_t>(ctx->pcm_elems * elem, 16)));
+    const size_t o1 = align_up(jl.size() * sizeof(L3PlanarJob), 256), o2 = o1 + align_up(tjob.size() * 4, 256);
+    CK(ctx->d_pl_jobs.ensure(std::max<size_t>(o2 + tfirst.size() * 4, 16)));
+    if (!jl.empty()) {
+        char *b = ctx->d_pl_jobs.as<char>();
+        CK(cudaMemcpyAsync(b, jl.data(), jl.size() * sizeof(L3PlanarJob), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b + o1, tjob.data(), tjob.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b + o2, tfirst.data(), tfirst.size() * 4, cudaMemcpyHostToDevice, st));
+        l3_launch_planar(ctx->pcm().p, ctx->d_pl.p, ctx->opts.pcm_format, reinterpret_cast<const L3PlanarJob *>(b),
+                         reinterpret_cast<const uint32_t *>(b + o1), reinterpret_cast<const uint32_t *>(b + o2),
+                         (uint32_t)tjob.size(), st);
+    }
+    CK(cudaGetLastError());
+    ctx->have_pl = true;
+    return MP3B_OK;
+}
+
+int mp3b_batch_planar_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems)
+{
+    if (!ctx || !ptr) return MP3B_E_INVAL;
+    if (!ctx->have_pl) return MP3B_E_STATE;
+    *ptr = ctx->d_pl.p;
+    if (nelems) *nelems = ctx->pcm_elems;
+    return MP3B_OK;
+}
+
+int mp3b_batch_fetch_planar(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int where, uint64_t *got)
+{
+    if (!ctx || (!dst && cap_elems)) return MP3B_E_INVAL;
+    if (!ctx->have_pl) return MP3B_E_STATE;
+    if (cap_elems < ctx->pcm_elems) return MP3B_E_TRUNCATED;
+    const int elem = ctx->opts.pcm_format == MP3B_PCM_S16 ? 2 : 4;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->pcm_elems)
+        CK(cudaMemcpyAsync(dst, ctx->d_pl.p, ctx->pcm_elems * elem,
+                           where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (got) *got = ctx->pcm_elems;
     return MP3B_OK;
 }
 

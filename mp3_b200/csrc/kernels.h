@@ -107,6 +107,14 @@ struct L3ResampleJob {
     long long in_off, in_n, out_off, out_n;
     int channels, pad;
 };
+/* Planar copy of the PCM arena (k_planar.cu): one job per stream with audio, tiles of 2048 frames. */
+struct L3PlanarJob {
+    long long off, samples; /* element offset of the stream in both arenas; frames */
+    int channels, pad;
+};
+void l3_launch_planar(const void *in, void *out, int pcm_format, const L3PlanarJob *jobs, const uint32_t *tile_job,
+                      const uint32_t *tile_first, uint32_t ntiles, cudaStream_t st);
+
 /* Time-scale modification (k_stretch.cu).  One job (and one CTA) per stream. */
 struct L3StretchJob {
     long long in_off, in_n, out_off, out_n;

@@ -41,3 +41,19 @@ for num, den in ((1, 2), (3, 4)):
     ms = e0.elapsed_time(e1) / 3
     audio = 1024 * 383 * 1152 / 44100.0
     print("stretch speed %d/%d: %.3f ms per batch, %.2e x realtime (of input audio)" % (num, den, ms, audio / (ms * 1e-3)))
+
+import ctypes  # noqa: E402
+L = dec.L
+L.mp3b_batch_planar.argtypes = [ctypes.c_void_p]
+for _ in range(2):
+    L.mp3b_batch_planar(dec.ctx)
+dec.sync()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(st)
+for _ in range(10):
+    L.mp3b_batch_planar(dec.ctx)
+e1.record(st)
+dec.sync()
+ms = e0.elapsed_time(e1) / 10
+nbytes = 2 * 1024 * 383 * 1152 * 2 * 2  # read + write of the s16 stereo arena
+print("planar: %.3f ms per batch, %.0f GB/s of HBM traffic (read + write)" % (ms, nbytes / (ms * 1e-3) / 1e9))
