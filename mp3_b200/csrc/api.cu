@@ -438,7 +438,9 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             if (h.layer == 3) ntiles += (g + G - 1) / G;
             grans += g;
             units += g * h.nch;
-            payload = align_up(payload + r.payload_len, 16);
+            // 8..23 bytes of zero padding follow each stream's main data (k_payload_copy writes it): the last
+            // Huffman code of a damaged stream may read a few bits past the stream's end, and must see zeros
+            payload = align_up(payload + r.payload_len + L3_PAYLOAD_PAD, 16);
         }
     }
     if (units > L3G_UNIT_MASK || frames > 0xFFFFFFF0ull) { ctx->err = "batch too large"; return MP3B_E_INVAL; }

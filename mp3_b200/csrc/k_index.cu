@@ -323,6 +323,19 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
         gran_unit0[g0 + gr] = (u0 + (uint32_t)(gr * nch)) | (nch == 2 ? L3G_STEREO : 0u) |
                               ((fi == 0 && gr == 0) ? L3G_FIRST : 0u);
     }
+    // A frame's main data ends inside the frame (11172-3 2.4.2.7: the next frame's main_data_begin cannot
+    // point forward).  Side info that claims more bits than that is damaged: conceal the frame, so that no
+    // unit reads beyond its own stream's data.
+    const uint64_t frame_end = (sr.payload_base + fr.payload_off + (uint32_t)(h.frame_len - 4 - (h.crc ? 2 : 0) - h.side_len)) * 8ull;
+    if (valid && bit > frame_end) {
+        if (fi >= sr.skip_frames) atomicAdd(concealed, 1u);
+        for (int k = 0; k < ngr * nch; k++) {
+            L3UnitDesc &d = units[u0 + k];
+            d.bit_off = 0;
+            d.p23len = d.big_values = d.r1 = d.r2 = 0;
+            d.flags &= (uint8_t)~L3F_VALID;
+        }
+    }
 }
 
 // Main-data compaction.  A CTA takes 64 frames: 64 threads first resolve one frame each (record,
@@ -352,6 +365,11 @@ k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ 
             n = h.layer != 3 ? 0u : (uint32_t)h.frame_len - skip;
             s_src[threadIdx.x] = raw + sr.raw_off + fr.rel_off + skip;
             s_dst[threadIdx.x] = arena + sr.payload_base + fr.payload_off;
+            if (f + 1 == sr.frame_base + sr.nframes) { // the stream's last frame: zero the padding behind its main data
+                uint8_t *pad = arena + sr.payload_base + sr.payload_len;
+                const uint32_t npad = ((sr.payload_len + L3_PAYLOAD_PAD + 15u) & ~15u) - sr.payload_len;
+                for (uint32_t i = 0; i < npad; i++) pad[i] = 0;
+            }
         }
         s_n[threadIdx.x] = n;
     }

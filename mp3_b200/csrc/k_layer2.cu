@@ -38,8 +38,11 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total)
 }
 
 // n (0..16) bits at bit position `pos` of the staged frame (bytes past the frame read as zero)
-__device__ __forceinline__ uint32_t l2_bits(const uint8_t *f, uint32_t pos, int n)
+// Bits past the end of the frame read as zero (a damaged allocation can ask for far more bits than the
+// frame holds): the staged frame is followed by >= 4 zero bytes and the position is clamped to its end.
+__device__ __forceinline__ uint32_t l2_bits(const uint8_t *f, uint32_t pos, int n, uint32_t lim)
 {
+    pos = min(pos, lim);
     const uint32_t b = pos >> 3;
     const uint32_t w = ((uint32_t)f[b] << 24) | ((uint32_t)f[b + 1] << 16) | ((uint32_t)f[b + 2] << 8) | f[b + 3];
     return n ? (w << (pos & 7)) >> (32 - n) : 0u;
@@ -62,6 +65,7 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     const int flen = min(h.frame_len, L2_MAX_FRAME);
     for (int i = lane; i < flen + 8; i += 32) fb[i] = i < flen ? src[i] : (uint8_t)0;
     __syncwarp();
+    const uint32_t lim = (uint32_t)flen * 8u;
 
     const int nch = h.nch;
     const int tbl = l2_select_table(h.lsf, l3_sr_hz(h.sr_row), h.kbps, nch);
@@ -79,8 +83,8 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     int off = warp_excl_scan(nbal * ncode, lane, &tot);
     int alloc[2] = {0, 0};
     if (on) {
-        alloc[0] = (int)l2_bits(fb, pos + off, nbal);
-        alloc[1] = nch == 2 ? (sep ? (int)l2_bits(fb, pos + off + nbal, nbal) : alloc[0]) : 0;
+        alloc[0] = (int)l2_bits(fb, pos + off, nbal, lim);
+        alloc[1] = nch == 2 ? (sep ? (int)l2_bits(fb, pos + off + nbal, nbal, lim) : alloc[0]) : 0;
     }
     pos += (uint32_t)tot;
     // ---- scfsi: 2 bits per (subband, channel) that has samples
@@ -90,7 +94,7 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     {
         uint32_t p = pos + off;
         for (int ch = 0; ch < nch; ch++)
-            if (alloc[ch]) { scfsi[ch] = (int)l2_bits(fb, p, 2); p += 2; }
+            if (alloc[ch]) { scfsi[ch] = (int)l2_bits(fb, p, 2, lim); p += 2; }
     }
     pos += (uint32_t)tot;
     // ---- scalefactors: 3 / 2 / 1 / 2 indices of 6 bits by scfsi
@@ -102,12 +106,12 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
         uint32_t p = pos + off;
         for (int ch = 0; ch < nch; ch++) {
             if (!alloc[ch]) continue;
-            const float a = c_l2_scf[l2_bits(fb, p, 6)];
+            const float a = c_l2_scf[l2_bits(fb, p, 6, lim)];
             p += 6;
             float b = a, c = a;
-            if (scfsi[ch] == 0) { b = c_l2_scf[l2_bits(fb, p, 6)]; c = c_l2_scf[l2_bits(fb, p + 6, 6)]; p += 12; }
-            else if (scfsi[ch] == 1) { c = c_l2_scf[l2_bits(fb, p, 6)]; p += 6; }
-            else if (scfsi[ch] == 3) { b = c = c_l2_scf[l2_bits(fb, p, 6)]; p += 6; }
+            if (scfsi[ch] == 0) { b = c_l2_scf[l2_bits(fb, p, 6, lim)]; c = c_l2_scf[l2_bits(fb, p + 6, 6, lim)]; p += 12; }
+            else if (scfsi[ch] == 1) { c = c_l2_scf[l2_bits(fb, p, 6, lim)]; p += 6; }
+            else if (scfsi[ch] == 3) { b = c = c_l2_scf[l2_bits(fb, p, 6, lim)]; p += 6; }
             scf[ch][0] = a; scf[ch][1] = b; scf[ch][2] = c;
         }
     }
@@ -131,15 +135,15 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
             const int steps = c_l2_steps[q[k]], b = c_l2_bits[q[k]];
             int code[3];
             if (b < 0) {
-                uint32_t c = l2_bits(fb, p, -b);
+                uint32_t c = l2_bits(fb, p, -b, lim);
                 code[0] = (int)(c % (uint32_t)steps);
                 c /= (uint32_t)steps;
                 code[1] = (int)(c % (uint32_t)steps);
                 code[2] = (int)(c / (uint32_t)steps);
             } else {
-                code[0] = (int)l2_bits(fb, p, b);
-                code[1] = (int)l2_bits(fb, p + b, b);
-                code[2] = (int)l2_bits(fb, p + 2 * b, b);
+                code[0] = (int)l2_bits(fb, p, b, lim);
+                code[1] = (int)l2_bits(fb, p + b, b, lim);
+                code[2] = (int)l2_bits(fb, p + 2 * b, b, lim);
             }
             p += (uint32_t)cbits[k];
             const float inv = 1.f / (float)steps;
@@ -181,6 +185,7 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     const int flen = min(h.frame_len, L2_MAX_FRAME);
     for (int i = lane; i < flen + 8; i += 32) fb[i] = i < flen ? src[i] : (uint8_t)0;
     __syncwarp();
+    const uint32_t lim = (uint32_t)flen * 8u;
 
     const int nch = h.nch;
     const int bound = (h.mode == 1 && nch == 2) ? (h.mode_ext + 1) * 4 : 32;
@@ -190,8 +195,8 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     int tot;
     int off = warp_excl_scan(4 * ncode, lane, &tot);
     int alloc[2];
-    alloc[0] = (int)l2_bits(fb, pos + off, 4);
-    alloc[1] = nch == 2 ? (sep ? (int)l2_bits(fb, pos + off + 4, 4) : alloc[0]) : 0;
+    alloc[0] = (int)l2_bits(fb, pos + off, 4, lim);
+    alloc[1] = nch == 2 ? (sep ? (int)l2_bits(fb, pos + off + 4, 4, lim) : alloc[0]) : 0;
     pos += (uint32_t)tot;
     const int na = (alloc[0] ? 1 : 0) + (alloc[1] ? 1 : 0);
     off = warp_excl_scan(6 * na, lane, &tot);
@@ -199,7 +204,7 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     {
         uint32_t p = pos + off;
         for (int ch = 0; ch < nch; ch++)
-            if (alloc[ch]) { scf[ch] = c_l2_scf[l2_bits(fb, p, 6)]; p += 6; }
+            if (alloc[ch]) { scf[ch] = c_l2_scf[l2_bits(fb, p, 6, lim)]; p += 6; }
     }
     pos += (uint32_t)tot;
     int cb[2];
@@ -212,7 +217,7 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
         for (int k = 0; k < ncode; k++) {
             if (!cb[k]) continue;
             const int steps = (1 << cb[k]) - 1;
-            const int code = (int)l2_bits(fb, p, cb[k]);
+            const int code = (int)l2_bits(fb, p, cb[k], lim);
             p += (uint32_t)cb[k];
             const float fr3 = alloc[k] == 15 ? 0.f : (float)(2 * code + 1 - steps) / (float)steps;
             if (sep) v[k] = fr3 * scf[k];

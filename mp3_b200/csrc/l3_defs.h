@@ -56,6 +56,9 @@ typedef struct L3StreamRec {
 #define L3S_STREAMING 1u   /* more bytes may follow: stop at a valid header whose frame is not complete yet
                               instead of searching for a sync inside it; first_hdr may be preset */
 
+/* A stream's main data in the arena is followed by zero bytes up to the next 16-byte boundary, at least this many. */
+#define L3_PAYLOAD_PAD 8u
+
 /* One granule-channel ("unit": 576 spectral lines), from the side info (a2, a3). 32 bytes. */
 typedef struct __attribute__((aligned(16))) L3UnitDesc {
     uint64_t bit_off;     /* absolute bit offset of part2 in the main-data arena */

@@ -848,6 +848,14 @@ int l3o_decode(const uint8_t *buf, size_t len, l3o_info *info, double *pcm, size
             crc = l3o_crc16(crc, fp + 6, (size_t)h->side_len * 8);
             if (crc != (((unsigned)fp[4] << 8) | fp[5])) ok = 0;
         }
+        if (ok) { /* a frame's main data ends inside the frame (the next frame's main_data_begin cannot point
+                   * forward, 11172-3 2.4.2.7): side info claiming more bits than that is damaged */
+            size_t sum = 0;
+            for (int gr = 0; gr < ngr; gr++)
+                for (int ch = 0; ch < nch; ch++) sum += (size_t)si.gr[gr][ch].part2_3_length;
+            size_t own = (size_t)h->frame_len - 4 - (h->crc ? 2 : 0) - (size_t)h->side_len;
+            if ((fr[f].payload_off - si.main_data_begin) * 8 + sum > (fr[f].payload_off + own) * 8) ok = 0;
+        }
         if (!ok) info->concealed_frames++;
         size_t bitpos = ok ? (fr[f].payload_off - si.main_data_begin) * 8 : 0;
         uint8_t sf[2][MAXCH][40];

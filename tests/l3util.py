@@ -58,3 +58,30 @@ def assert_iso_full_accuracy(test, ref, what=""):
     assert rms < RMS_LIMIT and mx <= MAX_LIMIT, "%s: rms %.3g (limit %.3g) max %.3g (limit %.3g)" % (
         what, rms, RMS_LIMIT, mx, MAX_LIMIT)
     return rms, mx
+
+
+def patch_side_info(frame, unit, part2_3_length=None, big_values=None):
+    """Return a copy of a Layer III frame (no CRC fix-up) with fields of granule-channel `unit` (in side-info
+    order: [granule][channel]) overwritten: 11172-3 2.4.1.7 / 13818-3 2.4.1.7 bit layout."""
+    b = bytearray(frame)
+    lsf = ((b[1] >> 3) & 3) != 3
+    mono = (b[3] >> 6) == 3
+    crc = not (b[1] & 1)
+    base = (4 + (2 if crc else 0)) * 8
+    if lsf:
+        base += 9 if mono else 10
+        stride = 63
+    else:
+        base += 18 if mono else 20
+        stride = 59
+
+    def put(pos, n, v):
+        for i in range(n):
+            bit = (v >> (n - 1 - i)) & 1
+            byte, sh = (pos + i) >> 3, 7 - ((pos + i) & 7)
+            b[byte] = (b[byte] & ~(1 << sh)) | (bit << sh)
+    if part2_3_length is not None:
+        put(base + unit * stride, 12, part2_3_length)
+    if big_values is not None:
+        put(base + unit * stride + 12, 9, big_values)
+    return bytes(b)

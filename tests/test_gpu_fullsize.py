@@ -165,3 +165,42 @@ def test_damaged_streams_decode_like_the_oracle(mp3b, synth_mod, oracle_mod):
             scale = max(1.0, float(np.abs(r.pcm).max()))
             assert np.abs(got - r.pcm.T).max() <= 2.0 ** -14 * scale, i
         assert dec.stats().concealed_frames == concealed
+
+
+def test_side_info_that_overruns_the_stream(mp3b, synth_mod, oracle_mod):
+    """Two damage patterns at the END of a stream, where the next stream's bytes follow in the arena
+    (found by tools/fuzz_parity.py): (1) big_values inflated so that the last Huffman codes run into /
+    across the unit's end -- the bits past the stream's end read as zero; (2) part2_3_length inflated so
+    that the frame claims more main data than it can hold -- the frame is concealed.  Both in the middle
+    of a stream too.  Each damaged stream is followed by a healthy one full of set bits."""
+    cfgs = [dict(nframes=10, seed=21), dict(nframes=10, seed=22, mode=3, blocks=1),
+            dict(nframes=10, seed=23, mode=1, bitrate_kbps=320, blocks=1, mixed_pct=25),
+            dict(nframes=10, seed=24, sample_rate=22050, bitrate_kbps=64, mode=1, blocks=1),
+            dict(nframes=10, seed=25, sample_rate=8000, bitrate_kbps=16, blocks=1, mode=3)]
+    batch, expect_concealed = [], 0
+    for c in cfgs:
+        s = synth_mod.make_stream(**c)
+        frames = l3util.split_frames(s)
+        lsf = c.get("sample_rate", 44100) < 32000
+        nunits = (1 if lsf else 2) * (1 if c.get("mode", 0) == 3 else 2)
+        for what in ("big_values", "part2_3_length"):
+            for where in (len(frames) - 1, 4):
+                fr = list(frames)
+                for u in range(nunits):
+                    fr[where] = (l3util.patch_side_info(fr[where], u, big_values=288) if what == "big_values"
+                                 else l3util.patch_side_info(fr[where], u, part2_3_length=4095))
+                batch.append(b"".join(fr))
+                batch.append(s)
+    refs = [oracle_mod.decode(s) for s in batch]
+    assert sum(r.concealed_frames for r in refs) >= len(cfgs) * 2  # the inflated lengths are concealed
+    for fmt_pipe in (mp3b.PIPE_FUSED, mp3b.PIPE_STAGED):
+        with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=fmt_pipe) as dec:
+            dec.decode_batch(batch)
+            arena = dec.fetch_pcm()
+            for i, r in enumerate(refs):
+                inf = dec.stream_info(i)
+                assert (inf.frames, inf.samples) == (r.frames, r.samples), i
+                got = dec.stream_pcm(i, arena).astype(np.float64)
+                scale = max(1.0, float(np.abs(r.pcm).max()))
+                assert np.abs(got - r.pcm.T).max() <= 2.0 ** -14 * scale, i
+            assert dec.stats().concealed_frames == sum(r.concealed_frames for r in refs)

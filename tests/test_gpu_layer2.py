@@ -82,3 +82,33 @@ def test_layer2_incremental_stream(batch):
             cat = np.concatenate(got)
             assert cat.shape == whole.shape and np.array_equal(cat, whole), k
             h.close()
+
+
+def test_allocation_asking_for_more_bits_than_the_frame_holds(synth_mod, oracle_mod):
+    """A damaged Layer I / II frame whose allocation field demands more sample bits than the frame has:
+    bits past the frame's end read as zero in both implementations (found by tools/fuzz_parity.py)."""
+    import mp3_b200 as m
+    bad = []
+    for cfg, fill in ((dict(layer=1, bitrate_kbps=256, nframes=12, seed=7), 0xEE),
+                      (dict(layer=1, bitrate_kbps=64, sample_rate=48000, mode=3, nframes=12, seed=8), 0xDD),
+                      (dict(layer=2, bitrate_kbps=192, nframes=8, seed=5), 0xFF),
+                      (dict(layer=2, bitrate_kbps=32, sample_rate=32000, mode=3, nframes=8, seed=6), 0xFF),
+                      (dict(layer=2, bitrate_kbps=160, sample_rate=24000, nframes=8, seed=9), 0xFF)):
+        s = synth_mod.make_stream(**cfg)
+        frames = l3util.split_frames(s)
+        b = bytearray(s)
+        for k in (1, len(frames) - 1):  # a middle frame and the stream's last one
+            off = sum(len(f) for f in frames[:k])
+            for i in range(off + 4, off + 4 + 32):
+                b[i] = fill
+        bad.append(bytes(b))
+    refs = [oracle_mod.decode(s) for s in bad]
+    with m.Decoder(device=0, pcm_format=m.PCM_F32) as dec:
+        dec.decode_batch(bad)
+        arena = dec.fetch_pcm()
+        for i, r in enumerate(refs):
+            inf = dec.stream_info(i)
+            assert (inf.frames, inf.samples) == (r.frames, r.samples)
+            got = dec.stream_pcm(i, arena).astype(np.float64)
+            scale = max(1.0, float(np.abs(r.pcm).max()))
+            l3util.assert_iso_full_accuracy(got / scale, r.pcm.T / scale, "stream %d" % i)
