@@ -233,6 +233,25 @@ typedef struct mp3b_frame_rec { uint32_t offset, payload_offset, header, reserve
 int mp3b_index_stream_host(const uint8_t *bytes, size_t n, mp3b_frame_rec *frames, size_t cap_frames,
                            size_t *nframes, mp3b_stream_info *info, mp3b_tag_info *tag);
 
+/* ---- seek (no GPU involved) ------------------------------------------------------------------
+ * Where to start feeding a stream so that the PCM from `target_sample` on (per-channel sample index
+ * of the un-trimmed decode, i.e. before any gapless window) is bit-identical to a decode from the
+ * stream's start: far enough back that the target frame's two preceding granules decode from complete
+ * main data (bit reservoir: up to 511 bytes behind their headers), which re-derives the overlap and the
+ * synthesis history exactly.  Decode bytes[byte_offset ..] as a stream of its own (batch or
+ * mp3b_stream_open / enqueue) and drop the first discard_samples samples per channel; the frames in
+ * front of the target whose own reservoir is missing are concealed (and counted) -- they only warm up
+ * state.  `frames` is the table mp3b_index_stream_host returned for these bytes.  This is the
+ * "repeat the sentence" seek of the reference's player (/root/reference/README.md:46). */
+typedef struct mp3b_seek {
+    uint64_t byte_offset;     /* offset of the header of first_frame */
+    uint32_t first_frame;     /* frame to start feeding from */
+    uint32_t target_frame;    /* frame that holds target_sample */
+    int64_t discard_samples;  /* samples per channel to drop from the decode of bytes[byte_offset ..] */
+} mp3b_seek;
+int mp3b_seek_plan(const uint8_t *bytes, size_t n, const mp3b_frame_rec *frames, size_t nframes, int64_t target_sample,
+                   mp3b_seek *out);
+
 /* ---- debug / parity access to intermediates (keep_stages = 1) -------------------------------
  * stage: see mp3b_stage.  Copies the whole stage array for the last batch to host memory.
  * *elem_size receives the element size in bytes, *count the number of elements. */

@@ -70,7 +70,7 @@ EXPORTS = [
     "mp3b_batch_resampled_device_ptr", "mp3b_batch_fetch_resampled", "mp3b_resample_filter",
     "mp3b_batch_time_stretch", "mp3b_batch_stretched_info", "mp3b_batch_stretched_device_ptr",
     "mp3b_batch_fetch_stretched", "mp3b_batch_stretch_offsets", "mp3b_batch_planar",
-    "mp3b_batch_planar_device_ptr", "mp3b_batch_fetch_planar",
+    "mp3b_batch_planar_device_ptr", "mp3b_batch_fetch_planar", "mp3b_seek_plan",
 ]
 
 _lib = None
@@ -206,6 +206,31 @@ def index_stream_host(data):
     arr = np.frombuffer(frames, dtype=np.dtype([("offset", "<u4"), ("payload_offset", "<u4"), ("header", "<u4"),
                                                 ("reserved", "<u4")]), count=got.value).copy()
     return arr, info, tag
+
+
+class Seek(ctypes.Structure):
+    _fields_ = [("byte_offset", ctypes.c_uint64), ("first_frame", ctypes.c_uint32), ("target_frame", ctypes.c_uint32),
+                ("discard_samples", ctypes.c_int64)]
+
+
+def seek_plan(data, target_sample, frames=None):
+    """Where to start decoding `data` so that the PCM from target_sample on equals a decode from the start
+    (include/mp3b.h: mp3b_seek_plan).  Returns a Seek; decode data[seek.byte_offset:] and drop the first
+    seek.discard_samples samples per channel."""
+    L = load_library()
+    data = bytes(data)
+    if frames is None:
+        frames, _, _ = index_stream_host(data)
+    frames = np.ascontiguousarray(frames)
+    buf = (ctypes.c_uint8 * max(len(data), 1)).from_buffer_copy(data if data else b"\0")
+    out = Seek()
+    L.mp3b_seek_plan.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64,
+                                 ctypes.POINTER(Seek)]
+    rc = L.mp3b_seek_plan(buf, len(data), frames.ctypes.data_as(ctypes.c_void_p), len(frames), int(target_sample),
+                          ctypes.byref(out))
+    if rc != 0:
+        raise Mp3bError(rc, L.mp3b_strerror(rc).decode())
+    return out
 
 
 def resample_filter(in_rate, out_rate):

@@ -869,6 +869,35 @@ int mp3b_index_stream_host(const uint8_t *bytes, size_t n, mp3b_frame_rec *frame
     return MP3B_OK;
 }
 
+int mp3b_seek_plan(const uint8_t *bytes, size_t n, const mp3b_frame_rec *frames, size_t nframes, int64_t target_sample,
+                   mp3b_seek *out)
+{
+    if (!bytes || !frames || !nframes || !out || target_sample < 0) return MP3B_E_INVAL;
+    L3Hdr h;
+    if (!l3_parse_hdr(frames[0].header, &h)) return MP3B_E_INVAL;
+    const uint64_t t = (uint64_t)target_sample / (uint64_t)h.spf;
+    if (t >= nframes) return MP3B_E_INVAL;
+    // Two granules of exact spectra in front of the target make its output exact: the overlap comes from the
+    // granule before, the synthesis history (15 slots) from that granule's subband samples, which overlap
+    // with the one before it.  That is one 1152-sample frame, or two shorter ones.
+    const uint64_t warm = h.spf < 1152 ? 2 : 1;
+    const uint64_t a = t > warm ? t - warm : 0;
+    // ... and frame a needs the main data its main_data_begin reaches back for (Layer III only)
+    uint64_t s = a;
+    L3Hdr ha;
+    if (l3_parse_hdr(frames[a].header, &ha) && ha.layer == 3) {
+        const uint64_t side = (uint64_t)frames[a].offset + 4u + (ha.crc ? 2u : 0u);
+        if (side + 2 > n) return MP3B_E_INVAL;
+        const uint32_t mdb = ha.lsf ? bytes[side] : ((uint32_t)bytes[side] << 1) | (bytes[side + 1] >> 7);
+        while (s > 0 && frames[a].payload_offset - frames[s].payload_offset < mdb) s--;
+    }
+    out->byte_offset = frames[s].offset;
+    out->first_frame = (uint32_t)s;
+    out->target_frame = (uint32_t)t;
+    out->discard_samples = (int64_t)((t - s) * (uint64_t)h.spf + (uint64_t)target_sample % (uint64_t)h.spf);
+    return MP3B_OK;
+}
+
 int mp3b_decode_packed(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int nstreams, int where)
 {
     if (!ctx) return MP3B_E_INVAL;
