@@ -223,6 +223,21 @@ int mp3b_batch_fetch_stretched(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int
 /* The alignment offsets chosen for stream i (one per output segment of `hop` frames), for verification. */
 int mp3b_batch_stretch_offsets(mp3b_ctx *ctx, int stream_index, int32_t *dst, size_t cap, size_t *n, int *hop);
 
+/* ---- sentence boundaries of the last batch ------------------------------------------------------
+ * The other half of the reference's "repeat each sentence" feature (/root/reference/README.md:46): where the
+ * pauses are.  Integer arithmetic only, so the result is exactly reproducible: the PCM as s16 (float PCM is
+ * rounded), mono mix (L + R) >> 1, windows of sample_rate / 100 samples (10 ms), window energy = sum of
+ * squares; a window is silent iff energy <= threshold^2 x its length (threshold = RMS level in s16 units,
+ * 1 .. 32767; 328 is about -40 dBFS); a pause is a run of >= min_silence_ms / 10 silent windows; a sentence
+ * is a maximal run of windows that starts and ends voiced and holds no pause; sentences shorter than
+ * min_sentence_ms are dropped.  mp3b_batch_fetch_segments copies stream i's sentences to dst as
+ * {first sample, end sample} pairs (per-channel sample indices relative to the stream's PCM, i.e. to
+ * mp3b_stream_info.pcm_offset); *n = the number of pairs (MP3B_E_TRUNCATED if cap pairs are too few).
+ * mp3b_batch_window_energy returns the window energies the decision was made on. */
+int mp3b_batch_segments(mp3b_ctx *ctx, int threshold, int min_silence_ms, int min_sentence_ms);
+int mp3b_batch_fetch_segments(mp3b_ctx *ctx, int stream_index, int64_t *dst, size_t cap_pairs, size_t *n);
+int mp3b_batch_window_energy(mp3b_ctx *ctx, int stream_index, uint64_t *dst, size_t cap, size_t *n, int *window);
+
 /* ---- host-side frame index of one stream (no GPU involved) ---------------------------------
  * The frame walk of the host indexer (MP3B_INDEX_HOST) as a utility: sync search past ID3v2 / junk,
  * header validation, stream consistency, tag frame.  frames[i] = {byte offset of the header, main-data

@@ -71,6 +71,7 @@ EXPORTS = [
     "mp3b_batch_time_stretch", "mp3b_batch_stretched_info", "mp3b_batch_stretched_device_ptr",
     "mp3b_batch_fetch_stretched", "mp3b_batch_stretch_offsets", "mp3b_batch_planar",
     "mp3b_batch_planar_device_ptr", "mp3b_batch_fetch_planar", "mp3b_seek_plan",
+    "mp3b_batch_segments", "mp3b_batch_fetch_segments", "mp3b_batch_window_energy",
 ]
 
 _lib = None
@@ -414,6 +415,41 @@ class Decoder:
                                            ctypes.byref(got)))
         self.sync()
         return out
+
+    def segments(self, threshold=328, min_silence_ms=300, min_sentence_ms=200):
+        """Sentence boundaries of the last batch (include/mp3b.h: mp3b_batch_segments): a list with one
+        int64 array [n, 2] of {first sample, end sample} per stream."""
+        L = self.L
+        L.mp3b_batch_segments.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.mp3b_batch_fetch_segments.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                ctypes.POINTER(ctypes.c_size_t)]
+        self._ck(L.mp3b_batch_segments(self.ctx, int(threshold), int(min_silence_ms), int(min_sentence_ms)))
+        out = []
+        n = ctypes.c_size_t()
+        for i in range(self.nstreams):
+            rc = L.mp3b_batch_fetch_segments(self.ctx, i, None, 0, ctypes.byref(n))
+            if rc not in (0, -3):
+                self._ck(rc)
+            a = np.zeros((n.value, 2), np.int64)
+            if n.value:
+                self._ck(L.mp3b_batch_fetch_segments(self.ctx, i, a.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
+            out.append(a)
+        return out
+
+    def window_energy(self, i):
+        """(energies uint64[nwin], window length in samples) of stream i, after segments()."""
+        L = self.L
+        L.mp3b_batch_window_energy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                               ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int)]
+        n, w = ctypes.c_size_t(), ctypes.c_int()
+        rc = L.mp3b_batch_window_energy(self.ctx, int(i), None, 0, ctypes.byref(n), ctypes.byref(w))
+        if rc not in (0, -3):
+            self._ck(rc)
+        a = np.zeros(n.value, np.uint64)
+        if n.value:
+            self._ck(L.mp3b_batch_window_energy(self.ctx, int(i), a.ctypes.data_as(ctypes.c_void_p), n.value,
+                                                ctypes.byref(n), ctypes.byref(w)))
+        return a, w.value
 
     def time_stretch(self, num, den):
         """WSOLA time-scale modification of the last batch: speed = num / den (1, 2 = half speed); async."""

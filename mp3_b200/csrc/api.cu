@@ -134,6 +134,11 @@ struct mp3b_ctx {
     // planar copy of the last batch
     DevBuf d_pl, d_pl_jobs;
     bool have_pl = false;
+    DevBuf d_sg_jobs, d_sg_energy, d_sg_seg, d_sg_n;
+    std::vector<L3SegJob> sg_jobs;   // per stream of the batch (nwin = 0: no audio)
+    std::vector<long long> sg_seg;   // host copies, fetched on first use
+    std::vector<int> sg_n;
+    bool have_sg = false, sg_on_host = false;
     // time-stretched copy of the last batch
     DevBuf d_ts, d_ts_jobs, d_ts_off;
     std::vector<L3StretchJob> ts_jobs;
@@ -320,6 +325,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     ctx->have_rs = false;
     ctx->have_ts = false;
     ctx->have_pl = false;
+    ctx->have_sg = false;
     ctx->infos.assign((size_t)nstreams, mp3b_stream_info{});
     ctx->tags.assign((size_t)nstreams, mp3b_tag_info{});
     ctx->stats = mp3b_stats{};
@@ -771,7 +777,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_tiles2, &ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -1048,6 +1054,99 @@ int mp3b_batch_fetch_planar(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int wh
         CK(cudaMemcpyAsync(dst, ctx->d_pl.p, ctx->pcm_elems * elem,
                            where == MP3B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     if (got) *got = ctx->pcm_elems;
+    return MP3B_OK;
+}
+
+int mp3b_batch_segments(mp3b_ctx *ctx, int threshold, int min_silence_ms, int min_sentence_ms)
+{
+    if (!ctx || threshold < 1 || threshold > 32767 || min_silence_ms < 10 || min_sentence_ms < 0) return MP3B_E_INVAL;
+    if (!ctx->have_batch) return MP3B_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int G = min_silence_ms / 10, S = std::max(1, min_sentence_ms / 10);
+    const size_t ns = ctx->infos.size();
+    ctx->have_sg = ctx->sg_on_host = false;
+    ctx->sg_jobs.assign(ns, L3SegJob{});
+    std::vector<L3SegJob> jl;
+    uint64_t nwin = 0, nseg = 0;
+    unsigned max_nwin = 0;
+    for (size_t i = 0; i < ns; i++) {
+        const mp3b_stream_info &inf = ctx->infos[i];
+        if (!inf.frames || inf.sample_rate <= 0 || inf.samples <= 0) continue;
+        L3SegJob &jb = ctx->sg_jobs[i];
+        jb.off = inf.pcm_offset;
+        jb.samples = inf.samples;
+        jb.channels = inf.channels;
+        jb.window = inf.sample_rate / 100;
+        const uint64_t w = ((uint64_t)inf.samples + (uint64_t)jb.window - 1) / (uint64_t)jb.window;
+        if (w > 0xFFFFFFF0ull || nwin + w > 0xFFFFFFF0ull) { ctx->err = "too many windows"; return MP3B_E_INVAL; }
+        jb.win_base = (unsigned)nwin;
+        jb.nwin = (unsigned)w;
+        jb.seg_base = (unsigned)nseg;
+        jb.seg_cap = (unsigned)(w / (uint64_t)(G + 1) + 1); // a sentence and the pause behind it take >= G + 1 windows
+        nwin += w;
+        nseg += jb.seg_cap;
+        max_nwin = std::max(max_nwin, jb.nwin);
+        jl.push_back(jb);
+    }
+    CK(ctx->d_sg_jobs.ensure(std::max<size_t>(jl.size() * sizeof(L3SegJob), 16)));
+    CK(ctx->d_sg_energy.ensure(std::max<size_t>(nwin * 8, 16)));
+    CK(ctx->d_sg_seg.ensure(std::max<size_t>(nseg * 16, 16)));
+    CK(ctx->d_sg_n.ensure(std::max<size_t>(jl.size() * 4, 16)));
+    if (!jl.empty()) {
+        CK(cudaMemcpyAsync(ctx->d_sg_jobs.p, jl.data(), jl.size() * sizeof(L3SegJob), cudaMemcpyHostToDevice, st));
+        l3_launch_segments(ctx->pcm().p, ctx->opts.pcm_format, ctx->d_sg_jobs.as<L3SegJob>(), (int)jl.size(), max_nwin,
+                           ctx->d_sg_energy.as<unsigned long long>(), (unsigned long long)threshold * (unsigned long long)threshold,
+                           G, S, ctx->d_sg_seg.as<long long>(), ctx->d_sg_n.as<int>(), st);
+    }
+    CK(cudaGetLastError());
+    ctx->sg_seg.resize(nseg * 2);
+    ctx->sg_n.resize(jl.size());
+    ctx->have_sg = true;
+    return MP3B_OK;
+}
+
+int mp3b_batch_fetch_segments(mp3b_ctx *ctx, int i, int64_t *dst, size_t cap, size_t *n)
+{
+    if (!ctx || !n) return MP3B_E_INVAL;
+    if (!ctx->have_sg) return MP3B_E_STATE;
+    if (i < 0 || (size_t)i >= ctx->sg_jobs.size()) return MP3B_E_INVAL;
+    if (!ctx->sg_on_host) { // one copy of the whole (small) result per mp3b_batch_segments call
+        CK(cudaSetDevice(ctx->device));
+        if (!ctx->sg_n.empty()) {
+            CK(cudaMemcpyAsync(ctx->sg_n.data(), ctx->d_sg_n.p, ctx->sg_n.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->sg_seg.data(), ctx->d_sg_seg.p, ctx->sg_seg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->sg_on_host = true;
+    }
+    const L3SegJob &jb = ctx->sg_jobs[(size_t)i];
+    *n = 0;
+    if (!jb.nwin) return MP3B_OK;
+    size_t row = 0; // jobs were compacted over streams with audio
+    for (int k = 0; k < i; k++) row += ctx->sg_jobs[(size_t)k].nwin ? 1 : 0;
+    *n = (size_t)ctx->sg_n[row];
+    if (*n > cap || (!dst && *n)) return MP3B_E_TRUNCATED;
+    static_assert(sizeof(long long) == sizeof(int64_t), "segment pairs are int64");
+    memcpy(dst, ctx->sg_seg.data() + 2 * (size_t)jb.seg_base, *n * 16);
+    return MP3B_OK;
+}
+
+int mp3b_batch_window_energy(mp3b_ctx *ctx, int i, uint64_t *dst, size_t cap, size_t *n, int *window)
+{
+    if (!ctx || !n) return MP3B_E_INVAL;
+    if (!ctx->have_sg) return MP3B_E_STATE;
+    if (i < 0 || (size_t)i >= ctx->sg_jobs.size()) return MP3B_E_INVAL;
+    const L3SegJob &jb = ctx->sg_jobs[(size_t)i];
+    *n = jb.nwin;
+    if (window) *window = jb.window;
+    if (*n > cap || (!dst && *n)) return MP3B_E_TRUNCATED;
+    CK(cudaSetDevice(ctx->device));
+    if (*n) {
+        CK(cudaMemcpyAsync(dst, ctx->d_sg_energy.as<unsigned long long>() + jb.win_base, *n * 8, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return MP3B_OK;
 }
 

@@ -115,6 +115,17 @@ struct L3PlanarJob {
 void l3_launch_planar(const void *in, void *out, int pcm_format, const L3PlanarJob *jobs, const uint32_t *tile_job,
                       const uint32_t *tile_first, uint32_t ntiles, cudaStream_t st);
 
+/* Sentence boundaries (k_segments.cu): one job per stream with audio. */
+struct L3SegJob {
+    long long off, samples;      /* element offset of the stream in the PCM arena; frames */
+    int channels, window;        /* samples per 10-ms window */
+    unsigned win_base, nwin;     /* the stream's windows in the energy array */
+    unsigned seg_base, seg_cap;  /* the stream's slots in the segment array */
+};
+void l3_launch_segments(const void *pcm, int pcm_format, const L3SegJob *jobs, int njobs, unsigned max_nwin,
+                        unsigned long long *energy, unsigned long long thr2, int G, int S, long long *seg, int *nseg,
+                        cudaStream_t st);
+
 /* Time-scale modification (k_stretch.cu).  One job (and one CTA) per stream. */
 struct L3StretchJob {
     long long in_off, in_n, out_off, out_n;

@@ -57,3 +57,16 @@ dec.sync()
 ms = e0.elapsed_time(e1) / 10
 nbytes = 2 * 1024 * 383 * 1152 * 2 * 2  # read + write of the s16 stereo arena
 print("planar: %.3f ms per batch, %.0f GB/s of HBM traffic (read + write)" % (ms, nbytes / (ms * 1e-3) / 1e9))
+
+L.mp3b_batch_segments.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+for _ in range(2):
+    L.mp3b_batch_segments(dec.ctx, 328, 300, 200)
+dec.sync()
+e0.record(st)
+for _ in range(10):
+    L.mp3b_batch_segments(dec.ctx, 328, 300, 200)
+e1.record(st)
+dec.sync()
+ms = e0.elapsed_time(e1) / 10
+nbytes = 1024 * 383 * 1152 * 2 * 2  # one read of the s16 stereo arena
+print("segments: %.3f ms per batch, %.0f GB/s of PCM read" % (ms, nbytes / (ms * 1e-3) / 1e9))
