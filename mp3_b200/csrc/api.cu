@@ -137,7 +137,7 @@ struct mp3b_ctx {
     DevBuf d_sg_jobs, d_sg_energy, d_sg_seg, d_sg_n;
     std::vector<L3SegJob> sg_jobs;   // per stream of the batch (nwin = 0: no audio)
     std::vector<long long> sg_seg;   // host copies, fetched on first use
-    std::vector<int> sg_n;
+    std::vector<int> sg_n, sg_row;  // sg_row[i]: stream i's row in the compacted job list, -1 if no audio
     bool have_sg = false, sg_on_host = false;
     // time-stretched copy of the last batch
     DevBuf d_ts, d_ts_jobs, d_ts_off;
@@ -1067,6 +1067,7 @@ int mp3b_batch_segments(mp3b_ctx *ctx, int threshold, int min_silence_ms, int mi
     const size_t ns = ctx->infos.size();
     ctx->have_sg = ctx->sg_on_host = false;
     ctx->sg_jobs.assign(ns, L3SegJob{});
+    ctx->sg_row.assign(ns, -1);
     std::vector<L3SegJob> jl;
     uint64_t nwin = 0, nseg = 0;
     unsigned max_nwin = 0;
@@ -1087,6 +1088,7 @@ int mp3b_batch_segments(mp3b_ctx *ctx, int threshold, int min_silence_ms, int mi
         nwin += w;
         nseg += jb.seg_cap;
         max_nwin = std::max(max_nwin, jb.nwin);
+        ctx->sg_row[i] = (int)jl.size();
         jl.push_back(jb);
     }
     CK(ctx->d_sg_jobs.ensure(std::max<size_t>(jl.size() * sizeof(L3SegJob), 16)));
@@ -1123,9 +1125,7 @@ int mp3b_batch_fetch_segments(mp3b_ctx *ctx, int i, int64_t *dst, size_t cap, si
     const L3SegJob &jb = ctx->sg_jobs[(size_t)i];
     *n = 0;
     if (!jb.nwin) return MP3B_OK;
-    size_t row = 0; // jobs were compacted over streams with audio
-    for (int k = 0; k < i; k++) row += ctx->sg_jobs[(size_t)k].nwin ? 1 : 0;
-    *n = (size_t)ctx->sg_n[row];
+    *n = (size_t)ctx->sg_n[(size_t)ctx->sg_row[(size_t)i]];
     if (*n > cap || (!dst && *n)) return MP3B_E_TRUNCATED;
     static_assert(sizeof(long long) == sizeof(int64_t), "segment pairs are int64");
     memcpy(dst, ctx->sg_seg.data() + 2 * (size_t)jb.seg_base, *n * 16);

@@ -390,9 +390,12 @@ k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ 
         const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - sh);
         uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
         const uint32_t sel = 0x3210u + 0x1111u * sh;
-        for (uint32_t i = lane; i < nw; i += 32) {
-            const uint32_t a = __ldg(sw + i), b = sh ? __ldg(sw + i + 1) : 0u;
-            dw[i] = __byte_perm(a, b, sel);
+        for (uint32_t i0 = 0; i0 < nw; i0 += 32) { // warp-uniform trip count: the unrolled loop must not split the warp
+            const uint32_t i = i0 + lane;
+            if (i < nw) {
+                const uint32_t a = __ldg(sw + i), b = sh ? __ldg(sw + i + 1) : 0u;
+                dw[i] = __byte_perm(a, b, sel);
+            }
         }
         for (uint32_t i = nw * 4u + lane; i < n; i += 32) dst[i] = src[i];
     }
