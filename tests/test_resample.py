@@ -38,7 +38,7 @@ def test_filter_properties(rin, rout):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["f32", "s16"])
-@pytest.mark.parametrize("out_rate", [48000, 44100, 16000])
+@pytest.mark.parametrize("out_rate", [48000, 44100, 32000, 22050, 16000])
 def test_resample_matches_upfirdn(fmt, out_rate, synth_mod):
     from scipy.signal import upfirdn
     import mp3_b200 as m
