@@ -401,7 +401,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     uint64_t frames = 0, grans = 0, units = 0, payload = 0, ntiles = 0;
     std::vector<uint32_t> sgran((size_t)nstreams, 0), sunit((size_t)nstreams, 0), sskip((size_t)nstreams, 0);
     std::vector<uint8_t> sl2((size_t)nstreams, 0); // Layer I / II streams: decoded by k_layer1/2 + the synthesis kernel
-    bool any_l2 = false;
+    bool any_l2 = false, any_layer[4] = {false, false, false, false}; // which layers the batch holds: kernels of absent ones are not launched
     for (int i = 0; i < nstreams; i++) {
         L3StreamRec &r = hs[i];
         mp3b_stream_info &inf = ctx->infos[(size_t)i];
@@ -441,6 +441,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             sskip[(size_t)i] = (uint32_t)((uint64_t)skip * h.spf / 576); // whole granules before the first new sample
             sl2[(size_t)i] = h.layer != 3;
             any_l2 = any_l2 || h.layer != 3;
+            any_layer[h.layer & 3] = true;
             if (h.layer == 3) ntiles += (g + G - 1) / G;
             grans += g;
             units += g * h.nch;
@@ -579,8 +580,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     if (frames) {
         l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : d_scratch.as<L3FrameRec>(),
                              (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), ctx->opts.verify_crc, st);
-        l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
-        launches += 2;
+        if (any_layer[3]) l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
+        launches += any_layer[3] ? 2 : 1;
     }
     CK(cudaEventRecord(ctx->ev[EV_INDEX], st));
 
@@ -601,7 +602,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         float *imd = ctx->d_imd.as<float>() - (size_t)u_lo * 1152;
         float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
         uint8_t *nzv = ctx->d_nzv.as<uint8_t>() - (size_t)u_lo;
-        l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu,
+        if (any_layer[3] || !fused || keep) // (the staged pipeline and stage dumps want every unit's arrays written)
+            l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu,
                                 (uint32_t)((ctx->arena_bytes + units - 1) / std::max<uint64_t>(units, 1)), ctx->T, is, sf, nzv,
                                 (!fused || keep) ? 1 : 0, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
@@ -623,7 +625,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
                               pcm_dev, ctx->opts.pcm_format, st);
             if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
-            launches += 2;
+            launches += (any_layer[3] || keep ? 1 : 0) + (t_hi > t_lo ? 1 : 0);
             if (int rc = wave_done()) return rc;
             continue;
         }
@@ -659,13 +661,13 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
                 for (uint32_t a = sskip[(size_t)i]; a < sgran[(size_t)i]; a += (uint32_t)G)
                     t2[k++] = make_uint2(hs[i].gran_base + a, std::min<uint32_t>((uint32_t)G, sgran[(size_t)i] - a));
         float *sb2 = ctx->d_sb2.as<float>() - (size_t)u_min * 576;
-        l3_launch_layer2(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
-        l3_launch_layer1(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
+        if (any_layer[2]) l3_launch_layer2(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
+        if (any_layer[1]) l3_launch_layer1(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
         if (nt2) {
             CK(cudaMemcpyAsync(ctx->d_tiles2.p, t2, sizeof(uint2) * nt2, cudaMemcpyHostToDevice, st));
             l3_launch_synth(ctx->d_tiles2.as<uint2>(), (uint32_t)nt2, dg, sb2, pcm_dev, ctx->opts.pcm_format, st);
         }
-        launches += 2;
+        launches += (any_layer[2] ? 1 : 0) + (any_layer[1] ? 1 : 0) + (nt2 ? 1 : 0);
         if (sink) { // the waves above did not cover these streams' PCM: one more copy, whole ranges
             while (ctx->wave_ev.size() <= waves.size()) {
                 cudaEvent_t e;

@@ -38,21 +38,41 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total)
 }
 
 // n (0..16) bits at bit position `pos` of the staged frame (bytes past the frame read as zero)
-// Bits past the end of the frame read as zero (a damaged allocation can ask for far more bits than the
-// frame holds): the staged frame is followed by >= 4 zero bytes and the position is clamped to its end.
-__device__ __forceinline__ uint32_t l2_bits(const uint8_t *f, uint32_t pos, int n, uint32_t lim)
+// The frame is staged in shared memory as big-endian 32-bit words, so a field is two word loads and one
+// funnel shift.  Bits past the end of the frame read as zero (a damaged allocation can ask for far more
+// bits than the frame holds): the staged frame is followed by >= 8 zero bytes and the position is clamped
+// to its end.
+__device__ __forceinline__ uint32_t l2_bits(const uint32_t *f, uint32_t pos, int n, uint32_t lim)
 {
     pos = min(pos, lim);
-    const uint32_t b = pos >> 3;
-    const uint32_t w = ((uint32_t)f[b] << 24) | ((uint32_t)f[b + 1] << 16) | ((uint32_t)f[b + 2] << 8) | f[b + 3];
-    return n ? (w << (pos & 7)) >> (32 - n) : 0u;
+    const uint32_t i = pos >> 5;
+    const uint32_t w = __funnelshift_l(f[i + 1], f[i], pos & 31u);
+    return n ? w >> (32 - n) : 0u;
+}
+
+// Stage `flen` bytes at src (any alignment) as big-endian words, zero-padded by at least two words.
+__device__ __forceinline__ void l2_stage_frame(uint32_t *fw, const uint8_t *__restrict__ src, int flen, int lane)
+{
+    const int nw = (flen + 3) / 4 + 2;
+    for (int i0 = 0; i0 < nw; i0 += 32) { // warp-uniform trip count
+        const int i = i0 + lane;
+        if (i < nw) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int b = 4 * i + k;
+                w = (w << 8) | (b < flen ? (uint32_t)src[b] : 0u);
+            }
+            fw[i] = w;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(L2_WARPS * 32)
 k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams, const L3FrameRec *__restrict__ frames,
          uint32_t nframes, float *__restrict__ sb_out)
 {
-    __shared__ __align__(4) uint8_t s_frame[L2_WARPS][L2_MAX_FRAME + 12];
+    __shared__ uint32_t s_frame[L2_WARPS][L2_MAX_FRAME / 4 + 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t f = blockIdx.x * L2_WARPS + warp;
     if (f >= nframes) return;
@@ -61,9 +81,9 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     if (!l3_parse_hdr(fr.hdr, &h) || h.layer != 2) return;
     const L3StreamRec sr = streams[fr.stream];
     const uint8_t *src = raw + sr.raw_off + fr.rel_off;
-    uint8_t *fb = s_frame[warp];
+    uint32_t *fb = s_frame[warp];
     const int flen = min(h.frame_len, L2_MAX_FRAME);
-    for (int i = lane; i < flen + 8; i += 32) fb[i] = i < flen ? src[i] : (uint8_t)0;
+    l2_stage_frame(fb, src, flen, lane);
     __syncwarp();
     const uint32_t lim = (uint32_t)flen * 8u;
 
@@ -116,51 +136,62 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
         }
     }
     pos += (uint32_t)tot;
-    // ---- samples: 12 groups; within a group, subbands in order, channels inside a subband
-    int q[2], cbits[2];
+    // ---- samples: 12 groups; within a group, subbands in order, channels inside a subband.  Everything that
+    // depends only on the allocation is worked out once per frame: steps, field width, 1 / steps, and for
+    // the grouped classes (3, 5, 9 steps: one codeword = three base-`steps` digits) a multiply-shift
+    // reciprocal, exact for the 10-bit codewords.
+    int steps[2], fbits[2], cbits[2];
+    uint32_t rmul[2], rsh[2];
+    float inv[2];
     for (int k = 0; k < 2; k++) {
         const int a = k < ncode ? alloc[k] : 0;
-        q[k] = a ? row[a] : -1;
-        const int b = a ? c_l2_bits[q[k]] : 0;
-        cbits[k] = b < 0 ? -b : 3 * b;
+        const int q = a ? row[a] : 0;
+        steps[k] = a ? c_l2_steps[q] : 1;
+        fbits[k] = a ? c_l2_bits[q] : 0;                 // < 0: grouped
+        cbits[k] = fbits[k] < 0 ? -fbits[k] : 3 * fbits[k];
+        rmul[k] = steps[k] == 3 ? 0xAAABu : (steps[k] == 5 ? 0xCCCDu : 0xE38Fu);
+        rsh[k] = steps[k] == 3 ? 17u : (steps[k] == 5 ? 18u : 19u);
+        inv[k] = 1.f / (float)steps[k];
     }
     off = warp_excl_scan(cbits[0] + cbits[1], lane, &tot);
     const uint32_t fi = f - sr.frame_base;
     const size_t u0 = (size_t)sr.unit_base + (size_t)fi * 2u * (size_t)nch;
-    for (int gr = 0; gr < 12; gr++) {
+#pragma unroll
+    for (int part = 0; part < 3; part++) // scalefactor part: compile-time index into scf[][]
+    for (int gr = part * 4; gr < part * 4 + 4; gr++) {
         uint32_t p = pos + (uint32_t)(gr * tot + off);
         float v[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-        for (int k = 0; k < ncode; k++) {
-            if (q[k] < 0) continue;
-            const int steps = c_l2_steps[q[k]], b = c_l2_bits[q[k]];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!cbits[k]) continue;
             int code[3];
-            if (b < 0) {
-                uint32_t c = l2_bits(fb, p, -b, lim);
-                code[0] = (int)(c % (uint32_t)steps);
-                c /= (uint32_t)steps;
-                code[1] = (int)(c % (uint32_t)steps);
-                code[2] = (int)(c / (uint32_t)steps);
+            if (fbits[k] < 0) {
+                const uint32_t c = l2_bits(fb, p, -fbits[k], lim);
+                const uint32_t d1 = (c * rmul[k]) >> rsh[k], d2 = (d1 * rmul[k]) >> rsh[k];
+                code[0] = (int)(c - d1 * (uint32_t)steps[k]);
+                code[1] = (int)(d1 - d2 * (uint32_t)steps[k]);
+                code[2] = (int)d2;
             } else {
+                const int b = fbits[k];
                 code[0] = (int)l2_bits(fb, p, b, lim);
                 code[1] = (int)l2_bits(fb, p + b, b, lim);
                 code[2] = (int)l2_bits(fb, p + 2 * b, b, lim);
             }
             p += (uint32_t)cbits[k];
-            const float inv = 1.f / (float)steps;
+            const float sc0 = scf[0][part] * inv[k], sc1 = scf[1][part] * inv[k], sck = scf[k][part] * inv[k];
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                const float fr3 = (float)(2 * code[i] + 1 - steps) * inv;
-                if (sep) v[k][i] = fr3 * scf[k][gr >> 2];
-                else { v[0][i] = fr3 * scf[0][gr >> 2]; v[1][i] = fr3 * scf[1][gr >> 2]; }
+                const float fr3 = (float)(2 * code[i] + 1 - steps[k]);
+                if (sep) v[k][i] = fr3 * sck;
+                else { v[0][i] = fr3 * sc0; v[1][i] = fr3 * sc1; }
             }
         }
-        for (int ch = 0; ch < nch; ch++)
+        const int g2 = gr >= 6 ? 1 : 0, t0 = (gr - 6 * g2) * 3; // slots 3 gr .. 3 gr + 2 of granule g2
+        for (int ch = 0; ch < nch; ch++) {
+            float *o = sb_out + (u0 + (size_t)g2 * nch + ch) * 576 + (size_t)t0 * 32 + lane;
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const int slot = gr * 3 + i;
-                const size_t u = u0 + (size_t)(slot / 18) * nch + ch;
-                sb_out[u * 576 + (size_t)(slot % 18) * 32 + lane] = v[ch][i];
-            }
+            for (int i = 0; i < 3; i++) o[i * 32] = v[ch][i];
+        }
     }
 }
 
@@ -172,7 +203,7 @@ __global__ void __launch_bounds__(L2_WARPS * 32)
 k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams, const L3FrameRec *__restrict__ frames,
          uint32_t nframes, float *__restrict__ sb_out)
 {
-    __shared__ __align__(4) uint8_t s_frame[L2_WARPS][L2_MAX_FRAME + 12];
+    __shared__ uint32_t s_frame[L2_WARPS][L2_MAX_FRAME / 4 + 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t f = blockIdx.x * L2_WARPS + warp;
     if (f >= nframes) return;
@@ -181,9 +212,9 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     if (!l3_parse_hdr(fr.hdr, &h) || h.layer != 1) return;
     const L3StreamRec sr = streams[fr.stream];
     const uint8_t *src = raw + sr.raw_off + fr.rel_off;
-    uint8_t *fb = s_frame[warp];
+    uint32_t *fb = s_frame[warp];
     const int flen = min(h.frame_len, L2_MAX_FRAME);
-    for (int i = lane; i < flen + 8; i += 32) fb[i] = i < flen ? src[i] : (uint8_t)0;
+    l2_stage_frame(fb, src, flen, lane);
     __syncwarp();
     const uint32_t lim = (uint32_t)flen * 8u;
 
