@@ -204,3 +204,25 @@ def test_side_info_that_overruns_the_stream(mp3b, synth_mod, oracle_mod):
                 scale = max(1.0, float(np.abs(r.pcm).max()))
                 assert np.abs(got - r.pcm.T).max() <= 2.0 ** -14 * scale, i
             assert dec.stats().concealed_frames == sum(r.concealed_frames for r in refs)
+
+
+def test_one_long_stream(mp3b, synth_mod, oracle_mod):
+    """A single 6,000-frame stream (2.6 minutes, joint stereo, mixed block types, bit reservoir in use): the
+    frame chain is walked by one thread and the stream is cut into many tiles -- every sample against the
+    oracle, both output formats, plus the sentence / planar / seek operators on it."""
+    s = synth_mod.make_stream(nframes=6000, seed=77, mode=1, bitrate_kbps=192, blocks=1, mixed_pct=20, fill_lo_pct=40)
+    ref = oracle_mod.decode(s)
+    assert ref.frames == 6000 and ref.concealed_frames == 0
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
+        dec.decode_batch([s])
+        got = dec.stream_pcm(0, dec.fetch_pcm()).astype(np.float64)
+        assert got.shape == ref.pcm.T.shape
+        l3util.assert_iso_full_accuracy(got, ref.pcm.T, "long stream")
+        pl = dec.planar()
+        assert np.array_equal(pl.reshape(2, -1).T, dec.stream_pcm(0, dec.fetch_pcm()))
+        t = 4321 * 1152 + 77
+        sk = mp3b.seek_plan(s, t)
+        full = dec.stream_pcm(0, dec.fetch_pcm()).copy()
+        dec.decode_batch([s[sk.byte_offset:]])
+        part = dec.stream_pcm(0, dec.fetch_pcm())
+        assert np.array_equal(part[sk.discard_samples:], full[t:])
