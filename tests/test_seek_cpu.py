@@ -55,3 +55,30 @@ def test_seek_plan_rejects_bad_arguments(m, synth_mod):
         m.seek_plan(s, -1, frames)
     with pytest.raises(m.Mp3bError):
         m.seek_plan(s, 0, frames[:0])
+
+
+def test_seek_plan_property(m, synth_mod, oracle_mod):
+    """Random stream shapes and targets (hypothesis): the planned slice reproduces the tail exactly, the
+    pre-roll stays bounded, and a slice never starts after its target."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(seed=st.integers(1, 10 ** 6), rate=st.sampled_from([44100, 48000, 32000, 22050, 16000, 11025, 8000]),
+           mode=st.sampled_from([0, 1, 3]), blocks=st.sampled_from([0, 1]), vbr=st.booleans(), frac=st.floats(0.0, 0.999))
+    def check(seed, rate, mode, blocks, vbr, frac):
+        lsf = rate < 32000
+        cfg = dict(nframes=24, seed=seed, sample_rate=rate, mode=mode, blocks=blocks, bitrate_kbps=64 if lsf else 128,
+                   fill_lo_pct=30)
+        if vbr:
+            cfg.update(vbr_min_kbps=32 if lsf else 64, vbr_max_kbps=128 if lsf else 256)
+        s = synth_mod.make_stream(**cfg)
+        full = oracle_mod.decode(s)
+        frames, info, _ = m.index_stream_host(s)
+        t = int(frac * full.samples)
+        sk = m.seek_plan(s, t, frames)
+        spf = full.samples // full.frames
+        assert sk.first_frame <= sk.target_frame == t // spf
+        part = oracle_mod.decode(s[sk.byte_offset:])
+        assert np.array_equal(part.pcm[:, sk.discard_samples:], full.pcm[:, t:])
+
+    check()
