@@ -242,7 +242,7 @@ int mp3b_batch_window_energy(mp3b_ctx *ctx, int stream_index, uint64_t *dst, siz
  * The frame walk of the host indexer (MP3B_INDEX_HOST) as a utility: sync search past ID3v2 / junk,
  * header validation, stream consistency, tag frame.  frames[i] = {byte offset of the header, main-data
  * bytes of the stream before this frame, the 4 header bytes big-endian, 0}.  Returns MP3B_OK,
- * MP3B_E_NOSYNC if no Layer II / III frame was found, MP3B_E_TRUNCATED if cap_frames was too small
+ * MP3B_E_NOSYNC if no Layer I / II / III frame was found, MP3B_E_TRUNCATED if cap_frames was too small
  * (*nframes then holds the number needed). */
 typedef struct mp3b_frame_rec { uint32_t offset, payload_offset, header, reserved; } mp3b_frame_rec;
 int mp3b_index_stream_host(const uint8_t *bytes, size_t n, mp3b_frame_rec *frames, size_t cap_frames,

@@ -189,7 +189,7 @@ class FrameRec(ctypes.Structure):
 
 def index_stream_host(data):
     """Frame index of one stream computed on the host (no GPU): (frames[n] structured array, StreamInfo,
-    TagInfo), or (empty, info, tag) when no Layer III frame is found."""
+    TagInfo), or (empty, info, tag) when no MPEG audio frame is found."""
     L = load_library()
     data = bytes(data)
     n = len(data)
