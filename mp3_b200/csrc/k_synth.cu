@@ -15,7 +15,8 @@
 // of 1024 multiply-adds), one thread per (channel, slot) row; rows have an odd stride so that both the
 // row-per-lane transform and the column-per-lane window are free of bank conflicts.  This kernel is the
 // product path of Layer II (k_layer2.cu) and the last stage of the staged Layer III pipeline.
-// FP32 FMA throughout; lanes write interleaved (L, R) pairs so every store is a full 128-byte row.
+// FP32 FMA throughout; the window is a sliding accumulation (a warp per granule and channel: each of the 33
+// rows it touches is loaded once), the subband samples come in by 16-byte loads.
 // Restates oracle/l3_oracle.c::synth_slot in float32.
 // No reference code exists for this stage (/root/reference/README.md:1-84).
 #include <math.h>
@@ -60,16 +61,20 @@ k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__rest
 
     // ---- load subband samples: history (last 15 slots of the previous granule) + ng granules.
     // units of this stream are contiguous: unit(g, c) = u0 + (g - g0) * nch + c
+    // (16-byte loads: a unit's 576 samples are contiguous and 16-byte aligned; the padded rows take scalar stores)
     for (int c = 0; c < nch; c++) {
         float *dst = s_c + c * (K4_SLOTS * K4_FS);
-        for (int i = threadIdx.x; i < 15 * 32; i += K4_THREADS) {
-            float v = 0.f;
-            if (!first) v = sb[(size_t)(u0 - nch + c) * 576 + 3 * 32 + i];
-            dst[(i >> 5) * K4_FS + (i & 31)] = v;
+        for (int i = threadIdx.x; i < 15 * 8; i += K4_THREADS) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!first) v = __ldg(reinterpret_cast<const float4 *>(sb + (size_t)(u0 - nch + c) * 576 + 3 * 32) + i);
+            float *o = dst + (i >> 3) * K4_FS + (i & 7) * 4;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
         }
-        for (int i = threadIdx.x; i < (int)ng * 576; i += K4_THREADS) {
-            const int gi = i / 576, r = i % 576;
-            dst[(15 + (i >> 5)) * K4_FS + (i & 31)] = sb[(size_t)(u0 + gi * nch + c) * 576 + r];
+        for (int i = threadIdx.x; i < (int)ng * 144; i += K4_THREADS) {
+            const int gi = i / 144, r = i - gi * 144;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(sb + (size_t)(u0 + gi * nch + c) * 576) + r);
+            float *o = dst + (15 + gi * 18 + (r >> 3)) * K4_FS + (r & 7) * 4;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
         }
     }
     __syncthreads();
@@ -86,40 +91,38 @@ k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__rest
     }
     __syncthreads();
 
-    // ---- windowing
+    // ---- windowing: a warp per (granule, channel); sliding accumulation over the 33 rows a granule's 18
+    // output slots touch: each row is loaded once (2 LDS) and feeds the up to 16 outputs it contributes to,
+    // the 16-entry accumulator ring and the window taps live in registers (everything is unrolled)
     {
         float w[16];
 #pragma unroll
         for (int l = 0; l < 16; l++) w[l] = g_synwin[l][lane];
         const int src_e = lane <= 15 ? 16 + lane : (lane == 16 ? 0 : 48 - lane); // lane 16: weight is 0
         const int src_o = lane <= 16 ? 16 - lane : lane - 16;
-        for (int t = warp; t < (int)ng * 18; t += nwarps) {
-            const int T = 15 + t;
-            float out[2] = {0.f, 0.f};
-            for (int c = 0; c < nch; c++) {
-                const float *base = s_c + c * (K4_SLOTS * K4_FS) + T * K4_FS;
-                float acc = 0.f;
+        for (int task = warp; task < (int)ng * nch; task += nwarps) {
+            const int gi = task / nch, c = task - gi * nch;
+            const float *Fc = s_c + c * (K4_SLOTS * K4_FS) + gi * 18 * K4_FS; // rows T0 - 15 .. T0 + 17 of this granule
+            // PCM element index of (granule gi, slot 0, sample lane, channel c)
+            const size_t e0 = (size_t)(u0 + gi * nch) * 576 + (size_t)lane * nch + c;
+            float acc[16];
 #pragma unroll
-                for (int l = 0; l < 16; l += 2) {
-                    acc = fmaf(w[l], base[-l * K4_FS + src_e], acc);
-                    acc = fmaf(w[l + 1], base[-(l + 1) * K4_FS + src_o], acc);
+            for (int i = 0; i < 16; i++) acc[i] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 33; q++) {
+                const float e = Fc[q * K4_FS + src_e], o = Fc[q * K4_FS + src_o];
+#pragma unroll
+                for (int l = 0; l < 16; l++) {
+                    const int T = q + l - 15;
+                    if (T >= 0 && T < 18) acc[T & 15] = fmaf(w[l], (l & 1) ? o : e, acc[T & 15]);
                 }
-                out[c] = acc;
-            }
-            // PCM element index of (granule gi, slot tt, sample lane, channel 0)
-            const int gi = t / 18, tt = t % 18;
-            const size_t e0 = (size_t)(u0 + gi * nch) * 576 + (size_t)(tt * 32 + lane) * nch;
-            if (FMT == MP3B_PCM_S16) {
-                int16_t *p = reinterpret_cast<int16_t *>(pcm);
-                if (nch == 2) {
-                    const uint32_t pk = (uint16_t)to_s16(out[0]) | ((uint32_t)(uint16_t)to_s16(out[1]) << 16);
-                    *reinterpret_cast<uint32_t *>(p + e0) = pk;
-                } else
-                    p[e0] = to_s16(out[0]);
-            } else {
-                float *p = reinterpret_cast<float *>(pcm);
-                if (nch == 2) *reinterpret_cast<float2 *>(p + e0) = make_float2(out[0], out[1]);
-                else p[e0] = out[0];
+                if (q >= 15) {
+                    const float val = acc[(q - 15) & 15];
+                    acc[(q - 15) & 15] = 0.f;
+                    const size_t e1 = e0 + (size_t)(q - 15) * 32 * nch;
+                    if (FMT == MP3B_PCM_S16) reinterpret_cast<int16_t *>(pcm)[e1] = to_s16(val);
+                    else reinterpret_cast<float *>(pcm)[e1] = val;
+                }
             }
         }
     }
