@@ -23,7 +23,16 @@ __constant__ uint8_t c_l2_rows[8][16];
 __constant__ uint8_t c_l2_row_of_sb[5][30];
 __constant__ int32_t c_l2_steps[17];
 __constant__ int8_t c_l2_bits[17];
-__constant__ float c_l2_scf[64]; // 2^(1 - i / 3); index 63 is not a scalefactor: 0
+
+// Scalefactor 2^(1 - i / 3) for index i < 63, 0 for the forbidden index 63: a power of two times one of three
+// cube-root factors, which is the correctly rounded table value (the index differs from lane to lane, and a
+// lane-varying index into __constant__ memory is replayed once per distinct address).
+__device__ __forceinline__ float l2_scf_of(uint32_t i)
+{
+    const uint32_t q = (i * 171u) >> 9, r = i - 3u * q; // i / 3, i % 3 for i < 64
+    const float m = r == 0 ? 1.f : (r == 1 ? 0.79370052598409979f : 0.62996052494743658f);
+    return i >= 63u ? 0.f : __int_as_float((128u - q) << 23) * m;
+}
 
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total)
 {
@@ -50,10 +59,10 @@ __device__ __forceinline__ uint32_t l2_bits(const uint32_t *f, uint32_t pos, int
     return n ? w >> (32 - n) : 0u;
 }
 
-// Stage `flen` bytes at src (any alignment) as big-endian words, zero-padded by at least two words.
+// Stage `flen` bytes at src (any alignment) as big-endian words, zero-padded by at least three words.
 __device__ __forceinline__ void l2_stage_frame(uint32_t *fw, const uint8_t *__restrict__ src, int flen, int lane)
 {
-    const int nw = (flen + 3) / 4 + 2;
+    const int nw = (flen + 3) / 4 + 3;
     for (int i0 = 0; i0 < nw; i0 += 32) { // warp-uniform trip count
         const int i = i0 + lane;
         if (i < nw) {
@@ -123,16 +132,21 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     off = warp_excl_scan(6 * (nsf[0] + nsf[1]), lane, &tot);
     float scf[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     {
+        // one instruction stream for all lanes: an 18-bit window per channel, the indices picked by scfsi
         uint32_t p = pos + off;
-        for (int ch = 0; ch < nch; ch++) {
-            if (!alloc[ch]) continue;
-            const float a = c_l2_scf[l2_bits(fb, p, 6, lim)];
-            p += 6;
-            float b = a, c = a;
-            if (scfsi[ch] == 0) { b = c_l2_scf[l2_bits(fb, p, 6, lim)]; c = c_l2_scf[l2_bits(fb, p + 6, 6, lim)]; p += 12; }
-            else if (scfsi[ch] == 1) { c = c_l2_scf[l2_bits(fb, p, 6, lim)]; p += 6; }
-            else if (scfsi[ch] == 3) { b = c = c_l2_scf[l2_bits(fb, p, 6, lim)]; p += 6; }
-            scf[ch][0] = a; scf[ch][1] = b; scf[ch][2] = c;
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+            const uint32_t w18 = l2_bits(fb, p, 18, lim);
+            const uint32_t i0 = w18 >> 12, i1 = (w18 >> 6) & 63u, i2 = w18 & 63u;
+            const int sel = scfsi[ch];
+            const float a = l2_scf_of(i0), s1 = l2_scf_of(i1), s2 = l2_scf_of(i2);
+            const float b = sel == 0 || sel == 3 ? s1 : a;                      // 0: a b c   1: a a b   2: a a a   3: a b b
+            const float c = sel == 0 ? s2 : (sel == 2 ? a : s1);
+            const bool on_ch = nsf[ch] != 0;
+            scf[ch][0] = on_ch ? a : 0.f;
+            scf[ch][1] = on_ch ? b : 0.f;
+            scf[ch][2] = on_ch ? c : 0.f;
+            p += 6u * (uint32_t)nsf[ch];
         }
     }
     pos += (uint32_t)tot;
@@ -161,29 +175,35 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     for (int gr = part * 4; gr < part * 4 + 4; gr++) {
         uint32_t p = pos + (uint32_t)(gr * tot + off);
         float v[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        // one instruction stream for every lane, whatever its allocation class: a 64-bit window at the code
+        // set, three fields of the class's width (a grouped class uses the first only and splits it), selects
+        // instead of branches -- lanes of one warp hold different classes, a branch here ran 7 of 32 lanes
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            if (!cbits[k]) continue;
+            const uint32_t pc = min(p, lim), wi = pc >> 5, sh = pc & 31u;
+            const uint32_t hi0 = __funnelshift_l(fb[wi + 1], fb[wi], sh), lo0 = __funnelshift_l(fb[wi + 2], fb[wi + 1], sh);
+            const bool grouped = fbits[k] < 0;
+            const int nb = grouped ? -fbits[k] : fbits[k]; // 0 (no samples) .. 16
+            const uint32_t f0 = __funnelshift_l(hi0, 0u, nb);
+            const uint32_t hi1 = __funnelshift_l(lo0, hi0, nb), lo1 = lo0 << nb;
+            const uint32_t f1 = __funnelshift_l(hi1, 0u, nb);
+            const uint32_t f2 = __funnelshift_l(__funnelshift_l(lo1, hi1, nb), 0u, nb);
+            const uint32_t d1 = (f0 * rmul[k]) >> rsh[k], d2 = (d1 * rmul[k]) >> rsh[k];
             int code[3];
-            if (fbits[k] < 0) {
-                const uint32_t c = l2_bits(fb, p, -fbits[k], lim);
-                const uint32_t d1 = (c * rmul[k]) >> rsh[k], d2 = (d1 * rmul[k]) >> rsh[k];
-                code[0] = (int)(c - d1 * (uint32_t)steps[k]);
-                code[1] = (int)(d1 - d2 * (uint32_t)steps[k]);
-                code[2] = (int)d2;
-            } else {
-                const int b = fbits[k];
-                code[0] = (int)l2_bits(fb, p, b, lim);
-                code[1] = (int)l2_bits(fb, p + b, b, lim);
-                code[2] = (int)l2_bits(fb, p + 2 * b, b, lim);
-            }
+            code[0] = (int)(grouped ? f0 - d1 * (uint32_t)steps[k] : f0);
+            code[1] = (int)(grouped ? d1 - d2 * (uint32_t)steps[k] : f1);
+            code[2] = (int)(grouped ? d2 : f2);
             p += (uint32_t)cbits[k];
+            const bool on_k = cbits[k] != 0;
             const float sc0 = scf[0][part] * inv[k], sc1 = scf[1][part] * inv[k], sck = scf[k][part] * inv[k];
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                const float fr3 = (float)(2 * code[i] + 1 - steps[k]);
-                if (sep) v[k][i] = fr3 * sck;
-                else { v[0][i] = fr3 * sc0; v[1][i] = fr3 * sc1; }
+                const float fr3 = on_k ? (float)(2 * code[i] + 1 - steps[k]) : 0.f;
+                if (k == 0) { // the first code set feeds channel 0, and channel 1 too above the joint-stereo bound
+                    v[0][i] = fr3 * (sep ? sck : sc0);
+                    if (!sep) v[1][i] = fr3 * sc1;
+                } else if (on_k) // a second code set exists only where the channels are coded separately
+                    v[1][i] = fr3 * sck;
             }
         }
         const int g2 = gr >= 6 ? 1 : 0, t0 = (gr - 6 * g2) * 3; // slots 3 gr .. 3 gr + 2 of granule g2
@@ -235,7 +255,7 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     {
         uint32_t p = pos + off;
         for (int ch = 0; ch < nch; ch++)
-            if (alloc[ch]) { scf[ch] = c_l2_scf[l2_bits(fb, p, 6, lim)]; p += 6; }
+            if (alloc[ch]) { scf[ch] = l2_scf_of(l2_bits(fb, p, 6, lim)); p += 6; }
     }
     pos += (uint32_t)tot;
     int cb[2];
@@ -272,14 +292,10 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
 
 void l3_layer2_init(void)
 {
-    float scf[64];
-    for (int i = 0; i < 63; i++) scf[i] = (float)pow(2.0, 1.0 - i / 3.0);
-    scf[63] = 0.f;
     cudaMemcpyToSymbol(c_l2_rows, l2_rows, sizeof l2_rows);
     cudaMemcpyToSymbol(c_l2_row_of_sb, l2_row_of_sb, sizeof l2_row_of_sb);
     cudaMemcpyToSymbol(c_l2_steps, l2_quant_steps, sizeof l2_quant_steps);
     cudaMemcpyToSymbol(c_l2_bits, l2_quant_bits, sizeof l2_quant_bits);
-    cudaMemcpyToSymbol(c_l2_scf, scf, sizeof scf);
 }
 
 void l3_launch_layer2(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames, uint32_t nframes,
