@@ -345,8 +345,8 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
                          "whole_pipeline": {"algorithmic_bytes_per_unit": in_per_unit + 1152.0,
                                             "achieved": (in_per_unit + 1152.0) * units / (ms_dev * 1e-3) / 1e9,
                                             "frac": (in_per_unit + 1152.0) * units / (ms_dev * 1e-3) / 1e9 / hbm_peak},
-                         "note": "the back end is FP32 / shared-memory issue bound, not HBM bound (ncu: issue 71 %, LSU "
-                                 "58 %, FMA 37 %, DRAM 10 %); its DRAM traffic is at the algorithmic bytes (profiles/)"},
+                         "note": "the back end is FP32 / shared-memory issue bound, not HBM bound (ncu: issue 74 %, LSU "
+                                 "67 %, FMA 37 %, DRAM 10 %); its DRAM traffic is at the algorithmic bytes (profiles/)"},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "first %d streams of the workload (%.1f s of wall time on %d threads = %.0f s of "
                                        "CPU work), oracle/l3_oracle.c, one stream per host thread" % (
