@@ -258,21 +258,30 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
             if (alloc[ch]) { scf[ch] = l2_scf_of(l2_bits(fb, p, 6, lim)); p += 6; }
     }
     pos += (uint32_t)tot;
-    int cb[2];
-    for (int k = 0; k < 2; k++) cb[k] = (k < ncode && alloc[k]) ? alloc[k] + 1 : 0;
+    // per code set: field width, steps and 1 / steps (0 for "no samples" and for the forbidden allocation 15),
+    // worked out once; the sample loop is then one instruction stream for all lanes
+    int cb[2], stp[2];
+    float inv[2];
+    for (int k = 0; k < 2; k++) {
+        cb[k] = (k < ncode && alloc[k]) ? alloc[k] + 1 : 0;
+        stp[k] = (1 << cb[k]) - 1;
+        inv[k] = (cb[k] && alloc[k] != 15) ? 1.f / (float)stp[k] : 0.f;
+    }
     off = warp_excl_scan(cb[0] + cb[1], lane, &tot);
     const uint32_t fi = f - sr.frame_base;
     for (int t = 0; t < 12; t++) {
         uint32_t p = pos + (uint32_t)(t * tot + off);
         float v[2] = {0.f, 0.f};
-        for (int k = 0; k < ncode; k++) {
-            if (!cb[k]) continue;
-            const int steps = (1 << cb[k]) - 1;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
             const int code = (int)l2_bits(fb, p, cb[k], lim);
             p += (uint32_t)cb[k];
-            const float fr3 = alloc[k] == 15 ? 0.f : (float)(2 * code + 1 - steps) / (float)steps;
-            if (sep) v[k] = fr3 * scf[k];
-            else { v[0] = fr3 * scf[0]; v[1] = fr3 * scf[1]; }
+            const float fr3 = (float)(2 * code + 1 - stp[k]) * inv[k];
+            if (k == 0) {
+                v[0] = fr3 * scf[0];
+                if (!sep) v[1] = fr3 * scf[1];
+            } else if (cb[1])
+                v[1] = fr3 * scf[1];
         }
         const uint32_t slot = fi * 12u + (uint32_t)t;
         for (int ch = 0; ch < nch; ch++) {
