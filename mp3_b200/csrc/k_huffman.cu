@@ -629,12 +629,10 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     // Chunk length and stage size: as many CTAs per SM as still leave every warp a few groups to pull.
     // The stage holds the chunk's main data (average bytes per unit plus slack); a chunk whose range
     // does not fit (VBR peaks) takes the global-memory reader.
-    static long f_stage = -1, f_chunk = -1;
-    if (f_stage < 0) {
-        const char *e = getenv("MP3B_K1_STAGE"), *c = getenv("MP3B_K1_CHUNK");
-        f_stage = e ? atol(e) : 0;
-        f_chunk = c ? atol(c) : 0;
-    }
+    // tuning overrides, read once (function-local statics: initialisation is thread-safe, contexts on several
+    // host threads may get here together)
+    static const long f_stage = [] { const char *e = getenv("MP3B_K1_STAGE"); return e ? atol(e) : 0l; }();
+    static const long f_chunk = [] { const char *e = getenv("MP3B_K1_CHUNK"); return e ? atol(e) : 0l; }();
     const uint64_t per_unit = (uint64_t)avg_unit_bytes + avg_unit_bytes / 24 + 1;
     const uint64_t fixed = lut_bytes + 6656 + 1024; // LUT, static shared memory, per-CTA reservation
     uint64_t want = 0;

@@ -215,8 +215,10 @@ void l3_launch_segments(const void *pcm, int pcm_format, const L3SegJob *jobs, i
                         cudaStream_t st)
 {
     if (njobs <= 0) return;
-    static int wpw = -1; // window groups per warp
-    if (wpw < 0) { const char *e = getenv("MP3B_SG_WPW"); wpw = e ? std::max(1, atoi(e)) : 8; }
+    static const int wpw = [] { // window groups per warp (tuning override, read once, thread-safe)
+        const char *e = getenv("MP3B_SG_WPW");
+        return e ? std::max(1, atoi(e)) : 8;
+    }();
     const unsigned per_cta = (unsigned)(SG_WARPS * SG_NW * wpw);
     const unsigned nx = std::min(65535u, std::max(1u, (max_nwin + per_cta - 1) / per_cta));
     const dim3 grid(nx, (unsigned)std::min(njobs, 65535), (unsigned)((njobs + 65534) / 65535));
