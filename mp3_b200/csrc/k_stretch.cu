@@ -42,24 +42,47 @@ template <> __device__ __forceinline__ int ts_s16<float>(const float *p)
     asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r) : "f"(*p * 32768.f));
     return (int)(short)r;
 }
-template <typename T> __device__ __forceinline__ float ts_f(const T *p);
-template <> __device__ __forceinline__ float ts_f<int16_t>(const int16_t *p) { return (float)*p * (1.f / 32768.f); }
-template <> __device__ __forceinline__ float ts_f<float>(const float *p) { return *p; }
-__device__ __forceinline__ void ts_store(int16_t *p, float v)
+// one frame (1 or 2 channels) as floats; stereo frames are element-pair aligned (pcm offsets of stereo streams are even)
+template <typename T> __device__ __forceinline__ void ts_load_frame(const T *p, int nch, float &l, float &r);
+template <> __device__ __forceinline__ void ts_load_frame<int16_t>(const int16_t *p, int nch, float &l, float &r)
 {
-    int r;
-    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r) : "f"(v * 32768.f));
-    *p = (int16_t)r;
+    if (nch == 2) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+        l = (float)(short)(w & 0xffffu) * (1.f / 32768.f);
+        r = (float)((int)w >> 16) * (1.f / 32768.f);
+    } else
+        l = (float)*p * (1.f / 32768.f);
 }
-__device__ __forceinline__ void ts_store(float *p, float v) { *p = v; }
-
-// alignment signal at input frame n (zero outside [0, in_n))
-template <typename T>
-__device__ __forceinline__ int ts_align(const T *x, long long n, long long in_n, int nch)
+template <> __device__ __forceinline__ void ts_load_frame<float>(const float *p, int nch, float &l, float &r)
 {
-    if (n < 0 || n >= in_n) return 0;
-    int v = nch == 2 ? (ts_s16<T>(x + n * 2) + ts_s16<T>(x + n * 2 + 1)) >> 9 : ts_s16<T>(x + n) >> 8;
-    return max(-127, min(127, v));
+    if (nch == 2) {
+        const float2 w = *reinterpret_cast<const float2 *>(p);
+        l = w.x;
+        r = w.y;
+    } else
+        l = *p;
+}
+__device__ __forceinline__ void ts_store_frame(int16_t *p, int nch, float l, float r)
+{
+    int a, b;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(a) : "f"(l * 32768.f));
+    if (nch == 2) {
+        asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(b) : "f"(r * 32768.f));
+        *reinterpret_cast<uint32_t *>(p) = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+    } else
+        *p = (int16_t)a;
+}
+__device__ __forceinline__ void ts_store_frame(float *p, int nch, float l, float r)
+{
+    if (nch == 2) *reinterpret_cast<float2 *>(p) = make_float2(l, r);
+    else *p = l;
+}
+
+// L + R of one stereo frame in the s16 domain (the alignment signal is (L + R) >> 9)
+template <typename T> __device__ __forceinline__ int ts_pair_sum(const T *p) { return ts_s16<T>(p) + ts_s16<T>(p + 1); }
+template <> __device__ __forceinline__ int ts_pair_sum<int16_t>(const int16_t *p) // stereo frames are 4-byte aligned
+{
+    return __dp2a_lo((int)*reinterpret_cast<const uint32_t *>(p), 0x0101, 0);
 }
 
 template <typename T>
@@ -73,6 +96,7 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
     __shared__ __align__(16) signed char s_r2[3 * TS_MAX_HS / 2 + 32]; // region, every second sample
     __shared__ int s_best[TS_THREADS / 32], s_bestd[TS_THREADS / 32];
     __shared__ long long s_p;
+    __shared__ float s_w[TS_MAX_HS]; // the cross-fade window, once per CTA
     const L3StretchJob jb = jobs[blockIdx.x];
     const int nch = jb.channels, Hs = jb.hop, N = 2 * Hs, R = Hs / 2;
     const T *x = in + jb.in_off;
@@ -80,21 +104,31 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long nseg = (jb.out_n + Hs - 1) / Hs;
     const float wstep = 3.14159265358979323846f / (float)Hs;
+    for (int k = tid; k < Hs; k += TS_THREADS) s_w[k] = 0.5f - 0.5f * cosf(wstep * (float)k);
+    __syncthreads();
     long long p_prev = 0;
     for (long long m = 0; m < nseg; m++) {
         long long p = 0;
         if (m > 0) {
             const long long a = (m * Hs * (long long)num) / den, tpos = p_prev + Hs;
-            for (int i = tid; i < N; i += TS_THREADS) {
-                const signed char v = (signed char)ts_align<T>(x, tpos + i, jb.in_n, nch);
-                s_t[i] = v;
-                if (!(i & 1)) s_t2[i >> 1] = v;
-            }
-            for (int i = tid; i < N + 2 * R + 16; i += TS_THREADS) {
-                const signed char v = (signed char)(i < N + 2 * R ? ts_align<T>(x, a - R + i, jb.in_n, nch) : 0);
-                s_r[i] = v;
-                if (!(i & 1)) s_r2[i >> 1] = v;
-            }
+            // alignment signal of the template and of the search region: 32-bit indices relative to the
+            // piece's first frame, the valid range [lo, hi) worked out once per piece
+            auto fill = [&](signed char *dst, signed char *dst2, long long start, int count, int padded) {
+                const int lo = (int)max(0ll, min(-start, (long long)count));
+                const int hi = (int)max(0ll, min(jb.in_n - start, (long long)count));
+                for (int i = tid; i < padded; i += TS_THREADS) {
+                    int v = 0;
+                    if (i >= lo && i < hi) {
+                        const T *q = x + (start + i) * nch;
+                        v = nch == 2 ? ts_pair_sum<T>(q) >> 9 : ts_s16<T>(q) >> 8;
+                        v = max(-127, min(127, v));
+                    }
+                    dst[i] = (signed char)v;
+                    if (!(i & 1)) dst2[i >> 1] = (signed char)v;
+                }
+            };
+            fill(s_t, s_t2, tpos, N, N);
+            fill(s_r, s_r2, a - R, N + 2 * R, N + 2 * R + 16);
             __syncthreads();
             // ---- coarse: candidates d = -R + 4 j, every second sample; region byte 4 j = decimated byte 2 j
             int best = INT_MIN, bestd = 0;
@@ -105,7 +139,8 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
                     const unsigned sh = (unsigned)(j & 1) * 16u;
                     int acc = 0;
                     unsigned lo = rw[0];
-                    for (int k = 0; k < N / 8; k++) {
+#pragma unroll 8
+                    for (int k = 0; k < N / 8; k++) { // N / 8 is 32, 64 or 128
                         const unsigned hi = rw[k + 1];
                         acc = __dp4a((int)__funnelshift_r(lo, hi, sh), tw[k], acc);
                         lo = hi;
@@ -163,18 +198,24 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
             offsets_out[(size_t)blockIdx.x * max_frames] = 0;
         // output segment m
         const long long o0 = m * Hs;
-        for (int i = tid; i < Hs * nch; i += TS_THREADS) {
-            const int k = i / nch, c = i - k * nch;
-            if (o0 + k >= jb.out_n) continue;
-            const long long ia = p + k, ib = p_prev + Hs + k;
-            const float va = (ia >= 0 && ia < jb.in_n) ? ts_f<T>(x + ia * nch + c) : 0.f;
-            float v = va;
-            if (m > 0) {
-                const float vb = (ib >= 0 && ib < jb.in_n) ? ts_f<T>(x + ib * nch + c) : 0.f;
-                const float w = 0.5f - 0.5f * cosf(wstep * (float)k);
-                v = (1.f - w) * vb + w * va;
+        {
+            // a thread per output frame (both channels); valid input ranges as 32-bit offsets, once per segment
+            const int kmax = (int)min((long long)Hs, jb.out_n - o0);
+            const long long sa = p, sb = p_prev + Hs;
+            const int alo = (int)max(0ll, min(-sa, (long long)Hs)), ahi = (int)max(0ll, min(jb.in_n - sa, (long long)Hs));
+            const int blo = (int)max(0ll, min(-sb, (long long)Hs)), bhi = (int)max(0ll, min(jb.in_n - sb, (long long)Hs));
+            for (int k = tid; k < kmax; k += TS_THREADS) {
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                if (k >= alo && k < ahi) ts_load_frame<T>(x + (sa + k) * nch, nch, a0, a1);
+                float v0 = a0, v1 = a1;
+                if (m > 0) {
+                    if (k >= blo && k < bhi) ts_load_frame<T>(x + (sb + k) * nch, nch, b0, b1);
+                    const float w = s_w[k];
+                    v0 = (1.f - w) * b0 + w * a0;
+                    v1 = (1.f - w) * b1 + w * a1;
+                }
+                ts_store_frame(y + (o0 + k) * nch, nch, v0, v1);
             }
-            ts_store(y + (o0 + k) * nch + c, v);
         }
         p_prev = p;
         __syncthreads(); // s_t / s_r are rewritten by the next frame
