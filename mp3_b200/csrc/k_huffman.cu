@@ -22,6 +22,7 @@
 // Output is bit-exact by construction (integer work only) and is compared word for word with
 // oracle/l3_oracle.c::huffman_decode / read_scalefactors in tests/test_gpu_parity.py.
 // No reference code exists for this stage (/root/reference/README.md:1-84).
+#include <algorithm>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -39,6 +40,7 @@ __constant__ uint8_t c_lsf_nsfb[6][3][4] = {
 
 constexpr int K1_THREADS = 256;
 constexpr int K1_CHUNK = 512;       // most units per CTA (16 groups of 32 for 8 warps)
+constexpr uint64_t K1_MAX_DYN_SMEM = 200 * 1024; // dynamic shared memory the kernel may be launched with
 constexpr int K1_TAIL_PAD = 160;    // bytes staged beyond the last unit's part2_3 end (look-ahead, overruns)
 
 __device__ __forceinline__ uint32_t bits_at(const uint8_t *arena, uint64_t arena_bytes, uint64_t bit, int n);
@@ -622,7 +624,7 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     // that do not fit (high bitrates, VBR peaks) take the global-memory reader
     static std::atomic<unsigned long long> configured{0};
     if (l3_device_needs_setup(configured)) {
-        cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_DYN_SMEM);
         l3_device_setup_done(configured);
     }
     const uint64_t lut_bytes = ((uint64_t)T.huff_lut_len * sizeof(uint16_t) + 15) & ~15ull;
@@ -640,7 +642,9 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     // prefer 4 CTAs per SM if they get >= 8 groups each (measured: 0.88 ms against 0.91 with 3 x 480 units;
     // the code tables through L1 instead of a shared copy, to make room for a fifth CTA: 1.05 - 1.16 ms)
     for (int k = 4; k >= 1 && chunk < 256; k--) {
-        const uint64_t budget = (227ull * 1024 / k - fixed) & ~15ull;
+        // never more dynamic shared memory than the kernel was given (200 KB): large units -- 160 kbit/s mono at
+        // 8 kHz is 1,440 bytes per unit -- would otherwise ask for more at one CTA per SM and fail to launch
+        const uint64_t budget = std::min<uint64_t>(227ull * 1024 / k - fixed, K1_MAX_DYN_SMEM - lut_bytes) & ~15ull;
         uint64_t c = (budget - 1280) / per_unit / 32 * 32;
         c = c > K1_CHUNK ? K1_CHUNK : c;
         if (c >= 32) { chunk = (uint32_t)c; want = (c * per_unit + 1280 + 15) & ~15ull; }
@@ -648,6 +652,7 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     if (!chunk) { chunk = 32; want = 32 * 1024; }
     if (f_chunk > 0) { chunk = (uint32_t)(f_chunk > K1_CHUNK ? K1_CHUNK : f_chunk) / 32 * 32; want = (chunk * per_unit + 1280 + 15) & ~15ull; }
     if (f_stage > 0) want = ((uint64_t)f_stage + 15) & ~15ull;
+    want = std::min<uint64_t>(want, (K1_MAX_DYN_SMEM - lut_bytes) & ~15ull); // (overrides included; a chunk that does not fit reads global memory)
     const size_t smem = (size_t)(want + lut_bytes);
     k_huffman<<<(nunits + chunk - 1) / chunk, K1_THREADS, smem, st>>>(
         arena, arena_bytes, units, u_lo, nunits, T.huff_lut, T.huff_lut_len, (uint32_t)want, chunk, T.huff, T.quad_a,

@@ -226,3 +226,23 @@ def test_one_long_stream(mp3b, synth_mod, oracle_mod):
         dec.decode_batch([s[sk.byte_offset:]])
         part = dec.stream_pcm(0, dec.fetch_pcm())
         assert np.array_equal(part[sk.discard_samples:], full[t:])
+
+
+def test_batches_of_large_units(mp3b, synth_mod, oracle_mod):
+    """Low sample rate, high bitrate, mono: up to 1,440 bytes of frame per granule-channel.  Such a batch on
+    its own makes the Huffman kernel's bit stage as large as it gets (found by tools/fuzz_incremental.py: the
+    launch once asked for more shared memory than the kernel may have)."""
+    cfgs = [dict(nframes=10, seed=758025, sample_rate=12000, mode=3, bitrate_kbps=64, fill_lo_pct=30,
+                 vbr_min_kbps=32, vbr_max_kbps=128),
+            dict(nframes=12, seed=5, sample_rate=8000, mode=3, bitrate_kbps=160, blocks=1),
+            dict(nframes=12, seed=6, sample_rate=16000, mode=3, bitrate_kbps=160, fill_lo_pct=20),
+            dict(nframes=12, seed=7, sample_rate=32000, mode=3, bitrate_kbps=320, blocks=1, mixed_pct=30)]
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
+        for c in cfgs:  # each on its own: the stage is sized by the batch's average unit
+            s = synth_mod.make_stream(**c)
+            ref = oracle_mod.decode(s)
+            dec.decode_batch([s])
+            got = dec.stream_pcm(0, dec.fetch_pcm()).astype(np.float64)
+            assert got.shape == ref.pcm.T.shape, c
+            scale = max(1.0, float(np.abs(ref.pcm).max()))
+            l3util.assert_iso_full_accuracy(got / scale, ref.pcm.T / scale, str(c))
