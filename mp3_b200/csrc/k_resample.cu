@@ -237,10 +237,10 @@ void l3_launch_resample(const void *in, void *out, int pcm_format, const L3Resam
     // is a multiple of L
     if (taps == 65 || taps == 71 || taps == 97 || taps == 129) {
         const int T = L * ((128 + L - 1) / L); // threads per CTA = outputs per block: a multiple of L
-        if (T <= 320) {
-            const long long S = T;
-            const int span = (int)((RU_NB * S / L) * M) + taps + 4;
-            const size_t smem = (size_t)span * 2 * sizeof(float);
+        const long long S = T;
+        const int span = (int)((RU_NB * S / L) * M) + taps + 4;
+        const size_t smem = (size_t)span * 2 * sizeof(float);
+        if (T <= 320 && smem <= 48 * 1024) { // (the default dynamic shared-memory limit: odd rate pairs can exceed it)
             const long long chunks = (max_out_n + RU_NB * S - 1) / (RU_NB * S);
             long long want = (2048 + njobs - 1) / njobs;
             const unsigned gx = (unsigned)(want < 1 ? 1 : (want > chunks ? chunks : want));

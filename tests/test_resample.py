@@ -38,7 +38,7 @@ def test_filter_properties(rin, rout):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["f32", "s16"])
-@pytest.mark.parametrize("out_rate", [48000, 44100, 32000, 22050, 16000])
+@pytest.mark.parametrize("out_rate", [48000, 44100, 32000, 22100, 22050, 16000])
 def test_resample_matches_upfirdn(fmt, out_rate, synth_mod):
     from scipy.signal import upfirdn
     import mp3_b200 as m
@@ -80,3 +80,16 @@ def test_resample_matches_upfirdn(fmt, out_rate, synth_mod):
             else:
                 want = np.clip(np.round(ref * 32768.0), -32768, 32767)
                 assert np.abs(got - want).max() <= 1
+
+
+@pytest.mark.gpu
+def test_unusable_rate_pair_is_refused(synth_mod):
+    """A rate pair whose ratio needs more than 4,096 phases is refused with an error, not attempted."""
+    import mp3_b200 as m
+    with m.Decoder(device=0) as dec:
+        dec.decode_batch([synth_mod.make_stream(nframes=4, seed=1)])
+        with pytest.raises(m.Mp3bError):
+            dec.resample(47999)
+        dec.resample(48000)  # the context is still usable
+        out, where = dec.fetch_resampled()
+        assert where[0][1] > 0
