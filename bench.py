@@ -9,11 +9,17 @@ A "step" is one pass of the hot path over one batch of synthetic streams (BASELI
 decodes its own 1,024 streams); the only torch.distributed traffic is the barrier and the
 max-over-ranks of the timing.
 
-  value    = audio-seconds decoded per second, inputs (raw MP3 bytes) resident in HBM, PCM left in HBM
-  e2e      = the same metric through the C-ABI with pinned HOST buffers: H2D of the MP3 bytes and D2H
-             of the PCM inside the timed region
-  roofline = the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
-  cpu_baseline = the scalar from-spec oracle (oracle/l3_oracle.c) on the host cores, bounded sample
+  value        = audio-seconds decoded per second, inputs (raw MP3 bytes) resident in HBM, PCM left in HBM
+  e2e          = the same metric through the C-ABI with pinned HOST buffers: H2D of the MP3 bytes and D2H
+                 of the PCM inside the timed region; e2e.pcie_floor_ms = the same two copies alone
+  splits       = SURVEY.md 8(d) (i)-(iv): decode kernels only / + H2D / + indexing / + D2H
+  roofline     = the dominant kernel (the fused back end): executed and direct-form-effective FP32 flops
+                 against the MEASURED FP32 peak (profiles/fp32_peak.json), and the HBM view of the whole
+                 pipeline at SURVEY.md 8(d)'s 1256.5 algorithmic bytes per unit
+  parity_checked = streams compared with the oracle inside this run, before anything is timed
+  sweep_cfg5   = BASELINE.json configs[4]: 100,000 streams x 128 frames sharded over the N ranks (strong scaling)
+  cpu_baseline = the scalar from-spec oracle (oracle/l3_oracle.c) on the host cores, bounded sample;
+                 cpu_lines = oracle 1 thread / all threads and FFmpeg mp3float 1 thread / all threads
 
 `--impl reference` times the reference's CPU implementation of the path.  The reference repository
 ships no code (/root/reference/README.md:1-84), so that arm is the oracle port on all host threads.
@@ -32,6 +38,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "decoded_audio_seconds_per_second"
 UNIT = "audio-s/s"
+FUSED_IDEAL_PCM_BYTES = 1152.0          # 576 s16 samples out per unit
+DIRECT_FORM_FLOP_PER_UNIT = 137088.0    # 67,968 MAC, direct (definition) form
 
 
 # ------------------------------------------------------------------------------------ helpers
@@ -55,10 +63,23 @@ DEFAULT_FRAMES = {"cfg5": 128}
 DEFAULT_STREAMS = {"cfg1": 1, "cfg5": 100000}
 
 
+def workload_string(args, streams_per_gpu):
+    """The same string in both arms (the driver compares them)."""
+    return "%s: %d streams/GPU x %d frames, %s" % (
+        args.workload, streams_per_gpu, args.frames or DEFAULT_FRAMES.get(args.workload, 383), WORKLOADS[args.workload])
+
+
+def default_streams(args, world=1, rank=0):
+    if args.workload == "cfg5":
+        total = args.streams or DEFAULT_STREAMS["cfg5"]
+        return total // world + (1 if rank < total % world else 0)
+    return args.streams or DEFAULT_STREAMS.get(args.workload, 1024)
+
+
 def cpu_sample_size(nstreams, cores):
-    """Streams for the bounded CPU sample: about 10-30 s of CPU work (a 10-s stream costs the oracle
+    """Streams for the bounded CPU sample: about 10-30 s of CPU work per pass (a 10-s stream costs the oracle
     ~40 ms on one core), never more than the workload has."""
-    return max(1, min(nstreams, cores * 32))
+    return max(1, min(nstreams, cores * 64))
 
 
 class ClockSampler(threading.Thread):
@@ -104,25 +125,118 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons)}
 
 
-def cpu_oracle_throughput(streams, threads, min_seconds=0.0):
-    """Decode `streams` with the oracle on `threads` host threads; returns audio-s/s."""
+# ------------------------------------------------------------------------------------ CPU lines
+def cpu_oracle_throughput(streams, threads):
+    """Decode `streams` with the oracle on `threads` host threads; returns (audio-s/s, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
     oracle.lib()
-    info = oracle.decode(streams[0], want_pcm=False)
+    oracle.decode(streams[0], want_pcm=False)
+
+    def one(s):
+        d = oracle.decode(s, want_pcm=True)
+        return d.samples / float(d.sample_rate or 1)
+
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:  # l3o_decode releases the GIL (ctypes)
-        res = list(ex.map(lambda s: oracle.decode(s, want_pcm=True).samples, streams))
+    if threads <= 1:
+        res = [one(s) for s in streams]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:  # l3o_decode releases the GIL (ctypes)
+            res = list(ex.map(one, streams))
     dt = time.perf_counter() - t0
-    return sum(res) / float(info.sample_rate) / dt, dt
+    return sum(res) / dt, dt
+
+
+def _ffmpeg_line_lib():
+    """tools/ff_line.c: a C loop around libavcodec's mp3float (an independent production decoder; not the oracle)."""
+    import ctypes
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ffmpeg_ref
+    if not ffmpeg_ref.available():
+        return None
+    src, lib = os.path.join(ROOT, "tools", "ff_line.c"), os.path.join(ROOT, "tools", "libffline.so")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", src, "-o", lib, "-ldl"])
+    L = ctypes.CDLL(lib)
+    L.ffl_decode_stream.restype = ctypes.c_long
+    L.ffl_decode_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p]
+    return L if L.ffl_init() == 0 else None
+
+
+def cpu_ffmpeg_throughput(streams, threads):
+    """FFmpeg mp3float over `streams`; returns (audio-s/s, seconds) or None when libavcodec is not on the box."""
+    from concurrent.futures import ThreadPoolExecutor
+    try:
+        L = _ffmpeg_line_lib()
+    except Exception:  # noqa: BLE001
+        L = None
+    if L is None:
+        return None
+    import l3util
+    work = []
+    cache = {}
+    for s in streams:
+        if s not in cache:
+            fr = l3util.split_frames(s)
+            o = np.zeros(len(fr) + 1, np.uint32)
+            np.cumsum([len(f) for f in fr], out=o[1:])
+            h = fr[0] if fr else b"\xff\xfb\x90\x00"
+            sr = l3util._SR[(h[1] >> 3) & 3][(h[2] >> 2) & 3]
+            cache[s] = (np.frombuffer(s, np.uint8), o, float(sr))
+        work.append(cache[s])
+
+    def one(w):
+        n = L.ffl_decode_stream(w[0].ctypes.data, w[1].ctypes.data, len(w[1]) - 1, b"mp3float")
+        return n / w[2] if n >= 0 else -1.0
+
+    one(work[0])
+    t0 = time.perf_counter()
+    if threads <= 1:
+        res = [one(w) for w in work]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            res = list(ex.map(one, work))
+    dt = time.perf_counter() - t0
+    if min(res) < 0:
+        return None
+    return sum(res) / dt, dt
+
+
+def cpu_lines(streams, cores):
+    """The CPU lines of SURVEY.md 8(d) / BASELINE.md section 4, each on a bounded sample of the workload."""
+    out = []
+    n1 = max(1, min(len(streams), 16))
+    v, dt = cpu_oracle_throughput(streams[:n1], 1)
+    out.append({"decoder": "oracle/l3_oracle.c (from-spec, double, direct form)", "threads": 1, "value": v, "unit": UNIT,
+                "sample": "%d streams, %.1f s" % (n1, dt)})
+    na = cpu_sample_size(len(streams), cores)
+    v, dt = cpu_oracle_throughput(streams[:na], cores)
+    out.append({"decoder": "oracle/l3_oracle.c (from-spec, double, direct form)", "threads": cores, "value": v,
+                "unit": UNIT, "sample": "%d streams, %.1f s" % (na, dt)})
+    nf1 = max(1, min(len(streams), 64))
+    r = cpu_ffmpeg_throughput(streams[:nf1], 1)
+    if r:
+        out.append({"decoder": "FFmpeg libavcodec mp3float (float32, production decoder)", "threads": 1, "value": r[0],
+                    "unit": UNIT, "sample": "%d streams, %.1f s" % (nf1, r[1])})
+        nfa = max(1, min(len(streams), cores * 128))
+        work = (streams * (nfa // max(len(streams), 1) + 1))[:nfa] if nfa > len(streams) else streams[:nfa]
+        r = cpu_ffmpeg_throughput(work, cores)
+        if r:
+            out.append({"decoder": "FFmpeg libavcodec mp3float (float32, production decoder)", "threads": cores,
+                        "value": r[0], "unit": UNIT, "sample": "%d streams, %.1f s" % (len(work), r[1])})
+    else:
+        out.append({"decoder": "FFmpeg libavcodec mp3float", "unavailable": "libavcodec not found on this box"})
+    return out
 
 
 # ------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank):
+def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nsample = cpu_sample_size(1 << 30, cores)
+    per_gpu = default_streams(args)
+    nsample = cpu_sample_size(per_gpu * world if args.workload != "cfg5" else per_gpu, cores)
     streams, _ = workload(args.workload, nsample, args.frames, args.seed, None)
     vals = []
     for i in range(args.warmup + args.steps):
@@ -133,20 +247,70 @@ def run_reference(args, rank):
     ms = float(np.mean([b for _, b in vals]) * 1e3)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "cfg5" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %d-stream sample x %d frames, %s" % (
-            args.workload, nsample, args.frames or DEFAULT_FRAMES.get(args.workload, 383), WORKLOADS[args.workload])},
+        "config": {"workload": workload_string(args, default_streams(args, world, 0))},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d streams per step, all host threads; the reference repository has no code, "
-                                   "so this is the from-spec oracle port" % nsample},
+                         "sample": "each step decodes %d streams of the workload (a rate metric: the per-GPU batch is %d "
+                                   "streams), one stream per host thread, all %d host threads; the reference repository "
+                                   "has no code, so this is the from-spec oracle port oracle/l3_oracle.c"
+                                   % (nsample, per_gpu, cores)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        ff = cpu_ffmpeg_throughput((streams * 4)[: max(len(streams), cores * 64)], cores)
+        if ff:
+            line["cpu_lines"] = [{"decoder": "FFmpeg libavcodec mp3float (float32, production decoder)", "threads": cores,
+                                  "value": ff[0], "unit": UNIT,
+                                  "note": "a faster CPU decoder than the literal oracle port this arm times; reported so "
+                                          "that the GPU / CPU ratio can be read against either"}]
+    except Exception:  # noqa: BLE001
+        pass
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------ our arm
+def parity_gate(mp3_b200, dec, streams, pick):
+    """Accuracy gate of every reported run: `pick` streams of the decoded batch against the
+    oracle -- s16 PCM within 1 LSB of round(oracle * 32768), which is far inside ISO/IEC 11172-4.  Raises on mismatch."""
+    import torch
+    from oracle import oracle
+    ptr, n = dec.pcm_device()
+
+    class _View:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i2", "data": (ptr, False), "version": 2}
+    pcm = torch.as_tensor(_View(), device="cuda")
+    worst = 0
+    for i in pick:
+        inf = dec.stream_info(i)
+        ref = oracle.decode(streams[i])
+        want = np.clip(np.rint(ref.pcm.T * 32768.0), -32768, 32767).astype(np.int64)
+        got = pcm[inf.pcm_offset: inf.pcm_offset + inf.samples * inf.channels].cpu().numpy().astype(np.int64)
+        got = got.reshape(inf.samples, inf.channels)
+        if got.shape != want.shape:
+            raise SystemExit("parity gate: stream %d has shape %r, the oracle %r" % (i, got.shape, want.shape))
+        d = int(np.abs(got - want).max()) if got.size else 0
+        worst = max(worst, d)
+        if d > 1:
+            raise SystemExit("parity gate: stream %d differs from the oracle by %d LSB" % (i, d))
+    return len(pick), worst
+
+
+def time_steps(torch, tstream, barrier, fn, steps, after=None):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(tstream)
+    for _ in range(steps):
+        fn()
+    if after:
+        after()
+    e1.record(tstream)
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
 def run_ours(args, rank, world):
     import torch
     import mp3_b200
@@ -171,12 +335,9 @@ def run_ours(args, rank, world):
     # cfg2 (the headline config): weak scaling, every rank decodes its own 1,024 streams.
     # cfg5 (the 100k-stream sweep): strong scaling, the 100k streams are sharded over the ranks.
     strong = args.workload == "cfg5"
-    nstreams = args.streams
-    if strong:
-        total = args.streams or DEFAULT_STREAMS["cfg5"]
-        nstreams = total // world + (1 if rank < total % world else 0)
-        if args.distinct is None:
-            args.distinct = 1024  # bounds host-side generation; the decoder still decodes every stream
+    nstreams = default_streams(args, world, rank)
+    if strong and args.distinct is None:
+        args.distinct = 1024  # bounds host-side generation; the decoder still decodes every stream
     streams, gen_s = workload(args.workload, nstreams, args.frames, args.seed + 100000 * rank, args.distinct)
     packed, offs = mp3_b200.pack_streams(streams)
     nbytes_in = int(packed.size)
@@ -196,6 +357,13 @@ def run_ours(args, rank, world):
     def step_device():
         dec.decode_packed(d_raw.data_ptr(), offs, where=mp3_b200.DEVICE, sync=False)
 
+    # ---- accuracy gate, before anything is timed
+    step_device()
+    dec.sync()
+    npick = min(len(streams), 8)
+    pick = sorted(set(int(x) for x in np.linspace(0, len(streams) - 1, npick)))
+    parity_n, parity_worst = parity_gate(mp3_b200, dec, streams, pick)
+
     # ---- device-resident timing
     for _ in range(args.warmup):
         step_device()
@@ -208,127 +376,256 @@ def run_ours(args, rank, world):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = {k: 0.0 for k in ("index", "huffman", "requant", "imdct", "overlap", "synth", "fused")}
-    e0.record(tstream)
-    for _ in range(args.steps):
-        step_device()
-        if args.stage_times:
-            dec.sync()
-            st = dec.stats()
-            for k in stage_ms:
-                stage_ms[k] += getattr(st, "ms_" + k)
-    e1.record(tstream)
-    barrier()
-    ms_dev = e0.elapsed_time(e1) / args.steps
+    ms_dev = time_steps(torch, tstream, barrier, step_device, args.steps)
     launches = dec.stats().kernel_launches
 
     # per-stage CUDA-event times (library events on the launching stream), separate untimed passes
-    if not args.stage_times:
-        for _ in range(max(1, min(args.steps, 3))):
-            step_device()
-            dec.sync()
-            st = dec.stats()
-            for k in stage_ms:
-                stage_ms[k] += getattr(st, "ms_" + k)
-        nst = max(1, min(args.steps, 3))
-    else:
-        nst = args.steps
+    stage_ms = {k: 0.0 for k in ("index", "huffman", "requant", "imdct", "overlap", "synth", "fused")}
+    nst = max(1, min(args.steps, 5))
+    for _ in range(nst):
+        step_device()
+        dec.sync()
+        st = dec.stats()
+        for k in stage_ms:
+            stage_ms[k] += getattr(st, "ms_" + k)
     stage_ms = {k: v / nst for k, v in stage_ms.items()}
 
     # ---- end to end: pinned host in, pinned host out
     do_e2e = not args.no_e2e and pcm_bytes < (8 << 30)  # cfg5 would need 59 GB of pinned host memory
-    ms_e2e, checksum = float("nan"), None
+    e2e = None
+    checksum = None
     if do_e2e:
-        ms_e2e, checksum = run_e2e(args, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier)
+        e2e, checksum = run_e2e(args, torch, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier)
     sampler.stop_flag = True
-    finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, ms_e2e, stage_ms,
-           launches, sampler, gen_s, checksum, strong, numa)
+
+    sweep = None
+    if args.workload == "cfg2" and not args.no_sweep:
+        sweep = run_sweep_cfg5(args, torch, mp3_b200, dec, tstream, barrier, rank, world)
+    finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, e2e, stage_ms,
+           launches, sampler, gen_s, checksum, strong, numa, (parity_n, parity_worst), sweep, infos)
 
 
-def run_e2e(args, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier):
-    import torch
+def run_e2e(args, torch, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstream, barrier):
     h_in = mp3_b200.PinnedBuffer(nbytes_in + 64)
     h_in.view(np.uint8)[:nbytes_in] = packed
     h_out = mp3_b200.PinnedBuffer(pcm_bytes + 64)
     pcm_elems = pcm_bytes // 2
 
-    dec.set_pcm_sink(h_out.ptr, pcm_elems)  # D2H of each wave overlaps the next wave's kernels
-
-    def step_e2e():
+    # (ii)/(iii): host input, PCM left on the device (H2D + indexing + kernels)
+    def step_h2d():
         dec.decode_packed(h_in.ptr, offs, where=mp3_b200.HOST, sync=False)
 
-    for _ in range(min(args.warmup, 3)):
-        step_e2e()
+    for _ in range(2):
+        step_h2d()
     dec.sync()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(tstream)
-    for _ in range(args.steps):
-        step_e2e()
-    dec.flush()  # the stream (and so the end event) waits for every D2H copy of every step
-    e3.record(tstream)
-    barrier()
+    ms_h2d = time_steps(torch, tstream, barrier, step_h2d, args.steps)
+
+    # (iv): + D2H through the sink
+    dec.set_pcm_sink(h_out.ptr, pcm_elems)  # D2H of each wave overlaps the next wave's kernels
+    for _ in range(min(args.warmup, 3)):
+        step_h2d()
+    dec.sync()
+    # the stream (and so the end event) waits for every D2H copy of every step
+    ms_e2e = time_steps(torch, tstream, barrier, step_h2d, args.steps, after=dec.flush)
     dec.set_pcm_sink(0, 0)
-    ms_e2e = e2.elapsed_time(e3) / args.steps
     checksum = int(h_out.view(np.int16, pcm_elems)[:: max(1, pcm_elems // 4096)].astype(np.int64).sum())
-    return ms_e2e, checksum
+
+    # the floor: the same two transfers alone -- plain cudaMemcpyAsync, same pinned buffers, the library's own PCM
+    # arena as the device side, H2D and D2H on two streams as the library issues them
+    floor = None
+    try:
+        ptr, n = dec.pcm_device()
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (pcm_bytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        d_pcm = torch.as_tensor(_Dev(), device="cuda")
+        t_out = torch.from_numpy(h_out.view(np.uint8)[:pcm_bytes])
+        t_in = torch.from_numpy(h_in.view(np.uint8)[:nbytes_in])
+        d_in = torch.empty(nbytes_in, dtype=torch.uint8, device="cuda")
+        s2 = torch.cuda.Stream()
+
+        def copies():
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(s2):
+                d_in.copy_(t_in, non_blocking=True)
+                ev.record(s2)
+            with torch.cuda.stream(tstream):
+                t_out.copy_(d_pcm, non_blocking=True)
+                tstream.wait_event(ev)
+
+        pinned = bool(t_out.is_pinned() and t_in.is_pinned())
+        for _ in range(2):
+            copies()
+        torch.cuda.synchronize()
+        floor = {"ms": time_steps(torch, tstream, barrier, copies, max(3, min(args.steps, 10))), "pinned": pinned}
+    except Exception as e:  # noqa: BLE001
+        floor = {"ms": None, "error": str(e)[:200]}
+    return {"ms": ms_e2e, "ms_h2d_only": ms_h2d, "floor": floor}, checksum
 
 
-def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, ms_e2e, stage_ms,
-           launches, sampler, gen_s, checksum, strong, numa=None):
-    import torch
-    # ---- max over ranks
-    if dist is not None:
-        t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
-        tot = torch.tensor([audio_s, float(nbytes_in), float(pcm_bytes), float(units)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        audio_all, in_all, pcm_all, units_all = [float(x) for x in tot]
+def run_sweep_cfg5(args, torch, mp3_b200, dec, tstream, barrier, rank, world):
+    """BASELINE.json configs[4]: 100,000 streams of the cfg2 type x 128 frames, sharded over the ranks as contiguous
+    stream ranges (strong scaling: the job is fixed, N grows).  1,024 distinct streams per rank repeat (bounds the
+    host-side generation); every stream is decoded.  Inputs resident in HBM, PCM left in HBM (59 GB in total)."""
+    total, nf, distinct = args.sweep_streams, 128, 1024
+    n = total // world + (1 if rank < total % world else 0)
+    free, _ = torch.cuda.mem_get_info()
+    need = n * (nf * 1152 * 2 * 2 + 60000 * 2) * 1.15 + (4 << 30)
+    if free < need:
+        return {"skipped": "needs %.0f GB of device memory per rank, %.0f free" % (need / 1e9, free / 1e9)}
+    from mp3_b200 import synth
+    base = synth.make_workload("cfg5", min(distinct, n), nf, seed=args.seed + 100000 * rank)
+    lens = {len(s) for s in base}
+    D = len(base)
+    if len(lens) == 1:  # CBR streams of one rate: equal lengths, replicate on the device
+        slen = lens.pop()
+        p1, _ = mp3_b200.pack_streams(base)
+        d1 = torch.from_numpy(p1).cuda()
+        d_raw = d1.repeat(-(-n // D))[: n * slen].contiguous()
+        del d1
+        offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(slen)
     else:
-        audio_all, in_all, pcm_all, units_all = audio_s, float(nbytes_in), float(pcm_bytes), float(units)
+        p, offs = mp3_b200.pack_streams([base[i % D] for i in range(n)])
+        d_raw = torch.from_numpy(p).cuda()
+
+    def step():
+        dec.decode_packed(d_raw.data_ptr(), offs, where=mp3_b200.DEVICE, sync=False)
+
+    step()
+    dec.sync()
+    pick = sorted(set(int(x) for x in np.linspace(0, n - 1, 4)))
+    parity_n, _ = parity_gate(mp3_b200, dec, _Cyclic(base, n), pick)
+    for _ in range(2):
+        step()
+    dec.sync()
+    st = dec.stats()
+    steps = max(3, min(args.steps, 5))
+    ms = time_steps(torch, tstream, barrier, step, steps)
+    audio = st.frames * 1152 / 44100.0
+    out = {"ms": ms, "audio_s": audio, "pcm_bytes": st.pcm_bytes, "bytes_in": st.bytes_in, "units": st.units,
+           "streams": n, "steps": steps, "launches": int(st.kernel_launches) * steps, "parity_checked": parity_n}
+    del d_raw
+    return out
+
+
+class _Cyclic:
+    """streams[i] = base[i % len(base)] without materialising a 100,000-entry list."""
+
+    def __init__(self, base, n):
+        self.base, self.n = base, n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self.base[i % len(self.base)]
+
+
+def load_json(*path):
+    try:
+        return json.load(open(os.path.join(ROOT, *path)))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, e2e, stage_ms,
+           launches, sampler, gen_s, checksum, strong, numa, parity, sweep, infos):
+    import torch
+    ms_e2e = e2e["ms"] if e2e else float("nan")
+    ms_h2d = e2e["ms_h2d_only"] if e2e else float("nan")
+    ms_floor = (e2e["floor"] or {}).get("ms") if e2e else None
+    ms_floor = float("nan") if ms_floor is None else ms_floor
+    sw = sweep if sweep and "ms" in sweep else None
+    # ---- max over ranks (times), sum over ranks (work)
+    if dist is not None:
+        t = torch.tensor([ms_dev, ms_e2e, ms_h2d, ms_floor, sw["ms"] if sw else float("nan")], device="cuda",
+                         dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e, ms_h2d, ms_floor = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        if sw:
+            sw["ms"] = float(t[4])
+        tot = torch.tensor([audio_s, float(nbytes_in), float(pcm_bytes), float(units), float(parity[0])] +
+                           ([sw["audio_s"], float(sw["pcm_bytes"]), float(sw["bytes_in"]), float(sw["units"]),
+                             float(sw["streams"]), float(sw["launches"]), float(sw["parity_checked"])] if sw else [0.0] * 7),
+                           device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        audio_all, in_all, pcm_all, units_all, parity_all = [float(x) for x in tot[:5]]
+        if sw:
+            sw["audio_s"], sw["pcm_bytes"], sw["bytes_in"], sw["units"], sw["streams"], sw["launches"], \
+                sw["parity_checked"] = [float(x) for x in tot[5:]]
+    else:
+        audio_all, in_all, pcm_all, units_all, parity_all = audio_s, float(nbytes_in), float(pcm_bytes), float(units), \
+            float(parity[0])
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_json("MEASURED_PEAKS.json")
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # dominant kernel and its algorithmic bytes per unit:
-        # what the stage must read and write by definition, s16 PCM out
+        fp = load_json("profiles", "fp32_peak.json")
+        counts = load_json("profiles", "fp32_counts.json")
+        traffic = load_json("profiles", "traffic.json")
         in_per_unit = nbytes_in / max(units, 1)
-        alg = {"huffman": in_per_unit + 1152.0 + 40.0,           # compressed bits in; int16 spectrum + scalefactors out
-               "requant": 1152.0 + 2304.0, "imdct": 2304.0 + 4608.0, "overlap": 4608.0 + 2304.0,
-               "synth": 2304.0 + 1152.0,
-               "fused": 1152.0 + 40.0 + 1152.0}                  # int16 spectrum + scalefactors in; s16 PCM out
+        ideal_b = in_per_unit + FUSED_IDEAL_PCM_BYTES                  # SURVEY.md 8(d): fused ideal, 1256.5 at 128 kbit/s
         kern = {k: v for k, v in stage_ms.items() if k != "index" and v > 0}
-        if kern:
-            dom = max(kern, key=kern.get)
-            achieved = alg[dom] * units / (kern[dom] * 1e-3) / 1e9
-        else:  # a decode cut into several waves has no per-stage events: whole pipeline only
-            dom = "pipeline"
-            alg[dom] = in_per_unit + 1152.0
-            achieved = alg[dom] * units / (ms_dev * 1e-3) / 1e9
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = prof.get(dom, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        dom = max(kern, key=kern.get) if kern else "pipeline"
+        kms = kern.get(dom, ms_dev)
+        # algorithmic bytes per unit of each kernel's own interface (DESIGN.md section 3)
+        own = {"huffman": in_per_unit + 1152.0 + 40.0, "requant": 1152.0 + 2304.0, "imdct": 2304.0 + 4608.0,
+               "overlap": 4608.0 + 2304.0, "synth": 2304.0 + 1152.0, "fused": 1152.0 + 40.0 + 1152.0,
+               "pipeline": ideal_b}
+        if dom == "fused":
+            # FP32 / issue bound (ncu: issue slots ~74 %, DRAM ~10 %).  Peak = the measured FFMA rate of this GPU
+            # (tools/fp32_peak.cu -> profiles/fp32_peak.json; burst: the kernel is timed alone); executed flops per
+            # unit from ncu's smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on (profiles/fp32_counts.json).
+            fp_peak = fp.get("fp32_tflops_burst")
+            fp_src = "measured (profiles/fp32_peak.json, tools/fp32_peak.cu, burst)"
+            if not fp_peak:
+                fp_peak, fp_src = 74.4, "theoretical 148 SM x 128 FMA x 2 x 1.965 GHz (no measured file)"
+            exe = (counts.get(args.workload) or {}).get("fused", {}).get("flop_per_unit")
+            eff_tf = DIRECT_FORM_FLOP_PER_UNIT * units / (kms * 1e-3) / 1e12
+            exe_tf = exe * units / (kms * 1e-3) / 1e12 if exe else None
+            roof = {"bound": "fp32-issue", "kernel": "k_backend (fused a6-a11)", "unit": "TFLOP/s", "peak": fp_peak,
+                    "peak_source": fp_src,
+                    "achieved": exe_tf if exe_tf is not None else eff_tf,
+                    "frac": (exe_tf if exe_tf is not None else eff_tf) / fp_peak,
+                    "achieved_is": "executed FP32 flops (fast transforms)" if exe_tf is not None
+                                   else "direct-form effective flops (no executed-flop count for this workload)",
+                    "executed_flop_per_unit": exe, "executed": exe_tf,
+                    "executed_frac": exe_tf / fp_peak if exe_tf is not None else None,
+                    "effective_direct_form": eff_tf, "effective_direct_form_frac": eff_tf / fp_peak,
+                    "direct_form_flop_per_unit": DIRECT_FORM_FLOP_PER_UNIT}
+        else:
+            ach = own[dom] * units / (kms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src,
+                    "achieved": ach, "frac": ach / hbm_peak}
+        roof.update({
+            "traffic": (traffic.get(dom) or {}).get("dram_bytes_per_launch"),
+            "units_per_launch": units, "kernel_ms": kms,
+            "hbm": {
+                "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
+                "algorithmic_bytes_per_unit_fused_ideal": ideal_b,
+                "whole_pipeline": {"ms": ms_dev, "achieved": ideal_b * units / (ms_dev * 1e-3) / 1e9,
+                                   "frac": ideal_b * units / (ms_dev * 1e-3) / 1e9 / hbm_peak},
+                "dominant_kernel_at_fused_ideal": {"ms": kms, "achieved": ideal_b * units / (kms * 1e-3) / 1e9,
+                                                   "frac": ideal_b * units / (kms * 1e-3) / 1e9 / hbm_peak},
+                "dominant_kernel_own_interface": {"algorithmic_bytes_per_unit": own[dom],
+                                                  "achieved": own[dom] * units / (kms * 1e-3) / 1e9,
+                                                  "frac": own[dom] * units / (kms * 1e-3) / 1e9 / hbm_peak},
+            },
+            "note": "the back end is FP32 / shared-memory issue bound, not HBM bound; both views are printed. "
+                    "fused ideal = compressed bytes in + s16 PCM out per unit (SURVEY.md 8(d)); own interface = what the "
+                    "kernel itself reads and writes (it includes the int16 spectrum between the two kernels)"})
         cores = os.cpu_count() or 1
-        nsample = cpu_sample_size(len(streams), cores)
-        cpu_v, cpu_dt = cpu_oracle_throughput(streams[:nsample], cores)
+        # CPU lines: rank 0 at N = 1 only (they are per-box numbers, and the scaling runs need not repeat them)
+        lines = cpu_lines(streams, cores) if not args.no_cpu and world == 1 else []
+        allc = next((l for l in lines if l.get("threads") == cores and l["decoder"].startswith("oracle")), None)
+        kernels_only = stage_ms["huffman"] + sum(stage_ms[k] for k in ("requant", "imdct", "overlap", "synth", "fused"))
         line = {
             "metric": METRIC, "value": audio_all / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "%s: %d streams/GPU x %d frames, %s" % (
-                    args.workload, len(streams), args.frames or DEFAULT_FRAMES.get(args.workload, 383),
-                    WORKLOADS[args.workload]),
+                "workload": workload_string(args, len(streams)),
                 "streams_per_gpu": len(streams), "distinct_streams": args.distinct or len(streams),
                 "pcm": "s16 interleaved", "pipeline": args.pipeline, "indexer": "device",
                 "l2_policy": "inputs_larger_than_l2 (%.0f MB in, %.0f MB PCM out per step)" % (nbytes_in / 1e6, pcm_bytes / 1e6),
@@ -337,27 +634,56 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
             },
             "pcm_gbs": pcm_all / (ms_dev * 1e-3) / 1e9,
             "x_realtime_per_gpu": audio_all / world / (ms_dev * 1e-3),
+            "parity_checked": int(parity_all),
+            "parity": "s16 PCM of %d streams per rank within %d LSB of round(oracle x 32768) (gate: 1), checked before "
+                      "timing" % (parity[0], parity[1]),
             "stage_ms": stage_ms,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_unit": alg[dom], "units_per_launch": units,
-                         "kernel_ms": kern.get(dom),
-                         "whole_pipeline": {"algorithmic_bytes_per_unit": in_per_unit + 1152.0,
-                                            "achieved": (in_per_unit + 1152.0) * units / (ms_dev * 1e-3) / 1e9,
-                                            "frac": (in_per_unit + 1152.0) * units / (ms_dev * 1e-3) / 1e9 / hbm_peak},
-                         "note": "the back end is FP32 / shared-memory issue bound, not HBM bound (ncu: issue 74 %, LSU "
-                                 "67 %, FMA 37 %, DRAM 10 %); its DRAM traffic is at the algorithmic bytes (profiles/)"},
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "first %d streams of the workload (%.1f s of wall time on %d threads = %.0f s of "
-                                       "CPU work), oracle/l3_oracle.c, one stream per host thread" % (
-                                           nsample, cpu_dt, cores, cpu_dt * min(cores, nsample))},
+            "splits": {
+                "i_decode_kernels_only_ms": kernels_only,
+                "iii_plus_indexing_device_resident_ms": ms_dev,
+                "ii_iii_plus_h2d_ms": None if ms_h2d != ms_h2d else ms_h2d,
+                "iv_plus_d2h_ms": None if ms_e2e != ms_e2e else ms_e2e,
+                "note": "(i) Huffman + back end (library CUDA events); (iii) adds the device indexer (walk, side info, "
+                        "main-data compaction) and its one host round trip = `value`; (ii)+(iii) adds the H2D of the MP3 "
+                        "bytes from pinned memory; (iv) adds the D2H of the PCM = `e2e`",
+            },
+            "roofline": roof,
+            "cpu_baseline": ({"value": allc["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                              "sample": "first %s of the workload, oracle/l3_oracle.c, one stream per host thread"
+                                        % allc["sample"]} if allc else None),
+            "cpu_lines": lines,
             "e2e": ({"value": audio_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(in_all),
                      "d2h_bytes_per_step": int(pcm_all), "ms_per_step": ms_e2e,
-                     "pcm_gbs": pcm_all / (ms_e2e * 1e-3) / 1e9} if ms_e2e == ms_e2e else None),
+                     "pcm_gbs": pcm_all / (ms_e2e * 1e-3) / 1e9,
+                     "pcie_floor_ms": None if ms_floor != ms_floor else ms_floor,
+                     "frac_of_pcie_floor": None if ms_floor != ms_floor else ms_floor / ms_e2e,
+                     "pcie_floor_note": "the step's two transfers alone (plain cudaMemcpyAsync of the same pinned buffers, "
+                                        "same process, all ranks at once); floor / e2e = 1 means transfer bound"}
+                    if ms_e2e == ms_e2e else None),
             "gpu_launches": int(launches * args.steps),
             "clocks": sampler.result(),
             "gen_seconds": gen_s, "pcm_checksum": checksum,
         }
+        if sweep is not None:
+            if sw:
+                v = sw["audio_s"] / (sw["ms"] * 1e-3)
+                ideal5 = sw["bytes_in"] + sw["units"] * FUSED_IDEAL_PCM_BYTES
+                line["sweep_cfg5"] = {
+                    "workload": "cfg5: %d streams x 128 frames sharded over %d GPU(s), %s" % (
+                        int(sw["streams"]), world, WORKLOADS["cfg5"]),
+                    "scaling": "strong", "metric": METRIC, "value": v, "unit": UNIT, "ms_per_step": sw["ms"],
+                    "steps": sw["steps"], "streams": int(sw["streams"]), "units": int(sw["units"]),
+                    "pcm_gbs": sw["pcm_bytes"] / (sw["ms"] * 1e-3) / 1e9,
+                    "hbm": {"algorithmic_bytes": ideal5, "achieved": ideal5 / (sw["ms"] * 1e-3) / 1e9,
+                            "peak": hbm_peak * world, "frac": ideal5 / (sw["ms"] * 1e-3) / 1e9 / (hbm_peak * world),
+                            "note": "fused-ideal bytes (compressed in + s16 PCM out) of the whole job / max-over-ranks "
+                                    "time, against N x the measured HBM peak"},
+                    "x_realtime_per_gpu": v / world, "gpu_launches": int(sw["launches"]),
+                    "parity_checked": int(sw["parity_checked"]),
+                    "data": "synthetic; 1,024 distinct streams per rank repeat, every stream is decoded",
+                }
+            else:
+                line["sweep_cfg5"] = sweep
         print(json.dumps(line))
     dec.close()
     if dist is not None:
@@ -376,8 +702,10 @@ def main():
     ap.add_argument("--distinct", type=int, default=None, help="generate only this many distinct streams and repeat")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--pipeline", default="default", choices=["default", "fused", "staged"])
-    ap.add_argument("--stage-times", action="store_true", help="sync after every step to read per-stage events")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the cfg5 100k-stream sweep appended to a cfg2 run")
+    ap.add_argument("--sweep-streams", type=int, default=100000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU lines (profiling runs)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -387,7 +715,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
     else:
         run_ours(args, rank, world)
 

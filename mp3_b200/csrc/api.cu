@@ -84,6 +84,10 @@ struct mp3b_stream {
     int batch_index = -1;        // index in the last mp3b_decode() batch
     size_t cursor = 0;           // samples per channel of the last decode already fetched
     int64_t total_samples = 0;   // samples per channel emitted over the stream's life
+    // A leading ID3v2 tag is dropped as its bytes arrive (it may be far larger than one enqueue: cover art),
+    // so that the frame walk never searches a partly received tag body for syncs.
+    bool id3_checked = false;    // the first 10 bytes of the stream have been looked at
+    uint64_t id3_left = 0;       // tag bytes still to drop from coming enqueues
 };
 
 struct mp3b_ctx {
@@ -99,6 +103,7 @@ struct mp3b_ctx {
     std::vector<cudaEvent_t> wave_ev;
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t staging_done = nullptr; // the last H2D out of the pinned staging tables has executed
+    cudaEvent_t tiles2_done = nullptr;  // the same for the Layer I / II tile table
     void *sink = nullptr;
     uint64_t sink_cap = 0;
     cudaEvent_t ev[EV_COUNT]{};
@@ -150,6 +155,9 @@ struct mp3b_ctx {
     uint32_t nstreams = 0, nframes = 0, ngran = 0, nunits = 0, ntiles = 0;
     uint64_t wave_units = 2u << 20;
     uint32_t tile_override = 0; // MP3B_FUSED_TILE: granules per fused tile (tests)
+    bool poison = false;        // MP3B_DEBUG_POISON=1: every scratch / output buffer is filled with 0xFF before each
+                                // decode, so that a read of something this call did not write cannot go unnoticed
+                                // (buffers are grow-only and reused; the all-zero spectrum tails are never written)
     bool have_batch = false, timed = false;
     mp3b_stats stats{};
     std::vector<mp3b_stream *> open_streams;
@@ -226,8 +234,8 @@ void host_index_stream(const uint8_t *buf, L3StreamRec *r, std::vector<L3FrameRe
         L3Hdr h;
         uint32_t w;
         const int fa = l3_frame_at(buf, len, p, first, &h, &w);
-        if (fa != 1) {
-            if (fa == 2 && streaming) break;
+        if (fa != 1 && !(fa == 3 && !streaming)) {
+            if (fa >= 2 && streaming) break; // wait for the rest of the frame / the confirming next header
             p++;
             continue;
         }
@@ -398,7 +406,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
 
     // ---- prefix sums, per-stream info, synthesis tiles
     const int G = l3_synth_tile_granules();
-    uint64_t frames = 0, grans = 0, units = 0, payload = 0, ntiles = 0;
+    uint64_t frames = 0, grans = 0, units = 0, units_l2 = 0, payload = 0, ntiles = 0;
     std::vector<uint32_t> sgran((size_t)nstreams, 0), sunit((size_t)nstreams, 0), sskip((size_t)nstreams, 0);
     std::vector<uint8_t> sl2((size_t)nstreams, 0); // Layer I / II streams: decoded by k_layer1/2 + the synthesis kernel
     bool any_l2 = false, any_layer[4] = {false, false, false, false}; // which layers the batch holds: kernels of absent ones are not launched
@@ -440,6 +448,10 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             sunit[(size_t)i] = (uint32_t)(g * h.nch);
             sskip[(size_t)i] = (uint32_t)((uint64_t)skip * h.spf / 576); // whole granules before the first new sample
             sl2[(size_t)i] = h.layer != 3;
+            if (h.layer != 3) { // its subband samples go to a dense buffer of the Layer I / II streams only
+                r.sb_shift = (uint32_t)(units - units_l2);
+                units_l2 += g * h.nch;
+            }
             any_l2 = any_l2 || h.layer != 3;
             any_layer[h.layer & 3] = true;
             if (h.layer == 3) ntiles += (g + G - 1) / G;
@@ -552,6 +564,11 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         CK(ctx->d_sb.ensure(max_wave_units * 576 * sizeof(float)));
     }
 
+    if (ctx->poison) {
+        for (DevBuf *b : {&ctx->d_frames, &ctx->d_units, &ctx->d_gran, &ctx->d_arena, &ctx->d_tiles, &ctx->d_is, &ctx->d_sf,
+                          &ctx->d_nzv, &ctx->d_xr, &ctx->d_imd, &ctx->d_sb, &ctx->d_sb2, &ctx->pcm()})
+            if (b->p && b->cap) CK(cudaMemsetAsync(b->p, 0xFF, b->cap, st));
+    }
     if (ahead && where == MP3B_HOST && !nstreams) CK(cudaStreamSynchronize(ist));
     if (nstreams) CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
     if (ntiles)
@@ -635,7 +652,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_IMDCT], st));
         l3_launch_overlap_range(du, u_lo, nu, imd, sb, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_OVL], st));
-        l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, pcm_dev,
+        l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, nullptr, pcm_dev,
                         ctx->opts.pcm_format, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
         launches += 5;
@@ -650,22 +667,31 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
                 u_max = std::max<uint64_t>(u_max, (uint64_t)hs[i].unit_base + sunit[(size_t)i]);
                 nt2 += (sgran[(size_t)i] - sskip[(size_t)i] + G - 1) / G;
             }
-        CK(ctx->d_sb2.ensure(std::max<uint64_t>((u_max - u_min) * 576 * sizeof(float), 16)));
-        CK(ctx->h_tiles2.ensure(sizeof(uint2) * std::max<uint64_t>(nt2, 1)));
-        CK(ctx->d_tiles2.ensure(sizeof(uint2) * std::max<uint64_t>(nt2, 1)));
-        CK(cudaStreamSynchronize(st)); // h_tiles2 may still feed the previous call's upload (Layer II batches are rare)
+        const size_t sb2_cap0 = ctx->d_sb2.cap;
+        CK(ctx->d_sb2.ensure(std::max<uint64_t>(units_l2 * 576 * sizeof(float), 16)));
+        if (ctx->poison && ctx->d_sb2.cap != sb2_cap0) CK(cudaMemsetAsync(ctx->d_sb2.p, 0xFF, ctx->d_sb2.cap, st));
+        // tiles {first granule, granules} and, behind them, one dense-buffer shift per tile
+        CK(ctx->h_tiles2.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(nt2, 1)));
+        CK(ctx->d_tiles2.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(nt2, 1)));
+        CK(cudaEventSynchronize(ctx->tiles2_done)); // h_tiles2 may still feed the previous call's upload
         uint2 *t2 = ctx->h_tiles2.as<uint2>();
+        uint32_t *sh2 = reinterpret_cast<uint32_t *>(t2 + nt2);
         uint64_t k = 0;
         for (int i = 0; i < nstreams; i++)
             if (sl2[(size_t)i])
-                for (uint32_t a = sskip[(size_t)i]; a < sgran[(size_t)i]; a += (uint32_t)G)
+                for (uint32_t a = sskip[(size_t)i]; a < sgran[(size_t)i]; a += (uint32_t)G) {
+                    sh2[k] = hs[i].sb_shift;
                     t2[k++] = make_uint2(hs[i].gran_base + a, std::min<uint32_t>((uint32_t)G, sgran[(size_t)i] - a));
-        float *sb2 = ctx->d_sb2.as<float>() - (size_t)u_min * 576;
+                }
+        float *sb2 = ctx->d_sb2.as<float>();
         if (any_layer[2]) l3_launch_layer2(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
         if (any_layer[1]) l3_launch_layer1(ctx->raw_dev, ds, df, (uint32_t)frames, sb2, st);
         if (nt2) {
-            CK(cudaMemcpyAsync(ctx->d_tiles2.p, t2, sizeof(uint2) * nt2, cudaMemcpyHostToDevice, st));
-            l3_launch_synth(ctx->d_tiles2.as<uint2>(), (uint32_t)nt2, dg, sb2, pcm_dev, ctx->opts.pcm_format, st);
+            CK(cudaMemcpyAsync(ctx->d_tiles2.p, t2, sizeof(uint32_t) * 3 * nt2, cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(ctx->tiles2_done, st));
+            l3_launch_synth(ctx->d_tiles2.as<uint2>(), (uint32_t)nt2, dg, sb2,
+                            reinterpret_cast<const uint32_t *>(ctx->d_tiles2.as<uint2>() + nt2), pcm_dev,
+                            ctx->opts.pcm_format, st);
         }
         launches += (any_layer[2] ? 1 : 0) + (any_layer[1] ? 1 : 0) + (nt2 ? 1 : 0);
         if (sink) { // the waves above did not cover these streams' PCM: one more copy, whole ranges
@@ -729,22 +755,30 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
 {
     if (!out) return MP3B_E_INVAL;
     *out = nullptr;
+    // options first (no device needed to reject a malformed request)
+    mp3b_opts o;
+    mp3b_opts_default(&o);
+    if (opts) {
+        size_t sz = std::min<size_t>(opts->struct_size, sizeof(mp3b_opts));
+        if (sz < 8) return MP3B_E_INVAL;
+        memcpy(&o, opts, sz);
+        o.struct_size = sizeof(mp3b_opts);
+        if ((o.pcm_format != MP3B_PCM_S16 && o.pcm_format != MP3B_PCM_F32) ||
+            (o.indexer != MP3B_INDEX_DEVICE && o.indexer != MP3B_INDEX_HOST) ||
+            (o.pipeline != MP3B_PIPE_FUSED && o.pipeline != MP3B_PIPE_STAGED) || o.host_threads < 0)
+            return MP3B_E_INVAL;
+    }
     int n = mp3b_device_count();
     if (n <= 0 || device < 0 || device >= n) return MP3B_E_CUDA; // no CPU fallback, by design
     mp3b_ctx *ctx = new (std::nothrow) mp3b_ctx;
     if (!ctx) return MP3B_E_NOMEM;
     ctx->device = device;
-    mp3b_opts_default(&ctx->opts);
-    if (opts) {
-        size_t sz = std::min<size_t>(opts->struct_size, sizeof(mp3b_opts));
-        if (sz < 8) { delete ctx; return MP3B_E_INVAL; }
-        memcpy(&ctx->opts, opts, sz);
-        ctx->opts.struct_size = sizeof(mp3b_opts);
-    }
+    ctx->opts = o;
     if (const char *w = getenv("MP3B_WAVE_UNITS")) {
         long long v = atoll(w);
         if (v > 0) ctx->wave_units = (uint64_t)v;
     }
+    if (const char *w = getenv("MP3B_DEBUG_POISON")) ctx->poison = atoi(w) != 0;
     if (const char *w = getenv("MP3B_FUSED_TILE")) {
         int v = atoi(w);
         if (v > 0 && v <= 4096) ctx->tile_override = (uint32_t)v;
@@ -760,6 +794,7 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
         return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->staging_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->tiles2_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     for (auto &e : ctx->pcm_free)
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     for (auto &e : ctx->ev)
@@ -797,6 +832,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
         if (e) cudaEventDestroy(e);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
+    if (ctx->tiles2_done) cudaEventDestroy(ctx->tiles2_done);
     for (auto &e : ctx->pcm_free)
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -817,9 +853,9 @@ const char *mp3b_strerror(int status)
     switch (status) {
     case MP3B_OK: return "ok";
     case MP3B_E_INVAL: return "invalid argument";
-    case MP3B_E_NOSYNC: return "no Layer III frame found";
+    case MP3B_E_NOSYNC: return "no MPEG audio frame found";
     case MP3B_E_TRUNCATED: return "destination buffer too small";
-    case MP3B_E_UNSUPPORTED: return "unsupported stream (Layer I/II, free format or MPEG-2.5)";
+    case MP3B_E_UNSUPPORTED: return "unsupported (free-format stream, or a sample-rate pair the resampler has no filter for)";
     case MP3B_E_CUDA: return "CUDA error (no usable device, or a runtime failure)";
     case MP3B_E_NOMEM: return "out of memory";
     case MP3B_E_STATE: return "call order violated";
@@ -1171,6 +1207,9 @@ int mp3b_batch_time_stretch(mp3b_ctx *ctx, int num, int den)
         if (!inf.frames || inf.sample_rate <= 0 || inf.samples <= 0) continue;
         jb.in_off = inf.pcm_offset;
         jb.in_n = inf.samples;
+        // every stream's output starts on a 16-byte boundary: k_stretch stores a stereo frame as one 32-bit
+        // (s16) or 64-bit (f32) word, and an odd-length mono stream in front must not misalign it
+        out_elems = align_up(out_elems, 8);
         jb.out_off = (long long)out_elems;
         jb.out_n = inf.samples * den / num;
         jb.channels = inf.channels;
@@ -1284,6 +1323,7 @@ int mp3b_batch_resample(mp3b_ctx *ctx, int out_rate)
         const int64_t L = out_rate / g, M = inf.sample_rate / g;
         jb.in_off = inf.pcm_offset;
         jb.in_n = inf.samples;
+        out_elems = align_up(out_elems, 8); // 16-byte aligned stream starts, as in the stretched arena
         jb.out_off = (long long)out_elems;
         jb.out_n = (inf.samples * L + M - 1) / M;
         jb.channels = inf.channels;
@@ -1460,18 +1500,40 @@ void mp3b_stream_close(mp3b_stream *s)
     if (!s) return;
     finalize_stream_batch(s->ctx);
     auto &v = s->ctx->open_streams;
+    // the other streams keep their batch_index: it indexes the last decode's tables (ctx->infos), not
+    // open_streams, so their unfetched PCM stays fetchable; mp3b_decode() reassigns every index anyway
     v.erase(std::remove(v.begin(), v.end(), s), v.end());
-    for (auto *o : v) o->batch_index = -1; // batch indices are positional: invalidate
     delete s;
 }
 
 int mp3b_stream_enqueue(mp3b_stream *s, const uint8_t *bytes, size_t n)
 {
     if (!s || (n && !bytes)) return MP3B_E_INVAL;
+    if (s->id3_left) { // still inside the stream's leading ID3v2 tag
+        const size_t d = (size_t)std::min<uint64_t>(s->id3_left, n);
+        s->id3_left -= d;
+        bytes += d;
+        n -= d;
+    }
     try {
         s->pending.insert(s->pending.end(), bytes, bytes + n);
     } catch (...) {
         return MP3B_E_NOMEM;
+    }
+    if (!s->id3_checked && !s->pending.empty()) {
+        const std::vector<uint8_t> &pb = s->pending;
+        static const uint8_t magic[3] = {'I', 'D', '3'};
+        if (memcmp(pb.data(), magic, std::min<size_t>(3, pb.size())) != 0) s->id3_checked = true; // no tag
+        else if (pb.size() >= 10) { // (fewer bytes of a possible tag header: decide when they are all here)
+            s->id3_checked = true;
+            if (!((pb[6] | pb[7] | pb[8] | pb[9]) & 0x80)) {
+                uint64_t len = ((uint64_t)pb[6] << 21) | ((uint64_t)pb[7] << 14) | ((uint64_t)pb[8] << 7) | pb[9];
+                len += 10 + ((pb[5] & 0x10) ? 10 : 0);
+                const size_t d = (size_t)std::min<uint64_t>(len, pb.size());
+                s->id3_left = len - d;
+                s->pending.erase(s->pending.begin(), s->pending.begin() + (ptrdiff_t)d);
+            }
+        }
     }
     return MP3B_OK;
 }

@@ -55,8 +55,8 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
             }
         } else {
             const int fa = l3_frame_at(buf, len, p, first, &h, &w);
-            if (fa != 1) {
-                if (fa == 2 && streaming) break;
+            if (fa != 1 && !(fa == 3 && !streaming)) {
+                if (fa >= 2 && streaming) break; // wait for the rest of the frame / the confirming next header
                 p++;
                 continue;
             }

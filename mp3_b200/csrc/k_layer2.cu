@@ -169,7 +169,7 @@ k_layer2(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
     }
     off = warp_excl_scan(cbits[0] + cbits[1], lane, &tot);
     const uint32_t fi = f - sr.frame_base;
-    const size_t u0 = (size_t)sr.unit_base + (size_t)fi * 2u * (size_t)nch;
+    const size_t u0 = (size_t)(sr.unit_base - sr.sb_shift) + (size_t)fi * 2u * (size_t)nch; // dense index: Layer I / II streams only
 #pragma unroll
     for (int part = 0; part < 3; part++) // scalefactor part: compile-time index into scf[][]
     for (int gr = part * 4; gr < part * 4 + 4; gr++) {
@@ -285,14 +285,14 @@ k_layer1(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ stream
         }
         const uint32_t slot = fi * 12u + (uint32_t)t;
         for (int ch = 0; ch < nch; ch++) {
-            const size_t u = (size_t)sr.unit_base + (size_t)(slot / 18u) * nch + ch;
+            const size_t u = (size_t)(sr.unit_base - sr.sb_shift) + (size_t)(slot / 18u) * nch + ch;
             sb_out[u * 576 + (size_t)(slot % 18u) * 32 + lane] = v[ch];
         }
     }
     if (fi + 1 == sr.nframes) // the tail of the last granule
         for (uint32_t slot = sr.nframes * 12u; slot % 18u; slot++)
             for (int ch = 0; ch < nch; ch++) {
-                const size_t u = (size_t)sr.unit_base + (size_t)(slot / 18u) * nch + ch;
+                const size_t u = (size_t)(sr.unit_base - sr.sb_shift) + (size_t)(slot / 18u) * nch + ch;
                 sb_out[u * 576 + (size_t)(slot % 18u) * 32 + lane] = 0.f;
             }
 }

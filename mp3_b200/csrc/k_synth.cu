@@ -45,7 +45,7 @@ __device__ __forceinline__ int16_t to_s16(float v)
 template <int FMT>
 __global__ void __launch_bounds__(K4_THREADS)
 k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
-        const float *__restrict__ sb, void *__restrict__ pcm)
+        const float *__restrict__ sb_all, const uint32_t *__restrict__ tile_shift, void *__restrict__ pcm)
 {
     extern __shared__ float s_c[]; // [nch][K4_SLOTS][K4_FS]
     const uint32_t tile = blockIdx.x;
@@ -56,6 +56,8 @@ k_synth(const uint2 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__rest
     const bool first = (gu0 & L3G_FIRST) != 0;
     const int nch = (gu0 & L3G_STEREO) ? 2 : 1;
     const uint32_t u0 = gu0 & L3G_UNIT_MASK;
+    // Layer I / II: the subband samples live in a dense buffer of those streams only (unit - shift)
+    const float *sb = sb_all - (tile_shift ? (size_t)tile_shift[tile] * 576 : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = K4_THREADS / 32;
     const int nslots = 15 + (int)ng * 18;
 
@@ -146,8 +148,8 @@ void l3_synth_init(void)
     cudaMemcpyToSymbol(g_synwin, win, sizeof win);
 }
 
-void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const float *sb, void *pcm,
-                     int pcm_format, cudaStream_t st)
+void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const float *sb,
+                     const uint32_t *tile_shift, void *pcm, int pcm_format, cudaStream_t st)
 {
     if (!ntiles) return;
     const size_t smem = (size_t)2 * K4_SLOTS * K4_FS * sizeof(float);
@@ -158,7 +160,7 @@ void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_u
         l3_device_setup_done(attr);
     }
     if (pcm_format == MP3B_PCM_S16)
-        k_synth<MP3B_PCM_S16><<<ntiles, K4_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, sb, pcm);
+        k_synth<MP3B_PCM_S16><<<ntiles, K4_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, sb, tile_shift, pcm);
     else
-        k_synth<MP3B_PCM_F32><<<ntiles, K4_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, sb, pcm);
+        k_synth<MP3B_PCM_F32><<<ntiles, K4_THREADS, smem, st>>>(tiles, ntiles, gran_unit0, sb, tile_shift, pcm);
 }

@@ -88,7 +88,8 @@ void l3_synth_init(void);
 /* tiles[i] = {first global granule, number of granules (<= l3_synth_tile_granules())}; a tile
  * never spans two streams */
 int l3_synth_tile_granules(void);
-void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const float *sb, void *pcm,
+void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const float *sb,
+                     const uint32_t *tile_shift /* null: sb is indexed by unit */, void *pcm,
                      int pcm_format, cudaStream_t st);
 
 /* KF: fused back end (a6-a11).  tiles[i] = {first granule to output, granules to output,

@@ -43,7 +43,7 @@ typedef struct L3StreamRec {
     uint32_t tag_frames;   /* frame count field, 0 if absent */
     uint32_t tag_bytes;    /* byte count field, 0 if absent */
     uint32_t tag_delay_pad; /* encoder delay << 16 | padding (12 bits each; VBRI: delay only) */
-    uint32_t reserved;
+    uint32_t sb_shift;     /* Layer I / II: unit_base minus the stream's base in the dense subband-sample buffer */
 } L3StreamRec;
 
 #define L3T_NONE 0u
@@ -261,7 +261,9 @@ L3_HD uint32_t l3_parse_tag(const uint8_t *f, uint32_t flen, const L3Hdr *h, uin
 /* One step of the frame walk shared by the host and device indexers (the scan policy of
  * oracle/l3_oracle.c: l3o_decode): at byte p, is there a frame of this stream that fits?
  * `first` is the stream's first header (0 while none has been found). */
-/* returns 1: a complete frame; 2: a valid header of this stream whose frame runs past the buffer; 0: none */
+/* returns 1: a complete frame; 2: a valid header of this stream whose frame runs past the buffer; 0: none;
+ * 3: a complete first-frame candidate whose confirming next header lies beyond the buffer -- a one-shot decode
+ * accepts it (the buffer is the whole stream), an incremental one waits for the bytes (L3S_STREAMING) */
 L3_HD int l3_frame_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t first, L3Hdr *h, uint32_t *word)
 {
     if (p + 4 > len) return 0;
@@ -270,14 +272,15 @@ L3_HD int l3_frame_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t fir
     if (first && !l3_same_stream(w, first)) return 0;
     if (h->frame_len < 4 + (h->crc ? 2 : 0) + h->side_len) return 0;
     if (p + (uint32_t)h->frame_len > len) return 2;
-    if (!first && p + (uint32_t)h->frame_len + 4 <= len) {
+    *word = w;
+    if (!first) {
         /* the stream's first frame must be followed by a header of the same stream (when the bytes are
          * there to check): one valid-looking word inside junk or a tag does not start a stream */
+        if (p + (uint32_t)h->frame_len + 4 > len) return 3;
         const uint32_t w2 = l3_load_be32(buf + p + (uint32_t)h->frame_len);
         L3Hdr h2;
         if (!l3_parse_hdr(w2, &h2) || !l3_same_stream(w, w2)) return 0;
     }
-    *word = w;
     return 1;
 }
 

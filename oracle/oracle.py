@@ -80,8 +80,9 @@ def decode(data, dumps=False, want_pcm=True, verify_crc=False):
     max_units = cap_frames * 4
     d_is = np.zeros((max_units, 576), np.int16) if dumps else None
     d_sf = np.zeros((max_units, 40), np.uint8) if dumps else None
-    d_xr = np.zeros((max_units, 576), np.float64) if dumps else None
-    d_sb = np.zeros((max_units, 576), np.float64) if dumps else None
+    # dumps="int": only the integer stages (Huffman output, scalefactors) -- what the full-size parity tests need
+    d_xr = np.zeros((max_units, 576), np.float64) if dumps and dumps != "int" else None
+    d_sb = np.zeros((max_units, 576), np.float64) if dumps and dumps != "int" else None
 
     def ptr(a):
         return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
@@ -104,6 +105,7 @@ def decode(data, dumps=False, want_pcm=True, verify_crc=False):
         u = info.units
         out.is_ = d_is[:u]
         out.sf = d_sf[:u]
-        out.xr = d_xr[:u]
-        out.sb = d_sb[:u].reshape(u, 18, 32)
+        if d_xr is not None:
+            out.xr = d_xr[:u]
+            out.sb = d_sb[:u].reshape(u, 18, 32)
     return out

@@ -16,7 +16,7 @@ def build(tmp_path):
     exe = str(tmp_path / "cabi_check")
     cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "c", "cabi_check.c"), "-L" + os.path.join(ROOT, "mp3_b200"), "-lmp3b",
-           "-Wl,-rpath," + os.path.join(ROOT, "mp3_b200"), "-o", exe]
+           "-Wl,-rpath," + os.path.join(ROOT, "mp3_b200"), "-lm", "-o", exe]
     cuda_lib = "/usr/local/cuda/lib64"
     if os.path.isdir(cuda_lib):
         cmd += ["-L" + cuda_lib, "-Wl,-rpath," + cuda_lib]

@@ -32,6 +32,19 @@ def test_abi_version_and_strerror(lib):
     assert b"CUDA" in lib.mp3b_strerror(-5)
 
 
+def test_bad_options_are_rejected_before_any_device_is_touched(lib):
+    import mp3_b200
+    for field, val in (("pcm_format", 2), ("pcm_format", -1), ("indexer", 5), ("pipeline", 9), ("host_threads", -3),
+                       ("struct_size", 4)):
+        o = mp3_b200.Opts()
+        lib.mp3b_opts_default(ctypes.byref(o))
+        setattr(o, field, val)
+        ctx = ctypes.c_void_p()
+        assert lib.mp3b_ctx_create(0, ctypes.byref(o), ctypes.byref(ctx)) == -1, field
+        assert not ctx.value
+    assert b"Layer I" not in lib.mp3b_strerror(-4) and b"2.5" not in lib.mp3b_strerror(-4)  # both are decoded
+
+
 def test_no_cpu_fallback(lib):
     import mp3_b200
     if lib.mp3b_device_count() > 0:

@@ -1,8 +1,9 @@
 """Parity at BASELINE.json's full sizes, through size-independent properties and oracle samples.
 
   cfg2 (1024 x 383 frames), cfg3 (320 kbit/s joint stereo, switching windows, reservoir), cfg4 (LSF +
-  VBR + mono/stereo mix): a sample of streams against the oracle over their full length (ISO 11172-4),
-  every stream's length / rate / channel count, and
+  VBR + mono/stereo mix): EVERY stream against the oracle over its full length -- Huffman output and
+  scalefactors bit-exact, PCM under ISO 11172-4 --, every stream's length / rate / channel count;
+  cfg5 (100,000 streams x 128 frames) at full size: shapes, replica equality over every stream, 64 oracle checks; and
   * replication: the same stream at different batch positions decodes to identical PCM;
   * linearity: lowering every global_gain by 4 halves the float PCM exactly (requantiser gain is a
     power of two, all later stages are linear);
@@ -23,25 +24,49 @@ def mp3b():
     return mp3_b200
 
 
-def _check_sample(mp3b, oracle_mod, streams, pick, fmt_tol=True):
-    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32) as dec:
+def _check_all(mp3b, oracle_mod, streams):
+    """Every stream of the batch against the oracle: Huffman output and scalefactors bit-exact, PCM under
+    ISO/IEC 11172-4.  One fused decode with keep_stages (the product kernels; the Huffman kernel then also writes
+    the all-zero tails it normally skips, so that the dump is complete); the oracle runs on all host threads."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, keep_stages=True) as dec:
         dec.decode_batch(streams)
         arena = dec.fetch_pcm()
+        is_ = dec.stage(mp3b.STAGE_IS)
+        sf = dec.stage(mp3b.STAGE_SF)
         infos = [dec.stream_info(i) for i in range(len(streams))]
-        for i in pick:
-            ref = oracle_mod.decode(streams[i])
-            got = dec.stream_pcm(i, arena).astype(np.float64)
-            assert got.shape == ref.pcm.T.shape, i
-            l3util.assert_iso_full_accuracy(got, ref.pcm.T, "stream %d" % i)
         st = dec.stats()
-    return infos, st
+    distinct = {}
+    for i, s in enumerate(streams):
+        distinct.setdefault(s, []).append(i)
+
+    def check(item):
+        s, idx = item
+        ref = oracle_mod.decode(s, dumps="int")
+        want = ref.pcm.T
+        worst = (0.0, 0.0)
+        for i in idx:
+            inf = infos[i]
+            assert (inf.frames, inf.samples, inf.channels, inf.sample_rate) == (
+                ref.frames, ref.samples, ref.channels, ref.sample_rate), i
+            ub = inf.pcm_offset // 576
+            assert np.array_equal(is_[ub: ub + ref.units], ref.is_), "Huffman output of stream %d" % i
+            assert np.array_equal(sf[ub: ub + ref.units], ref.sf), "scalefactors of stream %d" % i
+            got = arena[inf.pcm_offset: inf.pcm_offset + inf.samples * inf.channels].reshape(inf.samples, inf.channels)
+            worst = max(worst, l3util.assert_iso_full_accuracy(got, want, "stream %d" % i))
+        return worst
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:  # l3o_decode and numpy release the GIL
+        worst = list(ex.map(check, distinct.items()))
+    return infos, st, max(w[0] for w in worst), max(w[1] for w in worst)
 
 
 @pytest.mark.parametrize("name,nstreams", [("cfg2", 1024), ("cfg3", 1024), ("cfg4", 1024)])
-def test_full_workloads_against_oracle_samples(name, nstreams, mp3b, synth_mod, oracle_mod):
+def test_full_workloads_every_stream_against_the_oracle(name, nstreams, mp3b, synth_mod, oracle_mod):
     streams = synth_mod.make_workload(name, nstreams)
-    pick = [0, 1, 2, 3, 4, 5, nstreams // 2, nstreams // 2 + 1, nstreams - 2, nstreams - 1]
-    infos, st = _check_sample(mp3b, oracle_mod, streams, pick)
+    infos, st, rms, mx = _check_all(mp3b, oracle_mod, streams)
+    print("%s: worst rms %.3g (limit %.3g), worst max %.3g (limit %.3g)" % (name, rms, l3util.RMS_LIMIT, mx, l3util.MAX_LIMIT))
     assert st.streams == nstreams and st.concealed_frames == 0
     for inf, s in zip(infos, streams):
         assert inf.frames == 383
@@ -50,6 +75,56 @@ def test_full_workloads_against_oracle_samples(name, nstreams, mp3b, synth_mod, 
     if name == "cfg4":
         assert {i.sample_rate for i in infos} == {22050, 24000, 44100}
         assert {i.channels for i in infos} == {1, 2}
+
+
+def test_cfg5_full_size(mp3b, synth_mod, oracle_mod):
+    """BASELINE.json configs[4] at its full size on one GPU: 100,000 streams x 128 frames (51.2 M units, 59 GB of s16
+    PCM, 26 waves).  1,024 distinct streams repeat; every one of the 100,000 must report the right shape, every
+    copy must equal the first copy of its stream bit for bit (compared on the device), and 64 streams spread over the
+    batch are checked against the oracle."""
+    torch = pytest.importorskip("torch")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * (1 << 30):
+        pytest.skip("needs ~75 GB of device memory")
+    N, D, NF = 100000, 1024, 128
+    base = synth_mod.make_workload("cfg5", D, NF)
+    assert len({len(s) for s in base}) == 1, "CBR streams of one rate: equal lengths (the device-side view relies on it)"
+    packed1, _ = mp3b.pack_streams(base)
+    slen = len(base[0])
+    d1 = torch.from_numpy(packed1).cuda()
+    reps = -(-N // D)
+    d_raw = d1.repeat(reps)[: N * slen].contiguous()
+    del d1
+    offs = np.arange(N + 1, dtype=np.uint64) * np.uint64(slen)
+    with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16) as dec:
+        dec.decode_packed(d_raw.data_ptr(), offs, where=mp3b.DEVICE)
+        st = dec.stats()
+        assert st.streams == N and st.frames == N * NF and st.units == N * NF * 4 and st.concealed_frames == 0
+        per = NF * 1152 * 2
+        for i in range(N):
+            inf = dec.stream_info(i)
+            assert (inf.frames, inf.samples, inf.channels, inf.sample_rate, inf.pcm_offset) == (
+                NF, NF * 1152, 2, 44100, i * per), i
+        ptr, n = dec.pcm_device()
+        assert n == N * per
+
+        class _View:  # the library's PCM arena as a torch tensor (zero copy)
+            __cuda_array_interface__ = {"shape": (N, per), "typestr": "<i2", "data": (ptr, False), "version": 2}
+        pcm = torch.as_tensor(_View(), device="cuda")
+        first = pcm[:D]
+        assert bool(first.any())
+        for k in range(1, reps):
+            blk = pcm[k * D: min((k + 1) * D, N)]
+            assert torch.equal(blk, first[: blk.shape[0]]), "replica block %d differs" % k
+        pick = sorted(set(int(x) for x in np.linspace(0, N - 1, 64)))
+        for i in pick:
+            ref = oracle_mod.decode(base[i % D])
+            got = pcm[i].cpu().numpy().reshape(-1, 2).astype(np.int64)
+            want = np.clip(np.rint(ref.pcm.T * 32768.0), -32768, 32767).astype(np.int64)
+            assert got.shape == want.shape and np.abs(got - want).max() <= 1, i
+        del pcm, first
+    del d_raw
+    torch.cuda.empty_cache()
 
 
 def test_replicated_streams_decode_identically(mp3b, synth_mod):
