@@ -82,6 +82,8 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
+    # MP3B_LIB: load another build of the library (kernel-tuning variants, tools/variant_bench.py)
+    LIB = os.environ.get("MP3B_LIB") or globals()["LIB"]
     if not os.path.exists(LIB):
         raise Mp3bError(-5, "libmp3b.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                             "there is no CPU fallback")

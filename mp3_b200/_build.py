@@ -60,3 +60,25 @@ def build_all(force=False):
     from . import synth
     synth.build(force)
     return build_lib(force)
+
+
+def build_variant(name, defines=(), sources=None):
+    """A tuning variant of the library: the translation units in `sources` (default: the two hot kernels) are
+    recompiled with extra -D flags and linked with the main build's other objects into
+    mp3_b200/variants/libmp3b_<name>.so.  Selected at run time with MP3B_LIB (tools/variant_bench.py)."""
+    build_lib()
+    sources = list(sources or ["k_fused.cu", "k_huffman.cu"])
+    vdir = os.path.join(HERE, "variants")
+    odir = os.path.join(vdir, "obj_" + name)
+    os.makedirs(odir, exist_ok=True)
+    objs = []
+    for src in CU_SOURCES + CPP_SOURCES:
+        if src in sources:
+            op = os.path.join(odir, src + ".o")
+            subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", op])
+        else:
+            op = os.path.join(OBJ, src + ".o")
+        objs.append(op)
+    lib = os.path.join(vdir, "libmp3b_%s.so" % name)
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcudart"])
+    return lib

@@ -53,4 +53,54 @@ template <> struct L3Dct2<1> {
     L3_FD static void run(float (&)[1]) {}
 };
 
+#if defined(__CUDACC__) && !defined(L3_NO_F32X2)
+#include "f32x2.h"
+/* The same recursion on PAIRS of independent sequences (x[k].x and x[k].y), one packed instruction (FADD2 / FMUL2,
+ * sm_100) per two scalar ones: the two half-size transforms of an even/odd split are such a pair.  Operation for
+ * operation the scalar algorithm, so the results are bit-identical to it. */
+template <int N> struct L3Dct2P {
+    L3_FD static void run(float2 (&x)[N])
+    {
+        float2 u[N / 2], v[N / 2];
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) {
+            u[k] = f2_add(x[k], x[N - 1 - k]);
+            v[k] = f2_mul_s(L3Twiddle<N>::at(k), f2_sub(x[k], x[N - 1 - k]));
+        }
+        L3Dct2P<N / 2>::run(u);
+        L3Dct2P<N / 2>::run(v);
+        float2 prev = f2_mul_s(0.5f, v[0]);
+        x[0] = u[0];
+        x[1] = prev;
+#pragma unroll
+        for (int m = 1; m < N / 2; m++) {
+            x[2 * m] = u[m];
+            prev = f2_sub(v[m], prev);
+            x[2 * m + 1] = prev;
+        }
+    }
+};
+template <> struct L3Dct2P<1> {
+    L3_FD static void run(float2 (&)[1]) {}
+};
+/* 32-point transform of one sequence: the first split in scalar form, its two 16-point halves as one packed pair */
+L3_FD void l3_dct2_32_packed(float (&x)[32])
+{
+    float2 h[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        h[k] = make_float2(x[k] + x[31 - k], (x[k] - x[31 - k]) * L3Twiddle<32>::at(k));
+    L3Dct2P<16>::run(h);
+    float prev = h[0].y * 0.5f;
+    x[0] = h[0].x;
+    x[1] = prev;
+#pragma unroll
+    for (int m = 1; m < 16; m++) {
+        x[2 * m] = h[m].x;
+        prev = h[m].y - prev;
+        x[2 * m + 1] = prev;
+    }
+}
+#endif
+
 #endif

@@ -33,21 +33,34 @@
 #include <type_traits>
 
 #include "consts_gen.h"
+#include "f32x2.h"
 #include "fast_dct.h"
 #include "fast_imdct.h"
 #include "iso_tables.h"
 #include "kernels.h"
 #include "mp3b.h"
 
+#ifndef KF_CTAS_S16
+#define KF_CTAS_S16 4    // resident CTAs per SM the s16 kernel is compiled for (4: 64 registers; 3: 80)
+#endif
+#ifndef KF_WIN_F32X2
+#define KF_WIN_F32X2 1   // S4: the synthesis window as packed FFMA2 (two output slots per instruction)
+#endif
+#ifndef KF_DCT_F32X2
+#define KF_DCT_F32X2 1   // S3: the two 16-point halves of the 32-point transform as one packed pair
+#endif
+
 namespace {
 
 constexpr int KF_B = 4;         // granules per batch
 constexpr int KF_THREADS = 256;
 constexpr int KF_ROWS = 15 + KF_B * 18;
-constexpr int XROW = 19;        // padded subband row of X
-constexpr int XSZ = 32 * XROW;  // 608 floats per channel spectrum
-constexpr int KF_POW_LUT = 512;
-constexpr int FS = 33;         // row stride of F: odd, so rows are conflict-free both by lane = column and lane = row
+constexpr int XROW = 18;        // subband row of X: unpadded -- S1 stores line pairs (8 bytes), S2 reads a row as nine
+                                // 8-byte words, and at a stride of 9 such words the 16 lanes of a half warp hit 16 banks pairs
+constexpr int XSZ = 32 * XROW;  // 576 floats per channel spectrum
+constexpr int KF_POW_LUT = 1024; // sign(x) |x|^(4/3) for x = -512 .. 511, indexed by x & 1023
+constexpr int FS = 36;         // row stride of F: 16-byte aligned rows, so S3 moves a row as eight 16-byte words (rows r .. r+7
+                               // of a quarter warp start 4 banks apart: conflict-free); by lane = column any stride is
 
 __constant__ float f_pow2q[4];
 __constant__ float f_is_kl[7], f_is_kr[7];
@@ -55,12 +68,12 @@ __constant__ float f_lsf_pow[2][16];
 __constant__ float f_cs[8], f_ca[8];
 __constant__ uint8_t f_pretab[22];
 __constant__ float f_win[4][36];
-__device__ float f_synwin[16][32];
+__device__ float f_synwin[2][16][32]; // [0] for float PCM; [1] scaled by 32768 for s16 PCM (exact: a power of two)
 
 struct GranMeta {
     L3UnitDesc d[2];
     int row, lay[2];
-    int joint;      // 0 = independent channels, 1 = MS and/or intensity processing applies
+    int slow;       // bit 16 c + 2q + h: the 64 lines from 128 q + 64 h on of unit c may hold |is| > 511 (S1)
     int ms, ist;
 };
 
@@ -74,11 +87,10 @@ template <> struct IsOwn<MP3B_PCM_S16> {};
 
 template <int FMT>
 struct FusedSharedT {
-    __align__(16) float X[KF_B][2][XSZ]; // spectra of the batch, padded rows; PCM staging in S4; (s16) next batch's is
-    float F[2][KF_ROWS][FS];        // rows 0..14: C history; rows 15..: first IMDCT halves -> S -> C
+    __align__(16) float X[KF_B][2][XSZ]; // spectra of the batch; PCM staging in S4; (s16) next batch's is
+    __align__(16) float F[2][KF_ROWS][FS]; // rows 0..14: C history; rows 15..: first IMDCT halves -> S -> C
     __align__(16) float Hc[2][18][32]; // second IMDCT half of the last granule of the previous batch
-    float pow43[KF_POW_LUT];        // |is|^(4/3) for the common small values
-    float win[16][32];              // per-lane window taps (copied from global once)
+    float pow43[KF_POW_LUT];        // sign(x) |x|^(4/3), x = -512 .. 511 at index x & 1023
     float gain[KF_B][2][40];
     float kl[KF_B][40], kr[KF_B][40];
     uint8_t nz[KF_B][40];           // right-channel band has a non-zero line (intensity bound)
@@ -99,6 +111,8 @@ struct FusedSharedT {
     }
 };
 static_assert(KF_B * 2 * 576 * 2 * 2 <= (int)sizeof(float) * KF_B * 2 * XSZ, "is buffer must fit behind the s16 staging area");
+// Huffman books whose escapes (linbits >= 9) can produce |is| > 511: table_select 22, 23, 29, 30, 31
+constexpr uint32_t KF_BIG_TABLES = (1u << 22) | (1u << 23) | (1u << 29) | (1u << 30) | (1u << 31);
 
 // f_pow2q[q & 3] * 2^(q >> 2), exactly (q >> 2 stays within the normal exponent range: -82 .. 11)
 __device__ __forceinline__ float gain_of(int q) { return __int_as_float((127 + (q >> 2)) << 23) * f_pow2q[q & 3]; }
@@ -107,12 +121,10 @@ __device__ __forceinline__ float gain_of(int q) { return __int_as_float((127 + (
 static_assert(sizeof(FusedSharedT<MP3B_PCM_S16>) <= 56 * 1024, "s16 back end: too large for 4 CTAs per SM");
 static_assert(sizeof(FusedSharedT<MP3B_PCM_F32>) <= 75 * 1024, "f32 back end: too large for 3 CTAs per SM");
 
-__device__ __forceinline__ int xpad(int i) { return i + ((i * 3641) >> 16); } // i + i / 18 for i < 608
-
-__device__ __forceinline__ int16_t to_s16(float v)
+__device__ __forceinline__ int16_t to_s16(float v) // v already in s16 units (the s16 window set is scaled)
 {
     int r;
-    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r) : "f"(v * 32768.f));
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r) : "f"(v));
     return (int16_t)r;
 }
 
@@ -220,9 +232,22 @@ __device__ __forceinline__ void finish_meta(SH &S, int tid, int nb, int nch)
         const bool ok = (m.d[0].flags & L3F_VALID) != 0;
         m.ms = (nch == 2 && ok && (m.d[0].hdr & L3H_MS)) ? 1 : 0;
         m.ist = (nch == 2 && ok && (m.d[0].hdr & L3H_IS)) ? 1 : 0;
-        m.joint = m.ms | m.ist;
         if (m.ist) S.any_ist = 1;
         if (m.lay[0] | m.lay[1]) S.any_short = 1;
+        // Which 64-line spans (one warp's share of one S1 trip) can hold a value outside the small signed
+        // |is|^(4/3) table: only the big_values regions coded with a book whose escapes reach that far.
+        // Everything else -- other books (|is| <= 270), the count1 region (+-1), the zero tail -- cannot.
+        int slow = 0;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const L3UnitDesc &dd = m.d[c];
+            const int lim[4] = {0, dd.r1, dd.r2, 2 * (int)dd.big_values};
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (((KF_BIG_TABLES >> dd.tsel[r]) & 1u) && lim[r + 1] > lim[r])
+                    for (int k = lim[r] >> 6; k <= (lim[r + 1] - 1) >> 6; k++) slow |= 1 << (16 * c + k);
+        }
+        m.slow = slow;
     }
 }
 
@@ -343,96 +368,170 @@ __device__ __forceinline__ void stage_intensity(SH &S, int gi, int u1 /* batch-l
     }
 }
 
+// One spectral value of a packed pair (low / high half of a 32-bit word of the Huffman output) times its band gain.
+// Fast: the signed table, for values known to lie in -512 .. 511 (index = the value's low ten bits, scaled to bytes).
+template <class SH> __device__ __forceinline__ float rq_lo(const SH &S, uint32_t w, float g)
+{
+    return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(S.pow43) + ((w << 2) & 0xffcu)) * g;
+}
+template <class SH> __device__ __forceinline__ float rq_hi(const SH &S, uint32_t w, float g)
+{
+    return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(S.pow43) + ((w >> 14) & 0xffcu)) * g;
+}
+// Any value (escapes up to 8206): the full table in global memory beyond the shared one.  Branch-free: the shared
+// lookup is always made (index clamped), the global one is a predicated load that only lanes with |v| > 511 perform.
 template <class SH>
-__device__ __forceinline__ float requant1(const SH &S, int v, float gain, const float *__restrict__ pow43)
+__device__ __forceinline__ float rq_any(const SH &S, int v, float gain, const float *__restrict__ pow43)
 {
     const int m = v < 0 ? -v : v;
-    const float p = m < KF_POW_LUT ? S.pow43[m] : __ldg(pow43 + m);
-    const float a = p * gain;
-    return v < 0 ? -a : a;
+    float p = S.pow43[min(m, 511)];
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %1, 511;\n\t@q ld.global.nc.f32 %0, [%2];\n\t}" : "+f"(p) : "r"(m), "l"(pow43 + m));
+    return __int_as_float(__float_as_int(p * gain) | (v & 0x80000000));
 }
 
-// ---- S1c: requantise + stereo + reorder, one (granule, line) per item -----------------------------
-// `bq` holds this thread's nine long-block band indices (lines t64 + 64 q), one byte each: they
-// depend only on the stream's sample rate, so the common case (both channels long blocks, no
-// intensity stereo) needs no table lookups, no reorder and no branches per line.
-// First half: every thread pulls its nine line pairs of the Huffman output into registers.  With s16
+// ---- S1c: requantise + stereo + reorder, one pair of adjacent lines of both channels per item -----------
+// 64 threads per granule: thread t64 takes the line pairs t64 + 64 q, q < 5 (288 pairs; the second warp
+// has no fifth trip).  A pair never straddles a scalefactor band (all band edges are even) nor a subband
+// row (18 is even), so it shares one gain per channel and leaves as one 8-byte store.
+// `bq` holds the long-block band index of this thread's five pairs, one byte each: they depend only on the
+// stream's sample rate, so the common case (both channels long blocks, no intensity stereo) needs no table
+// lookups, no reorder and no branches per line.
+// First half: every thread pulls its five word pairs of the Huffman output into registers.  With s16
 // output that buffer lives inside X, which the second half overwrites: the caller puts a barrier between
 // the two.
 template <class SH>
-__device__ __forceinline__ void requant_load(SH &S, int tid, int nb, uint32_t (&v)[9])
+__device__ __forceinline__ void requant_load(SH &S, int tid, int nb, uint32_t (&v)[10])
 {
     const int gi = tid >> 6, t64 = tid & 63;
     if (gi >= nb) return;
-    const uint16_t *s0 = reinterpret_cast<const uint16_t *>(S.is_buf()[gi * 2]);
-    const uint16_t *s1 = reinterpret_cast<const uint16_t *>(S.is_buf()[gi * 2 + 1]);
+    const uint32_t *s0 = reinterpret_cast<const uint32_t *>(S.is_buf()[gi * 2]);
+    const uint32_t *s1 = reinterpret_cast<const uint32_t *>(S.is_buf()[gi * 2 + 1]);
 #pragma unroll
-    for (int q = 0; q < 9; q++) v[q] = (uint32_t)s0[t64 + 64 * q] | ((uint32_t)s1[t64 + 64 * q] << 16); // packed pair
+    for (int q = 0; q < 5; q++)
+        if (q < 4 || t64 < 32) { // (warp-uniform)
+            v[2 * q] = s0[t64 + 64 * q];
+            v[2 * q + 1] = s1[t64 + 64 * q];
+        }
 }
 
 template <class SH>
 __device__ __forceinline__ void stage_requant(SH &S, int tid, int nb, const L3BandTables *__restrict__ bands,
-                                              const float *__restrict__ pow43, const uint32_t (&bq)[3],
-                                              const uint32_t (&v)[9])
+                                              const float *__restrict__ pow43, const uint32_t (&bq)[2],
+                                              const uint32_t (&v)[10])
 {
-    constexpr int ITEMS = 576 / 64; // 9 lines per thread: 64 threads per granule
     const float isq2 = 0.70710678118654752440f;
     const int gi = tid >> 6, t64 = tid & 63;
     if (gi >= nb) return;
     const GranMeta &m = S.gm[gi];
     const int lay0 = m.lay[0], lay1 = m.lay[1];
     const float *g0 = S.gain[gi][0], *g1 = S.gain[gi][1];
+    // bit 2q (unit 0) / 16 + 2q (unit 1): this warp's span of trip q may hold values beyond the shared table
+    const uint32_t slow = (uint32_t)m.slow >> ((tid >> 5) & 1);
     if ((lay0 | lay1) == 0 && !m.ist) {
-        float *X0 = S.X[gi][0], *X1 = S.X[gi][1];
+        float2 *X0 = reinterpret_cast<float2 *>(S.X[gi][0]), *X1 = reinterpret_cast<float2 *>(S.X[gi][1]);
         // MS: (M +- S) / sqrt 2; stage_gains has folded the factor into this granule's band gains
         auto lines = [&](auto ms_tag) {
 #pragma unroll
-            for (int q = 0; q < ITEMS; q++) {
-                const int b = (bq[q >> 2] >> (8 * (q & 3))) & 0xff;
-                const int w0 = (int)(short)(v[q] & 0xffffu), w1 = (int)v[q] >> 16;
-                const int m0 = abs(w0), m1 = abs(w1);
-                const float p0 = m0 < KF_POW_LUT ? S.pow43[m0] : __ldg(pow43 + m0);
-                const float p1 = m1 < KF_POW_LUT ? S.pow43[m1] : __ldg(pow43 + m1);
-                const float a = __int_as_float(__float_as_int(p0 * g0[b]) | (w0 & 0x80000000));
-                const float c = __int_as_float(__float_as_int(p1 * g1[b]) | (w1 & 0x80000000));
-                const int xp = xpad(t64 + 64 * q);
-                X0[xp] = decltype(ms_tag)::value ? a + c : a;
-                X1[xp] = decltype(ms_tag)::value ? a - c : c;
+            for (int q = 0; q < 5; q++) {
+                if (q == 4 && t64 >= 32) break;
+                uint32_t bw = bq[q >> 2];
+                asm volatile("" : "+r"(bw)); // opaque: the gain addresses are cheap to form, costly to keep (spills)
+                const int b = (bw >> (8 * (q & 3))) & 0xff;
+                const float ga = g0[b], gb = g1[b];
+                const uint32_t wa = v[2 * q], wb = v[2 * q + 1];
+                float a0, a1, c0, c1;
+                if (slow & (1u << (2 * q))) { // (warp-uniform)
+                    a0 = rq_any(S, (int)(short)(wa & 0xffffu), ga, pow43);
+                    a1 = rq_any(S, (int)wa >> 16, ga, pow43);
+                } else {
+                    a0 = rq_lo(S, wa, ga);
+                    a1 = rq_hi(S, wa, ga);
+                }
+                if (slow & (0x10000u << (2 * q))) {
+                    c0 = rq_any(S, (int)(short)(wb & 0xffffu), gb, pow43);
+                    c1 = rq_any(S, (int)wb >> 16, gb, pow43);
+                } else {
+                    c0 = rq_lo(S, wb, gb);
+                    c1 = rq_hi(S, wb, gb);
+                }
+                const int p = t64 + 64 * q;
+                X0[p] = decltype(ms_tag)::value ? make_float2(a0 + c0, a1 + c1) : make_float2(a0, a1);
+                X1[p] = decltype(ms_tag)::value ? make_float2(a0 - c0, a1 - c1) : make_float2(c0, c1);
             }
         };
         if (m.ms) lines(std::true_type{});
         else lines(std::false_type{});
         return;
     }
-    // general path (short / mixed blocks, intensity stereo): band and reordered padded position of every
-    // line from the per-rate line map (global memory, L1-resident)
-    const uint32_t *lm0 = bands->lmap[m.row][lay0], *lm1 = bands->lmap[m.row][lay1];
+    // general path (short / mixed blocks, intensity stereo): band and reordered position of every line from the
+    // per-rate line map (global memory, L1-resident)
+    const uint2 *lm0 = reinterpret_cast<const uint2 *>(bands->lmap[m.row][lay0]);
+    const uint2 *lm1 = reinterpret_cast<const uint2 *>(bands->lmap[m.row][lay1]);
     const bool ist = m.ist != 0, ms = m.ms != 0;
 #pragma unroll
-    for (int q = 0; q < ITEMS; q++) {
-        const int i = t64 + 64 * q;
-        const uint32_t e0 = __ldg(lm0 + i), e1 = __ldg(lm1 + i);
-        const int b1 = (int)(e1 & 0xffu);
-        float l = requant1(S, (int)(short)(v[q] & 0xffffu), g0[e0 & 0xffu], pow43);
-        float r = requant1(S, (int)v[q] >> 16, g1[b1], pow43);
-        if (ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
-        else if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
-        S.X[gi][1][e1 >> 8] = r;
-        S.X[gi][0][e0 >> 8] = l;
+    for (int q = 0; q < 5; q++) {
+        if (q == 4 && t64 >= 32) break;
+        const int p = t64 + 64 * q;
+        const uint2 e0 = __ldg(lm0 + p), e1 = __ldg(lm1 + p);
+        const uint32_t wa = v[2 * q], wb = v[2 * q + 1];
+        const bool sla = (slow & (1u << (2 * q))) != 0, slb = (slow & (0x10000u << (2 * q))) != 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t f0 = h ? e0.y : e0.x, f1 = h ? e1.y : e1.x;
+            const int b1 = (int)(f1 & 0xffu);
+            const float ga = g0[f0 & 0xffu], gb = g1[b1];
+            float l, r;
+            if (sla) l = rq_any(S, h ? (int)wa >> 16 : (int)(short)(wa & 0xffffu), ga, pow43);
+            else l = h ? rq_hi(S, wa, ga) : rq_lo(S, wa, ga);
+            if (slb) r = rq_any(S, h ? (int)wb >> 16 : (int)(short)(wb & 0xffffu), gb, pow43);
+            else r = h ? rq_hi(S, wb, gb) : rq_lo(S, wb, gb);
+            if (ist && S.mode[gi][b1]) { const float a = l; l = a * S.kl[gi][b1]; r = a * S.kr[gi][b1]; }
+            else if (ms) { const float a = l, c = r; l = (a + c) * isq2; r = (a - c) * isq2; }
+            S.X[gi][1][f1 >> 8] = r;
+            S.X[gi][0][f0 >> 8] = l;
+        }
     }
 }
 
 // ---- S2: alias reduction + IMDCT of one (granule, channel) by one warp, lane = subband ----------
-// First halves go to Fdst (plus `carry`, the previous batch's last second half, for the batch's first
-// granule); the second half stays in registers (h) and is added to the next granule's rows after a
-// barrier, so no second-half buffer is needed.
-__device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lane, uint8_t flags,
-                                            float *__restrict__ Fdst /* [18][32] */,
-                                            const float *__restrict__ carry /* [18][32] or null */, float (&h)[18])
+// First halves go to the granule's rows of F.  Second halves (overlap-add with the NEXT granule) go to Hdst as
+// [slot t][32 subbands], row t rotated by 4 t floats: the granule's own, now dead, spectrum X -- S3 adds them
+// to the next granule's rows while it loads those, 16 bytes at a time, and the rotation keeps the eight rows a
+// quarter warp reads together in different banks -- or, for the last granule of a batch, the carry buffer Hc
+// (plain layout), whose previous content the warp of the batch's FIRST granule adds to its first halves here.
+// Those two warps touch Hc in the same phase: the reader announces on a named barrier (role 1) that its loads
+// are done, the writer waits there (role 2) before storing; a batch of one granule is both (role 3: program order).
+// (barrier 0 is __syncthreads; 1 and 2 serve the two channel sequences; immediates, so that no more are reserved)
+__device__ __forceinline__ void named_arrive(int id)
 {
+    if (id == 1) asm volatile("barrier.arrive 1, 64;" ::: "memory");
+    else asm volatile("barrier.arrive 2, 64;" ::: "memory");
+}
+__device__ __forceinline__ void named_sync(int id)
+{
+    if (id == 1) asm volatile("barrier.sync 1, 64;" ::: "memory");
+    else asm volatile("barrier.sync 2, 64;" ::: "memory");
+}
+
+__device__ __forceinline__ void stage_imdct(float *__restrict__ X, int lane, uint8_t flags,
+                                            float *__restrict__ Fdst /* [18][FS] */, float *__restrict__ Hc,
+                                            int role, int bar_id)
+{
+    const bool reads_carry = (role & 1) != 0, writes_carry = (role & 2) != 0;
+    float *const Hdst = writes_carry ? Hc : X;
+    const int rot = writes_carry ? 0 : 4;
+    float h[18];
     float x[18];
+    {
+        const float2 *Xr = reinterpret_cast<const float2 *>(X + lane * XROW); // 72-byte rows: 8-byte aligned
 #pragma unroll
-    for (int k = 0; k < 18; k++) x[k] = X[lane * XROW + k];
+        for (int k = 0; k < 9; k++) {
+            const float2 t = Xr[k];
+            x[2 * k] = t.x;
+            x[2 * k + 1] = t.y;
+        }
+        __syncwarp(); // the warp's second halves will overwrite this spectrum
+    }
     int bt = flags & L3F_BT_MASK;
     const bool mixed = bt == 2 && (flags & L3F_MIXED);
     // alias butterflies between subband `lane - 1` (its lines 17-i) and `lane` (its lines i), i < 8
@@ -462,7 +561,7 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
             // opposite parity, so exactly one of each pair takes the inversion sign
             const float sa_s = sa * sgn, sb_s = sb * sgn;
             float f0 = ((i & 1) ? sa_s : sa) * w[i], f1 = -((i & 1) ? sa : sa_s) * w[17 - i];
-            if (carry) { f0 += carry[i * 32 + lane]; f1 += carry[(17 - i) * 32 + lane]; }
+            if (reads_carry) { f0 += Hc[i * 32 + lane]; f1 += Hc[(17 - i) * 32 + lane]; }
             Fdst[i * FS + lane] = f0;
             Fdst[(17 - i) * FS + lane] = f1;
             h[i] = ((i & 1) ? sb_s : sb) * w[18 + i];
@@ -491,10 +590,10 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
         for (int i = 0; i < 6; i++) {
             const float s_i = (i & 1) ? sgn : 1.f; // 6 and 12 are even: parity of i everywhere
             float f0 = 0.f, f1 = y[0][i] * s_i, f2 = (y[0][6 + i] + y[1][i]) * s_i;
-            if (carry) {
-                f0 += carry[i * 32 + lane];
-                f1 += carry[(6 + i) * 32 + lane];
-                f2 += carry[(12 + i) * 32 + lane];
+            if (reads_carry) {
+                f0 += Hc[i * 32 + lane];
+                f1 += Hc[(6 + i) * 32 + lane];
+                f2 += Hc[(12 + i) * 32 + lane];
             }
             Fdst[i * FS + lane] = f0;
             Fdst[(6 + i) * FS + lane] = f1;
@@ -504,6 +603,10 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
             h[12 + i] = 0.f;
         }
     }
+    if (role == 1) named_arrive(bar_id); // (the carry has been added: those loads are complete)
+    if (role == 2) named_sync(bar_id);
+#pragma unroll
+    for (int t = 0; t < 18; t++) Hdst[t * 32 + ((lane + rot * t) & 31)] = h[t];
 }
 
 // ---- S4: synthesis window for one (granule, channel), lane = sample j ---------------------------
@@ -512,6 +615,40 @@ __device__ __forceinline__ void stage_imdct(const float *__restrict__ X, int lan
 // evaluated as a sliding accumulation over the rows: each row is loaded once (2 LDS) and feeds the
 // up to 16 outputs it contributes to.  Everything is unrolled, so the 16-entry accumulator ring and
 // the window taps live in registers.
+#if KF_WIN_F32X2
+// Packed form (FFMA2, sm_100): two consecutive output slots T = 2k, 2k + 1 share every weight,
+//   (out[2k], out[2k+1]) = sum_i W[2i] (e[2a+1], e[2a+2]) + W[2i+1] (o[2a], o[2a+1]),  a = k + 7 - i,
+// so an instruction takes a scalar weight (broadcast operand) times a PAIR of rows: 144 FFMA2 per granule and
+// channel instead of 288 FFMA.  e / o: the row's even- / odd-tap column of this lane; rows are relative to r0.
+template <typename Emit>
+__device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r0, int src_e, int src_o,
+                                             const float (&wn)[16], Emit emit)
+{
+    float2 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 16; a++) {
+        const float *row = Fc + (r0 + 2 * a) * FS;
+        const float2 ep = make_float2(row[FS + src_e], row[2 * FS + src_e]); // rows 2a + 1, 2a + 2
+        const float2 op = make_float2(row[src_o], row[FS + src_o]);         // rows 2a, 2a + 1
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int k = a - 7 + i;
+            if (k >= 0 && k <= 8) {
+                acc[k & 7] = f2_fma_s(wn[2 * i], ep, acc[k & 7]);
+                acc[k & 7] = f2_fma_s(wn[2 * i + 1], op, acc[k & 7]);
+            }
+        }
+        if (a >= 7) {
+            const int k = a - 7;
+            emit(2 * k, acc[k & 7].x);
+            emit(2 * k + 1, acc[k & 7].y);
+            acc[k & 7] = make_float2(0.f, 0.f);
+        }
+    }
+}
+#else
 template <typename Emit>
 __device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r0, int src_e, int src_o,
                                              const float (&wn)[16], Emit emit)
@@ -533,6 +670,7 @@ __device__ __forceinline__ void stage_window(const float *__restrict__ Fc, int r
         }
     }
 }
+#endif
 
 // One tile.  MONO is a compile-time switch so that the stereo path carries none of the mono index
 // arithmetic: pairs of consecutive mono granules take the two slots a stereo granule's channels would,
@@ -557,9 +695,12 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = tid; i < 2 * 15 * FS; i += KF_THREADS) S.F[i / (15 * FS)][0][i % (15 * FS)] = 0.f;
+        static_assert(FS % 4 == 0, "rows move as 16-byte words");
         for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.Hc[i / 144][0][0])[i % 144] = z;
-        for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) S.pow43[i] = pow43[i];
-        for (int i = tid; i < 512; i += KF_THREADS) (&S.win[0][0])[i] = (&f_synwin[0][0])[i];
+        for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) { // signed: index = the value's low ten bits
+            const int x = i < KF_POW_LUT / 2 ? i : i - KF_POW_LUT;
+            S.pow43[i] = x < 0 ? -pow43[-x] : pow43[x];
+        }
         load_meta(S, tid, ubase, min(KFG, total) * nch, units);
         prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in, nzv_in);
     }
@@ -568,12 +709,13 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
     const int src_e = lane <= 15 ? 16 + lane : (lane == 16 ? 0 : 48 - lane);
     const int src_o = lane <= 16 ? 16 - lane : lane - 16;
     pcm_t *stage = reinterpret_cast<pcm_t *>(&S.X[0][0][0]);
-    uint32_t bq[3] = {0, 0, 0}; // long-block band index of this thread's nine lines (see stage_requant)
+    uint32_t bq[2] = {0, 0}; // long-block band index of this thread's five line pairs (see stage_requant)
     {
         const int row0 = (units[ubase].hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
 #pragma unroll
-        for (int q = 0; q < 9; q++)
-            bq[q >> 2] |= (uint32_t)bands->line2band[row0][0][(tid & 63) + 64 * q] << (8 * (q & 3));
+        for (int q = 0; q < 5; q++)
+            if (q < 4 || (tid & 63) < 32)
+                bq[q >> 2] |= (uint32_t)bands->line2band[row0][0][2 * ((tid & 63) + 64 * q)] << (8 * (q & 3));
     }
 
     for (int b0 = 0; b0 < total; b0 += KFG) {
@@ -594,65 +736,75 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
             __syncthreads();
         }
         {
-            uint32_t v[9];
+            uint32_t v[10];
             requant_load(S, tid, np, v);
             if (FMT == MP3B_PCM_S16) __syncthreads(); // the Huffman output sits inside X, which is written next
             stage_requant(S, tid, np, bands, pow43, bq, v);
         }
         __syncthreads();
-        // ---- S2: alias + IMDCT; second halves travel in registers to the next granule's rows
+        // ---- S2: alias + IMDCT; first halves -> F rows, second halves -> the granule's dead spectrum / Hc
         {
             // warp -> slot (gi, c); j = its granule inside the batch, seq = the row sequence it belongs to
             const int gi = warp >> 1, c = warp & 1;
             const int j = mono ? warp : gi;
-            const bool act = j < nb;
-            float *const seq = mono ? Fm : &S.F[c][0][0];
-            float *const hc = &S.Hc[mono ? 0 : c][0][0];
-            float h[18];
-            if (act)
-                stage_imdct(S.X[gi][c], lane, S.gm[gi].d[c].flags, seq + (15 + j * 18) * FS, j == 0 ? hc : nullptr, h);
-            __syncthreads();
-            if (act) {
-                float *dst = j + 1 < nb ? seq + (15 + (j + 1) * 18) * FS : hc;
-                if (j + 1 < nb) {
-#pragma unroll
-                    for (int t = 0; t < 18; t++) dst[t * FS + lane] += h[t];
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 18; t++) dst[t * 32 + lane] = h[t];
-                }
+            if (j < nb) {
+                const int role = (j == 0 ? 1 : 0) | (j == nb - 1 ? 2 : 0);
+                stage_imdct(S.X[gi][c], lane, S.gm[gi].d[c].flags, (mono ? Fm : &S.F[c][0][0]) + (15 + j * 18) * FS,
+                            &S.Hc[mono ? 0 : c][0][0], role, 1 + (mono ? 0 : c));
             }
         }
         __syncthreads();
-        // next batch: descriptors (gm is dead until the next S1) and, behind S3..S5, spectra + scalefactors
-        if (b0 + KFG < total) {
+        // next batch: descriptors (gm is dead until the next S1)
+        if (b0 + KFG < total)
             load_meta(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, units);
-            prefetch_units(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, is_in, sf_in,
-                           nzv_in);
-        }
-        // ---- S3: 32-point transform of every slot, in place; one thread per (channel, slot) row,
-        // the whole transform in registers (fast_dct.h: 304 operations instead of 1024 FMAs)
+        // ---- S3: overlap-add + 32-point transform of every slot, in place; one thread per (channel, slot) row,
+        // the whole transform in registers (fast_dct.h: 304 operations instead of 1024 FMAs).  The row's other
+        // summand, the previous granule's second half, comes from that granule's X (rotated rows, see S2); the
+        // batch's first granule took its carry in S2.
         {
             const int rows_c = nb * 18; // rows per sequence: stereo has two sequences, mono one
             if (tid < nch * rows_c) {
-                const int c = tid >= rows_c ? 1 : 0;
-                float *row = &S.F[c][0][0] + (15 + tid - c * rows_c) * FS;
+                const int c = tid >= rows_c ? 1 : 0, r = tid - c * rows_c;
+                const int j = (r * 57) >> 10, t = r - 18 * j; // r / 18 for r < 160
+                float4 *row = reinterpret_cast<float4 *>(&S.F[c][0][0] + (15 + r) * FS);
                 float x[32];
 #pragma unroll
-                for (int k = 0; k < 32; k++) x[k] = row[k];
-                L3Dct2<32>::run(x);
+                for (int k = 0; k < 8; k++) {
+                    const float4 q = row[k];
+                    x[4 * k] = q.x; x[4 * k + 1] = q.y; x[4 * k + 2] = q.z; x[4 * k + 3] = q.w;
+                }
+                if (j > 0) {
+                    const int jp = j - 1; // slot of the previous granule: stereo (jp, c), mono (jp >> 1, jp & 1)
+                    const float4 *hrow = reinterpret_cast<const float4 *>(
+                        (mono ? &S.X[jp >> 1][jp & 1][0] : &S.X[jp][c][0]) + t * 32);
 #pragma unroll
-                for (int k = 0; k < 32; k++) row[k] = x[k];
+                    for (int k = 0; k < 8; k++) {
+                        const float4 q = hrow[(k + t) & 7];
+                        x[4 * k] += q.x; x[4 * k + 1] += q.y; x[4 * k + 2] += q.z; x[4 * k + 3] += q.w;
+                    }
+                }
+#if KF_DCT_F32X2
+                l3_dct2_32_packed(x);
+#else
+                L3Dct2<32>::run(x);
+#endif
+#pragma unroll
+                for (int k = 0; k < 8; k++) row[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
             }
         }
         __syncthreads();
+        // next batch's spectra + scalefactors, behind S4 / S5 (not earlier: with s16 output the fetch buffer lies
+        // inside X, whose second halves S3 has just consumed)
+        if (b0 + KFG < total)
+            prefetch_units(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, is_in, sf_in,
+                           nzv_in);
         // ---- S4: window -> PCM staging (X is free now)
         {
             const int c = mono ? 0 : (warp & 1), j = mono ? warp : (warp >> 1);
             if (j < nb && b0 + j >= warm) {
-                float wn[16];
+                float wn[16]; // this lane's 16 taps (L1-resident; the s16 set carries the factor 32768)
 #pragma unroll
-                for (int l = 0; l < 16; l++) wn[l] = S.win[l][lane];
+                for (int l = 0; l < 16; l++) wn[l] = __ldg(&f_synwin[FMT == MP3B_PCM_S16 ? 1 : 0][l][lane]);
                 pcm_t *dst = stage + (size_t)j * 576 * nch + c;
                 stage_window(&S.F[c][0][0], j * 18, src_e, src_o, wn, [&](int t, float val) {
                     if (FMT == MP3B_PCM_S16) dst[(t * 32 + lane) * nch] = (pcm_t)to_s16(val);
@@ -670,18 +822,23 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
                 const uint32_t bytes = (uint32_t)((nb - first_out) * 576 * nch) * (uint32_t)sizeof(pcm_t);
                 bulk_s2g(reinterpret_cast<pcm_t *>(pcm) + e0, stage + (size_t)first_out * 576 * nch, bytes);
             }
-            for (int k = tid; k < 15 * FS; k += KF_THREADS) {
-                Fm[k] = Fm[nb * 18 * FS + k];
-                if (!mono) S.F[1][0][k] = S.F[1][nb * 18][k];
+            {
+                // the last 15 transformed slots become the history rows (16-byte words; stereo: two sequences)
+                constexpr int NV = 15 * FS / 4;
+                for (int i = tid; i < (mono ? NV : 2 * NV); i += KF_THREADS) {
+                    float4 *seq = reinterpret_cast<float4 *>(i < NV ? Fm : &S.F[1][0][0]);
+                    const int k = i < NV ? i : i - NV;
+                    seq[k] = seq[nb * 18 * (FS / 4) + k];
+                }
             }
         }
-        __syncthreads();
+        // (no barrier here: nothing before the next batch's first barrier touches what S5 reads or writes)
     }
     if (tid == KF_THREADS - 32) bulk_wait_read_all(); // the last PCM store must have read the staging buffer
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(KF_THREADS, FMT == MP3B_PCM_S16 ? 4 : 3)
+__global__ void __launch_bounds__(KF_THREADS, FMT == MP3B_PCM_S16 ? KF_CTAS_S16 : 3)
 k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__restrict__ gran_unit0,
           const L3UnitDesc *__restrict__ units, const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
           const uint8_t *__restrict__ nzv_in, const L3BandTables *__restrict__ bands,
@@ -741,14 +898,15 @@ void l3_fused_init(void)
     }
     cudaMemcpyToSymbol(f_win, W, sizeof W);
 
-    static float win[16][32];
+    static float win[2][16][32];
     for (int l = 0; l < 16; l++)
         for (int j = 0; j < 32; j++) {
             const int i = l >> 1;
             double v;
             if (!(l & 1)) v = l3_dwin(64 * i + j) * (j <= 15 ? 1.0 : (j == 16 ? 0.0 : -1.0));
             else v = -l3_dwin(64 * i + 32 + j);
-            win[l][j] = (float)v;
+            win[0][l][j] = (float)v;
+            win[1][l][j] = (float)v * 32768.f;
         }
     cudaMemcpyToSymbol(f_synwin, win, sizeof win);
     cudaFuncSetAttribute(k_backend<MP3B_PCM_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize,

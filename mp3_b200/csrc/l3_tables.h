@@ -23,7 +23,7 @@ typedef struct L3HuffInfo {
 typedef struct L3BandTables {
     uint8_t line2band[9][3][576];
     uint16_t dst[9][3][576]; /* where bitstream line i goes after the short-block reorder (identity for long bands) */
-    uint32_t lmap[9][3][576]; /* band | (dst + dst / 18) << 8: band and reordered position in rows padded to 19 */
+    uint32_t lmap[9][3][576]; /* band | dst << 8: band and reordered position of a line, one word (fused back end) */
     uint16_t start[9][3][40];
     uint8_t width[9][3][40];
     int8_t win[9][3][40];    /* window 0..2 of a short band, -1 for a long band */

@@ -120,7 +120,7 @@ extern "C" void l3_build_host_tables(L3HostTables *t)
                     // short bands are transmitted window by window; the spectrum interleaves the windows
                     B.dst[row][lay][line] = (uint16_t)(w < 0 ? line : (B.start[row][lay][b] - w * wd) + 3 * i + w);
                     const uint32_t dl = B.dst[row][lay][line];
-                    B.lmap[row][lay][line] = (uint32_t)b | ((dl + dl / 18) << 8);
+                    B.lmap[row][lay][line] = (uint32_t)b | (dl << 8);
                 }
         }
     }

@@ -28,6 +28,61 @@ __global__ void __launch_bounds__(256) k_ffma(float *out, int iters, float a, fl
     if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s; // never true: keeps the chains alive
 }
 
+// Register-operand form (what a real kernel issues: both multiplicands in registers) and the packed form of
+// sm_100 (fma.rn.f32x2 -> SASS FFMA2: two FMAs per lane and instruction, one issue slot).
+template <int ILP>
+__global__ void __launch_bounds__(256) k_ffma_rrr(float *out, int iters, float a, float b)
+{
+    float x[ILP], m[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) { x[k] = (float)(threadIdx.x + k) * 1e-3f; m[k] = a + (float)(k + (int)threadIdx.x) * 1e-7f; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int k = 0; k < ILP; k++) x[k] = fmaf(x[k], m[k], m[(k + 1) % ILP]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) s += x[k];
+    if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s + b;
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long aa, bb, cc, rr;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rr) : "l"(aa), "l"(bb), "l"(cc));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rr));
+    return r;
+}
+
+// BCAST = 1: one multiplicand is a scalar register broadcast to both halves (FFMA2 R, Rw.F32, Rx.F32x2, Racc)
+template <int ILP, int BCAST>
+__global__ void __launch_bounds__(256) k_ffma2(float *out, int iters, float a, float b)
+{
+    float2 x[ILP], m[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+        x[k] = make_float2((float)(threadIdx.x + k) * 1e-3f, (float)(threadIdx.x + k) * 2e-3f);
+        m[k] = make_float2(a + (float)(k + (int)threadIdx.x) * 1e-7f, a - (float)(k + (int)threadIdx.x) * 1e-7f);
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int k = 0; k < ILP; k++)
+                x[k] = BCAST ? ffma2(make_float2(m[k].x, m[k].x), x[k], m[(k + 1) % ILP]) : ffma2(m[k], x[k], m[(k + 1) % ILP]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) s += x[k].x + x[k].y;
+    if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s + b;
+}
+
 #define CK(c) do { cudaError_t e = (c); if (e != cudaSuccess) { fprintf(stderr, "%s: %s\n", #c, cudaGetErrorString(e)); return 1; } } while (0)
 
 int main(int argc, char **argv)
@@ -71,12 +126,31 @@ int main(int argc, char **argv)
         CK(cudaEventElapsedTime(&ms_tot, e0, e1));
     } while (ms_tot < sustain_s * 1e3);
     const double sustained = flop * n / (ms_tot * 1e-3) / 1e12;
+    // the other instruction forms, same grid, best of 5 (flop per launch differs: FFMA2 does two FMAs per lane)
+    auto best_of = [&](auto launch, double fl) -> double {
+        double bst = 0.0;
+        for (int r = 0; r < 6; r++) {
+            cudaEventRecord(e0);
+            launch();
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r) bst = fl / (ms * 1e-3) / 1e12 > bst ? fl / (ms * 1e-3) / 1e12 : bst;
+        }
+        return bst;
+    };
+    const double rrr = best_of([&] { k_ffma_rrr<ILP><<<grid, 256>>>(out, iters, 0.999f, 1e-3f); }, flop);
+    const double p2 = best_of([&] { k_ffma2<ILP, 0><<<grid, 256>>>(out, iters, 0.999f, 1e-3f); }, 2.0 * flop);
+    const double p2b = best_of([&] { k_ffma2<ILP, 1><<<grid, 256>>>(out, iters, 0.999f, 1e-3f); }, 2.0 * flop);
+    CK(cudaGetLastError());
     int clk_khz = 0;
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"ctas_per_sm\": %d, \"ilp\": %d, \"fp32_tflops_burst\": %.2f, "
-           "\"fp32_tflops_sustained\": %.2f, \"sustained_seconds\": %.2f, \"theoretical_tflops_at_max_clock\": %.2f, "
+           "\"fp32_tflops_sustained\": %.2f, \"sustained_seconds\": %.2f, \"ffma_reg_operands_tflops\": %.2f, "
+           "\"ffma2_packed_tflops\": %.2f, \"ffma2_packed_broadcast_tflops\": %.2f, \"theoretical_tflops_at_max_clock\": %.2f, "
            "\"max_clock_mhz\": %.0f}\n",
-           p.name, p.multiProcessorCount, per_sm, ILP, best, sustained, ms_tot * 1e-3,
+           p.name, p.multiProcessorCount, per_sm, ILP, best, sustained, ms_tot * 1e-3, rrr, p2, p2b,
            2.0 * p.multiProcessorCount * 128.0 * clk_khz * 1e3 / 1e12, clk_khz / 1e3);
     return 0;
 }
