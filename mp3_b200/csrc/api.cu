@@ -118,6 +118,9 @@ struct mp3b_ctx {
     // call N's kernels are still queued, so it must not overwrite what call N's side-info / payload
     // kernels read.
     DevBuf d_raw[2], d_streams[2], d_scratch[2];
+    DevBuf d_sparse[2], d_segs[2];         // time-parallel walk: per-segment records and bookkeeping
+    int walk_mode = 0;                     // 0 = choose by batch shape, 1 = thread per stream, 2 = CTA per stream (MP3B_WALK)
+    uint32_t walk_seg = 4096;              // bytes per segment of the time-parallel walk (MP3B_WALK_SEG)
     DevBuf d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_pcm2;
     int pcm_cur = 0;                       // PCM arena of the last decode (two alternate in sink mode)
     cudaEvent_t pcm_free[2] = {nullptr, nullptr}; // sink copies out of arena i have finished
@@ -392,7 +395,18 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         CK(d_scratch.ensure(sizeof(L3FrameRec) * l3_index_scratch_records(raw_total, (uint64_t)nstreams)));
         CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, ist));
         if (ahead) CK(cudaEventRecord(ctx->walk_t0, ist));
-        l3_launch_index_walk(ctx->raw_dev, d_streams.as<L3StreamRec>(), nstreams, d_scratch.as<L3FrameRec>(), ist);
+        // Long streams are walked time-parallel (a CTA per stream, segments of walk_seg bytes); many short ones by a
+        // thread each.  Both leave the same table.
+        const bool par = ctx->walk_mode == 2 ||
+                         (ctx->walk_mode == 0 && raw_total / (uint64_t)nstreams >= (96u << 10) && nstreams <= 16384);
+        if (par) {
+            DevBuf &d_sparse = ctx->d_sparse[ctx->idx_cur], &d_segs = ctx->d_segs[ctx->idx_cur];
+            CK(d_sparse.ensure(sizeof(L3FrameRec) * l3_walk_sparse_records(raw_total, (uint64_t)nstreams, ctx->walk_seg)));
+            CK(d_segs.ensure(16 * l3_walk_segments(raw_total, (uint64_t)nstreams, ctx->walk_seg)));
+            l3_launch_index_walk_par(ctx->raw_dev, d_streams.as<L3StreamRec>(), nstreams, d_scratch.as<L3FrameRec>(),
+                                     d_sparse.as<L3FrameRec>(), d_segs.p, ctx->walk_seg, ist);
+        } else
+            l3_launch_index_walk(ctx->raw_dev, d_streams.as<L3StreamRec>(), nstreams, d_scratch.as<L3FrameRec>(), ist);
         launches++;
         l3_launch_publish(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, ist);
         launches++;
@@ -779,6 +793,11 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
         if (v > 0) ctx->wave_units = (uint64_t)v;
     }
     if (const char *w = getenv("MP3B_DEBUG_POISON")) ctx->poison = atoi(w) != 0;
+    if (const char *w = getenv("MP3B_WALK")) ctx->walk_mode = !strcmp(w, "serial") ? 1 : (!strcmp(w, "par") ? 2 : 0);
+    if (const char *w = getenv("MP3B_WALK_SEG")) {
+        long v = atol(w);
+        if (v >= 48 && v <= (1 << 24)) ctx->walk_seg = (uint32_t)v / 24 * 24;
+    }
     if (const char *w = getenv("MP3B_FUSED_TILE")) {
         int v = atoi(w);
         if (v > 0 && v <= 4096) ctx->tile_override = (uint32_t)v;
@@ -813,7 +832,8 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     for (auto *s : ctx->open_streams) delete s;
     if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
-                      &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
+                      &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_sparse[0], &ctx->d_sparse[1], &ctx->d_segs[0],
+                      &ctx->d_segs[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
                       &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();

@@ -210,45 +210,55 @@ __device__ __forceinline__ void prefetch_units(SH &S, int tid, uint32_t u_first,
 // granules of a mono stream (which doubles the granules per batch, so that mono tiles keep all eight
 // warps busy).  `nun` = units in the batch; an odd mono batch repeats its last descriptor.
 template <class SH>
-__device__ __forceinline__ void load_meta(SH &S, int tid, uint32_t u_first, int nun,
+__device__ __forceinline__ void load_meta(SH &S, int tid, uint32_t u_first, int nun, int nch,
                                           const L3UnitDesc *__restrict__ units)
 {
-    if (tid < ((nun + 1) & ~1)) S.gm[tid >> 1].d[tid & 1] = units[u_first + (uint32_t)min(tid, nun - 1)];
     for (int i = tid; i < KF_B * 40; i += KF_THREADS) {
         (&S.nz[0][0])[i] = 0;
         (&S.mode[0][0])[i] = 0;
     }
-    if (tid == 0) { S.any_ist = 0; S.any_short = 0; }
-}
-
-template <class SH>
-__device__ __forceinline__ void finish_meta(SH &S, int tid, int nb, int nch)
-{
-    if (tid < nb) {
-        GranMeta &m = S.gm[tid];
-        m.row = (m.d[0].hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
-        for (int c = 0; c < 2; c++)
-            m.lay[c] = (m.d[c].flags & L3F_BT_MASK) == 2 ? ((m.d[c].flags & L3F_MIXED) ? 2 : 1) : 0;
-        const bool ok = (m.d[0].flags & L3F_VALID) != 0;
-        m.ms = (nch == 2 && ok && (m.d[0].hdr & L3H_MS)) ? 1 : 0;
-        m.ist = (nch == 2 && ok && (m.d[0].hdr & L3H_IS)) ? 1 : 0;
-        if (m.ist) S.any_ist = 1;
-        if (m.lay[0] | m.lay[1]) S.any_short = 1;
-        // Which 64-line spans (one warp's share of one S1 trip) can hold a value outside the small signed
-        // |is|^(4/3) table: only the big_values regions coded with a book whose escapes reach that far.
-        // Everything else -- other books (|is| <= 270), the count1 region (+-1), the zero tail -- cannot.
-        int slow = 0;
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const L3UnitDesc &dd = m.d[c];
-            const int lim[4] = {0, dd.r1, dd.r2, 2 * (int)dd.big_values};
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-                if (((KF_BIG_TABLES >> dd.tsel[r]) & 1u) && lim[r + 1] > lim[r])
-                    for (int k = lim[r] >> 6; k <= (lim[r + 1] - 1) >> 6; k++) slow |= 1 << (16 * c + k);
-        }
-        m.slow = slow;
+    // Everything else is the last warp's (it has no S3 work, so this is off the critical path): lane k takes
+    // unit slot k, the two slots of a pair combine by shuffle.
+    if ((tid >> 5) != KF_THREADS / 32 - 1) return;
+    const int k = tid & 31, npairs = (nun + 1) >> 1;
+    const bool mine = k < 2 * npairs;
+    L3UnitDesc d;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(units + u_first + (uint32_t)min(mine ? k : 0, nun - 1));
+        uint4 *dst = reinterpret_cast<uint4 *>(&d);
+        dst[0] = __ldg(src);
+        dst[1] = __ldg(src + 1);
     }
+    const int lay = (d.flags & L3F_BT_MASK) == 2 ? ((d.flags & L3F_MIXED) ? 2 : 1) : 0;
+    // Which 64-line spans (one warp's share of one S1 trip) can hold a value outside the small signed
+    // |is|^(4/3) table: only the big_values regions coded with a book whose escapes reach that far.
+    // Everything else -- other books (|is| <= 270), the count1 region (+-1), the zero tail -- cannot.
+    int slow = 0;
+    {
+        const int lim[4] = {0, d.r1, d.r2, 2 * (int)d.big_values};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            if (((KF_BIG_TABLES >> d.tsel[r]) & 1u) && lim[r + 1] > lim[r]) {
+                const int lo = lim[r] >> 6, hi = (lim[r + 1] - 1) >> 6;
+                slow |= (2 << hi) - (1 << lo); // bits lo .. hi
+            }
+    }
+    const int lay_o = __shfl_xor_sync(0xffffffffu, lay, 1), slow_o = __shfl_xor_sync(0xffffffffu, slow, 1);
+    const bool ok = (d.flags & L3F_VALID) != 0;
+    const int ms = (nch == 2 && ok && (d.hdr & L3H_MS)) ? 1 : 0, ist = (nch == 2 && ok && (d.hdr & L3H_IS)) ? 1 : 0;
+    const bool head = mine && !(k & 1); // slot 0 of a pair writes the pair's record
+    const uint32_t any_i = __ballot_sync(0xffffffffu, head && ist), any_s = __ballot_sync(0xffffffffu, mine && lay != 0);
+    if (mine) S.gm[k >> 1].d[k & 1] = d;
+    if (head) {
+        GranMeta &m = S.gm[k >> 1];
+        m.row = (d.hdr >> L3H_SR_SHIFT) & L3H_SR_MASK;
+        m.lay[0] = lay;
+        m.lay[1] = lay_o;
+        m.ms = ms;
+        m.ist = ist;
+        m.slow = slow | (slow_o << 16);
+    }
+    if (k == 0) { S.any_ist = any_i != 0; S.any_short = any_s != 0; }
 }
 
 // ---- S1a: per-band gains, and the right channel's non-zero bands for intensity granules ---------
@@ -494,11 +504,11 @@ __device__ __forceinline__ void stage_requant(SH &S, int tid, int nb, const L3Ba
 }
 
 // ---- S2: alias reduction + IMDCT of one (granule, channel) by one warp, lane = subband ----------
-// First halves go to the granule's rows of F.  Second halves (overlap-add with the NEXT granule) go to Hdst as
-// [slot t][32 subbands], row t rotated by 4 t floats: the granule's own, now dead, spectrum X -- S3 adds them
-// to the next granule's rows while it loads those, 16 bytes at a time, and the rotation keeps the eight rows a
-// quarter warp reads together in different banks -- or, for the last granule of a batch, the carry buffer Hc
-// (plain layout), whose previous content the warp of the batch's FIRST granule adds to its first halves here.
+// First halves go to the granule's rows of F.  Second halves (overlap-add with the NEXT granule) go to
+// [slot t][32 subbands] with the 16-byte groups of row t XORed by t & 7: the granule's own, now dead, spectrum X
+// -- S3 adds them to the next granule's rows while it loads those, 16 bytes at a time, and the swizzle keeps the
+// eight rows a quarter warp reads together in different banks -- or, for the last granule of a batch, the carry
+// buffer Hc (plain layout), whose previous content the warp of the batch's FIRST granule adds to its rows here.
 // Those two warps touch Hc in the same phase: the reader announces on a named barrier (role 1) that its loads
 // are done, the writer waits there (role 2) before storing; a batch of one granule is both (role 3: program order).
 // (barrier 0 is __syncthreads; 1 and 2 serve the two channel sequences; immediates, so that no more are reserved)
@@ -518,8 +528,6 @@ __device__ __forceinline__ void stage_imdct(float *__restrict__ X, int lane, uin
                                             int role, int bar_id)
 {
     const bool reads_carry = (role & 1) != 0, writes_carry = (role & 2) != 0;
-    float *const Hdst = writes_carry ? Hc : X;
-    const int rot = writes_carry ? 0 : 4;
     float h[18];
     float x[18];
     {
@@ -551,22 +559,26 @@ __device__ __forceinline__ void stage_imdct(float *__restrict__ X, int lane, uin
     if (mixed && lane < 2) bt = 0;
     const float sgn = (lane & 1) ? -1.f : 1.f; // frequency inversion: odd subband, odd slot
     if (bt != 2) {
-        const float *w = f_win[bt];
         float Z[18];
         l3_dct4_18(x, Z); // the 18 distinct IMDCT values (fast_imdct.h)
+        // window + frequency inversion; the window of each block type as immediates (a warp-uniform switch)
+        auto emit = [&](auto bt_tag) {
+            constexpr int BT = decltype(bt_tag)::value;
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
-            const float sa = Z[9 + i], sb = -Z[8 - i];
-            // out[i] = sa, out[17-i] = -sa, out[18+i] = sb, out[35-i] = sb; slots i and 17 - i have
-            // opposite parity, so exactly one of each pair takes the inversion sign
-            const float sa_s = sa * sgn, sb_s = sb * sgn;
-            float f0 = ((i & 1) ? sa_s : sa) * w[i], f1 = -((i & 1) ? sa : sa_s) * w[17 - i];
-            if (reads_carry) { f0 += Hc[i * 32 + lane]; f1 += Hc[(17 - i) * 32 + lane]; }
-            Fdst[i * FS + lane] = f0;
-            Fdst[(17 - i) * FS + lane] = f1;
-            h[i] = ((i & 1) ? sb_s : sb) * w[18 + i];
-            h[17 - i] = ((i & 1) ? sb : sb_s) * w[35 - i];
-        }
+            for (int i = 0; i < 9; i++) {
+                const float sa = Z[9 + i], sb = -Z[8 - i];
+                // out[i] = sa, out[17-i] = -sa, out[18+i] = sb, out[35-i] = sb; slots i and 17 - i have
+                // opposite parity, so exactly one of each pair takes the inversion sign
+                const float sa_s = sa * sgn, sb_s = sb * sgn;
+                Fdst[i * FS + lane] = ((i & 1) ? sa_s : sa) * WIN36[BT][i];
+                Fdst[(17 - i) * FS + lane] = ((i & 1) ? sa : sa_s) * -WIN36[BT][17 - i];
+                h[i] = ((i & 1) ? sb_s : sb) * WIN36[BT][18 + i];
+                h[17 - i] = ((i & 1) ? sb : sb_s) * WIN36[BT][35 - i];
+            }
+        };
+        if (bt == 0) emit(std::integral_constant<int, 0>{});
+        else if (bt == 1) emit(std::integral_constant<int, 1>{});
+        else emit(std::integral_constant<int, 3>{});
     } else {
         // 12-point IMDCT per window.  Only six of the twelve values are distinct (y[5-i] = -y[i],
         // y[11-i] = y[6+i]: the kernel is a 6-point DCT-IV), so six dot products per window, not twelve.
@@ -581,20 +593,15 @@ __device__ __forceinline__ void stage_imdct(float *__restrict__ X, int lane, uin
                     a = fmaf(x[3 * k + wdw], K12[i][k], a);
                     b = fmaf(x[3 * k + wdw], K12[6 + i][k], b);
                 }
-                y[wdw][i] = a * f_win[2][i];
-                y[wdw][5 - i] = -a * f_win[2][5 - i];
-                y[wdw][6 + i] = b * f_win[2][6 + i];
-                y[wdw][11 - i] = b * f_win[2][11 - i];
+                y[wdw][i] = a * WIN36[2][i];
+                y[wdw][5 - i] = -a * WIN36[2][5 - i];
+                y[wdw][6 + i] = b * WIN36[2][6 + i];
+                y[wdw][11 - i] = b * WIN36[2][11 - i];
             }
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             const float s_i = (i & 1) ? sgn : 1.f; // 6 and 12 are even: parity of i everywhere
-            float f0 = 0.f, f1 = y[0][i] * s_i, f2 = (y[0][6 + i] + y[1][i]) * s_i;
-            if (reads_carry) {
-                f0 += Hc[i * 32 + lane];
-                f1 += Hc[(6 + i) * 32 + lane];
-                f2 += Hc[(12 + i) * 32 + lane];
-            }
+            const float f0 = 0.f, f1 = y[0][i] * s_i, f2 = (y[0][6 + i] + y[1][i]) * s_i;
             Fdst[i * FS + lane] = f0;
             Fdst[(6 + i) * FS + lane] = f1;
             Fdst[(12 + i) * FS + lane] = f2;
@@ -603,10 +610,19 @@ __device__ __forceinline__ void stage_imdct(float *__restrict__ X, int lane, uin
             h[12 + i] = 0.f;
         }
     }
-    if (role == 1) named_arrive(bar_id); // (the carry has been added: those loads are complete)
-    if (role == 2) named_sync(bar_id);
+    if (reads_carry) { // the batch's first granule: + the previous batch's last second half (this lane's own column)
 #pragma unroll
-    for (int t = 0; t < 18; t++) Hdst[t * 32 + ((lane + rot * t) & 31)] = h[t];
+        for (int t = 0; t < 18; t++) Fdst[t * FS + lane] += Hc[t * 32 + lane];
+    }
+    if (role == 1) named_arrive(bar_id); // (the sums above are stored: those loads of Hc are complete)
+    if (role == 2) named_sync(bar_id);
+    if (writes_carry) {
+#pragma unroll
+        for (int t = 0; t < 18; t++) Hc[t * 32 + lane] = h[t];
+    } else {
+#pragma unroll
+        for (int t = 0; t < 18; t++) X[t * 32 + (lane ^ ((t & 7) << 2))] = h[t];
+    }
 }
 
 // ---- S4: synthesis window for one (granule, channel), lane = sample j ---------------------------
@@ -701,7 +717,7 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
             const int x = i < KF_POW_LUT / 2 ? i : i - KF_POW_LUT;
             S.pow43[i] = x < 0 ? -pow43[-x] : pow43[x];
         }
-        load_meta(S, tid, ubase, min(KFG, total) * nch, units);
+        load_meta(S, tid, ubase, min(KFG, total) * nch, nch, units);
         prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in, nzv_in);
     }
     __syncthreads();
@@ -723,22 +739,22 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
         const int np = mono ? (nb + 1) >> 1 : nb;      // slot pairs of this batch
         const uint32_t u_first = ubase + (uint32_t)b0 * nch;
         // ---- S1
-        finish_meta(S, tid, np, nch);
         cp_async_wait_all();                        // scalefactors (LDGSTS)
         mbar_wait(&S.bar, (uint32_t)(b0 / KFG) & 1u); // spectra (TMA); one phase per batch
         if (tid == KF_THREADS - 32) bulk_wait_read_all(); // the previous batch's PCM has left the staging buffer
         __syncthreads();
-        stage_gains(S, tid, np, 2, bands);
-        __syncthreads();
-        if (S.any_ist) { // stereo only
-            if ((tid & 32) == 0 && (tid >> 6) < np && S.gm[tid >> 6].ist) // first warp of each granule's 64 threads
-                stage_intensity(S, tid >> 6, (tid >> 6) * 2 + 1, lane, bands);
-            __syncthreads();
-        }
         {
+            // the Huffman output into registers first: with s16 output it sits inside X, which stage_requant
+            // overwrites -- the barrier behind the gains then covers that hazard too
             uint32_t v[10];
             requant_load(S, tid, np, v);
-            if (FMT == MP3B_PCM_S16) __syncthreads(); // the Huffman output sits inside X, which is written next
+            stage_gains(S, tid, np, 2, bands);
+            __syncthreads();
+            if (S.any_ist) { // stereo only
+                if ((tid & 32) == 0 && (tid >> 6) < np && S.gm[tid >> 6].ist) // first warp of each granule's 64 threads
+                    stage_intensity(S, tid >> 6, (tid >> 6) * 2 + 1, lane, bands);
+                __syncthreads();
+            }
             stage_requant(S, tid, np, bands, pow43, bq, v);
         }
         __syncthreads();
@@ -756,7 +772,7 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
         __syncthreads();
         // next batch: descriptors (gm is dead until the next S1)
         if (b0 + KFG < total)
-            load_meta(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, units);
+            load_meta(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, nch, units);
         // ---- S3: overlap-add + 32-point transform of every slot, in place; one thread per (channel, slot) row,
         // the whole transform in registers (fast_dct.h: 304 operations instead of 1024 FMAs).  The row's other
         // summand, the previous granule's second half, comes from that granule's X (rotated rows, see S2); the
@@ -779,7 +795,7 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
                         (mono ? &S.X[jp >> 1][jp & 1][0] : &S.X[jp][c][0]) + t * 32);
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
-                        const float4 q = hrow[(k + t) & 7];
+                        const float4 q = hrow[k ^ (t & 7)];
                         x[4 * k] += q.x; x[4 * k + 1] += q.y; x[4 * k + 2] += q.z; x[4 * k + 3] += q.w;
                     }
                 }

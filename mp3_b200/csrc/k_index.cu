@@ -12,6 +12,7 @@
 // frame, and parallel across streams only.  Everything else is embarrassingly parallel.
 // No reference code exists for this stage (/root/reference/README.md:1-84).
 #include "kernels.h"
+#include "walk_par.h"
 
 namespace {
 
@@ -97,76 +98,8 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     streams[s].tag_delay_pad = tag_dp;
 }
 
-// ---- the same walk, time-parallel inside a stream ---------------------------------------------------------
-// One thread per stream leaves a long stream (an hour of audio: 138 k frames, 90 ms of dependent loads) to a single
-// thread.  The walk is a deterministic function of the position once the stream's first header is known (what is
-// accepted at byte p depends on p and `first` only), so it can be cut: the bytes behind the first frame are split
-// into segments of `seg` bytes; every thread of the stream's CTA guesses where the chain enters its segments (the
-// first header of this stream that is followed by another one), walks to the segment's end and leaves its
-// records in a sparse table; then the guesses are checked in order -- segment t is right iff it starts where
-// segment t - 1 left (`exit`) -- and a segment whose guess was wrong (a header look-alike in front of the real
-// frame, lost sync, frames longer than a segment) is walked again from the true position by one thread.  The dense
-// frame table that results is the serial walk's, record for record (tests compare both, on damaged streams too).
-struct L3WalkSeg {
-    uint32_t start;    // where the segment's walk began (guess), 0xffffffff: no frame start found in it
-    uint32_t exit;     // position after its last frame (>= the segment's end), or where the walk stopped
-    uint32_t n;        // frames recorded
-    uint32_t payload;  // main-data bytes of those frames
-};
+// ---- the same walk, time-parallel inside a stream (walk_par.h has the algorithm; this is its CTA mapping) ----
 constexpr int WP_THREADS = 128;
-constexpr uint32_t WP_NONE = 0xffffffffu;
-
-// Walk from p while frames START below `limit`; the loop of k_index_walk with `first` known.  Returns the exit
-// position; *stopped = the walk ended for good (end of the bytes, or an incomplete frame of a stream still growing).
-__device__ __forceinline__ uint32_t walk_span(const uint8_t *__restrict__ buf, uint32_t len, uint32_t p, uint32_t limit,
-                                              uint32_t first, bool streaming, uint32_t stream, L3FrameRec *__restrict__ out,
-                                              uint32_t *n_out, uint32_t *payload_out, uint32_t *last_end, bool *stopped)
-{
-    const uint32_t GEOM = 0xFFFFFCC0u;
-    uint32_t prev_w = 0, base_len = 0, overhead = 0, pad_unit = 1, n = 0, payload = 0;
-    bool l2 = false;
-    *stopped = true;
-    while (p + 4 <= len) {
-        if (p >= limit) { *stopped = false; break; }
-        L3Hdr h;
-        uint32_t w = l3_load_be32(buf + p), flen;
-        if (n && ((w ^ prev_w) & GEOM) == 0) {
-            flen = base_len + ((w >> 9) & 1u) * pad_unit;
-            if (p + flen > len) {
-                if (streaming) break;
-                p++;
-                continue;
-            }
-        } else {
-            const int fa = l3_frame_at(buf, len, p, first, &h, &w);
-            if (fa != 1) { // (`first` is set: no confirmation case here)
-                if (fa >= 2 && streaming) break;
-                p++;
-                continue;
-            }
-            flen = (uint32_t)h.frame_len;
-            prev_w = w;
-            pad_unit = h.layer == 1 ? 4u : 1u;
-            base_len = flen - ((w >> 9) & 1u) * pad_unit;
-            overhead = 4u + (h.crc ? 2u : 0u) + (uint32_t)h.side_len;
-            l2 = h.layer != 3;
-        }
-        if (p + 4u * flen < len) prefetch_l2(buf + p + 4 * flen);
-        L3FrameRec f;
-        f.rel_off = p;
-        f.payload_off = payload;
-        f.hdr = w;
-        f.stream = stream;
-        out[n] = f;
-        n++;
-        payload += l2 ? 0u : flen - overhead;
-        p += flen;
-        *last_end = p;
-    }
-    *n_out = n;
-    *payload_out = payload;
-    return p;
-}
 
 __global__ void __launch_bounds__(WP_THREADS)
 k_index_walk_par(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams,
@@ -178,42 +111,23 @@ k_index_walk_par(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ stre
     const L3StreamRec r = streams[s];
     const uint8_t *buf = raw + r.raw_off;
     const uint32_t len = r.raw_len;
-    const bool streaming = (r.flags & L3S_STREAMING) != 0;
+    const int streaming = (r.flags & L3S_STREAMING) != 0;
     L3FrameRec *out = dense + scratch_base(r, (uint32_t)s);
     const uint64_t seg0 = r.raw_off / seg + (uint64_t)s; // this stream's first segment record / sparse block
-    __shared__ uint32_t sh_first, sh_pf, sh_have, sh_end0, sh_tag[4], sh_bad;
+    __shared__ L3WalkFirst sh_f;
+    __shared__ uint32_t sh_bad;
     __shared__ uint32_t sh_scan[2][WP_THREADS];
 
-    // ---- phase 0: the stream's first frame (one thread: ID3v2 skip, sync search with confirmation, tag frame)
+    // ---- phase 0: the stream's first frame (one thread)
     if (tid == 0) {
-        uint32_t p = l3_id3v2_len(buf, len), first = r.first_hdr, have = 0;
-        uint32_t tk = L3T_NONE, tf = 0, tb = 0, td = 0;
-        sh_end0 = p;
-        while (p + 4 <= len) {
-            L3Hdr h;
-            uint32_t w;
-            const int fa = l3_frame_at(buf, len, p, first, &h, &w);
-            if (fa != 1 && !(fa == 3 && !streaming)) {
-                if (fa >= 2 && streaming) break;
-                p++;
-                continue;
-            }
-            first = first ? first : w;
-            if (r.skip_frames == 0) tk = l3_parse_tag(buf + p, (uint32_t)h.frame_len, &h, &tf, &tb, &td);
-            have = 1;
-            break;
-        }
-        sh_first = first;
-        sh_pf = p;
-        sh_have = have;
-        sh_tag[0] = tk; sh_tag[1] = tf; sh_tag[2] = tb; sh_tag[3] = td;
+        l3wp_first(buf, len, r.first_hdr, r.skip_frames, streaming, &sh_f);
         sh_bad = 0;
     }
     __syncthreads();
-    const uint32_t first = sh_first, pf = sh_pf;
-    if (!sh_have) { // no frame at all (or not yet): same outputs as the serial walk
+    const uint32_t first = sh_f.first, pf = sh_f.pf;
+    if (!sh_f.have) { // no frame at all (or not yet): same outputs as the serial walk
         if (tid == 0) {
-            streams[s].end_off = sh_end0;
+            streams[s].end_off = sh_f.end0;
             streams[s].first_off = 0;
             streams[s].first_hdr = first;
             streams[s].nframes = 0;
@@ -229,72 +143,21 @@ k_index_walk_par(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ stre
 
     // ---- phase 1: speculative walk of every segment
     for (uint32_t t = tid; t < nseg; t += WP_THREADS) {
-        const uint32_t lo = pf + t * seg, hi = (t + 1 < nseg) ? lo + seg : 0xffffffffu;
-        uint32_t g = lo;
-        if (t) { // guess: the first header of this stream in the segment that is followed by another one
-            g = WP_NONE;
-            for (uint32_t p = lo; p < hi && p + 4 <= len; p++) {
-                L3Hdr h, h2;
-                uint32_t w;
-                if (l3_frame_at(buf, len, p, first, &h, &w) != 1) continue;
-                const uint32_t q = p + (uint32_t)h.frame_len;
-                if (q + 4 <= len) {
-                    const uint32_t w2 = l3_load_be32(buf + q);
-                    if (!l3_parse_hdr(w2, &h2) || !l3_same_stream(w2, first)) continue;
-                }
-                g = p;
-                break;
-            }
-        }
         L3WalkSeg e;
-        e.start = g;
-        e.exit = g;
-        e.n = e.payload = 0;
-        if (g != WP_NONE) {
-            uint32_t last_end = 0;
-            bool stopped;
-            e.exit = walk_span(buf, len, g, hi, first, streaming, (uint32_t)s, sp + (size_t)t * seg_cap, &e.n, &e.payload,
-                               &last_end, &stopped);
-            if (stopped) e.exit = WP_NONE - 1; // nothing can follow: any later segment is void
-        }
+        l3wp_segment(buf, len, pf, seg, nseg, t, first, streaming, (uint32_t)s, sp + (size_t)t * seg_cap, &e);
         sg[t] = e;
     }
     __syncthreads();
-    // ---- phase 2: do the guesses chain up?  (segment t is right iff it starts where segment t - 1 left)
+    // ---- phase 2: do the guesses chain up?  If not, one thread follows the chain and repairs.
     {
         uint32_t bad = 0;
-        for (uint32_t t = tid; t < nseg; t += WP_THREADS) {
-            const uint32_t want = t ? sg[t - 1].exit : pf;
-            if (sg[t].start != want) bad = 1;
-        }
+        for (uint32_t t = tid; t < nseg; t += WP_THREADS)
+            if (!l3wp_chained(sg, t, pf)) bad = 1;
         if (bad) sh_bad = 1;
     }
     __syncthreads();
-    uint32_t total_n = 0, total_pay = 0;
     if (sh_bad) {
-        // one thread repairs in order: a segment that the chain does not enter where it was guessed is walked
-        // again from the true position (its sparse block is rewritten)
-        if (tid == 0) {
-            uint32_t cur = pf;
-            bool dead = false; // the chain has ended (end of bytes / incomplete frame)
-            for (uint32_t t = 0; t < nseg; t++) {
-                const uint32_t lo = pf + t * seg, hi = (t + 1 < nseg) ? lo + seg : 0xffffffffu;
-                L3WalkSeg e = sg[t];
-                if (dead || cur >= hi) { // the chain does not enter this segment
-                    e.start = cur; e.exit = cur; e.n = e.payload = 0;
-                } else if (e.start != cur) {
-                    uint32_t last_end = 0;
-                    bool stopped;
-                    e.start = cur;
-                    e.exit = walk_span(buf, len, cur, hi, first, streaming, (uint32_t)s, sp + (size_t)t * seg_cap, &e.n,
-                                       &e.payload, &last_end, &stopped);
-                    if (stopped) e.exit = WP_NONE - 1;
-                }
-                if (e.exit == WP_NONE - 1) dead = true;
-                else cur = e.exit;
-                sg[t] = e;
-            }
-        }
+        if (tid == 0) l3wp_repair(buf, len, pf, seg, nseg, first, streaming, (uint32_t)s, sp, seg_cap, sg);
         __syncthreads();
     }
     // ---- phase 3: dense positions (exclusive scan of the segments' frame and main-data counts), compaction
@@ -305,10 +168,12 @@ k_index_walk_par(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ stre
         sh_scan[0][tid] = n;
         sh_scan[1][tid] = pay;
         __syncthreads();
-        uint32_t bn = 0, bp = 0; // exclusive prefix inside the chunk (a serial loop over <= 128 shared words)
-        for (int k = 0; k < tid; k++) { bn += sh_scan[0][k]; bp += sh_scan[1][k]; }
-        uint32_t cn = 0, cp = 0;
-        for (int k = 0; k < WP_THREADS; k++) { cn += sh_scan[0][k]; cp += sh_scan[1][k]; }
+        uint32_t bn = 0, bp = 0, cn = 0, cp = 0; // exclusive prefix inside the chunk, chunk totals
+        for (int k = 0; k < WP_THREADS; k++) {
+            if (k == tid) { bn = cn; bp = cp; }
+            cn += sh_scan[0][k];
+            cp += sh_scan[1][k];
+        }
         if (t < nseg) {
             const L3FrameRec *src = sp + (size_t)t * seg_cap;
             L3FrameRec *dst = out + run_n + bn;
@@ -322,16 +187,10 @@ k_index_walk_par(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ stre
         run_pay += cp;
         __syncthreads();
     }
-    total_n = run_n;
-    total_pay = run_pay;
     if (tid == 0) {
-        // end of the last frame = header offset + length of the last record
-        uint32_t end_off = sh_end0;
-        if (total_n) {
-            uint32_t last_t = nseg;
-            for (uint32_t t = nseg; t-- > 0;)
-                if (sg[t].n) { last_t = t; break; }
-            const L3FrameRec lf = sp[(size_t)last_t * seg_cap + sg[last_t].n - 1];
+        uint32_t end_off = sh_f.end0;
+        if (run_n) { // end of the last frame = header offset + length of the last record
+            const L3FrameRec lf = out[run_n - 1];
             L3Hdr h;
             l3_parse_hdr(lf.hdr, &h);
             end_off = lf.rel_off + (uint32_t)h.frame_len;
@@ -339,12 +198,12 @@ k_index_walk_par(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ stre
         streams[s].end_off = end_off;
         streams[s].first_off = pf;
         streams[s].first_hdr = first;
-        streams[s].nframes = total_n;
-        streams[s].payload_len = total_pay;
-        streams[s].tag_kind = sh_tag[0];
-        streams[s].tag_frames = sh_tag[1];
-        streams[s].tag_bytes = sh_tag[2];
-        streams[s].tag_delay_pad = sh_tag[3];
+        streams[s].nframes = run_n;
+        streams[s].payload_len = run_pay;
+        streams[s].tag_kind = sh_f.tag_kind;
+        streams[s].tag_frames = sh_f.tag_frames;
+        streams[s].tag_bytes = sh_f.tag_bytes;
+        streams[s].tag_delay_pad = sh_f.tag_delay_pad;
     }
 }
 
@@ -680,7 +539,7 @@ void l3_launch_index_walk_par(const uint8_t *raw, L3StreamRec *streams, int nstr
 {
     if (nstreams <= 0) return;
     k_index_walk_par<<<nstreams, WP_THREADS, 0, st>>>(raw, streams, nstreams, dense, sparse, static_cast<L3WalkSeg *>(segs),
-                                                      seg_bytes, l3_walk_seg_cap(seg_bytes));
+                                                      seg_bytes, l3wp_seg_cap(seg_bytes));
 }
 void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
                           const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,

@@ -47,14 +47,13 @@ void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams
                           cudaStream_t st);
 /* The time-parallel walk (a CTA per stream, segments of seg_bytes): same dense table as l3_launch_index_walk.
  * sparse: l3_walk_sparse_records() records; segs: l3_walk_segments() entries of 16 bytes. */
-static inline uint32_t l3_walk_seg_cap(uint32_t seg_bytes) { return seg_bytes / 24 + 2; } /* frames that can start in a segment */
 static inline uint64_t l3_walk_segments(uint64_t raw_total, uint64_t nstreams, uint32_t seg_bytes)
 {
     return raw_total / seg_bytes + nstreams + 2;
 }
 static inline uint64_t l3_walk_sparse_records(uint64_t raw_total, uint64_t nstreams, uint32_t seg_bytes)
 {
-    return l3_walk_segments(raw_total, nstreams, seg_bytes) * l3_walk_seg_cap(seg_bytes);
+    return l3_walk_segments(raw_total, nstreams, seg_bytes) * (uint64_t)(seg_bytes / 24 + 2); /* l3wp_seg_cap() records per segment */
 }
 void l3_launch_index_walk_par(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *dense, L3FrameRec *sparse,
                               void *segs, uint32_t seg_bytes, cudaStream_t st);
