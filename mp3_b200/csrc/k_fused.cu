@@ -171,16 +171,27 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // units into shared memory; the caller waits (cp_async_wait_all + barrier) before reading them.
 // Only the vectors that hold data are fetched (nzv_in[u] of the 72 per unit); the all-zero tail of
 // each spectrum is never written by the Huffman kernel nor read here: it is zeroed in place.
+// The vector counts the fetch needs: nzv of unit `lane` (for the last warp's copies) and of unit `warp` (for the tail
+// this warp zeroes), packed as lane's | warp's << 8.  Loaded ahead of prefetch_units so that the load's latency does
+// not sit between a barrier and the copies.
+__device__ __forceinline__ uint32_t prefetch_counts(int tid, uint32_t u_first, int n, const uint8_t *__restrict__ nzv_in)
+{
+    const int unit = tid >> 5, k = tid & 31;
+    const uint32_t a = (unit == KF_THREADS / 32 - 1 && k < n) ? nzv_in[u_first + k] : 0u;
+    const uint32_t b = unit < n ? nzv_in[u_first + unit] : 0u;
+    return a | (b << 8);
+}
+
 template <class SH>
 __device__ __forceinline__ void prefetch_units(SH &S, int tid, uint32_t u_first, int n,
                                                const int16_t *__restrict__ is_in, const uint8_t *__restrict__ sf_in,
-                                               const uint8_t *__restrict__ nzv_in)
+                                               uint32_t counts)
 {
     // spectra: one TMA bulk copy per unit, issued by the lanes of the last warp (which has no S3 work);
     // every warp zeroes the tail of "its" unit
     if ((tid >> 5) == KF_THREADS / 32 - 1) {
         const int k = tid & 31;
-        const uint32_t b = k < n ? 16u * nzv_in[u_first + k] : 0u;
+        const uint32_t b = 16u * (counts & 0xffu);
         uint32_t tot = b;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -194,7 +205,7 @@ __device__ __forceinline__ void prefetch_units(SH &S, int tid, uint32_t u_first,
     const int unit = tid >> 5, lane = tid & 31;
     if (unit < n || (unit == n && (n & 1))) { // an odd mono batch leaves one slot of the last pair empty: all zero
         char *si = reinterpret_cast<char *>(&S.is_buf()[unit][0]);
-        const int nv = unit < n ? nzv_in[u_first + unit] : 0;
+        const int nv = (int)(counts >> 8);
 #pragma unroll
         for (int v = lane; v < 72; v += 32)
             if (v >= nv) *reinterpret_cast<uint4 *>(si + v * 16) = make_uint4(0, 0, 0, 0);
@@ -610,11 +621,12 @@ __device__ __forceinline__ void stage_imdct(float *__restrict__ X, int lane, uin
             h[12 + i] = 0.f;
         }
     }
-    if (reads_carry) { // the batch's first granule: + the previous batch's last second half (this lane's own column)
+    if (reads_carry) { // the batch's first granule: + the previous batch's last second half (this lane's own column);
+                       // a pass of its own: specialising the loops above for it costs more (code size) than it saves
 #pragma unroll
         for (int t = 0; t < 18; t++) Fdst[t * FS + lane] += Hc[t * 32 + lane];
     }
-    if (role == 1) named_arrive(bar_id); // (the sums above are stored: those loads of Hc are complete)
+    if (role == 1) named_arrive(bar_id); // (the sums are stored: the loads of Hc are complete)
     if (role == 2) named_sync(bar_id);
     if (writes_carry) {
 #pragma unroll
@@ -718,7 +730,8 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
             S.pow43[i] = x < 0 ? -pow43[-x] : pow43[x];
         }
         load_meta(S, tid, ubase, min(KFG, total) * nch, nch, units);
-        prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in, nzv_in);
+        prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in,
+                       prefetch_counts(tid, ubase, min(KFG, total) * nch, nzv_in));
     }
     __syncthreads();
 
@@ -770,9 +783,12 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
             }
         }
         __syncthreads();
-        // next batch: descriptors (gm is dead until the next S1)
-        if (b0 + KFG < total)
+        // next batch: descriptors (gm is dead until the next S1), and the vector counts of its spectra
+        uint32_t counts = 0;
+        if (b0 + KFG < total) {
             load_meta(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, nch, units);
+            counts = prefetch_counts(tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, nzv_in);
+        }
         // ---- S3: overlap-add + 32-point transform of every slot, in place; one thread per (channel, slot) row,
         // the whole transform in registers (fast_dct.h: 304 operations instead of 1024 FMAs).  The row's other
         // summand, the previous granule's second half, comes from that granule's X (rotated rows, see S2); the
@@ -813,7 +829,7 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
         // inside X, whose second halves S3 has just consumed)
         if (b0 + KFG < total)
             prefetch_units(S, tid, u_first + (uint32_t)KFG * nch, min(KFG, total - b0 - KFG) * nch, is_in, sf_in,
-                           nzv_in);
+                           counts);
         // ---- S4: window -> PCM staging (X is free now)
         {
             const int c = mono ? 0 : (warp & 1), j = mono ? warp : (warp >> 1);

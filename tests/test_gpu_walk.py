@@ -111,7 +111,7 @@ def test_parallel_walk_incremental(mp3b, streams, monkeypatch):
             h.close()
 
 
-def test_one_hour_stream_is_walked_in_parallel(mp3b, synth_mod, monkeypatch):
+def test_long_stream_is_walked_in_parallel(mp3b, synth_mod, monkeypatch):
     """A long stream takes the parallel walk by default (batch shape); same table and PCM as the serial walk, and the
     index stage is far shorter (the serial chain is one dependent load per frame)."""
     s = synth_mod.make_stream(nframes=20000, seed=5, mode=1, bitrate_kbps=128, blocks=1)   # 8.7 minutes
@@ -119,7 +119,7 @@ def test_one_hour_stream_is_walked_in_parallel(mp3b, synth_mod, monkeypatch):
     for mode in ("serial", "auto"):
         monkeypatch.setenv("MP3B_WALK", mode)
         with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_S16, keep_stages=True) as dec:
-            for _ in range(2):
+            for _ in range(4):
                 dec.decode_batch([s])
             res[mode] = (dec.stage(mp3b.STAGE_FRAMES).copy(), dec.fetch_pcm().copy(), dec.stats().ms_index)
     assert res["serial"][0].shape[0] == 20000
