@@ -121,19 +121,7 @@ struct mp3b_ctx {
     DevBuf d_sparse[2], d_segs[2];         // time-parallel walk: per-segment records and bookkeeping
     int walk_mode = 0;                     // 0 = choose by batch shape, 1 = thread per stream, 2 = CTA per stream (MP3B_WALK)
     uint32_t walk_seg = 0;                 // bytes per segment of the time-parallel walk (MP3B_WALK_SEG); 0 = by stream length
-    // the tables the indexing kernels write, two sets as well: with the run-ahead the side-info parse and the
-    // main-data compaction of call N+1 also execute under call N's Huffman / back-end kernels, which read set N
-    DevBuf d_frames_[2], d_units_[2], d_gran_[2], d_arena_[2], d_tiles_[2], d_counter_[2];
-    DevBuf &d_frames() { return d_frames_[idx_cur]; }
-    DevBuf &d_units() { return d_units_[idx_cur]; }
-    DevBuf &d_gran() { return d_gran_[idx_cur]; }
-    DevBuf &d_arena() { return d_arena_[idx_cur]; }
-    DevBuf &d_tiles() { return d_tiles_[idx_cur]; }
-    DevBuf &d_counter() { return d_counter_[idx_cur]; }
-    DevBuf d_pcm, d_pcm2;
-    cudaEvent_t index_done = nullptr;  // run-ahead: the indexing chain of this call has finished (index stream)
-    cudaEvent_t st_entered = nullptr;  // the context's stream has started this call's decode kernels: every kernel of
-                                       // the call before has finished, so the table set it used is free again
+    DevBuf d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_pcm2;
     int pcm_cur = 0;                       // PCM arena of the last decode (two alternate in sink mode)
     cudaEvent_t pcm_free[2] = {nullptr, nullptr}; // sink copies out of arena i have finished
     DevBuf &pcm() { return pcm_cur ? d_pcm2 : d_pcm; }
@@ -374,9 +362,6 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     // the pinned staging tables (stream records, tiles, frames) are rewritten below: the previous call's
     // asynchronous uploads out of them must have executed (they are early in that call, so this is short)
     CK(cudaEventSynchronize(ctx->staging_done));
-    // ... and the table set this call is about to write (two alternate) was read by the kernels of the call before the
-    // previous one: the context's stream must have got past them, i.e. have entered the previous call's kernels
-    CK(cudaEventSynchronize(ctx->st_entered));
     CK(cudaEventRecord(ctx->ev[EV_START], st));
     // ---- raw bytes to the device
     if (where == MP3B_HOST) {
@@ -432,6 +417,11 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         launches++;
         l3_launch_publish(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, ist);
         launches++;
+        if (ahead) {
+            CK(cudaEventRecord(ctx->walk_t1, ist));
+            CK(cudaEventRecord(ctx->walk_done, ist));
+            CK(cudaStreamWaitEvent(st, ctx->walk_done, 0));
+        }
         CK(cudaStreamSynchronize(ist)); // the one host round trip: sizes of everything downstream
     }
 
@@ -539,12 +529,12 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     }
 
     // ---- device buffers
-    CK(ctx->d_frames().ensure(sizeof(L3FrameRec) * std::max<uint64_t>(frames, 1)));
-    CK(ctx->d_units().ensure(sizeof(L3UnitDesc) * std::max<uint64_t>(units, 1)));
-    CK(ctx->d_gran().ensure(sizeof(uint32_t) * std::max<uint64_t>(grans, 1)));
-    CK(ctx->d_arena().ensure(ctx->arena_bytes));
-    CK(ctx->d_tiles().ensure(sizeof(uint4) * std::max<uint64_t>(ntiles, 1)));
-    CK(ctx->d_counter().ensure(64));
+    CK(ctx->d_frames.ensure(sizeof(L3FrameRec) * std::max<uint64_t>(frames, 1)));
+    CK(ctx->d_units.ensure(sizeof(L3UnitDesc) * std::max<uint64_t>(units, 1)));
+    CK(ctx->d_gran.ensure(sizeof(uint32_t) * std::max<uint64_t>(grans, 1)));
+    CK(ctx->d_arena.ensure(ctx->arena_bytes));
+    CK(ctx->d_tiles.ensure(sizeof(uint4) * std::max<uint64_t>(ntiles, 1)));
+    CK(ctx->d_counter.ensure(64));
     CK(ctx->h_counter.ensure(64));
 
     const bool keep = ctx->opts.keep_stages != 0;
@@ -595,28 +585,24 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         CK(ctx->d_sb.ensure(max_wave_units * 576 * sizeof(float)));
     }
 
-    // With the run-ahead the rest of the indexing chain (table uploads, side info, main-data compaction) stays on the
-    // index stream: it executes under the previous call's kernels, and the context's stream joins at index_done.
-    cudaStream_t xst = ahead ? ist : st;
     if (ctx->poison) {
-        for (DevBuf *b : {&ctx->d_frames(), &ctx->d_units(), &ctx->d_gran(), &ctx->d_arena(), &ctx->d_tiles()})
-            if (b->p && b->cap) CK(cudaMemsetAsync(b->p, 0xFF, b->cap, xst));
-        for (DevBuf *b : {&ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr, &ctx->d_imd, &ctx->d_sb, &ctx->d_sb2, &ctx->pcm()})
+        for (DevBuf *b : {&ctx->d_frames, &ctx->d_units, &ctx->d_gran, &ctx->d_arena, &ctx->d_tiles, &ctx->d_is, &ctx->d_sf,
+                          &ctx->d_nzv, &ctx->d_xr, &ctx->d_imd, &ctx->d_sb, &ctx->d_sb2, &ctx->pcm()})
             if (b->p && b->cap) CK(cudaMemsetAsync(b->p, 0xFF, b->cap, st));
     }
     if (ahead && where == MP3B_HOST && !nstreams) CK(cudaStreamSynchronize(ist));
-    if (nstreams) CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, xst));
+    if (nstreams) CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
     if (ntiles)
-        CK(cudaMemcpyAsync(ctx->d_tiles().p, ctx->h_tiles.p, (fused ? sizeof(uint4) : sizeof(uint2)) * ntiles,
-                           cudaMemcpyHostToDevice, xst));
-    CK(cudaMemsetAsync(ctx->d_counter().p, 0, 64, xst));
+        CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->h_tiles.p, (fused ? sizeof(uint4) : sizeof(uint2)) * ntiles,
+                           cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, st));
     bool staging_recorded = false;
-    if (!host_index) { CK(cudaEventRecord(ctx->staging_done, xst)); staging_recorded = true; }
-    CK(cudaMemsetAsync(ctx->d_arena().as<uint8_t>() + (ctx->arena_bytes - 48), 0, 48, xst));
+    if (!host_index) { CK(cudaEventRecord(ctx->staging_done, st)); staging_recorded = true; }
+    CK(cudaMemsetAsync(ctx->d_arena.as<uint8_t>() + (ctx->arena_bytes - 48), 0, 48, st));
 
     // ---- frame table
     L3StreamRec *ds = d_streams.as<L3StreamRec>();
-    L3FrameRec *df = ctx->d_frames().as<L3FrameRec>();
+    L3FrameRec *df = ctx->d_frames.as<L3FrameRec>();
     if (host_index) {
         CK(ctx->h_frames.ensure(sizeof(L3FrameRec) * std::max<uint64_t>(frames, 1)));
         L3FrameRec *hf = ctx->h_frames.as<L3FrameRec>();
@@ -624,23 +610,17 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             if (!host_frames[i].empty())
                 memcpy(hf + hs[i].frame_base, host_frames[i].data(), host_frames[i].size() * sizeof(L3FrameRec));
         });
-        if (frames) CK(cudaMemcpyAsync(df, hf, sizeof(L3FrameRec) * frames, cudaMemcpyHostToDevice, xst));
+        if (frames) CK(cudaMemcpyAsync(df, hf, sizeof(L3FrameRec) * frames, cudaMemcpyHostToDevice, st));
     }
-    if (!staging_recorded) CK(cudaEventRecord(ctx->staging_done, xst));
-    L3UnitDesc *du = ctx->d_units().as<L3UnitDesc>();
-    uint32_t *dg = ctx->d_gran().as<uint32_t>();
+    if (!staging_recorded) CK(cudaEventRecord(ctx->staging_done, st));
+    L3UnitDesc *du = ctx->d_units.as<L3UnitDesc>();
+    uint32_t *dg = ctx->d_gran.as<uint32_t>();
     if (frames) {
         l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : d_scratch.as<L3FrameRec>(),
-                             (uint32_t)frames, ctx->T, du, dg, ctx->d_counter().as<uint32_t>(), ctx->opts.verify_crc, xst);
-        if (any_layer[3]) l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena().as<uint8_t>(), xst);
+                             (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), ctx->opts.verify_crc, st);
+        if (any_layer[3]) l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
         launches += any_layer[3] ? 2 : 1;
     }
-    if (ahead) {
-        CK(cudaEventRecord(ctx->walk_t1, ist)); // (the whole chain is timed: walk, side info, compaction)
-        CK(cudaEventRecord(ctx->index_done, ist));
-        CK(cudaStreamWaitEvent(st, ctx->index_done, 0));
-    }
-    CK(cudaEventRecord(ctx->st_entered, st));
     CK(cudaEventRecord(ctx->ev[EV_INDEX], st));
 
     // ---- decode waves
@@ -661,7 +641,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
         uint8_t *nzv = ctx->d_nzv.as<uint8_t>() - (size_t)u_lo;
         if (any_layer[3] || !fused || keep) // (the staged pipeline and stage dumps want every unit's arrays written)
-            l3_launch_huffman_range(ctx->d_arena().as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu,
+            l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu,
                                 (uint32_t)((ctx->arena_bytes + units - 1) / std::max<uint64_t>(units, 1)), ctx->T, is, sf, nzv,
                                 (!fused || keep) ? 1 : 0, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
@@ -680,7 +660,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             return MP3B_OK;
         };
         if (fused) {
-            l3_launch_backend(ctx->d_tiles().as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
+            l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
                               pcm_dev, ctx->opts.pcm_format, st);
             if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
             launches += (any_layer[3] || keep ? 1 : 0) + (t_hi > t_lo ? 1 : 0);
@@ -693,7 +673,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_IMDCT], st));
         l3_launch_overlap_range(du, u_lo, nu, imd, sb, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_OVL], st));
-        l3_launch_synth(ctx->d_tiles().as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, nullptr, pcm_dev,
+        l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, nullptr, pcm_dev,
                         ctx->opts.pcm_format, st);
         if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
         launches += 5;
@@ -749,7 +729,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         }
     }
     if (sink) CK(cudaEventRecord(ctx->pcm_free[ctx->pcm_cur], ctx->copy_stream));
-    l3_launch_publish(ctx->d_counter().p, ctx->h_counter.p, 4, st);
+    l3_launch_publish(ctx->d_counter.p, ctx->h_counter.p, 4, st);
     launches++;
     CK(cudaEventRecord(ctx->ev[EV_END], st));
     CK(cudaGetLastError());
@@ -836,8 +816,6 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->index_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->walk_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
-    if (cudaEventCreateWithFlags(&ctx->index_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
-    if (cudaEventCreateWithFlags(&ctx->st_entered, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaEventCreate(&ctx->walk_t0) != cudaSuccess || cudaEventCreate(&ctx->walk_t1) != cudaSuccess)
         return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
@@ -862,9 +840,8 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     if (ctx->index_stream) cudaStreamSynchronize(ctx->index_stream);
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_sparse[0], &ctx->d_sparse[1], &ctx->d_segs[0],
-                      &ctx->d_segs[1], &ctx->d_frames_[0], &ctx->d_frames_[1], &ctx->d_units_[0], &ctx->d_units_[1],
-                      &ctx->d_gran_[0], &ctx->d_gran_[1], &ctx->d_arena_[0], &ctx->d_arena_[1], &ctx->d_tiles_[0],
-                      &ctx->d_tiles_[1], &ctx->d_counter_[0], &ctx->d_counter_[1], &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_segs[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_tiles2, &ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -878,7 +855,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     }
     for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
     if (ctx->index_stream) cudaStreamDestroy(ctx->index_stream);
-    for (cudaEvent_t e : {ctx->walk_done, ctx->walk_t0, ctx->walk_t1, ctx->index_done, ctx->st_entered})
+    for (cudaEvent_t e : {ctx->walk_done, ctx->walk_t0, ctx->walk_t1})
         if (e) cudaEventDestroy(e);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
@@ -1622,7 +1599,7 @@ int mp3b_decode(mp3b_ctx *ctx)
     // the frame table comes back for the bookkeeping done in finalize_stream_batch()
     CK(ctx->h_frames_out.ensure(sizeof(L3FrameRec) * std::max<uint32_t>(ctx->nframes, 1)));
     if (ctx->nframes)
-        CK(cudaMemcpyAsync(ctx->h_frames_out.p, ctx->d_frames().p, sizeof(L3FrameRec) * ctx->nframes,
+        CK(cudaMemcpyAsync(ctx->h_frames_out.p, ctx->d_frames.p, sizeof(L3FrameRec) * ctx->nframes,
                            cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stream_batch_pending = true;
     return MP3B_OK;
@@ -1680,9 +1657,9 @@ int mp3b_debug_stage(mp3b_ctx *ctx, int stage, void *dst, uint64_t cap_bytes, ui
     uint32_t es = 1;
     uint64_t n = 0;
     switch (stage) {
-    case MP3B_STAGE_FRAMES: src = ctx->d_frames().p; es = 16; n = ctx->nframes; break;
-    case MP3B_STAGE_UNITDESC: src = ctx->d_units().p; es = 32; n = ctx->nunits; break;
-    case MP3B_STAGE_MAINDATA: src = ctx->d_arena().p; es = 1; n = ctx->arena_bytes; break;
+    case MP3B_STAGE_FRAMES: src = ctx->d_frames.p; es = 16; n = ctx->nframes; break;
+    case MP3B_STAGE_UNITDESC: src = ctx->d_units.p; es = 32; n = ctx->nunits; break;
+    case MP3B_STAGE_MAINDATA: src = ctx->d_arena.p; es = 1; n = ctx->arena_bytes; break;
     case MP3B_STAGE_IS: src = ctx->d_is.p; es = 2; n = (uint64_t)ctx->nunits * 576; break;
     case MP3B_STAGE_SF: src = ctx->d_sf.p; es = 1; n = (uint64_t)ctx->nunits * 40; break;
     case MP3B_STAGE_XR: src = ctx->d_xr.p; es = 4; n = (uint64_t)ctx->nunits * 576; break;
