@@ -581,7 +581,11 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
             fp_src = "measured (profiles/fp32_peak.json, tools/fp32_peak.cu, burst)"
             if not fp_peak:
                 fp_peak, fp_src = 74.4, "theoretical 148 SM x 128 FMA x 2 x 1.965 GHz (no measured file)"
-            exe = (counts.get(args.workload) or {}).get("fused", {}).get("flop_per_unit")
+            cnt = (counts.get(args.workload) or {}).get("fused", {})
+            exe = cnt.get("flop_per_unit")
+            wi = cnt.get("warp_instructions_per_unit")
+            sms, mhz = fp.get("sms", 148), fp.get("max_clock_mhz", 1965)
+            issue_ms = wi * units / (sms * 4 * mhz * 1e6) * 1e3 if wi else None  # one warp instruction per scheduler and clock
             eff_tf = DIRECT_FORM_FLOP_PER_UNIT * units / (kms * 1e-3) / 1e12
             exe_tf = exe * units / (kms * 1e-3) / 1e12 if exe else None
             roof = {"bound": "fp32-issue", "kernel": "k_backend (fused a6-a11)", "unit": "TFLOP/s", "peak": fp_peak,
@@ -593,7 +597,14 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
                     "executed_flop_per_unit": exe, "executed": exe_tf,
                     "executed_frac": exe_tf / fp_peak if exe_tf is not None else None,
                     "effective_direct_form": eff_tf, "effective_direct_form_frac": eff_tf / fp_peak,
-                    "direct_form_flop_per_unit": DIRECT_FORM_FLOP_PER_UNIT}
+                    "direct_form_flop_per_unit": DIRECT_FORM_FLOP_PER_UNIT,
+                    "peak_register_operands": fp.get("ffma_reg_operands_tflops"),
+                    "peak_note": "peak = FFMA with one constant operand (the usual definition); with all three operands in "
+                                 "registers the same pipe measures peak_register_operands, and the packed FFMA2 form the same "
+                                 "flops in half the instructions",
+                    "issue": ({"warp_instructions_per_unit": wi, "issue_limited_ms": issue_ms, "frac": issue_ms / kms,
+                               "note": "the kernel's executed warp instructions (ncu) at one instruction per scheduler and "
+                                       "clock: the bound the kernel actually runs against"} if issue_ms else None)}
         else:
             ach = own[dom] * units / (kms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src,
