@@ -10,7 +10,8 @@
  *
  * Conventions
  *   - plain C types only; no C++ types, exceptions, errno or signals cross this boundary;
- *   - every function returning int returns MP3B_OK (0) or a negative mp3b_status;
+ *   - every function returning int returns MP3B_OK (0) or a negative mp3b_status; mp3b_ctx_create rejects
+ *     option values outside the enums below with MP3B_E_INVAL before it touches a device;
  *   - one mp3b_ctx per GPU, owned by one thread; different contexts share nothing, so N GPUs are
  *     N contexts in N threads or processes with no communication (no NCCL);
  *   - corrupt or undecodable frames are never fatal: they are skipped (sync search) or
@@ -167,8 +168,12 @@ int mp3b_set_pcm_sink(mp3b_ctx *ctx, void *host_dst, uint64_t cap_elems);
  * Incremental: bytes may be enqueued in pieces of any size; each mp3b_decode() decodes the frames
  * completed since the previous call (for every open stream, as one batch) and mp3b_stream_fetch_pcm
  * returns exactly their samples -- concatenated over the calls, the PCM equals a one-shot decode of
- * the whole stream.  PCM of a call that is not fetched before the next mp3b_decode() is dropped.
- * frames / samples in mp3b_stream_info describe the last call, total_samples the stream's life. */
+ * the whole stream.  PCM of a call that is not fetched before the next mp3b_decode() is dropped; closing one
+ * stream does not touch the others' unfetched PCM.
+ * frames / samples in mp3b_stream_info describe the last call, total_samples the stream's life.
+ * A leading ID3v2 tag is dropped as its bytes arrive, however large.  A stream's first frame is emitted once the
+ * header of the frame behind it has arrived (sync confirmation; a lone look-alike in junk must not fix the stream's
+ * identity), so a stream that consists of a single frame decodes in the batch interface only. */
 int mp3b_stream_open(mp3b_ctx *ctx, mp3b_stream **out);
 void mp3b_stream_close(mp3b_stream *s);
 /* Appends raw MP3 bytes; the library copies, the caller may free its buffer on return. */
@@ -187,8 +192,8 @@ int mp3b_stream_pcm_device_ptr(const mp3b_stream *s, const void **ptr, size_t *n
  * opts.gapless is set) is converted to out_rate by a polyphase Kaiser-windowed-sinc FIR (FP32
  * accumulation, 32 zero crossings each side, pass band to 0.82 of the lower Nyquist frequency, about
  * -90 dB from that Nyquist frequency up), into a second arena of the
- * context's pcm_format, streams back to back.  Stream i then holds ceil(samples * out_rate / rate)
- * frames at mp3b_batch_resampled_info's offset.  Asynchronous on the context's stream; the arena
+ * context's pcm_format, streams in input order, each starting on a 16-byte boundary.  Stream i then holds
+ * ceil(samples * out_rate / rate) frames at mp3b_batch_resampled_info's offset.  Asynchronous on the context's stream; the arena
  * stays valid until the next decode or resample call. */
 int mp3b_batch_resample(mp3b_ctx *ctx, int out_rate);
 int mp3b_batch_resampled_info(const mp3b_ctx *ctx, int stream_index, int64_t *offset_elems, int64_t *samples);
@@ -214,8 +219,9 @@ int mp3b_batch_fetch_planar(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int wh
  * speed, the "slow listening" of the reference's README).  Segments of 2 * hop samples (hop = 512 / 256 /
  * 128 by sample rate) are re-spaced and each is shifted by up to hop / 2 samples to where it best
  * continues the previous one (exact integer cross-correlation of an 8-bit alignment signal), then
- * cross-faded with a Hann window.  Result in a third arena of the context's pcm_format, streams back to
- * back; asynchronous on the context's stream; valid until the next decode or stretch call. */
+ * cross-faded with a Hann window.  Result in a third arena of the context's pcm_format, streams in input
+ * order, each starting on a 16-byte boundary (mp3b_batch_stretched_info gives the offset); asynchronous on the
+ * context's stream; valid until the next decode or stretch call. */
 int mp3b_batch_time_stretch(mp3b_ctx *ctx, int speed_num, int speed_den);
 int mp3b_batch_stretched_info(const mp3b_ctx *ctx, int stream_index, int64_t *offset_elems, int64_t *samples);
 int mp3b_batch_stretched_device_ptr(const mp3b_ctx *ctx, const void **ptr, uint64_t *nelems);
