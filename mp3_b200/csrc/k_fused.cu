@@ -43,6 +43,13 @@
 #ifndef KF_CTAS_S16
 #define KF_CTAS_S16 4    // resident CTAs per SM the s16 kernel is compiled for (4: 64 registers; 3: 80)
 #endif
+#ifndef KF_MS_MERGE
+#define KF_MS_MERGE 1    // S1: one copy of the long-block requantiser for MS and non-MS granules (smaller code:
+                         // cfg3 -2.3 %, cfg4 -1.3 %, cfg2 unchanged)
+#endif
+#ifndef KF_GEN_ROLL
+#define KF_GEN_ROLL 0    // S1 general path: the two lines of a pair as a rolled loop (smaller code)
+#endif
 #ifndef KF_WIN_F32X2
 #define KF_WIN_F32X2 1   // S4: the synthesis window as packed FFMA2 (two output slots per instruction)
 #endif
@@ -213,6 +220,9 @@ __device__ __forceinline__ void prefetch_units(SH &S, int tid, uint32_t u_first,
     const char *gs = reinterpret_cast<const char *>(sf_in + (size_t)u_first * 40);
     char *ss = reinterpret_cast<char *>(&S.sf_buf[0][0]);
     for (int i = tid; i < n * 5; i += KF_THREADS) cp_async8(ss + i * 8, gs + i * 8);
+    // the empty slot of an odd mono batch: scalefactors 0, so that its (unused) gains stay finite -- the merged
+    // requantiser multiplies them by zero, and stale bytes can decode to an infinite gain
+    if ((n & 1) && tid < 5) *reinterpret_cast<uint2 *>(ss + (n * 5 + tid) * 8) = make_uint2(0u, 0u);
     cp_async_commit();
 }
 
@@ -291,7 +301,12 @@ __device__ __forceinline__ void stage_gains(SH &S, int tid, int nb, int nch,
                 // 1 / sqrt 2 from the gains; the general path applies it per line
                 const GranMeta &m = S.gm[gi];
                 const bool fold = m.ms && (m.lay[0] | m.lay[1]) == 0 && !m.ist;
+#if KF_MS_MERGE
+                // (merged copy: the right channel of an MS granule is requantised with the opposite sign, see stage_requant)
+                S.gain[gi][c][b] = gain_of(q) * (fold ? (c ? -0.70710678118654752440f : 0.70710678118654752440f) : 1.f);
+#else
                 S.gain[gi][c][b] = gain_of(q) * (fold ? 0.70710678118654752440f : 1.f);
+#endif
             }
         }
     }
@@ -407,7 +422,7 @@ __device__ __forceinline__ float rq_any(const SH &S, int v, float gain, const fl
     const int m = v < 0 ? -v : v;
     float p = S.pow43[min(m, 511)];
     asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %1, 511;\n\t@q ld.global.nc.f32 %0, [%2];\n\t}" : "+f"(p) : "r"(m), "l"(pow43 + m));
-    return __int_as_float(__float_as_int(p * gain) | (v & 0x80000000));
+    return __int_as_float(__float_as_int(p * gain) ^ (v & 0x80000000)); // (xor: the gain may carry a sign of its own)
 }
 
 // ---- S1c: requantise + stereo + reorder, one pair of adjacent lines of both channels per item -----------
@@ -451,6 +466,8 @@ __device__ __forceinline__ void stage_requant(SH &S, int tid, int nb, const L3Ba
     if ((lay0 | lay1) == 0 && !m.ist) {
         float2 *X0 = reinterpret_cast<float2 *>(S.X[gi][0]), *X1 = reinterpret_cast<float2 *>(S.X[gi][1]);
         // MS: (M +- S) / sqrt 2; stage_gains has folded the factor into this granule's band gains
+        const float mf = m.ms ? 1.f : 0.f;
+        (void)mf;
         auto lines = [&](auto ms_tag) {
 #pragma unroll
             for (int q = 0; q < 5; q++) {
@@ -476,12 +493,23 @@ __device__ __forceinline__ void stage_requant(SH &S, int tid, int nb, const L3Ba
                     c1 = rq_hi(S, wb, gb);
                 }
                 const int p = t64 + 64 * q;
+#if KF_MS_MERGE
+                // c = -S for an MS granule (sign folded into the gains): M + S = a - mf c, M - S = mf a + c; mf = 0: (a, c)
+                const float2 A = make_float2(a0, a1), C = make_float2(c0, c1);
+                X0[p] = f2_fma_s(-mf, C, A);
+                X1[p] = f2_fma_s(mf, A, C);
+#else
                 X0[p] = decltype(ms_tag)::value ? make_float2(a0 + c0, a1 + c1) : make_float2(a0, a1);
                 X1[p] = decltype(ms_tag)::value ? make_float2(a0 - c0, a1 - c1) : make_float2(c0, c1);
+#endif
             }
         };
+#if KF_MS_MERGE
+        lines(std::false_type{});
+#else
         if (m.ms) lines(std::true_type{});
         else lines(std::false_type{});
+#endif
         return;
     }
     // general path (short / mixed blocks, intensity stereo): band and reordered position of every line from the
@@ -496,7 +524,11 @@ __device__ __forceinline__ void stage_requant(SH &S, int tid, int nb, const L3Ba
         const uint2 e0 = __ldg(lm0 + p), e1 = __ldg(lm1 + p);
         const uint32_t wa = v[2 * q], wb = v[2 * q + 1];
         const bool sla = (slow & (1u << (2 * q))) != 0, slb = (slow & (0x10000u << (2 * q))) != 0;
+#if KF_GEN_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int h = 0; h < 2; h++) {
             const uint32_t f0 = h ? e0.y : e0.x, f1 = h ? e1.y : e1.x;
             const int b1 = (int)(f1 & 0xffu);

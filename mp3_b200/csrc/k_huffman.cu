@@ -93,6 +93,87 @@ struct SmemReader {
     }
 };
 
+// ---- the same stage through a three-word register window -----------------------------------------
+// A peek costs no load at all (two funnel shifts out of w0..w2); a skip moves the window by a predicated load of ONE
+// word, and only in the lanes that crossed a word boundary.  The kernel is bound by shared-memory wavefronts (every lane
+// reads its own unit's bits, at random banks): this reader issues one load per 32 bits consumed instead of three per
+// code word, at the price of a few more integer instructions per skip.
+struct SmemWinReader {
+    const uint32_t *w;      // stage base (random access for scfsi reuse)
+    const uint32_t *p;      // word `wi` of the stage
+    uint32_t w0, w1, w2;    // words wi, wi + 1, wi + 2
+    uint32_t wi, pos;       // pos: bit position relative to the stage start
+    uint64_t base_bit;
+    uint32_t span_bits;
+
+    __device__ __forceinline__ void init(const uint32_t *stage, uint32_t bit, uint64_t stage_bit0, uint32_t nbits)
+    {
+        w = stage;
+        pos = bit;
+        wi = bit >> 5;
+        p = stage + wi;
+        w0 = p[0];
+        w1 = p[1];
+        w2 = p[2];
+        base_bit = stage_bit0;
+        span_bits = nbits;
+    }
+    __device__ __forceinline__ uint32_t bits_abs(const uint8_t *arena, uint64_t arena_bytes, uint64_t bit, int n) const
+    {
+        const uint64_t rel = bit - base_bit;
+        if (bit >= base_bit && rel + 64 <= span_bits) {
+            const uint32_t r = (uint32_t)rel;
+            const uint32_t *q = w + (r >> 5);
+            return __funnelshift_l(__funnelshift_l(q[1], q[0], r), 0u, n);
+        }
+        return bits_at(arena, arena_bytes, bit, n);
+    }
+    __device__ __forceinline__ uint32_t bitpos() const { return pos; }
+    __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_l(w1, w0, pos); }
+    __device__ __forceinline__ void peek64(uint32_t &hi, uint32_t &lo) const
+    {
+        hi = __funnelshift_l(w1, w0, pos); // the shift count wraps at 32
+        lo = __funnelshift_l(w2, w1, pos);
+    }
+    __device__ __forceinline__ void advance()
+    {
+        const uint32_t cross = (pos >> 5) != wi ? 1u : 0u;
+        uint32_t nw = w2;
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u32 %0, [%1+12];\n\t}"
+                     : "+r"(nw) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(cross));
+        w0 = cross ? w1 : w0;
+        w1 = cross ? w2 : w1;
+        w2 = nw;
+        p += cross;
+        wi += cross;
+    }
+    __device__ __forceinline__ void skip(int k) // k in 0..32: at most one word boundary
+    {
+        pos += (uint32_t)k;
+        advance();
+    }
+    __device__ __forceinline__ void skip_long(int k) // k in 0..64: a second boundary is rare (long escapes)
+    {
+        pos += (uint32_t)k;
+        advance();
+        if ((pos >> 5) != wi) advance();
+    }
+    __device__ __forceinline__ uint32_t get(int k) // k in 0..16 (0 reads nothing), branch-free
+    {
+        const uint32_t v = (peek32() >> 1) >> (31 - k);
+        skip(k);
+        return v;
+    }
+};
+#ifndef K1_WINDOW
+#define K1_WINDOW 0
+#endif
+#if K1_WINDOW
+typedef SmemWinReader StageReader;
+#else
+typedef SmemReader StageReader;
+#endif
+
 // ---- fallback reader over the big-endian arena in global memory ---------------------------------
 // Three consecutive words are cached in registers (the third one raw, loaded a word ahead).  The
 // refill has no branch: the load is predicated and the window moves by selects, so lanes that cross
@@ -534,7 +615,7 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         uint32_t *out32 = reinterpret_cast<uint32_t *>(is_out + (size_t)u * 576);
         uint32_t stw;
         if (staged) {
-            SmemReader br;
+            StageReader br;
             br.init(stage, valid ? (uint32_t)(d.bit_off - a0 * 8) : 0u, a0 * 8, span * 8);
             const uint32_t start = br.bitpos();
             read_scalefactors(br, d, u, valid, units, arena, arena_bytes, sfw);
@@ -591,7 +672,7 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         if (!(stw & 0x80000000u) && used < p23) {
             const uint32_t qoff = (d.flags & L3F_C1TAB) ? 64u : 0u;
             if (staged) {
-                SmemReader br;
+                StageReader br;
                 br.init(stage, (uint32_t)(d.bit_off - a0 * 8) + used, a0 * 8, span * 8);
                 i = decode_count1(br, br.bitpos() + (p23 - used), i, qoff, S, out32);
             } else {
