@@ -124,6 +124,11 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx);
  * the caller's events / graphs / other kernels order with the decode.  NULL restores the
  * context's own stream.  The caller keeps ownership of the stream. */
 int mp3b_ctx_set_stream(mp3b_ctx *ctx, void *cuda_stream);
+/* Per-stage timing (mp3b_stats.ms_index / ms_huffman / ms_fused ...): on = CUDA events are recorded between the
+ * kernels of a decode.  Off (default; MP3B_STAGE_TIMING=1 in the environment turns it on) = only ms_total is
+ * measured (0.03 ms less per 1,024-stream step), and with MP3B_PDL=1 every kernel of the chain is launched as a
+ * programmatic dependent of the one before it (measured: no further gain, hence off by default). */
+int mp3b_ctx_set_stage_timing(mp3b_ctx *ctx, int on);
 const char *mp3b_strerror(int status);
 const char *mp3b_last_error(const mp3b_ctx *ctx);
 

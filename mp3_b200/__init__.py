@@ -62,7 +62,7 @@ class Stats(ctypes.Structure):
 
 EXPORTS = [
     "mp3b_abi_version", "mp3b_device_count", "mp3b_opts_default", "mp3b_ctx_create", "mp3b_ctx_destroy",
-    "mp3b_ctx_set_stream", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
+    "mp3b_ctx_set_stream", "mp3b_ctx_set_stage_timing", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
     "mp3b_decode_packed", "mp3b_sync", "mp3b_flush", "mp3b_batch_stream_info", "mp3b_batch_tag_info", "mp3b_batch_pcm_device_ptr",
     "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_set_pcm_sink", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
@@ -98,6 +98,7 @@ def load_library():
     L.mp3b_ctx_create.argtypes = [i32, ctypes.POINTER(Opts), ctypes.POINTER(vp)]
     L.mp3b_ctx_destroy.argtypes = [vp]
     L.mp3b_ctx_set_stream.argtypes = [vp, vp]
+    L.mp3b_ctx_set_stage_timing.argtypes = [vp, ctypes.c_int]
     L.mp3b_opts_default.argtypes = [ctypes.POINTER(Opts)]
     L.mp3b_decode_batch.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), i32]
     L.mp3b_decode_packed.argtypes = [vp, vp, ctypes.POINTER(u64), i32, i32]
@@ -291,6 +292,11 @@ class Decoder:
     def set_stream(self, cuda_stream_handle):
         """Enqueue on the caller's CUDA stream (an integer cudaStream_t, e.g. torch's .cuda_stream)."""
         self._ck(self.L.mp3b_ctx_set_stream(self.ctx, ctypes.c_void_p(cuda_stream_handle)))
+
+    def set_stage_timing(self, on):
+        """Per-stage CUDA events between the kernels (stats().ms_huffman ...); off by default: the kernels then
+        overlap through programmatic dependent launch."""
+        self._ck(self.L.mp3b_ctx_set_stage_timing(self.ctx, 1 if on else 0))
 
     def __enter__(self):
         return self

@@ -99,6 +99,9 @@ struct mp3b_ctx {
     cudaStream_t index_stream = nullptr; // run-ahead frame walk (opts.async_index)
     cudaEvent_t walk_done = nullptr, walk_t0 = nullptr, walk_t1 = nullptr;
     bool walk_timed = false;
+    bool stage_timing = false;           // CUDA events between the kernels of a decode (mp3b_ctx_set_stage_timing)
+    bool use_pdl = false;                // MP3B_PDL=1: programmatic dependent launch between them when no stage events are
+                                         // recorded (measured: no gain -- cfg2 3.92 ms against 3.86 without, cfg3 5.93 / 5.95)
     int idx_cur = 0;                     // which set of (raw, stream records, walk scratch) the last call used
     std::vector<cudaEvent_t> wave_ev;
     cudaEvent_t copy_done = nullptr;
@@ -127,6 +130,10 @@ struct mp3b_ctx {
     DevBuf &pcm() { return pcm_cur ? d_pcm2 : d_pcm; }
     const DevBuf &pcm() const { return pcm_cur ? d_pcm2 : d_pcm; }
     DevBuf d_is, d_sf, d_nzv, d_xr, d_imd, d_sb; // wave-sized intermediates
+    DevBuf d_hkeys, d_hperm, d_hstate, d_hctl;           // sorted Huffman variant: keys, order, histogram / cursors (wave-sized)
+    int k1_mode = 0;                             // 0 = chunked Huffman kernel (default), 1 = sorted persistent one (MP3B_K1_MODE=sorted:
+                                                 // measured slower)
+    int sm_count = 148;
     DevBuf d_sb2, d_tiles2;                      // Layer II: subband samples of its streams, synthesis tiles
     PinBuf h_tiles2;
     PinBuf h_streams, h_frames, h_tiles, h_stage, h_counter;
@@ -161,7 +168,7 @@ struct mp3b_ctx {
     bool poison = false;        // MP3B_DEBUG_POISON=1: every scratch / output buffer is filled with 0xFF before each
                                 // decode, so that a read of something this call did not write cannot go unnoticed
                                 // (buffers are grow-only and reused; the all-zero spectrum tails are never written)
-    bool have_batch = false, timed = false;
+    bool have_batch = false, timed = false, index_timed = false;
     mp3b_stats stats{};
     std::vector<mp3b_stream *> open_streams;
     bool stream_batch_pending = false; // mp3b_decode() issued, per-stream bookkeeping not done yet
@@ -579,6 +586,12 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(ctx->d_is.ensure(max_wave_units * 576 * sizeof(int16_t)));
     CK(ctx->d_sf.ensure(max_wave_units * 40));
     CK(ctx->d_nzv.ensure(max_wave_units + 16));
+    if (ctx->k1_mode == 1) {
+        CK(ctx->d_hkeys.ensure(max_wave_units * sizeof(uint16_t) + 16));
+        CK(ctx->d_hperm.ensure(max_wave_units * sizeof(uint32_t) + 16));
+        CK(ctx->d_hstate.ensure(max_wave_units * sizeof(uint32_t) + 16));
+        CK(ctx->d_hctl.ensure(l3_huff_sort_ctl_bytes()));
+    }
     if (!fused) {
         CK(ctx->d_xr.ensure(max_wave_units * 576 * sizeof(float)));
         CK(ctx->d_imd.ensure(max_wave_units * 1152 * sizeof(float)));
@@ -587,7 +600,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
 
     if (ctx->poison) {
         for (DevBuf *b : {&ctx->d_frames, &ctx->d_units, &ctx->d_gran, &ctx->d_arena, &ctx->d_tiles, &ctx->d_is, &ctx->d_sf,
-                          &ctx->d_nzv, &ctx->d_xr, &ctx->d_imd, &ctx->d_sb, &ctx->d_sb2, &ctx->pcm()})
+                          &ctx->d_nzv, &ctx->d_hkeys, &ctx->d_hperm, &ctx->d_hstate, &ctx->d_xr, &ctx->d_imd, &ctx->d_sb, &ctx->d_sb2, &ctx->pcm()})
             if (b->p && b->cap) CK(cudaMemsetAsync(b->p, 0xFF, b->cap, st));
     }
     if (ahead && where == MP3B_HOST && !nstreams) CK(cudaStreamSynchronize(ist));
@@ -618,10 +631,17 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     if (frames) {
         l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : d_scratch.as<L3FrameRec>(),
                              (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), ctx->opts.verify_crc, st);
-        if (any_layer[3]) l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st);
+        if (any_layer[3])
+            l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st,
+                                   ctx->use_pdl && !ctx->stage_timing);
         launches += any_layer[3] ? 2 : 1;
     }
-    CK(cudaEventRecord(ctx->ev[EV_INDEX], st));
+    // Per-stage events only on request: an event between two kernels makes the second one wait for the first one's
+    // last CTA; without them each kernel of the chain is launched as a programmatic dependent of the one before
+    // (kernels.h), so its CTAs fill the SMs the predecessor's tail leaves idle.
+    const bool stage_ev = ctx->stage_timing;
+    const bool pdl = ctx->use_pdl && !stage_ev;
+    if (stage_ev) CK(cudaEventRecord(ctx->ev[EV_INDEX], st));
 
     // ---- decode waves
     for (size_t w = 0; w < waves.size(); w++) {
@@ -640,11 +660,20 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         float *imd = ctx->d_imd.as<float>() - (size_t)u_lo * 1152;
         float *sb = ctx->d_sb.as<float>() - (size_t)u_lo * 576;
         uint8_t *nzv = ctx->d_nzv.as<uint8_t>() - (size_t)u_lo;
-        if (any_layer[3] || !fused || keep) // (the staged pipeline and stage dumps want every unit's arrays written)
-            l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu,
-                                (uint32_t)((ctx->arena_bytes + units - 1) / std::max<uint64_t>(units, 1)), ctx->T, is, sf, nzv,
-                                (!fused || keep) ? 1 : 0, st);
-        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
+        if (any_layer[3] || !fused || keep) { // (the staged pipeline and stage dumps want every unit's arrays written)
+            const uint32_t avg_unit = (uint32_t)((ctx->arena_bytes + units - 1) / std::max<uint64_t>(units, 1));
+            if (ctx->k1_mode == 1) {
+                const L3HuffSort scr = {ctx->d_hkeys.as<uint16_t>(), ctx->d_hperm.as<uint32_t>(), ctx->d_hstate.as<uint32_t>(),
+                                        ctx->d_hctl.as<uint32_t>(),
+                                        ctx->sm_count};
+                l3_launch_huffman_sorted(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, avg_unit, ctx->T, scr, is,
+                                         sf, nzv, (!fused || keep) ? 1 : 0, st, pdl);
+                launches += 3;
+            } else
+                l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, avg_unit, ctx->T, is, sf,
+                                        nzv, (!fused || keep) ? 1 : 0, st, pdl && frames);
+        }
+        if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_HUFF], st));
         auto wave_done = [&]() -> int {
             if (!sink) return MP3B_OK;
             while (ctx->wave_ev.size() <= w) {
@@ -661,21 +690,21 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         };
         if (fused) {
             l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
-                              pcm_dev, ctx->opts.pcm_format, st);
-            if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
+                              pcm_dev, ctx->opts.pcm_format, st, pdl && (any_layer[3] || keep));
+            if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
             launches += (any_layer[3] || keep ? 1 : 0) + (t_hi > t_lo ? 1 : 0);
             if (int rc = wave_done()) return rc;
             continue;
         }
         l3_launch_requant_range(du, dg, g_lo, ngw, is, sf, ctx->T, xr, st);
-        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_REQ], st));
+        if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_REQ], st));
         l3_launch_imdct_range(du, u_lo, nu, xr, imd, st);
-        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_IMDCT], st));
+        if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_IMDCT], st));
         l3_launch_overlap_range(du, u_lo, nu, imd, sb, st);
-        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_OVL], st));
+        if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_OVL], st));
         l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, nullptr, pcm_dev,
                         ctx->opts.pcm_format, st);
-        if (waves.size() == 1) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
+        if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
         launches += 5;
         if (int rc = wave_done()) return rc;
     }
@@ -734,7 +763,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(cudaEventRecord(ctx->ev[EV_END], st));
     CK(cudaGetLastError());
 
-    ctx->timed = waves.size() == 1;
+    ctx->timed = waves.size() == 1 && stage_ev;
+    ctx->index_timed = stage_ev;
     ctx->walk_timed = ahead && nstreams > 0;
     ctx->stats.streams = nstreams;
     ctx->stats.frames = (int64_t)frames;
@@ -800,6 +830,9 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
         if (v > 0) ctx->wave_units = (uint64_t)v;
     }
     if (const char *w = getenv("MP3B_DEBUG_POISON")) ctx->poison = atoi(w) != 0;
+    if (const char *w = getenv("MP3B_STAGE_TIMING")) ctx->stage_timing = atoi(w) != 0;
+    if (const char *w = getenv("MP3B_PDL")) ctx->use_pdl = atoi(w) != 0;
+    if (const char *w = getenv("MP3B_K1_MODE")) ctx->k1_mode = !strcmp(w, "sorted") ? 1 : 0;
     if (const char *w = getenv("MP3B_WALK")) ctx->walk_mode = !strcmp(w, "serial") ? 1 : (!strcmp(w, "par") ? 2 : 0);
     if (const char *w = getenv("MP3B_WALK_SEG")) {
         long v = atol(w);
@@ -811,6 +844,8 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     }
     auto bail = [&](int rc) { mp3b_ctx_destroy(ctx); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(MP3B_E_CUDA);
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count < 1)
+        return bail(MP3B_E_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     ctx->stream = ctx->own_stream;
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
@@ -841,7 +876,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_sparse[0], &ctx->d_sparse[1], &ctx->d_segs[0],
                       &ctx->d_segs[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_hkeys, &ctx->d_hperm, &ctx->d_hstate, &ctx->d_hctl, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_tiles2, &ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -864,6 +899,13 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+}
+
+int mp3b_ctx_set_stage_timing(mp3b_ctx *ctx, int on)
+{
+    if (!ctx) return MP3B_E_INVAL;
+    ctx->stage_timing = on != 0;
+    return MP3B_OK;
 }
 
 int mp3b_ctx_set_stream(mp3b_ctx *ctx, void *cuda_stream)
@@ -1014,7 +1056,7 @@ int mp3b_sync(mp3b_ctx *ctx)
             return v;
         };
         ctx->stats.ms_total = ms(EV_START, EV_END);
-        ctx->stats.ms_index = ms(EV_START, EV_INDEX);
+        ctx->stats.ms_index = ctx->index_timed ? ms(EV_START, EV_INDEX) : 0.f;
         if (ctx->walk_timed) { // the run-ahead walk is not between those two events: add its own time
             float v = 0.f;
             if (cudaEventElapsedTime(&v, ctx->walk_t0, ctx->walk_t1) != cudaSuccess) { cudaGetLastError(); v = 0.f; }

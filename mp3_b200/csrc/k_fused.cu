@@ -749,22 +749,10 @@ __device__ __forceinline__ void backend_tile(FusedSharedT<FMT> &S, const int war
     constexpr int KFG = mono ? 2 * KF_B : KF_B;
     float *const Fm = &S.F[0][0][0];
 
-    if (tid == 0) mbar_init(&S.bar, 1);
-    __syncthreads();
-    // history starts at zero (stream head, or about to be re-derived by the warm-up granules)
-    {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = tid; i < 2 * 15 * FS; i += KF_THREADS) S.F[i / (15 * FS)][0][i % (15 * FS)] = 0.f;
-        static_assert(FS % 4 == 0, "rows move as 16-byte words");
-        for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.Hc[i / 144][0][0])[i % 144] = z;
-        for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) { // signed: index = the value's low ten bits
-            const int x = i < KF_POW_LUT / 2 ? i : i - KF_POW_LUT;
-            S.pow43[i] = x < 0 ? -pow43[-x] : pow43[x];
-        }
-        load_meta(S, tid, ubase, min(KFG, total) * nch, nch, units);
-        prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in,
-                       prefetch_counts(tid, ubase, min(KFG, total) * nch, nzv_in));
-    }
+    // (the kernel body has initialised the barrier, zeroed the history and built the |x|^(4/3) table)
+    load_meta(S, tid, ubase, min(KFG, total) * nch, nch, units);
+    prefetch_units(S, tid, ubase, min(KFG, total) * nch, is_in, sf_in,
+                   prefetch_counts(tid, ubase, min(KFG, total) * nch, nzv_in));
     __syncthreads();
 
     const int src_e = lane <= 15 ? 16 + lane : (lane == 16 ? 0 : 48 - lane);
@@ -910,7 +898,25 @@ k_backend(const uint4 *__restrict__ tiles, uint32_t ntiles, const uint32_t *__re
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSharedT<FMT> &S = *reinterpret_cast<FusedSharedT<FMT> *>(smem_raw);
+    pdl_launch_dependents();
     if (blockIdx.x >= ntiles) return;
+    // ---- set-up that reads constant data only: it may run while the Huffman kernel is still draining (programmatic
+    // dependent launch, kernels.h).  History starts at zero (stream head, or about to be re-derived by the warm-up
+    // granules).
+    {
+        const int tid = threadIdx.x;
+        if (tid == 0) mbar_init(&S.bar, 1);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < 2 * 15 * FS; i += KF_THREADS) S.F[i / (15 * FS)][0][i % (15 * FS)] = 0.f;
+        static_assert(FS % 4 == 0, "rows move as 16-byte words");
+        for (int i = tid; i < 2 * 144; i += KF_THREADS) reinterpret_cast<float4 *>(&S.Hc[i / 144][0][0])[i % 144] = z;
+        for (int i = tid; i < KF_POW_LUT; i += KF_THREADS) { // signed: index = the value's low ten bits
+            const int x = i < KF_POW_LUT / 2 ? i : i - KF_POW_LUT;
+            S.pow43[i] = x < 0 ? -pow43[-x] : pow43[x];
+        }
+    }
+    pdl_wait(); // everything below reads what the indexing and Huffman kernels wrote
+    __syncthreads();
     const uint4 tl = tiles[blockIdx.x];
     const int warm = (int)tl.z, ng = (int)tl.y;    // granules before g0 to re-derive state from
     const uint32_t gstart = tl.x - (uint32_t)warm;  // first granule processed
@@ -981,13 +987,13 @@ void l3_fused_init(void)
 
 void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const L3UnitDesc *units,
                        const int16_t *is_in, const uint8_t *sf_in, const uint8_t *nzv_in, const L3DevTables &T,
-                       void *pcm, int pcm_format, cudaStream_t st)
+                       void *pcm, int pcm_format, cudaStream_t st, bool pdl)
 {
     if (!ntiles) return;
     if (pcm_format == MP3B_PCM_S16)
-        k_backend<MP3B_PCM_S16><<<ntiles, KF_THREADS, sizeof(FusedSharedT<MP3B_PCM_S16>), st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
-                                                                  nzv_in, T.bands, T.pow43, pcm);
+        l3_launch_k(k_backend<MP3B_PCM_S16>, dim3(ntiles), dim3(KF_THREADS), sizeof(FusedSharedT<MP3B_PCM_S16>), st, pdl, tiles,
+                    ntiles, gran_unit0, units, is_in, sf_in, nzv_in, T.bands, T.pow43, pcm);
     else
-        k_backend<MP3B_PCM_F32><<<ntiles, KF_THREADS, sizeof(FusedSharedT<MP3B_PCM_F32>), st>>>(tiles, ntiles, gran_unit0, units, is_in, sf_in,
-                                                                  nzv_in, T.bands, T.pow43, pcm);
+        l3_launch_k(k_backend<MP3B_PCM_F32>, dim3(ntiles), dim3(KF_THREADS), sizeof(FusedSharedT<MP3B_PCM_F32>), st, pdl, tiles,
+                    ntiles, gran_unit0, units, is_in, sf_in, nzv_in, T.bands, T.pow43, pcm);
 }

@@ -518,7 +518,9 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
     const int n = (int)min(chunk, nunits - chunk_first);
     const L3UnitDesc *cu = units + u_lo + chunk_first;
 
-    // ---- tables, histogram, the chunk's bit range
+    // ---- code tables into shared memory: constant data, so this part may run while the kernel before this one in the
+    // stream is still draining (programmatic dependent launch, kernels.h)
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(&S.bar, 1);
         S.lo_bit = ~0ull;
@@ -526,7 +528,28 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         S.next = 0;
     }
     for (int k = tid; k < 160; k += K1_THREADS) S.hist[k] = 0;
+    {   // 16 bytes per load (the table's allocation and its shared copy are both padded to a multiple of 16 bytes)
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_lut);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (uint32_t k = tid; k < (lut_len * 2 + 15) / 16; k += K1_THREADS) dst[k] = __ldg(src + k);
+    }
+    if (tid < 32)
+        S.info[tid] = g_info->base[tid] | ((uint32_t)g_info->root[tid] << 16) | ((uint32_t)g_info->linbits[tid] << 24);
+    if (tid < 64) S.quad[tid] = g_quad[tid];
+    else if (tid < 128) S.quad[tid] = (uint8_t)((4u << 4) | (15u - ((tid - 64u) >> 2)));
+    {
+        const uint32_t sym = tid >> 4, s4 = tid & 15u;
+        uint32_t val[4], k = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            val[c] = 0;
+            if (sym & (8u >> c)) { val[c] = ((s4 >> (3 - k)) & 1u) ? 0xffffu : 1u; k++; }
+        }
+        S.c1[tid] = make_uint2(val[0] | (val[1] << 16), val[2] | (val[3] << 16));
+    }
+    pdl_wait(); // unit descriptors and the main-data arena: written by the indexing kernels
     __syncthreads();
+    // ---- histogram, the chunk's bit range
     uint32_t bucket[2];
     {
         unsigned long long lo = ~0ull, hi = 0ull;
@@ -564,21 +587,6 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
     if (tid == 0 && ncopy) {
         mbar_expect_tx(&S.bar, ncopy);
         bulk_g2s(stage, arena + a0, ncopy, &S.bar);
-    }
-    for (uint32_t k = tid; k < lut_len; k += K1_THREADS) s_lut[k] = g_lut[k];
-    if (tid < 32)
-        S.info[tid] = g_info->base[tid] | ((uint32_t)g_info->root[tid] << 16) | ((uint32_t)g_info->linbits[tid] << 24);
-    if (tid < 64) S.quad[tid] = g_quad[tid];
-    else if (tid < 128) S.quad[tid] = (uint8_t)((4u << 4) | (15u - ((tid - 64u) >> 2)));
-    {
-        const uint32_t sym = tid >> 4, s4 = tid & 15u;
-        uint32_t val[4], k = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            val[c] = 0;
-            if (sym & (8u >> c)) { val[c] = ((s4 >> (3 - k)) & 1u) ? 0xffffu : 1u; k++; }
-        }
-        S.c1[tid] = make_uint2(val[0] | (val[1] << 16), val[2] | (val[3] << 16));
     }
     // sort the chunk by big_values, longest first
     cta_scan160(S.hist);
@@ -694,11 +702,249 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
     }
 }
 
+
+// =====================================================================================================================
+// The sorted variant (MP3B_K1_MODE=sorted; measured, NOT the default -- numbers in DESIGN.md): the same decode with
+// the balance across warps the chunked kernel cannot have.
+//
+// In k_huffman a CTA sorts ITS chunk, so its eight warps get groups of very different length (a chunk holds 9 groups,
+// longest first: ncu shows 17.6 % of all warp time waiting at the barrier behind the pair phase, and 28 of 32 lanes
+// active inside it).  Here blocks of 2,048 consecutive units are counting-sorted by length (k_hsort_local) and ONE
+// persistent CTA per SM runs up to 32 independent warps: a warp pulls the next 32 units of the sorted order from a
+// global counter, copies their bits into its private part of shared memory (the lanes together, contiguous bytes per
+// unit, byte-swapped on the way) and decodes its 32 units, which now have the same trip count (31.8 of 32 lanes
+// active).  No CTA barrier after the tables are loaded; tables are loaded once per SM, not once per chunk.  Two passes,
+// each with its own order: A = scalefactors + big_values pairs, sorted by (big_values, block type); B = count1
+// quadruples + the zero tail, sorted by the bits pass A left.  A group whose bits do not fit the warp's part of shared
+// memory (very high bitrates) reads global memory through the register window instead.
+// Why blocks and not the whole wave: with a wave-wide order the 32 lanes of a store instruction hit 32 different
+// 2-MB pages and the load / store unit replays it page by page (1.66 ms); inside a block they share one or two.
+// Why it still loses (1.18 ms against 0.875): every group starts with a chain of dependent global loads (counter, order,
+// descriptor, bits: 27 % of pass A's warp time is long-scoreboard stall, 55 % of pass B's), which the chunked kernel
+// pays once per 288 units with one TMA copy.
+constexpr int HS_KEYS = 512;           // pass A: (min(big_values, 288) >> 1) * 2 + (block_type == 2); pass B: see hs_key_b
+constexpr int HS_SORT_THREADS = 256;
+constexpr int HS_SORT_ITEMS = 8;       // units per thread of the sort kernel
+constexpr int HS_BLOCK = HS_SORT_THREADS * HS_SORT_ITEMS; // units sorted together
+constexpr int HS_CTL_WORDS = 4;        // control block (device words): the group counters of the two passes
+
+__device__ __forceinline__ uint32_t hs_key_a(const L3UnitDesc &d)
+{
+    if (!(d.flags & L3F_VALID)) return 0u;
+    return ((uint32_t)min((int)d.big_values, 288) >> 1) * 2u + ((d.flags & L3F_BT_MASK) == 2 ? 1u : 0u);
+}
+// count1 work left behind the pairs: by the bits (a quadruple takes about five) and by the lines that are left
+__device__ __forceinline__ uint32_t hs_key_b(const L3UnitDesc &d, uint32_t stw)
+{
+    const uint32_t used = stw & 0x1fffu, i = (stw >> 13) & 0x3ffu;
+    if (!(d.flags & L3F_VALID) || used >= d.p23len || i > 572u) return 0u;
+    const uint32_t by_bits = ((uint32_t)d.p23len - used) >> 2, by_lines = (576u - i) >> 1;
+    return (1u + min(min(by_bits, by_lines), 254u)) * 2u + ((d.flags & L3F_C1TAB) ? 1u : 0u);
+}
+
+// Counting sort of each block of HS_BLOCK consecutive units by descending key, in shared memory: perm[position] = unit
+// (both relative to u_lo; a block keeps its place, so a group of 32 consecutive positions holds units that lie within
+// HS_BLOCK units of each other).  Order inside a key is arbitrary (atomics); the decoded output does not depend on it.
+// PASS 0 computes the key from the descriptor, PASS 1 reads the key pass A of the decode left in `keys`.
+template <int PASS>
+__global__ void __launch_bounds__(HS_SORT_THREADS)
+k_hsort_local(const L3UnitDesc *__restrict__ units, uint32_t u_lo, uint32_t nunits, const uint16_t *__restrict__ keys,
+              uint32_t *__restrict__ perm)
+{
+    __shared__ uint32_t cnt[HS_KEYS];   // count per key, then the first position of the key inside the block
+    pdl_launch_dependents();
+    for (int k = threadIdx.x; k < HS_KEYS; k += HS_SORT_THREADS) cnt[k] = 0;
+    pdl_wait();
+    __syncthreads();
+    const uint32_t base = blockIdx.x * HS_BLOCK;
+    uint32_t key[HS_SORT_ITEMS], rank[HS_SORT_ITEMS];
+#pragma unroll
+    for (int r = 0; r < HS_SORT_ITEMS; r++) {
+        const uint32_t i = base + r * HS_SORT_THREADS + threadIdx.x;
+        key[r] = i < nunits ? (PASS == 0 ? hs_key_a(units[u_lo + i]) : (uint32_t)keys[i]) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < HS_SORT_ITEMS; r++) rank[r] = key[r] != 0xffffffffu ? atomicAdd(&cnt[key[r]], 1u) : 0u;
+    __syncthreads();
+    if (threadIdx.x < 32) { // descending exclusive scan by one warp: units with a larger key come first
+        uint32_t carry = 0;
+        for (int b = 0; b < HS_KEYS / 32; b++) {
+            const int c = HS_KEYS - 1 - (b * 32 + (int)threadIdx.x);
+            const uint32_t v = cnt[c];
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += t;
+            }
+            cnt[c] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < HS_SORT_ITEMS; r++)
+        if (key[r] != 0xffffffffu) perm[base + cnt[key[r]] + rank[r]] = base + r * HS_SORT_THREADS + threadIdx.x;
+}
+
+// The bits of the warp's 32 units into its region: unit k's words [w0_k, w0_k + nw_k) to region[off_k ..), byte-swapped.
+// Eight units at a time, two words per lane and unit (a unit of up to 256 bytes), all sixteen loads in flight before
+// the first store; longer units finish in a loop.
+__device__ __forceinline__ void hs_stage_group(uint32_t *__restrict__ region, const uint32_t *__restrict__ words,
+                                               uint32_t wlimit, uint32_t w0, uint32_t nw, uint32_t off, int lane)
+{
+#pragma unroll 1
+    for (int k0 = 0; k0 < 32; k0 += 8) {
+        uint32_t v[8][2], n_k[8], o_k[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            n_k[q] = __shfl_sync(0xffffffffu, nw, k0 + q);
+            o_k[q] = __shfl_sync(0xffffffffu, off, k0 + q);
+            const uint32_t w = __shfl_sync(0xffffffffu, w0, k0 + q) + lane;
+            v[q][0] = (lane < n_k[q] && w < wlimit) ? __ldg(words + w) : 0u;
+            v[q][1] = (lane + 32 < n_k[q] && w + 32 < wlimit) ? __ldg(words + w + 32) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (lane < n_k[q]) region[o_k[q] + lane] = __byte_perm(v[q][0], 0, 0x0123);
+            if (lane + 32 < n_k[q]) region[o_k[q] + lane + 32] = __byte_perm(v[q][1], 0, 0x0123);
+        }
+#pragma unroll 1
+        for (int q = 0; q < 8; q++) {
+            const uint32_t n = __shfl_sync(0xffffffffu, nw, k0 + q);
+            if (n <= 64) continue; // (warp-uniform)
+            const uint32_t o = __shfl_sync(0xffffffffu, off, k0 + q), wb = __shfl_sync(0xffffffffu, w0, k0 + q);
+            for (uint32_t j = 64 + lane; j < n; j += 32)
+                region[o + j] = wb + j < wlimit ? __byte_perm(__ldg(words + wb + j), 0, 0x0123) : 0u;
+        }
+    }
+}
+
+// PASS 0: scalefactors + pairs (state word and pass-B key out); PASS 1: count1 + zero tail + vector count.
+template <int PASS>
+__global__ void __launch_bounds__(1024, 1)
+k_huffman_sorted(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitDesc *__restrict__ units,
+                 uint32_t u_lo, uint32_t nunits, const uint32_t *__restrict__ perm, uint32_t *__restrict__ group_counter,
+                 uint32_t *__restrict__ state, uint16_t *__restrict__ keys_b,
+                 const uint16_t *__restrict__ g_lut, uint32_t lut_len, uint32_t lut_bytes, uint32_t region_words,
+                 const L3HuffInfo *__restrict__ g_info, const uint8_t *__restrict__ g_quad, int16_t *__restrict__ is_out,
+                 uint8_t *__restrict__ sf_out, uint8_t *__restrict__ nzv_out, int zero_fill)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ K1Shared S; // (info, quad, c1 are used; the chunk bookkeeping is not)
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *region = reinterpret_cast<uint32_t *>(smem_raw + lut_bytes) + (size_t)warp * region_words;
+
+    pdl_launch_dependents();
+    if (PASS == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_lut);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (uint32_t k = tid; k < (lut_len * 2 + 15) / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+    }
+    for (int t = tid; t < 256; t += blockDim.x) {
+        if (t < 32) S.info[t] = g_info->base[t] | ((uint32_t)g_info->root[t] << 16) | ((uint32_t)g_info->linbits[t] << 24);
+        if (t < 64) S.quad[t] = g_quad[t];
+        else if (t < 128) S.quad[t] = (uint8_t)((4u << 4) | (15u - ((t - 64u) >> 2)));
+        const uint32_t sym = t >> 4, s4 = t & 15u;
+        uint32_t val[4], k = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            val[c] = 0;
+            if (sym & (8u >> c)) { val[c] = ((s4 >> (3 - k)) & 1u) ? 0xffffu : 1u; k++; }
+        }
+        S.c1[t] = make_uint2(val[0] | (val[1] << 16), val[2] | (val[3] << 16));
+    }
+    pdl_wait(); // descriptors, main-data arena, the sorted order: written by the kernels before this one
+    __syncthreads();
+
+    const uint32_t ngroups = (nunits + 31) >> 5;
+    const uint32_t wlimit = (uint32_t)min((unsigned long long)(arena_bytes >> 2), 0xffffffffull);
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(arena);
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(group_counter, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= ngroups) break;
+        const uint32_t idx = g * 32 + lane;
+        const bool mine = idx < nunits;
+        const uint32_t rel = perm[mine ? idx : g * 32], u = u_lo + rel;
+        const L3UnitDesc d = units[u];
+        const bool valid = (d.flags & L3F_VALID) != 0;
+        uint32_t stw = 0, used = 0;
+        bool work = mine && valid; // this lane reads bits
+        if (PASS == 1) {
+            stw = state[rel];
+            used = stw & 0x1fffu;
+            work = work && used < d.p23len;
+        }
+        // Words this lane's reader may touch.  Pass A: scalefactors (<= 200 bits even when part2_3_length says less: a
+        // damaged side info), one code word past the end (<= 47 bits), the 64-bit look-ahead of a peek.  Pass B: the
+        // bits behind the pairs, one quadruple past the end (<= 10 bits), the look-ahead.
+        const uint64_t bit0 = d.bit_off + used;
+        const uint32_t w0 = (uint32_t)(bit0 >> 5);
+        const uint32_t span = PASS == 0 ? max((uint32_t)d.p23len, 200u) + 47u : ((uint32_t)d.p23len - used) + 10u;
+        const uint32_t nw = work ? (((uint32_t)bit0 & 31u) + span + 64u + 31u) / 32u + 1u : 0u;
+        uint32_t off = nw; // exclusive prefix over the lanes = the unit's place in the warp's region
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, off, o);
+            if (lane >= o) off += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
+        off -= nw;
+        const bool staged = total <= region_words; // (warp-uniform)
+        if (staged) {
+            __syncwarp(); // the previous group's readers are done with the region
+            hs_stage_group(region, words, wlimit, w0, nw, off, lane);
+            __syncwarp();
+        }
+        if (mine) {
+            uint32_t *out32 = reinterpret_cast<uint32_t *>(is_out + (size_t)u * 576);
+            auto pass = [&](auto &br) {
+                if (PASS == 0) {
+                    uint32_t sfw[10];
+                    const uint32_t start = br.bitpos();
+                    read_scalefactors(br, d, u, valid, units, arena, arena_bytes, sfw);
+                    const uint32_t st = decode_pairs(br, start, d, valid, s_lut, S, out32);
+                    uint2 *o = reinterpret_cast<uint2 *>(sf_out + (size_t)u * 40);
+#pragma unroll
+                    for (int k = 0; k < 5; k++) o[k] = make_uint2(sfw[2 * k], sfw[2 * k + 1]);
+                    const uint32_t kb = hs_key_b(d, st);
+                    state[rel] = st;
+                    keys_b[rel] = (uint16_t)kb;
+                } else {
+                    int i = (int)((stw >> 13) & 0x3ffu);
+                    if (work) i = decode_count1(br, br.bitpos() + ((uint32_t)d.p23len - used), i, (d.flags & L3F_C1TAB) ? 64u : 0u, S, out32);
+                    // zero the rest of the last 16-byte vector; the all-zero tail of the spectrum is not written:
+                    // nzv_out[u] tells the consumer how many vectors hold data (zero_fill: staged pipeline, parity dumps)
+                    const int nst = (i + 7) >> 3;
+                    for (int k = i >> 1; k < nst * 4; k++) out32[k] = 0u;
+                    nzv_out[u] = (uint8_t)nst;
+                    if (zero_fill) {
+                        uint4 *out = reinterpret_cast<uint4 *>(out32);
+                        for (int k = nst; k < 72; k++) out[k] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+            };
+            if (staged) {
+                SmemReader br;
+                br.init(region + off, work ? ((uint32_t)bit0 & 31u) : 0u, (uint64_t)w0 * 32u, nw * 32u);
+                pass(br);
+            } else {
+                GlobalReader br;
+                br.init(arena, arena_bytes, bit0);
+                pass(br);
+            }
+        }
+    }
+}
+
 } // namespace
 
 void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
                              uint32_t nunits, uint32_t avg_unit_bytes, const L3DevTables &T, int16_t *is_out,
-                             uint8_t *sf_out, uint8_t *nzv_out, int zero_fill, cudaStream_t st)
+                             uint8_t *sf_out, uint8_t *nzv_out, int zero_fill, cudaStream_t st, bool pdl)
 {
     if (!nunits) return;
     // stage size: the average chunk plus slack, bounded so that at least one CTA fits an SM; chunks
@@ -735,7 +981,54 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     if (f_stage > 0) want = ((uint64_t)f_stage + 15) & ~15ull;
     want = std::min<uint64_t>(want, (K1_MAX_DYN_SMEM - lut_bytes) & ~15ull); // (overrides included; a chunk that does not fit reads global memory)
     const size_t smem = (size_t)(want + lut_bytes);
-    k_huffman<<<(nunits + chunk - 1) / chunk, K1_THREADS, smem, st>>>(
-        arena, arena_bytes, units, u_lo, nunits, T.huff_lut, T.huff_lut_len, (uint32_t)want, chunk, T.huff, T.quad_a,
-        is_out, sf_out, nzv_out, zero_fill);
+    l3_launch_k(k_huffman, dim3((nunits + chunk - 1) / chunk), dim3(K1_THREADS), smem, st, pdl, arena, arena_bytes, units, u_lo,
+                nunits, T.huff_lut, T.huff_lut_len, (uint32_t)want, chunk, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
+}
+
+size_t l3_huff_sort_ctl_bytes(void) { return sizeof(uint32_t) * HS_CTL_WORDS; }
+
+// The sorted variant: counting sort of the wave's units, then one persistent CTA per SM (see k_huffman_sorted).
+void l3_launch_huffman_sorted(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
+                              uint32_t nunits, uint32_t avg_unit_bytes, const L3DevTables &T, const L3HuffSort &scr,
+                              int16_t *is_out, uint8_t *sf_out, uint8_t *nzv_out, int zero_fill, cudaStream_t st, bool pdl)
+{
+    if (!nunits) return;
+    static std::atomic<unsigned long long> configured{0};
+    if (l3_device_needs_setup(configured)) {
+        cudaFuncSetAttribute(k_huffman_sorted<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_huffman_sorted<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        l3_device_setup_done(configured);
+    }
+    // tuning / test overrides (read per launch: the tests switch them inside one process)
+    const char *e_head = getenv("MP3B_K1_HEADROOM"), *e_warps = getenv("MP3B_K1_WARPS"), *e_region = getenv("MP3B_K1_REGION");
+    const double f_head = e_head ? atof(e_head) : 1.5;
+    const long f_warps = e_warps ? atol(e_warps) : 0l, f_region = e_region ? atol(e_region) : 0l;
+    const uint32_t lut_bytes = (uint32_t)(((uint64_t)T.huff_lut_len * sizeof(uint16_t) + 15) & ~15ull);
+    const uint32_t avail = 220u * 1024u - lut_bytes; // (6.6 KB of static shared memory and the per-CTA reservation stay free)
+    // a warp's part of shared memory: its 32 units' main data (+ 24 bytes of look-ahead and alignment each), with
+    // headroom for the groups at the heavy end of the sorted order; as many warps as then fit, at most 32
+    const uint32_t want = (uint32_t)(32.0 * (avg_unit_bytes + 24) * f_head);
+    uint32_t warps = std::max(1u, std::min(32u, avail / std::max(want, 256u)));
+    if (f_warps > 0) warps = (uint32_t)std::min(32l, f_warps);
+    uint32_t region_words = (avail / warps / 16u * 16u) / 4u;
+    if (f_region > 0) region_words = std::min<uint32_t>(region_words, (uint32_t)f_region); // (small: every group reads global memory)
+    const uint32_t ngroups = (nunits + 31) / 32;
+    const uint32_t sms = (uint32_t)std::max(1, scr.sm_count);
+    // a small batch spreads over the SMs (fewer warps per CTA), a large one runs `warps` warps on every SM
+    const uint32_t w_a = std::max(1u, std::min(warps, (ngroups + sms - 1) / sms));
+    const uint32_t ctas_a = std::min(sms, (ngroups + w_a - 1) / w_a);
+    // pass B stages a few words per unit and needs no code tables: always 32 warps, 1 KB each
+    const uint32_t w_b = std::max(1u, std::min(32u, (ngroups + sms - 1) / sms));
+    const uint32_t ctas_b = std::min(sms, (ngroups + w_b - 1) / w_b);
+    const uint32_t region_b = f_region > 0 ? std::min<uint32_t>(1024u, (uint32_t)f_region) : 1024u; // words: 32 units x 128 bytes
+    const uint32_t sort_ctas = (nunits + HS_BLOCK - 1) / HS_BLOCK;
+    cudaMemsetAsync(scr.ctl, 0, sizeof(uint32_t) * HS_CTL_WORDS, st);
+    l3_launch_k(k_hsort_local<0>, dim3(sort_ctas), dim3(HS_SORT_THREADS), 0, st, false, units, u_lo, nunits, scr.keys, scr.perm);
+    l3_launch_k(k_huffman_sorted<0>, dim3(ctas_a), dim3(32 * w_a), (size_t)lut_bytes + (size_t)warps * region_words * 4, st,
+                pdl, arena, arena_bytes, units, u_lo, nunits, scr.perm, scr.ctl, scr.state, scr.keys, T.huff_lut,
+                T.huff_lut_len, lut_bytes, region_words, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
+    l3_launch_k(k_hsort_local<1>, dim3(sort_ctas), dim3(HS_SORT_THREADS), 0, st, pdl, units, u_lo, nunits, scr.keys, scr.perm);
+    l3_launch_k(k_huffman_sorted<1>, dim3(ctas_b), dim3(32 * w_b), (size_t)32 * region_b * 4, st, pdl, arena, arena_bytes,
+                units, u_lo, nunits, scr.perm, scr.ctl + 1, scr.state, scr.keys, T.huff_lut, T.huff_lut_len, 0u,
+                region_b, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
 }

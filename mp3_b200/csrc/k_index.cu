@@ -277,6 +277,7 @@ __global__ void k_side_parse(const uint8_t *__restrict__ raw, const L3StreamRec 
                              L3UnitDesc *__restrict__ units, uint32_t *__restrict__ gran_unit0,
                              uint32_t *__restrict__ concealed, int verify_crc)
 {
+    pdl_launch_dependents(); // the main-data compaction may be scheduled behind this grid's last wave (kernels.h)
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     L3FrameRec fr;
@@ -462,6 +463,8 @@ k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ 
     __shared__ const uint8_t *s_src[PC_FRAMES];
     __shared__ uint8_t *s_dst[PC_FRAMES];
     __shared__ uint32_t s_n[PC_FRAMES];
+    pdl_launch_dependents();
+    pdl_wait(); // frame records: written by k_side_parse
     const uint32_t f0 = blockIdx.x * PC_FRAMES, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < PC_FRAMES) {
         const uint32_t f = f0 + threadIdx.x;
@@ -550,8 +553,9 @@ void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int ns
                                                         units, gran_unit0, concealed_counter, verify_crc);
 }
 void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
-                            uint32_t nframes, uint8_t *arena, cudaStream_t st)
+                            uint32_t nframes, uint8_t *arena, cudaStream_t st, bool pdl)
 {
     if (!nframes) return;
-    k_payload_copy<<<(nframes + PC_FRAMES - 1) / PC_FRAMES, PC_THREADS, 0, st>>>(raw, streams, frames, nframes, arena);
+    l3_launch_k(k_payload_copy, dim3((nframes + PC_FRAMES - 1) / PC_FRAMES), dim3(PC_THREADS), 0, st, pdl, raw, streams, frames,
+                nframes, arena);
 }

@@ -22,6 +22,33 @@ static inline unsigned long long l3_device_bit(void)
 }
 static inline bool l3_device_needs_setup(const std::atomic<unsigned long long> &mask) { return (mask.load() & l3_device_bit()) == 0; }
 static inline void l3_device_setup_done(std::atomic<unsigned long long> &mask) { mask.fetch_or(l3_device_bit()); }
+
+/* Programmatic dependent launch (sm_90+): with `pdl` the kernel may be scheduled while the kernel before it in the
+ * stream is still draining -- its CTAs run their prologue (tables into shared memory, barriers) on the SMs the
+ * predecessor's tail leaves idle and block in pdl_wait() until the predecessor has completed and its writes are
+ * visible.  Every kernel of the decode chain calls pdl_launch_dependents() first thing and pdl_wait() before its first
+ * access to anything an earlier kernel wrote; without the launch attribute both are no-ops. */
+#include <utility>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t l3_launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                      Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 #endif
 
 /* Device-resident tables (pointers into one allocation owned by the context). */
@@ -62,7 +89,7 @@ void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int ns
                           const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,
                           uint32_t *gran_unit0, uint32_t *concealed_counter, int verify_crc, cudaStream_t st);
 void l3_launch_payload_copy(const uint8_t *raw, const L3StreamRec *streams, const L3FrameRec *frames,
-                            uint32_t nframes, uint8_t *arena, cudaStream_t st);
+                            uint32_t nframes, uint8_t *arena, cudaStream_t st, bool pdl = false);
 
 /* K1: scalefactor + Huffman / count1 decode (a4, a5) */
 /* arena_bytes: readable size of the main-data arena (a multiple of 4; reads beyond it return 0) */
@@ -72,7 +99,23 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
                              uint32_t nunits, uint32_t avg_unit_bytes, const L3DevTables &T, int16_t *is_out,
                              uint8_t *sf_out,
                              uint8_t *nzv_out /* [unit]: 16-byte vectors of is_out that hold data */,
-                             int zero_fill /* also write the all-zero tail */, cudaStream_t st);
+                             int zero_fill /* also write the all-zero tail */, cudaStream_t st, bool pdl = false);
+
+/* The sorted variant (default; k_huffman.cu): the wave's units are counting-sorted by (big_values, block type) and
+ * decoded by one persistent CTA per SM whose warps pull groups of 32 equal-length units.  Scratch per wave:
+ * see L3HuffSort (ctl is zeroed by the launcher). */
+struct L3HuffSort {
+    uint16_t *keys;   /* [nunits] sort keys (pass A, then pass B) */
+    uint32_t *perm;   /* [nunits] sorted order (pass A, then pass B) */
+    uint32_t *state;  /* [nunits] per unit behind the pairs: bits consumed | line index << 13 */
+    uint32_t *ctl;    /* l3_huff_sort_ctl_bytes(): histograms, cursors, group counters */
+    int sm_count;
+};
+size_t l3_huff_sort_ctl_bytes(void);
+void l3_launch_huffman_sorted(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
+                              uint32_t nunits, uint32_t avg_unit_bytes, const L3DevTables &T, const L3HuffSort &scr,
+                              int16_t *is_out, uint8_t *sf_out, uint8_t *nzv_out, int zero_fill, cudaStream_t st,
+                              bool pdl = false);
 
 /* K2: requantise + stereo + reorder + alias reduction (a6-a8) */
 /* granules [g_lo, g_lo + ngranules) */
@@ -109,7 +152,7 @@ void l3_launch_synth(const uint2 *tiles, uint32_t ntiles, const uint32_t *gran_u
 void l3_fused_init(void);
 void l3_launch_backend(const uint4 *tiles, uint32_t ntiles, const uint32_t *gran_unit0, const L3UnitDesc *units,
                        const int16_t *is_in, const uint8_t *sf_in, const uint8_t *nzv_in, const L3DevTables &T,
-                       void *pcm, int pcm_format, cudaStream_t st);
+                       void *pcm, int pcm_format, cudaStream_t st, bool pdl = false);
 
 
 /* Sample-rate conversion of decoded PCM (k_resample.cu).  One job per stream; offsets in elements

@@ -19,6 +19,7 @@ def index_ms(m, streams, mode, seg=None, reps=4):
     else:
         os.environ.pop("MP3B_WALK_SEG", None)
     with m.Decoder(device=0, pcm_format=m.PCM_S16) as dec:
+        dec.set_stage_timing(True)
         v, tot = [], []
         for _ in range(reps):
             dec.decode_batch(streams)
@@ -44,6 +45,7 @@ def main():
     os.environ.pop("MP3B_WALK_SEG", None)
     one = synth.make_workload("cfg1", 1)
     with m.Decoder(device=0, pcm_format=m.PCM_S16) as dec:
+        dec.set_stage_timing(True)
         lat = []
         for _ in range(12):
             t = time.perf_counter()
@@ -57,6 +59,7 @@ def main():
                                "audio_s": 10.005, "pcm_samples": int(pcm.size)}
     t = time.perf_counter()
     with m.Decoder(device=0, pcm_format=m.PCM_S16) as dec:
+        dec.set_stage_timing(True)
         for _ in range(3):
             t = time.perf_counter()
             dec.decode_batch([hour])
