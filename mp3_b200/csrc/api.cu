@@ -131,8 +131,8 @@ struct mp3b_ctx {
     const DevBuf &pcm() const { return pcm_cur ? d_pcm2 : d_pcm; }
     DevBuf d_is, d_sf, d_nzv, d_xr, d_imd, d_sb; // wave-sized intermediates
     DevBuf d_hkeys, d_hperm, d_hstate, d_hctl;           // sorted Huffman variant: keys, order, histogram / cursors (wave-sized)
-    int k1_mode = 0;                             // 0 = chunked Huffman kernel (default), 1 = sorted persistent one (MP3B_K1_MODE=sorted:
-                                                 // measured slower)
+    int k1_mode = -1;                            // Huffman kernel (MP3B_K1_MODE): -1 = by batch size (default: warp-per-unit for waves of
+                                                 // <= 4096 units, chunked above), 0 = chunked, 1 = sorted persistent, 2 = warp-per-unit
     int sm_count = 148;
     DevBuf d_sb2, d_tiles2;                      // Layer II: subband samples of its streams, synthesis tiles
     PinBuf h_tiles2;
@@ -586,6 +586,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(ctx->d_is.ensure(max_wave_units * 576 * sizeof(int16_t)));
     CK(ctx->d_sf.ensure(max_wave_units * 40));
     CK(ctx->d_nzv.ensure(max_wave_units + 16));
+    CK(ctx->d_hctl.ensure(l3_huff_sort_ctl_bytes()));
     if (ctx->k1_mode == 1) {
         CK(ctx->d_hkeys.ensure(max_wave_units * sizeof(uint16_t) + 16));
         CK(ctx->d_hperm.ensure(max_wave_units * sizeof(uint32_t) + 16));
@@ -662,13 +663,20 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         uint8_t *nzv = ctx->d_nzv.as<uint8_t>() - (size_t)u_lo;
         if (any_layer[3] || !fused || keep) { // (the staged pipeline and stage dumps want every unit's arrays written)
             const uint32_t avg_unit = (uint32_t)((ctx->arena_bytes + units - 1) / std::max<uint64_t>(units, 1));
-            if (ctx->k1_mode == 1) {
+            // one short stream: a warp per unit (speculative decode at 32 bit positions) finishes sooner than a thread
+            // per unit -- 0.037 ms against 0.060 for one 10-s stream, break-even at about four (profiles/r02_k1_modes.json)
+            const int k1 = ctx->k1_mode >= 0 ? ctx->k1_mode : (nu <= 4096u ? 2 : 0);
+            if (k1 == 1) {
                 const L3HuffSort scr = {ctx->d_hkeys.as<uint16_t>(), ctx->d_hperm.as<uint32_t>(), ctx->d_hstate.as<uint32_t>(),
                                         ctx->d_hctl.as<uint32_t>(),
                                         ctx->sm_count};
                 l3_launch_huffman_sorted(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, avg_unit, ctx->T, scr, is,
                                          sf, nzv, (!fused || keep) ? 1 : 0, st, pdl);
                 launches += 3;
+            } else if (k1 == 2) {
+                const L3HuffSort scr = {nullptr, nullptr, nullptr, ctx->d_hctl.as<uint32_t>(), ctx->sm_count};
+                l3_launch_huffman_warp(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, ctx->T, scr, is, sf, nzv,
+                                       (!fused || keep) ? 1 : 0, st);
             } else
                 l3_launch_huffman_range(ctx->d_arena.as<uint8_t>(), ctx->arena_bytes, du, u_lo, nu, avg_unit, ctx->T, is, sf,
                                         nzv, (!fused || keep) ? 1 : 0, st, pdl && frames);
@@ -832,7 +840,7 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     if (const char *w = getenv("MP3B_DEBUG_POISON")) ctx->poison = atoi(w) != 0;
     if (const char *w = getenv("MP3B_STAGE_TIMING")) ctx->stage_timing = atoi(w) != 0;
     if (const char *w = getenv("MP3B_PDL")) ctx->use_pdl = atoi(w) != 0;
-    if (const char *w = getenv("MP3B_K1_MODE")) ctx->k1_mode = !strcmp(w, "sorted") ? 1 : 0;
+    if (const char *w = getenv("MP3B_K1_MODE")) ctx->k1_mode = !strcmp(w, "sorted") ? 1 : (!strcmp(w, "warp") ? 2 : (!strcmp(w, "chunk") ? 0 : -1));
     if (const char *w = getenv("MP3B_WALK")) ctx->walk_mode = !strcmp(w, "serial") ? 1 : (!strcmp(w, "par") ? 2 : 0);
     if (const char *w = getenv("MP3B_WALK_SEG")) {
         long v = atol(w);

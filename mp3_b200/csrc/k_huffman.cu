@@ -299,18 +299,20 @@ __device__ __forceinline__ void cta_scan160(uint32_t *hist)
     }
 }
 
-struct K1Shared {
+template <int CH>
+struct K1SharedT {
     uint32_t info[32];        // per table_select: base | root << 16 | linbits << 24
     uint8_t quad[128];        // count1 book A (6-bit peek), then book B (4-bit code = 15 - value)
     uint2 c1[256];            // (symbol vwxy << 4 | next 4 bits) -> the four signed lines, packed
     uint32_t hist[160];
-    uint16_t perm[K1_CHUNK];  // sorted order -> slot (unit of the chunk)
-    uint32_t state[K1_CHUNK]; // per slot after the pair loop: bits consumed (13) | line index (10) << 13 | dead << 31
-    uint8_t est[K1_CHUNK];    // per slot: estimated count1 iterations (sort key)
+    uint16_t perm[CH];  // sorted order -> slot (unit of the chunk)
+    uint32_t state[CH]; // per slot after the pair loop: bits consumed (13) | line index (10) << 13 | dead << 31
+    uint8_t est[CH];    // per slot: estimated count1 iterations (sort key)
     unsigned long long lo_bit, hi_bit; // bit range of the chunk's main data in the arena
     uint32_t next;            // group counter of the running phase
     __align__(8) uint64_t bar;
 };
+typedef K1SharedT<K1_CHUNK> K1Shared;
 
 // ---------------------------------------------------------------- part 2: scalefactors (a4)
 template <class R>
@@ -404,9 +406,9 @@ __device__ __forceinline__ void read_scalefactors(R &br, const L3UnitDesc &d, ui
 // what stopping at the first such pair does); the empty book is a real table whose two leaves are
 // (0, 0) of length 0; bit fields come out of the stream with single funnel shifts; four pairs are
 // decoded per trip, so the 16-byte store needs no shift register.
-template <class R>
+template <class R, class SH>
 __device__ __forceinline__ uint32_t decode_pairs(R &br, uint32_t start, const L3UnitDesc &d, bool valid,
-                                                 const uint16_t *__restrict__ s_lut, const K1Shared &S,
+                                                 const uint16_t *__restrict__ s_lut, const SH &S,
                                                  uint32_t *__restrict__ out32)
 {
     uint4 *out = reinterpret_cast<uint4 *>(out32);
@@ -484,8 +486,8 @@ __device__ __forceinline__ uint32_t decode_pairs(R &br, uint32_t start, const L3
 
 // ---------------------------------------------------------------- part 3b: count1 quadruples (a5)
 // code (<= 6 bits) + up to 4 sign bits per iteration; returns the line index after the last one
-template <class R>
-__device__ __forceinline__ int decode_count1(R &br, uint32_t limit, int i, uint32_t qoff, const K1Shared &S,
+template <class R, class SH>
+__device__ __forceinline__ int decode_count1(R &br, uint32_t limit, int i, uint32_t qoff, const SH &S,
                                              uint32_t *__restrict__ out32)
 {
     while (i <= 572 && br.bitpos() < limit) {
@@ -503,14 +505,17 @@ __device__ __forceinline__ int decode_count1(R &br, uint32_t limit, int i, uint3
     return i;
 }
 
-__global__ void __launch_bounds__(K1_THREADS)
+// NT threads per CTA (256: four CTAs per SM; 512: two, with chunks of up to 1,024 units -- more groups per warp to
+// balance, see the launcher), chunks of up to 2 NT units
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
 k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitDesc *__restrict__ units,
           uint32_t u_lo, uint32_t nunits, const uint16_t *__restrict__ g_lut, uint32_t lut_len,
           uint32_t stage_bytes, uint32_t chunk, const L3HuffInfo *__restrict__ g_info, const uint8_t *__restrict__ g_quad,
           int16_t *__restrict__ is_out, uint8_t *__restrict__ sf_out, uint8_t *__restrict__ nzv_out, int zero_fill)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ K1Shared S;
+    __shared__ K1SharedT<2 * NT> S;
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);                // stage_bytes
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw + stage_bytes);  // lut_len entries
     const int tid = threadIdx.x, lane = tid & 31;
@@ -527,17 +532,17 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         S.hi_bit = 0ull;
         S.next = 0;
     }
-    for (int k = tid; k < 160; k += K1_THREADS) S.hist[k] = 0;
+    for (int k = tid; k < 160; k += NT) S.hist[k] = 0;
     {   // 16 bytes per load (the table's allocation and its shared copy are both padded to a multiple of 16 bytes)
         const uint4 *src = reinterpret_cast<const uint4 *>(g_lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (uint32_t k = tid; k < (lut_len * 2 + 15) / 16; k += K1_THREADS) dst[k] = __ldg(src + k);
+        for (uint32_t k = tid; k < (lut_len * 2 + 15) / 16; k += NT) dst[k] = __ldg(src + k);
     }
     if (tid < 32)
         S.info[tid] = g_info->base[tid] | ((uint32_t)g_info->root[tid] << 16) | ((uint32_t)g_info->linbits[tid] << 24);
     if (tid < 64) S.quad[tid] = g_quad[tid];
     else if (tid < 128) S.quad[tid] = (uint8_t)((4u << 4) | (15u - ((tid - 64u) >> 2)));
-    {
+    if (tid < 256) {
         const uint32_t sym = tid >> 4, s4 = tid & 15u;
         uint32_t val[4], k = 0;
 #pragma unroll
@@ -555,7 +560,7 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         unsigned long long lo = ~0ull, hi = 0ull;
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            const int slot = tid + r * K1_THREADS;
+            const int slot = tid + r * NT;
             bucket[r] = 0;
             if (slot < n) {
                 const L3UnitDesc dd = cu[slot];
@@ -593,17 +598,17 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const int slot = tid + r * K1_THREADS;
+        const int slot = tid + r * NT;
         if (slot < n) S.perm[n - 1 - (int)atomicAdd(&S.hist[bucket[r]], 1u)] = (uint16_t)slot;
     }
     if (ncopy) {
         mbar_wait(&S.bar, 0);
-        for (uint32_t k = tid; k < (ncopy >> 2); k += K1_THREADS) stage[k] = __byte_perm(stage[k], 0, 0x0123);
+        for (uint32_t k = tid; k < (ncopy >> 2); k += NT) stage[k] = __byte_perm(stage[k], 0, 0x0123);
     }
     if (staged)
-        for (uint32_t k = (ncopy >> 2) + tid; k < (span >> 2); k += K1_THREADS) stage[k] = 0u; // past the arena
+        for (uint32_t k = (ncopy >> 2) + tid; k < (span >> 2); k += NT) stage[k] = 0u; // past the arena
     __syncthreads();
-    for (int k = tid; k < 160; k += K1_THREADS) S.hist[k] = 0; // reused by the count1 sort
+    for (int k = tid; k < 160; k += NT) S.hist[k] = 0; // reused by the count1 sort
     __syncthreads();
 
     const int ngroups = (n + 31) >> 5;
@@ -657,7 +662,7 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const int slot = tid + r * K1_THREADS;
+        const int slot = tid + r * NT;
         if (slot < n) S.perm[n - 1 - (int)atomicAdd(&S.hist[S.est[slot]], 1u)] = (uint16_t)slot;
     }
     __syncthreads();
@@ -940,6 +945,274 @@ k_huffman_sorted(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const 
     }
 }
 
+
+// =====================================================================================================================
+// The warp-per-unit variant (MP3B_K1_MODE=warp; measured, NOT the default -- numbers in DESIGN.md): what BASELINE.json's
+// north_star sketches ("a warp-per-granule Huffman / count1 decode").  A code word's position depends on every code
+// word before it, so the 32 lanes cannot share one unit's walk; what they can do is SPECULATE: lane l decodes the code
+// word that would start at bit `pos + l`, for all 32 start positions at once (the look-ahead words are the same for
+// all lanes: broadcast loads), and the true chain is then followed through the lanes' lengths by shuffles -- lane 0 is
+// real, the lane at its end is real, and so on until the chain leaves the 32-bit window, the region or the unit.  A
+// round yields window / (average code length) pairs (four to six) for one look-up per lane.  Scalefactors: a lane per
+// band, positions by a warp prefix sum over the field widths.  Persistent CTAs; warps pull units from a counter.
+struct WarpBits {
+    const uint32_t *words; // arena as words
+    uint32_t wlimit;
+    // 64 bits at absolute bit position p (zeros beyond the arena)
+    __device__ __forceinline__ void peek64(uint64_t p, uint32_t &hi, uint32_t &lo) const
+    {
+        const uint64_t w = p >> 5;
+        const uint32_t a = w < wlimit ? __byte_perm(__ldg(words + w), 0, 0x0123) : 0u;
+        const uint32_t b = w + 1 < wlimit ? __byte_perm(__ldg(words + w + 1), 0, 0x0123) : 0u;
+        const uint32_t c = w + 2 < wlimit ? __byte_perm(__ldg(words + w + 2), 0, 0x0123) : 0u;
+        const uint32_t sh = (uint32_t)p & 31u;
+        hi = __funnelshift_l(b, a, sh);
+        lo = __funnelshift_l(c, b, sh);
+    }
+    __device__ __forceinline__ uint32_t bits(uint64_t p, int n) const // n in 0..16
+    {
+        uint32_t hi, lo;
+        peek64(p, hi, lo);
+        return (hi >> 1) >> (31 - n);
+    }
+};
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t &total)
+{
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
+// Part 2 of one unit by the whole warp: lane b takes bands b and b + 32.  Same rules as read_scalefactors.
+// Returns the number of bits part 2 occupies in this unit.
+__device__ __forceinline__ uint32_t warp_scalefactors(const WarpBits &wb, const L3UnitDesc &d, uint32_t u, bool valid,
+                                                      const L3UnitDesc *__restrict__ units, uint8_t *__restrict__ sf_out,
+                                                      int lane)
+{
+    const int bt = d.flags & L3F_BT_MASK;
+    const bool mixed = (d.flags & L3F_MIXED) != 0, lsf = (d.hdr & L3H_LSF) != 0;
+    int w[2] = {0, 0};          // field width of bands lane, lane + 32 in this unit
+    uint64_t reuse[2] = {0, 0}; // scfsi: absolute bit position of the band's value in granule 0
+    int rw[2] = {0, 0};         // ... and its width there
+    bool use_g0[2] = {false, false};
+    bool ist = false;
+    if (valid) {
+        if (!lsf) {
+            const unsigned long long SL1 = 0x4433322211130000ull, SL2 = 0x3232132132103210ull;
+            const int s1 = (int)((SL1 >> (4 * d.sfc)) & 15), s2 = (int)((SL2 >> (4 * d.sfc)) & 15);
+            if (bt == 2) {
+                const int n1 = mixed ? 17 : 18, ntot = mixed ? 35 : 36;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int b = lane + 32 * r;
+                    w[r] = b < n1 ? s1 : (b < ntot ? s2 : 0);
+                }
+            } else {
+                const uint32_t scfsi = (d.pos & L3P_GR) ? (d.pos >> L3P_SCFSI_SHIFT) & 15u : 0u;
+                int g0_s1 = 0, g0_s2 = 0, g0_n1 = 11, g0_ntot = 21;
+                uint64_t g0_bit = 0;
+                if (scfsi) {
+                    const L3UnitDesc d0 = units[u - ((d.hdr & L3H_STEREO) ? 2u : 1u)];
+                    g0_bit = d0.bit_off;
+                    g0_s1 = (int)((SL1 >> (4 * d0.sfc)) & 15);
+                    g0_s2 = (int)((SL2 >> (4 * d0.sfc)) & 15);
+                    if ((d0.flags & L3F_BT_MASK) == 2) {
+                        g0_n1 = (d0.flags & L3F_MIXED) ? 17 : 18;
+                        g0_ntot = (d0.flags & L3F_MIXED) ? 35 : 36;
+                    }
+                }
+                const int b = lane;
+                if (b < 21) {
+                    const int grp = b < 6 ? 0 : (b < 11 ? 1 : (b < 16 ? 2 : 3));
+                    if ((scfsi >> grp) & 1u) {
+                        use_g0[0] = true;
+                        rw[0] = b < g0_n1 ? g0_s1 : (b < g0_ntot ? g0_s2 : 0);
+                        reuse[0] = g0_bit + (b < g0_n1 ? (uint64_t)(b * g0_s1) : (uint64_t)(g0_n1 * g0_s1 + (b - g0_n1) * g0_s2));
+                    } else
+                        w[0] = b < 11 ? s1 : s2;
+                }
+            }
+        } else {
+            int sfc = d.sfc, sl0, sl1, sl2, sl3, tbl;
+            ist = (d.hdr & L3H_IS) && (d.pos & L3P_CH);
+            if (!ist) {
+                if (sfc < 400) { sl0 = (sfc >> 4) / 5; sl1 = (sfc >> 4) % 5; sl2 = (sfc & 15) >> 2; sl3 = sfc & 3; tbl = 0; }
+                else if (sfc < 500) { sfc -= 400; sl0 = (sfc >> 2) / 5; sl1 = (sfc >> 2) % 5; sl2 = sfc & 3; sl3 = 0; tbl = 1; }
+                else { sfc -= 500; sl0 = sfc / 3; sl1 = sfc % 3; sl2 = 0; sl3 = 0; tbl = 2; }
+            } else {
+                sfc >>= 1;
+                if (sfc < 180) { sl0 = sfc / 36; sl1 = (sfc % 36) / 6; sl2 = sfc % 6; sl3 = 0; tbl = 3; }
+                else if (sfc < 244) { sfc -= 180; sl0 = (sfc & 63) >> 4; sl1 = (sfc & 15) >> 2; sl2 = sfc & 3; sl3 = 0; tbl = 4; }
+                else { sfc -= 244; sl0 = sfc / 3; sl1 = sfc % 3; sl2 = 0; sl3 = 0; tbl = 5; }
+            }
+            const int lay = bt == 2 ? (mixed ? 2 : 1) : 0;
+            const int e0 = c_lsf_nsfb[tbl][lay][0], e1 = e0 + c_lsf_nsfb[tbl][lay][1];
+            const int e2 = e1 + c_lsf_nsfb[tbl][lay][2], e3 = e2 + c_lsf_nsfb[tbl][lay][3];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int b = lane + 32 * r;
+                w[r] = b >= 40 ? 0 : (b < e0 ? sl0 : (b < e1 ? sl1 : (b < e2 ? sl2 : (b < e3 ? sl3 : 0))));
+            }
+        }
+    }
+    uint32_t tot0, tot1;
+    const uint32_t o0 = warp_excl_scan((uint32_t)w[0], lane, tot0);
+    const uint32_t o1 = tot0 + warp_excl_scan((uint32_t)w[1], lane, tot1);
+    uint32_t v0 = use_g0[0] ? wb.bits(reuse[0], rw[0]) : wb.bits(d.bit_off + o0, w[0]);
+    uint32_t v1 = wb.bits(d.bit_off + o1, w[1]);
+    if (ist && w[0] && v0 == (1u << w[0]) - 1u) v0 |= 0x80u; // illegal intensity position
+    if (ist && w[1] && v1 == (1u << w[1]) - 1u) v1 |= 0x80u;
+    sf_out[(size_t)u * 40 + lane] = (uint8_t)v0;
+    if (lane < 8) sf_out[(size_t)u * 40 + 32 + lane] = (uint8_t)v1;
+    return tot0 + tot1;
+}
+
+constexpr int KW_THREADS = 256;
+__global__ void __launch_bounds__(KW_THREADS)
+k_huffman_warp(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitDesc *__restrict__ units, uint32_t u_lo,
+               uint32_t nunits, uint32_t *__restrict__ unit_counter, const uint16_t *__restrict__ g_lut, uint32_t lut_len,
+               const L3HuffInfo *__restrict__ g_info, const uint8_t *__restrict__ g_quad, int16_t *__restrict__ is_out,
+               uint8_t *__restrict__ sf_out, uint8_t *__restrict__ nzv_out, int zero_fill)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_info[32];
+    __shared__ uint8_t s_quad[128];
+    __shared__ uint2 s_c1[256];
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    pdl_launch_dependents();
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_lut);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (uint32_t k = tid; k < (lut_len * 2 + 15) / 16; k += KW_THREADS) dst[k] = __ldg(src + k);
+    }
+    if (tid < 32) s_info[tid] = g_info->base[tid] | ((uint32_t)g_info->root[tid] << 16) | ((uint32_t)g_info->linbits[tid] << 24);
+    if (tid < 64) s_quad[tid] = g_quad[tid];
+    else if (tid < 128) s_quad[tid] = (uint8_t)((4u << 4) | (15u - ((tid - 64u) >> 2)));
+    {
+        const uint32_t sym = tid >> 4, s4 = tid & 15u;
+        uint32_t val[4], k = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            val[c] = 0;
+            if (sym & (8u >> c)) { val[c] = ((s4 >> (3 - k)) & 1u) ? 0xffffu : 1u; k++; }
+        }
+        s_c1[tid] = make_uint2(val[0] | (val[1] << 16), val[2] | (val[3] << 16));
+    }
+    pdl_wait();
+    __syncthreads();
+
+    WarpBits wb;
+    wb.words = reinterpret_cast<const uint32_t *>(arena);
+    wb.wlimit = (uint32_t)min((unsigned long long)(arena_bytes >> 2), 0xffffffffull);
+    for (;;) {
+        uint32_t ui = 0;
+        if (lane == 0) ui = atomicAdd(unit_counter, 1u);
+        ui = __shfl_sync(0xffffffffu, ui, 0);
+        if (ui >= nunits) break;
+        const uint32_t u = u_lo + ui;
+        const L3UnitDesc d = units[u];
+        const bool valid = (d.flags & L3F_VALID) != 0;
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(is_out + (size_t)u * 576);
+        const uint64_t start = d.bit_off, limit = start + d.p23len;
+        uint64_t pos = start + warp_scalefactors(wb, d, u, valid, units, sf_out, lane);
+        // ---- big_values pairs
+        const int bv2 = valid ? d.big_values * 2 : 0;
+        int i = 0;
+        while (i < bv2) {
+            const int reg = i < d.r1 ? 0 : (i < d.r2 ? 1 : 2);
+            const int nextb = min(bv2, reg == 0 ? (int)d.r1 : (reg == 1 ? (int)d.r2 : bv2));
+            const uint32_t info = s_info[d.tsel[reg]];
+            const uint32_t base = info & 0xffffu;
+            const int root = (int)((info >> 16) & 0xffu), lin = (int)(info >> 24);
+            // this lane's guess: the pair that starts at pos + lane
+            uint32_t hi, lo;
+            wb.peek64(pos + lane, hi, lo);
+            const uint32_t e1 = s_lut[base + __funnelshift_l(hi, 0u, root)];
+            const bool lng = (e1 & 0x8000u) != 0;
+            const uint32_t w2 = (e1 >> 11) & 15u;
+            const uint32_t e = lng ? s_lut[base + (e1 & 0x7ffu) + __funnelshift_l(hi << root, 0u, w2)] : e1;
+            const int len = (int)((e >> 8) & 15u) + (lng ? root : 0);
+            int x = (e >> 4) & 15, y = e & 15;
+            uint32_t rest = __funnelshift_l(lo, hi, len);
+            const int lx = x == 15 ? lin : 0;
+            x += (int)__funnelshift_l(rest, 0u, lx);
+            rest <<= lx;
+            const int sx = x != 0;
+            { const int m = (int)rest >> 31; x = (x ^ m) - m; }
+            rest <<= sx;
+            const int ly = y == 15 ? lin : 0;
+            y += (int)__funnelshift_l(rest, 0u, ly);
+            rest <<= ly;
+            const int sy = y != 0;
+            { const int m = (int)rest >> 31; y = (y ^ m) - m; }
+            const int n = len + lx + sx + ly + sy;
+            const uint32_t word = __byte_perm((uint32_t)x, (uint32_t)y, 0x5410);
+            // follow the true chain through the lanes
+            const int maxk = (nextb - i) >> 1;
+            int cur = 0, k = 0, myk = -1;
+            bool dead = false, empty = false;
+            while (cur < 32 && k < maxk) {
+                if (pos + cur >= limit) { dead = true; break; } // out of bits: this and all later pairs are (0, 0)
+                const int n_cur = __shfl_sync(0xffffffffu, n, cur);
+                if (n_cur == 0) { empty = true; break; }        // the empty book: the rest of the region is (0, 0)
+                if (lane == cur) myk = k;
+                cur += n_cur;
+                k++;
+            }
+            if (myk >= 0) out32[(i >> 1) + myk] = word;
+            pos += (uint32_t)cur;
+            i += 2 * k;
+            if (dead || empty) {
+                const int stop = dead ? bv2 : nextb;
+                for (int q = (i >> 1) + lane; q < (stop >> 1); q += 32) out32[q] = 0u;
+                i = stop;
+            }
+        }
+        // ---- count1 quadruples
+        if (valid) {
+            const uint32_t qoff = (d.flags & L3F_C1TAB) ? 64u : 0u;
+            bool stop = false;
+            while (!stop && i <= 572 && pos < limit) {
+                uint32_t hi, lo;
+                wb.peek64(pos + lane, hi, lo);
+                const uint32_t e = s_quad[qoff + (hi >> 26)];
+                const uint32_t sym = e & 15u, len = e >> 4;
+                const uint32_t s4 = (hi << len) >> 28;
+                const int n = (int)(len + __popc(sym));
+                const uint2 vw = s_c1[(sym << 4) | s4];
+                int cur = 0, k = 0, myk = -1;
+                while (cur < 32 && i + 4 * k <= 572 && pos + cur < limit) {
+                    const int n_cur = __shfl_sync(0xffffffffu, n, cur);
+                    if (pos + cur + n_cur > limit) { stop = true; break; } // overran part2_3_length: discard, and end
+                    if (lane == cur) myk = k;
+                    cur += n_cur;
+                    k++;
+                }
+                if (myk >= 0) {
+                    out32[(i >> 1) + 2 * myk] = vw.x;
+                    out32[(i >> 1) + 2 * myk + 1] = vw.y;
+                }
+                pos += (uint32_t)cur;
+                i += 4 * k;
+            }
+        }
+        const int nst = (i + 7) >> 3;
+        for (int q = (i >> 1) + lane; q < nst * 4; q += 32) out32[q] = 0u;
+        if (lane == 0) nzv_out[u] = (uint8_t)nst;
+        if (zero_fill) {
+            uint4 *out = reinterpret_cast<uint4 *>(out32);
+            for (int q = nst + lane; q < 72; q += 32) out[q] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
 } // namespace
 
 void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
@@ -951,7 +1224,8 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     // that do not fit (high bitrates, VBR peaks) take the global-memory reader
     static std::atomic<unsigned long long> configured{0};
     if (l3_device_needs_setup(configured)) {
-        cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_DYN_SMEM);
+        cudaFuncSetAttribute(k_huffman<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_DYN_SMEM);
+        cudaFuncSetAttribute(k_huffman<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_DYN_SMEM);
         l3_device_setup_done(configured);
     }
     const uint64_t lut_bytes = ((uint64_t)T.huff_lut_len * sizeof(uint16_t) + 15) & ~15ull;
@@ -962,27 +1236,34 @@ void l3_launch_huffman_range(const uint8_t *arena, uint64_t arena_bytes, const L
     // host threads may get here together)
     static const long f_stage = [] { const char *e = getenv("MP3B_K1_STAGE"); return e ? atol(e) : 0l; }();
     static const long f_chunk = [] { const char *e = getenv("MP3B_K1_CHUNK"); return e ? atol(e) : 0l; }();
+    static const long f_threads = [] { const char *e = getenv("MP3B_K1_THREADS"); return e ? atol(e) : 0l; }();
+    const int nt = f_threads == 512 ? 512 : 256;
+    const int max_chunk = 2 * nt, max_ctas = 1024 / nt;
     const uint64_t per_unit = (uint64_t)avg_unit_bytes + avg_unit_bytes / 24 + 1;
-    const uint64_t fixed = lut_bytes + 6656 + 1024; // LUT, static shared memory, per-CTA reservation
+    const uint64_t fixed = lut_bytes + (nt == 512 ? 10240 : 6656) + 1024; // LUT, static shared memory, per-CTA reservation
     uint64_t want = 0;
     uint32_t chunk = 0;
     // prefer 4 CTAs per SM if they get >= 8 groups each (measured: 0.88 ms against 0.91 with 3 x 480 units;
     // the code tables through L1 instead of a shared copy, to make room for a fifth CTA: 1.05 - 1.16 ms)
-    for (int k = 4; k >= 1 && chunk < 256; k--) {
+    for (int k = max_ctas; k >= 1 && chunk < (uint32_t)nt; k--) {
         // never more dynamic shared memory than the kernel was given (200 KB): large units -- 160 kbit/s mono at
         // 8 kHz is 1,440 bytes per unit -- would otherwise ask for more at one CTA per SM and fail to launch
         const uint64_t budget = std::min<uint64_t>(227ull * 1024 / k - fixed, K1_MAX_DYN_SMEM - lut_bytes) & ~15ull;
         uint64_t c = (budget - 1280) / per_unit / 32 * 32;
-        c = c > K1_CHUNK ? K1_CHUNK : c;
+        c = c > (uint64_t)max_chunk ? (uint64_t)max_chunk : c;
         if (c >= 32) { chunk = (uint32_t)c; want = (c * per_unit + 1280 + 15) & ~15ull; }
     }
     if (!chunk) { chunk = 32; want = 32 * 1024; }
-    if (f_chunk > 0) { chunk = (uint32_t)(f_chunk > K1_CHUNK ? K1_CHUNK : f_chunk) / 32 * 32; want = (chunk * per_unit + 1280 + 15) & ~15ull; }
+    if (f_chunk > 0) { chunk = (uint32_t)(f_chunk > max_chunk ? max_chunk : f_chunk) / 32 * 32; want = (chunk * per_unit + 1280 + 15) & ~15ull; }
     if (f_stage > 0) want = ((uint64_t)f_stage + 15) & ~15ull;
     want = std::min<uint64_t>(want, (K1_MAX_DYN_SMEM - lut_bytes) & ~15ull); // (overrides included; a chunk that does not fit reads global memory)
     const size_t smem = (size_t)(want + lut_bytes);
-    l3_launch_k(k_huffman, dim3((nunits + chunk - 1) / chunk), dim3(K1_THREADS), smem, st, pdl, arena, arena_bytes, units, u_lo,
-                nunits, T.huff_lut, T.huff_lut_len, (uint32_t)want, chunk, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
+    if (nt == 512)
+        l3_launch_k(k_huffman<512>, dim3((nunits + chunk - 1) / chunk), dim3(512), smem, st, pdl, arena, arena_bytes, units, u_lo,
+                    nunits, T.huff_lut, T.huff_lut_len, (uint32_t)want, chunk, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
+    else
+        l3_launch_k(k_huffman<256>, dim3((nunits + chunk - 1) / chunk), dim3(256), smem, st, pdl, arena, arena_bytes, units, u_lo,
+                    nunits, T.huff_lut, T.huff_lut_len, (uint32_t)want, chunk, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
 }
 
 size_t l3_huff_sort_ctl_bytes(void) { return sizeof(uint32_t) * HS_CTL_WORDS; }
@@ -1031,4 +1312,18 @@ void l3_launch_huffman_sorted(const uint8_t *arena, uint64_t arena_bytes, const 
     l3_launch_k(k_huffman_sorted<1>, dim3(ctas_b), dim3(32 * w_b), (size_t)32 * region_b * 4, st, pdl, arena, arena_bytes,
                 units, u_lo, nunits, scr.perm, scr.ctl + 1, scr.state, scr.keys, T.huff_lut, T.huff_lut_len, 0u,
                 region_b, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
+}
+
+void l3_launch_huffman_warp(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
+                            uint32_t nunits, const L3DevTables &T, const L3HuffSort &scr, int16_t *is_out, uint8_t *sf_out,
+                            uint8_t *nzv_out, int zero_fill, cudaStream_t st, bool pdl)
+{
+    if (!nunits) return;
+    const uint32_t lut_bytes = (uint32_t)(((uint64_t)T.huff_lut_len * sizeof(uint16_t) + 15) & ~15ull);
+    const uint32_t sms = (uint32_t)std::max(1, scr.sm_count);
+    const uint32_t ctas = std::min(sms * 8u, (nunits + 7u) / 8u); // persistent: 8 CTAs of 8 warps per SM
+    cudaMemsetAsync(scr.ctl, 0, sizeof(uint32_t) * HS_CTL_WORDS, st);
+    l3_launch_k(k_huffman_warp, dim3(ctas), dim3(KW_THREADS), (size_t)lut_bytes, st, false, arena, arena_bytes, units, u_lo, nunits,
+                scr.ctl, T.huff_lut, T.huff_lut_len, T.huff, T.quad_a, is_out, sf_out, nzv_out, zero_fill);
+    (void)pdl;
 }

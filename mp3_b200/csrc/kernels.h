@@ -117,6 +117,11 @@ void l3_launch_huffman_sorted(const uint8_t *arena, uint64_t arena_bytes, const 
                               int16_t *is_out, uint8_t *sf_out, uint8_t *nzv_out, int zero_fill, cudaStream_t st,
                               bool pdl = false);
 
+/* The warp-per-unit variant (speculative decode at 32 bit positions, chain followed by shuffles); uses scr.ctl only */
+void l3_launch_huffman_warp(const uint8_t *arena, uint64_t arena_bytes, const L3UnitDesc *units, uint32_t u_lo,
+                            uint32_t nunits, const L3DevTables &T, const L3HuffSort &scr, int16_t *is_out, uint8_t *sf_out,
+                            uint8_t *nzv_out, int zero_fill, cudaStream_t st, bool pdl = false);
+
 /* K2: requantise + stereo + reorder + alias reduction (a6-a8) */
 /* granules [g_lo, g_lo + ngranules) */
 void l3_launch_requant_range(const L3UnitDesc *units, const uint32_t *gran_unit0, uint32_t g_lo, uint32_t ngranules,

@@ -75,7 +75,7 @@ def test_huffman_and_scalefactors_bit_exact(k, decoded, batch):
     assert np.array_equal(decoded["is_"][ub: ub + r.units], r.is_), NAMES[k]
 
 
-@pytest.mark.parametrize("mode,env", [("chunk", {}), ("sorted", {"MP3B_K1_WARPS": "3"}), ("sorted", {"MP3B_K1_WARPS": "32"}),
+@pytest.mark.parametrize("mode,env", [("chunk", {}), ("warp", {}), ("sorted", {"MP3B_K1_WARPS": "3"}), ("sorted", {"MP3B_K1_WARPS": "32"}),
                                       ("sorted", {"MP3B_K1_REGION": "64"})])
 def test_huffman_variants_bit_exact(mode, env, mp3b, batch, monkeypatch):
     """Both Huffman kernels -- the default chunked one (a CTA sorts its chunk) and the sorted one (blocks of 2,048 units
@@ -89,7 +89,7 @@ def test_huffman_variants_bit_exact(mode, env, mp3b, batch, monkeypatch):
     with mp3b.Decoder(device=0, pcm_format=mp3b.PCM_F32, pipeline=mp3b.PIPE_FUSED, keep_stages=True) as dec:
         dec.decode_batch(streams)
         is_, sf = dec.stage(mp3b.STAGE_IS), dec.stage(mp3b.STAGE_SF)
-        assert dec.stats().kernel_launches == (7 if mode == "chunk" else 10)
+        assert dec.stats().kernel_launches == (10 if mode == "sorted" else 7)
         for k, r in enumerate(refs):
             ub = dec.stream_info(k).pcm_offset // 576
             assert np.array_equal(sf[ub: ub + r.units], r.sf), NAMES[k]
