@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmp3b.so")
 
-CU_SOURCES = ["k_index.cu", "k_huffman.cu", "k_requant.cu", "k_hybrid.cu", "k_synth.cu", "k_fused.cu", "k_resample.cu", "k_stretch.cu", "k_layer2.cu", "k_planar.cu", "k_segments.cu",
+CU_SOURCES = ["k_index.cu", "k_huffman.cu", "k_requant.cu", "k_hybrid.cu", "k_synth.cu", "k_fused.cu", "k_resample.cu", "k_resample_tc.cu", "k_stretch.cu", "k_layer2.cu", "k_planar.cu", "k_segments.cu",
               "api.cu"]
 CPP_SOURCES = ["tables_build.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -143,6 +143,10 @@ struct mp3b_ctx {
     std::vector<mp3b_tag_info> tags;
     // resampled copy of the last batch
     DevBuf d_rs, d_rs_jobs, d_rs_taps;
+    DevBuf d_rs_tcA, d_rs_tcpfx;         // tensor-core resampler: coefficient tiles of the cached rate pair, entry table
+    L3RsTcPlan rs_tc_plan;
+    long long rs_tc_key = -1;            // in_rate << 32 | out_rate of rs_tc_plan (and of d_rs_tcA's content); -2: pair not served
+    int rs_tc_mode = -1;                 // MP3B_RS_TC: -1 by batch size, 0 never, 1 whenever the pair is served
     std::vector<L3ResampleJob> rs_jobs; // per stream (in_n = 0 for streams without audio)
     uint64_t rs_elems = 0;
     bool have_rs = false;
@@ -840,6 +844,7 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     if (const char *w = getenv("MP3B_DEBUG_POISON")) ctx->poison = atoi(w) != 0;
     if (const char *w = getenv("MP3B_STAGE_TIMING")) ctx->stage_timing = atoi(w) != 0;
     if (const char *w = getenv("MP3B_PDL")) ctx->use_pdl = atoi(w) != 0;
+    if (const char *w = getenv("MP3B_RS_TC")) ctx->rs_tc_mode = atoi(w) != 0 ? 1 : 0;
     if (const char *w = getenv("MP3B_K1_MODE")) ctx->k1_mode = !strcmp(w, "sorted") ? 1 : (!strcmp(w, "warp") ? 2 : (!strcmp(w, "chunk") ? 0 : -1));
     if (const char *w = getenv("MP3B_WALK")) ctx->walk_mode = !strcmp(w, "serial") ? 1 : (!strcmp(w, "par") ? 2 : 0);
     if (const char *w = getenv("MP3B_WALK_SEG")) {
@@ -884,7 +889,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_sparse[0], &ctx->d_sparse[1], &ctx->d_segs[0],
                       &ctx->d_segs[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_hkeys, &ctx->d_hperm, &ctx->d_hstate, &ctx->d_hctl, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_rs_tcA, &ctx->d_rs_tcpfx, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_hkeys, &ctx->d_hperm, &ctx->d_hstate, &ctx->d_hctl, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_tiles2, &ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -1434,8 +1439,40 @@ int mp3b_batch_resample(mp3b_ctx *ctx, int out_rate)
         CK(cudaMemcpyAsync(dt, taps[r].data(), taps[r].size() * sizeof(float), cudaMemcpyHostToDevice, st));
         long long mx = 0;
         for (const auto &j : jl[r]) mx = std::max(mx, j.out_n);
+        // Stereo s16 streams of a large batch go through the tensor cores (k_resample_tc.cu); the rest -- mono, float
+        // PCM, rate pairs whose window does not fit, small batches -- through the FP32 kernels.
+        int mask = 3;
+        if (ctx->opts.pcm_format == MP3B_PCM_S16 && ctx->rs_tc_mode != 0 && rates[r] != out_rate && pT[r] == 65) {
+            const long long key = ((long long)rates[r] << 32) | (long long)out_rate;
+            if (ctx->rs_tc_key != key) {
+                ctx->rs_tc_key = -1;
+                if (l3_resample_tc_plan(taps[r].data(), pL[r], pM[r], pT[r], pH[r], &ctx->rs_tc_plan)) {
+                    CK(ctx->d_rs_tcA.ensure(ctx->rs_tc_plan.A.size() * sizeof(uint16_t)));
+                    CK(cudaMemcpyAsync(ctx->d_rs_tcA.p, ctx->rs_tc_plan.A.data(), ctx->rs_tc_plan.A.size() * sizeof(uint16_t),
+                                       cudaMemcpyHostToDevice, st));
+                    ctx->rs_tc_key = key;
+                } else
+                    ctx->rs_tc_plan = L3RsTcPlan{};
+            }
+            if (ctx->rs_tc_key == key) {
+                std::vector<uint32_t> pfx;
+                const unsigned long long total = l3_resample_tc_prefix(ctx->rs_tc_plan, jl[r].data(), (int)jl[r].size(), &pfx);
+                // worth it from a few groups per CTA on (one short stream is faster on the FP32 kernel)
+                if (total && (ctx->rs_tc_mode == 1 || total >= 4096ull)) {
+                    CK(ctx->d_rs_tcpfx.ensure(pfx.size() * sizeof(uint32_t)));
+                    CK(cudaMemcpyAsync(ctx->d_rs_tcpfx.p, pfx.data(), pfx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                    uint32_t mxe = 0;
+                    for (int k = 0; k < ctx->rs_tc_plan.NK; k++)
+                        mxe = std::max(mxe, pfx[(size_t)k * (jl[r].size() + 1) + jl[r].size()]);
+                    l3_launch_resample_tc(ctx->pcm().p, ctx->d_rs.p, reinterpret_cast<const L3ResampleJob *>(dj), (int)jl[r].size(),
+                                          ctx->d_rs_tcpfx.as<uint32_t>(), mxe, ctx->d_rs_tcA.as<uint16_t>(), ctx->rs_tc_plan,
+                                          ctx->sm_count, st);
+                    mask = 1;
+                }
+            }
+        }
         l3_launch_resample(ctx->pcm().p, ctx->d_rs.p, ctx->opts.pcm_format, reinterpret_cast<const L3ResampleJob *>(dj),
-                           (int)jl[r].size(), mx, reinterpret_cast<const float *>(dt), pL[r], pM[r], pT[r], pH[r], st);
+                           (int)jl[r].size(), mx, reinterpret_cast<const float *>(dt), pL[r], pM[r], pT[r], pH[r], st, mask);
         jo += align_up(jl[r].size() * sizeof(L3ResampleJob), 256);
         to += align_up(taps[r].size() * sizeof(float), 256);
     }

@@ -230,9 +230,10 @@ size_t l3_resample_design(int in_rate, int out_rate, std::vector<float> *hp, int
 }
 
 void l3_launch_resample(const void *in, void *out, int pcm_format, const L3ResampleJob *jobs, int njobs,
-                        long long max_out_n, const float *hp, int L, int M, int taps, int half, cudaStream_t st)
+                        long long max_out_n, const float *hp, int L, int M, int taps, int half, cudaStream_t st,
+                        int channel_mask)
 {
-    if (njobs <= 0 || max_out_n <= 0) return;
+    if (njobs <= 0 || max_out_n <= 0 || !(channel_mask & 3)) return;
     // the register-coefficient kernel, when the tap count is one it is built for and a block size exists that
     // is a multiple of L
     if (taps == 65 || taps == 71 || taps == 97 || taps == 129) {
@@ -249,10 +250,12 @@ void l3_launch_resample(const void *in, void *out, int pcm_format, const L3Resam
                 dim3 grid(gx, (unsigned)nj);
 #define RS_REG(TT, TAPS)                                                                                                 \
     do {                                                                                                                 \
-        k_resample_reg<TT, 2, TAPS><<<grid, T, smem, st>>>(static_cast<const TT *>(in), static_cast<TT *>(out), jobs + j0, \
-                                                           hp, L, M, half, span);                                        \
-        k_resample_reg<TT, 1, TAPS><<<grid, T, smem, st>>>(static_cast<const TT *>(in), static_cast<TT *>(out), jobs + j0, \
-                                                           hp, L, M, half, span);                                        \
+        if (channel_mask & 2)                                                                                            \
+            k_resample_reg<TT, 2, TAPS><<<grid, T, smem, st>>>(static_cast<const TT *>(in), static_cast<TT *>(out),      \
+                                                               jobs + j0, hp, L, M, half, span);                         \
+        if (channel_mask & 1)                                                                                            \
+            k_resample_reg<TT, 1, TAPS><<<grid, T, smem, st>>>(static_cast<const TT *>(in), static_cast<TT *>(out),      \
+                                                               jobs + j0, hp, L, M, half, span);                         \
     } while (0)
 #define RS_REG_T(TT)                                                                                                     \
     do {                                                                                                                 \

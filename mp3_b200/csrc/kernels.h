@@ -196,8 +196,21 @@ int l3_stretch_hop(int sample_rate);
 void l3_launch_stretch(const void *in, void *out, int pcm_format, const L3StretchJob *jobs, int njobs, int num, int den,
                        int *offsets_out, int max_frames, cudaStream_t st);
 size_t l3_resample_design(int in_rate, int out_rate, std::vector<float> *hp, int *L, int *M, int *taps, int *half);
+/* channel_mask: bit 0 = convert the mono jobs, bit 1 = the stereo jobs (those may have gone to the tensor-core path) */
 void l3_launch_resample(const void *in, void *out, int pcm_format, const L3ResampleJob *jobs, int njobs,
-                        long long max_out_n, const float *hp, int L, int M, int taps, int half, cudaStream_t st);
+                        long long max_out_n, const float *hp, int L, int M, int taps, int half, cudaStream_t st,
+                        int channel_mask = 3);
+/* Tensor-core path for stereo s16 jobs (k_resample_tc.cu): tiles of 128 outputs as [128 x K] x [K x 64] products. */
+struct L3RsTcPlan {
+    int L = 0, M = 0, taps = 0, half = 0, NK = 0, Kpad = 0;
+    std::vector<uint16_t> A; /* [NK][hi, lo][128 x Kpad] fp16 bit patterns in the MMA's shared-memory layout */
+};
+bool l3_resample_tc_plan(const float *hp, int L, int M, int taps, int half, L3RsTcPlan *plan);
+unsigned long long l3_resample_tc_prefix(const L3RsTcPlan &plan, const L3ResampleJob *jobs, int njobs,
+                                         std::vector<uint32_t> *prefix);
+void l3_launch_resample_tc(const void *in, void *out, const L3ResampleJob *jobs_dev, int njobs, const uint32_t *prefix_dev,
+                           uint32_t max_entries_per_kind, const uint16_t *A_dev, const L3RsTcPlan &plan, int sm_count,
+                           cudaStream_t st);
 #endif
 
 #endif

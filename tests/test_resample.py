@@ -83,6 +83,58 @@ def test_resample_matches_upfirdn(fmt, out_rate, synth_mod):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("out_rate", [48000, 44100, 96000])
+def test_tensor_core_path_matches_upfirdn(out_rate, synth_mod, monkeypatch):
+    """The tensor-core resampler (stereo s16, forced on with MP3B_RS_TC=1 -- by default it serves large batches only)
+    against the same float64 reference, within the same 1 LSB, and against the FP32 kernels' output: streams of several
+    input rates, lengths that are not a multiple of the 128-output tile, a stream shorter than one tile, a mono stream
+    in between (which stays on the FP32 kernel)."""
+    from scipy.signal import upfirdn
+    import mp3_b200 as m
+    cfgs = [dict(nframes=40, seed=11, mode=1), dict(nframes=3, seed=12), dict(nframes=9, seed=13, mode=3),
+            dict(nframes=25, seed=14, sample_rate=22050, bitrate_kbps=64), dict(nframes=1, seed=15, sample_rate=32000),
+            dict(nframes=30, seed=16, sample_rate=32000, mode=1, bitrate_kbps=192), dict(nframes=17, seed=17, sample_rate=8000,
+                                                                                        bitrate_kbps=16, mode=1),
+            dict(nframes=21, seed=18, sample_rate=48000)]
+    streams = [synth_mod.make_stream(**c) for c in cfgs]
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("MP3B_RS_TC", tc)
+        with m.Decoder(device=0, pcm_format=m.PCM_S16) as dec:
+            dec.decode_batch(streams)
+            arena = dec.fetch_pcm().copy()
+            dec.resample(out_rate)
+            out, where = dec.fetch_resampled()
+            outs[tc] = (out.copy(), where)
+            if tc == "0":
+                continue
+            for i in range(len(cfgs)):
+                inf = dec.stream_info(i)
+                x = dec.stream_pcm(i, arena).astype(np.float64) / 32768.0
+                taps, L, M = m.resample_filter(inf.sample_rate, out_rate)
+                D = (taps.shape[1] // 2) * L
+                nout = -(-inf.samples * L // M)
+                off, cnt = where[i]
+                assert cnt == nout
+                got = out[off: off + cnt * inf.channels].reshape(cnt, inf.channels).astype(np.float64)
+                if L == 1 and M == 1:
+                    ref = x
+                else:
+                    r = (-D) % M
+                    g = np.concatenate([np.zeros(r), full_filter(taps.astype(np.float64), L)])
+                    k = (D + r) // M
+                    ref = np.stack([upfirdn(g, x[:, c], up=L, down=M)[k: k + nout] for c in range(inf.channels)], axis=1)
+                    if ref.shape[0] < nout:
+                        ref = np.pad(ref, ((0, nout - ref.shape[0]), (0, 0)))
+                want = np.clip(np.round(ref * 32768.0), -32768, 32767)
+                assert np.abs(got - want).max() <= 1, (i, cfgs[i])
+    a, b = outs["1"][0].astype(np.int32), outs["0"][0].astype(np.int32)
+    assert outs["1"][1] == outs["0"][1]
+    assert np.abs(a - b).max() <= 1          # both within 1 LSB of the exact value's rounding ...
+    assert np.mean(a != b) < 0.02            # ... and they differ only where that value sits at a rounding boundary
+
+
+@pytest.mark.gpu
 def test_unusable_rate_pair_is_refused(synth_mod):
     """A rate pair whose ratio needs more than 4,096 phases is refused with an error, not attempted."""
     import mp3_b200 as m
