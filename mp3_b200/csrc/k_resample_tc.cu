@@ -9,8 +9,8 @@
 // and A depends on n0 only through (n0 M + D) mod L: tiles t = n0 / 128 of the same "kind" t mod NK share it
 // (NK = 5 for 44.1 -> 48 kHz).  So:  D[128 x N] = A_k[128 x K] * X[K x N],  one column of X per (tile, channel).
 // Exact split-precision operands in fp16 (kind::f16, FP32 accumulation in TMEM):
-//   * a sample x (s16) = 256 hi + lo with hi in -128 .. 127, lo in 0 .. 255: both halves are exact fp16 numbers
-//     (256 hi <= 32768 is a small integer times a power of two);
+//   * a sample x (s16) = 256 hi + lo with hi in -128 .. 127, lo in 0 .. 255: both halves are exact fp16 numbers (the
+//     factor 256 is applied to the hi accumulator when it is read out);
 //   * a coefficient c (float) = c1 + c2 + O(2^-22 c) with c1 = fp16(c), c2 = fp16(c - c1);
 //   four products per K step: (c1 + c2)(256 hi + lo).  What is dropped is 2^-22 of a coefficient times a 16-bit
 //   sample: below the FP32 kernel's own rounding.  Results equal the FP32 kernel's within its 1-LSB bound
@@ -41,7 +41,12 @@ constexpr int RT_N = 2 * RT_COLS; // MMA N: the hi halves of the 64 columns, the
 constexpr int RT_LBO_B = RT_N / 8 * 128 + 16; // K-chunk stride of the signal operand: 16 bytes of padding, so that the
                                               // threads that build it (one K chunk each) store to different banks
 constexpr int RT_KMAX = 192;     // largest padded input window per tile (multiple of 16)
-constexpr int RT_THREADS = 288;   // 4 epilogue warps, 4 producer warps, 1 MMA-issue warp
+#ifndef RT_PWARPS_N
+#define RT_PWARPS_N 8
+#endif
+constexpr int RT_PWARPS = RT_PWARPS_N;                 // producer warps (8 or 16)
+constexpr int RT_EWARPS = 8;                           // read-out warps: warp e owns TMEM lanes 32 (e % 4) .., columns 32 (e / 4) ..
+constexpr int RT_THREADS = 32 * (RT_EWARPS + RT_PWARPS + 2); // read-out warps, producer warps, 1 MMA-issue warp, 1 metadata warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,14 +76,14 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t d
 
 struct RtMeta {          // one (tile, channel pair) of the staged group
     long long in_off;    // element offset of the stream's PCM in the arena
-    long long in_n;      // its frames
     long long base;      // first input frame of the tile's window (may be negative, may run past in_n)
     long long out_off;   // element offset of the tile's first output frame
+    int in_n;            // the stream's frames
     int rows;            // output frames of the tile that exist (0: padding entry)
-    int pad;
 };
 
-constexpr int RT_META = 8; // ring of per-group metadata: written a group ahead, read two groups behind
+constexpr int RT_META = 16; // ring of per-group metadata: written up to four groups ahead of the producers, read by the
+                            // read-out warps up to four groups behind them
 struct RtShared {
     RtMeta meta[RT_META][RT_PAIRS];
     __align__(8) uint64_t full[2];      // signal operand b staged (one producer thread arrives)
@@ -86,6 +91,9 @@ struct RtShared {
     __align__(8) uint64_t tmem_free[2]; // accumulator b has been read out and stored (one lane per epilogue warp)
     uint32_t tmem_base;
     int job_cursor; // job of the last group's first entry: entries come in increasing order, the next search starts here
+    volatile int meta_done; // groups whose metadata the metadata warp has published
+    volatile int prod_done; // groups the producers have staged (throttles the metadata warp: the ring has RT_META slots)
+    __align__(16) uint32_t scratch[RT_PWARPS][RT_KMAX]; // per producer warp: one input window on its way from lane = frame to lane = K chunk
 };
 
 __device__ __forceinline__ void rt_bar_init(uint64_t *bar, int count)
@@ -110,15 +118,14 @@ __device__ __forceinline__ void rt_bar_wait(uint64_t *bar, uint32_t parity)
 __device__ __forceinline__ void split8(const uint32_t (&w)[8], uint4 &lhi, uint4 &llo, uint4 &rhi, uint4 &rlo)
 {
     uint32_t hi[8], lo[8]; // per frame: (left, right) as half2
-    const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f), k1152 = __floats2half2_rn(1152.f, 1152.f),
-                  k256 = __floats2half2_rn(256.f, 256.f);
+    const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f), k1152 = __floats2half2_rn(1152.f, 1152.f);
 #pragma unroll
     for (int f = 0; f < 8; f++) {
         // 0x6400 | b is the fp16 number 1024 + b for b in 0 .. 1023
         uint32_t l = (w[f] & 0x00ff00ffu) | 0x64006400u;
-        uint32_t h = (((w[f] >> 8) & 0x00ff00ffu) ^ 0x00800080u) | 0x64006400u; // 1024 + (signed high byte + 128)
+        uint32_t h = ((w[f] >> 8) & 0x00ff00ffu) ^ 0x64806480u; // 1024 + (signed high byte + 128)
         __half2 lh = __hsub2(*reinterpret_cast<__half2 *>(&l), k1024);
-        __half2 hh = __hmul2(__hsub2(*reinterpret_cast<__half2 *>(&h), k1152), k256);
+        __half2 hh = __hsub2(*reinterpret_cast<__half2 *>(&h), k1152); // (the factor 256 is applied at the read-out)
         lo[f] = *reinterpret_cast<uint32_t *>(&lh);
         hi[f] = *reinterpret_cast<uint32_t *>(&hh);
     }
@@ -132,11 +139,13 @@ __device__ __forceinline__ void split8(const uint32_t (&w)[8], uint4 &lhi, uint4
                      __byte_perm(lo[6], lo[7], 0x7632));
 }
 
-// Roles: warps 0-3 read accumulators out and store PCM (warp w owns TMEM lanes 32 w ..), warps 4-7 build the signal
-// operand, warp 8 (one lane) issues the MMAs.  They meet only through mbarriers: full[b] -> MMA -> mma_done[b] ->
+// Roles: warps 0-3 read accumulators out and store PCM (warp w owns TMEM lanes 32 w ..), warps 4-11 build the signal
+// operand (raw frames of the group after next are already in registers: two register sets, so that a full group's
+// time hides the latency of the loads), one warp (one lane) issues the MMAs, one warp works out a few groups ahead which
+// stream and tile every entry of a group is (dependent loads of the entry table: off everybody's critical path).  They meet only through mbarriers: full[b] -> MMA -> mma_done[b] ->
 // epilogue -> tmem_free[b]; mma_done[b] also tells the producers that operand buffer b may be overwritten.
-constexpr int RT_PRODUCERS = 128;
-constexpr int RT_TASKS = 6; // K chunks per producer thread and group: 32 windows x 24 chunks (K = 192) / 128 threads
+constexpr int RT_WIN = RT_PAIRS / RT_PWARPS; // input windows per producer warp and group
+constexpr int RT_LD = RT_KMAX / 32;       // coalesced 32-frame loads per window
 
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L3ResampleJob *__restrict__ jobs, int njobs,
@@ -168,10 +177,12 @@ k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L
     }
     if (tid == 0) {
         S.job_cursor = 0;
+        S.meta_done = 0;
+        S.prod_done = 0;
         for (int b = 0; b < 2; b++) {
             rt_bar_init(&S.full[b], 1);
             rt_bar_init(&S.mma_done[b], 1);
-            rt_bar_init(&S.tmem_free[b], 4);
+            rt_bar_init(&S.tmem_free[b], RT_EWARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -182,88 +193,76 @@ k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L
     const uint32_t tmem = S.tmem_base;
     const long long D = (long long)half * L;
 
-    if (warp >= 4 && warp < 8) {
-        // ================= producers: metadata a group ahead, raw frames in registers a group ahead =================
-        const int ptid = tid - 128;
-        const int kchunks = Kpad >> 3, ntask = RT_PAIRS * kchunks;
-        auto make_meta = [&](int it) { // by warp 4
-            const uint32_t e = (blockIdx.x + (uint32_t)it * gridDim.x) * RT_PAIRS + lane;
-            RtMeta m;
-            m.rows = 0;
-            m.in_off = m.in_n = m.base = m.out_off = 0;
-            m.pad = 0;
-            int lo = S.job_cursor; // last job with pfx[job] <= e: a short walk from where the previous group started
-            __syncwarp();
-            if (e < npairs) {
-                while (lo + 1 < njobs && pfx[lo + 1] <= e) lo++;
-                const L3ResampleJob jb = jobs[lo];
-                const long long t = kind + (long long)NK * (e - pfx[lo]);
-                const long long q0 = (t * RT_ROWS * M + D) / L;
-                m.in_off = jb.in_off;
-                m.in_n = jb.in_n;
-                m.base = q0 - (taps - 1);
-                m.out_off = jb.out_off + t * RT_ROWS * 2;
-                const long long left = jb.out_n - t * RT_ROWS;
-                m.rows = (int)(left < RT_ROWS ? left : RT_ROWS);
-            }
-            S.meta[it & (RT_META - 1)][lane] = m;
-            if (lane == 0) S.job_cursor = lo;
-        };
-        uint32_t w[RT_TASKS][8];
-        auto load_raw = [&](int it) {
+    if (warp >= RT_EWARPS && warp < RT_EWARPS + RT_PWARPS) {
+        // ================= producers: metadata and raw frames two groups ahead =================
+        const int ptid = tid - 32 * RT_EWARPS;
+        const int kchunks = Kpad >> 3;
+        // A window = Kpad consecutive stereo frames (4 bytes each) of one stream.  Loads: lane = frame, 128 contiguous
+        // bytes per instruction, the words of the group after next parked in registers.  Conversion needs 8 consecutive
+        // frames per thread (one 16-byte K chunk per operand piece): the window passes through a 768-byte scratch row
+        // of the warp (transpose), then lane kc builds chunk kc.
+        const int pw = warp - RT_EWARPS;
+        uint32_t *scratch = reinterpret_cast<uint32_t *>(S.scratch[pw]);
+        auto load_raw = [&](int it, uint32_t (&w)[RT_WIN][RT_LD]) {
+            for (uint32_t spins = 0; S.meta_done <= it;) // (the metadata warp runs a few groups ahead: normally no wait)
+                if (++spins > (1u << 26)) __trap();
+            __threadfence_block();
             const RtMeta *mt = S.meta[it & (RT_META - 1)];
 #pragma unroll
-            for (int j = 0; j < RT_TASKS; j++) {
-                const int task = j * RT_PRODUCERS + ptid;
-                const int pi = task / kchunks, kc = task - pi * kchunks; // (consecutive threads: consecutive chunks of a window)
-                if (task < ntask) {
-                    const RtMeta &m = mt[pi];
-                    const long long f0 = m.base + 8 * kc;
-                    if (m.rows > 0 && f0 >= 0 && f0 + 8 <= m.in_n) {
-                        const uint32_t *src = reinterpret_cast<const uint32_t *>(in + m.in_off) + f0;
+            for (int q = 0; q < RT_WIN; q++) {
+                const RtMeta &m = mt[pw + RT_PWARPS * q];
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(in + m.in_off);
+                const long long base = m.base, in_n = m.rows > 0 ? m.in_n : 0;
 #pragma unroll
-                        for (int f = 0; f < 8; f++) w[j][f] = __ldg(src + f);
-                    } else {
-#pragma unroll
-                        for (int f = 0; f < 8; f++) {
-                            const long long fi = f0 + f;
-                            w[j][f] = (m.rows > 0 && fi >= 0 && fi < m.in_n)
-                                          ? __ldg(reinterpret_cast<const uint32_t *>(in + m.in_off) + fi) : 0u;
-                        }
-                    }
+                for (int f = 0; f < RT_LD; f++) {
+                    const int x = lane + 32 * f;
+                    const long long fi = base + x;
+                    w[q][f] = (x < Kpad && fi >= 0 && fi < in_n) ? __ldg(src + fi) : 0u;
                 }
             }
         };
-        if (warp == 4) make_meta(0);
-        asm volatile("barrier.sync 1, 128;" ::: "memory");
-        load_raw(0);
-        for (int it = 0; it < nit; it++) {
+        uint32_t w0[RT_WIN][RT_LD], w1[RT_WIN][RT_LD]; // raw frames of the groups `it` (even / odd)
+        // one group: convert the register set into operand buffer b, publish it, refill the set for group it + 2
+        auto step = [&](int it, uint32_t (&w)[RT_WIN][RT_LD]) {
             const int b = it & 1, k = it >> 1;
             if (k > 0) rt_bar_wait(&S.mma_done[b], (uint32_t)(k - 1) & 1u); // the MMAs that read this buffer are done
             unsigned char *Bb = Bbuf + (size_t)b * b_bytes;
 #pragma unroll
-            for (int j = 0; j < RT_TASKS; j++) {
-                const int task = j * RT_PRODUCERS + ptid;
-                const int pi = task / kchunks, kc = task - pi * kchunks;
-                if (task < ntask) {
+            for (int q = 0; q < RT_WIN; q++) {
+#pragma unroll
+                for (int f = 0; f < RT_LD; f++) scratch[lane + 32 * f] = w[q][f];
+                __syncwarp();
+                if (lane < kchunks) {
+                    const uint4 a0 = reinterpret_cast<const uint4 *>(scratch)[2 * lane], a1 = reinterpret_cast<const uint4 *>(scratch)[2 * lane + 1];
+                    const uint32_t ww[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                     uint4 lhi, llo, rhi, rlo;
-                    split8(w[j], lhi, llo, rhi, rlo);
+                    split8(ww, lhi, llo, rhi, rlo);
                     // column c of the group: hi half at MMA column c, lo half at 64 + c
-                    unsigned char *chunk = Bb + (size_t)kc * RT_LBO_B;
+                    const int pi = pw + RT_PWARPS * q;
+                    unsigned char *chunk = Bb + (size_t)lane * RT_LBO_B;
                     const int cl = 2 * pi, cr = 2 * pi + 1;
                     *reinterpret_cast<uint4 *>(chunk + (cl >> 3) * 128 + (cl & 7) * 16) = lhi;
                     *reinterpret_cast<uint4 *>(chunk + (cr >> 3) * 128 + (cr & 7) * 16) = rhi;
                     *reinterpret_cast<uint4 *>(chunk + ((cl + RT_COLS) >> 3) * 128 + (cl & 7) * 16) = llo;
                     *reinterpret_cast<uint4 *>(chunk + ((cr + RT_COLS) >> 3) * 128 + (cr & 7) * 16) = rlo;
                 }
+                __syncwarp();
             }
-            if (warp == 4 && it + 1 < nit) make_meta(it + 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core
-            asm volatile("barrier.sync 1, 128;" ::: "memory");
-            if (ptid == 0) rt_bar_arrive(&S.full[b]);
-            if (it + 1 < nit) load_raw(it + 1);
+            asm volatile("barrier.sync 1, %0;" ::"n"(32 * RT_PWARPS) : "memory");
+            if (ptid == 0) {
+                rt_bar_arrive(&S.full[b]);
+                S.prod_done = it + 1;
+            }
+            if (it + 2 < nit) load_raw(it + 2, w);
+        };
+        load_raw(0, w0);
+        if (nit > 1) load_raw(1, w1);
+        for (int it = 0; it < nit; it += 2) {
+            step(it, w0);
+            if (it + 1 < nit) step(it + 1, w1);
         }
-    } else if (warp == 8) {
+    } else if (warp == RT_EWARPS + RT_PWARPS) {
         // ================= MMA issue: one thread =================
         if (lane == 0) {
             const uint32_t a_hi = smem_u32(Ahi), a_lo = smem_u32(Alo);
@@ -286,19 +285,49 @@ k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L
                              ::"r"(smem_u32(&S.mma_done[b])) : "memory");
             }
         }
+    } else if (warp == RT_EWARPS + RT_PWARPS + 1) {
+        // ================= metadata: which stream and tile each of the group's 32 entries is, a few groups ahead =================
+        // q0 of tile t = kind + NK j is q0(kind) + j * (NK 128 M / L): no division per entry (NK 128 M is a multiple of L)
+        const long long q0k = ((long long)kind * RT_ROWS * M + D) / L, qstep = (long long)NK * RT_ROWS * M / L;
+        for (int it = 0; it < nit; it++) {
+            for (uint32_t spins = 0; S.prod_done < it - 3;) // slot it & 15: read last by the read-out of group it - 16, long finished
+                if (++spins > (1u << 26)) __trap();
+            const uint32_t e = (blockIdx.x + (uint32_t)it * gridDim.x) * RT_PAIRS + lane;
+            RtMeta m;
+            m.rows = 0;
+            m.in_n = 0;
+            m.in_off = m.base = m.out_off = 0;
+            int lo = S.job_cursor; // last job with pfx[job] <= e: a short walk from where the previous group started
+            __syncwarp();
+            if (e < npairs) {
+                while (lo + 1 < njobs && pfx[lo + 1] <= e) lo++;
+                const L3ResampleJob jb = jobs[lo];
+                const long long j = (long long)(e - pfx[lo]), t = kind + (long long)NK * j;
+                m.in_off = jb.in_off;
+                m.in_n = (int)jb.in_n;
+                m.base = q0k + j * qstep - (taps - 1);
+                m.out_off = jb.out_off + t * RT_ROWS * 2;
+                const long long left = jb.out_n - t * RT_ROWS;
+                m.rows = (int)(left < RT_ROWS ? left : RT_ROWS);
+            }
+            S.meta[it & (RT_META - 1)][lane] = m;
+            if (lane == 0) S.job_cursor = lo;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) S.meta_done = it + 1;
+        }
     } else {
         // ================= epilogue: row r = 32 warp + lane of the accumulator; frame i of the group = columns 2i, 2i + 1
         // (signal hi part) plus 64 + 2i, 64 + 2i + 1 (lo part) =================
-        const int r = warp * 32 + lane;
+        const int quarter = warp & 3, hcol = warp >> 2; // TMEM lanes 32 quarter .., signal columns 32 hcol .. (16 frames)
+        const int r = quarter * 32 + lane;
         for (int it = 0; it < nit; it++) {
             const int b = it & 1, k = it >> 1;
             rt_bar_wait(&S.mma_done[b], (uint32_t)k & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const RtMeta *mt = S.meta[it & (RT_META - 1)];
-#pragma unroll
-            for (int hcol = 0; hcol < 2; hcol++) {
-                uint32_t v[32], u[32];
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * RT_N + hcol * 32);
+            const RtMeta *mt = S.meta[it & (RT_META - 1)] + hcol * 16;
+            uint32_t v[32], u[32];
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * RT_N + hcol * 32);
 #define RT_LD32(dst, addr)                                                                                                     \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                     \
@@ -309,24 +338,23 @@ k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L
                    "=r"(dst[22]), "=r"(dst[23]), "=r"(dst[24]), "=r"(dst[25]), "=r"(dst[26]), "=r"(dst[27]), "=r"(dst[28]),    \
                    "=r"(dst[29]), "=r"(dst[30]), "=r"(dst[31])                                                                 \
                  : "r"(addr) : "memory")
-                RT_LD32(v, taddr);
-                RT_LD32(u, taddr + RT_COLS);
+            RT_LD32(v, taddr);
+            RT_LD32(u, taddr + RT_COLS);
 #undef RT_LD32
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const RtMeta &m = mt[hcol * 16 + i];
-                    int l16, r16;
-                    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(l16) : "f"(__uint_as_float(v[2 * i]) + __uint_as_float(u[2 * i])));
-                    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r16) : "f"(__uint_as_float(v[2 * i + 1]) + __uint_as_float(u[2 * i + 1])));
-                    if (r < m.rows)
-                        *reinterpret_cast<uint32_t *>(out + m.out_off + 2 * r) = ((uint32_t)l16 & 0xffffu) | ((uint32_t)r16 << 16);
-                }
-            }
-            // accumulator b (and this group's metadata) may be reused: after the stores, see the note at RT_META
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // the accumulator is in registers: the MMAs of the group after next may overwrite it
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) rt_bar_arrive(&S.tmem_free[b]);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const RtMeta &m = mt[i];
+                int l16, r16;
+                asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(l16) : "f"(fmaf(__uint_as_float(v[2 * i]), 256.f, __uint_as_float(u[2 * i]))));
+                asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r16) : "f"(fmaf(__uint_as_float(v[2 * i + 1]), 256.f, __uint_as_float(u[2 * i + 1]))));
+                if (r < m.rows)
+                    *reinterpret_cast<uint32_t *>(out + m.out_off + 2 * r) = ((uint32_t)l16 & 0xffffu) | ((uint32_t)r16 << 16);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -397,6 +425,7 @@ unsigned long long l3_resample_tc_prefix(const L3RsTcPlan &plan, const L3Resampl
         uint64_t run = 0;
         for (int j = 0; j < njobs; j++) {
             p[j] = (uint32_t)run;
+            if (jobs[j].channels == 2 && (jobs[j].in_n > 0x7fffffffll || jobs[j].out_n > 0x7fffffffll)) return 0; // (32-bit frame counts in the kernel)
             if (jobs[j].channels == 2 && jobs[j].out_n > 0) {
                 const long long ntile = (jobs[j].out_n + RT_ROWS - 1) / RT_ROWS;
                 if (ntile > k) run += (uint64_t)((ntile - k + plan.NK - 1) / plan.NK);
