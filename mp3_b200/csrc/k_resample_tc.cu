@@ -217,7 +217,11 @@ k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L
                 for (int f = 0; f < RT_LD; f++) {
                     const int x = lane + 32 * f;
                     const long long fi = base + x;
+#ifdef RT_DBG_NO_LOAD
+                    w[q][f] = (x < Kpad && fi >= 0 && fi < in_n) ? (uint32_t)fi : 0u;
+#else
                     w[q][f] = (x < Kpad && fi >= 0 && fi < in_n) ? __ldg(src + fi) : 0u;
+#endif
                 }
             }
         };
@@ -274,7 +278,11 @@ k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t bb = smem_u32(Bbuf + (size_t)b * b_bytes);
                 const uint32_t d = tmem + (uint32_t)b * RT_N;
+#ifdef RT_DBG_NO_MMA
+                for (int ks = 0; ks < 1; ks++) {
+#else
                 for (int ks = 0; ks < (Kpad >> 4); ks++) { // K step = 16 elements = two 16-byte chunks
+#endif
                     const uint64_t dah = make_desc(a_hi + 2 * ks * lbo_a, lbo_a, 128);
                     const uint64_t dal = make_desc(a_lo + 2 * ks * lbo_a, lbo_a, 128);
                     const uint64_t db = make_desc(bb + 2 * ks * RT_LBO_B, RT_LBO_B, 128);
@@ -352,7 +360,11 @@ k_resample_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, const L
                 int l16, r16;
                 asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(l16) : "f"(fmaf(__uint_as_float(v[2 * i]), 256.f, __uint_as_float(u[2 * i]))));
                 asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r16) : "f"(fmaf(__uint_as_float(v[2 * i + 1]), 256.f, __uint_as_float(u[2 * i + 1]))));
+#ifdef RT_DBG_NO_STORE
+                if (r < m.rows && l16 == 123456789)
+#else
                 if (r < m.rows)
+#endif
                     *reinterpret_cast<uint32_t *>(out + m.out_off + 2 * r) = ((uint32_t)l16 & 0xffffu) | ((uint32_t)r16 << 16);
             }
         }

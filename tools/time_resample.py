@@ -17,13 +17,13 @@ streams = synth.make_workload("cfg2", 1024, 383)
 audio = 1024 * 383 * 1152 / 44100.0
 res = {}
 outs = {}
-for tc in ("1", "0"):
+for tc in (("1",) if os.environ.get("RS_TC_ONLY") else ("1", "0")):
     os.environ["MP3B_RS_TC"] = tc
     dec = mp3_b200.Decoder(device=0)
     st = torch.cuda.Stream()
     dec.set_stream(st.cuda_stream)
     dec.decode_batch(streams)
-    for rate in (48000, 96000, 88200):
+    for rate in ([int(a) for a in sys.argv[1:]] or [48000, 96000, 88200]):
         for _ in range(2):
             dec.resample(rate)
         dec.sync()
@@ -41,6 +41,7 @@ for tc in ("1", "0"):
         if rate == 48000:
             outs[tc] = out[: 1 << 26].astype(np.int32)
     dec.close()
-d = np.abs(outs["1"] - outs["0"])
-res["agreement_48000"] = {"max_abs_diff_lsb": int(d.max()), "fraction_differing": float(np.mean(d != 0))}
+if "0" in outs and "1" in outs:
+    d = np.abs(outs["1"] - outs["0"])
+    res["agreement_48000"] = {"max_abs_diff_lsb": int(d.max()), "fraction_differing": float(np.mean(d != 0))}
 print(json.dumps(res))
