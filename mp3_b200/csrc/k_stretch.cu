@@ -91,7 +91,8 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
           int *__restrict__ offsets_out /* optional: chosen d per frame, [job][max_frames] */, int max_frames)
 {
     __shared__ __align__(16) signed char s_t[2 * TS_MAX_HS + 16];      // template: c[p_prev + Hs + k], k < N
-    __shared__ __align__(16) signed char s_r[3 * TS_MAX_HS + 16 + 16]; // region: c[a - R + i], i < N + 2 R (+ pad)
+    __shared__ __align__(16) signed char s_r[4 * TS_MAX_HS + 16 + 16]; // c[a - R + i]: the region (i < N + 2 R) and, behind it,
+                                                                       // what the template of a slowed-down stream reaches
     __shared__ __align__(16) signed char s_t2[TS_MAX_HS + 16];         // template, every second sample
     __shared__ __align__(16) signed char s_r2[3 * TS_MAX_HS / 2 + 32]; // region, every second sample
     __shared__ int s_best[TS_THREADS / 32], s_bestd[TS_THREADS / 32];
@@ -107,16 +108,30 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
     for (int k = tid; k < Hs; k += TS_THREADS) s_w[k] = 0.5f - 0.5f * cosf(wstep * (float)k);
     __syncthreads();
     long long p_prev = 0;
+    // nominal start a_m = floor(m Hs num / den), advanced exactly without a 64-bit division per segment
+    const int astep = Hs * num, aq = astep / den, ar = astep % den;
+    long long a = 0;
+    int arem = 0;
+    // The search region of a segment overlaps the previous one's (by 83 % at half speed), and the template -- the
+    // natural continuation of the previous frame -- starts (Hs - advance) + d + R bytes into it: the alignment signal
+    // is therefore kept in shared memory from segment to segment as ONE run c[ra .. ra + ULEN) that covers both, moved
+    // by the advance of `a`, and only its new tail is converted from the PCM: a few hundred samples per segment instead
+    // of 2,576.  (Speeds above 1 put the template in front of the run: it is then converted on its own, as before.)
+    const int ULEN = 4 * Hs + 16;    // region N + 2 R = 3 Hs, template reach up to Hs more, 16 bytes for the word reads
+    long long ra = 0;                // s_r holds c[ra .. ra + ULEN)
+    bool have_run = false;
     for (long long m = 0; m < nseg; m++) {
         long long p = 0;
         if (m > 0) {
-            const long long a = (m * Hs * (long long)num) / den, tpos = p_prev + Hs;
-            // alignment signal of the template and of the search region: 32-bit indices relative to the
-            // piece's first frame, the valid range [lo, hi) worked out once per piece
-            auto fill = [&](signed char *dst, signed char *dst2, long long start, int count, int padded) {
-                const int lo = (int)max(0ll, min(-start, (long long)count));
-                const int hi = (int)max(0ll, min(jb.in_n - start, (long long)count));
-                for (int i = tid; i < padded; i += TS_THREADS) {
+            a += aq;
+            arem += ar;
+            if (arem >= den) { arem -= den; a += 1; }
+            const long long tpos = p_prev + Hs, ra_new = a - R;
+            // alignment signal c[start + i], i in [i0, i1), into dst[i] (zero outside the stream)
+            auto fill = [&](signed char *dst, long long start, int i0, int i1) {
+                const int lo = (int)max((long long)i0, min(-start, (long long)i1));
+                const int hi = (int)max((long long)i0, min(jb.in_n - start, (long long)i1));
+                for (int i = i0 + tid; i < i1; i += TS_THREADS) {
                     int v = 0;
                     if (i >= lo && i < hi) {
                         const T *q = x + (start + i) * nch;
@@ -124,11 +139,55 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
                         v = max(-127, min(127, v));
                     }
                     dst[i] = (signed char)v;
-                    if (!(i & 1)) dst2[i >> 1] = (signed char)v;
                 }
             };
-            fill(s_t, s_t2, tpos, N, N);
-            fill(s_r, s_r2, a - R, N + 2 * R, N + 2 * R + 16);
+            unsigned *uw = reinterpret_cast<unsigned *>(s_r);
+            // ---- (A) move the run by delta = ra_new - ra bytes (through registers: it overlaps itself), (B) convert the
+            // new tail
+            const long long delta = ra_new - ra;
+            const bool shift = have_run && delta >= 0 && delta < ULEN;
+            const int keepw = shift ? (int)((ULEN - delta) >> 2) : 0; // whole words that survive
+            constexpr int UW = (4 * TS_MAX_HS + 16) / 4 / TS_THREADS + 1; // words per thread
+            unsigned kept[UW];
+            {
+                const int w0 = (int)(delta >> 2);
+                const unsigned sh = (unsigned)(delta & 3) * 8u;
+#pragma unroll
+                for (int q = 0; q < UW; q++) {
+                    const int i = tid + q * TS_THREADS;
+                    kept[q] = i < keepw ? __funnelshift_r(uw[w0 + i], uw[w0 + i + 1], sh) : 0u;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < UW; q++) {
+                const int i = tid + q * TS_THREADS;
+                if (i < keepw) uw[i] = kept[q];
+            }
+            fill(s_r, ra_new, keepw * 4, ULEN);
+            ra = ra_new;
+            have_run = true;
+            __syncthreads();
+            // ---- (C) the template out of the run (or from the PCM when it is not inside), every-second-sample copies
+            const long long toff = tpos - ra_new;
+            const bool t_in_run = toff >= 0 && toff + N <= ULEN - 4;
+            if (t_in_run) {
+                const int w0 = (int)(toff >> 2);
+                const unsigned sh = (unsigned)(toff & 3) * 8u;
+                for (int w = tid; w < N / 4; w += TS_THREADS)
+                    reinterpret_cast<unsigned *>(s_t)[w] = __funnelshift_r(uw[w0 + w], uw[w0 + w + 1], sh);
+                for (int w = tid; w < N / 8; w += TS_THREADS) {
+                    const unsigned t0 = __funnelshift_r(uw[w0 + 2 * w], uw[w0 + 2 * w + 1], sh);
+                    const unsigned t1 = __funnelshift_r(uw[w0 + 2 * w + 1], uw[w0 + 2 * w + 2], sh);
+                    reinterpret_cast<unsigned *>(s_t2)[w] = __byte_perm(t0, t1, 0x6420);
+                }
+            } else {
+                fill(s_t, tpos, 0, N);
+                __syncthreads();
+                const unsigned *tw = reinterpret_cast<const unsigned *>(s_t);
+                for (int w = tid; w < N / 8; w += TS_THREADS) reinterpret_cast<unsigned *>(s_t2)[w] = __byte_perm(tw[2 * w], tw[2 * w + 1], 0x6420);
+            }
+            for (int w = tid; w < (N + 2 * R + 16) / 8; w += TS_THREADS) reinterpret_cast<unsigned *>(s_r2)[w] = __byte_perm(uw[2 * w], uw[2 * w + 1], 0x6420);
             __syncthreads();
             // ---- coarse: candidates d = -R + 4 j, every second sample; region byte 4 j = decimated byte 2 j
             int best = INT_MIN, bestd = 0;
