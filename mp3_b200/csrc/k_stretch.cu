@@ -95,7 +95,7 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
                                                                        // what the template of a slowed-down stream reaches
     __shared__ __align__(16) signed char s_t2[TS_MAX_HS + 16];         // template, every second sample
     __shared__ __align__(16) signed char s_r2[3 * TS_MAX_HS / 2 + 32]; // region, every second sample
-    __shared__ int s_best[TS_THREADS / 32], s_bestd[TS_THREADS / 32];
+    __shared__ unsigned long long s_key[2]; // arg max of the coarse / fine search: score (order-preserving) << 32 | ~candidate
     __shared__ long long s_p;
     __shared__ float s_w[TS_MAX_HS]; // the cross-fade window, once per CTA
     const L3StretchJob jb = jobs[blockIdx.x];
@@ -142,6 +142,7 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
                 }
             };
             unsigned *uw = reinterpret_cast<unsigned *>(s_r);
+            if (tid == 0) s_key[0] = s_key[1] = 0ull; // (read last behind the previous segment's searches; next written after two barriers)
             // ---- (A) move the run by delta = ra_new - ra bytes (through registers: it overlaps itself), (B) convert the
             // new tail
             const long long delta = ra_new - ra;
@@ -189,47 +190,54 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
             }
             for (int w = tid; w < (N + 2 * R + 16) / 8; w += TS_THREADS) reinterpret_cast<unsigned *>(s_r2)[w] = __byte_perm(uw[2 * w], uw[2 * w + 1], 0x6420);
             __syncthreads();
-            // ---- coarse: candidates d = -R + 4 j, every second sample; region byte 4 j = decimated byte 2 j
+            // ---- coarse: candidates d = -R + 4 j, every second sample; region byte 4 j = decimated byte 2 j.  A thread
+            // scores the candidates 2 i and 2 i + 1: they read the same words of the decimated region (byte offsets 4 i and
+            // 4 i + 2), so every load serves two dot products.
             int best = INT_MIN, bestd = 0;
+            const int ncand = R / 2 + 1; // 4 j <= 2 R
+            const int i = tid >> 1, h = tid & 1;
             {
+                // (the dot products are the serial part of a segment: each pair of candidates is split over two adjacent
+                // lanes -- the halves of the template -- and every lane keeps two accumulators per candidate)
                 const int *tw = reinterpret_cast<const int *>(s_t2);
-                for (int j = tid; 4 * j <= 2 * R; j += TS_THREADS) {
-                    const unsigned *rw = reinterpret_cast<const unsigned *>(s_r2) + (j >> 1);
-                    const unsigned sh = (unsigned)(j & 1) * 16u;
-                    int acc = 0;
+                const int kh = N / 16; // words per half
+                int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+                if (2 * i < ncand) {
+                    const unsigned *rw = reinterpret_cast<const unsigned *>(s_r2) + i + h * kh;
+                    const int *tq = tw + h * kh;
                     unsigned lo = rw[0];
-#pragma unroll 8
-                    for (int k = 0; k < N / 8; k++) { // N / 8 is 32, 64 or 128
-                        const unsigned hi = rw[k + 1];
-                        acc = __dp4a((int)__funnelshift_r(lo, hi, sh), tw[k], acc);
+#pragma unroll 4
+                    for (int k = 0; k < kh; k += 2) { // kh is 16, 32 or 64
+                        const unsigned mid = rw[k + 1], hi = rw[k + 2];
+                        const int t0 = tq[k], t1 = tq[k + 1];
+                        a0 = __dp4a((int)lo, t0, a0);
+                        a1 = __dp4a((int)__funnelshift_r(lo, mid, 16u), t0, a1);
+                        b0 = __dp4a((int)mid, t1, b0);
+                        b1 = __dp4a((int)__funnelshift_r(mid, hi, 16u), t1, b1);
                         lo = hi;
                     }
-                    if (acc > best) { best = acc; bestd = j; }
+                }
+                int acc0 = a0 + b0, acc1 = a1 + b1;
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); // (all lanes: the pair's two halves)
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+                if (h == 0 && 2 * i < ncand) {
+                    if (acc0 > best) { best = acc0; bestd = 2 * i; }               // (first maximum: the smaller index wins ties)
+                    if (2 * i + 1 < ncand && acc1 > best) { best = acc1; bestd = 2 * i + 1; }
                 }
             }
-            auto cta_argmax = [&]() { // larger score, then smaller candidate index; result in s_best[0] / s_bestd[0]
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int ob = __shfl_xor_sync(0xffffffffu, best, o), od = __shfl_xor_sync(0xffffffffu, bestd, o);
-                    if (ob > best || (ob == best && od < bestd)) { best = ob; bestd = od; }
+            // arg max over the CTA: larger score, then smaller candidate index, as one unsigned 64-bit maximum
+            {
+                const bool has = best != INT_MIN || (h == 0 && 2 * i < ncand);
+                const unsigned us = has ? (unsigned)best ^ 0x80000000u : 0u;
+                if (warp * 32 < 2 * ((ncand + 1) / 2)) { // (warp-uniform: the warps that hold candidates)
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, us);
+                    const unsigned mi = __reduce_min_sync(0xffffffffu, has && us == mx ? (unsigned)bestd : 0xffffffffu);
+                    if (lane == 0) atomicMax(&s_key[0], ((unsigned long long)mx << 32) | (0xffffffffu - mi));
                 }
-                if (lane == 0) { s_best[warp] = best; s_bestd[warp] = bestd; }
-                __syncthreads();
-                if (tid == 0) {
-                    int bb = s_best[0], dd = s_bestd[0];
-                    for (int w = 1; w < TS_THREADS / 32; w++)
-                        if (s_best[w] > bb || (s_best[w] == bb && s_bestd[w] < dd)) { bb = s_best[w]; dd = s_bestd[w]; }
-                    s_best[0] = bb;
-                    s_bestd[0] = dd;
-                }
-                __syncthreads();
-            };
-            cta_argmax();
-            const int c0 = 4 * s_bestd[0]; // coarse winner as a region byte offset (d0 = c0 - R)
+            }
             __syncthreads();
+            const int c0 = 4 * (int)(0xffffffffu - (unsigned)(s_key[0] & 0xffffffffull)); // coarse winner as a region byte offset (d0 = c0 - R)
             // ---- fine: candidates c0 - 3 .. c0 + 3 (clipped to 0 .. 2 R) in full, one warp each
-            best = INT_MIN;
-            bestd = 0;
             if (warp < 7) {
                 const int c = c0 - 3 + warp;
                 if (c >= 0 && c <= 2 * R) {
@@ -239,15 +247,14 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
                     int acc = 0;
                     for (int k = lane; k < N / 4; k += 32)
                         acc = __dp4a((int)__funnelshift_r(rw[k], rw[k + 1], sh), tw[k], acc);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    best = acc;
-                    bestd = c;
+                    acc = __reduce_add_sync(0xffffffffu, acc);
+                    if (lane == 0)
+                        atomicMax(&s_key[1], ((unsigned long long)((unsigned)acc ^ 0x80000000u) << 32) | (0xffffffffu - (unsigned)c));
                 }
             }
-            cta_argmax();
+            __syncthreads();
             if (tid == 0) {
-                const int d = s_bestd[0] - R;
+                const int d = (int)(0xffffffffu - (unsigned)(s_key[1] & 0xffffffffull)) - R;
                 s_p = a + d;
                 if (offsets_out && m < max_frames) offsets_out[(size_t)blockIdx.x * max_frames + m] = d;
             }
