@@ -48,10 +48,10 @@ template <> __device__ __forceinline__ void ts_load_frame<int16_t>(const int16_t
 {
     if (nch == 2) {
         const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
-        l = (float)(short)(w & 0xffffu) * (1.f / 32768.f);
-        r = (float)((int)w >> 16) * (1.f / 32768.f);
+        l = (float)(short)(w & 0xffffu); // (s16 units: the cross-fade is linear, the scale cancels)
+        r = (float)((int)w >> 16);
     } else
-        l = (float)*p * (1.f / 32768.f);
+        l = (float)*p;
 }
 template <> __device__ __forceinline__ void ts_load_frame<float>(const float *p, int nch, float &l, float &r)
 {
@@ -65,9 +65,9 @@ template <> __device__ __forceinline__ void ts_load_frame<float>(const float *p,
 __device__ __forceinline__ void ts_store_frame(int16_t *p, int nch, float l, float r)
 {
     int a, b;
-    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(a) : "f"(l * 32768.f));
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(a) : "f"(l));
     if (nch == 2) {
-        asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(b) : "f"(r * 32768.f));
+        asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(b) : "f"(r));
         *reinterpret_cast<uint32_t *>(p) = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
     } else
         *p = (int16_t)a;
@@ -277,8 +277,8 @@ k_stretch(const T *__restrict__ in, T *__restrict__ out, const L3StretchJob *__r
                 if (m > 0) {
                     if (k >= blo && k < bhi) ts_load_frame<T>(x + (sb + k) * nch, nch, b0, b1);
                     const float w = s_w[k];
-                    v0 = (1.f - w) * b0 + w * a0;
-                    v1 = (1.f - w) * b1 + w * a1;
+                    v0 = fmaf(w, a0 - b0, b0); // (1 - w) b + w a
+                    v1 = fmaf(w, a1 - b1, b1);
                 }
                 ts_store_frame(y + (o0 + k) * nch, nch, v0, v1);
             }
