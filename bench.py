@@ -407,6 +407,8 @@ def run_ours(args, rank, world):
     sweep = None
     if args.workload == "cfg2" and not args.no_sweep:
         sweep = run_sweep_cfg5(args, torch, mp3_b200, dec, tstream, barrier, rank, world)
+    global CFG1_LATENCY
+    CFG1_LATENCY = run_cfg1_latency(mp3_b200, local, streams[0]) if (rank == 0 and not args.no_e2e) else None
     finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, e2e, stage_ms,
            launches, sampler, gen_s, checksum, strong, numa, (parity_n, parity_worst), sweep, infos)
 
@@ -467,6 +469,26 @@ def run_e2e(args, torch, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstr
     except Exception as e:  # noqa: BLE001
         floor = {"ms": None, "error": str(e)[:200]}
     return {"ms": ms_e2e, "ms_h2d_only": ms_h2d, "floor": floor}, checksum
+
+
+CFG1_LATENCY = None
+
+
+def run_cfg1_latency(mp3_b200, device, stream_bytes):
+    """BASELINE.json configs[0] on the GPU: ONE 10-s stream, pageable host bytes in -> host PCM out through the batch
+    call of the C-ABI, wall clock around the calls (median of 20 after 3 warm-ups).  The player's actual case."""
+    with mp3_b200.Decoder(device=device, pcm_format=mp3_b200.PCM_S16) as d1:
+        lat = []
+        for _ in range(23):
+            t0 = time.perf_counter()
+            d1.decode_batch([stream_bytes])
+            pcm = d1.fetch_pcm()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        inf = d1.stream_info(0)
+        audio = inf.samples / float(inf.sample_rate)
+    med = float(np.median(lat[3:]))
+    return {"workload": "cfg1: one %.1f-s stream, host bytes in -> host s16 PCM out (mp3b_decode_batch + fetch)" % audio,
+            "ms_median": med, "ms_min": float(min(lat[3:])), "x_realtime": audio / (med * 1e-3), "pcm_samples": int(pcm.size)}
 
 
 def run_sweep_cfg5(args, torch, mp3_b200, dec, tstream, barrier, rank, world):
@@ -678,6 +700,7 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
                                         "same process, all ranks at once); floor / e2e = 1 means transfer bound"}
                     if ms_e2e == ms_e2e else None),
             "gpu_launches": int(launches * args.steps),
+            "cfg1_latency": CFG1_LATENCY,
             "clocks": sampler.result(),
             "gen_seconds": gen_s, "pcm_checksum": checksum,
         }
