@@ -780,3 +780,277 @@ size_t l3gen_stream(const l3gen_cfg *c, uint8_t *out, size_t cap)
     free(fr);
     return o;
 }
+
+/* =====================================================================================================================
+ * l3enc_stream: a small ENCODER of real signals, so that the decoders (oracle, CUDA path, FFmpeg) also see streams
+ * whose statistics come from audio and not from a random generator: s16 PCM in, MPEG-1 Layer III out (32 / 44.1 / 48
+ * kHz, mono or plain stereo, CBR with the bit reservoir in use, long blocks, all scalefactors zero).  It is the
+ * encoding process of ISO/IEC 11172-3 Annex C read backwards from the decoder: polyphase analysis with the window
+ * C[i] = D[i] / 32, frequency inversion, 36-point MDCT with the sine window, alias butterflies, power-law quantiser
+ * with one global gain per granule and channel found by bisection against the bit budget, Huffman table per region by
+ * exhaustive bit count.  No psychoacoustic model: the quantisation noise is white inside a granule, which is enough for
+ * what the tests ask of it -- a stream a third-party decoder reconstructs to the input signal within the noise the bit
+ * rate allows, with real big_values / count1 / reservoir statistics.  Test infrastructure, like the generator above.
+ * ===================================================================================================================== */
+typedef struct {
+    double fifo[512];      /* analysis input, newest sample first */
+    double prev[32][18];   /* previous granule's subband samples (MDCT overlap) */
+} enc_ch;
+
+static void enc_analysis(enc_ch *e, const double *in32 /* 32 new samples, oldest first */, double *S /* 32 */)
+{
+    memmove(e->fifo + 32, e->fifo, sizeof(double) * 480);
+    for (int i = 0; i < 32; i++) e->fifo[31 - i] = in32[i];
+    double y[64];
+    for (int i = 0; i < 64; i++) {
+        double a = 0.0;
+        for (int j = 0; j < 8; j++) {
+            const int idx = i + 64 * j; /* C[i] = D[i] / 32 (11172-3 Table C.1 against Table B.3) */
+            a += l3_dwin(idx) / 32.0 * e->fifo[idx];
+        }
+        y[i] = a;
+    }
+    for (int k = 0; k < 32; k++) {
+        double a = 0.0;
+        for (int i = 0; i < 64; i++) a += cos((2 * k + 1) * (i - 16) * M_PI / 64.0) * y[i];
+        S[k] = a;
+    }
+}
+
+/* one granule of one channel: 576 PCM samples -> 576 spectral lines */
+static void enc_granule_spectrum(enc_ch *e, const double *pcm576, double *xr /* 576 */)
+{
+    static double cur[32][18];
+    for (int t = 0; t < 18; t++) {
+        double S[32];
+        enc_analysis(e, pcm576 + 32 * t, S);
+        for (int sb = 0; sb < 32; sb++) cur[sb][t] = ((sb & 1) && (t & 1)) ? -S[sb] : S[sb]; /* frequency inversion */
+    }
+    for (int sb = 0; sb < 32; sb++) {
+        double in[36];
+        for (int n = 0; n < 18; n++) { in[n] = e->prev[sb][n]; in[18 + n] = cur[sb][n]; }
+        for (int k = 0; k < 18; k++) {
+            double a = 0.0;
+            for (int n = 0; n < 36; n++)
+                a += sin(M_PI / 36.0 * (n + 0.5)) * in[n] * cos(M_PI / 72.0 * (2 * n + 1 + 18) * (2 * k + 1));
+            xr[sb * 18 + k] = a / 9.0;
+        }
+        memcpy(e->prev[sb], cur[sb], sizeof e->prev[sb]);
+    }
+    for (int sb = 1; sb < 32; sb++) /* alias butterflies: the inverse rotation of the decoder's */
+        for (int i = 0; i < 8; i++) {
+            double ci = l3_alias_ci[i], cs = 1.0 / sqrt(1.0 + ci * ci), ca = ci / sqrt(1.0 + ci * ci);
+            double lo = xr[sb * 18 - 1 - i], hi = xr[sb * 18 + i];
+            xr[sb * 18 - 1 - i] = lo * cs + hi * ca;
+            xr[sb * 18 + i] = hi * cs - lo * ca;
+        }
+}
+
+static int enc_best_table(const int *ix, int lo, int hi, int *bits_out)
+{
+    int mx = 0;
+    for (int i = lo; i < hi; i++) if (abs(ix[i]) > mx) mx = abs(ix[i]);
+    if (lo >= hi || mx == 0) { *bits_out = 0; return 0; }
+    int best = -1, bb = 1 << 30;
+    for (int t = 1; t < 32; t++) {
+        if (t == 4 || t == 14) continue;
+        int book = l3_book_of_table[t], lin = l3_linbits_of_table[t];
+        const uint8_t *hl;
+        const uint32_t *hc;
+        int dim = l3_book(book, &hl, &hc);
+        if (!dim) continue;
+        int cap = lin ? 15 + ((1 << lin) - 1) : dim - 1;
+        if (mx > cap) continue;
+        int b = 0;
+        for (int i = lo; i < hi; i += 2) b += pair_bits(t, ix[i], ix[i + 1]);
+        if (b < bb) { bb = b; best = t; }
+    }
+    *bits_out = bb;
+    return best;
+}
+
+typedef struct { int bv2, c1end, r1, r2, a, c, tsel[3], c1tab, bits; } enc_plan;
+
+/* bits of the quantised spectrum with the best tables; fills the plan */
+static int enc_count(const int *ix, int row, enc_plan *p)
+{
+    int last = 576;
+    while (last > 0 && ix[last - 1] == 0) last--;
+    last = (last + 1) & ~1;
+    int c1end = (last + 3) & ~3;
+    if (c1end > 576) c1end = 576;
+    /* count1 region: quadruples from the top whose magnitudes are all <= 1 */
+    int bv2 = c1end;
+    while (bv2 >= 4 && abs(ix[bv2 - 1]) <= 1 && abs(ix[bv2 - 2]) <= 1 && abs(ix[bv2 - 3]) <= 1 && abs(ix[bv2 - 4]) <= 1) bv2 -= 4;
+    if (bv2 > 576) bv2 = 576;
+    p->bv2 = bv2;
+    p->c1end = c1end;
+    /* region boundaries at scalefactor-band edges near the thirds of big_values */
+    const uint16_t *sfb = l3_sfb_long[row];
+    int a = 1, c = 2;
+    for (int k = 1; k <= 16; k++) if (sfb[k] <= bv2 / 3 || k == 1) a = k;
+    for (int k = a + 1; k <= a + 8 && k <= 22; k++) if (sfb[k] <= 2 * bv2 / 3 || k == a + 1) c = k;
+    p->a = a;
+    p->c = c;
+    p->r1 = sfb[a] < bv2 ? sfb[a] : bv2;
+    p->r2 = sfb[c] < bv2 ? sfb[c] : bv2;
+    int b0, b1, b2;
+    p->tsel[0] = enc_best_table(ix, 0, p->r1, &b0);
+    p->tsel[1] = enc_best_table(ix, p->r1, p->r2, &b1);
+    p->tsel[2] = enc_best_table(ix, p->r2, bv2, &b2);
+    if (p->tsel[0] < 0 || p->tsel[1] < 0 || p->tsel[2] < 0) return 1 << 30; /* a value no table can hold */
+    int ca = 0, cb = 0;
+    for (int i = bv2; i < c1end; i += 4) {
+        int sym = (ix[i] != 0) << 3 | (ix[i + 1] != 0) << 2 | (ix[i + 2] != 0) << 1 | (ix[i + 3] != 0);
+        int ns = (ix[i] != 0) + (ix[i + 1] != 0) + (ix[i + 2] != 0) + (ix[i + 3] != 0);
+        ca += l3_quad_hlen[0][sym] + ns;
+        cb += l3_quad_hlen[1][sym] + ns;
+    }
+    p->c1tab = cb < ca;
+    p->bits = b0 + b1 + b2 + (cb < ca ? cb : ca);
+    return p->bits;
+}
+
+static int enc_quantise(const double *xr, int gg, int *ix)
+{
+    const double step = pow(2.0, -(gg - 210) * 3.0 / 16.0);
+    int mx = 0;
+    for (int i = 0; i < 576; i++) {
+        int q = (int)(pow(fabs(xr[i]), 0.75) * step + 0.4054);
+        if (q > 8191 + 15) q = 8191 + 15 + 1; /* marks "too fine" */
+        ix[i] = xr[i] < 0 ? -q : q;
+        if (q > mx) mx = q;
+    }
+    return mx;
+}
+
+/* pcm: interleaved s16, nsamples per channel.  Returns bytes written (0: bad arguments / buffer too small). */
+size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, int kbps, uint8_t *out, size_t cap)
+{
+    int row = -1;
+    for (int i = 0; i < 3; i++) if ((int)l3_sample_rate[i] == sample_rate) row = i;
+    const int bri = bitrate_index(0, kbps);
+    if (row < 0 || bri < 0 || (nch != 1 && nch != 2) || nsamples <= 0) return 0;
+    const int nframes = (nsamples + 1151) / 1152 + 1; /* one more frame flushes the filterbank's delay */
+    const int side_len = nch == 1 ? 17 : 32;
+    size_t lcap = (size_t)(144 * kbps * 1000 / sample_rate + 1) * nframes + 1024;
+    uint8_t *logical = (uint8_t *)calloc(lcap, 1);
+    typedef struct { uint8_t hdr[4]; uint8_t side[32]; int payload; } efr_t;
+    efr_t *fr = (efr_t *)calloc((size_t)nframes, sizeof(efr_t));
+    enc_ch *ech = (enc_ch *)calloc(2, sizeof(enc_ch));
+    size_t lstart = 0, wcur = 0;
+    long pad_rest = 0;
+    double e_avg = 0.0;
+    for (int f = 0; f < nframes; f++) {
+        int pad = 0;
+        long num = 144L * kbps * 1000;
+        pad_rest -= num % sample_rate;
+        if (pad_rest < 0) { pad = 1; pad_rest += sample_rate; }
+        const int frame_len = 144 * kbps * 1000 / sample_rate + pad, payload = frame_len - 4 - side_len;
+        size_t tail = lstart - wcur;
+        const int mdb = tail > 511 ? 511 : (int)tail;
+        const size_t dstart = lstart - (size_t)mdb;
+        long avail = 8L * (mdb + payload);
+        bitw w = {logical, lcap * 8, dstart * 8};
+        const size_t wstart = w.pos;
+        gr_side gs[2][2];
+        int u = 0;
+        for (int gr = 0; gr < 2; gr++)
+            for (int ch = 0; ch < nch; ch++, u++) {
+                double x[576], xr[576];
+                double energy = 0.0;
+                for (int i = 0; i < 576; i++) {
+                    const long n = (long)f * 1152 + gr * 576 + i;
+                    x[i] = n < nsamples ? pcm[n * nch + ch] / 32768.0 : 0.0;
+                }
+                enc_granule_spectrum(&ech[ch], x, xr);
+                for (int i = 0; i < 576; i++) energy += xr[i] * xr[i];
+                /* budget: the mean of what is left, more for loud granules, less for quiet ones (those feed the reservoir) */
+                const long left = avail - (long)(w.pos - wstart);
+                long budget = left / (2 * nch - u);
+                e_avg = e_avg * 0.9 + energy * 0.1;
+                double fac = e_avg > 0.0 ? sqrt(energy / e_avg) : 1.0;
+                if (fac < 0.5) fac = 0.5;
+                if (fac > 1.5) fac = 1.5;
+                budget = (long)(budget * fac);
+                if (budget > left) budget = left;
+                if (budget > 4095) budget = 4095;
+                /* finest global gain whose spectrum fits: bits fall as the gain rises */
+                int ix[576], lo = 0, hi = 255, best_gg = 255;
+                enc_plan plan, best_plan;
+                memset(&best_plan, 0, sizeof best_plan);
+                while (lo <= hi) {
+                    const int gg = (lo + hi) / 2;
+                    const int mx = enc_quantise(xr, gg, ix);
+                    const int bits = mx > 8191 + 15 ? (1 << 30) : enc_count(ix, row, &plan);
+                    if (bits <= budget) { best_gg = gg; best_plan = plan; hi = gg - 1; }
+                    else lo = gg + 1;
+                }
+                enc_quantise(xr, best_gg, ix);
+                if (enc_count(ix, row, &best_plan) > budget) { /* (not even the coarsest fits: silence) */
+                    memset(ix, 0, sizeof ix);
+                    enc_count(ix, row, &best_plan);
+                }
+                gr_side *s = &gs[gr][ch];
+                memset(s, 0, sizeof *s);
+                s->global_gain = best_gg;
+                s->big_values = best_plan.bv2 / 2;
+                s->table_select[0] = best_plan.tsel[0];
+                s->table_select[1] = best_plan.tsel[1];
+                s->table_select[2] = best_plan.tsel[2];
+                s->region0_count = best_plan.a - 1;
+                s->region1_count = best_plan.c - best_plan.a - 1;
+                s->count1table = best_plan.c1tab;
+                const size_t p0 = w.pos;
+                for (int i = 0; i < best_plan.bv2; i += 2)
+                    put_pair(&w, best_plan.tsel[i < best_plan.r1 ? 0 : (i < best_plan.r2 ? 1 : 2)], ix[i], ix[i + 1]);
+                for (int i = best_plan.bv2; i < best_plan.c1end; i += 4) {
+                    const int sym = (ix[i] != 0) << 3 | (ix[i + 1] != 0) << 2 | (ix[i + 2] != 0) << 1 | (ix[i + 3] != 0);
+                    putbits(&w, l3_quad_hcod[best_plan.c1tab][sym], l3_quad_hlen[best_plan.c1tab][sym]);
+                    for (int k = 0; k < 4; k++) if (ix[i + k]) putbits(&w, ix[i + k] < 0, 1);
+                }
+                s->part2_3_length = (int)(w.pos - p0);
+            }
+        wcur = dstart + (w.pos - wstart + 7) / 8;
+        uint8_t *h = fr[f].hdr;
+        h[0] = 0xFF;
+        h[1] = (uint8_t)(0xE0 | (3 << 3) | (1 << 1) | 1);
+        h[2] = (uint8_t)((bri << 4) | (row << 2) | (pad << 1));
+        h[3] = (uint8_t)((nch == 1 ? 3 : 0) << 6);
+        bitw sw = {fr[f].side, (size_t)side_len * 8, 0};
+        putbits(&sw, (unsigned)mdb, 9);
+        putbits(&sw, 0, nch == 1 ? 5 : 3);
+        for (int ch = 0; ch < nch; ch++) putbits(&sw, 0, 4);
+        for (int gr = 0; gr < 2; gr++)
+            for (int ch = 0; ch < nch; ch++) {
+                const gr_side *s = &gs[gr][ch];
+                putbits(&sw, (unsigned)s->part2_3_length, 12);
+                putbits(&sw, (unsigned)s->big_values, 9);
+                putbits(&sw, (unsigned)s->global_gain, 8);
+                putbits(&sw, 0, 4);  /* scalefac_compress 0: no scalefactor bits */
+                putbits(&sw, 0, 1);  /* window_switching_flag */
+                for (int k = 0; k < 3; k++) putbits(&sw, (unsigned)s->table_select[k], 5);
+                putbits(&sw, (unsigned)s->region0_count, 4);
+                putbits(&sw, (unsigned)s->region1_count, 3);
+                putbits(&sw, 0, 1);  /* preflag */
+                putbits(&sw, 0, 1);  /* scalefac_scale */
+                putbits(&sw, (unsigned)s->count1table, 1);
+            }
+        fr[f].payload = payload;
+        lstart += (size_t)payload;
+    }
+    size_t o = 0, lp = 0;
+    for (int f = 0; f < nframes; f++) {
+        const size_t need = 4 + (size_t)side_len + (size_t)fr[f].payload;
+        if (o + need > cap) { o = 0; break; }
+        memcpy(out + o, fr[f].hdr, 4);
+        memcpy(out + o + 4, fr[f].side, (size_t)side_len);
+        memcpy(out + o + 4 + side_len, logical + lp, (size_t)fr[f].payload);
+        o += need;
+        lp += (size_t)fr[f].payload;
+    }
+    free(logical);
+    free(fr);
+    free(ech);
+    return o;
+}
