@@ -485,11 +485,29 @@ __device__ __forceinline__ uint32_t decode_pairs(R &br, uint32_t start, const L3
 }
 
 // ---------------------------------------------------------------- part 3b: count1 quadruples (a5)
-// code (<= 6 bits) + up to 4 sign bits per iteration; returns the line index after the last one
+// code (<= 6 bits) + up to 4 sign bits per iteration; returns the line index after the last one.
+// Real music has long count1 regions (the +-1 lines of the upper bands: 300 lines per granule at 128 kbit/s, where the
+// generator's random spectra have 45), and with a thread per unit every store instruction touches 32 different units:
+// two 4-byte stores per quadruple made this loop store-bound (135 SM cycles per warp and quadruple).  The quadruples are
+// therefore collected in a 16-byte register window and leave as one 16-byte store per two of them: a quadruple's two
+// words go to word position (i >> 1) & 3 of the window -- by selects, the position differs between lanes --, the window
+// is stored when its last word has been written, and it starts out with the words the pair loop left in that vector.
+// On return the vector that holds line i has been written completely (zeros behind the data).
 template <class R, class SH>
 __device__ __forceinline__ int decode_count1(R &br, uint32_t limit, int i, uint32_t qoff, const SH &S,
                                              uint32_t *__restrict__ out32)
 {
+    uint4 *out = reinterpret_cast<uint4 *>(out32);
+    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    {
+        const int wp = (i >> 1) & 3; // words of the current vector that the pair loop has written already
+        if (wp) {
+            const uint4 cur = out[i >> 3];
+            v0 = cur.x;
+            v1 = wp > 1 ? cur.y : 0u;
+            v2 = wp > 2 ? cur.z : 0u;
+        }
+    }
     while (i <= 572 && br.bitpos() < limit) {
         const uint32_t bits = br.peek32();
         const uint32_t e = S.quad[qoff + (bits >> 26)];
@@ -498,10 +516,19 @@ __device__ __forceinline__ int decode_count1(R &br, uint32_t limit, int i, uint3
         br.skip((int)(len + __popc(sym)));
         if (br.bitpos() > limit) break; // overran part2_3_length: discard this quadruple
         const uint2 vw = S.c1[(sym << 4) | s4];
-        out32[i >> 1] = vw.x;
-        out32[(i >> 1) + 1] = vw.y;
+        const int wp = (i >> 1) & 3;
+        v0 = wp == 0 ? vw.x : v0;
+        v1 = wp == 0 ? vw.y : (wp == 1 ? vw.x : v1);
+        v2 = wp == 1 ? vw.y : (wp == 2 ? vw.x : v2);
+        v3 = wp == 2 ? vw.y : (wp == 3 ? vw.x : v3);
+        if (wp >= 2) { // the vector is complete
+            out[i >> 3] = make_uint4(v0, v1, v2, v3);
+            v0 = wp == 3 ? vw.y : 0u; // (the quadruple's second word opens the next vector)
+            v1 = v2 = v3 = 0u;
+        }
         i += 4;
     }
+    if ((i >> 1) & 3) out[i >> 3] = make_uint4(v0, v1, v2, v3); // the last, partly filled vector: zeros behind the data
     return i;
 }
 
@@ -682,8 +709,10 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         const uint32_t used = stw & 0x1fffu, p23 = d.p23len;
         int i = (int)((stw >> 13) & 0x3ffu);
         uint32_t *out32 = reinterpret_cast<uint32_t *>(is_out + (size_t)u * 576);
+        bool c1 = false; // decode_count1 ran: it completes the last vector itself
         if (!(stw & 0x80000000u) && used < p23) {
             const uint32_t qoff = (d.flags & L3F_C1TAB) ? 64u : 0u;
+            c1 = true;
             if (staged) {
                 StageReader br;
                 br.init(stage, (uint32_t)(d.bit_off - a0 * 8) + used, a0 * 8, span * 8);
@@ -698,7 +727,8 @@ k_huffman(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const L3UnitD
         // nzv_out[u] tells the consumer how many 16-byte vectors (8 lines each) hold data, and it treats
         // the rest as zero.  zero_fill (staged pipeline, parity dumps) writes the tail anyway.
         const int nst = (i + 7) >> 3;
-        for (int k = i >> 1; k < nst * 4; k++) out32[k] = 0u;
+        if (!c1)
+            for (int k = i >> 1; k < nst * 4; k++) out32[k] = 0u;
         nzv_out[u] = (uint8_t)nst;
         if (zero_fill) {
             uint4 *out = reinterpret_cast<uint4 *>(out32);
@@ -921,10 +951,12 @@ k_huffman_sorted(const uint8_t *__restrict__ arena, uint64_t arena_bytes, const 
                 } else {
                     int i = (int)((stw >> 13) & 0x3ffu);
                     if (work) i = decode_count1(br, br.bitpos() + ((uint32_t)d.p23len - used), i, (d.flags & L3F_C1TAB) ? 64u : 0u, S, out32);
-                    // zero the rest of the last 16-byte vector; the all-zero tail of the spectrum is not written:
-                    // nzv_out[u] tells the consumer how many vectors hold data (zero_fill: staged pipeline, parity dumps)
+                    // zero the rest of the last 16-byte vector (decode_count1 does it itself); the all-zero tail of the
+                    // spectrum is not written: nzv_out[u] tells the consumer how many vectors hold data (zero_fill:
+                    // staged pipeline, parity dumps)
                     const int nst = (i + 7) >> 3;
-                    for (int k = i >> 1; k < nst * 4; k++) out32[k] = 0u;
+                    if (!work)
+                        for (int k = i >> 1; k < nst * 4; k++) out32[k] = 0u;
                     nzv_out[u] = (uint8_t)nst;
                     if (zero_fill) {
                         uint4 *out = reinterpret_cast<uint4 *>(out32);
