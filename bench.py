@@ -407,8 +407,9 @@ def run_ours(args, rank, world):
     sweep = None
     if args.workload == "cfg2" and not args.no_sweep:
         sweep = run_sweep_cfg5(args, torch, mp3_b200, dec, tstream, barrier, rank, world)
-    global CFG1_LATENCY
+    global CFG1_LATENCY, REAL_SIGNAL
     CFG1_LATENCY = run_cfg1_latency(mp3_b200, local, streams[0]) if (rank == 0 and not args.no_e2e) else None
+    REAL_SIGNAL = run_real_signal(mp3_b200, local) if (rank == 0 and args.workload == "cfg2" and not args.no_sweep) else None
     finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, audio_s, ms_dev, e2e, stage_ms,
            launches, sampler, gen_s, checksum, strong, numa, (parity_n, parity_worst), sweep, infos)
 
@@ -472,6 +473,46 @@ def run_e2e(args, torch, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstr
 
 
 CFG1_LATENCY = None
+REAL_SIGNAL = None
+
+
+def _encode_real(seed):
+    from mp3_b200 import signals, synth
+    return synth.encode_pcm(signals.stereo(44100, 10.0, 1 + 2 * seed), 44100, 128)
+
+
+def run_real_signal(mp3_b200, device, distinct=16, nstreams=1024):
+    """The cfg2 shape on REAL-SIGNAL streams: synthetic music + speech through the in-tree encoder (gen/l3gen.c::
+    l3enc_stream; 16 distinct 10-s streams, each used 64 times), device-resident, library CUDA events.  The generator's
+    random spectra -- the workload `value` is measured on, as BASELINE.json defines it -- have short count1 regions;
+    real audio has long ones and spends more of its time in the Huffman stage.  Reported next to the headline, not
+    instead of it."""
+    import multiprocessing as mp
+    try:
+        with mp.get_context("spawn").Pool(min(distinct, os.cpu_count() or 1)) as pool:
+            uniq = pool.map(_encode_real, range(distinct))
+    except Exception as e:  # noqa: BLE001
+        return {"error": "encoder pool failed: %r" % (e,)}
+    streams = [uniq[i % distinct] for i in range(nstreams)]
+    packed, offs = mp3_b200.pack_streams(streams)
+    import torch
+    d_raw = torch.empty(int(packed.size) + 64, dtype=torch.uint8, device="cuda")
+    d_raw[: packed.size].copy_(torch.from_numpy(packed))
+    torch.cuda.synchronize()
+    with mp3_b200.Decoder(device=device, pcm_format=mp3_b200.PCM_S16) as d2:
+        d2.set_stage_timing(True)
+        best = None
+        for _ in range(8):
+            d2.decode_packed(d_raw.data_ptr(), offs, where=mp3_b200.DEVICE, sync=True)
+            st = d2.stats()
+            if best is None or st.ms_total < best.ms_total:
+                best = st
+        audio = sum(d2.stream_info(i).samples / float(d2.stream_info(i).sample_rate) for i in range(nstreams))
+    return {"workload": "1024 x 10 s, 44.1 kHz stereo 128 kbit/s CBR, real signals (synthetic music + speech) through the "
+                        "in-tree encoder, %d distinct streams" % distinct,
+            "ms_per_step": best.ms_total, "value": audio / (best.ms_total * 1e-3), "unit": UNIT,
+            "stage_ms": {"index": best.ms_index, "huffman": best.ms_huffman, "fused": best.ms_fused},
+            "note": "stage events on (0.03 ms slower than the headline's mode); best of 8"}
 
 
 def run_cfg1_latency(mp3_b200, device, stream_bytes):
@@ -701,6 +742,7 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
                     if ms_e2e == ms_e2e else None),
             "gpu_launches": int(launches * args.steps),
             "cfg1_latency": CFG1_LATENCY,
+            "real_signal": REAL_SIGNAL,
             "clocks": sampler.result(),
             "gen_seconds": gen_s, "pcm_checksum": checksum,
         }

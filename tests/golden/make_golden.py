@@ -53,7 +53,7 @@ def main():
             out[name + ".mp3"] = np.frombuffer(s, np.uint8)
             out[name + ".pcm"] = pcm.astype(np.float32)
     # real signals through the in-tree encoder (gen/l3gen.c::l3enc_stream): music + speech, bit reservoir in use
-    import signals  # noqa: E402
+    from mp3_b200 import signals  # noqa: E402
     for name, sr, nch, kbps in (("enc_stereo_44k_128", 44100, 2, 128), ("enc_mono_44k_64", 44100, 1, 64)):
         src = signals.stereo(sr, 0.6) if nch == 2 else signals.to_s16(signals.speech(sr, 0.6) * 0.8)
         s = synth.encode_pcm(src, sr, kbps)

@@ -9,16 +9,12 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np  # noqa: E402
 
 
 def one(seed):
-    import signals
-    from mp3_b200 import synth
-    m, s = signals.music(44100, 10.0, seed), signals.speech(44100, 10.0, seed + 1000)
-    pcm = signals.to_s16(np.stack([0.8 * m + 0.15 * s, 0.25 * m + 0.7 * s], axis=1) * 0.9)
-    return synth.encode_pcm(pcm, 44100, 128)
+    from mp3_b200 import signals, synth
+    return synth.encode_pcm(signals.stereo(44100, 10.0, 1 + 2 * seed), 44100, 128)
 
 
 def run(m, streams):
