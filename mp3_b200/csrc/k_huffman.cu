@@ -508,6 +508,30 @@ __device__ __forceinline__ int decode_count1(R &br, uint32_t limit, int i, uint3
             v2 = wp > 2 ? cur.z : 0u;
         }
     }
+    // Two quadruples per trip while both are certain to be taken (<= 20 bits: one 32-bit peek holds them): the second
+    // look-up does not wait for a new peek, and their four words complete exactly one vector.  The last quadruples of
+    // a unit -- where the end of part2_3_length or of the spectrum has to be checked between them -- take the
+    // single-step loop below, which has the exact rules.
+    while (i <= 568 && br.bitpos() < limit) {
+        const uint32_t bits = br.peek32();
+        const uint32_t e1 = S.quad[qoff + (bits >> 26)];
+        const uint32_t sym1 = e1 & 15u, len1 = e1 >> 4, n1 = len1 + __popc(sym1);
+        const uint32_t bits2 = bits << n1;
+        const uint32_t e2 = S.quad[qoff + (bits2 >> 26)];
+        const uint32_t sym2 = e2 & 15u, len2 = e2 >> 4, n2 = len2 + __popc(sym2);
+        const uint32_t p1 = br.bitpos() + n1;
+        if (p1 >= limit || p1 + n2 > limit) break;
+        br.skip((int)(n1 + n2));
+        const uint2 a = S.c1[(sym1 << 4) | ((bits << len1) >> 28)], b = S.c1[(sym2 << 4) | ((bits2 << len2) >> 28)];
+        const int wp = (i >> 1) & 3; // (the same in every trip of this loop)
+        out[i >> 3] = make_uint4(wp == 0 ? a.x : v0, wp == 0 ? a.y : (wp == 1 ? a.x : v1),
+                                 wp == 0 ? b.x : (wp == 1 ? a.y : (wp == 2 ? a.x : v2)),
+                                 wp == 0 ? b.y : (wp == 1 ? b.x : (wp == 2 ? a.y : a.x)));
+        v0 = wp == 1 ? b.y : (wp == 2 ? b.x : (wp == 3 ? a.y : 0u));
+        v1 = wp == 2 ? b.y : (wp == 3 ? b.x : 0u);
+        v2 = wp == 3 ? b.y : 0u;
+        i += 8;
+    }
     while (i <= 572 && br.bitpos() < limit) {
         const uint32_t bits = br.peek32();
         const uint32_t e = S.quad[qoff + (bits >> 26)];
