@@ -355,19 +355,30 @@ __device__ __forceinline__ void read_scalefactors(R &br, const L3UnitDesc &d, ui
                         g0_ntot = (d0.flags & L3F_MIXED) ? 35 : 36;
                     }
                 }
+                // the four scfsi groups (bands 0-5, 6-10, 11-15, 16-20): a group that is transmitted is <= 6 fields of
+                // one width (<= 24 bits) and comes out of ONE peek -- 4 dependent reads per unit instead of 21
 #pragma unroll
-                for (int b = 0; b < 21; b++) {
-                    const int grp = b < 6 ? 0 : (b < 11 ? 1 : (b < 16 ? 2 : 3));
-                    uint32_t v;
+                for (int grp = 0; grp < 4; grp++) {
+                    const int b0 = grp == 0 ? 0 : (grp == 1 ? 6 : (grp == 2 ? 11 : 16)), nb = grp == 0 ? 6 : 5;
                     if ((scfsi >> grp) & 1u) {
-                        // b-th transmitted scalefactor of granule 0
-                        int w0 = b < g0_n1 ? g0_s1 : (b < g0_ntot ? g0_s2 : 0);
-                        uint64_t off = b < g0_n1 ? (uint64_t)(b * g0_s1)
-                                                 : (uint64_t)(g0_n1 * g0_s1 + (b - g0_n1) * g0_s2);
-                        v = br.bits_abs(arena, arena_bytes, g0_bit + off, w0);
-                    } else
-                        v = br.get(b < 11 ? s1 : s2);
-                    sfw[b >> 2] |= v << (8 * (b & 3));
+#pragma unroll
+                        for (int k = 0; k < nb; k++) { // b-th transmitted scalefactor of granule 0
+                            const int b = b0 + k;
+                            const int w0 = b < g0_n1 ? g0_s1 : (b < g0_ntot ? g0_s2 : 0);
+                            const uint64_t off = b < g0_n1 ? (uint64_t)(b * g0_s1)
+                                                           : (uint64_t)(g0_n1 * g0_s1 + (b - g0_n1) * g0_s2);
+                            sfw[b >> 2] |= br.bits_abs(arena, arena_bytes, g0_bit + off, w0) << (8 * (b & 3));
+                        }
+                    } else {
+                        const int w = grp < 2 ? s1 : s2;
+                        const uint32_t v = br.peek32();
+#pragma unroll
+                        for (int k = 0; k < nb; k++) {
+                            const int b = b0 + k;
+                            sfw[b >> 2] |= (((v << (k * w)) >> 1) >> (31 - w)) << (8 * (b & 3)); // (w = 0 reads as 0)
+                        }
+                        br.skip(nb * w);
+                    }
                 }
             }
         } else {
