@@ -333,10 +333,19 @@ __device__ __forceinline__ void read_scalefactors(R &br, const L3UnitDesc &d, ui
             const int s1 = (int)((SL1 >> (4 * d.sfc)) & 15), s2 = (int)((SL2 >> (4 * d.sfc)) & 15);
             if (bt == 2) {
                 const int n1 = mixed ? 17 : 18, ntot = mixed ? 35 : 36;
+                // six fields (<= 24 bits) per peek
 #pragma unroll
-                for (int b = 0; b < 36; b++) {
-                    int w = b < n1 ? s1 : (b < ntot ? s2 : 0);
-                    sfw[b >> 2] |= br.get(w) << (8 * (b & 3));
+                for (int c = 0; c < 6; c++) {
+                    const uint32_t v = br.peek32();
+                    int sh = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const int b = 6 * c + k;
+                        const int w = b < n1 ? s1 : (b < ntot ? s2 : 0);
+                        sfw[b >> 2] |= (((v << sh) >> 1) >> (31 - w)) << (8 * (b & 3));
+                        sh += w;
+                    }
+                    br.skip(sh);
                 }
             } else {
                 const bool gr1 = (d.pos & L3P_GR) != 0;
@@ -397,12 +406,21 @@ __device__ __forceinline__ void read_scalefactors(R &br, const L3UnitDesc &d, ui
             const int lay = bt == 2 ? (mixed ? 2 : 1) : 0;
             const int e0 = c_lsf_nsfb[tbl][lay][0], e1 = e0 + c_lsf_nsfb[tbl][lay][1];
             const int e2 = e1 + c_lsf_nsfb[tbl][lay][2], e3 = e2 + c_lsf_nsfb[tbl][lay][3];
+            // five fields (<= 25 bits) per peek
 #pragma unroll
-            for (int b = 0; b < 40; b++) {
-                int w = b < e0 ? sl0 : (b < e1 ? sl1 : (b < e2 ? sl2 : (b < e3 ? sl3 : 0)));
-                uint32_t v = br.get(w);
-                if (ist && w && v == (1u << w) - 1u) v |= 0x80u; // illegal intensity position
-                sfw[b >> 2] |= v << (8 * (b & 3));
+            for (int c = 0; c < 8; c++) {
+                const uint32_t pk = br.peek32();
+                int sh = 0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const int b = 5 * c + k;
+                    const int w = b < e0 ? sl0 : (b < e1 ? sl1 : (b < e2 ? sl2 : (b < e3 ? sl3 : 0)));
+                    uint32_t v = ((pk << sh) >> 1) >> (31 - w);
+                    if (ist && w && v == (1u << w) - 1u) v |= 0x80u; // illegal intensity position
+                    sfw[b >> 2] |= v << (8 * (b & 3));
+                    sh += w;
+                }
+                br.skip(sh);
             }
         }
     }
