@@ -477,25 +477,21 @@ __device__ __forceinline__ void stage_requant(SH &S, int tid, int nb, const L3Ba
                 const int b = (bw >> (8 * (q & 3))) & 0xff;
                 const float ga = g0[b], gb = g1[b];
                 const uint32_t wa = v[2 * q], wb = v[2 * q + 1];
-                float a0, a1, c0, c1;
-                if (slow & (1u << (2 * q))) { // (warp-uniform)
-                    a0 = rq_any(S, (int)(short)(wa & 0xffffu), ga, pow43);
-                    a1 = rq_any(S, (int)wa >> 16, ga, pow43);
-                } else {
-                    a0 = rq_lo(S, wa, ga);
-                    a1 = rq_hi(S, wa, ga);
-                }
-                if (slow & (0x10000u << (2 * q))) {
-                    c0 = rq_any(S, (int)(short)(wb & 0xffffu), gb, pow43);
-                    c1 = rq_any(S, (int)wb >> 16, gb, pow43);
-                } else {
-                    c0 = rq_lo(S, wb, gb);
-                    c1 = rq_hi(S, wb, gb);
-                }
+                // (the two lines of a pair times their band gain as ONE packed multiply)
+                float2 A, C;
+                if (slow & (1u << (2 * q))) // (warp-uniform)
+                    A = make_float2(rq_any(S, (int)(short)(wa & 0xffffu), ga, pow43), rq_any(S, (int)wa >> 16, ga, pow43));
+                else
+                    A = f2_mul_s(ga, make_float2(rq_lo(S, wa, 1.f), rq_hi(S, wa, 1.f)));
+                if (slow & (0x10000u << (2 * q)))
+                    C = make_float2(rq_any(S, (int)(short)(wb & 0xffffu), gb, pow43), rq_any(S, (int)wb >> 16, gb, pow43));
+                else
+                    C = f2_mul_s(gb, make_float2(rq_lo(S, wb, 1.f), rq_hi(S, wb, 1.f)));
                 const int p = t64 + 64 * q;
+                const float a0 = A.x, a1 = A.y, c0 = C.x, c1 = C.y;
+                (void)a0; (void)a1; (void)c0; (void)c1;
 #if KF_MS_MERGE
                 // c = -S for an MS granule (sign folded into the gains): M + S = a - mf c, M - S = mf a + c; mf = 0: (a, c)
-                const float2 A = make_float2(a0, a1), C = make_float2(c0, c1);
                 X0[p] = f2_fma_s(-mf, C, A);
                 X1[p] = f2_fma_s(mf, A, C);
 #else
