@@ -817,8 +817,19 @@ static void enc_analysis(enc_ch *e, const double *in32 /* 32 new samples, oldest
     }
 }
 
-/* one granule of one channel: 576 PCM samples -> 576 spectral lines */
-static void enc_granule_spectrum(enc_ch *e, const double *pcm576, double *xr /* 576 */)
+static double enc_window(int bt, int i) /* the decoder's window shapes (11172-3 2.4.3.4.10.3) */
+{
+    switch (bt) {
+    case 0: return sin(M_PI / 36.0 * (i + 0.5));
+    case 1: return i < 18 ? sin(M_PI / 36.0 * (i + 0.5)) : (i < 24 ? 1.0 : (i < 30 ? sin(M_PI / 12.0 * (i - 18 + 0.5)) : 0.0));
+    case 3: return i < 6 ? 0.0 : (i < 12 ? sin(M_PI / 12.0 * (i - 6 + 0.5)) : (i < 18 ? 1.0 : sin(M_PI / 36.0 * (i + 0.5))));
+    default: return sin(M_PI / 12.0 * (i + 0.5));
+    }
+}
+
+/* one granule of one channel: 576 PCM samples -> 576 spectral lines in BITSTREAM order (short blocks: per scalefactor
+ * band the three windows one after the other).  bt = block type of the granule (2: three short windows, not mixed). */
+static void enc_granule_spectrum(enc_ch *e, const double *pcm576, double *xr /* 576 */, int bt, int row)
 {
     static double cur[32][18];
     for (int t = 0; t < 18; t++) {
@@ -829,21 +840,42 @@ static void enc_granule_spectrum(enc_ch *e, const double *pcm576, double *xr /* 
     for (int sb = 0; sb < 32; sb++) {
         double in[36];
         for (int n = 0; n < 18; n++) { in[n] = e->prev[sb][n]; in[18 + n] = cur[sb][n]; }
-        for (int k = 0; k < 18; k++) {
-            double a = 0.0;
-            for (int n = 0; n < 36; n++)
-                a += sin(M_PI / 36.0 * (n + 0.5)) * in[n] * cos(M_PI / 72.0 * (2 * n + 1 + 18) * (2 * k + 1));
-            xr[sb * 18 + k] = a / 9.0;
+        if (bt != 2) {
+            for (int k = 0; k < 18; k++) {
+                double a = 0.0;
+                for (int n = 0; n < 36; n++)
+                    a += enc_window(bt, n) * in[n] * cos(M_PI / 72.0 * (2 * n + 1 + 18) * (2 * k + 1));
+                xr[sb * 18 + k] = a / 9.0;
+            }
+        } else {
+            for (int w = 0; w < 3; w++)
+                for (int k = 0; k < 6; k++) {
+                    double a = 0.0;
+                    for (int n = 0; n < 12; n++)
+                        a += enc_window(2, n) * in[6 + 6 * w + n] * cos(M_PI / 24.0 * (2 * n + 1 + 6) * (2 * k + 1));
+                    xr[sb * 18 + 3 * k + w] = a / 3.0; /* the decoder's (reordered) layout: windows interleaved */
+                }
         }
         memcpy(e->prev[sb], cur[sb], sizeof e->prev[sb]);
     }
-    for (int sb = 1; sb < 32; sb++) /* alias butterflies: the inverse rotation of the decoder's */
-        for (int i = 0; i < 8; i++) {
-            double ci = l3_alias_ci[i], cs = 1.0 / sqrt(1.0 + ci * ci), ca = ci / sqrt(1.0 + ci * ci);
-            double lo = xr[sb * 18 - 1 - i], hi = xr[sb * 18 + i];
-            xr[sb * 18 - 1 - i] = lo * cs + hi * ca;
-            xr[sb * 18 + i] = hi * cs - lo * ca;
+    if (bt != 2) {
+        for (int sb = 1; sb < 32; sb++) /* alias butterflies: the inverse rotation of the decoder's */
+            for (int i = 0; i < 8; i++) {
+                double ci = l3_alias_ci[i], cs = 1.0 / sqrt(1.0 + ci * ci), ca = ci / sqrt(1.0 + ci * ci);
+                double lo = xr[sb * 18 - 1 - i], hi = xr[sb * 18 + i];
+                xr[sb * 18 - 1 - i] = lo * cs + hi * ca;
+                xr[sb * 18 + i] = hi * cs - lo * ca;
+            }
+    } else { /* back to transmission order: the inverse of the decoder's reorder */
+        double t[576];
+        memcpy(t, xr, sizeof t);
+        const uint16_t *bs = l3_sfb_short[row];
+        for (int sfb = 0; sfb < 13; sfb++) {
+            const int s0 = 3 * bs[sfb], wd = bs[sfb + 1] - bs[sfb];
+            for (int win = 0; win < 3; win++)
+                for (int k = 0; k < wd; k++) xr[s0 + win * wd + k] = t[s0 + 3 * k + win];
         }
+    }
 }
 
 static int enc_best_table(const int *ix, int lo, int hi, int *bits_out)
@@ -871,8 +903,9 @@ static int enc_best_table(const int *ix, int lo, int hi, int *bits_out)
 
 typedef struct { int bv2, c1end, r1, r2, a, c, tsel[3], c1tab, bits; } enc_plan;
 
-/* bits of the quantised spectrum with the best tables; fills the plan */
-static int enc_count(const int *ix, int row, enc_plan *p)
+/* bits of the quantised spectrum with the best tables; fills the plan.  bt != 0: window switching -- two regions, the
+ * first one fixed by the standard (36 lines; 2.4.2.7 region0_count 7 / 8) */
+static int enc_count(const int *ix, int row, enc_plan *p, int bt)
 {
     int last = 576;
     while (last > 0 && ix[last - 1] == 0) last--;
@@ -894,6 +927,11 @@ static int enc_count(const int *ix, int row, enc_plan *p)
     p->c = c;
     p->r1 = sfb[a] < bv2 ? sfb[a] : bv2;
     p->r2 = sfb[c] < bv2 ? sfb[c] : bv2;
+    if (bt) {
+        const int r1 = bt == 2 ? 3 * l3_sfb_short[row][3] : sfb[8];
+        p->r1 = r1 < bv2 ? r1 : bv2;
+        p->r2 = bv2;
+    }
     int b0, b1, b2;
     p->tsel[0] = enc_best_table(ix, 0, p->r1, &b0);
     p->tsel[1] = enc_best_table(ix, p->r1, p->r2, &b1);
@@ -925,7 +963,16 @@ static int enc_quantise(const double *xr, int gg, int *ix)
 }
 
 /* pcm: interleaved s16, nsamples per channel.  Returns bytes written (0: bad arguments / buffer too small). */
+size_t l3enc_stream2(const int16_t *pcm, int nsamples, int nch, int sample_rate, int kbps, int use_short, uint8_t *out,
+                     size_t cap);
 size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, int kbps, uint8_t *out, size_t cap)
+{
+    return l3enc_stream2(pcm, nsamples, nch, sample_rate, kbps, 0, out, cap);
+}
+
+/* use_short: 1 = window switching on attacks */
+size_t l3enc_stream2(const int16_t *pcm, int nsamples, int nch, int sample_rate, int kbps, int use_short, uint8_t *out,
+                     size_t cap)
 {
     int row = -1;
     for (int i = 0; i < 3; i++) if ((int)l3_sample_rate[i] == sample_rate) row = i;
@@ -941,6 +988,42 @@ size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, 
     size_t lstart = 0, wcur = 0;
     long pad_rest = 0;
     double e_avg = 0.0;
+    /* window switching: a granule whose energy jumps by more than 16 x between thirds (an attack) is coded with three
+     * short windows; the granules around a run of short ones take the start / stop windows (0 -> 1 -> 2 .. 2 -> 3 -> 0).
+     * The filterbank delays the signal by 480 samples and the MDCT looks one granule back: the attack detector reads the
+     * PCM that far behind the granule it labels. */
+    const int ngran = 2 * nframes;
+    uint8_t *btype[2];
+    for (int ch = 0; ch < 2; ch++) {
+        btype[ch] = (uint8_t *)calloc((size_t)ngran + 2, 1);
+        if (!use_short || ch >= nch) continue;
+        double prev_e = 0.0;
+        for (int g = 1; g < ngran; g++) {
+            int attack = 0;
+            for (int third = 0; third < 3; third++) {
+                double en = 1e-9;
+                for (int i = 0; i < 192; i++) {
+                    const long n = (long)g * 576 + third * 192 + i - 480 - 288;
+                    const double v = (n >= 0 && n < nsamples) ? pcm[n * nch + ch] / 32768.0 : 0.0;
+                    en += v * v;
+                }
+                if (en > 16.0 * prev_e && en > 192 * 1e-4) attack = 1;
+                prev_e = en;
+            }
+            if (attack) btype[ch][g] = 2; /* (for now: "wants short windows") */
+        }
+        /* legal sequence with one granule of look-ahead: 0 -> {0, 1}, 1 -> 2, 2 -> {2, 3}, 3 -> {0, 1} */
+        int prev = 0;
+        for (int g = 0; g < ngran; g++) {
+            const int want = btype[ch][g] == 2, want_next = g + 1 < ngran && btype[ch][g + 1] == 2;
+            int bt;
+            if (prev == 1) bt = 2;
+            else if (prev == 2) bt = (want || want_next) ? 2 : 3;
+            else bt = want_next ? 1 : 0;
+            btype[ch][g] = (uint8_t)bt;
+            prev = bt;
+        }
+    }
     for (int f = 0; f < nframes; f++) {
         int pad = 0;
         long num = 144L * kbps * 1000;
@@ -963,7 +1046,8 @@ size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, 
                     const long n = (long)f * 1152 + gr * 576 + i;
                     x[i] = n < nsamples ? pcm[n * nch + ch] / 32768.0 : 0.0;
                 }
-                enc_granule_spectrum(&ech[ch], x, xr);
+                const int bt = btype[ch][2 * f + gr];
+                enc_granule_spectrum(&ech[ch], x, xr, bt, row);
                 for (int i = 0; i < 576; i++) energy += xr[i] * xr[i];
                 /* budget: the mean of what is left, more for loud granules, less for quiet ones (those feed the reservoir) */
                 const long left = avail - (long)(w.pos - wstart);
@@ -982,14 +1066,14 @@ size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, 
                 while (lo <= hi) {
                     const int gg = (lo + hi) / 2;
                     const int mx = enc_quantise(xr, gg, ix);
-                    const int bits = mx > 8191 + 15 ? (1 << 30) : enc_count(ix, row, &plan);
+                    const int bits = mx > 8191 + 15 ? (1 << 30) : enc_count(ix, row, &plan, bt);
                     if (bits <= budget) { best_gg = gg; best_plan = plan; hi = gg - 1; }
                     else lo = gg + 1;
                 }
                 enc_quantise(xr, best_gg, ix);
-                if (enc_count(ix, row, &best_plan) > budget) { /* (not even the coarsest fits: silence) */
+                if (enc_count(ix, row, &best_plan, bt) > budget) { /* (not even the coarsest fits: silence) */
                     memset(ix, 0, sizeof ix);
-                    enc_count(ix, row, &best_plan);
+                    enc_count(ix, row, &best_plan, bt);
                 }
                 gr_side *s = &gs[gr][ch];
                 memset(s, 0, sizeof *s);
@@ -1001,6 +1085,8 @@ size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, 
                 s->region0_count = best_plan.a - 1;
                 s->region1_count = best_plan.c - best_plan.a - 1;
                 s->count1table = best_plan.c1tab;
+                s->window_switching = bt != 0;
+                s->block_type = bt;
                 const size_t p0 = w.pos;
                 for (int i = 0; i < best_plan.bv2; i += 2)
                     put_pair(&w, best_plan.tsel[i < best_plan.r1 ? 0 : (i < best_plan.r2 ? 1 : 2)], ix[i], ix[i + 1]);
@@ -1028,10 +1114,18 @@ size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, 
                 putbits(&sw, (unsigned)s->big_values, 9);
                 putbits(&sw, (unsigned)s->global_gain, 8);
                 putbits(&sw, 0, 4);  /* scalefac_compress 0: no scalefactor bits */
-                putbits(&sw, 0, 1);  /* window_switching_flag */
-                for (int k = 0; k < 3; k++) putbits(&sw, (unsigned)s->table_select[k], 5);
-                putbits(&sw, (unsigned)s->region0_count, 4);
-                putbits(&sw, (unsigned)s->region1_count, 3);
+                putbits(&sw, (unsigned)s->window_switching, 1);
+                if (s->window_switching) {
+                    putbits(&sw, (unsigned)s->block_type, 2);
+                    putbits(&sw, 0, 1); /* mixed_block_flag */
+                    putbits(&sw, (unsigned)s->table_select[0], 5);
+                    putbits(&sw, (unsigned)s->table_select[1], 5);
+                    putbits(&sw, 0, 9); /* subblock_gain x 3 */
+                } else {
+                    for (int k = 0; k < 3; k++) putbits(&sw, (unsigned)s->table_select[k], 5);
+                    putbits(&sw, (unsigned)s->region0_count, 4);
+                    putbits(&sw, (unsigned)s->region1_count, 3);
+                }
                 putbits(&sw, 0, 1);  /* preflag */
                 putbits(&sw, 0, 1);  /* scalefac_scale */
                 putbits(&sw, (unsigned)s->count1table, 1);
@@ -1052,5 +1146,7 @@ size_t l3enc_stream(const int16_t *pcm, int nsamples, int nch, int sample_rate, 
     free(logical);
     free(fr);
     free(ech);
+    free(btype[0]);
+    free(btype[1]);
     return o;
 }

@@ -53,6 +53,18 @@ def speech(sr, seconds, seed=2):
     return x
 
 
+def castanets(sr, seconds, seed=5):
+    """Sharp noise bursts over a quiet tone: attacks that make an encoder switch to short windows."""
+    rng = np.random.default_rng(seed)
+    n = int(sr * seconds)
+    x = 0.05 * np.sin(2 * np.pi * 440.0 * np.arange(n) / sr)
+    for t0 in np.arange(0.15, seconds, 0.21):
+        i0 = int(t0 * sr)
+        m = min(2000, n - i0)
+        x[i0: i0 + m] += 0.7 * rng.standard_normal(m) * np.exp(-np.arange(m) / 300.0)
+    return x
+
+
 def to_s16(x):
     return np.clip(np.round(np.asarray(x) * 32767.0), -32768, 32767).astype(np.int16)
 

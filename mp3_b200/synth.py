@@ -56,23 +56,24 @@ def _load():
         _lib.l3gen_stream.argtypes = [ctypes.POINTER(Cfg), ctypes.c_void_p, ctypes.c_size_t]
         _lib.l3gen_max_bytes.restype = ctypes.c_size_t
         _lib.l3gen_max_bytes.argtypes = [ctypes.POINTER(Cfg)]
-        _lib.l3enc_stream.restype = ctypes.c_size_t
-        _lib.l3enc_stream.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_void_p, ctypes.c_size_t]
+        _lib.l3enc_stream2.restype = ctypes.c_size_t
+        _lib.l3enc_stream2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_size_t]
     return _lib
 
 
-def encode_pcm(pcm, sample_rate=44100, bitrate_kbps=128):
+def encode_pcm(pcm, sample_rate=44100, bitrate_kbps=128, short_blocks=False):
     """Encode real audio: pcm = int16 array [samples] (mono) or [samples, 2]; returns the MPEG-1 Layer III stream
-    (gen/l3gen.c::l3enc_stream: CBR, bit reservoir in use, long blocks, no psychoacoustic model)."""
+    (gen/l3gen.c::l3enc_stream2: CBR, bit reservoir in use, no psychoacoustic model; short_blocks: window switching on
+    attacks -- start / short / stop windows --, else long blocks only)."""
     L = _load()
     a = np.ascontiguousarray(pcm, dtype=np.int16)
     nch = 1 if a.ndim == 1 else a.shape[1]
     n = a.shape[0]
     cap = (144 * bitrate_kbps * 1000 // sample_rate + 1) * ((n + 1151) // 1152 + 2) + 64
     buf = np.zeros(cap, np.uint8)
-    m = L.l3enc_stream(a.ctypes.data_as(ctypes.c_void_p), n, nch, sample_rate, bitrate_kbps,
-                       buf.ctypes.data_as(ctypes.c_void_p), cap)
+    m = L.l3enc_stream2(a.ctypes.data_as(ctypes.c_void_p), n, nch, sample_rate, bitrate_kbps, 1 if short_blocks else 0,
+                        buf.ctypes.data_as(ctypes.c_void_p), cap)
     if m == 0:
         raise ValueError("encoder rejected the arguments")
     return buf[:m].tobytes()

@@ -55,3 +55,42 @@ def test_speech_pauses_feed_the_reservoir(oracle_mod, synth_mod):
     d = oracle_mod.decode(stream, dumps=True)
     snr, worst = signals.snr_db(d.pcm.T, pcm16)
     assert snr > 15.0 and worst < 0.25
+
+
+def _block_types(stream):
+    """block_type of every (granule, channel 0) of a stereo MPEG-1 stream, from the side info"""
+    out = []
+    for f in l3util.split_frames(stream):
+        v = int.from_bytes(f[4:36], "big")
+        for gr in range(2):
+            base = 20 + gr * 118
+            ws = (v >> (256 - (base + 33) - 1)) & 1
+            out.append((v >> (256 - (base + 34) - 2)) & 3 if ws else 0)
+    return out
+
+
+def test_window_switching_on_attacks(oracle_mod, synth_mod):
+    """Noise bursts make the encoder switch windows (start -> short ... -> stop): the sequence is legal, the decoders
+    agree on the stream, and the short windows pay -- the same signal coded with long windows only has the lower SNR."""
+    sr = 44100
+    x = signals.castanets(sr, 2.0)
+    pcm16 = signals.to_s16(np.stack([x, 0.6 * x], axis=1))
+    snr = {}
+    for short in (False, True):
+        stream = synth_mod.encode_pcm(pcm16, sr, 320, short_blocks=short)
+        d = oracle_mod.decode(stream, dumps=True)
+        assert d.concealed_frames == 0
+        snr[short] = signals.snr_db(d.pcm.T, pcm16)[0]
+        bt = _block_types(stream)
+        if short:
+            assert bt.count(2) >= 5 and bt.count(1) >= 5 and bt.count(3) >= 5
+            legal = {0: (0, 1), 1: (2,), 2: (2, 3), 3: (0, 1)}
+            assert all(b in legal[a] for a, b in zip(bt, bt[1:]))
+        else:
+            assert set(bt) == {0}
+        if ffmpeg_ref.available():
+            pcm, per = ffmpeg_ref.decode_frames(l3util.split_frames(stream), 2)
+            assert all(p is not None for p in per)
+            rms, mx = l3util.iso_compliance(pcm, d.pcm)
+            assert rms < 5e-7 and mx < 1e-5, (rms, mx)
+    assert snr[True] > snr[False] + 0.5 and snr[True] > 15.0, snr

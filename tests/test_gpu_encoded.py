@@ -24,6 +24,22 @@ def encoded(synth_mod, oracle_mod):
     return srcs, streams, refs
 
 
+def test_window_switching_stream(synth_mod, oracle_mod):
+    """Attacks coded with start / short / stop windows by the in-tree encoder: bit-exact through Huffman, ISO accuracy."""
+    import mp3_b200 as m
+    x = signals.castanets(44100, 2.0)
+    pcm16 = signals.to_s16(np.stack([x, 0.6 * x], axis=1))
+    s = synth_mod.encode_pcm(pcm16, 44100, 192, short_blocks=True)
+    r = oracle_mod.decode(s, dumps=True)
+    with m.Decoder(device=0, pcm_format=m.PCM_F32, keep_stages=True) as dec:
+        dec.decode_batch([s])
+        assert np.array_equal(dec.stage(m.STAGE_IS)[: r.units], r.is_)
+        got = dec.stream_pcm(0, dec.fetch_pcm()).astype(np.float64)
+        l3util.assert_iso_full_accuracy(got, r.pcm.T, "window switching")
+        snr, worst = signals.snr_db(got, pcm16)
+        assert snr > 8.0
+
+
 @pytest.mark.parametrize("k1", ["auto", "chunk", "warp", "sorted"])
 def test_encoded_streams_bit_exact_and_iso(k1, encoded, synth_mod, monkeypatch):
     import mp3_b200 as m
