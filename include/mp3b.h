@@ -207,6 +207,11 @@ int mp3b_batch_fetch_resampled(mp3b_ctx *ctx, void *dst, uint64_t cap_elems, int
 /* The FIR used for in_rate -> out_rate, for verification: out_rate / in_rate = L / M in lowest terms;
  * taps[p * taps_per_phase + j] = h[p + j L], h centred at half * L with taps_per_phase = 2 half + 1.
  * Returns MP3B_OK, MP3B_E_TRUNCATED (cap too small; *ncoef = needed) or MP3B_E_INVAL. */
+/* The tensor-core resampler's plan for a rate pair (verification, no GPU needed): tiles of 128 outputs come in
+ * *nkinds kinds; a tile of kind k starting at output n0 = 128 t (t = k mod *nkinds) is y[n0 + r] = sum_c a[r][c] x[base + c],
+ * base = (n0 M + half L) div L - (taps_per_phase - 1), c < *kpad.  a (optional): kind `kind`'s matrix, [128][*kpad] floats.
+ * MP3B_E_UNSUPPORTED: the pair is not served by that path (mp3b_batch_resample then uses the FP32 kernels). */
+int mp3b_resample_tc_plan(int in_rate, int out_rate, int kind, float *a, size_t cap, int *nkinds, int *kpad);
 int mp3b_resample_filter(int in_rate, int out_rate, float *taps, size_t cap, size_t *ncoef, int *L, int *M,
                          int *taps_per_phase);
 

@@ -62,7 +62,7 @@ class Stats(ctypes.Structure):
 
 EXPORTS = [
     "mp3b_abi_version", "mp3b_device_count", "mp3b_opts_default", "mp3b_ctx_create", "mp3b_ctx_destroy",
-    "mp3b_ctx_set_stream", "mp3b_ctx_set_stage_timing", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
+    "mp3b_ctx_set_stream", "mp3b_ctx_set_stage_timing", "mp3b_resample_tc_plan", "mp3b_strerror", "mp3b_last_error", "mp3b_host_alloc", "mp3b_host_free", "mp3b_decode_batch",
     "mp3b_decode_packed", "mp3b_sync", "mp3b_flush", "mp3b_batch_stream_info", "mp3b_batch_tag_info", "mp3b_batch_pcm_device_ptr",
     "mp3b_batch_fetch_pcm", "mp3b_get_stats", "mp3b_set_pcm_sink", "mp3b_stream_open", "mp3b_stream_close", "mp3b_stream_enqueue",
     "mp3b_decode", "mp3b_stream_get_info", "mp3b_stream_fetch_pcm", "mp3b_stream_pcm_device_ptr",
@@ -234,6 +234,29 @@ def seek_plan(data, target_sample, frames=None):
                           ctypes.byref(out))
     if rc != 0:
         raise Mp3bError(rc, L.mp3b_strerror(rc).decode())
+    return out
+
+
+def resample_tc_plan(in_rate, out_rate):
+    """The tensor-core resampler's plan: list of per-kind coefficient matrices [128, K] (float32), or None if the rate
+    pair is not served by that path."""
+    L = load_library()
+    L.mp3b_resample_tc_plan.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    nk, kp = ctypes.c_int(), ctypes.c_int()
+    rc = L.mp3b_resample_tc_plan(in_rate, out_rate, 0, None, 0, ctypes.byref(nk), ctypes.byref(kp))
+    if rc == -4:  # MP3B_E_UNSUPPORTED
+        return None
+    if rc != 0:
+        raise Mp3bError(rc, L.mp3b_strerror(rc).decode())
+    out = []
+    for k in range(nk.value):
+        a = np.empty((128, kp.value), np.float32)
+        rc = L.mp3b_resample_tc_plan(in_rate, out_rate, k, a.ctypes.data_as(ctypes.c_void_p), a.size, ctypes.byref(nk),
+                                     ctypes.byref(kp))
+        if rc != 0:
+            raise Mp3bError(rc, L.mp3b_strerror(rc).decode())
+        out.append(a)
     return out
 
 

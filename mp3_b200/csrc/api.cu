@@ -1384,6 +1384,48 @@ int mp3b_resample_filter(int in_rate, int out_rate, float *taps, size_t cap, siz
     return MP3B_OK;
 }
 
+// The tensor-core path's plan for a rate pair, for verification without a GPU: the number of tile kinds, the padded
+// window length K, and -- if `a` is given -- kind `kind`'s coefficient matrix [128][K] as c1 + c2 (the two fp16 pieces
+// added in float), row-major.  MP3B_E_UNSUPPORTED: the pair is not served by that path.
+int mp3b_resample_tc_plan(int in_rate, int out_rate, int kind, float *a, size_t cap, int *nkinds, int *kpad)
+{
+    std::vector<float> hp;
+    int l = 0, m = 0, t = 0, h = 0;
+    if (in_rate == out_rate || !l3_resample_design(in_rate, out_rate, &hp, &l, &m, &t, &h)) return MP3B_E_INVAL;
+    L3RsTcPlan plan;
+    if (t != 65 || !l3_resample_tc_plan(hp.data(), l, m, t, h, &plan)) return MP3B_E_UNSUPPORTED;
+    if (nkinds) *nkinds = plan.NK;
+    if (kpad) *kpad = plan.Kpad;
+    if (!a) return MP3B_OK;
+    if (kind < 0 || kind >= plan.NK) return MP3B_E_INVAL;
+    if (cap < (size_t)128 * plan.Kpad) return MP3B_E_TRUNCATED;
+    auto half_to_float = [](uint16_t v) -> float { // IEEE binary16 -> binary32
+        const uint32_t s = (uint32_t)(v >> 15) << 31, e = (v >> 10) & 31u, f = v & 1023u;
+        uint32_t bits;
+        if (e == 0) {
+            if (!f) bits = s;
+            else { // subnormal: normalise
+                int sh = 0;
+                uint32_t ff = f;
+                while (!(ff & 1024u)) { ff <<= 1; sh++; }
+                bits = s | ((uint32_t)(127 - 15 - sh + 1) << 23) | ((ff & 1023u) << 13);
+            }
+        } else if (e == 31) bits = s | 0x7f800000u | (f << 13);
+        else bits = s | ((e - 15 + 127) << 23) | (f << 13);
+        float r;
+        memcpy(&r, &bits, 4);
+        return r;
+    };
+    const uint16_t *hi = plan.A.data() + (size_t)kind * 2 * 128 * plan.Kpad, *lo = hi + (size_t)128 * plan.Kpad;
+    for (int r = 0; r < 128; r++)
+        for (int c = 0; c < plan.Kpad; c++) {
+            // the MMA's K-major core-matrix layout (k_resample_tc.cu canon_off16): 8 rows x 8 elements per 128 bytes
+            const size_t off = ((size_t)(c >> 3) * (128 >> 3) + (size_t)(r >> 3)) * 64 + (size_t)(r & 7) * 8 + (size_t)(c & 7);
+            a[(size_t)r * plan.Kpad + c] = half_to_float(hi[off]) + half_to_float(lo[off]);
+        }
+    return MP3B_OK;
+}
+
 int mp3b_batch_resample(mp3b_ctx *ctx, int out_rate)
 {
     if (!ctx || out_rate <= 0) return MP3B_E_INVAL;

@@ -36,6 +36,38 @@ def test_filter_properties(rin, rout):
     assert 20 * np.log10(H[f >= ny].max()) < -85.0                          # nothing left to alias / image
 
 
+@pytest.mark.parametrize("rin,rout,nk", [(44100, 48000, 5), (22050, 44100, 1), (32000, 48000, 3), (8000, 48000, 3),
+                                         (44100, 96000, 5), (24000, 44100, 147)])
+def test_tensor_core_plan_is_the_polyphase_filter(rin, rout, nk):
+    """The tensor-core resampler's host-side plan (no GPU needed): every tile kind's banded matrix, applied to the input
+    window of a tile of that kind, gives the 128 outputs of the polyphase definition -- the fp16 split of the
+    coefficients (c1 + c2) costs less than 1e-6 of the filter's gain."""
+    import mp3_b200
+    taps, L, M = mp3_b200.resample_filter(rin, rout)
+    T = taps.shape[1]
+    half = T // 2
+    mats = mp3_b200.resample_tc_plan(rin, rout)
+    assert mats is not None and len(mats) == nk
+    K = mats[0].shape[1]
+    assert K % 16 == 0 and K <= 192
+    rng = np.random.default_rng(rin + rout)
+    x = rng.integers(-32768, 32768, 40000).astype(np.float64)
+    for t in list(range(min(nk, 7))) + [nk + 1, 3 * nk + 2]:
+        k = t % nk
+        n0 = 128 * t
+        base = (n0 * M + half * L) // L - (T - 1)
+        win = np.array([x[base + c] if 0 <= base + c < x.size else 0.0 for c in range(K)])
+        got = mats[k].astype(np.float64) @ win
+        ref = np.empty(128)
+        for r in range(128):
+            u = (n0 + r) * M + half * L
+            q, p = divmod(u, L)
+            ref[r] = sum(float(taps[p, j]) * (x[q - j] if 0 <= q - j < x.size else 0.0) for j in range(T))
+        assert np.abs(got - ref).max() < 1e-6 * 32768 * np.abs(taps).sum(axis=1).max(), (t, np.abs(got - ref).max())
+    assert mp3_b200.resample_tc_plan(48000, 44100) is None      # downwards: the window does not fit, FP32 kernels
+    assert mp3_b200.resample_tc_plan(32000, 44100) is None      # 441 kinds: too many
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["f32", "s16"])
 @pytest.mark.parametrize("out_rate", [48000, 44100, 32000, 22100, 22050, 16000])
