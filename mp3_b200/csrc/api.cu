@@ -507,7 +507,9 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     // fused back end: tile length chosen so that the grid has a few CTAs per SM-resident slot
     uint32_t GF = 8;
     if (fused) {
-        uint64_t want = grans / 1776; // 148 SMs x 3 resident CTAs x 4 waves
+        // about three waves of tiles over the SMs' resident CTA slots (four per SM for s16, three for f32 output); the SM
+        // count is the device's (cudaDevAttrMultiProcessorCount), not a constant
+        uint64_t want = grans / ((uint64_t)ctx->sm_count * 12u);
         GF = (uint32_t)std::min<uint64_t>(128, std::max<uint64_t>(8, want / 4 * 4));
         if (ctx->tile_override) GF = ctx->tile_override;
         ntiles = 0;
