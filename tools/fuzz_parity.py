@@ -22,6 +22,10 @@ base = synth.make_workload("cfg3", 6, 24) + synth.make_workload("cfg4", 9, 24) +
     synth.make_stream(sample_rate=11025, bitrate_kbps=32, mode=1, blocks=1, mixed_pct=30, nframes=16, seed=10, crc=1),
     synth.make_stream(nframes=16, seed=11, crc=1, mode=1, blocks=1),
     synth.make_stream(nframes=16, seed=12, tag=1, tag_lame=1, enc_delay=576, enc_padding=1000)]
+# real-signal streams from the in-tree encoder (long count1 regions, bit reservoir up to 511 bytes, window switching)
+from mp3_b200 import signals  # noqa: E402
+base += [synth.encode_pcm(signals.stereo(44100, 0.5), 44100, 128), synth.encode_pcm(signals.to_s16(signals.speech(48000, 0.5) * 0.8), 48000, 96),
+         synth.encode_pcm(signals.to_s16(signals.castanets(44100, 0.6)), 44100, 160, short_blocks=True)]
 crc = int(os.environ.get("FUZZ_CRC", "0"))
 
 bad, what = [], []
