@@ -42,7 +42,7 @@ constexpr int RT_LBO_B = RT_N / 8 * 128 + 16; // K-chunk stride of the signal op
                                               // threads that build it (one K chunk each) store to different banks
 constexpr int RT_KMAX = 192;     // largest padded input window per tile (multiple of 16)
 #ifndef RT_PWARPS_N
-#define RT_PWARPS_N 8
+#define RT_PWARPS_N 8 /* (16 was measured with four read-out warps: no faster; with eight it does not fit the register file) */
 #endif
 constexpr int RT_PWARPS = RT_PWARPS_N;                 // producer warps (8 or 16)
 constexpr int RT_EWARPS = 8;                           // read-out warps: warp e owns TMEM lanes 32 (e % 4) .., columns 32 (e / 4) ..
@@ -82,6 +82,9 @@ struct RtMeta {          // one (tile, channel pair) of the staged group
     int rows;            // output frames of the tile that exist (0: padding entry)
 };
 
+static_assert(RT_THREADS <= 576, "more threads than registers: the read-out warps hold 64 accumulator values each");
+// (measurement switches, all off: -DRT_DBG_NO_STORE / RT_DBG_NO_LOAD / RT_DBG_NO_MMA take the PCM stores, the PCM loads or
+// all but one K step out of the kernel -- the numbers in DESIGN.md that show it is bound by neither)
 constexpr int RT_META = 16; // ring of per-group metadata: written up to four groups ahead of the producers, read by the
                             // read-out warps up to four groups behind them
 struct RtShared {
