@@ -487,36 +487,37 @@ k_payload_copy(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ 
         s_n[threadIdx.x] = n;
     }
     __syncthreads();
+    // Each warp copies eight frames.  A frame's bytes: up to 15 single bytes until the destination is 16-byte aligned,
+    // then 16-byte vectors -- a lane builds one from five aligned source words (byte permute; the source has any
+    // alignment) --, then the rest as bytes.  Vectors that would need a source word beyond the frame's own bytes are
+    // left to the byte loop: nothing is read past the frame.
     for (uint32_t k = warp; k < PC_FRAMES; k += PC_THREADS / 32) {
-        uint32_t n = s_n[k];
+        const uint32_t n = s_n[k];
         if (!n) continue;
         const uint8_t *src = s_src[k];
         uint8_t *dst = s_dst[k];
-        const uint32_t head = min(n, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+        const uint32_t head = min(n, (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
         if (lane < head) dst[lane] = src[lane];
-        src += head;
-        dst += head;
-        n -= head;
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
-        // words whose two source words lie inside the frame's own bytes (no read past the stream's end)
-        const uint32_t nw = n >= 8u ? (n - (sh ? 4u : 0u)) >> 2 : 0u;
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - sh);
-        uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+        const uint8_t *sb = src + head;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sb) & 3u);
+        const uint32_t rest = n - head;
+        const uint32_t nv = rest >= 20u ? (rest - (sh ? 4u : 0u)) >> 4 : 0u;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sb - sh);
+        uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
         const uint32_t sel = 0x3210u + 0x1111u * sh;
-        for (uint32_t i0 = 0; i0 < nw; i0 += 32) { // warp-uniform trip count: the unrolled loop must not split the warp
-            const uint32_t i = i0 + lane;
-            if (i < nw) {
-                const uint32_t a = __ldg(sw + i), b = sh ? __ldg(sw + i + 1) : 0u;
-                dw[i] = __byte_perm(a, b, sel);
+        for (uint32_t v0 = 0; v0 < nv; v0 += 32) { // (warp-uniform trip count)
+            const uint32_t v = v0 + lane;
+            if (v < nv) {
+                const uint32_t *q = sw + 4 * v;
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = sh ? __ldg(q + 4) : 0u;
+                dv[v] = make_uint4(__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel),
+                                   __byte_perm(w3, w4, sel));
             }
         }
-        for (uint32_t i = nw * 4u + lane; i < n; i += 32) dst[i] = src[i];
+        for (uint32_t i = head + nv * 16u + lane; i < n; i += 32) dst[i] = src[i];
     }
 }
 
-// Small results go to the host through stores into pinned (UVA-mapped) memory instead of a D2H
-// memcpy: a memcpy would queue on the DMA engine behind the multi-hundred-megabyte PCM copies of the
-// previous call and serialise the pipeline on a 64-byte transfer.
 __global__ void k_publish_words(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst_host, uint32_t n)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst_host[i] = src[i];
