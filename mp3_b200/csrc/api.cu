@@ -406,23 +406,22 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         CK(d_scratch.ensure(sizeof(L3FrameRec) * l3_index_scratch_records(raw_total, (uint64_t)nstreams)));
         CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, ist));
         if (ahead) CK(cudaEventRecord(ctx->walk_t0, ist));
-        // A few long streams are walked time-parallel (a CTA per stream, speculative segments: an hour of audio in
-        // 10 ms instead of 107); a batch of many streams has its parallelism across streams, and the thread-per-stream
-        // walk, a handful of small CTAs, hides best under the previous call's kernels.  Both leave the same table.
-        const bool par = ctx->walk_mode == 2 ||
-                         (ctx->walk_mode == 0 && raw_total / (uint64_t)nstreams >= (64u << 10) && nstreams <= 128);
+        // Streams of some length are walked time-parallel (speculative segments, a thread each, stitched per stream:
+        // four small kernels that use the whole chip -- an hour of audio in 0.2 ms instead of 107, the cfg2 batch in
+        // 0.10 ms instead of 0.25); a batch of short streams has its parallelism across streams and takes the
+        // thread-per-stream walk.  Both leave the same table.
+        const bool par = ctx->walk_mode == 2 || (ctx->walk_mode == 0 && raw_total / (uint64_t)nstreams >= (64u << 10));
         if (par) {
             uint32_t seg = ctx->walk_seg;
-            if (!seg) { // about eight segments per thread of the longest stream, 4 .. 64 KB
-                uint64_t longest = 0;
-                for (int i = 0; i < nstreams; i++) longest = std::max<uint64_t>(longest, hs[i].raw_len);
-                seg = (uint32_t)std::min<uint64_t>(65520, std::max<uint64_t>(4080, longest / 1024)) / 24 * 24;
-            }
+            if (!seg) // a thread per segment: some ten frames each, and at most a million segments in the batch
+                seg = (uint32_t)std::min<uint64_t>(65520, std::max<uint64_t>(4080, raw_total >> 20)) / 24 * 24;
             DevBuf &d_sparse = ctx->d_sparse[ctx->idx_cur], &d_segs = ctx->d_segs[ctx->idx_cur];
             CK(d_sparse.ensure(sizeof(L3FrameRec) * l3_walk_sparse_records(raw_total, (uint64_t)nstreams, seg)));
-            CK(d_segs.ensure(16 * l3_walk_segments(raw_total, (uint64_t)nstreams, seg)));
+            CK(d_segs.ensure(l3_walk_seg_bytes(raw_total, (uint64_t)nstreams, seg)));
             l3_launch_index_walk_par(ctx->raw_dev, d_streams.as<L3StreamRec>(), nstreams, d_scratch.as<L3FrameRec>(),
-                                     d_sparse.as<L3FrameRec>(), d_segs.p, seg, ist);
+                                     d_sparse.as<L3FrameRec>(), d_segs.p, l3_walk_segments(raw_total, (uint64_t)nstreams, seg), seg,
+                                     ist);
+            launches += 3; // (four kernels)
         } else
             l3_launch_index_walk(ctx->raw_dev, d_streams.as<L3StreamRec>(), nstreams, d_scratch.as<L3FrameRec>(), ist);
         launches++;

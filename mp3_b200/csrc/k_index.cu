@@ -98,112 +98,179 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
     streams[s].tag_delay_pad = tag_dp;
 }
 
-// ---- the same walk, time-parallel inside a stream (walk_par.h has the algorithm; this is its CTA mapping) ----
+// ---- the same walk, time-parallel inside a stream (walk_par.h has the algorithm; this is its mapping) ----
+// Four small kernels, so that ONE long stream is spread over the whole chip instead of one CTA:
+//   k_walk_first     a thread per stream: the first frame (phase 0)
+//   k_walk_segments  a thread per segment slot of the batch: the speculative walks (phase 1) -- an hour of audio is
+//                    some 14,000 segments of 4 KB, i.e. about ten frames per thread
+//   k_walk_stitch    a CTA per stream: do the guesses chain up (else one thread repairs), exclusive scan of the
+//                    segments' frame and main-data counts, the stream's totals (phases 2 and 3)
+//   k_walk_compact   a warp per segment slot: its records to their dense positions
+// Slot j of the batch belongs to the stream s with seg0(s) <= j < seg0(s + 1), seg0(s) = raw_off / seg + s (every
+// stream has at least the slots its own segments need); slots beyond a stream's last segment stay empty.
 constexpr int WP_THREADS = 128;
+static_assert(sizeof(L3WalkFirst) == 32 && sizeof(L3WalkSeg) == 16, "l3_walk_seg_bytes (kernels.h) sizes the buffer with these");
 
-__global__ void __launch_bounds__(WP_THREADS)
-k_index_walk_par(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams,
-                 L3FrameRec *__restrict__ dense, L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs,
-                 uint32_t seg, uint32_t seg_cap)
+__device__ __forceinline__ uint64_t wp_seg0(const L3StreamRec *streams, int s, uint32_t seg)
 {
-    const int s = blockIdx.x, tid = threadIdx.x;
+    return streams[s].raw_off / seg + (uint64_t)s;
+}
+// the stream that owns slot j (the last one whose first slot is <= j)
+__device__ __forceinline__ int wp_stream_of(const L3StreamRec *__restrict__ streams, int nstreams, uint32_t seg, uint64_t j)
+{
+    int lo = 0, hi = nstreams - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (wp_seg0(streams, mid, seg) <= j) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t wp_nseg(const L3WalkFirst &f, uint32_t len, uint32_t seg)
+{
+    return f.have ? (len - f.pf + seg - 1) / seg : 0u;
+}
+
+__global__ void k_walk_first(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams,
+                             L3WalkFirst *__restrict__ firsts)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nstreams) return;
     const L3StreamRec r = streams[s];
-    const uint8_t *buf = raw + r.raw_off;
-    const uint32_t len = r.raw_len;
-    const int streaming = (r.flags & L3S_STREAMING) != 0;
-    L3FrameRec *out = dense + scratch_base(r, (uint32_t)s);
-    const uint64_t seg0 = r.raw_off / seg + (uint64_t)s; // this stream's first segment record / sparse block
-    __shared__ L3WalkFirst sh_f;
-    __shared__ uint32_t sh_bad;
-    __shared__ uint32_t sh_scan[2][WP_THREADS];
+    L3WalkFirst f;
+    l3wp_first(raw + r.raw_off, r.raw_len, r.first_hdr, r.skip_frames, (r.flags & L3S_STREAMING) != 0, &f);
+    firsts[s] = f;
+    if (!f.have) { // no frame at all (or not yet): same outputs as the serial walk
+        streams[s].end_off = f.end0;
+        streams[s].first_off = 0;
+        streams[s].first_hdr = f.first;
+        streams[s].nframes = 0;
+        streams[s].payload_len = 0;
+        streams[s].tag_kind = L3T_NONE;
+        streams[s].tag_frames = streams[s].tag_bytes = streams[s].tag_delay_pad = 0;
+    }
+}
 
-    // ---- phase 0: the stream's first frame (one thread)
-    if (tid == 0) {
-        l3wp_first(buf, len, r.first_hdr, r.skip_frames, streaming, &sh_f);
-        sh_bad = 0;
-    }
-    __syncthreads();
-    const uint32_t first = sh_f.first, pf = sh_f.pf;
-    if (!sh_f.have) { // no frame at all (or not yet): same outputs as the serial walk
-        if (tid == 0) {
-            streams[s].end_off = sh_f.end0;
-            streams[s].first_off = 0;
-            streams[s].first_hdr = first;
-            streams[s].nframes = 0;
-            streams[s].payload_len = 0;
-            streams[s].tag_kind = L3T_NONE;
-            streams[s].tag_frames = streams[s].tag_bytes = streams[s].tag_delay_pad = 0;
-        }
-        return;
-    }
-    const uint32_t nseg = (len - pf + seg - 1) / seg;
+__global__ void __launch_bounds__(WP_THREADS)
+k_walk_segments(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams, int nstreams,
+                const L3WalkFirst *__restrict__ firsts, L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs,
+                uint64_t nslots, uint32_t seg, uint32_t seg_cap)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * WP_THREADS + threadIdx.x;
+    if (j >= nslots) return;
+    const int s = wp_stream_of(streams, nstreams, seg, j);
+    const L3StreamRec r = streams[s];
+    const L3WalkFirst f = firsts[s];
+    const uint64_t t = j - wp_seg0(streams, s, seg);
+    L3WalkSeg e;
+    e.start = e.exit = L3WP_NONE;
+    e.n = e.payload = 0;
+    if (t < wp_nseg(f, r.raw_len, seg))
+        l3wp_segment(raw + r.raw_off, r.raw_len, f.pf, seg, wp_nseg(f, r.raw_len, seg), (uint32_t)t, f.first,
+                     (r.flags & L3S_STREAMING) != 0, (uint32_t)s, sparse + j * seg_cap, &e);
+    segs[j] = e;
+}
+
+__global__ void __launch_bounds__(WP_THREADS)
+k_walk_stitch(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams,
+              const L3WalkFirst *__restrict__ firsts, L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs,
+              uint32_t seg, uint32_t seg_cap)
+{
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const L3WalkFirst f = firsts[s];
+    if (!f.have) return;
+    const L3StreamRec r = streams[s];
+    const uint8_t *buf = raw + r.raw_off;
+    const uint32_t len = r.raw_len, nseg = wp_nseg(f, len, seg);
+    const uint64_t seg0 = wp_seg0(streams, s, seg);
     L3WalkSeg *sg = segs + seg0;
     L3FrameRec *sp = sparse + seg0 * seg_cap;
-
-    // ---- phase 1: speculative walk of every segment
-    for (uint32_t t = tid; t < nseg; t += WP_THREADS) {
-        L3WalkSeg e;
-        l3wp_segment(buf, len, pf, seg, nseg, t, first, streaming, (uint32_t)s, sp + (size_t)t * seg_cap, &e);
-        sg[t] = e;
+    __shared__ uint32_t sh_bad, sh_last;
+    __shared__ uint32_t sh_n[WP_THREADS], sh_pay[WP_THREADS];
+    if (tid == 0) {
+        sh_bad = 0;
+        sh_last = 0; // 1 + the last segment that holds a frame
     }
     __syncthreads();
     // ---- phase 2: do the guesses chain up?  If not, one thread follows the chain and repairs.
     {
         uint32_t bad = 0;
         for (uint32_t t = tid; t < nseg; t += WP_THREADS)
-            if (!l3wp_chained(sg, t, pf)) bad = 1;
+            if (!l3wp_chained(sg, t, f.pf)) bad = 1;
         if (bad) sh_bad = 1;
     }
     __syncthreads();
     if (sh_bad) {
-        if (tid == 0) l3wp_repair(buf, len, pf, seg, nseg, first, streaming, (uint32_t)s, sp, seg_cap, sg);
+        if (tid == 0)
+            l3wp_repair(buf, len, f.pf, seg, nseg, f.first, (r.flags & L3S_STREAMING) != 0, (uint32_t)s, sp, seg_cap, sg);
         __syncthreads();
     }
-    // ---- phase 3: dense positions (exclusive scan of the segments' frame and main-data counts), compaction
-    uint32_t run_n = 0, run_pay = 0;
-    for (uint32_t t0 = 0; t0 < nseg; t0 += WP_THREADS) {
-        const uint32_t t = t0 + tid;
-        const uint32_t n = t < nseg ? sg[t].n : 0, pay = t < nseg ? sg[t].payload : 0;
-        sh_scan[0][tid] = n;
-        sh_scan[1][tid] = pay;
-        __syncthreads();
-        uint32_t bn = 0, bp = 0, cn = 0, cp = 0; // exclusive prefix inside the chunk, chunk totals
-        for (int k = 0; k < WP_THREADS; k++) {
-            if (k == tid) { bn = cn; bp = cp; }
-            cn += sh_scan[0][k];
-            cp += sh_scan[1][k];
-        }
-        if (t < nseg) {
-            const L3FrameRec *src = sp + (size_t)t * seg_cap;
-            L3FrameRec *dst = out + run_n + bn;
-            for (uint32_t i = 0; i < n; i++) {
-                L3FrameRec f = src[i];
-                f.payload_off += run_pay + bp;
-                dst[i] = f;
-            }
-        }
-        run_n += cn;
-        run_pay += cp;
-        __syncthreads();
+    // ---- phase 3: dense positions = exclusive scan of the segments' frame and main-data counts.  A thread owns a
+    // run of consecutive segments; the segment records' start / exit fields (dead from here on) take the bases.
+    const uint32_t per = (nseg + WP_THREADS - 1) / WP_THREADS, t0 = min(nseg, tid * per), t1 = min(nseg, t0 + per);
+    uint32_t cn = 0, cp = 0, last = 0;
+    for (uint32_t t = t0; t < t1; t++) {
+        const uint32_t n = sg[t].n;
+        cn += n;
+        cp += sg[t].payload;
+        if (n) last = t + 1;
+    }
+    sh_n[tid] = cn;
+    sh_pay[tid] = cp;
+    if (last) atomicMax(&sh_last, last);
+    __syncthreads();
+    uint32_t bn = 0, bp = 0, tot_n = 0, tot_p = 0;
+    for (int k = 0; k < WP_THREADS; k++) {
+        if (k == tid) { bn = tot_n; bp = tot_p; }
+        tot_n += sh_n[k];
+        tot_p += sh_pay[k];
+    }
+    for (uint32_t t = t0; t < t1; t++) {
+        L3WalkSeg e = sg[t];
+        e.start = bn;
+        e.exit = bp;
+        bn += e.n;
+        bp += e.payload;
+        sg[t] = e;
     }
     if (tid == 0) {
-        uint32_t end_off = sh_f.end0;
-        if (run_n) { // end of the last frame = header offset + length of the last record
-            const L3FrameRec lf = out[run_n - 1];
+        uint32_t end_off = f.end0;
+        if (sh_last) { // end of the last frame = header offset + length of the last record
+            const uint32_t t = sh_last - 1;
+            const L3FrameRec lf = sp[(size_t)t * seg_cap + (sg[t].n - 1)];
             L3Hdr h;
             l3_parse_hdr(lf.hdr, &h);
             end_off = lf.rel_off + (uint32_t)h.frame_len;
         }
         streams[s].end_off = end_off;
-        streams[s].first_off = pf;
-        streams[s].first_hdr = first;
-        streams[s].nframes = run_n;
-        streams[s].payload_len = run_pay;
-        streams[s].tag_kind = sh_f.tag_kind;
-        streams[s].tag_frames = sh_f.tag_frames;
-        streams[s].tag_bytes = sh_f.tag_bytes;
-        streams[s].tag_delay_pad = sh_f.tag_delay_pad;
+        streams[s].first_off = f.pf;
+        streams[s].first_hdr = f.first;
+        streams[s].nframes = tot_n;
+        streams[s].payload_len = tot_p;
+        streams[s].tag_kind = f.tag_kind;
+        streams[s].tag_frames = f.tag_frames;
+        streams[s].tag_bytes = f.tag_bytes;
+        streams[s].tag_delay_pad = f.tag_delay_pad;
+    }
+}
+
+__global__ void __launch_bounds__(WP_THREADS)
+k_walk_compact(const L3StreamRec *__restrict__ streams, int nstreams, const L3FrameRec *__restrict__ sparse,
+               const L3WalkSeg *__restrict__ segs, L3FrameRec *__restrict__ dense, uint64_t nslots, uint32_t seg,
+               uint32_t seg_cap)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * (WP_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= nslots) return;
+    const L3WalkSeg e = segs[j];
+    if (!e.n) return;
+    const int s = wp_stream_of(streams, nstreams, seg, j);
+    const L3FrameRec *src = sparse + j * seg_cap;
+    L3FrameRec *dst = dense + scratch_base(streams[s], (uint32_t)s) + e.start;
+    for (uint32_t i = lane; i < e.n; i += 32) {
+        L3FrameRec f = src[i];
+        f.payload_off += e.exit;
+        dst[i] = f;
     }
 }
 
@@ -539,11 +606,18 @@ void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams
     k_index_walk<<<(nstreams + 31) / 32, 32, 0, st>>>(raw, streams, nstreams, scratch);
 }
 void l3_launch_index_walk_par(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *dense, L3FrameRec *sparse,
-                              void *segs, uint32_t seg_bytes, cudaStream_t st)
+                              void *segs, uint64_t nslots, uint32_t seg_bytes, cudaStream_t st)
 {
     if (nstreams <= 0) return;
-    k_index_walk_par<<<nstreams, WP_THREADS, 0, st>>>(raw, streams, nstreams, dense, sparse, static_cast<L3WalkSeg *>(segs),
-                                                      seg_bytes, l3wp_seg_cap(seg_bytes));
+    L3WalkSeg *sg = static_cast<L3WalkSeg *>(segs);
+    L3WalkFirst *firsts = reinterpret_cast<L3WalkFirst *>(sg + nslots); // (behind the segment records, see l3_walk_seg_bytes)
+    const uint32_t cap = l3wp_seg_cap(seg_bytes);
+    k_walk_first<<<(nstreams + 31) / 32, 32, 0, st>>>(raw, streams, nstreams, firsts);
+    k_walk_segments<<<(unsigned)((nslots + WP_THREADS - 1) / WP_THREADS), WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, sparse, sg,
+                                                                                         nslots, seg_bytes, cap);
+    k_walk_stitch<<<nstreams, WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, sparse, sg, seg_bytes, cap);
+    k_walk_compact<<<(unsigned)((nslots + WP_THREADS / 32 - 1) / (WP_THREADS / 32)), WP_THREADS, 0, st>>>(streams, nstreams, sparse, sg, dense,
+                                                                                                  nslots, seg_bytes, cap);
 }
 void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
                           const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,

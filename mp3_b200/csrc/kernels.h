@@ -72,8 +72,9 @@ static inline uint64_t l3_index_scratch_records(uint64_t raw_total, uint64_t nst
 void l3_launch_publish(const void *src_dev, void *dst_pinned_host, size_t bytes, cudaStream_t st);
 void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *scratch,
                           cudaStream_t st);
-/* The time-parallel walk (a CTA per stream, segments of seg_bytes): same dense table as l3_launch_index_walk.
- * sparse: l3_walk_sparse_records() records; segs: l3_walk_segments() entries of 16 bytes. */
+/* The time-parallel walk (segments of seg_bytes walked speculatively by a thread each, then stitched per stream: four
+ * kernels): same dense table as l3_launch_index_walk.  nslots = l3_walk_segments(); sparse: l3_walk_sparse_records()
+ * records; segs: l3_walk_seg_bytes() bytes (the segment records and, behind them, one first-frame record per stream). */
 static inline uint64_t l3_walk_segments(uint64_t raw_total, uint64_t nstreams, uint32_t seg_bytes)
 {
     return raw_total / seg_bytes + nstreams + 2;
@@ -82,8 +83,12 @@ static inline uint64_t l3_walk_sparse_records(uint64_t raw_total, uint64_t nstre
 {
     return l3_walk_segments(raw_total, nstreams, seg_bytes) * (uint64_t)(seg_bytes / 24 + 2); /* l3wp_seg_cap() records per segment */
 }
+static inline uint64_t l3_walk_seg_bytes(uint64_t raw_total, uint64_t nstreams, uint32_t seg_bytes)
+{
+    return 16 * l3_walk_segments(raw_total, nstreams, seg_bytes) + 32 * nstreams + 32;
+}
 void l3_launch_index_walk_par(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *dense, L3FrameRec *sparse,
-                              void *segs, uint32_t seg_bytes, cudaStream_t st);
+                              void *segs, uint64_t nslots, uint32_t seg_bytes, cudaStream_t st);
 /* scratch == NULL: `frames` is already dense (host indexer) */
 void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
                           const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,

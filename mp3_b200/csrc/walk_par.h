@@ -9,7 +9,7 @@
  * than a segment) is walked again from the true position.  The dense table that results equals the serial walk's
  * (k_index_walk / host_index_stream) record for record.
  *
- * The CUDA kernel (k_index.cu: k_index_walk_par, a CTA per stream) and the host emulation the CPU tests run
+ * The CUDA kernels (k_index.cu: k_walk_first / _segments / _stitch / _compact) and the host emulation the CPU tests run
  * (tests/c/walk_emu.cpp) call the same functions, so the logic is tested without a GPU.
  * No reference code exists for this stage (/root/reference/README.md:1-84).
  */

@@ -1,4 +1,4 @@
-// Host emulation of k_index_walk_par: the same phase functions (mp3_b200/csrc/walk_par.h), the CTA's threads run one
+// Host emulation of the time-parallel walk (k_walk_* in k_index.cu): the same phase functions (mp3_b200/csrc/walk_par.h), the CTA's threads run one
 // after the other.  Built and driven by tests/test_walk_par_cpu.py; returns the dense frame table and how many segments
 // had to be repaired.
 #include <cstdint>

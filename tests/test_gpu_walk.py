@@ -1,5 +1,5 @@
-"""The time-parallel frame walk (k_index_walk_par: a CTA per stream, the bytes cut into segments that are walked
-speculatively and then stitched) must leave exactly the table of the serial walk (k_index_walk, one thread per
+"""The time-parallel frame walk (k_walk_first / _segments / _stitch / _compact: the bytes cut into segments that are walked
+speculatively, a thread each, and then stitched per stream) must leave exactly the table of the serial walk (k_index_walk, one thread per
 stream): frame records, stream records, tags, concealment, PCM -- on healthy streams of every kind, on damaged ones
 (where guesses are wrong and segments are repaired), with segments shorter than a frame (the chain skips segments),
 through the incremental interface, and on one long stream."""

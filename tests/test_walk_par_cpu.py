@@ -1,5 +1,5 @@
 """The time-parallel frame walk's logic on the CPU: tests/c/walk_emu.cpp runs the phase functions of
-mp3_b200/csrc/walk_par.h (the ones the CUDA kernel k_index_walk_par calls) one thread after the other; the frame
+mp3_b200/csrc/walk_par.h (the ones the CUDA kernels k_walk_* call) one thread after the other; the frame
 table must equal the serial host walk (mp3b_index_stream_host) for every segment length, on healthy and damaged streams,
 and healthy streams must need no repair at the default segment length."""
 import ctypes
