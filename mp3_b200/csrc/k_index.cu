@@ -107,21 +107,18 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
 //                    segments' frame and main-data counts, the stream's totals (phases 2 and 3)
 //   k_walk_compact   a warp per segment slot: its records to their dense positions
 // Slot j of the batch belongs to the stream s with seg0(s) <= j < seg0(s + 1), seg0(s) = raw_off / seg + s (every
-// stream has at least the slots its own segments need); slots beyond a stream's last segment stay empty.
+// stream has at least the slots its own segments need; k_walk_first leaves the table); slots beyond a stream's last
+// segment stay empty.
 constexpr int WP_THREADS = 128;
 static_assert(sizeof(L3WalkFirst) == 32 && sizeof(L3WalkSeg) == 16, "l3_walk_seg_bytes (kernels.h) sizes the buffer with these");
 
-__device__ __forceinline__ uint64_t wp_seg0(const L3StreamRec *streams, int s, uint32_t seg)
-{
-    return streams[s].raw_off / seg + (uint64_t)s;
-}
 // the stream that owns slot j (the last one whose first slot is <= j)
-__device__ __forceinline__ int wp_stream_of(const L3StreamRec *__restrict__ streams, int nstreams, uint32_t seg, uint64_t j)
+__device__ __forceinline__ int wp_stream_of(const uint32_t *__restrict__ seg0, int nstreams, uint32_t j)
 {
     int lo = 0, hi = nstreams - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (wp_seg0(streams, mid, seg) <= j) lo = mid;
+        if (__ldg(seg0 + mid) <= j) lo = mid;
         else hi = mid - 1;
     }
     return lo;
@@ -132,11 +129,12 @@ __device__ __forceinline__ uint32_t wp_nseg(const L3WalkFirst &f, uint32_t len, 
 }
 
 __global__ void k_walk_first(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams,
-                             L3WalkFirst *__restrict__ firsts)
+                             L3WalkFirst *__restrict__ firsts, uint32_t *__restrict__ seg0, uint32_t seg)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nstreams) return;
     const L3StreamRec r = streams[s];
+    seg0[s] = (uint32_t)(r.raw_off / seg) + (uint32_t)s;
     L3WalkFirst f;
     l3wp_first(raw + r.raw_off, r.raw_len, r.first_hdr, r.skip_frames, (r.flags & L3S_STREAMING) != 0, &f);
     firsts[s] = f;
@@ -153,28 +151,28 @@ __global__ void k_walk_first(const uint8_t *__restrict__ raw, L3StreamRec *__res
 
 __global__ void __launch_bounds__(WP_THREADS)
 k_walk_segments(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__ streams, int nstreams,
-                const L3WalkFirst *__restrict__ firsts, L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs,
-                uint64_t nslots, uint32_t seg, uint32_t seg_cap)
+                const L3WalkFirst *__restrict__ firsts, const uint32_t *__restrict__ seg0,
+                L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs, uint32_t nslots, uint32_t seg, uint32_t seg_cap)
 {
-    const uint64_t j = (uint64_t)blockIdx.x * WP_THREADS + threadIdx.x;
+    const uint32_t j = blockIdx.x * WP_THREADS + threadIdx.x;
     if (j >= nslots) return;
-    const int s = wp_stream_of(streams, nstreams, seg, j);
+    const int s = wp_stream_of(seg0, nstreams, j);
     const L3StreamRec r = streams[s];
     const L3WalkFirst f = firsts[s];
-    const uint64_t t = j - wp_seg0(streams, s, seg);
+    const uint32_t t = j - seg0[s];
     L3WalkSeg e;
     e.start = e.exit = L3WP_NONE;
     e.n = e.payload = 0;
     if (t < wp_nseg(f, r.raw_len, seg))
-        l3wp_segment(raw + r.raw_off, r.raw_len, f.pf, seg, wp_nseg(f, r.raw_len, seg), (uint32_t)t, f.first,
-                     (r.flags & L3S_STREAMING) != 0, (uint32_t)s, sparse + j * seg_cap, &e);
+        l3wp_segment(raw + r.raw_off, r.raw_len, f.pf, seg, wp_nseg(f, r.raw_len, seg), t, f.first,
+                     (r.flags & L3S_STREAMING) != 0, (uint32_t)s, sparse + (size_t)j * seg_cap, &e);
     segs[j] = e;
 }
 
 __global__ void __launch_bounds__(WP_THREADS)
 k_walk_stitch(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams, int nstreams,
-              const L3WalkFirst *__restrict__ firsts, L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs,
-              uint32_t seg, uint32_t seg_cap)
+              const L3WalkFirst *__restrict__ firsts, const uint32_t *__restrict__ seg0v,
+              L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs, uint32_t seg, uint32_t seg_cap)
 {
     const int s = blockIdx.x, tid = threadIdx.x;
     const L3WalkFirst f = firsts[s];
@@ -182,27 +180,38 @@ k_walk_stitch(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams
     const L3StreamRec r = streams[s];
     const uint8_t *buf = raw + r.raw_off;
     const uint32_t len = r.raw_len, nseg = wp_nseg(f, len, seg);
-    const uint64_t seg0 = wp_seg0(streams, s, seg);
+    const size_t seg0 = seg0v[s];
     L3WalkSeg *sg = segs + seg0;
     L3FrameRec *sp = sparse + seg0 * seg_cap;
-    __shared__ uint32_t sh_bad, sh_last;
+    __shared__ uint32_t sh_bad, sh_last, sh_from;
     __shared__ uint32_t sh_n[WP_THREADS], sh_pay[WP_THREADS];
     if (tid == 0) {
-        sh_bad = 0;
-        sh_last = 0; // 1 + the last segment that holds a frame
+        sh_bad = L3WP_NONE; // the first segment at or behind sh_from that does not chain up
+        sh_from = 0;
+        sh_last = 0;        // 1 + the last segment that holds a frame
     }
     __syncthreads();
-    // ---- phase 2: do the guesses chain up?  If not, one thread follows the chain and repairs.
-    {
-        uint32_t bad = 0;
-        for (uint32_t t = tid; t < nseg; t += WP_THREADS)
-            if (!l3wp_chained(sg, t, f.pf)) bad = 1;
-        if (bad) sh_bad = 1;
-    }
-    __syncthreads();
-    if (sh_bad) {
-        if (tid == 0)
-            l3wp_repair(buf, len, f.pf, seg, nseg, f.first, (r.flags & L3S_STREAMING) != 0, (uint32_t)s, sp, seg_cap, sg);
+    // ---- phase 2: do the guesses chain up?  Where they do not, one thread follows the chain from the first such
+    // segment until the guesses hold again (l3wp_repair_run); the search for the next one is parallel again.  A stream
+    // that needs many such rounds (damage all over, segments shorter than its frames) gets one serial pass instead.
+    for (int round = 0;; round++) {
+        const uint32_t from = sh_from;
+        uint32_t bad = L3WP_NONE;
+        for (uint32_t t = from + tid; t < nseg; t += WP_THREADS)
+            if (!l3wp_chained(sg, t, f.pf)) {
+                bad = t;
+                break;
+            }
+        if (bad != L3WP_NONE) atomicMin(&sh_bad, bad);
+        __syncthreads();
+        const uint32_t t0 = sh_bad;
+        if (t0 == L3WP_NONE) break;
+        __syncthreads();
+        if (tid == 0) {
+            sh_from = l3wp_repair_run(buf, len, f.pf, seg, nseg, f.first, (r.flags & L3S_STREAMING) != 0, (uint32_t)s, sp, seg_cap, sg,
+                                      t0, round >= 32);
+            sh_bad = L3WP_NONE;
+        }
         __syncthreads();
     }
     // ---- phase 3: dense positions = exclusive scan of the segments' frame and main-data counts.  A thread owns a
@@ -255,17 +264,17 @@ k_walk_stitch(const uint8_t *__restrict__ raw, L3StreamRec *__restrict__ streams
 }
 
 __global__ void __launch_bounds__(WP_THREADS)
-k_walk_compact(const L3StreamRec *__restrict__ streams, int nstreams, const L3FrameRec *__restrict__ sparse,
-               const L3WalkSeg *__restrict__ segs, L3FrameRec *__restrict__ dense, uint64_t nslots, uint32_t seg,
-               uint32_t seg_cap)
+k_walk_compact(const L3StreamRec *__restrict__ streams, int nstreams, const uint32_t *__restrict__ seg0,
+               const L3FrameRec *__restrict__ sparse, const L3WalkSeg *__restrict__ segs, L3FrameRec *__restrict__ dense,
+               uint32_t nslots, uint32_t seg_cap)
 {
-    const uint64_t j = (uint64_t)blockIdx.x * (WP_THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t j = blockIdx.x * (WP_THREADS / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= nslots) return;
     const L3WalkSeg e = segs[j];
     if (!e.n) return;
-    const int s = wp_stream_of(streams, nstreams, seg, j);
-    const L3FrameRec *src = sparse + j * seg_cap;
+    const int s = wp_stream_of(seg0, nstreams, j);
+    const L3FrameRec *src = sparse + (size_t)j * seg_cap;
     L3FrameRec *dst = dense + scratch_base(streams[s], (uint32_t)s) + e.start;
     for (uint32_t i = lane; i < e.n; i += 32) {
         L3FrameRec f = src[i];
@@ -606,18 +615,21 @@ void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams
     k_index_walk<<<(nstreams + 31) / 32, 32, 0, st>>>(raw, streams, nstreams, scratch);
 }
 void l3_launch_index_walk_par(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *dense, L3FrameRec *sparse,
-                              void *segs, uint64_t nslots, uint32_t seg_bytes, cudaStream_t st)
+                              void *segs, uint64_t nslots64, uint32_t seg_bytes, cudaStream_t st)
 {
     if (nstreams <= 0) return;
+    const uint32_t nslots = (uint32_t)nslots64; // (the caller sizes the segments so that a batch has a few million at most)
     L3WalkSeg *sg = static_cast<L3WalkSeg *>(segs);
-    L3WalkFirst *firsts = reinterpret_cast<L3WalkFirst *>(sg + nslots); // (behind the segment records, see l3_walk_seg_bytes)
+    // behind the segment records: a first-frame record and the first slot of every stream (see l3_walk_seg_bytes)
+    L3WalkFirst *firsts = reinterpret_cast<L3WalkFirst *>(sg + nslots);
+    uint32_t *seg0 = reinterpret_cast<uint32_t *>(firsts + nstreams);
     const uint32_t cap = l3wp_seg_cap(seg_bytes);
-    k_walk_first<<<(nstreams + 31) / 32, 32, 0, st>>>(raw, streams, nstreams, firsts);
-    k_walk_segments<<<(unsigned)((nslots + WP_THREADS - 1) / WP_THREADS), WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, sparse, sg,
-                                                                                         nslots, seg_bytes, cap);
-    k_walk_stitch<<<nstreams, WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, sparse, sg, seg_bytes, cap);
-    k_walk_compact<<<(unsigned)((nslots + WP_THREADS / 32 - 1) / (WP_THREADS / 32)), WP_THREADS, 0, st>>>(streams, nstreams, sparse, sg, dense,
-                                                                                                  nslots, seg_bytes, cap);
+    k_walk_first<<<(nstreams + 31) / 32, 32, 0, st>>>(raw, streams, nstreams, firsts, seg0, seg_bytes);
+    k_walk_segments<<<(nslots + WP_THREADS - 1) / WP_THREADS, WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, seg0, sparse, sg, nslots,
+                                                                             seg_bytes, cap);
+    k_walk_stitch<<<nstreams, WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, seg0, sparse, sg, seg_bytes, cap);
+    k_walk_compact<<<(nslots + WP_THREADS / 32 - 1) / (WP_THREADS / 32), WP_THREADS, 0, st>>>(streams, nstreams, seg0, sparse, sg, dense, nslots,
+                                                                                      cap);
 }
 void l3_launch_side_parse(const uint8_t *raw, const L3StreamRec *streams, int nstreams, L3FrameRec *frames,
                           const L3FrameRec *scratch, uint32_t nframes, const L3DevTables &T, L3UnitDesc *units,

@@ -74,7 +74,7 @@ void l3_launch_index_walk(const uint8_t *raw, L3StreamRec *streams, int nstreams
                           cudaStream_t st);
 /* The time-parallel walk (segments of seg_bytes walked speculatively by a thread each, then stitched per stream: four
  * kernels): same dense table as l3_launch_index_walk.  nslots = l3_walk_segments(); sparse: l3_walk_sparse_records()
- * records; segs: l3_walk_seg_bytes() bytes (the segment records and, behind them, one first-frame record per stream). */
+ * records; segs: l3_walk_seg_bytes() bytes (the segment records and, behind them, one first-frame record and one first-slot index per stream). */
 static inline uint64_t l3_walk_segments(uint64_t raw_total, uint64_t nstreams, uint32_t seg_bytes)
 {
     return raw_total / seg_bytes + nstreams + 2;
@@ -85,7 +85,7 @@ static inline uint64_t l3_walk_sparse_records(uint64_t raw_total, uint64_t nstre
 }
 static inline uint64_t l3_walk_seg_bytes(uint64_t raw_total, uint64_t nstreams, uint32_t seg_bytes)
 {
-    return 16 * l3_walk_segments(raw_total, nstreams, seg_bytes) + 32 * nstreams + 32;
+    return 16 * l3_walk_segments(raw_total, nstreams, seg_bytes) + (32 + 4) * nstreams + 32;
 }
 void l3_launch_index_walk_par(const uint8_t *raw, L3StreamRec *streams, int nstreams, L3FrameRec *dense, L3FrameRec *sparse,
                               void *segs, uint64_t nslots, uint32_t seg_bytes, cudaStream_t st);

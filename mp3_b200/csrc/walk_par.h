@@ -115,68 +115,122 @@ L3_HD uint32_t l3wp_span(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t 
     return ended ? L3WP_END : p;
 }
 
+/* the guess: is p the first header of this stream that is followed by another one? */
+L3_HD int l3wp_entry_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t first)
+{
+    L3Hdr h, h2;
+    uint32_t w;
+    if (l3_frame_at(buf, len, p, first, &h, &w) != 1) return 0;
+    const uint32_t q = p + (uint32_t)h.frame_len;
+    if (q + 4 <= len) {
+        const uint32_t w2 = l3_load_be32(buf + q);
+        if (!l3_parse_hdr(w2, &h2) || !l3_same_stream(w2, first)) return 0;
+    }
+    return 1;
+}
+
+L3_HD uint32_t l3wp_ctz(uint32_t x) /* x != 0 */
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+
+/* 16 bytes from a 16-byte aligned address, as four little-endian words */
+L3_HD void l3wp_load16(const uint8_t *p, uint32_t w[4])
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#else
+    for (int k = 0; k < 4; k++)
+        w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+#endif
+}
+
+/* The first entry point in [lo, hi) (positions p with p + 4 <= len), or L3WP_NONE.  A header starts with 0xFF: 255 of
+ * 256 positions are rejected on that byte, sixteen positions per load where the address allows it. */
+L3_HD uint32_t l3wp_guess(const uint8_t *buf, uint32_t len, uint32_t lo, uint32_t hi, uint32_t first)
+{
+    uint32_t p = lo;
+    while (p < hi && p + 4 <= len) {
+        if ((((uintptr_t)(buf + p)) & 15u) == 0 && hi - p >= 16 && len - p >= 19) { /* 16 positions, all inside both bounds */
+            uint32_t w[4];
+            l3wp_load16(buf + p, w);
+            for (int k = 0; k < 4; k++) {
+                /* bit 8 j + 7 set iff byte j of w[k] is 0xFF (exact: no carries between the bytes) */
+                const uint32_t v = ~w[k];
+                uint32_t ff = ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v | 0x7f7f7f7fu);
+                while (ff) {
+                    const uint32_t q = p + 4u * (uint32_t)k + (l3wp_ctz(ff) >> 3);
+                    if (l3wp_entry_at(buf, len, q, first)) return q;
+                    ff &= ff - 1;
+                }
+            }
+            p += 16;
+            continue;
+        }
+        if (buf[p] == 0xFF && l3wp_entry_at(buf, len, p, first)) return p;
+        p++;
+    }
+    return L3WP_NONE;
+}
+
 /* phase 1: segment t of [pf, len) -- guess the entry, walk to the segment's end, records to `sp` (this segment's block) */
 L3_HD void l3wp_segment(const uint8_t *buf, uint32_t len, uint32_t pf, uint32_t seg, uint32_t nseg, uint32_t t,
                         uint32_t first, int streaming, uint32_t stream, L3FrameRec *sp, L3WalkSeg *out)
 {
     const uint32_t lo = pf + t * seg, hi = (t + 1 < nseg) ? lo + seg : L3WP_NONE;
-    uint32_t g = lo;
-    if (t) { /* the first header of this stream in the segment that is followed by another one */
-        g = L3WP_NONE;
-        for (uint32_t p = lo; p < hi && p + 4 <= len; p++) {
-            if (buf[p] != 0xFF) continue; /* (cheap reject: 255 of 256 positions) */
-            L3Hdr h, h2;
-            uint32_t w;
-            if (l3_frame_at(buf, len, p, first, &h, &w) != 1) continue;
-            const uint32_t q = p + (uint32_t)h.frame_len;
-            if (q + 4 <= len) {
-                const uint32_t w2 = l3_load_be32(buf + q);
-                if (!l3_parse_hdr(w2, &h2) || !l3_same_stream(w2, first)) continue;
-            }
-            g = p;
-            break;
-        }
-    }
+    const uint32_t g = t ? l3wp_guess(buf, len, lo, hi, first) : lo;
     out->start = g;
     out->exit = g;
     out->n = out->payload = 0;
     if (g != L3WP_NONE) out->exit = l3wp_span(buf, len, g, hi, first, streaming, stream, sp, &out->n, &out->payload);
 }
 
-/* phase 2 (one thread, only when some guess was wrong): follow the chain through the segments in order; a segment
- * the chain enters elsewhere than guessed is walked again from the true position, a segment it does not enter
- * (a long frame spans it, or the chain has ended) is voided.  `sparse` = the stream's blocks of `cap` records. */
-L3_HD void l3wp_repair(const uint8_t *buf, uint32_t len, uint32_t pf, uint32_t seg, uint32_t nseg, uint32_t first,
-                       int streaming, uint32_t stream, L3FrameRec *sparse, uint32_t cap, L3WalkSeg *sg)
+/* the guess of segment t is consistent with the chain arriving at `want` (the exit of its predecessor, pf for t = 0) */
+L3_HD int l3wp_chained_to(const L3WalkSeg *e, uint32_t want)
 {
-    uint32_t cur = pf;
-    int dead = 0;
-    for (uint32_t t = 0; t < nseg; t++) {
+    if (want == L3WP_END) return e->n == 0; /* the chain has ended: later segments are empty */
+    return e->start == want;
+}
+/* phase 2's parallel pre-check */
+L3_HD int l3wp_chained(const L3WalkSeg *sg, uint32_t t, uint32_t pf) { return l3wp_chained_to(&sg[t], t ? sg[t - 1].exit : pf); }
+
+/* phase 2 (one thread, only when some guess was wrong): segment t0 is the first one that does not chain up (all before
+ * it do).  Follow the chain from there: a segment the chain enters elsewhere than guessed is walked again from the
+ * true position, a segment it does not enter (a long frame spans it, or the chain has ended) is voided; every
+ * segment's `exit` becomes the chain's position behind it.  Stops at the first segment that chains up with what was
+ * repaired -- from there on the pre-check's verdicts hold again -- and returns it (nseg: none); with `to_end` it goes
+ * through all remaining segments instead.  `sparse` = the stream's blocks of `cap` records. */
+L3_HD uint32_t l3wp_repair_run(const uint8_t *buf, uint32_t len, uint32_t pf, uint32_t seg, uint32_t nseg, uint32_t first,
+                               int streaming, uint32_t stream, L3FrameRec *sparse, uint32_t cap, L3WalkSeg *sg, uint32_t t0,
+                               int to_end)
+{
+    uint32_t cur = t0 ? sg[t0 - 1].exit : pf;
+    for (uint32_t t = t0; t < nseg; t++) {
         const uint32_t lo = pf + t * seg, hi = (t + 1 < nseg) ? lo + seg : L3WP_NONE;
         L3WalkSeg e = sg[t];
-        if (dead || cur >= hi) { /* the chain does not enter this segment */
-            if (e.n) {
-                e.n = e.payload = 0;
-                sg[t] = e;
-            }
+        if (t > t0 && l3wp_chained_to(&e, cur) && (cur == L3WP_END || cur < hi)) {
+            if (!to_end) return t;
+            if (cur != L3WP_END) cur = e.exit;
             continue;
         }
-        if (e.start != cur) {
-            e.start = cur;
-            e.exit = l3wp_span(buf, len, cur, hi, first, streaming, stream, sparse + (size_t)t * cap, &e.n, &e.payload);
+        if (cur == L3WP_END || cur >= hi) { /* the chain does not enter this segment */
+            e.start = L3WP_NONE;
+            e.exit = cur;
+            e.n = e.payload = 0;
             sg[t] = e;
+            continue;
         }
-        if (e.exit == L3WP_END) dead = 1;
-        else cur = e.exit;
+        e.start = cur;
+        e.exit = l3wp_span(buf, len, cur, hi, first, streaming, stream, sparse + (size_t)t * cap, &e.n, &e.payload);
+        sg[t] = e;
+        cur = e.exit;
     }
-}
-
-/* the guess of segment t is consistent with its predecessor (phase 2's parallel pre-check) */
-L3_HD int l3wp_chained(const L3WalkSeg *sg, uint32_t t, uint32_t pf)
-{
-    const uint32_t want = t ? sg[t - 1].exit : pf;
-    if (want == L3WP_END) return sg[t].n == 0; /* the chain has ended: later segments must be empty */
-    return sg[t].start == want;
+    return nseg;
 }
 
 #endif

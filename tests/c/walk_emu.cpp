@@ -29,7 +29,14 @@ extern "C" int walk_emu(const uint8_t *buf, uint32_t len, uint32_t seg, int stre
     uint32_t bad = 0;
     for (uint32_t t = 0; t < nseg; t++) bad += !l3wp_chained(sg.data(), t, f.pf);
     *bad_segments = bad;
-    if (bad) l3wp_repair(buf, len, f.pf, seg, nseg, f.first, streaming, 0, sparse.data(), cap, sg.data());
+    // as k_walk_stitch does: repair run by run from the first segment that does not chain up, one pass to the end
+    // after 32 rounds
+    for (uint32_t from = 0, round = 0; from < nseg; round++) {
+        uint32_t t0 = from;
+        while (t0 < nseg && l3wp_chained(sg.data(), t0, f.pf)) t0++;
+        if (t0 == nseg) break;
+        from = l3wp_repair_run(buf, len, f.pf, seg, nseg, f.first, streaming, 0, sparse.data(), cap, sg.data(), t0, round >= 32);
+    }
     uint32_t n = 0, pay = 0;
     for (uint32_t t = 0; t < nseg; t++) {
         if (sg[t].n > cap) return -2;

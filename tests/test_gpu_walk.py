@@ -33,8 +33,15 @@ def streams(synth_mod):
         out.append(a[rng.integers(1, 700):].tobytes())        # lost head
         out.append(id3 + s)                                   # tag in front
         out.append(s[:900] + bytes(rng.integers(0, 256, 1500, dtype=np.uint8)) + s[900:])   # junk inside
+    long_ = [synth_mod.make_stream(nframes=300, seed=9, mode=1, bitrate_kbps=320, blocks=1, mixed_pct=25, fill_lo_pct=35),
+             synth_mod.make_stream(nframes=400, seed=10, vbr_min_kbps=32, vbr_max_kbps=320, blocks=1)]
+    # wrong guesses by construction: false chain entries inside the main data, every few segments
+    out += [plant_false_entries(long_[0]), plant_false_entries(long_[1], every=1700, start=900)]
     out += [b"", b"\xff" * 40, bytes(rng.integers(0, 256, 5000, dtype=np.uint8)), bytes([0xFF, 0xFB, 0x90, 0x00]) * 300]
     return out
+
+
+from test_walk_par_cpu import plant_false_entries  # noqa: E402
 
 
 def _decode(mp3b, streams, monkeypatch, mode, seg=None):

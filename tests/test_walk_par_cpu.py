@@ -47,6 +47,27 @@ def serial(data):
     return fr, tag
 
 
+def plant_false_entries(s, every=2500, start=2000):
+    """Copies of the stream's own second header written into the main data of later frames, each followed by another
+    copy one frame length on: positions that look exactly like the chain to a walk that starts in the middle (a wrong
+    guess of the time-parallel walk), while the chain itself never reads them."""
+    import mp3_b200
+    fr, _, _ = mp3_b200.index_stream_host(s)
+    a = bytearray(s)
+    if len(fr) < 8:
+        return bytes(a)
+    hdr = bytes(a[int(fr["offset"][1]): int(fr["offset"][1]) + 4])
+    flen = int(fr["offset"][2]) - int(fr["offset"][1])
+    starts = fr["offset"].astype(np.int64)
+    for x in range(start, len(a) - 2 * flen - 8, every):
+        # keep clear of the real headers and side info: 40 bytes behind a frame start at least, both copies
+        ok = all(np.min(np.abs(starts - y - d)) > 44 for y in (x, x + flen) for d in (0,))
+        if ok:
+            a[x: x + 4] = hdr
+            a[x + flen: x + flen + 4] = hdr
+    return bytes(a)
+
+
 @pytest.fixture(scope="module")
 def streams(synth_mod):
     allc = dict(cases.FF)
@@ -71,6 +92,8 @@ def streams(synth_mod):
         bad.append(a[rng.integers(1, 700):].tobytes())
         bad.append(id3 + s)
         bad.append(s[:900] + bytes(rng.integers(0, 256, 1500, dtype=np.uint8)) + s[900:])
+    # wrong guesses by construction: false chain entries inside the main data, every few segments
+    bad += [plant_false_entries(good[-3]), plant_false_entries(good[-2], every=1700, start=900)]
     bad += [b"", b"\xff" * 40, bytes(rng.integers(0, 256, 5000, dtype=np.uint8)), bytes([0xFF, 0xFB, 0x90, 0x00]) * 300]
     return good, bad
 
