@@ -268,8 +268,10 @@ L3_HD int l3_frame_at(const uint8_t *buf, uint32_t len, uint32_t p, uint32_t fir
 {
     if (p + 4 > len) return 0;
     uint32_t w = l3_load_be32(buf + p);
-    if (!l3_parse_hdr(w, h)) return 0;
+    /* (the cheap test first: main data is full of 0xFF 0xFx pairs -- five per frame in the generator's streams --,
+     * and the time-parallel walk tries every one of them as an entry point) */
     if (first && !l3_same_stream(w, first)) return 0;
+    if (!l3_parse_hdr(w, h)) return 0;
     if (h->frame_len < 4 + (h->crc ? 2 : 0) + h->side_len) return 0;
     if (p + (uint32_t)h->frame_len > len) return 2;
     *word = w;
