@@ -110,6 +110,9 @@ __global__ void k_index_walk(const uint8_t *__restrict__ raw, L3StreamRec *__res
 // stream has at least the slots its own segments need; k_walk_first leaves the table); slots beyond a stream's last
 // segment stay empty.
 constexpr int WP_THREADS = 128;
+#ifndef WP_SPREAD
+#define WP_SPREAD 4
+#endif
 static_assert(sizeof(L3WalkFirst) == 32 && sizeof(L3WalkSeg) == 16, "l3_walk_seg_bytes (kernels.h) sizes the buffer with these");
 
 // the stream that owns slot j (the last one whose first slot is <= j)
@@ -154,8 +157,11 @@ k_walk_segments(const uint8_t *__restrict__ raw, const L3StreamRec *__restrict__
                 const L3WalkFirst *__restrict__ firsts, const uint32_t *__restrict__ seg0,
                 L3FrameRec *__restrict__ sparse, L3WalkSeg *__restrict__ segs, uint32_t nslots, uint32_t seg, uint32_t seg_cap)
 {
-    const uint32_t j = blockIdx.x * WP_THREADS + threadIdx.x;
-    if (j >= nslots) return;
+    // Only every WP_SPREAD-th lane works.  The kernel is bound by latency, not by throughput: the lanes of a warp part
+    // ways in the entry search (sync look-alikes in the main data), so a warp's time is the SUM of its lanes'
+    // searches; spreading the segments over more warps shortens every warp's serial instruction stream.
+    const uint32_t gt = blockIdx.x * WP_THREADS + threadIdx.x, j = gt / WP_SPREAD;
+    if (gt % WP_SPREAD || j >= nslots) return;
     const int s = wp_stream_of(seg0, nstreams, j);
     const L3StreamRec r = streams[s];
     const L3WalkFirst f = firsts[s];
@@ -625,7 +631,7 @@ void l3_launch_index_walk_par(const uint8_t *raw, L3StreamRec *streams, int nstr
     uint32_t *seg0 = reinterpret_cast<uint32_t *>(firsts + nstreams);
     const uint32_t cap = l3wp_seg_cap(seg_bytes);
     k_walk_first<<<(nstreams + 31) / 32, 32, 0, st>>>(raw, streams, nstreams, firsts, seg0, seg_bytes);
-    k_walk_segments<<<(nslots + WP_THREADS - 1) / WP_THREADS, WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, seg0, sparse, sg, nslots,
+    k_walk_segments<<<(unsigned)(((uint64_t)nslots * WP_SPREAD + WP_THREADS - 1) / WP_THREADS), WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, seg0, sparse, sg, nslots,
                                                                              seg_bytes, cap);
     k_walk_stitch<<<nstreams, WP_THREADS, 0, st>>>(raw, streams, nstreams, firsts, seg0, sparse, sg, seg_bytes, cap);
     k_walk_compact<<<(nslots + WP_THREADS / 32 - 1) / (WP_THREADS / 32), WP_THREADS, 0, st>>>(streams, nstreams, seg0, sparse, sg, dense, nslots,
