@@ -124,7 +124,13 @@ struct mp3b_ctx {
     DevBuf d_sparse[2], d_segs[2];         // time-parallel walk: per-segment records and bookkeeping
     int walk_mode = 0;                     // 0 = choose by batch shape, 1 = thread per stream, 2 = CTA per stream (MP3B_WALK)
     uint32_t walk_seg = 0;                 // bytes per segment of the time-parallel walk (MP3B_WALK_SEG); 0 = by stream length
-    DevBuf d_frames, d_units, d_gran, d_arena, d_tiles, d_counter, d_pcm, d_pcm2;
+    DevBuf d_frames, d_units, d_gran, d_arena, d_pcm, d_pcm2;
+    // Two sets as well (same index): the tile table and the concealment counter of call N+1 are written on the index
+    // stream, behind its walk, while call N's back end still reads call N's -- so that on the context's stream nothing
+    // but kernels stands between two calls (the table uploads and the memset used to: 35 us of a 3.76-ms step).
+    DevBuf d_tiles[2], d_counter[2];
+    cudaEvent_t end_ev[2] = {nullptr, nullptr}; // the call that used set i has finished on the context's stream
+    cudaEvent_t tables_done = nullptr;          // this call's tables are in place (index stream)
     int pcm_cur = 0;                       // PCM arena of the last decode (two alternate in sink mode)
     cudaEvent_t pcm_free[2] = {nullptr, nullptr}; // sink copies out of arena i have finished
     DevBuf &pcm() { return pcm_cur ? d_pcm2 : d_pcm; }
@@ -369,6 +375,8 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     DevBuf &d_raw = ctx->d_raw[ctx->idx_cur], &d_streams = ctx->d_streams[ctx->idx_cur],
            &d_scratch = ctx->d_scratch[ctx->idx_cur];
     cudaStream_t ist = ahead ? ctx->index_stream : st;
+    // the call before the previous one used this set of buffers: nothing of this call may touch them before it is done
+    if (ahead) CK(cudaStreamWaitEvent(ist, ctx->end_ev[ctx->idx_cur], 0));
 
     // the pinned staging tables (stream records, tiles, frames) are rewritten below: the previous call's
     // asynchronous uploads out of them must have executed (they are early in that call, so this is short)
@@ -545,8 +553,9 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     CK(ctx->d_units.ensure(sizeof(L3UnitDesc) * std::max<uint64_t>(units, 1)));
     CK(ctx->d_gran.ensure(sizeof(uint32_t) * std::max<uint64_t>(grans, 1)));
     CK(ctx->d_arena.ensure(ctx->arena_bytes));
-    CK(ctx->d_tiles.ensure(sizeof(uint4) * std::max<uint64_t>(ntiles, 1)));
-    CK(ctx->d_counter.ensure(64));
+    DevBuf &d_tiles = ctx->d_tiles[ctx->idx_cur], &d_counter = ctx->d_counter[ctx->idx_cur];
+    CK(d_tiles.ensure(sizeof(uint4) * std::max<uint64_t>(ntiles, 1)));
+    CK(d_counter.ensure(64));
     CK(ctx->h_counter.ensure(64));
 
     const bool keep = ctx->opts.keep_stages != 0;
@@ -605,18 +614,25 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     }
 
     if (ctx->poison) {
-        for (DevBuf *b : {&ctx->d_frames, &ctx->d_units, &ctx->d_gran, &ctx->d_arena, &ctx->d_tiles, &ctx->d_is, &ctx->d_sf,
+        for (DevBuf *b : {&ctx->d_frames, &ctx->d_units, &ctx->d_gran, &ctx->d_arena, &d_tiles, &ctx->d_is, &ctx->d_sf,
                           &ctx->d_nzv, &ctx->d_hkeys, &ctx->d_hperm, &ctx->d_hstate, &ctx->d_xr, &ctx->d_imd, &ctx->d_sb, &ctx->d_sb2, &ctx->pcm()})
             if (b->p && b->cap) CK(cudaMemsetAsync(b->p, 0xFF, b->cap, st));
     }
     if (ahead && where == MP3B_HOST && !nstreams) CK(cudaStreamSynchronize(ist));
-    if (nstreams) CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, st));
+    // the tables go up on the index stream (behind the walk, under the previous call's kernels); poisoned buffers are
+    // filled on the context's stream just above, so then the tables follow there
+    cudaStream_t tst = (ahead && !ctx->poison) ? ist : st;
+    if (nstreams) CK(cudaMemcpyAsync(d_streams.p, hs, sizeof(L3StreamRec) * nstreams, cudaMemcpyHostToDevice, tst));
     if (ntiles)
-        CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->h_tiles.p, (fused ? sizeof(uint4) : sizeof(uint2)) * ntiles,
-                           cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, st));
+        CK(cudaMemcpyAsync(d_tiles.p, ctx->h_tiles.p, (fused ? sizeof(uint4) : sizeof(uint2)) * ntiles,
+                           cudaMemcpyHostToDevice, tst));
+    CK(cudaMemsetAsync(d_counter.p, 0, 64, tst));
     bool staging_recorded = false;
-    if (!host_index) { CK(cudaEventRecord(ctx->staging_done, st)); staging_recorded = true; }
+    if (!host_index) { CK(cudaEventRecord(ctx->staging_done, tst)); staging_recorded = true; }
+    if (tst != st) {
+        CK(cudaEventRecord(ctx->tables_done, tst));
+        CK(cudaStreamWaitEvent(st, ctx->tables_done, 0));
+    }
     CK(cudaMemsetAsync(ctx->d_arena.as<uint8_t>() + (ctx->arena_bytes - 48), 0, 48, st));
 
     // ---- frame table
@@ -636,7 +652,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
     uint32_t *dg = ctx->d_gran.as<uint32_t>();
     if (frames) {
         l3_launch_side_parse(ctx->raw_dev, ds, nstreams, df, host_index ? nullptr : d_scratch.as<L3FrameRec>(),
-                             (uint32_t)frames, ctx->T, du, dg, ctx->d_counter.as<uint32_t>(), ctx->opts.verify_crc, st);
+                             (uint32_t)frames, ctx->T, du, dg, d_counter.as<uint32_t>(), ctx->opts.verify_crc, st);
         if (any_layer[3])
             l3_launch_payload_copy(ctx->raw_dev, ds, df, (uint32_t)frames, ctx->d_arena.as<uint8_t>(), st,
                                    ctx->use_pdl && !ctx->stage_timing);
@@ -702,7 +718,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
             return MP3B_OK;
         };
         if (fused) {
-            l3_launch_backend(ctx->d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
+            l3_launch_backend(d_tiles.as<uint4>() + t_lo, (uint32_t)(t_hi - t_lo), dg, du, is, sf, nzv, ctx->T,
                               pcm_dev, ctx->opts.pcm_format, st, pdl && (any_layer[3] || keep));
             if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
             launches += (any_layer[3] || keep ? 1 : 0) + (t_hi > t_lo ? 1 : 0);
@@ -715,7 +731,7 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_IMDCT], st));
         l3_launch_overlap_range(du, u_lo, nu, imd, sb, st);
         if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_OVL], st));
-        l3_launch_synth(ctx->d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, nullptr, pcm_dev,
+        l3_launch_synth(d_tiles.as<uint2>() + t_lo, (uint32_t)(t_hi - t_lo), dg, sb, nullptr, pcm_dev,
                         ctx->opts.pcm_format, st);
         if (waves.size() == 1 && stage_ev) CK(cudaEventRecord(ctx->ev[EV_SYNTH], st));
         launches += 5;
@@ -771,9 +787,10 @@ int decode_impl(mp3b_ctx *ctx, const uint8_t *base, const uint64_t *offsets, int
         }
     }
     if (sink) CK(cudaEventRecord(ctx->pcm_free[ctx->pcm_cur], ctx->copy_stream));
-    l3_launch_publish(ctx->d_counter.p, ctx->h_counter.p, 4, st);
+    l3_launch_publish(d_counter.p, ctx->h_counter.p, 4, st);
     launches++;
     CK(cudaEventRecord(ctx->ev[EV_END], st));
+    if (ahead) CK(cudaEventRecord(ctx->end_ev[ctx->idx_cur], st));
     CK(cudaGetLastError());
 
     ctx->timed = waves.size() == 1 && stage_ev;
@@ -865,6 +882,8 @@ int mp3b_ctx_create(int device, const mp3b_opts *opts, mp3b_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->index_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->walk_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
+    for (cudaEvent_t *e : {&ctx->end_ev[0], &ctx->end_ev[1], &ctx->tables_done})
+        if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
     if (cudaEventCreate(&ctx->walk_t0) != cudaSuccess || cudaEventCreate(&ctx->walk_t1) != cudaSuccess)
         return bail(MP3B_E_CUDA);
     if (cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) != cudaSuccess) return bail(MP3B_E_CUDA);
@@ -890,7 +909,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     for (DevBuf *b : {&ctx->d_tables, &ctx->d_raw[0], &ctx->d_raw[1], &ctx->d_streams[0], &ctx->d_streams[1],
                       &ctx->d_scratch[0], &ctx->d_scratch[1], &ctx->d_sparse[0], &ctx->d_sparse[1], &ctx->d_segs[0],
                       &ctx->d_segs[1], &ctx->d_frames, &ctx->d_units, &ctx->d_gran,
-                      &ctx->d_arena, &ctx->d_tiles, &ctx->d_counter, &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_rs_tcA, &ctx->d_rs_tcpfx, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_hkeys, &ctx->d_hperm, &ctx->d_hstate, &ctx->d_hctl, &ctx->d_xr,
+                      &ctx->d_arena, &ctx->d_tiles[0], &ctx->d_tiles[1], &ctx->d_counter[0], &ctx->d_counter[1], &ctx->d_pcm, &ctx->d_pcm2, &ctx->d_rs, &ctx->d_rs_jobs, &ctx->d_rs_taps, &ctx->d_rs_tcA, &ctx->d_rs_tcpfx, &ctx->d_ts, &ctx->d_ts_jobs, &ctx->d_ts_off, &ctx->d_pl, &ctx->d_pl_jobs, &ctx->d_sg_jobs, &ctx->d_sg_energy, &ctx->d_sg_seg, &ctx->d_sg_n, &ctx->d_sb2, &ctx->d_tiles2, &ctx->d_is, &ctx->d_sf, &ctx->d_nzv, &ctx->d_hkeys, &ctx->d_hperm, &ctx->d_hstate, &ctx->d_hctl, &ctx->d_xr,
                       &ctx->d_imd, &ctx->d_sb})
         b->release();
     for (PinBuf *b : {&ctx->h_tiles2, &ctx->h_streams, &ctx->h_frames, &ctx->h_tiles, &ctx->h_stage, &ctx->h_counter, &ctx->h_gather,
@@ -904,7 +923,7 @@ void mp3b_ctx_destroy(mp3b_ctx *ctx)
     }
     for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
     if (ctx->index_stream) cudaStreamDestroy(ctx->index_stream);
-    for (cudaEvent_t e : {ctx->walk_done, ctx->walk_t0, ctx->walk_t1})
+    for (cudaEvent_t e : {ctx->walk_done, ctx->walk_t0, ctx->walk_t1, ctx->end_ev[0], ctx->end_ev[1], ctx->tables_done})
         if (e) cudaEventDestroy(e);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
